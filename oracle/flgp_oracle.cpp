@@ -1,0 +1,601 @@
+// flgp_oracle.cpp — CPU ORACLE for the FLGP spectral core.  TEST INFRASTRUCTURE ONLY.
+//
+// This file is the checker, never the product: only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may load it.  The product
+// (flgp_b200/csrc, libflgp_b200.so) never links, imports or calls anything here.
+//
+// It restates, stage by stage, the reference's algorithm for the hot path
+// (all citations relative to /root/reference):
+//   src/Utils.cpp:32-45     subsample_cpp "kmeans"   -> orc_kmeans_*      (see PARITY below)
+//   src/Utils.cpp:72-97     KNN_Index (std::partial_sort, literal)        -> orc_knn
+//   src/Utils.cpp:102-192   KNN_cpp  (distance formula, sparse output)    -> orc_knn
+//   src/lae.cpp:137-153     v_to_z_cpp                                    -> orc_simplex_project
+//   src/lae.cpp:76-133      local_anchor_embedding_cpp                    -> orc_lae_point
+//   src/lae.cpp:48-70       LAE_cpp (CSR assembly, column-sorted rows)    -> orc_lae
+//   src/Utils.cpp:195-212   graphLaplacian_cpp                            -> orc_graph_laplacian
+//   src/Spectrum.cpp:120-142 cross_similarity_se_cpp (exp weights)        -> orc_se_weights
+//   src/Spectrum.cpp:146-161 spectrum_from_Z_cpp (column scale, Gram)     -> orc_spectrum_scale, orc_gram
+//   src/TruncatedSVD.cpp:9-34 (u = A v / sigma lift)                      -> orc_lift
+//   src/Spectrum.cpp:83-94  HK_from_spectrum_cpp                          -> orc_hk_from_spectrum
+//
+// PARITY STATUS: **parity unpinned**.  The reference ships no tests, golden vectors or
+// fixtures and cannot be built here (needs R, Rcpp, RcppEigen,
+// RcppParallel/TBB; none present).  Three arithmetic kernels of the path live in
+// un-vendored, unpinned third-party R packages:
+//   * stats::kmeans (base R, Hartigan-Wong, R-RNG init; call site src/Utils.cpp:37-42)
+//       -> replaced by Lloyd's algorithm with explicit initial row indices, iter.max
+//          iterations, stop when no assignment changes (contract defined HERE).
+//   * RSpectra::svds (call site src/TruncatedSVD.cpp:23-28)
+//       -> replaced by a dense symmetric eigendecomposition of the Gram A^T A
+//          (LAPACK through scipy, in oracle/oracle.py).
+//   * Eigen (GEMM / reductions summation order) -> every dot product and norm is
+//     evaluated here in plain sequential index order, separate multiply and add
+//     (no FMA; build with -ffp-contract=off), which is what Eigen's GEBP does per
+//     output coefficient for small depth and what its non-vectorised reductions do.
+//
+// Arithmetic contract shared with the CUDA path (bit-exact where stated):
+//   * all reals IEEE fp64, round-to-nearest-even; no FMA except where std::fma is
+//     written explicitly (k-means scores only).
+//   * order-independent sums (k-means centroid sums, column sums, Gram) are offered in
+//     two flavours: `exact=0` literal sequential fp64 in row order (what the reference
+//     does) and `exact=1` two-limb 62-bit fixed point (associative => identical for
+//     any sharding / thread order).  The CUDA path implements exact=1.
+//
+// Layout: every matrix is column-major with an explicit leading dimension; indices are
+// int32, 0-based; CSR has exactly r entries per row (p[i] = i*r implicit).
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <numeric>
+#include <thread>
+#include <vector>
+
+namespace {
+
+template <class F>
+void parallel_rows(int64_t n, int nthreads, F f) {
+  if (nthreads <= 1 || n < 2 * (int64_t)nthreads) {
+    f(0, n, 0);
+    return;
+  }
+  std::vector<std::thread> th;
+  int64_t chunk = (n + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; ++t) {
+    int64_t lo = (int64_t)t * chunk, hi = std::min<int64_t>(n, lo + chunk);
+    if (lo >= hi) break;
+    th.emplace_back([=] { f(lo, hi, t); });
+  }
+  for (auto& x : th) x.join();
+}
+
+// ---- two-limb fixed point -------------------------------------------------------------
+// Values with |x| < 2^E, at most `count` addends.  L = ceil(log2 count), B = 62 - L bits
+// per limb: x = hi*q1 + lo*q2 + (dropped bits below q2), q1 = 2^(E-B), q2 = 2^(E-2B).
+struct Fx {
+  double q1, q2, iq1, iq2;
+  int E, B;
+};
+
+int fx_make(double maxabs, int64_t count, Fx* fx) {
+  if (!std::isfinite(maxabs) || count < 1) return 1;
+  int E = (maxabs > 0.0) ? std::ilogb(maxabs) + 1 : 0;
+  if (E < -800) E = -800;
+  if (E > 800) return 1;
+  int L = 0;
+  while (((int64_t)1 << L) < count) ++L;
+  int B = 62 - L;
+  fx->E = E;
+  fx->B = B;
+  fx->q1 = std::ldexp(1.0, E - B);
+  fx->q2 = std::ldexp(1.0, E - 2 * B);
+  fx->iq1 = std::ldexp(1.0, B - E);
+  fx->iq2 = std::ldexp(1.0, 2 * B - E);
+  return 0;
+}
+inline void fx_encode(const Fx& fx, double x, int64_t* hi, int64_t* lo) {
+  int64_t h = (int64_t)(x * fx.iq1);  // truncation; x*iq1 is exact (power of two)
+  double rem = x - (double)h * fx.q1; // exact
+  *hi = h;
+  *lo = (int64_t)(rem * fx.iq2);
+}
+inline double fx_decode(const Fx& fx, int64_t hi, int64_t lo) {
+  return (double)hi * fx.q1 + (double)lo * fx.q2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int orc_version() { return 1; }
+
+// max |x| over a buffer (used to pick the fixed-point scale; NaN-free input assumed)
+double orc_maxabs(const double* x, int64_t len) {
+  double m = 0.0;
+  for (int64_t i = 0; i < len; ++i) {
+    double a = std::fabs(x[i]);
+    if (a > m) m = a;
+  }
+  return m;
+}
+
+// fixed-point helpers exported for tests (shard-invariance, codec round trips)
+int orc_fx_encode(double maxabs, int64_t count, const double* x, int64_t len, int64_t* hi, int64_t* lo) {
+  Fx fx;
+  if (fx_make(maxabs, count, &fx)) return 1;
+  for (int64_t i = 0; i < len; ++i) fx_encode(fx, x[i], hi + i, lo + i);
+  return 0;
+}
+int orc_fx_decode(double maxabs, int64_t count, const int64_t* hi, const int64_t* lo, int64_t len, double* x) {
+  Fx fx;
+  if (fx_make(maxabs, count, &fx)) return 1;
+  for (int64_t i = 0; i < len; ++i) x[i] = fx_decode(fx, hi[i], lo[i]);
+  return 0;
+}
+
+// =========================================================================================
+// k-means (Lloyd).  Contract replacing stats::kmeans at src/Utils.cpp:37-45.
+//   score(i,j) = fma(x_{d-1}, -2c_{j,d-1}, ... fma(x_0, -2c_{j,0}, |c_j|^2))   (= |x-c|^2 - |x|^2)
+//   |c_j|^2    = fma chain over k ascending starting from 0
+//   assign(i)  = argmin_j score, lowest j wins ties (strict <, j ascending)
+//   centroid   = decode(sum of fixed-point encodings) / count   (empty cluster keeps its centre)
+// acc layout (int64): hi[s*d] (j + s*k), lo[s*d], cnt[s], changed[1]  => 2*s*d + s + 1 words.
+// =========================================================================================
+int orc_kmeans_step(const double* X, int64_t n, int64_t ldx, int d, const double* C, int s,
+                    double maxabs, int64_t n_total, int32_t* assign, int64_t* acc, int nthreads) {
+  Fx fx;
+  if (fx_make(maxabs, n_total, &fx)) return 1;
+  std::vector<double> c2((size_t)s * d), cn(s);
+  for (int j = 0; j < s; ++j) {
+    double a = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double c = C[j + (size_t)s * k];
+      a = std::fma(c, c, a);
+      c2[(size_t)j * d + k] = -2.0 * c;
+    }
+    cn[j] = a;
+  }
+  const size_t words = (size_t)2 * s * d + s + 1;
+  int T = std::max(1, nthreads);
+  std::vector<std::vector<int64_t>> part(T);
+  parallel_rows(n, T, [&](int64_t lo, int64_t hi, int t) {
+    std::vector<int64_t>& a = part[t];
+    a.assign(words, 0);
+    std::vector<double> x(d);
+    for (int64_t i = lo; i < hi; ++i) {
+      for (int k = 0; k < d; ++k) x[k] = X[i + ldx * k];
+      double best = 0.0;
+      int bj = 0;
+      for (int j = 0; j < s; ++j) {
+        double e = cn[j];
+        const double* cj = &c2[(size_t)j * d];
+        for (int k = 0; k < d; ++k) e = std::fma(x[k], cj[k], e);
+        if (j == 0 || e < best) {
+          best = e;
+          bj = j;
+        }
+      }
+      if (assign[i] != bj) a[words - 1] += 1;
+      assign[i] = bj;
+      for (int k = 0; k < d; ++k) {
+        int64_t h, l;
+        fx_encode(fx, x[k], &h, &l);
+        a[bj + (size_t)s * k] += h;
+        a[(size_t)s * d + bj + (size_t)s * k] += l;
+      }
+      a[(size_t)2 * s * d + bj] += 1;
+    }
+  });
+  for (int t = 0; t < T; ++t)
+    if (!part[t].empty())
+      for (size_t w = 0; w < words; ++w) acc[w] += part[t][w];
+  return 0;
+}
+
+int orc_kmeans_update(const int64_t* acc, int s, int d, double maxabs, int64_t n_total, double* C,
+                      double* sizes) {
+  Fx fx;
+  if (fx_make(maxabs, n_total, &fx)) return 1;
+  for (int j = 0; j < s; ++j) {
+    int64_t cnt = acc[(size_t)2 * s * d + j];
+    if (sizes) sizes[j] = (double)cnt;
+    if (cnt == 0) continue;
+    for (int k = 0; k < d; ++k) {
+      double sum = fx_decode(fx, acc[j + (size_t)s * k], acc[(size_t)s * d + j + (size_t)s * k]);
+      C[j + (size_t)s * k] = sum / (double)cnt;
+    }
+  }
+  return 0;
+}
+
+// Full Lloyd loop on one shard (= the whole data).  U is s x (d+1): centres, then sizes
+// (src/Utils.cpp:43-45).  assign (n) is scratch/out.  Returns iterations done in *iters.
+int orc_kmeans_lloyd(const double* X, int64_t n, int64_t ldx, int d, int s, const int32_t* init_idx,
+                     int iter_max, int nthreads, double* U, int32_t* assign, int* iters) {
+  if (s < 1 || s > n || d < 1) return 1;
+  double maxabs = 0.0;
+  for (int k = 0; k < d; ++k) maxabs = std::max(maxabs, orc_maxabs(X + ldx * k, n));
+  std::vector<double> C((size_t)s * d);
+  for (int j = 0; j < s; ++j) {
+    if (init_idx[j] < 0 || init_idx[j] >= n) return 1;
+    for (int k = 0; k < d; ++k) C[j + (size_t)s * k] = X[init_idx[j] + ldx * k];
+  }
+  for (int64_t i = 0; i < n; ++i) assign[i] = -1;
+  const size_t words = (size_t)2 * s * d + s + 1;
+  std::vector<int64_t> acc(words);
+  std::vector<double> sizes(s, 0.0);
+  int it = 0;
+  while (it < iter_max) {
+    ++it;
+    std::fill(acc.begin(), acc.end(), 0);
+    if (orc_kmeans_step(X, n, ldx, d, C.data(), s, maxabs, n, assign, acc.data(), nthreads)) return 1;
+    for (int j = 0; j < s; ++j) sizes[j] = (double)acc[(size_t)2 * s * d + j];
+    if (acc[words - 1] == 0) break;  // no assignment changed: centres already consistent
+    if (orc_kmeans_update(acc.data(), s, d, maxabs, n, C.data(), nullptr)) return 1;
+  }
+  for (int j = 0; j < s; ++j) {
+    for (int k = 0; k < d; ++k) U[j + (size_t)s * k] = C[j + (size_t)s * k];
+    U[j + (size_t)s * d] = sizes[j];
+  }
+  if (iters) *iters = it;
+  return 0;
+}
+
+// =========================================================================================
+// KNN  (src/Utils.cpp:72-97, 102-192)
+//   D(i,j) = ((-2 * sum_k x_ik u_jk) + |x_i|^2) + |u_j|^2        (src/Utils.cpp:121)
+//   top-r by the LITERAL std::partial_sort(ind, ind+r, ind+s, D[i1] < D[i2])  (:91-94)
+// ind: n x r (ld = n), ascending distance; dist (optional): D at the selected columns,
+// same order.  `batch` never changes the result so it is not a parameter.
+// =========================================================================================
+int orc_knn(const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu, int r,
+            int32_t* ind, double* dist, int nthreads) {
+  if (r < 1 || r > s) return 1;
+  std::vector<double> un(s);
+  for (int j = 0; j < s; ++j) {
+    double a = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double u = U[j + ldu * k];
+      a = a + u * u;
+    }
+    un[j] = a;
+  }
+  parallel_rows(n, nthreads, [&](int64_t lo, int64_t hi, int) {
+    std::vector<double> row(s), x(d);
+    std::vector<int> idx(s);
+    for (int64_t i = lo; i < hi; ++i) {
+      double xn = 0.0;
+      for (int k = 0; k < d; ++k) {
+        x[k] = X[i + ldx * k];
+        xn = xn + x[k] * x[k];
+      }
+      for (int j = 0; j < s; ++j) {
+        double acc = 0.0;
+        for (int k = 0; k < d; ++k) acc = acc + x[k] * U[j + ldu * k];
+        row[j] = ((-2.0 * acc) + xn) + un[j];
+      }
+      std::iota(idx.begin(), idx.end(), 0);
+      const double* rw = row.data();
+      std::partial_sort(idx.data(), idx.data() + r, idx.data() + s,
+                        [rw](int i1, int i2) { return rw[i1] < rw[i2]; });
+      for (int j = 0; j < r; ++j) {
+        ind[i + n * j] = idx[j];
+        if (dist) dist[i + n * j] = row[idx[j]];
+      }
+    }
+  });
+  return 0;
+}
+
+// =========================================================================================
+// v_to_z_cpp  (src/lae.cpp:137-153): Euclidean projection onto the simplex.
+// =========================================================================================
+void orc_simplex_project(const double* v, int r, double* z) {
+  std::vector<double> vd(v, v + r), cs(r);
+  std::sort(vd.begin(), vd.end(), std::greater<double>());   // :140
+  std::partial_sum(vd.begin(), vd.end(), cs.begin());        // :142
+  int rho;
+  for (rho = r; rho > 0; --rho) {                            // :145-147
+    double vstar = vd[rho - 1] - (cs[rho - 1] - 1.0) / (double)rho;  // :143
+    if (vstar > 0) break;
+  }
+  double head = 0.0;                                         // v_desc.head(rho).sum(), sequential
+  for (int k = 0; k < rho; ++k) head = (k == 0) ? vd[0] : head + vd[k];
+  double theta = (head - 1.0) / (double)rho;                 // :149 (rho == 0 -> -inf, as the reference)
+  for (int k = 0; k < r; ++k) z[k] = std::max(v[k] - theta, 0.0);  // :150-151
+}
+
+// =========================================================================================
+// local_anchor_embedding_cpp  (src/lae.cpp:76-133).  Ur is r x d (ld = ldu).
+// The reference's `while(true)` back-tracking (:108-125) does not terminate when the
+// objective is NaN or beta overflows; it is capped here at j = 1100 (2^j = inf from 1024)
+// after which the step is accepted.  Unreachable for finite, sanely scaled data.
+// =========================================================================================
+int orc_lae_point(const double* x, int d, const double* Ur, int64_t ldu, int r, double* z_out, int* iters,
+                  int* backtracks) {
+  const double tol = 1e-5;
+  const int T = 100, JCAP = 1100;
+  std::vector<double> zp(r, 1.0 / r), zc(r, 1.0 / r), v(r), g(r), vt(r), z(r), UUt((size_t)r * r), xUt(r),
+      res(d);
+  for (int a = 0; a < r; ++a)
+    for (int b = 0; b < r; ++b) {                           // :90  UUt = U * U^T
+      double s = 0.0;
+      for (int k = 0; k < d; ++k) s = s + Ur[a + ldu * k] * Ur[b + ldu * k];
+      UUt[a + (size_t)r * b] = s;
+    }
+  for (int a = 0; a < r; ++a) {                             // x * Ut (constant across iterations)
+    double s = 0.0;
+    for (int k = 0; k < d; ++k) s = s + x[k] * Ur[a + ldu * k];
+    xUt[a] = s;
+  }
+  auto objective = [&](const double* w) {                   // (x - w*U).squaredNorm()/2.0   :103,:116
+    double sq = 0.0;
+    for (int k = 0; k < d; ++k) {
+      double wu = 0.0;
+      for (int a = 0; a < r; ++a) wu = wu + w[a] * Ur[a + ldu * k];
+      double df = x[k] - wu;
+      sq = sq + df * df;
+    }
+    return sq / 2.0;
+  };
+  double delta_prev = 0.0, delta_curr = 1.0, beta_curr = 1.0;
+  int t = 0, nbt = 0;
+  for (t = 0; t < T; ++t) {
+    double alpha = (delta_prev - 1.0) / delta_curr;                            // :99
+    for (int a = 0; a < r; ++a) v[a] = zc[a] + alpha * (zc[a] - zp[a]);        // :101
+    double g_v = objective(v.data());                                         // :103
+    for (int b = 0; b < r; ++b) {                                              // :105
+      double s = 0.0;
+      for (int a = 0; a < r; ++a) s = s + v[a] * UUt[a + (size_t)r * b];
+      g[b] = s - xUt[b];
+    }
+    int j = 0;
+    while (true) {
+      double beta = std::ldexp(1.0, j) * beta_curr;                            // :110  pow(2,j)*beta_curr
+      double ib = 1.0 / beta;
+      for (int a = 0; a < r; ++a) vt[a] = v[a] - ib * g[a];                    // :112
+      orc_simplex_project(vt.data(), r, z.data());                            // :114
+      double g_z = objective(z.data());                                       // :116
+      double dot = 0.0, sq = 0.0;
+      for (int a = 0; a < r; ++a) {
+        double dz = z[a] - v[a];
+        dot = dot + g[a] * dz;
+        sq = sq + dz * dz;
+      }
+      double g_tilde = g_v + dot + beta * sq / 2.0;                            // :117
+      if (g_z <= g_tilde || j >= JCAP) {                                       // :118
+        beta_curr = beta;
+        zp = zc;
+        zc = z;
+        break;
+      }
+      ++j;
+      ++nbt;
+    }
+    delta_prev = delta_curr;                                                   // :126
+    delta_curr = (1.0 + std::sqrt(1.0 + 4.0 * delta_curr * delta_curr)) / 2.0; // :127
+    double sq = 0.0;
+    for (int a = 0; a < r; ++a) {
+      double dz = zc[a] - zp[a];
+      sq = sq + dz * dz;
+    }
+    if (sq < tol) {                                                            // :129
+      ++t;
+      break;
+    }
+  }
+  for (int a = 0; a < r; ++a) z_out[a] = zc[a];
+  if (iters) *iters = t;
+  if (backtracks) *backtracks = nbt;
+  return 0;
+}
+
+// =========================================================================================
+// LAE_cpp (src/lae.cpp:48-70): weights for every row on its KNN anchors (in KNN order),
+// then CSR with rows sorted by column (SparseMatrix::insert, :63-67); explicit zeros kept.
+// ind: n x r (ld n).  Outputs Zj/Zx: n*r, row i at [i*r, i*r+r).  W (optional): dense n x r
+// weights in KNN order (ld n).  stats (optional, 2 x int64): total iterations, total backtracks.
+// =========================================================================================
+int orc_lae(const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu, int r,
+            const int32_t* ind, int32_t* Zj, double* Zx, double* W, int64_t* stats, int nthreads) {
+  int T = std::max(1, nthreads);
+  std::vector<int64_t> st((size_t)2 * T, 0);
+  parallel_rows(n, T, [&](int64_t lo, int64_t hi, int t) {
+    std::vector<double> Ur((size_t)r * d), x(d), z(r);
+    std::vector<std::pair<int32_t, double>> row(r);
+    for (int64_t i = lo; i < hi; ++i) {
+      for (int k = 0; k < d; ++k) x[k] = X[i + ldx * k];
+      for (int a = 0; a < r; ++a) {
+        int32_t c = ind[i + n * a];
+        for (int k = 0; k < d; ++k) Ur[a + (size_t)r * k] = U[c + ldu * k];  // mat_indexing, :41
+      }
+      int it = 0, bt = 0;
+      orc_lae_point(x.data(), d, Ur.data(), r, r, z.data(), &it, &bt);
+      st[2 * t] += it;
+      st[2 * t + 1] += bt;
+      for (int a = 0; a < r; ++a) {
+        row[a] = {ind[i + n * a], z[a]};
+        if (W) W[i + n * a] = z[a];
+      }
+      std::sort(row.begin(), row.end(), [](auto& p, auto& q) { return p.first < q.first; });
+      for (int a = 0; a < r; ++a) {
+        Zj[i * r + a] = row[a].first;
+        Zx[i * r + a] = row[a].second;
+      }
+    }
+  });
+  if (stats) {
+    stats[0] = stats[1] = 0;
+    for (int t = 0; t < T; ++t) {
+      stats[0] += st[2 * t];
+      stats[1] += st[2 * t + 1];
+    }
+  }
+  return 0;
+}
+
+// KNN sparse output (src/Utils.cpp:145-189): CSR, column-sorted rows, x = D(i, col).
+int orc_knn_to_csr(int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx) {
+  std::vector<std::pair<int32_t, double>> row(r);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int a = 0; a < r; ++a) row[a] = {ind[i + n * a], dist[i + n * a]};
+    std::sort(row.begin(), row.end(), [](auto& p, auto& q) { return p.first < q.first; });
+    for (int a = 0; a < r; ++a) {
+      Zj[i * r + a] = row[a].first;
+      Zx[i * r + a] = row[a].second;
+    }
+  }
+  return 0;
+}
+
+// Z.x = exp(-dist / denom)   (src/Spectrum.cpp:132 with denom = 4 eps^2; src/Fit.cpp:150 with a2*mean)
+void orc_se_weights(const double* dist, int64_t len, double denom, double* out) {
+  for (int64_t i = 0; i < len; ++i) out[i] = std::exp(-dist[i] / denom);
+}
+
+// column sums of a fixed-r CSR.  exact=0: sequential fp64 in row order (reference);
+// exact=1: two-limb fixed point with |x| < 2 and at most n_total addends per column.
+// hi/lo (optional, exact=1): raw limbs are ADDED into them (for shard tests); c is always set.
+int orc_colsum(int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int exact, int64_t n_total,
+               double* c, int64_t* hi, int64_t* lo) {
+  if (!exact) {
+    std::fill(c, c + s, 0.0);
+    for (int64_t e = 0; e < n * r; ++e) c[Zj[e]] += Zx[e];
+    return 0;
+  }
+  Fx fx;
+  if (fx_make(1.0, n_total, &fx)) return 1;
+  std::vector<int64_t> h(s, 0), l(s, 0);
+  for (int64_t e = 0; e < n * r; ++e) {
+    int64_t a, b;
+    fx_encode(fx, Zx[e], &a, &b);
+    h[Zj[e]] += a;
+    l[Zj[e]] += b;
+  }
+  for (int j = 0; j < s; ++j) {
+    c[j] = fx_decode(fx, h[j], l[j]);
+    if (hi) hi[j] += h[j];
+    if (lo) lo[j] += l[j];
+  }
+  return 0;
+}
+
+// =========================================================================================
+// graphLaplacian_cpp (src/Utils.cpp:195-212).  mode 0 "rw", 1 "normalized", 2 "cluster-normalized".
+// colsum (s) must hold the column sums of the INPUT Z for modes 1,2 (computed by orc_colsum, so
+// that sharded callers can all-reduce them first).  In place on Zx.
+// =========================================================================================
+int orc_graph_laplacian_apply(int64_t n, int s, int r, const int32_t* Zj, double* Zx, int mode,
+                              const double* colsum, const double* num_class) {
+  if (mode < 0 || mode > 2) return 1;
+  std::vector<double> inv(s, 1.0);
+  if (mode >= 1)
+    for (int j = 0; j < s; ++j) inv[j] = 1.0 / (colsum[j] + 1e-9);  // :201,:204
+  for (int64_t i = 0; i < n; ++i) {
+    double rs = 0.0;
+    for (int a = 0; a < r; ++a) {
+      int64_t e = i * r + a;
+      double z = Zx[e];
+      if (mode >= 1) z = z * inv[Zj[e]];
+      if (mode == 2) z = z * num_class[Zj[e]];                       // :205
+      Zx[e] = z;
+      rs = (a == 0) ? (0.0 + z) : rs + z;                            // :210 Z * ones, storage order
+    }
+    double ir = 1.0 / (rs + 1e-9);                                   // :211
+    for (int a = 0; a < r; ++a) Zx[i * r + a] = ir * Zx[i * r + a];
+  }
+  return 0;
+}
+
+int orc_graph_laplacian(int64_t n, int s, int r, const int32_t* Zj, double* Zx, int mode,
+                        const double* num_class, int exact) {
+  std::vector<double> c(s, 0.0);
+  if (mode >= 1 && orc_colsum(n, s, r, Zj, Zx, exact, n, c.data(), nullptr, nullptr)) return 1;
+  return orc_graph_laplacian_apply(n, s, r, Zj, Zx, mode, c.data(), num_class);
+}
+
+// spectrum_from_Z_cpp (src/Spectrum.cpp:149-150): w_j = 1/sqrt(|colsum_j| + 1e-9); A = Z diag(w).
+void orc_spectrum_scale(int s, const double* colsum, double* w) {
+  for (int j = 0; j < s; ++j) w[j] = 1.0 / std::sqrt(std::fabs(colsum[j]) + 1e-9);
+}
+
+// Gram G = A^T A, A(i,j) = Z(i,j) * w_j (each entry rounded, as the reference materialises A).
+// exact=0: sequential fp64 in row order; exact=1: two-limb fixed point (|a_ia a_ib| < 2).
+// G: s x s column-major (symmetric).  hi/lo (optional, s*s): limbs ADDED (exact=1) for shard tests.
+int orc_gram(int64_t n, int s, int r, const int32_t* Zj, const double* Zx, const double* w, int exact,
+             int64_t n_total, double* G, int64_t* hi, int64_t* lo) {
+  size_t ss = (size_t)s * s;
+  std::vector<double> a(r);
+  if (!exact) {
+    std::fill(G, G + ss, 0.0);
+    for (int64_t i = 0; i < n; ++i) {
+      for (int p = 0; p < r; ++p) a[p] = Zx[i * r + p] * w[Zj[i * r + p]];
+      for (int p = 0; p < r; ++p)
+        for (int q = 0; q < r; ++q) G[Zj[i * r + p] + (size_t)s * Zj[i * r + q]] += a[p] * a[q];
+    }
+    return 0;
+  }
+  Fx fx;
+  if (fx_make(1.0, n_total, &fx)) return 1;
+  std::vector<int64_t> h(ss, 0), l(ss, 0);
+  for (int64_t i = 0; i < n; ++i) {
+    for (int p = 0; p < r; ++p) a[p] = Zx[i * r + p] * w[Zj[i * r + p]];
+    for (int p = 0; p < r; ++p)
+      for (int q = 0; q < r; ++q) {
+        int64_t x, y;
+        fx_encode(fx, a[p] * a[q], &x, &y);
+        size_t at = Zj[i * r + p] + (size_t)s * Zj[i * r + q];
+        h[at] += x;
+        l[at] += y;
+      }
+  }
+  for (size_t e = 0; e < ss; ++e) {
+    G[e] = fx_decode(fx, h[e], l[e]);
+    if (hi) hi[e] += h[e];
+    if (lo) lo[e] += l[e];
+  }
+  return 0;
+}
+
+// Lift (src/TruncatedSVD.cpp:23-30 semantics of svds' u, then src/Spectrum.cpp:157-158):
+//   vectors(i,k) = sqrt(n_total) * (sum_p A(i,c_p) Y(c_p,k)) / sigma_k
+// Y: s x K (ld s) eigenvectors of the Gram, sigma: K singular values.  V: n x K (ld n).
+int orc_lift(int64_t n, int s, int r, const int32_t* Zj, const double* Zx, const double* w, const double* Y,
+             const double* sigma, int K, int64_t n_total, double* V, int nthreads) {
+  double sq = std::sqrt((double)n_total);
+  parallel_rows(n, nthreads, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t i = lo; i < hi; ++i)
+      for (int k = 0; k < K; ++k) {
+        double acc = 0.0;
+        for (int p = 0; p < r; ++p) {
+          int32_t c = Zj[i * r + p];
+          acc = acc + (Zx[i * r + p] * w[c]) * Y[c + (size_t)s * k];
+        }
+        V[i + n * k] = (acc / sigma[k]) * sq;
+      }
+  });
+  return 0;
+}
+
+// HK_from_spectrum_cpp (src/Spectrum.cpp:83-94):
+//   H = V[idx0,:K] diag(exp(-t (1 - values[:K]))) V[idx1,:K]^T ; H is n0 x n1 (ld n0).
+int orc_hk_from_spectrum(const double* V, int64_t ldv, const double* values, int K, double t,
+                         const int32_t* idx0, int64_t n0, const int32_t* idx1, int64_t n1, double* H,
+                         int nthreads) {
+  std::vector<double> lam(K);
+  for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * (1.0 - values[k]));
+  parallel_rows(n1, nthreads, [&](int64_t lo, int64_t hi, int) {
+    for (int64_t b = lo; b < hi; ++b)
+      for (int64_t a = 0; a < n0; ++a) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k)
+          acc = acc + (V[idx0[a] + ldv * k] * lam[k]) * V[idx1[b] + ldv * k];
+        H[a + n0 * b] = acc;
+      }
+  });
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,428 @@
+"""ctypes binding + numpy glue for the CPU ORACLE (oracle/flgp_oracle.cpp).
+
+TEST INFRASTRUCTURE ONLY — parity unpinned (see the header of flgp_oracle.cpp).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module.  The product package (flgp_b200) never does.
+
+Stages that the reference delegates to un-vendored third-party code are restated here:
+  * RSpectra::svds (src/TruncatedSVD.cpp:23-28)  -> scipy.linalg.eigh of the Gram A^T A
+  * Eigen::LLT (src/Predict.cpp:57,66; src/Utils.cpp:234,242) -> scipy cho_factor/cho_solve
+All citations are relative to /root/reference.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+GL_MODES = {"rw": 0, "normalized": 1, "cluster-normalized": 2}
+
+
+def build(force: bool = False) -> str:
+    """Compile the C++ restatement with the committed Makefile (g++ -O2)."""
+    so = os.path.join(_HERE, "libflgp_oracle.so")
+    src = os.path.join(_HERE, "flgp_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "libflgp_oracle.so"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_maxabs.restype = C.c_double
+    return _LIB
+
+
+def _f(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _p(a, t=C.c_double):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+I64 = C.c_int64
+
+
+# ------------------------------------------------------------------ fixed point (tests)
+def fx_encode(x, maxabs, count):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    hi = np.zeros(x.shape, np.int64)
+    lo = np.zeros(x.shape, np.int64)
+    rc = lib().orc_fx_encode(C.c_double(maxabs), I64(count), _p(x), I64(x.size), _p(hi, I64), _p(lo, I64))
+    assert rc == 0
+    return hi, lo
+
+
+def fx_decode(hi, lo, maxabs, count):
+    hi = np.ascontiguousarray(hi, dtype=np.int64)
+    lo = np.ascontiguousarray(lo, dtype=np.int64)
+    x = np.zeros(hi.shape, np.float64)
+    rc = lib().orc_fx_decode(C.c_double(maxabs), I64(count), _p(hi, I64), _p(lo, I64), I64(hi.size), _p(x))
+    assert rc == 0
+    return x
+
+
+# ------------------------------------------------------------------ k-means
+def kmeans_acc_words(s, d):
+    return 2 * s * d + s + 1
+
+
+def kmeans_step(X, C_, maxabs, n_total, assign, acc, nthreads=1):
+    """One Lloyd assign+accumulate pass over a shard; adds into acc (int64)."""
+    X = _f(X)
+    C_ = _f(C_)
+    n, d = X.shape
+    s = C_.shape[0]
+    rc = lib().orc_kmeans_step(_p(X), I64(n), I64(n), d, _p(C_), s, C.c_double(maxabs), I64(n_total),
+                               _p(assign, C.c_int32), _p(acc, I64), nthreads)
+    assert rc == 0
+
+
+def kmeans_update(acc, C_, maxabs, n_total):
+    """Centroid update from (all-reduced) accumulators; returns (C_new, sizes)."""
+    C_ = _f(C_).copy(order="F")
+    s, d = C_.shape
+    sizes = np.zeros(s)
+    rc = lib().orc_kmeans_update(_p(acc, I64), s, d, C.c_double(maxabs), I64(n_total), _p(C_), _p(sizes))
+    assert rc == 0
+    return C_, sizes
+
+
+def kmeans_lloyd(X, s, init_idx, iter_max=100, nthreads=1):
+    """subsample_cpp(method="kmeans") contract (src/Utils.cpp:32-45): U = [centres, size]."""
+    X = _f(X)
+    n, d = X.shape
+    init_idx = _i32(init_idx)
+    U = np.zeros((s, d + 1), order="F")
+    assign = np.zeros(n, np.int32)
+    iters = C.c_int(0)
+    rc = lib().orc_kmeans_lloyd(_p(X), I64(n), I64(n), d, s, _p(init_idx, C.c_int32), iter_max, nthreads,
+                                _p(U), _p(assign, C.c_int32), C.byref(iters))
+    if rc:
+        raise ValueError("orc_kmeans_lloyd failed")
+    return U, assign, iters.value
+
+
+# ------------------------------------------------------------------ KNN / LAE
+def knn(X, U, r, want_dist=False, nthreads=1):
+    """KNN_cpp (src/Utils.cpp:102-192): ind_knn n x r (0-based, ascending distance)."""
+    X = _f(X)
+    U = _f(U)
+    n, d = X.shape
+    s = U.shape[0]
+    assert U.shape[1] == d
+    ind = np.zeros((n, r), np.int32, order="F")
+    dist = np.zeros((n, r), order="F") if want_dist else None
+    rc = lib().orc_knn(_p(X), I64(n), I64(n), d, _p(U), s, I64(s), r, _p(ind, C.c_int32),
+                       _p(dist) if want_dist else None, nthreads)
+    if rc:
+        raise ValueError("orc_knn failed (need 1 <= r <= s)")
+    return (ind, dist) if want_dist else ind
+
+
+def simplex_project(v):
+    """v_to_z_cpp (src/lae.cpp:137-153)."""
+    v = np.ascontiguousarray(v, dtype=np.float64)
+    z = np.zeros_like(v)
+    lib().orc_simplex_project(_p(v), v.size, _p(z))
+    return z
+
+
+def lae_point(x, Ur, want_stats=False):
+    """local_anchor_embedding_cpp (src/lae.cpp:76-133); Ur is r x d."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    Ur = _f(Ur)
+    r, d = Ur.shape
+    z = np.zeros(r)
+    it = C.c_int(0)
+    bt = C.c_int(0)
+    lib().orc_lae_point(_p(x), d, _p(Ur), I64(r), r, _p(z), C.byref(it), C.byref(bt))
+    return (z, it.value, bt.value) if want_stats else z
+
+
+def lae(X, U, r, ind=None, nthreads=1, want_stats=False):
+    """LAE_cpp (src/lae.cpp:48-70): returns CSR (Zj, Zx) as (n, r) arrays, rows column-sorted,
+    and the dense n x r weights in KNN order."""
+    X = _f(X)
+    U = _f(U)
+    n, d = X.shape
+    s = U.shape[0]
+    if ind is None:
+        ind = knn(X, U, r, nthreads=nthreads)
+    ind = np.asfortranarray(ind, dtype=np.int32)
+    Zj = np.zeros((n, r), np.int32)
+    Zx = np.zeros((n, r))
+    W = np.zeros((n, r), order="F")
+    stats = np.zeros(2, np.int64)
+    rc = lib().orc_lae(_p(X), I64(n), I64(n), d, _p(U), s, I64(s), r, _p(ind, C.c_int32), _p(Zj, C.c_int32),
+                       _p(Zx), _p(W), _p(stats, I64), nthreads)
+    assert rc == 0
+    if want_stats:
+        return Zj, Zx, W, stats
+    return Zj, Zx, W
+
+
+def knn_csr(ind, dist):
+    """distances_sp of KNN_cpp(output=true) (src/Utils.cpp:145-189) as fixed-r CSR."""
+    ind = np.asfortranarray(ind, dtype=np.int32)
+    dist = _f(dist)
+    n, r = ind.shape
+    Zj = np.zeros((n, r), np.int32)
+    Zx = np.zeros((n, r))
+    lib().orc_knn_to_csr(I64(n), r, _p(ind, C.c_int32), _p(dist), _p(Zj, C.c_int32), _p(Zx))
+    return Zj, Zx
+
+
+def se_weights(dist, denom):
+    dist = np.ascontiguousarray(dist, dtype=np.float64)
+    out = np.zeros_like(dist)
+    lib().orc_se_weights(_p(dist), I64(dist.size), C.c_double(denom), _p(out))
+    return out
+
+
+# ------------------------------------------------------------------ GL, spectrum
+def colsum(Zj, Zx, s, exact=1, n_total=None, limbs=None):
+    Zj = _i32(Zj)
+    Zx = np.ascontiguousarray(Zx, dtype=np.float64)
+    n, r = Zj.shape
+    c = np.zeros(s)
+    hi = lo = None
+    if limbs is not None:
+        hi, lo = limbs
+    rc = lib().orc_colsum(I64(n), s, r, _p(Zj, C.c_int32), _p(Zx), exact, I64(n_total or n), _p(c),
+                          _p(hi, I64) if hi is not None else None, _p(lo, I64) if lo is not None else None)
+    assert rc == 0
+    return c
+
+
+def graph_laplacian_apply(Zj, Zx, s, mode, colsum_, num_class=None):
+    Zj = _i32(Zj)
+    Zx = np.ascontiguousarray(Zx, dtype=np.float64).copy()
+    n, r = Zj.shape
+    m = GL_MODES[mode] if isinstance(mode, str) else mode
+    nc = np.ascontiguousarray(num_class, dtype=np.float64) if num_class is not None else np.ones(s)
+    cs = np.ascontiguousarray(colsum_, dtype=np.float64) if colsum_ is not None else np.zeros(s)
+    rc = lib().orc_graph_laplacian_apply(I64(n), s, r, _p(Zj, C.c_int32), _p(Zx), m, _p(cs), _p(nc))
+    if rc:
+        raise ValueError("Error: the type of graph Laplacian is not supported!")
+    return Zx
+
+
+def graph_laplacian(Zj, Zx, s, mode, num_class=None, exact=1):
+    """graphLaplacian_cpp (src/Utils.cpp:195-212); returns the scaled values."""
+    if mode not in GL_MODES:
+        raise ValueError("Error: the type of graph Laplacian is not supported!")
+    if mode == "cluster-normalized" and num_class is None:
+        raise ValueError("cluster-normalized needs cluster sizes")
+    c = colsum(Zj, Zx, s, exact) if GL_MODES[mode] >= 1 else None
+    return graph_laplacian_apply(Zj, Zx, s, mode, c, num_class)
+
+
+def spectrum_scale(c):
+    c = np.ascontiguousarray(c, dtype=np.float64)
+    w = np.zeros_like(c)
+    lib().orc_spectrum_scale(c.size, _p(c), _p(w))
+    return w
+
+
+def gram(Zj, Zx, w, s, exact=1, n_total=None, limbs=None):
+    Zj = _i32(Zj)
+    Zx = np.ascontiguousarray(Zx, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    n, r = Zj.shape
+    G = np.zeros((s, s), order="F")
+    hi = lo = None
+    if limbs is not None:
+        hi, lo = limbs
+    rc = lib().orc_gram(I64(n), s, r, _p(Zj, C.c_int32), _p(Zx), _p(w), exact, I64(n_total or n), _p(G),
+                        _p(hi, I64) if hi is not None else None, _p(lo, I64) if lo is not None else None)
+    assert rc == 0
+    return G
+
+
+def gram_eigh(G, K):
+    """Top-K eigenpairs of the symmetric Gram, descending (replaces RSpectra::svds on A)."""
+    import scipy.linalg as sla
+
+    s = G.shape[0]
+    lam, Y = sla.eigh(G, subset_by_index=[s - K, s - 1])
+    return lam[::-1].copy(), np.asfortranarray(Y[:, ::-1])
+
+
+def lift(Zj, Zx, w, Y, sigma, n_total=None, nthreads=1):
+    Zj = _i32(Zj)
+    Zx = np.ascontiguousarray(Zx, dtype=np.float64)
+    w = np.ascontiguousarray(w, dtype=np.float64)
+    Y = _f(Y)
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    n, r = Zj.shape
+    s, K = Y.shape
+    V = np.zeros((n, K), order="F")
+    lib().orc_lift(I64(n), s, r, _p(Zj, C.c_int32), _p(Zx), _p(w), _p(Y), _p(sigma), K, I64(n_total or n),
+                   _p(V), nthreads)
+    return V
+
+
+def spectrum_from_Z(Zj, Zx, s, K, root=True, exact=1, nthreads=1, want_internals=False):
+    """spectrum_from_Z_cpp (src/Spectrum.cpp:146-161) through the Gram route.
+    values: sigma (root) or sigma^2, descending; vectors: sqrt(n) * U (n x K)."""
+    if K < 0:
+        K = s
+    c2 = colsum(Zj, Zx, s, exact)
+    w = spectrum_scale(c2)
+    G = gram(Zj, Zx, w, s, exact)
+    lam, Y = gram_eigh(G, K)
+    lam = np.maximum(lam, 0.0)
+    sigma = np.sqrt(lam)
+    V = lift(Zj, Zx, w, Y, sigma, nthreads=nthreads)
+    values = sigma if root else lam
+    if want_internals:
+        return values, V, dict(w=w, G=G, Y=Y, lam=lam, c2=c2)
+    return values, V
+
+
+def hk_from_spectrum(V, values, K, t, idx0, idx1, nthreads=1):
+    """HK_from_spectrum_cpp (src/Spectrum.cpp:83-94)."""
+    V = _f(V)
+    values = np.ascontiguousarray(values, dtype=np.float64)
+    idx0 = _i32(idx0)
+    idx1 = _i32(idx1)
+    H = np.zeros((idx0.size, idx1.size), order="F")
+    lib().orc_hk_from_spectrum(_p(V), I64(V.shape[0]), _p(values), K, C.c_double(t), _p(idx0, C.c_int32),
+                               I64(idx0.size), _p(idx1, C.c_int32), I64(idx1.size), _p(H), nthreads)
+    return H
+
+
+# ------------------------------------------------------------------ orchestrators
+def cross_similarity_lae(X, U, r, gl, exact=1, nthreads=1):
+    """cross_similarity_lae_cpp (src/Spectrum.cpp:101-117); U is s x (d+1) for cluster-normalized."""
+    X = _f(X)
+    d = X.shape[1]
+    U = _f(U)
+    if gl == "cluster-normalized" and U.shape[1] < d + 1:
+        raise ValueError("cluster-normalized needs the cluster-size column of U")
+    Zj, Zx, _ = lae(X, U[:, :d], r, nthreads=nthreads)
+    nc = U[:, d] if gl == "cluster-normalized" else None
+    return Zj, graph_laplacian(Zj, Zx, U.shape[0], gl, nc, exact)
+
+
+def cross_similarity_se(X, U, r, gl, epsilon=0.1, exact=1, nthreads=1):
+    """cross_similarity_se_cpp (src/Spectrum.cpp:120-142)."""
+    X = _f(X)
+    d = X.shape[1]
+    U = _f(U)
+    ind, dist = knn(X, U[:, :d], r, want_dist=True, nthreads=nthreads)
+    Zj, Zd = knn_csr(ind, dist)
+    Zx = se_weights(Zd, 4.0 * epsilon * epsilon)
+    nc = U[:, d] if gl == "cluster-normalized" else None
+    return Zj, graph_laplacian(Zj, Zx, U.shape[0], gl, nc, exact)
+
+
+def heat_kernel_spectrum(X, X_new, s, r, K, init_idx, kernel="lae", gl="cluster-normalized", root=True,
+                         epsilon=0.1, iter_max=100, exact=1, nthreads=1, want_internals=False):
+    """heat_kernel_spectrum_cpp (src/Spectrum.cpp:48-76) with subsample="kmeans" (Lloyd contract)."""
+    X_all = np.asfortranarray(np.vstack([X, X_new])) if X_new is not None and len(X_new) else _f(X)
+    U, assign, iters = kmeans_lloyd(X_all, s, init_idx, iter_max, nthreads)
+    if kernel == "lae":
+        Zj, Zx = cross_similarity_lae(X_all, U, r, gl, exact, nthreads)
+    elif kernel == "se":
+        Zj, Zx = cross_similarity_se(X_all, U, r, gl, epsilon, exact, nthreads)
+    else:
+        raise ValueError("The kernel type is not supported!")
+    if K < 0:
+        K = s
+    out = spectrum_from_Z(Zj, Zx, s, K, root, exact, nthreads, want_internals)
+    if want_internals:
+        out[2].update(U=U, assign=assign, iters=iters, Zj=Zj, Zx=Zx)
+    return out
+
+
+def lae_eigenmap(X, s, r, ndim, init_idx, norm="cluster-normalized", **kw):
+    """lae_eigenmap (src/Spectrum.cpp:17-25): eigenvalues = 1 - values (root=true)."""
+    values, V = heat_kernel_spectrum(X, None, s, r, ndim, init_idx, kernel="lae", gl=norm, root=True, **kw)
+    return 1.0 - values, V
+
+
+# ------------------------------------------------------------------ GPR tail (fixed hyper-parameters)
+def predict_regression(V, values, Y, idx0, idx1, K, pars, sigma):
+    """predict_regression_cpp, noise="same" (src/Predict.cpp:40-75)."""
+    import scipy.linalg as sla
+
+    t, noise = pars[0], pars[1]
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    m = Y.size
+    ev = 1.0 - values[:K]
+    if m <= K:
+        Cvv = hk_from_spectrum(V, values, K, t, idx0, idx0)
+        Cn = Cvv.copy()
+        Cn[np.diag_indices(m)] += sigma
+        Cn[np.diag_indices(m)] += noise
+        Cnv = hk_from_spectrum(V, values, K, t, idx1, idx0)
+        alpha = sla.cho_solve(sla.cho_factor(Cn, lower=True), Y)
+        return Cnv @ alpha
+    V1 = V[np.asarray(idx0), :K]
+    ls = np.exp(-0.5 * t * ev) + 0.0
+    Q = (ls[:, None] * (V1.T @ V1)) * ls[None, :]
+    Q[np.diag_indices(K)] += noise + sigma
+    cf = sla.cho_factor(Q, lower=True)
+    alpha = 1.0 / (noise + sigma) * (Y - V1 @ (ls * sla.cho_solve(cf, ls * (V1.T @ Y))))
+    Vnv = V[np.asarray(idx1), :K]
+    return Vnv @ (np.exp(-t * ev + 0.0) * (V1.T @ alpha))
+
+
+def posterior_covariance_regression(V, values, idx0, idx1, K, pars, sigma):
+    """posterior_covariance_regression (src/Utils.cpp:215-249)."""
+    import scipy.linalg as sla
+
+    m = len(idx0)
+    t, var = pars[0], pars[1]
+    ev = 1.0 - values[:K]
+    V2 = V[np.asarray(idx1), :K]
+    lam = np.exp(-t * ev)
+    if m <= K:
+        C11 = hk_from_spectrum(V, values, K, t, idx0, idx0)
+        K11 = C11.copy()
+        K11[np.diag_indices(m)] += var + sigma
+        C21 = hk_from_spectrum(V, values, K, t, idx1, idx0)
+        alpha = C21 @ sla.cho_solve(sla.cho_factor(K11, lower=True), np.eye(m))
+        beta = (C21 * alpha).sum(axis=1)
+    else:
+        V1 = V[np.asarray(idx0), :K]
+        ls = np.exp(-0.5 * t * ev) + 0.0
+        G1 = V1.T @ V1
+        Q = (ls[:, None] * G1) * ls[None, :]
+        Q[np.diag_indices(K)] += var + sigma
+        cf = sla.cho_factor(Q, lower=True)
+        inner = V1 - V1 @ (ls[:, None] * sla.cho_solve(cf, ls[:, None] * G1))
+        alpha = 1.0 / (var + sigma) * (lam[:, None] * (V1.T @ inner)) * lam[None, :]
+        beta = (V2 * (V2 @ alpha)).sum(axis=1)
+    return ((V2 * lam[None, :]) * V2).sum(axis=1) + var + sigma - beta
+
+
+def fit_lae_regression_fixed(X, Y, X_new, s, r, K, pars, init_idx, sigma=1e-5, gl="cluster-normalized",
+                             root=True, iter_max=100, nthreads=1):
+    """fit_lae_regression_gp_cpp (src/Fit.cpp:20-99) with pars=(t, noise) supplied instead of optimised."""
+    m = len(X)
+    n = m + len(X_new)
+    if K < 0:
+        K = s
+    values, V = heat_kernel_spectrum(X, X_new, s, r, K, init_idx, "lae", gl, root, iter_max=iter_max,
+                                     nthreads=nthreads)
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n, dtype=np.int32)
+    train = predict_regression(V, values, Y, idx0, idx0, K, pars, sigma)
+    test = predict_regression(V, values, Y, idx0, idx1, K, pars, sigma)
+    cov = posterior_covariance_regression(V, values, idx0, idx1, K, pars, sigma)
+    return dict(train=train, test=test, cov=cov, values=values, vectors=V)
