@@ -1,0 +1,484 @@
+"""Host-side mirror of FLGP's Rcpp export surface for the spectral core, bound to libflgp_b200.so.
+
+Function names, argument meaning and error behaviour follow the reference's exports
+(/root/reference/R/RcppExports.R, src/RcppExports.cpp:471-504) so that tests read like calls into
+the R package: KNN_cpp, LAE_cpp, subsample_cpp, v_to_z_cpp, local_anchor_embedding_cpp,
+cross_similarity_lae_cpp, lae_eigenmap, heat_kernel_covariance_rcpp, fit_lae_regression_gp_rcpp ...
+Matrices go in as anything numpy can view; they are handed to the C ABI column-major (R's layout).
+Sparse results come back as scipy CSR with exactly r stored entries per row (the dgRMatrix of the
+reference, explicit zeros kept).  Every numeric operation runs in the CUDA library; nothing here
+computes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import FlgpError, check
+
+GL = {"rw": 0, "normalized": 1, "cluster-normalized": 2}
+DEFAULT_MODELS = dict(subsample="kmeans", kernel="lae", gl="cluster-normalized", root=True)
+
+
+def _gl(name) -> int:
+    if isinstance(name, str):
+        if name not in GL:
+            raise FlgpError("Error: the type of graph Laplacian is not supported!")
+        return GL[name]
+    return int(name)
+
+
+def _f64(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _pf(a):
+    return a.ctypes.data_as(_lib.p_f64) if a is not None else None
+
+
+def _pi(a):
+    return a.ctypes.data_as(_lib.p_i32) if a is not None else None
+
+
+def _idx(a):
+    return np.ascontiguousarray(a, dtype=np.int32) if a is not None else None
+
+
+def _b(s: Optional[str]):
+    return s.encode() if s is not None else None
+
+
+class Context:
+    """One per process / GPU: device, stream, (optional) NCCL communicator."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = C.c_void_p()
+        check(self._lib.flgp_ctx_create(device, C.byref(self._h)))
+        self.device = device
+        self.rank, self.nranks = 0, 1
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.flgp_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- streams / accounting
+    def set_stream(self, cuda_stream: Optional[int]):
+        check(self._lib.flgp_ctx_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def synchronize(self):
+        check(self._lib.flgp_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self._lib.flgp_ctx_launch_count(self._h))
+
+    def set_timing(self, on: bool):
+        check(self._lib.flgp_ctx_set_timing(self._h, int(on)))
+
+    def stage_reset(self):
+        check(self._lib.flgp_ctx_stage_reset(self._h))
+
+    def stages(self):
+        out = []
+        for i in range(self._lib.flgp_ctx_stage_count(self._h)):
+            name = C.create_string_buffer(64)
+            ms, fl, by = C.c_double(), C.c_double(), C.c_double()
+            ln = C.c_uint64()
+            check(self._lib.flgp_ctx_stage_get(self._h, i, name, 64, C.byref(ms), C.byref(ln), C.byref(fl), C.byref(by)))
+            out.append(dict(name=name.value.decode(), ms=ms.value, launches=int(ln.value), flops=fl.value,
+                            bytes=by.value))
+        return out
+
+    def dfma_peak_tflops(self, iters: int = 1 << 15) -> float:
+        v = C.c_double()
+        check(self._lib.flgp_dfma_peak(self._h, iters, C.byref(v)))
+        return v.value
+
+    # -- multi-GPU
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        check(_lib.load().flgp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id: Optional[bytes], rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128) if unique_id is not None else None
+        check(self._lib.flgp_ctx_comm_init(self._h, buf, rank, nranks))
+        self.rank, self.nranks = rank, nranks
+
+
+_default_ctx: Optional[Context] = None
+
+
+def default_ctx() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(0)
+    return _default_ctx
+
+
+def default_init(n: int, s: int, seed: int = 0) -> np.ndarray:
+    """The s distinct sorted row indices the library starts Lloyd from when none are given."""
+    out = np.zeros(s, np.int32)
+    check(_lib.load().flgp_default_init(n, s, seed, _pi(out)))
+    return out
+
+
+def _csr(n, s, r, Zj, Zx):
+    import scipy.sparse as sp
+
+    return sp.csr_matrix((Zx.reshape(-1), Zj.reshape(-1), np.arange(0, n * r + 1, r)), shape=(n, s))
+
+
+def _from_csr(Z, r=None):
+    """(Zj, Zx, n, s, r) from a scipy CSR / (Zj, Zx, s) triple with exactly r entries per row."""
+    if isinstance(Z, tuple):
+        Zj, Zx, s = Z
+        Zj = np.ascontiguousarray(Zj, dtype=np.int32)
+        n, r = Zj.shape
+        return Zj, np.ascontiguousarray(Zx, dtype=np.float64), n, s, r
+    n, s = Z.shape
+    cnt = np.diff(Z.indptr)
+    if n == 0 or not np.all(cnt == cnt[0]):
+        raise FlgpError("the sparse matrix must store the same number of entries in every row")
+    r = int(cnt[0])
+    return (np.ascontiguousarray(Z.indices, dtype=np.int32).reshape(n, r),
+            np.ascontiguousarray(Z.data, dtype=np.float64).reshape(n, r), n, s, r)
+
+
+# ------------------------------------------------------------------------------------------------
+# Rcpp exports
+# ------------------------------------------------------------------------------------------------
+def subsample_cpp(X, s: int, method: str = "kmeans", nstart: int = 1, *, init_idx=None, seed: int = 0,
+                  iter_max: int = 100, return_info: bool = False, ctx: Optional[Context] = None):
+    """subsample_cpp (src/Utils.cpp:32-68).  "kmeans": U = [centres, size] (s x (d+1)); "random": s x d."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    n, d = X.shape
+    ucols = d + 1 if method == "kmeans" else d
+    U = np.zeros((s, ucols), order="F")
+    assign = np.zeros(n, np.int32)
+    iters = C.c_int(0)
+    check(ctx._lib.flgp_subsample(ctx._h, _pf(X), n, d, s, _b(method), iter_max, nstart, _pi(_idx(init_idx)), seed,
+                                  _pf(U), _pi(assign), C.byref(iters)))
+    if return_info:
+        return U, assign, iters.value
+    return U
+
+
+def KNN_cpp(X, U, r: int, distance: str = "Euclidean", output: bool = False, batch: int = 100, *,
+            ctx: Optional[Context] = None):
+    """KNN_cpp (src/Utils.cpp:102-192) -> {"ind_knn": n x r int32 (0-based), ["distances_sp": CSR n x s]}.
+    `batch` only bounded the reference's working set; it never changed the result and is ignored."""
+    if distance != "Euclidean":
+        raise FlgpError("The distance method of KNN is not supported!")
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    U = _f64(U)
+    n, d = X.shape
+    s = U.shape[0]
+    if U.shape[1] != d:
+        raise FlgpError("X and U must have the same number of columns")
+    ind = np.zeros((n, r), np.int32, order="F")
+    if output:
+        Zj = np.zeros((n, r), np.int32)
+        Zx = np.zeros((n, r))
+        check(ctx._lib.flgp_knn(ctx._h, _pf(X), n, d, _pf(U), s, r, _pi(ind), None, _pi(Zj), _pf(Zx)))
+        return {"ind_knn": ind, "distances_sp": _csr(n, s, r, Zj, Zx)}
+    check(ctx._lib.flgp_knn(ctx._h, _pf(X), n, d, _pf(U), s, r, _pi(ind), None, None, None))
+    return {"ind_knn": ind}
+
+
+def knn_distances(X, U, r: int, *, ctx: Optional[Context] = None):
+    """ind_knn together with the n x r squared distances in the same (ascending) order."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    U = _f64(U)
+    n, d = X.shape
+    s = U.shape[0]
+    ind = np.zeros((n, r), np.int32, order="F")
+    dist = np.zeros((n, r), order="F")
+    check(ctx._lib.flgp_knn(ctx._h, _pf(X), n, d, _pf(U), s, r, _pi(ind), _pf(dist), None, None))
+    return ind, dist
+
+
+def v_to_z_cpp(v, *, ctx: Optional[Context] = None):
+    """v_to_z_cpp (src/lae.cpp:137-153)."""
+    ctx = ctx or default_ctx()
+    v = np.ascontiguousarray(v, dtype=np.float64).reshape(-1)
+    z = np.zeros_like(v)
+    check(ctx._lib.flgp_simplex_project(ctx._h, _pf(v), v.size, _pf(z)))
+    return z
+
+
+def local_anchor_embedding_cpp(x, U, *, ctx: Optional[Context] = None):
+    """local_anchor_embedding_cpp (src/lae.cpp:76-133); U is r x d."""
+    ctx = ctx or default_ctx()
+    x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+    U = _f64(U)
+    r, d = U.shape
+    if x.size != d:
+        raise FlgpError("x and U must have the same number of columns")
+    z = np.zeros(r)
+    check(ctx._lib.flgp_lae_point(ctx._h, _pf(x), d, _pf(U), r, _pf(z)))
+    return z
+
+
+def LAE_cpp(X, U, r: int, *, return_stats: bool = False, ctx: Optional[Context] = None):
+    """LAE_cpp (src/lae.cpp:48-70): sparse n x s matrix of simplex weights on the r nearest anchors."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    U = _f64(U)
+    n, d = X.shape
+    s = U.shape[0]
+    Zj = np.zeros((n, r), np.int32)
+    Zx = np.zeros((n, r))
+    stats = np.zeros(2, np.int64)
+    check(ctx._lib.flgp_lae(ctx._h, _pf(X), n, d, _pf(U), s, r, _pi(Zj), _pf(Zx), stats.ctypes.data_as(_lib.p_i64)))
+    Z = _csr(n, s, r, Zj, Zx)
+    return (Z, stats) if return_stats else Z
+
+
+def graphLaplacian_cpp(Z, gl: str, num_class=None, *, ctx: Optional[Context] = None):
+    """graphLaplacian_cpp (src/Utils.cpp:195-212); returns the scaled matrix (the reference works in place)."""
+    ctx = ctx or default_ctx()
+    Zj, Zx, n, s, r = _from_csr(Z)
+    Zx = Zx.copy()
+    nc = np.ascontiguousarray(num_class, dtype=np.float64) if num_class is not None else None
+    check(ctx._lib.flgp_graph_laplacian(ctx._h, n, s, r, _pi(Zj), _pf(Zx), _gl(gl), _pf(nc)))
+    return _csr(n, s, r, Zj, Zx)
+
+
+def cross_similarity_lae_cpp(X, U, r: int, gl: str = "rw", *, ctx: Optional[Context] = None):
+    """cross_similarity_lae_cpp (src/Spectrum.cpp:101-117); U is s x (d+1) for cluster-normalized."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    U = _f64(U)
+    n, d = X.shape
+    s, ucols = U.shape
+    Zj = np.zeros((n, r), np.int32)
+    Zx = np.zeros((n, r))
+    check(ctx._lib.flgp_cross_similarity_lae(ctx._h, _pf(X), n, d, _pf(U), s, ucols, r, _gl(gl), _pi(Zj), _pf(Zx)))
+    return _csr(n, s, r, Zj, Zx)
+
+
+def cross_similarity_se_cpp(X, U, r: int, gl: str = "rw", epsilon: float = 0.1, *, ctx: Optional[Context] = None):
+    """cross_similarity_se_cpp (src/Spectrum.cpp:120-142)."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    U = _f64(U)
+    n, d = X.shape
+    s, ucols = U.shape
+    Zj = np.zeros((n, r), np.int32)
+    Zx = np.zeros((n, r))
+    check(ctx._lib.flgp_cross_similarity_se(ctx._h, _pf(X), n, d, _pf(U), s, ucols, r, _gl(gl), epsilon, _pi(Zj),
+                                            _pf(Zx)))
+    return _csr(n, s, r, Zj, Zx)
+
+
+class EigenPair:
+    """Device-resident EigenPair (src/Spectrum.h:117-124): values (K) and the n x K vectors, which are
+    kept factored (sparse A times an s x K lift operator) and only materialised on request."""
+
+    def __init__(self, ctx: Context, handle):
+        self.ctx = ctx
+        self._h = handle
+        info = np.zeros(10, np.int64)
+        check(ctx._lib.flgp_spectrum_info(self._h, info.ctypes.data_as(_lib.p_i64)))
+        (self.n_local, self.n_total, self.row_offset, self.d, self.s, self.r, self.K, self.kmeans_iters,
+         self.lae_iters, self.lae_backtracks) = (int(v) for v in info)
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            self.ctx._lib.flgp_spectrum_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def values(self) -> np.ndarray:
+        v = np.zeros(self.K)
+        check(self.ctx._lib.flgp_spectrum_values(self._h, _pf(v)))
+        return v
+
+    @property
+    def vectors(self) -> np.ndarray:
+        V = np.zeros((self.n_local, self.K), order="F")
+        check(self.ctx._lib.flgp_spectrum_vectors(self._h, _pf(V)))
+        return V
+
+    def anchors(self, ucols: Optional[int] = None) -> np.ndarray:
+        U = np.zeros((self.s, ucols or self.d + 1), order="F")
+        check(self.ctx._lib.flgp_spectrum_anchors(self._h, _pf(U)))
+        return U
+
+    def Z(self):
+        Zj = np.zeros((self.n_local, self.r), np.int32)
+        Zx = np.zeros((self.n_local, self.r))
+        check(self.ctx._lib.flgp_spectrum_z(self._h, _pi(Zj), _pf(Zx)))
+        return _csr(self.n_local, self.s, self.r, Zj, Zx)
+
+    def rows(self, idx) -> np.ndarray:
+        """mat_indexing(eigenvectors, idx, 0..K-1) (src/Utils.h:130-137)."""
+        idx = _idx(idx)
+        V = np.zeros((idx.size, self.K), order="F")
+        check(self.ctx._lib.flgp_spectrum_gather_rows(self._h, _pi(idx), idx.size, _pf(V)))
+        return V
+
+
+def spectrum_from_Z_cpp(Z, K: int, root: bool = False, *, ctx: Optional[Context] = None) -> EigenPair:
+    """spectrum_from_Z_cpp (src/Spectrum.cpp:146-161)."""
+    ctx = ctx or default_ctx()
+    Zj, Zx, n, s, r = _from_csr(Z)
+    h = C.c_void_p()
+    check(ctx._lib.flgp_spectrum_from_z(ctx._h, n, s, r, _pi(Zj), _pf(Zx), K, int(root), None, None, C.byref(h)))
+    return EigenPair(ctx, h)
+
+
+def heat_kernel_spectrum_cpp(X, X_new, s: int, r: int, K: int, models=None, nstart: int = 1, epsilon: float = 0.1, *,
+                             init_idx=None, seed: int = 0, iter_max: int = 100,
+                             ctx: Optional[Context] = None) -> EigenPair:
+    """heat_kernel_spectrum_cpp (src/Spectrum.cpp:48-76)."""
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    X = _f64(X)
+    m, d = X.shape
+    if X_new is not None and len(X_new):
+        X_new = _f64(X_new)
+        m_new = X_new.shape[0]
+    else:
+        X_new, m_new = None, 0
+    h = C.c_void_p()
+    check(ctx._lib.flgp_heat_kernel_spectrum(ctx._h, _pf(X), m, _pf(X_new), m_new, d, s, r, K, _b(mo["subsample"]),
+                                             _b(mo["kernel"]), _gl(mo["gl"]), int(bool(mo["root"])), nstart, epsilon,
+                                             iter_max, _pi(_idx(init_idx)), seed, C.byref(h)))
+    return EigenPair(ctx, h)
+
+
+def heat_kernel_spectrum_sharded(X_local, n_total: int, row_offset: int, s: int, r: int, K: int, models=None,
+                                 nstart: int = 1, epsilon: float = 0.1, *, init_idx=None, seed: int = 0,
+                                 iter_max: int = 100, ctx: Optional[Context] = None, device_ptr: Optional[int] = None,
+                                 n_local: Optional[int] = None, d: Optional[int] = None) -> EigenPair:
+    """The same on one contiguous block of rows of X_all (multi-GPU); with `device_ptr` the block already
+    lives in HBM (column-major, leading dimension n_local)."""
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    h = C.c_void_p()
+    args = (s, r, K, _b(mo["subsample"]), _b(mo["kernel"]), _gl(mo["gl"]), int(bool(mo["root"])), nstart, epsilon,
+            iter_max, _pi(_idx(init_idx)), seed, C.byref(h))
+    if device_ptr is not None:
+        check(ctx._lib.flgp_heat_kernel_spectrum_dev(ctx._h, C.c_void_p(device_ptr), n_local, n_total, row_offset, d,
+                                                     *args))
+    else:
+        X_local = _f64(X_local)
+        n_local, d = X_local.shape
+        check(ctx._lib.flgp_heat_kernel_spectrum_sharded(ctx._h, _pf(X_local), n_local, n_total, row_offset, d, *args))
+    return EigenPair(ctx, h)
+
+
+def HK_from_spectrum_cpp(eigenpair: EigenPair, K: int, t: float, idx0, idx1) -> np.ndarray:
+    """HK_from_spectrum_cpp (src/Spectrum.cpp:83-94)."""
+    idx0 = _idx(idx0)
+    idx1 = _idx(idx1)
+    H = np.zeros((idx0.size, idx1.size), order="F")
+    check(eigenpair.ctx._lib.flgp_hk_from_spectrum(eigenpair._h, K, t, _pi(idx0), idx0.size, _pi(idx1), idx1.size,
+                                                   _pf(H)))
+    return H
+
+
+def lae_eigenmap(X, s: int, r: int, ndim: int, subsample: str = "kmeans", norm: str = "cluster-normalized",
+                 nstart: int = 1, *, init_idx=None, seed: int = 0, iter_max: int = 100,
+                 ctx: Optional[Context] = None):
+    """lae_eigenmap (src/Spectrum.cpp:17-25) -> {"eigenvalues", "eigenvectors"}."""
+    ctx = ctx or default_ctx()
+    X = _f64(X)
+    n, d = X.shape
+    ev = np.zeros(ndim)
+    V = np.zeros((n, ndim), order="F")
+    check(ctx._lib.flgp_lae_eigenmap(ctx._h, _pf(X), n, d, s, r, ndim, _b(subsample), _gl(norm), nstart, iter_max,
+                                     _pi(_idx(init_idx)), seed, _pf(ev), _pf(V)))
+    return {"eigenvalues": ev, "eigenvectors": V}
+
+
+def heat_kernel_covariance_rcpp(X, X_new, s: int, r: int, t: float, K: int = -1, models=None, nstart: int = 1,
+                                epsilon: float = 0.1, *, init_idx=None, seed: int = 0, iter_max: int = 100,
+                                ctx: Optional[Context] = None) -> np.ndarray:
+    """heat_kernel_covariance_rcpp (R/Fit.R:760-770 -> src/Spectrum.cpp:28-43): H is (m+m_new) x m."""
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    X = _f64(X)
+    m, d = X.shape
+    if X_new is not None and len(X_new):
+        X_new = _f64(X_new)
+        m_new = X_new.shape[0]
+    else:
+        X_new, m_new = None, 0
+    H = np.zeros((m + m_new, m), order="F")
+    check(ctx._lib.flgp_heat_kernel_covariance(ctx._h, _pf(X), m, _pf(X_new), m_new, d, s, r, t, K,
+                                               _b(mo["subsample"]), _b(mo["kernel"]), _gl(mo["gl"]),
+                                               int(bool(mo["root"])), nstart, epsilon, iter_max, _pi(_idx(init_idx)),
+                                               seed, _pf(H)))
+    return H
+
+
+def regression_fixed(eigenpair: EigenPair, Y_local, m_total: int, K: int, pars: Sequence[float], sigma: float = 1e-5,
+                     want_cov: bool = True):
+    """predict_regression_cpp + posterior_covariance_regression at fixed pars = (t, noise) on a handle."""
+    Y_local = np.ascontiguousarray(Y_local, dtype=np.float64).reshape(-1)
+    y = np.zeros(eigenpair.n_local)
+    cov = np.zeros(eigenpair.n_local) if want_cov else None
+    check(eigenpair.ctx._lib.flgp_regression_fixed(eigenpair._h, _pf(Y_local), m_total, K, pars[0], pars[1], sigma,
+                                                   _pf(y), _pf(cov)))
+    return y, cov
+
+
+def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, approach="posterior",
+                               noise="same", models=None, output_cov: bool = False, nstart: int = 1, *,
+                               pars: Sequence[float], init_idx=None, seed: int = 0, iter_max: int = 100,
+                               ctx: Optional[Context] = None):
+    """fit_lae_regression_gp_rcpp (R/Fit.R:56-69 -> src/Fit.cpp:20-99) with the hyper-parameters
+    pars = (t, noise variance) SUPPLIED: the nlopt optimiser of the reference (src/train.cpp:557-671) is
+    outside the hot path."""
+    if noise != "same":
+        raise FlgpError("The noise setting is illegal!" if noise != "different"
+                        else "noise=\"different\" needs the optimiser; not part of the fixed-parameter path")
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    train = np.zeros(m)
+    test = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    check(ctx._lib.flgp_fit_lae_regression_fixed(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma,
+                                                 pars[0], pars[1], _b(mo["subsample"]), _b(mo["kernel"]),
+                                                 _gl(mo["gl"]), int(bool(mo["root"])), nstart, iter_max,
+                                                 _pi(_idx(init_idx)), seed, _pf(train), _pf(test), _pf(cov)))
+    res = {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(pars)}
+    if output_cov:
+        res["C"] = heat_kernel_covariance_rcpp(X, X_new, s, r, pars[0], K, mo, nstart, init_idx=init_idx, seed=seed,
+                                               iter_max=iter_max, ctx=ctx)
+    return res

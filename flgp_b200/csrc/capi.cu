@@ -1,0 +1,982 @@
+// capi.cu — the C ABI (include/flgp.h) and the host-side orchestration that mirrors the reference's
+// C++ seams: subsample_cpp, KNN_cpp, LAE_cpp, graphLaplacian_cpp, cross_similarity_{lae,se}_cpp,
+// spectrum_from_Z_cpp, heat_kernel_spectrum_cpp, HK_from_spectrum_cpp, lae_eigenmap,
+// heat_kernel_covariance_cpp and the fixed-hyper-parameter GPR tail (file:line in include/flgp.h).
+// Error behaviour mirrors Rcpp::stop: C++ exception inside, status + message at the boundary.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <unordered_set>
+
+#include "../../include/flgp.h"
+#include "kernels.cuh"
+
+using namespace flgp;
+
+namespace flgp {
+void comm_unique_id(void* out128);
+void comm_init(Ctx* c, const void* id128, int rank, int nranks);
+}  // namespace flgp
+
+struct flgp_ctx {
+  Ctx c;
+};
+
+struct flgp_spectrum {
+  Ctx* c = nullptr;
+  int64_t n_local = 0, n_total = 0, row_offset = 0;
+  int d = 0, s = 0, r = 0, K = 0, ucols = 0;
+  bool root = true;
+  DevBuf<int32_t> Zj;
+  DevBuf<double> Zx;   // final Z (after graph-Laplacian scaling), n_local * r
+  DevBuf<double> w;    // s: A = Z diag(w)
+  DevBuf<double> Wm;   // s x K row-major: Y(:,k) * sqrt(n_total) / sigma_k   (lift operator)
+  DevBuf<double> U;    // s x ucols anchors (+ sizes)
+  std::vector<double> values;  // K, as exported (sigma or sigma^2)
+  int kmeans_iters = 0;
+  long long lae_iters = 0, lae_bts = 0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+template <class F>
+int guard(F f) {
+  try {
+    f();
+    return 0;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return 1;
+  }
+}
+
+void need(bool ok, const char* msg) {
+  if (!ok) fail(2, "%s", msg);
+}
+
+int parse_gl(int gl) {
+  if (gl < 0 || gl > 2) fail(2, "Error: the type of graph Laplacian is not supported!");
+  return gl;
+}
+
+std::vector<int32_t> default_init(int64_t n, int s, uint64_t seed) {
+  if (s < 1 || s > n) fail(2, "subsample: need 1 <= s <= n");
+  std::unordered_set<int64_t> seen;
+  std::vector<int32_t> idx;
+  idx.reserve(s);
+  uint64_t state = seed;
+  while ((int)idx.size() < s) {
+    state += 0x9E3779B97F4A7C15ull;
+    uint64_t z = state;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    int64_t i = (int64_t)(z % (uint64_t)n);
+    if (seen.insert(i).second) idx.push_back((int32_t)i);
+  }
+  std::sort(idx.begin(), idx.end());
+  return idx;
+}
+
+// ---- small dense host algebra for the m- and K-sized GP back-end (reference: Eigen LLT) ----------
+// column-major n x n, lower Cholesky in place; returns false if not positive definite
+bool chol_lower(std::vector<double>& A, int n) {
+  for (int j = 0; j < n; ++j) {
+    double dj = A[j + (size_t)n * j];
+    for (int k = 0; k < j; ++k) dj -= A[j + (size_t)n * k] * A[j + (size_t)n * k];
+    if (!(dj > 0.0)) return false;
+    dj = std::sqrt(dj);
+    A[j + (size_t)n * j] = dj;
+    for (int i = j + 1; i < n; ++i) {
+      double v = A[i + (size_t)n * j];
+      for (int k = 0; k < j; ++k) v -= A[i + (size_t)n * k] * A[j + (size_t)n * k];
+      A[i + (size_t)n * j] = v / dj;
+    }
+  }
+  return true;
+}
+// solve L L^T x = b in place for nrhs columns (B column-major n x nrhs)
+void chol_solve(const std::vector<double>& L, int n, double* B, int nrhs) {
+  for (int c = 0; c < nrhs; ++c) {
+    double* b = B + (size_t)n * c;
+    for (int i = 0; i < n; ++i) {
+      double v = b[i];
+      for (int k = 0; k < i; ++k) v -= L[i + (size_t)n * k] * b[k];
+      b[i] = v / L[i + (size_t)n * i];
+    }
+    for (int i = n - 1; i >= 0; --i) {
+      double v = b[i];
+      for (int k = i + 1; k < n; ++k) v -= L[k + (size_t)n * i] * b[k];
+      b[i] = v / L[i + (size_t)n * i];
+    }
+  }
+}
+
+__global__ void build_lift_kernel(const double* __restrict__ Y, int s, int K, const double* __restrict__ scale,
+                                  double* __restrict__ Wm) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s * K) return;
+  int k = e % K, cidx = e / K;
+  Wm[e] = Y[cidx + (size_t)s * k] * scale[k];
+}
+
+__global__ void gather_rows_kernel(const double* __restrict__ src, int64_t ld, int cols, const int32_t* __restrict__ idx,
+                                   int s, double* __restrict__ dst) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= s * cols) return;
+  int j = e % s, k = e / s;
+  dst[j + (size_t)s * k] = src[idx[j] + ld * k];
+}
+
+// ---- stages on device buffers ----------------------------------------------------------------------
+struct Models {
+  std::string subsample, kernel;
+  int gl;
+  bool root;
+  double epsilon;
+  int nstart, iter_max;
+};
+
+// anchors: fills sp->U (s x ucols)
+void stage_subsample(Ctx* c, flgp_spectrum* sp, const double* X, const Models& mo, const int32_t* init_idx,
+                     uint64_t seed, int32_t* assign_out) {
+  const int s = sp->s, d = sp->d;
+  std::vector<int32_t> own;
+  if (!init_idx) {
+    own = default_init(sp->n_total, s, seed);
+    init_idx = own.data();
+  }
+  if (mo.subsample == "kmeans") {
+    need(mo.nstart >= 1, "nstart must be >= 1");
+    sp->ucols = d + 1;
+    sp->U.alloc((size_t)s * (d + 1));
+    DevBuf<int32_t> assign;
+    int32_t* ap = assign_out;
+    if (!ap) {
+      assign.alloc(std::max<int64_t>(sp->n_local, 1));
+      ap = assign.p;
+    }
+    StageScope st(c, "kmeans");
+    kmeans_run(c, X, sp->n_local, sp->n_local, d, s, sp->n_total, sp->row_offset, init_idx, mo.iter_max, sp->U.p, ap,
+               &sp->kmeans_iters);
+    if (st.idx >= 0) {
+      c->stages[st.idx].flops = 2.0 * s * d * (double)sp->n_local * sp->kmeans_iters;
+      c->stages[st.idx].bytes = (8.0 * d + 4.0) * (double)sp->n_local * sp->kmeans_iters;
+    }
+  } else if (mo.subsample == "random") {
+    if (mo.gl == FLGP_GL_CLUSTER_NORMALIZED)
+      fail(2, "subsample=\"random\" returns no cluster sizes; it cannot be combined with gl=\"cluster-normalized\"");
+    need(c->nranks == 1, "subsample=\"random\" is single-GPU only");
+    sp->ucols = d;
+    sp->U.alloc((size_t)s * d);
+    for (int j = 0; j < s; ++j) need(init_idx[j] >= 0 && init_idx[j] < sp->n_local, "initial index out of range");
+    DevBuf<int32_t> idx(s);
+    idx.upload(init_idx, s, c->stream);
+    FLGP_LAUNCH(c, gather_rows_kernel, ceil_div(s * d, 256), 256, 0, X, sp->n_local, d, idx.p, s, sp->U.p);
+    sync(c);
+  } else {
+    fail(2, "The subsample method is not supported!");
+  }
+}
+
+// Z for the local rows (before graph-Laplacian scaling) into sp->Zj / sp->Zx
+void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const double* U, const std::string& kernel,
+                            double epsilon) {
+  const int64_t n = sp->n_local;
+  const int s = sp->s, d = sp->d, r = sp->r;
+  sp->Zj.alloc(std::max<int64_t>(n * r, 1));
+  sp->Zx.alloc(std::max<int64_t>(n * r, 1));
+  DevBuf<int32_t> ind(std::max<int64_t>(n * r, 1));
+  if (kernel == "lae") {
+    {
+      StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 4.0 * r) * (double)n);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, nullptr);
+    }
+    DevBuf<long long> stats(2);
+    stats.zero(c->stream);
+    {
+      StageScope st(c, "lae", 0.0, (8.0 * d + 4.0 * r + 12.0 * r) * (double)n);
+      lae_run(c, X, n, n, d, U, s, s, r, ind.p, sp->Zj.p, sp->Zx.p, nullptr, stats.p);
+    }
+    long long h[2];
+    stats.download(h, 2, c->stream);
+    sync(c);
+    sp->lae_iters = h[0];
+    sp->lae_bts = h[1];
+  } else if (kernel == "se") {
+    DevBuf<double> dist(std::max<int64_t>(n * r, 1));
+    {
+      StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 12.0 * r) * (double)n);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, dist.p);
+    }
+    StageScope st(c, "se_weights", 0.0, 36.0 * r * (double)n);
+    knn_to_csr_run(c, n, r, ind.p, dist.p, sp->Zj.p, sp->Zx.p);
+    se_weights_run(c, sp->Zx.p, n * r, 4.0 * epsilon * epsilon, sp->Zx.p);
+    sync(c);
+  } else {
+    fail(2, "The kernel type is not supported!");
+  }
+}
+
+void stage_graph_laplacian(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int gl,
+                           const double* num_class, int64_t n_total) {
+  StageScope st(c, "graph_laplacian", 0.0, (gl >= 1 ? 36.0 : 24.0) * r * (double)n);
+  DevBuf<double> cs(s);
+  if (gl >= 1) colsum_run(c, n, s, r, Zj, Zx, n_total, cs.p);
+  gl_apply_run(c, n, s, r, Zj, Zx, gl, cs.p, num_class);
+  sync(c);
+}
+
+// spectrum_from_Z_cpp on sp->Zj/Zx: fills w, Wm, values
+void stage_spectrum(Ctx* c, flgp_spectrum* sp, int K, bool root) {
+  const int s = sp->s, r = sp->r;
+  const int64_t n = sp->n_local;
+  if (K < 0) K = s;
+  need(K >= 1 && K <= s, "need 1 <= K <= s");
+  sp->K = K;
+  sp->root = root;
+  sp->w.alloc(s);
+  DevBuf<double> G((size_t)s * s);
+  {
+    StageScope st(c, "gram", 2.0 * r * r * (double)n, 24.0 * r * (double)n + 8.0 * s * s);
+    DevBuf<double> cs(s);
+    colsum_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->n_total, cs.p);
+    spectrum_scale_run(c, s, cs.p, sp->w.p);
+    gram_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->n_total, G.p);
+  }
+  DevBuf<double> lam(K), Y((size_t)s * K);
+  {
+    StageScope st(c, "eigh", (4.0 / 3.0) * s * (double)s * s + 2.0 * s * (double)s * K, 8.0 * s * (double)s * s);
+    eigh_topk_run(c, G.p, s, K, lam.p, Y.p);
+  }
+  std::vector<double> lam_h(K), scale(K);
+  lam.download(lam_h.data(), K, c->stream);
+  sync(c);
+  sp->values.resize(K);
+  const double sq = std::sqrt((double)sp->n_total);
+  for (int k = 0; k < K; ++k) {
+    double l = lam_h[k] > 0.0 ? lam_h[k] : 0.0;
+    double sg = std::sqrt(l);
+    sp->values[k] = root ? sg : l;           // src/Spectrum.cpp:153-155
+    scale[k] = sg > 0.0 ? sq / sg : 0.0;     // src/Spectrum.cpp:157-158 (sqrt(n)) and u = A v / sigma
+  }
+  DevBuf<double> dscale(K);
+  dscale.upload(scale.data(), K, c->stream);
+  sp->Wm.alloc((size_t)s * K);
+  FLGP_LAUNCH(c, build_lift_kernel, ceil_div(s * K, 256), 256, 0, Y.p, s, K, dscale.p, sp->Wm.p);
+  sync(c);
+}
+
+std::unique_ptr<flgp_spectrum> spectrum_pipeline(Ctx* c, const double* Xdev, int64_t n_local, int64_t n_total,
+                                                 int64_t row_offset, int d, int s, int r, int K, const Models& mo,
+                                                 const int32_t* init_idx, uint64_t seed) {
+  need(n_local >= 0 && n_total >= 1 && d >= 1, "bad matrix shape");
+  need(row_offset >= 0 && row_offset + n_local <= n_total, "shard outside the matrix");
+  need(s >= 1 && s <= n_total, "need 1 <= s <= n");
+  need(r >= 1 && r <= s, "need 1 <= r <= s");
+  need(n_total < ((int64_t)1 << 31), "n must fit in int32 indices per process API");
+  parse_gl(mo.gl);
+  std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
+  sp->c = c;
+  sp->n_local = n_local;
+  sp->n_total = n_total;
+  sp->row_offset = row_offset;
+  sp->d = d;
+  sp->s = s;
+  sp->r = r;
+  stage_subsample(c, sp.get(), Xdev, mo, init_idx, seed, nullptr);
+  stage_cross_similarity(c, sp.get(), Xdev, sp->U.p, mo.kernel, mo.epsilon);
+  const double* nc = (mo.gl == FLGP_GL_CLUSTER_NORMALIZED) ? sp->U.p + (size_t)s * d : nullptr;
+  stage_graph_laplacian(c, n_local, s, r, sp->Zj.p, sp->Zx.p, mo.gl, nc, n_total);
+  stage_spectrum(c, sp.get(), K, mo.root);
+  return sp;
+}
+
+// upload [X; X_new] as one column-major n x d device matrix (the concat of src/Spectrum.cpp:50-53)
+DevBuf<double> upload_concat(Ctx* c, const double* X, int64_t m, const double* X_new, int64_t m_new, int d) {
+  const int64_t n = m + m_new;
+  DevBuf<double> dX((size_t)std::max<int64_t>(n * d, 1));
+  if (m > 0)
+    FLGP_CUDA(cudaMemcpy2DAsync(dX.p, n * sizeof(double), X, m * sizeof(double), m * sizeof(double), d,
+                                cudaMemcpyHostToDevice, c->stream));
+  if (m_new > 0)
+    FLGP_CUDA(cudaMemcpy2DAsync(dX.p + m, n * sizeof(double), X_new, m_new * sizeof(double), m_new * sizeof(double), d,
+                                cudaMemcpyHostToDevice, c->stream));
+  return dX;
+}
+
+Models make_models(const char* subsample, const char* kernel, int gl, int root, int nstart, double epsilon,
+                   int iter_max) {
+  Models mo;
+  mo.subsample = subsample ? subsample : "kmeans";
+  mo.kernel = kernel ? kernel : "lae";
+  mo.gl = gl;
+  mo.root = root != 0;
+  mo.epsilon = epsilon;
+  mo.nstart = nstart;
+  mo.iter_max = iter_max > 0 ? iter_max : 100;
+  return mo;
+}
+
+// ---- GPR tail -------------------------------------------------------------------------------------
+// Everything n-sized is folded through the r non-zeros of each row of A:
+//   mean_i = a_i . (Wm coef),   var_i = add + a_i^T (Wm M Wm^T) a_i,
+// coef (K) and M (K x K) come from the K x K (m > K, Woodbury) or m x m (m <= K) system on the host.
+void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double t, double noise,
+                          double sigma, double* y_pred, double* cov) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total, "bad number of training rows");
+  const int s = sp->s, r = sp->r, KK = sp->K;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  StageScope st(c, "gpr_tail", 2.0 * r * (double)sp->n_local * (1 + r), 24.0 * r * (double)sp->n_local);
+  std::vector<double> lam(K), ls(K);
+  for (int k = 0; k < K; ++k) {
+    double ev = 1.0 - sp->values[k];
+    lam[k] = std::exp(-t * ev);
+    ls[k] = std::exp(-0.5 * t * ev) + 0.0;
+  }
+  const double ns = noise + sigma;
+  std::vector<double> coef(KK, 0.0), M((size_t)KK * KK, 0.0);  // padded to the handle's K with zeros
+  // training rows of the lifted eigenvectors, row-major m_local x KK
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
+  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  if (m_total > K) {
+    // Woodbury branch (src/Predict.cpp:61-74, src/Utils.cpp:237-244)
+    DevBuf<double> Gg((size_t)KK * KK + KK);
+    gram_small_run(c, V1.p, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
+    comm_allreduce_f64(c, Gg.p, (size_t)KK * KK + KK);
+    std::vector<double> Gh((size_t)KK * KK + KK);
+    Gg.download(Gh.data(), Gh.size(), c->stream);
+    sync(c);
+    auto G1 = [&](int i, int j) { return Gh[i + (size_t)KK * j]; };
+    const double* g1 = Gh.data() + (size_t)KK * KK;
+    std::vector<double> Q((size_t)K * K);
+    for (int j = 0; j < K; ++j)
+      for (int i = 0; i < K; ++i) Q[i + (size_t)K * j] = ls[i] * G1(i, j) * ls[j] + (i == j ? ns : 0.0);
+    if (!chol_lower(Q, K)) fail(2, "regression: K x K system is not positive definite");
+    // q = Q^-1 (ls o g1);  V1^T alpha = (g1 - G1 (ls o q)) / ns;  coef = lam o V1^T alpha
+    std::vector<double> q(K);
+    for (int k = 0; k < K; ++k) q[k] = ls[k] * g1[k];
+    chol_solve(Q, K, q.data(), 1);
+    for (int i = 0; i < K; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < K; ++j) acc += G1(i, j) * (ls[j] * q[j]);
+      coef[i] = lam[i] * ((g1[i] - acc) / ns);
+    }
+    // alphaM = (1/ns) Lam (G1 - G1 Ls Q^-1 Ls G1) Lam ;  M = Lam - alphaM
+    std::vector<double> R((size_t)K * K);
+    for (int j = 0; j < K; ++j)
+      for (int i = 0; i < K; ++i) R[i + (size_t)K * j] = ls[i] * G1(i, j);
+    chol_solve(Q, K, R.data(), K);  // Q^-1 Ls G1
+    for (int j = 0; j < K; ++j)
+      for (int i = 0; i < K; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc += G1(i, k) * ls[k] * R[k + (size_t)K * j];
+        double am = lam[i] * (G1(i, j) - acc) * lam[j] / ns;
+        M[i + (size_t)KK * j] = (i == j ? lam[i] : 0.0) - am;
+      }
+  } else {
+    // direct branch (src/Predict.cpp:47-59, src/Utils.cpp:228-236): every rank needs all m rows
+    const int m = (int)m_total;
+    DevBuf<double> Vall((size_t)m * KK + m);
+    Vall.zero(c->stream);
+    if (m_local > 0) {
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+                                cudaMemcpyDeviceToDevice, c->stream));
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + sp->row_offset, Ydev, sizeof(double) * m_local,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    }
+    comm_allreduce_f64(c, Vall.p, (size_t)m * KK + m);
+    std::vector<double> Vh((size_t)m * KK + m);
+    Vall.download(Vh.data(), Vh.size(), c->stream);
+    sync(c);
+    const double* Yh = Vh.data() + (size_t)m * KK;
+    auto V = [&](int i, int k) { return Vh[(size_t)i * KK + k]; };
+    std::vector<double> Cn((size_t)m * m);
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
+        Cn[i + (size_t)m * j] = acc + (i == j ? ns : 0.0);
+      }
+    if (!chol_lower(Cn, m)) fail(2, "regression: m x m covariance is not positive definite");
+    std::vector<double> alpha(Yh, Yh + m);
+    chol_solve(Cn, m, alpha.data(), 1);
+    for (int k = 0; k < K; ++k) {
+      double acc = 0.0;
+      for (int i = 0; i < m; ++i) acc += V(i, k) * alpha[i];
+      coef[k] = lam[k] * acc;
+    }
+    // M = Lam - Lam V1^T K11^-1 V1 Lam
+    std::vector<double> S((size_t)m * K);  // V1 Lam, column-major m x K
+    for (int k = 0; k < K; ++k)
+      for (int i = 0; i < m; ++i) S[i + (size_t)m * k] = V(i, k) * lam[k];
+    std::vector<double> S2 = S;
+    chol_solve(Cn, m, S2.data(), K);  // K11^-1 V1 Lam
+    for (int b = 0; b < K; ++b)
+      for (int a = 0; a < K; ++a) {
+        double acc = 0.0;
+        for (int i = 0; i < m; ++i) acc += S[i + (size_t)m * a] * S2[i + (size_t)m * b];
+        M[a + (size_t)KK * b] = (a == b ? lam[a] : 0.0) - acc;
+      }
+  }
+  // fold through the lift operator Wm (s x KK row-major)
+  DevBuf<double> dcoef(KK), dM((size_t)KK * KK), wv(s), T((size_t)s * KK), B((size_t)s * s);
+  dcoef.upload(coef.data(), KK, c->stream);
+  dM.upload(M.data(), (size_t)KK * KK, c->stream);
+  gemv_run(c, sp->Wm.p, dcoef.p, s, KK, wv.p);
+  sparse_rowdot_run(c, sp->n_local, r, sp->Zj.p, sp->Zx.p, sp->w.p, wv.p, y_pred);
+  if (cov) {
+    // M is symmetric, so its column-major image is also its row-major image
+    gemm_nn_run(c, sp->Wm.p, dM.p, s, KK, KK, T.p);               // T = Wm M        (s x KK row-major)
+    gemm_nt_run(c, T.p, sp->Wm.p, nullptr, s, s, KK, B.p, s);     // B = T Wm^T      (s x s)
+    sparse_quadform_run(c, sp->n_local, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, B.p, ns, cov);
+  }
+  sync(c);
+}
+
+}  // namespace
+
+extern "C" {
+
+int flgp_version(void) { return 100; }
+const char* flgp_last_error(void) { return g_err.c_str(); }
+
+int flgp_ctx_create(int device, flgp_ctx** out) {
+  return guard([&] {
+    need(out != nullptr, "null output");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      fail(3, "no CUDA device available (%s): libflgp_b200 has no CPU fallback", cudaGetErrorString(e));
+    need(device >= 0 && device < count, "device index out of range");
+    FLGP_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    FLGP_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) fail(3, "libflgp_b200 is built for sm_100a only (found sm_%d%d)", prop.major, prop.minor);
+    std::unique_ptr<flgp_ctx> h(new flgp_ctx);
+    h->c.device = device;
+    h->c.sm_count = prop.multiProcessorCount;
+    FLGP_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
+    h->c.own_stream = true;
+    FLGP_CUDA(cudaMallocHost(&h->c.pinned, 64 * sizeof(int64_t)));
+    *out = h.release();
+  });
+}
+
+void flgp_ctx_destroy(flgp_ctx* ctx) {
+  if (!ctx) return;
+  comm_destroy(&ctx->c);
+  for (auto& s : ctx->c.stages) {
+    cudaEventDestroy(s.beg);
+    cudaEventDestroy(s.end);
+  }
+  if (ctx->c.pinned) cudaFreeHost(ctx->c.pinned);
+  if (ctx->c.own_stream && ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+int flgp_ctx_set_stream(flgp_ctx* ctx, void* cuda_stream) {
+  return guard([&] {
+    need(ctx != nullptr, "null context");
+    FLGP_CUDA(cudaSetDevice(ctx->c.device));
+    if (ctx->c.own_stream && ctx->c.stream) {
+      FLGP_CUDA(cudaStreamSynchronize(ctx->c.stream));
+      cudaStreamDestroy(ctx->c.stream);
+    }
+    if (cuda_stream) {
+      ctx->c.stream = (cudaStream_t)cuda_stream;
+      ctx->c.own_stream = false;
+    } else {
+      FLGP_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+      ctx->c.own_stream = true;
+    }
+  });
+}
+
+int flgp_ctx_synchronize(flgp_ctx* ctx) {
+  return guard([&] {
+    need(ctx != nullptr, "null context");
+    sync(&ctx->c);
+  });
+}
+
+uint64_t flgp_ctx_launch_count(const flgp_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int flgp_ctx_set_timing(flgp_ctx* ctx, int on) {
+  if (!ctx) return 2;
+  ctx->c.timing = on != 0;
+  return 0;
+}
+int flgp_ctx_stage_reset(flgp_ctx* ctx) {
+  if (!ctx) return 2;
+  for (auto& s : ctx->c.stages) {
+    cudaEventDestroy(s.beg);
+    cudaEventDestroy(s.end);
+  }
+  ctx->c.stages.clear();
+  return 0;
+}
+int flgp_ctx_stage_count(flgp_ctx* ctx) { return ctx ? (int)ctx->c.stages.size() : 0; }
+int flgp_ctx_stage_get(flgp_ctx* ctx, int i, char* name, int name_len, double* ms, uint64_t* launches, double* flops,
+                       double* bytes) {
+  return guard([&] {
+    need(ctx && i >= 0 && i < (int)ctx->c.stages.size(), "stage index out of range");
+    StageRec& s = ctx->c.stages[i];
+    FLGP_CUDA(cudaEventSynchronize(s.end));
+    float t = 0.f;
+    FLGP_CUDA(cudaEventElapsedTime(&t, s.beg, s.end));
+    if (name && name_len > 0) {
+      std::strncpy(name, s.name.c_str(), name_len - 1);
+      name[name_len - 1] = 0;
+    }
+    if (ms) *ms = t;
+    if (launches) *launches = s.launches;
+    if (flops) *flops = s.flops;
+    if (bytes) *bytes = s.bytes;
+  });
+}
+
+int flgp_dfma_peak(flgp_ctx* ctx, int iters, double* tflops) {
+  return guard([&] {
+    need(ctx && tflops, "null argument");
+    *tflops = dfma_peak_run(&ctx->c, iters);
+  });
+}
+
+int flgp_comm_unique_id(void* out128) {
+  return guard([&] {
+    need(out128 != nullptr, "null output");
+    comm_unique_id(out128);
+  });
+}
+int flgp_ctx_comm_init(flgp_ctx* ctx, const void* id128, int rank, int nranks) {
+  return guard([&] {
+    need(ctx && (id128 || nranks == 1), "null argument");
+    comm_init(&ctx->c, id128, rank, nranks);
+  });
+}
+
+int flgp_default_init(int64_t n, int s, uint64_t seed, int32_t* init_idx) {
+  return guard([&] {
+    need(init_idx != nullptr, "null output");
+    auto v = default_init(n, s, seed);
+    std::memcpy(init_idx, v.data(), sizeof(int32_t) * s);
+  });
+}
+
+int flgp_subsample(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, const char* method, int iter_max,
+                   int nstart, const int32_t* init_idx, uint64_t seed, double* U, int32_t* assign, int* iters) {
+  return guard([&] {
+    need(ctx && X && U, "null argument");
+    need(n >= 1 && d >= 1, "bad matrix shape");
+    Ctx* c = &ctx->c;
+    need(c->nranks == 1, "flgp_subsample is single-process; use the sharded spectrum entry for multi-GPU");
+    DevBuf<double> dX((size_t)n * d);
+    dX.upload(X, (size_t)n * d, c->stream);
+    flgp_spectrum sp;
+    sp.c = c;
+    sp.n_local = sp.n_total = n;
+    sp.d = d;
+    sp.s = s;
+    Models mo = make_models(method, "lae", FLGP_GL_RW, 1, nstart, 0.1, iter_max);
+    DevBuf<int32_t> dassign((size_t)n);
+    stage_subsample(c, &sp, dX.p, mo, init_idx, seed, dassign.p);
+    sp.U.download(U, (size_t)s * sp.ucols, c->stream);
+    if (assign && mo.subsample == "kmeans") dassign.download(assign, n, c->stream);
+    sync(c);
+    if (iters) *iters = sp.kmeans_iters;
+  });
+}
+
+int flgp_knn(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int r, int32_t* ind,
+             double* dist, int32_t* Zj, double* Zx) {
+  return guard([&] {
+    need(ctx && X && U && ind, "null argument");
+    need(n >= 0 && d >= 1 && s >= 1, "bad matrix shape");
+    need((Zj == nullptr) == (Zx == nullptr), "Zj and Zx go together");
+    Ctx* c = &ctx->c;
+    const bool want_dist = dist || Zj;
+    DevBuf<double> dX((size_t)std::max<int64_t>(n * d, 1)), dU((size_t)s * d), ddist;
+    DevBuf<int32_t> dind((size_t)std::max<int64_t>(n * r, 1));
+    if (n) dX.upload(X, (size_t)n * d, c->stream);
+    dU.upload(U, (size_t)s * d, c->stream);
+    if (want_dist) ddist.alloc((size_t)std::max<int64_t>(n * r, 1));
+    knn_run(c, dX.p, n, n, d, dU.p, s, s, r, dind.p, want_dist ? ddist.p : nullptr);
+    if (n) {
+      dind.download(ind, (size_t)n * r, c->stream);
+      if (dist) ddist.download(dist, (size_t)n * r, c->stream);
+      if (Zj) {
+        DevBuf<int32_t> dZj((size_t)n * r);
+        DevBuf<double> dZx((size_t)n * r);
+        knn_to_csr_run(c, n, r, dind.p, ddist.p, dZj.p, dZx.p);
+        dZj.download(Zj, (size_t)n * r, c->stream);
+        dZx.download(Zx, (size_t)n * r, c->stream);
+        sync(c);
+      }
+    }
+    sync(c);
+  });
+}
+
+int flgp_simplex_project(flgp_ctx* ctx, const double* v, int r, double* z) {
+  return guard([&] {
+    need(ctx && v && z && r >= 1, "bad argument");
+    Ctx* c = &ctx->c;
+    DevBuf<double> dv(r), dz(r);
+    dv.upload(v, r, c->stream);
+    simplex_project_run(c, dv.p, r, dz.p);
+    dz.download(z, r, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_lae_point(flgp_ctx* ctx, const double* x, int d, const double* Ur, int r, double* z) {
+  return guard([&] {
+    need(ctx && x && Ur && z && d >= 1, "bad argument");
+    Ctx* c = &ctx->c;
+    DevBuf<double> dx(d), dU((size_t)r * d), dz(r);
+    dx.upload(x, d, c->stream);
+    dU.upload(Ur, (size_t)r * d, c->stream);
+    lae_point_run(c, dx.p, d, dU.p, r, dz.p);
+    dz.download(z, r, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_lae(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int r, int32_t* Zj, double* Zx,
+             int64_t* stats) {
+  return guard([&] {
+    need(ctx && X && U && Zj && Zx, "null argument");
+    need(n >= 1 && d >= 1 && s >= 1, "bad matrix shape");
+    Ctx* c = &ctx->c;
+    DevBuf<double> dX((size_t)n * d), dU((size_t)s * d), dZx((size_t)n * r);
+    DevBuf<int32_t> dind((size_t)n * r), dZj((size_t)n * r);
+    DevBuf<long long> dst(2);
+    dst.zero(c->stream);
+    dX.upload(X, (size_t)n * d, c->stream);
+    dU.upload(U, (size_t)s * d, c->stream);
+    knn_run(c, dX.p, n, n, d, dU.p, s, s, r, dind.p, nullptr);
+    lae_run(c, dX.p, n, n, d, dU.p, s, s, r, dind.p, dZj.p, dZx.p, nullptr, dst.p);
+    dZj.download(Zj, (size_t)n * r, c->stream);
+    dZx.download(Zx, (size_t)n * r, c->stream);
+    long long h[2] = {0, 0};
+    dst.download(h, 2, c->stream);
+    sync(c);
+    if (stats) {
+      stats[0] = h[0];
+      stats[1] = h[1];
+    }
+  });
+}
+
+int flgp_graph_laplacian(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int gl,
+                         const double* num_class) {
+  return guard([&] {
+    need(ctx && Zj && Zx, "null argument");
+    need(n >= 1 && s >= 1 && r >= 1, "bad shape");
+    parse_gl(gl);
+    need(gl != FLGP_GL_CLUSTER_NORMALIZED || num_class, "cluster-normalized needs the cluster sizes");
+    Ctx* c = &ctx->c;
+    DevBuf<int32_t> dZj((size_t)n * r);
+    DevBuf<double> dZx((size_t)n * r), dnc(s);
+    dZj.upload(Zj, (size_t)n * r, c->stream);
+    dZx.upload(Zx, (size_t)n * r, c->stream);
+    if (num_class) dnc.upload(num_class, s, c->stream);
+    stage_graph_laplacian(c, n, s, r, dZj.p, dZx.p, gl, dnc.p, n);
+    dZx.download(Zx, (size_t)n * r, c->stream);
+    sync(c);
+  });
+}
+
+static int cross_similarity(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int ucols, int r,
+                            int gl, const char* kernel, double epsilon, int32_t* Zj, double* Zx) {
+  return guard([&] {
+    need(ctx && X && U && Zj && Zx, "null argument");
+    need(n >= 1 && d >= 1 && s >= 1, "bad matrix shape");
+    need(ucols == d || ucols == d + 1, "U must have d or d+1 columns");
+    parse_gl(gl);
+    if (gl == FLGP_GL_CLUSTER_NORMALIZED && ucols != d + 1)
+      fail(2, "gl=\"cluster-normalized\" needs the cluster-size column of U (SURVEY Appendix A.1)");
+    Ctx* c = &ctx->c;
+    flgp_spectrum sp;
+    sp.c = c;
+    sp.n_local = sp.n_total = n;
+    sp.d = d;
+    sp.s = s;
+    sp.r = r;
+    DevBuf<double> dX((size_t)n * d), dU((size_t)s * ucols);
+    dX.upload(X, (size_t)n * d, c->stream);
+    dU.upload(U, (size_t)s * ucols, c->stream);
+    stage_cross_similarity(c, &sp, dX.p, dU.p, kernel, epsilon);
+    stage_graph_laplacian(c, n, s, r, sp.Zj.p, sp.Zx.p, gl, ucols == d + 1 ? dU.p + (size_t)s * d : nullptr, n);
+    sp.Zj.download(Zj, (size_t)n * r, c->stream);
+    sp.Zx.download(Zx, (size_t)n * r, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_cross_similarity_lae(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int ucols, int r,
+                              int gl, int32_t* Zj, double* Zx) {
+  return cross_similarity(ctx, X, n, d, U, s, ucols, r, gl, "lae", 0.1, Zj, Zx);
+}
+int flgp_cross_similarity_se(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int ucols, int r,
+                             int gl, double epsilon, int32_t* Zj, double* Zx) {
+  return cross_similarity(ctx, X, n, d, U, s, ucols, r, gl, "se", epsilon, Zj, Zx);
+}
+
+int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int K, int root,
+                         double* values, double* vectors, flgp_spectrum** handle) {
+  return guard([&] {
+    need(ctx && Zj && Zx, "null argument");
+    need(n >= 1 && s >= 1 && r >= 1 && r <= s, "bad shape");
+    Ctx* c = &ctx->c;
+    std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
+    sp->c = c;
+    sp->n_local = sp->n_total = n;
+    sp->s = s;
+    sp->r = r;
+    sp->Zj.alloc((size_t)n * r);
+    sp->Zx.alloc((size_t)n * r);
+    sp->Zj.upload(Zj, (size_t)n * r, c->stream);
+    sp->Zx.upload(Zx, (size_t)n * r, c->stream);
+    stage_spectrum(c, sp.get(), K, root != 0);
+    if (values) std::memcpy(values, sp->values.data(), sizeof(double) * sp->K);
+    if (vectors) {
+      DevBuf<double> V((size_t)n * sp->K);
+      lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, sp->K, nullptr, n, V.p, n, true);
+      V.download(vectors, (size_t)n * sp->K, c->stream);
+      sync(c);
+    }
+    if (handle) *handle = sp.release();
+  });
+}
+
+int flgp_heat_kernel_spectrum_dev(flgp_ctx* ctx, const double* X_local_dev, int64_t n_local, int64_t n_total,
+                                  int64_t row_offset, int d, int s, int r, int K, const char* subsample,
+                                  const char* kernel, int gl, int root, int nstart, double epsilon, int iter_max,
+                                  const int32_t* init_idx, uint64_t seed, flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && out && (X_local_dev || n_local == 0), "null argument");
+    Models mo = make_models(subsample, kernel, gl, root, nstart, epsilon, iter_max);
+    *out = spectrum_pipeline(&ctx->c, X_local_dev, n_local, n_total, row_offset, d, s, r, K, mo, init_idx, seed)
+               .release();
+  });
+}
+
+int flgp_heat_kernel_spectrum_sharded(flgp_ctx* ctx, const double* X_local, int64_t n_local, int64_t n_total,
+                                      int64_t row_offset, int d, int s, int r, int K, const char* subsample,
+                                      const char* kernel, int gl, int root, int nstart, double epsilon, int iter_max,
+                                      const int32_t* init_idx, uint64_t seed, flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && out && (X_local || n_local == 0), "null argument");
+    need(n_local >= 0 && d >= 1, "bad matrix shape");
+    Ctx* c = &ctx->c;
+    DevBuf<double> dX((size_t)std::max<int64_t>(n_local * d, 1));
+    if (n_local) dX.upload(X_local, (size_t)n_local * d, c->stream);
+    Models mo = make_models(subsample, kernel, gl, root, nstart, epsilon, iter_max);
+    *out = spectrum_pipeline(c, dX.p, n_local, n_total, row_offset, d, s, r, K, mo, init_idx, seed).release();
+  });
+}
+
+int flgp_heat_kernel_spectrum(flgp_ctx* ctx, const double* X, int64_t m, const double* X_new, int64_t m_new, int d,
+                              int s, int r, int K, const char* subsample, const char* kernel, int gl, int root,
+                              int nstart, double epsilon, int iter_max, const int32_t* init_idx, uint64_t seed,
+                              flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && out && X, "null argument");
+    need(m >= 1 && m_new >= 0 && d >= 1 && (X_new || m_new == 0), "bad matrix shape");
+    Ctx* c = &ctx->c;
+    need(c->nranks == 1, "use flgp_heat_kernel_spectrum_sharded for multi-GPU runs");
+    DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+    Models mo = make_models(subsample, kernel, gl, root, nstart, epsilon, iter_max);
+    *out = spectrum_pipeline(c, dX.p, m + m_new, m + m_new, 0, d, s, r, K, mo, init_idx, seed).release();
+  });
+}
+
+void flgp_spectrum_free(flgp_spectrum* h) { delete h; }
+
+int flgp_spectrum_info(const flgp_spectrum* h, int64_t* info10) {
+  if (!h || !info10) return 2;
+  int64_t v[10] = {h->n_local, h->n_total, h->row_offset, h->d, h->s, h->r, h->K, h->kmeans_iters, h->lae_iters,
+                   h->lae_bts};
+  std::memcpy(info10, v, sizeof v);
+  return 0;
+}
+
+int flgp_spectrum_values(const flgp_spectrum* h, double* values) {
+  if (!h || !values) return 2;
+  std::memcpy(values, h->values.data(), sizeof(double) * h->K);
+  return 0;
+}
+
+int flgp_spectrum_anchors(const flgp_spectrum* h, double* U) {
+  return guard([&] {
+    need(h && U && h->U.p, "no anchors in this handle");
+    h->U.download(U, (size_t)h->s * h->ucols, h->c->stream);
+    sync(h->c);
+  });
+}
+
+int flgp_spectrum_z(const flgp_spectrum* h, int32_t* Zj, double* Zx) {
+  return guard([&] {
+    need(h && Zj && Zx, "null argument");
+    h->Zj.download(Zj, (size_t)h->n_local * h->r, h->c->stream);
+    h->Zx.download(Zx, (size_t)h->n_local * h->r, h->c->stream);
+    sync(h->c);
+  });
+}
+
+int flgp_spectrum_vectors(flgp_spectrum* h, double* vectors) {
+  return guard([&] {
+    need(h && vectors, "null argument");
+    Ctx* c = h->c;
+    DevBuf<double> V((size_t)std::max<int64_t>(h->n_local * h->K, 1));
+    lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, h->K, nullptr, h->n_local, V.p, h->n_local, true);
+    if (h->n_local) V.download(vectors, (size_t)h->n_local * h->K, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_spectrum_gather_rows(flgp_spectrum* h, const int32_t* idx, int64_t n_idx, double* V) {
+  return guard([&] {
+    need(h && idx && V && n_idx >= 1, "bad argument");
+    for (int64_t a = 0; a < n_idx; ++a) need(idx[a] >= 0 && idx[a] < h->n_local, "row index out of range");
+    Ctx* c = h->c;
+    DevBuf<int32_t> di((size_t)n_idx);
+    DevBuf<double> dV((size_t)n_idx * h->K);
+    di.upload(idx, n_idx, c->stream);
+    lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, h->K, di.p, n_idx, dV.p, n_idx, true);
+    dV.download(V, (size_t)n_idx * h->K, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_hk_from_spectrum(flgp_spectrum* h, int K, double t, const int32_t* idx0, int64_t n0, const int32_t* idx1,
+                          int64_t n1, double* H) {
+  return guard([&] {
+    need(h && idx0 && idx1 && H && n0 >= 1 && n1 >= 1, "bad argument");
+    if (K < 0) K = h->K;
+    need(K >= 1 && K <= h->K, "K exceeds the number of computed eigenpairs");
+    for (int64_t a = 0; a < n0; ++a) need(idx0[a] >= 0 && idx0[a] < h->n_local, "row index out of range");
+    for (int64_t a = 0; a < n1; ++a) need(idx1[a] >= 0 && idx1[a] < h->n_local, "row index out of range");
+    Ctx* c = h->c;
+    const int KK = h->K;
+    StageScope st(c, "hk_from_spectrum", 2.0 * K * (double)n0 * n1, 8.0 * (double)n0 * n1);
+    DevBuf<int32_t> d0((size_t)n0), d1((size_t)n1);
+    DevBuf<double> V0((size_t)n0 * KK), V1((size_t)n1 * KK), dl(K), dH((size_t)n0 * n1);
+    d0.upload(idx0, n0, c->stream);
+    d1.upload(idx1, n1, c->stream);
+    std::vector<double> lam(K);
+    for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * (1.0 - h->values[k]));  // src/Spectrum.cpp:86,90
+    dl.upload(lam.data(), K, c->stream);
+    lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, KK, d0.p, n0, V0.p, KK, false);
+    lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, KK, d1.p, n1, V1.p, KK, false);
+    // rows are KK long but only the first K columns enter: strided operands with ld = KK
+    // gemm_nt_run assumes ld == K, so when K < KK compact through the general kernel below
+    if (K == KK) {
+      gemm_nt_run(c, V0.p, V1.p, dl.p, n0, n1, K, dH.p, n0);
+    } else {
+      DevBuf<double> A0((size_t)n0 * K), A1((size_t)n1 * K);
+      FLGP_CUDA(cudaMemcpy2DAsync(A0.p, K * sizeof(double), V0.p, KK * sizeof(double), K * sizeof(double), n0,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+      FLGP_CUDA(cudaMemcpy2DAsync(A1.p, K * sizeof(double), V1.p, KK * sizeof(double), K * sizeof(double), n1,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+      gemm_nt_run(c, A0.p, A1.p, dl.p, n0, n1, K, dH.p, n0);
+      sync(c);
+    }
+    dH.download(H, (size_t)n0 * n1, c->stream);
+    sync(c);
+  });
+}
+
+int flgp_lae_eigenmap(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, int r, int ndim, const char* subsample,
+                      int gl, int nstart, int iter_max, const int32_t* init_idx, uint64_t seed, double* eigenvalues,
+                      double* eigenvectors) {
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, n, nullptr, 0, d, s, r, ndim, subsample, "lae", gl, 1, nstart, 0.1, iter_max,
+                                     init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  if (eigenvalues)
+    for (int k = 0; k < h->K; ++k) eigenvalues[k] = 1.0 - h->values[k];  // src/Spectrum.cpp:23
+  if (eigenvectors) return flgp_spectrum_vectors(h, eigenvectors);
+  return 0;
+}
+
+int flgp_heat_kernel_covariance(flgp_ctx* ctx, const double* X, int64_t m, const double* X_new, int64_t m_new, int d,
+                                int s, int r, double t, int K, const char* subsample, const char* kernel, int gl,
+                                int root, int nstart, double epsilon, int iter_max, const int32_t* init_idx,
+                                uint64_t seed, double* H) {
+  if (K < 0) K = s;  // src/Spectrum.cpp:31-33
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, m, X_new, m_new, d, s, r, K, subsample, kernel, gl, root, nstart, epsilon,
+                                     iter_max, init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  const int64_t n = m + m_new;
+  std::vector<int32_t> idx0(n), idx1(m);
+  for (int64_t i = 0; i < n; ++i) idx0[i] = (int32_t)i;
+  for (int64_t i = 0; i < m; ++i) idx1[i] = (int32_t)i;
+  return flgp_hk_from_spectrum(h, K, t, idx0.data(), n, idx1.data(), m, H);
+}
+
+int flgp_regression_fixed_dev(flgp_spectrum* h, const double* Y_local_dev, int64_t m_total, int K, double t, double noise,
+                              double sigma, double* y_pred_dev, double* cov_dev) {
+  return guard([&] {
+    need(h && y_pred_dev, "null argument");
+    if (K < 0) K = h->K;
+    regression_fixed_dev(h, Y_local_dev, m_total, K, t, noise, sigma, y_pred_dev, cov_dev);
+  });
+}
+
+int flgp_regression_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t, double noise,
+                          double sigma, double* y_pred, double* cov) {
+  return guard([&] {
+    need(h && y_pred, "null argument");
+    if (K < 0) K = h->K;
+    Ctx* c = h->c;
+    const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
+    need(Y_local || m_local == 0, "labels missing");
+    DevBuf<double> dY((size_t)std::max<int64_t>(m_local, 1)), dy((size_t)std::max<int64_t>(h->n_local, 1)),
+        dc((size_t)std::max<int64_t>(h->n_local, 1));
+    if (m_local) dY.upload(Y_local, m_local, c->stream);
+    regression_fixed_dev(h, dY.p, m_total, K, t, noise, sigma, dy.p, cov ? dc.p : nullptr);
+    if (h->n_local) {
+      dy.download(y_pred, h->n_local, c->stream);
+      if (cov) dc.download(cov, h->n_local, c->stream);
+    }
+    sync(c);
+  });
+}
+
+int flgp_fit_lae_regression_fixed(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                  int64_t m_new, int d, int s, int r, int K, double sigma, double t, double noise,
+                                  const char* subsample, const char* kernel, int gl, int root, int nstart, int iter_max,
+                                  const int32_t* init_idx, uint64_t seed, double* train, double* test, double* cov) {
+  if (K < 0) K = s;  // src/Fit.cpp:37-39
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, m, X_new, m_new, d, s, r, K, subsample, kernel, gl, root, nstart, 0.1,
+                                     iter_max, init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  return guard([&] {
+    need(Y && train, "null argument");
+    const int64_t n = m + m_new;
+    std::vector<double> y(n), cv(n);
+    int rc2 = flgp_regression_fixed(h, Y, m, K, t, noise, sigma, y.data(), cv.data());
+    if (rc2) fail(rc2, "%s", g_err.c_str());
+    std::memcpy(train, y.data(), sizeof(double) * m);
+    if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
+    if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
+}  // extern "C"

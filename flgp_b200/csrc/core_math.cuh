@@ -1,0 +1,308 @@
+// core_math.cuh — per-thread arithmetic of the FLGP hot path, written once for device code.
+//
+// Everything here is `FLGP_HD` so that a test-only host shim (tests/hostcheck/) can compile the
+// very same source with g++ and compare it against the oracle on the CPU box before any GPU
+// time is spent.  The product only ever calls these from CUDA kernels.
+//
+// Arithmetic contract: fp64, round-to-nearest; multiplies and adds are NEVER
+// contracted (the library is compiled with -fmad=false); fused multiply-adds appear only where
+// `fma()` is written out (k-means scores, GEMMs, eigensolver).
+#pragma once
+#include <cmath>
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define FLGP_HD __host__ __device__ __forceinline__
+#else
+#define FLGP_HD inline
+#endif
+
+namespace flgp {
+
+// ---------------------------------------------------------------------------------------------
+// Two-limb fixed point: order-independent (hence shard- and schedule-independent) summation.
+// |x| < 2^E, at most `count` addends; L = ceil(log2 count), B = 62 - L bits per limb.
+//   x ~ hi*q1 + lo*q2,  q1 = 2^(E-B), q2 = 2^(E-2B);  sums of hi / lo never overflow int64.
+// ---------------------------------------------------------------------------------------------
+struct Fx {
+  double q1, q2, iq1, iq2;
+  int E, B;
+};
+
+inline int fx_make(double maxabs, int64_t count, Fx* fx) {  // host only
+  if (!std::isfinite(maxabs) || count < 1) return 1;
+  int E = (maxabs > 0.0) ? std::ilogb(maxabs) + 1 : 0;
+  if (E < -800) E = -800;
+  if (E > 800) return 1;
+  int L = 0;
+  while (((int64_t)1 << L) < count) ++L;
+  int B = 62 - L;
+  fx->E = E;
+  fx->B = B;
+  fx->q1 = std::ldexp(1.0, E - B);
+  fx->q2 = std::ldexp(1.0, E - 2 * B);
+  fx->iq1 = std::ldexp(1.0, B - E);
+  fx->iq2 = std::ldexp(1.0, 2 * B - E);
+  return 0;
+}
+
+FLGP_HD long long fx_trunc(double v) {
+#if defined(__CUDA_ARCH__)
+  return __double2ll_rz(v);
+#else
+  return (long long)v;
+#endif
+}
+FLGP_HD double fx_todouble(long long v) {
+#if defined(__CUDA_ARCH__)
+  return __ll2double_rn(v);
+#else
+  return (double)v;
+#endif
+}
+FLGP_HD void fx_encode(const Fx& fx, double x, long long* hi, long long* lo) {
+  long long h = fx_trunc(x * fx.iq1);
+  double rem = x - fx_todouble(h) * fx.q1;
+  *hi = h;
+  *lo = fx_trunc(rem * fx.iq2);
+}
+FLGP_HD double fx_decode(const Fx& fx, long long hi, long long lo) {
+  return fx_todouble(hi) * fx.q1 + fx_todouble(lo) * fx.q2;
+}
+
+// ---------------------------------------------------------------------------------------------
+// libstdc++ heap primitives on (key, id) pairs, comparator key[a] < key[b].  These follow the
+// ALGORITHM of std::partial_sort = __heap_select + __sort_heap (bits/stl_algo.h, stl_heap.h)
+// step for step, so that the selected set AND order agree with the reference's literal
+// std::partial_sort call (src/Utils.cpp:93) even on exact ties.
+// ---------------------------------------------------------------------------------------------
+FLGP_HD void heap_adjust(double* hk, int* hi, int hole, int len, double vk, int vi) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (hk[child] < hk[child - 1]) child--;
+    hk[hole] = hk[child];
+    hi[hole] = hi[child];
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    hk[hole] = hk[child - 1];
+    hi[hole] = hi[child - 1];
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && hk[parent] < vk) {
+    hk[hole] = hk[parent];
+    hi[hole] = hi[parent];
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  hk[hole] = vk;
+  hi[hole] = vi;
+}
+FLGP_HD void heap_make(double* hk, int* hi, int len) {
+  if (len < 2) return;
+  int parent = (len - 2) / 2;
+  while (true) {
+    double vk = hk[parent];
+    int vi = hi[parent];
+    heap_adjust(hk, hi, parent, len, vk, vi);
+    if (parent == 0) return;
+    parent--;
+  }
+}
+// element (k,i) of the tail [middle,last): replaces the heap top iff k < top key
+FLGP_HD void heap_select_step(double* hk, int* hi, int r, double k, int i) {
+  if (k < hk[0]) heap_adjust(hk, hi, 0, r, k, i);
+}
+FLGP_HD void heap_sort(double* hk, int* hi, int r) {
+  int last = r;
+  while (last > 1) {
+    --last;
+    double vk = hk[last];
+    int vi = hi[last];
+    hk[last] = hk[0];
+    hi[last] = hi[0];
+    heap_adjust(hk, hi, 0, last, vk, vi);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// v_to_z_cpp (src/lae.cpp:137-153): projection of v (length r) onto the simplex.
+// `vd` is scratch of length r.  Sequential cumulative sum, as std::partial_sum.
+// ---------------------------------------------------------------------------------------------
+template <int RT>
+FLGP_HD void simplex_project(const double* v, int r_in, double* z, double* vd) {
+  const int r = RT ? RT : r_in;
+#pragma unroll
+  for (int a = 0; a < r; ++a) vd[a] = v[a];
+  // insertion sort, descending (values only: the order of equal keys is irrelevant)
+#pragma unroll
+  for (int a = 1; a < r; ++a) {
+    double key = vd[a];
+    int b = a - 1;
+    while (b >= 0 && vd[b] < key) {
+      vd[b + 1] = vd[b];
+      --b;
+    }
+    vd[b + 1] = key;
+  }
+  double cs = 0.0, cs_rho = 0.0;
+  int rho = 0;
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+    cs = (a == 0) ? vd[0] : cs + vd[a];
+    double vstar = vd[a] - (cs - 1.0) / (double)(a + 1);
+    if (vstar > 0) {  // the reference scans from r down and stops at the LAST index with v* > 0
+      rho = a + 1;
+      cs_rho = cs;
+    }
+  }
+  double theta = (cs_rho - 1.0) / (double)rho;  // rho == 0 -> -inf, as the reference
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+    double t = v[a] - theta;
+    z[a] = (t > 0.0) ? t : 0.0;  // std::max(t, 0.0)
+  }
+}
+
+// exact 2^j as a double (inf for j >= 1024), replacing pow(2, j) at src/lae.cpp:110
+FLGP_HD double pow2i(int j) {
+  if (j >= 1024) return INFINITY;
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((1023 + j) << 20, 0);
+#else
+  return std::ldexp(1.0, j);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// local_anchor_embedding_cpp (src/lae.cpp:76-133).
+//   RT, DT : compile-time r, d (0 = run-time, arrays sized RMAX).
+//   UAcc   : functor (a,k) -> U(a,k), the r gathered anchors.
+//   x      : the point (length d), readable by index.
+// Operation order is the oracle's (oracle/flgp_oracle.cpp orc_lae_point): every dot product and
+// norm is a sequential left-to-right sum of separately rounded products.
+// ---------------------------------------------------------------------------------------------
+constexpr int LAE_RMAX = 16;
+constexpr int LAE_T = 100;
+constexpr int LAE_JCAP = 1100;
+
+template <int RT, int DT, class XAcc, class UAcc>
+FLGP_HD void lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out, int* iters, int* bts) {
+  constexpr int RA = RT ? RT : LAE_RMAX;
+  const int r = RT ? RT : r_in;
+  const int d = DT ? DT : d_in;
+  double UUt[RA * RA], xUt[RA], zp[RA], zc[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+#pragma unroll
+    for (int b = 0; b < r; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < d; ++k) s = s + U(a, k) * U(b, k);
+      UUt[a * RA + b] = s;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < d; ++k) s = s + x(k) * U(a, k);
+    xUt[a] = s;
+    zp[a] = 1.0 / (double)r;
+    zc[a] = 1.0 / (double)r;
+  }
+  auto objective = [&](const double* w) {
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+      double wu = 0.0;
+#pragma unroll
+      for (int a = 0; a < r; ++a) wu = wu + w[a] * U(a, k);
+      double df = x(k) - wu;
+      sq = sq + df * df;
+    }
+    return sq / 2.0;
+  };
+  double delta_prev = 0.0, delta_curr = 1.0, beta_curr = 1.0;
+  int t = 0, nbt = 0;
+  for (t = 0; t < LAE_T; ++t) {
+    const double alpha = (delta_prev - 1.0) / delta_curr;
+#pragma unroll
+    for (int a = 0; a < r; ++a) v[a] = zc[a] + alpha * (zc[a] - zp[a]);
+    const double g_v = objective(v);
+#pragma unroll
+    for (int b = 0; b < r; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int a = 0; a < r; ++a) s = s + v[a] * UUt[a * RA + b];
+      g[b] = s - xUt[b];
+    }
+    int j = 0;
+    while (true) {
+      const double beta = pow2i(j) * beta_curr;
+      const double ib = 1.0 / beta;
+#pragma unroll
+      for (int a = 0; a < r; ++a) vt[a] = v[a] - ib * g[a];
+      simplex_project<RT>(vt, r, z, scratch);
+      const double g_z = objective(z);
+      double dot = 0.0, sq = 0.0;
+#pragma unroll
+      for (int a = 0; a < r; ++a) {
+        double dz = z[a] - v[a];
+        dot = dot + g[a] * dz;
+        sq = sq + dz * dz;
+      }
+      const double g_tilde = g_v + dot + beta * sq / 2.0;
+      if (g_z <= g_tilde || j >= LAE_JCAP) {
+        beta_curr = beta;
+#pragma unroll
+        for (int a = 0; a < r; ++a) {
+          zp[a] = zc[a];
+          zc[a] = z[a];
+        }
+        break;
+      }
+      ++j;
+      ++nbt;
+    }
+    delta_prev = delta_curr;
+    delta_curr = (1.0 + sqrt(1.0 + 4.0 * delta_curr * delta_curr)) / 2.0;
+    double sq = 0.0;
+#pragma unroll
+    for (int a = 0; a < r; ++a) {
+      double dz = zc[a] - zp[a];
+      sq = sq + dz * dz;
+    }
+    if (sq < 1e-5) {
+      ++t;
+      break;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < r; ++a) z_out[a] = zc[a];
+  if (iters) *iters = t;
+  if (bts) *bts = nbt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Symmetric tridiagonal helpers (eigensolver).  d[0..n), e[0..n-1) sub-diagonal, e2 = e*e.
+// ---------------------------------------------------------------------------------------------
+// number of eigenvalues strictly below x (Sturm count, LAPACK dlaebz/dstebz recurrence)
+FLGP_HD int sturm_count(const double* d, const double* e2, int n, double x, double pivmin) {
+  int cnt = 0;
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  if (q < 0.0) ++cnt;
+  for (int i = 1; i < n; ++i) {
+    q = d[i] - x - e2[i - 1] / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    if (q < 0.0) ++cnt;
+  }
+  return cnt;
+}
+
+}  // namespace flgp

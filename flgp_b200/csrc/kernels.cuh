@@ -1,0 +1,71 @@
+// kernels.cuh — host-callable stage launchers.  All pointers are DEVICE pointers unless named *_h.
+// Matrices are column-major with explicit leading dimensions; CSR has exactly r entries per row.
+#pragma once
+#include "common.cuh"
+
+namespace flgp {
+
+// ---- kmeans.cu -------------------------------------------------------------------------------
+// Lloyd iterations on this rank's rows; centroid sums are all-reduced (int64 limbs).
+// U: s x (d+1) column-major (centres, sizes).  assign: n_local (scratch/out).
+void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, int s, int64_t n_total,
+                int64_t row_offset, const int32_t* init_idx_h, int iter_max, double* U, int32_t* assign,
+                int* iters_out);
+double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);  // all-reduced, host value
+
+// ---- knn.cu ----------------------------------------------------------------------------------
+// ind: n x r (ld n), ascending distance, libstdc++ partial_sort tie behaviour.  dist: optional.
+void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
+             int r, int32_t* ind, double* dist);
+
+// ---- lae.cu ----------------------------------------------------------------------------------
+// Zj/Zx: n*r CSR (row i at i*r), rows sorted by column.  Wd: optional dense n x r weights (ld n)
+// in KNN order.  stats: optional 2 x int64 on device (iterations, back-tracks), accumulated.
+void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
+             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats);
+void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx);
+void se_weights_run(Ctx* c, const double* dist, int64_t len, double denom, double* out);
+// one point / one vector, for the exported helpers
+void lae_point_run(Ctx* c, const double* x, int d, const double* Ur, int r, double* z);
+void simplex_project_run(Ctx* c, const double* v, int r, double* z);
+
+// ---- sparse.cu -------------------------------------------------------------------------------
+void colsum_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int64_t n_total,
+                double* colsum);  // fixed-point, all-reduced
+void gl_apply_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int mode,
+                  const double* colsum, const double* num_class);
+void spectrum_scale_run(Ctx* c, int s, const double* colsum, double* w);
+void gram_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, const double* w,
+              int64_t n_total, double* G);  // s x s, fixed-point, all-reduced, symmetric
+// rows of the lifted eigenvectors: out(a, k) = sum_p Z(i_a, c_p) w(c_p) Wm(c_p, k),  i_a = idx ? idx[a] : a
+// Wm: s x K row-major.  out: n_rows x K, column-major (ld = ldo) if colmajor else row-major (ld = K).
+void lift_rows_run(Ctx* c, int r, const int32_t* Zj, const double* Zx, const double* w, const double* Wm,
+                   int K, const int32_t* idx, int64_t n_rows, double* out, int64_t ldo, bool colmajor);
+// y_i = sum_p a_ip v(c_p)   (folded prediction)
+void sparse_rowdot_run(Ctx* c, int64_t n, int r, const int32_t* Zj, const double* Zx, const double* w,
+                       const double* v, double* y);
+// q_i = add + sum_{p,q} a_ip a_iq B(c_p, c_q)   (folded posterior variance), B: s x s
+void sparse_quadform_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx,
+                         const double* w, const double* B, double add, double* q);
+
+// ---- gemm.cu ---------------------------------------------------------------------------------
+// C(M x N, col-major ldc) = sum_k A(i,k) * sc[k] * B(j,k);  A: M x K and B: N x K, both ROW-major (ld K).
+// sc may be null.  fp64 FMA accumulation in ascending k.
+void gemm_nt_run(Ctx* c, const double* A, const double* B, const double* sc, int64_t M, int64_t N, int K,
+                 double* C, int64_t ldc);
+// C(M x N row-major) = A(M x K row-major) * B(K x N row-major)
+void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C);
+// small: y(M) = A(M x K row-major) x(K)
+void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double* y);
+// G(K x K, col-major) = V^T V and g = V^T y over n_rows rows of V (row-major n_rows x K); deterministic
+void gram_small_run(Ctx* c, const double* V, const double* y, int64_t n_rows, int K, double* G, double* g);
+
+// ---- eigh.cu ---------------------------------------------------------------------------------
+// Top-K eigenpairs (descending) of the symmetric s x s matrix G (full storage; destroyed).
+// lam: K.  Y: s x K column-major, orthonormal columns.
+void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y);
+
+// ---- misc ------------------------------------------------------------------------------------
+double dfma_peak_run(Ctx* c, int iters);  // measured fp64 FMA TFLOP/s (roofline denominator)
+
+}  // namespace flgp

@@ -1,0 +1,209 @@
+// lae.cu — Local Anchor Embedding weights and the fixed-r CSR cross-similarity matrix
+// (replaces LAE_cpp / local_anchor_embedding_cpp / v_to_z_cpp, /root/reference/src/lae.cpp:15-153,
+//  and the sparse output of KNN_cpp, src/Utils.cpp:145-189).
+//
+// One thread owns one point: gathers its r anchors into registers, runs the Nesterov projected
+// gradient with doubling back-tracking in the oracle's exact operation order (core_math.cuh
+// lae_solve; no FMA contraction, sequential reductions), sorts its r (column, weight) pairs and
+// writes its CSR row.  p[i] = i*r is implicit; explicit zeros are kept (src/lae.cpp:61-67).
+//
+// Roofline: HBM (8d + 4r bytes read, 12r written per point); the solver itself is latency /
+// divergence bound (data-dependent 1..100 outer iterations) and is reported with its iteration
+// count, as SURVEY.md §8d asks.
+#include "kernels.cuh"
+
+namespace flgp {
+
+namespace {
+
+template <int R, int D>
+struct RegU {
+  double u[R][D];
+  __device__ __forceinline__ double operator()(int a, int k) const { return u[a][k]; }
+};
+template <int D>
+struct RegX {
+  double x[D];
+  __device__ __forceinline__ double operator()(int k) const { return x[k]; }
+};
+struct GlobU {  // anchors read in place (large d): U(c_a, k)
+  const double* U;
+  int64_t ldu;
+  int c[LAE_RMAX];
+  __device__ __forceinline__ double operator()(int a, int k) const { return U[c[a] + ldu * k]; }
+};
+struct GlobX {
+  const double* X;
+  int64_t ldx;
+  __device__ __forceinline__ double operator()(int k) const { return X[ldx * k]; }
+};
+
+template <int RMAXT>
+__device__ __forceinline__ void write_row(int r, const int* col, const double* z, int64_t i, int64_t n,
+                                          int32_t* Zj, double* Zx, double* Wd) {
+  int cj[RMAXT];
+  double cz[RMAXT];
+#pragma unroll
+  for (int a = 0; a < RMAXT; ++a)
+    if (a < r) {
+      cj[a] = col[a];
+      cz[a] = z[a];
+      if (Wd) Wd[i + n * a] = z[a];
+    }
+  // insertion sort by column (columns are distinct)
+#pragma unroll
+  for (int a = 1; a < RMAXT; ++a)
+    if (a < r) {
+      int kj = cj[a];
+      double kz = cz[a];
+      int b = a - 1;
+      while (b >= 0 && cj[b] > kj) {
+        cj[b + 1] = cj[b];
+        cz[b + 1] = cz[b];
+        --b;
+      }
+      cj[b + 1] = kj;
+      cz[b + 1] = kz;
+    }
+#pragma unroll
+  for (int a = 0; a < RMAXT; ++a)
+    if (a < r) {
+      Zj[i * r + a] = cj[a];
+      Zx[i * r + a] = cz[a];
+    }
+}
+
+__device__ __forceinline__ void add_stats(long long* stats, int it, int bt) {
+  if (!stats) return;
+  for (int o = 16; o; o >>= 1) {
+    it += __shfl_xor_sync(0xffffffffu, it, o);
+    bt += __shfl_xor_sync(0xffffffffu, bt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats), (unsigned long long)it);
+    atomicAdd(reinterpret_cast<unsigned long long*>(stats) + 1, (unsigned long long)bt);
+  }
+}
+
+template <int R, int D>
+__global__ void __launch_bounds__(128)
+lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ U, int64_t ldu,
+                 const int32_t* __restrict__ ind, int32_t* __restrict__ Zj, double* __restrict__ Zx,
+                 double* __restrict__ Wd, long long* stats) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int it = 0, bt = 0;
+  if (i < n) {
+    RegX<D> x;
+    RegU<R, D> Ur;
+    int col[R];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x.x[k] = X[i + ldx * k];
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      col[a] = ind[i + n * a];
+#pragma unroll
+      for (int k = 0; k < D; ++k) Ur.u[a][k] = U[col[a] + ldu * k];
+    }
+    double z[R];
+    lae_solve<R, D>(R, D, x, Ur, z, &it, &bt);
+    write_row<R>(R, col, z, i, n, Zj, Zx, Wd);
+  }
+  add_stats(stats, it, bt);
+}
+
+__global__ void __launch_bounds__(128)
+lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ U,
+                   int64_t ldu, int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj,
+                   double* __restrict__ Zx, double* __restrict__ Wd, long long* stats) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int it = 0, bt = 0;
+  if (i < n) {
+    GlobX x{X + i, ldx};
+    GlobU Ur;
+    Ur.U = U;
+    Ur.ldu = ldu;
+    for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
+    double z[LAE_RMAX];
+    lae_solve<0, 0>(r, d, x, Ur, z, &it, &bt);
+    write_row<LAE_RMAX>(r, Ur.c, z, i, n, Zj, Zx, Wd);
+  }
+  add_stats(stats, it, bt);
+}
+
+__global__ void knn_to_csr_kernel(int64_t n, int r, const int32_t* __restrict__ ind, const double* __restrict__ dist,
+                                  int32_t* __restrict__ Zj, double* __restrict__ Zx) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int col[32];
+  double v[32];
+  for (int a = 0; a < r; ++a) {
+    col[a] = ind[i + n * a];
+    v[a] = dist[i + n * a];
+  }
+  write_row<32>(r, col, v, i, n, Zj, Zx, nullptr);
+}
+
+__global__ void se_weights_kernel(const double* __restrict__ dist, int64_t len, double denom, double* out) {
+  int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e < len) out[e] = exp(-dist[e] / denom);
+}
+
+__global__ void lae_point_kernel(const double* x, int d, const double* Ur, int r, double* z) {
+  if (threadIdx.x || blockIdx.x) return;
+  GlobX xa{x, 1};
+  GlobU ua;
+  ua.U = Ur;  // r x d column-major, ld r
+  ua.ldu = r;
+  for (int a = 0; a < r; ++a) ua.c[a] = a;
+  double zz[LAE_RMAX];
+  lae_solve<0, 0>(r, d, xa, ua, zz, nullptr, nullptr);
+  for (int a = 0; a < r; ++a) z[a] = zz[a];
+}
+
+__global__ void simplex_project_kernel(const double* v, int r, double* z, double* scratch) {
+  if (threadIdx.x || blockIdx.x) return;
+  simplex_project<0>(v, r, z, scratch);
+}
+
+}  // namespace
+
+void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
+             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats) {
+  (void)s;
+  if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
+  if (n <= 0) return;
+  const int grid = ceil_div(n, 128);
+#define LAE_CASE(R_, D_)                                                                                  \
+  if (r == R_ && d == D_) {                                                                               \
+    FLGP_LAUNCH(c, (lae_small_kernel<R_, D_>), grid, 128, 0, X, n, ldx, U, ldu, ind, Zj, Zx, Wd, stats);  \
+    return;                                                                                               \
+  }
+  LAE_CASE(2, 2) LAE_CASE(3, 2) LAE_CASE(4, 2) LAE_CASE(5, 2)
+  LAE_CASE(2, 3) LAE_CASE(3, 3) LAE_CASE(4, 3) LAE_CASE(5, 3)
+#undef LAE_CASE
+  FLGP_LAUNCH(c, lae_generic_kernel, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats);
+}
+
+void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx) {
+  if (r < 1 || r > 32) fail(2, "r=%d outside 1..32", r);
+  if (n <= 0) return;
+  FLGP_LAUNCH(c, knn_to_csr_kernel, ceil_div(n, 128), 128, 0, n, r, ind, dist, Zj, Zx);
+}
+
+void se_weights_run(Ctx* c, const double* dist, int64_t len, double denom, double* out) {
+  if (len <= 0) return;
+  FLGP_LAUNCH(c, se_weights_kernel, ceil_div(len, 256), 256, 0, dist, len, denom, out);
+}
+
+void lae_point_run(Ctx* c, const double* x, int d, const double* Ur, int r, double* z) {
+  if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
+  FLGP_LAUNCH(c, lae_point_kernel, 1, 32, 0, x, d, Ur, r, z);
+}
+
+void simplex_project_run(Ctx* c, const double* v, int r, double* z) {
+  DevBuf<double> scratch(r);
+  FLGP_LAUNCH(c, simplex_project_kernel, 1, 32, 0, v, r, z, scratch.p);
+  sync(c);
+}
+
+}  // namespace flgp

@@ -1,0 +1,165 @@
+/* flgp.h — C ABI of libflgp_b200.so: the B200-native spectral core of FLGP.
+ *
+ * Drop-in boundary for the path BASELINE.json:north_star names.  Each entry point replaces one seam
+ * of the reference (citations relative to the reference repository junhuihe2000/FLGP):
+ * an Rcpp export registered in src/RcppExports.cpp:471-504, or an internal C++ seam the fit drivers
+ * call (src/Spectrum.h:53-114, src/Utils.h:39-41).  INTEGRATION.md shows the Rcpp shim that binds them.
+ *
+ * Conventions (same as the R/Eigen side):
+ *   - HOST pointers in and out unless the name ends in _dev; the caller owns every buffer.
+ *   - matrices are COLUMN-MAJOR fp64 (R's layout); indices are int32 and 0-BASED
+ *     (the reference returns 0-based indices to R as well, src/Utils.cpp:144).
+ *   - sparse matrices are CSR with exactly r entries per row, rows sorted by column
+ *     (dgRMatrix slots j, x; p[i] = i*r is implicit), explicit zeros kept (src/lae.cpp:61-67).
+ *   - every function returns 0 on success; otherwise flgp_last_error() holds the message that the
+ *     R shim passes to Rcpp::stop.  2 = invalid argument, 3 = CUDA error, 4 = NCCL error.
+ *   - there is NO CPU fallback: without a CUDA device flgp_ctx_create fails.
+ *   - k-means: the reference calls R's stats::kmeans (Hartigan-Wong, R RNG).  This library runs
+ *     Lloyd's algorithm from explicit initial row indices `init_idx` (s distinct rows of X), or, when
+ *     init_idx is NULL, from flgp_default_init(n, s, seed); at most `iter_max` (reference: 100)
+ *     iterations; stops when no assignment changes.  See DESIGN.md §2.
+ */
+#ifndef FLGP_H
+#define FLGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct flgp_ctx flgp_ctx;            /* device, stream, communicator; one per process/GPU */
+typedef struct flgp_spectrum flgp_spectrum;  /* device-resident EigenPair (src/Spectrum.h:117-124) */
+
+/* graph-Laplacian types of graphLaplacian_cpp (src/Utils.cpp:198-208) */
+enum { FLGP_GL_RW = 0, FLGP_GL_NORMALIZED = 1, FLGP_GL_CLUSTER_NORMALIZED = 2 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int flgp_version(void);
+const char* flgp_last_error(void);
+int flgp_ctx_create(int device, flgp_ctx** out);
+void flgp_ctx_destroy(flgp_ctx* ctx);
+/* run on the caller's CUDA stream (cudaStream_t as void*); NULL restores the library's own stream */
+int flgp_ctx_set_stream(flgp_ctx* ctx, void* cuda_stream);
+int flgp_ctx_synchronize(flgp_ctx* ctx);
+/* kernels launched by this context so far */
+uint64_t flgp_ctx_launch_count(const flgp_ctx* ctx);
+/* per-stage CUDA-event timing on the library's stream */
+int flgp_ctx_set_timing(flgp_ctx* ctx, int on);
+int flgp_ctx_stage_reset(flgp_ctx* ctx);
+int flgp_ctx_stage_count(flgp_ctx* ctx);
+int flgp_ctx_stage_get(flgp_ctx* ctx, int i, char* name, int name_len, double* ms, uint64_t* launches,
+                       double* flops, double* bytes);
+/* measured fp64 FMA throughput of this GPU in TFLOP/s (the FP64 roofline denominator) */
+int flgp_dfma_peak(flgp_ctx* ctx, int iters, double* tflops);
+
+/* ---- multi-GPU: one process per GPU, rows of X_all sharded in contiguous blocks -------------- */
+/* rank 0 calls flgp_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed);
+ * every rank then calls flgp_ctx_comm_init.  Collectives used: int64 all-reduce of fixed-point limbs
+ * (k-means sums, column sums, Gram) and fp64 all-reduce of K x K blocks. */
+int flgp_comm_unique_id(void* out128);
+int flgp_ctx_comm_init(flgp_ctx* ctx, const void* id128, int rank, int nranks);
+
+/* ---- stage entry points (one per Rcpp export / C++ seam) ------------------------------------ */
+/* deterministic default initial rows for k-means: s distinct sorted indices in [0, n) */
+int flgp_default_init(int64_t n, int s, uint64_t seed, int32_t* init_idx);
+
+/* subsample_cpp (src/Utils.cpp:32-68).  method "kmeans": U is s x (d+1) = [centres, cluster sizes];
+ * "random": U is s x d = X[init_idx,] (no size column, as the reference).  assign (n, optional) and
+ * iters (optional) report the final assignment and the Lloyd iterations run. */
+int flgp_subsample(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, const char* method, int iter_max,
+                   int nstart, const int32_t* init_idx, uint64_t seed, double* U, int32_t* assign, int* iters);
+
+/* KNN_cpp (src/Utils.cpp:102-192), distance "Euclidean".  ind: n x r, ascending distance, ties as
+ * libstdc++ std::partial_sort.  dist (optional): n x r squared distances in the same order.
+ * Zj/Zx (optional, both or neither): distances_sp as CSR. */
+int flgp_knn(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int r, int32_t* ind,
+             double* dist, int32_t* Zj, double* Zx);
+
+/* v_to_z_cpp (src/lae.cpp:137-153) */
+int flgp_simplex_project(flgp_ctx* ctx, const double* v, int r, double* z);
+/* local_anchor_embedding_cpp (src/lae.cpp:76-133); Ur is r x d */
+int flgp_lae_point(flgp_ctx* ctx, const double* x, int d, const double* Ur, int r, double* z);
+/* LAE_cpp (src/lae.cpp:48-70); U is s x d.  stats (optional, 2): solver iterations, back-tracks */
+int flgp_lae(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int r, int32_t* Zj,
+             double* Zx, int64_t* stats);
+/* graphLaplacian_cpp (src/Utils.cpp:195-212), in place on Zx; num_class (s) only for cluster-normalized */
+int flgp_graph_laplacian(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int gl,
+                         const double* num_class);
+/* cross_similarity_lae_cpp / cross_similarity_se_cpp (src/Spectrum.cpp:101-142); U is s x ucols,
+ * ucols = d or d+1 (cluster sizes in the last column; required for cluster-normalized) */
+int flgp_cross_similarity_lae(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int ucols,
+                              int r, int gl, int32_t* Zj, double* Zx);
+int flgp_cross_similarity_se(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, int s, int ucols,
+                             int r, int gl, double epsilon, int32_t* Zj, double* Zx);
+/* spectrum_from_Z_cpp + truncated_SVD_cpp (src/Spectrum.cpp:146-161, src/TruncatedSVD.cpp:9-34).
+ * K < 0 means K = s.  values (K): sigma (root) or sigma^2, descending.  vectors (optional): n x K
+ * = sqrt(n) U.  handle (optional) keeps the result on the device. */
+int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int K,
+                         int root, double* values, double* vectors, flgp_spectrum** handle);
+
+/* heat_kernel_spectrum_cpp (src/Spectrum.cpp:48-76): X (m x d) and X_new (m_new x d, may be NULL with
+ * m_new = 0) are concatenated, training rows first.  models = {subsample, kernel, gl, root}. */
+int flgp_heat_kernel_spectrum(flgp_ctx* ctx, const double* X, int64_t m, const double* X_new, int64_t m_new, int d,
+                              int s, int r, int K, const char* subsample, const char* kernel, int gl, int root,
+                              int nstart, double epsilon, int iter_max, const int32_t* init_idx, uint64_t seed,
+                              flgp_spectrum** out);
+/* the same on one shard of X_all (rows [row_offset, row_offset + n_local) of n_total), for multi-GPU runs;
+ * X_local is n_local x d with leading dimension n_local. */
+int flgp_heat_kernel_spectrum_sharded(flgp_ctx* ctx, const double* X_local, int64_t n_local, int64_t n_total,
+                                      int64_t row_offset, int d, int s, int r, int K, const char* subsample,
+                                      const char* kernel, int gl, int root, int nstart, double epsilon,
+                                      int iter_max, const int32_t* init_idx, uint64_t seed, flgp_spectrum** out);
+/* the same with X_local already in device memory (column-major, ld = n_local) */
+int flgp_heat_kernel_spectrum_dev(flgp_ctx* ctx, const double* X_local_dev, int64_t n_local, int64_t n_total,
+                                  int64_t row_offset, int d, int s, int r, int K, const char* subsample,
+                                  const char* kernel, int gl, int root, int nstart, double epsilon, int iter_max,
+                                  const int32_t* init_idx, uint64_t seed, flgp_spectrum** out);
+
+/* ---- EigenPair handle ------------------------------------------------------------------------ */
+void flgp_spectrum_free(flgp_spectrum* h);
+/* info[0..7] = n_local, n_total, row_offset, d, s, r, K, kmeans iterations; info[8..9] = LAE iterations, back-tracks */
+int flgp_spectrum_info(const flgp_spectrum* h, int64_t* info10);
+int flgp_spectrum_values(const flgp_spectrum* h, double* values);  /* K */
+int flgp_spectrum_anchors(const flgp_spectrum* h, double* U);      /* s x (d+1), or s x d for "random" */
+int flgp_spectrum_z(const flgp_spectrum* h, int32_t* Zj, double* Zx); /* local rows */
+int flgp_spectrum_vectors(flgp_spectrum* h, double* vectors);      /* n_local x K */
+/* mat_indexing(eigenvectors, idx, 0..K-1) (src/Utils.h:130-137); idx are LOCAL row numbers */
+int flgp_spectrum_gather_rows(flgp_spectrum* h, const int32_t* idx, int64_t n_idx, double* V);
+/* HK_from_spectrum_cpp (src/Spectrum.cpp:83-94): H (n0 x n1) = V[idx0,:K] diag(exp(-t(1-values))) V[idx1,:K]^T */
+int flgp_hk_from_spectrum(flgp_spectrum* h, int K, double t, const int32_t* idx0, int64_t n0, const int32_t* idx1,
+                          int64_t n1, double* H);
+
+/* lae_eigenmap (src/Spectrum.cpp:17-25): eigenvalues (ndim) = 1 - sigma, eigenvectors n x ndim */
+int flgp_lae_eigenmap(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, int r, int ndim, const char* subsample,
+                      int gl, int nstart, int iter_max, const int32_t* init_idx, uint64_t seed, double* eigenvalues,
+                      double* eigenvectors);
+/* heat_kernel_covariance_cpp (src/Spectrum.cpp:28-43): H is (m + m_new) x m */
+int flgp_heat_kernel_covariance(flgp_ctx* ctx, const double* X, int64_t m, const double* X_new, int64_t m_new, int d,
+                                int s, int r, double t, int K, const char* subsample, const char* kernel, int gl,
+                                int root, int nstart, double epsilon, int iter_max, const int32_t* init_idx,
+                                uint64_t seed, double* H);
+
+/* ---- GPR tail at FIXED hyper-parameters --------------------------------- */
+/* predict_regression_cpp, noise = "same" (src/Predict.cpp:40-75) + posterior_covariance_regression
+ * (src/Utils.cpp:215-249) as called by fit_lae_regression_gp_cpp (src/Fit.cpp:64-77), with
+ * pars = (t, noise) supplied instead of optimised.  The first m_total rows of X_all are the training
+ * rows; Y_local holds the labels of the training rows THIS rank owns.  Outputs are per local row:
+ * y_pred (n_local): posterior mean at every local row (training rows first), cov (n_local): posterior
+ * variance (meaningful for the test rows, as the reference evaluates it there). */
+int flgp_regression_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t, double noise,
+                          double sigma, double* y_pred, double* cov);
+int flgp_regression_fixed_dev(flgp_spectrum* h, const double* Y_local_dev, int64_t m_total, int K, double t,
+                              double noise, double sigma, double* y_pred_dev, double* cov_dev);
+/* fit_lae_regression_gp_cpp (src/Fit.cpp:20-99) with fixed pars, single process: Y_train (m),
+ * outputs train (m), test (m_new), cov (m_new). */
+int flgp_fit_lae_regression_fixed(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                  int64_t m_new, int d, int s, int r, int K, double sigma, double t, double noise,
+                                  const char* subsample, const char* kernel, int gl, int root, int nstart,
+                                  int iter_max, const int32_t* init_idx, uint64_t seed, double* train, double* test,
+                                  double* cov);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLGP_H */

@@ -1,0 +1,57 @@
+"""The drop-in boundary: libflgp_b200.so loads here (no GPU) and exports every symbol include/flgp.h declares;
+without a device it fails loudly instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "flgp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(flgp_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(flgp):
+    lib = flgp._lib.load()
+    syms = _header_symbols()
+    assert len(syms) >= 35
+    for s in syms:
+        assert hasattr(lib, s), "missing export: " + s
+    # and the ctypes mirror declares a signature for each of them
+    assert set(flgp._lib.SIGNATURES) == set(syms)
+
+
+def test_no_silent_fallback_without_gpu(flgp):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(flgp.FlgpError, match="no CPU fallback"):
+        flgp.Context(0)
+
+
+def test_default_init_is_deterministic_sorted_distinct(flgp):
+    a = flgp.default_init(100000, 500, seed=7)
+    b = flgp.default_init(100000, 500, seed=7)
+    c = flgp.default_init(100000, 500, seed=8)
+    assert (a == b).all() and (a != c).any()
+    assert (a[1:] > a[:-1]).all() and a.min() >= 0 and a.max() < 100000
+    with pytest.raises(flgp.FlgpError):
+        flgp.default_init(10, 11)
+
+
+def test_product_never_imports_the_oracle():
+    """The product package and the C sources must not reference oracle/ (③: oracle is test infrastructure)."""
+    bad = []
+    for base, _, files in os.walk(os.path.join(ROOT, "flgp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                t = open(os.path.join(base, f), errors="replace").read()
+                if re.search(r"^\s*(import|from)\s+oracle|#include\s*[<\"][^>\"]*oracle|libflgp_oracle|dlopen\([^)]*oracle",
+                             t, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad

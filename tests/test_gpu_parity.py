@@ -1,0 +1,310 @@
+"""GPU parity tests proper: every stage through the C ABI (ctypes mirror of the Rcpp exports) against the
+oracle on the same seeded inputs.  Bit-exact: k-means assignments/centres, KNN indices+distances, LAE weights,
+Z pattern and values, Gram-side sums.  1e-8 relative (fp64): eigenvalues, heat kernel, predictions."""
+import numpy as np
+import pytest
+
+from conftest import spiral, swiss
+
+pytestmark = pytest.mark.gpu
+
+NT = 8  # oracle threads
+
+
+def _init(n, s, seed=0):
+    return np.sort(np.random.default_rng(seed).choice(n, s, replace=False)).astype(np.int32)
+
+
+def _csr_parts(Z):
+    n = Z.shape[0]
+    r = Z.indptr[1] - Z.indptr[0]
+    return Z.indices.reshape(n, r), Z.data.reshape(n, r)
+
+
+# ------------------------------------------------------------------------------------------- k-means
+@pytest.mark.parametrize("n,d,s", [(4000, 2, 500), (20000, 3, 200), (1500, 1, 20), (3000, 4, 64),
+                                    (3000, 5, 70), (2500, 16, 100), (700, 37, 33)])
+def test_kmeans_bitexact(flgp, oracle, n, d, s):
+    rng = np.random.default_rng(n + d)
+    if d == 2:
+        X, _ = spiral(n, 1)
+    elif d == 3:
+        X, _ = swiss(n, 1)
+    else:
+        X = np.asfortranarray(rng.standard_normal((n, d)) + 3 * rng.integers(0, 4, (n, 1)))
+    init = _init(n, s, 2)
+    U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, return_info=True)
+    Uo, ao, io = oracle.kmeans_lloyd(X, s, init, 100, NT)
+    assert iters == io
+    assert np.array_equal(assign, ao)
+    assert np.array_equal(U, Uo)  # centres AND sizes, bit for bit
+    assert U[:, d].sum() == n
+
+
+def test_kmeans_iter_cap_and_default_init(flgp, oracle):
+    X, _ = swiss(6000, 3)
+    init = flgp.default_init(6000, 300, seed=9)
+    U, assign, iters = flgp.subsample_cpp(X, 300, "kmeans", seed=9, iter_max=5, return_info=True)
+    Uo, ao, io = oracle.kmeans_lloyd(X, 300, init, 5, NT)
+    assert iters == io == 5 and np.array_equal(U, Uo) and np.array_equal(assign, ao)
+
+
+def test_subsample_random_and_errors(flgp):
+    X, _ = spiral(500, 4)
+    init = _init(500, 30, 1)
+    U = flgp.subsample_cpp(X, 30, "random", init_idx=init)
+    assert U.shape == (30, 2) and np.array_equal(U, X[init])
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.subsample_cpp(X, 30, "minibatchkmeans")
+    with pytest.raises(flgp.FlgpError):
+        flgp.subsample_cpp(X, 501, "kmeans")
+
+
+# ------------------------------------------------------------------------------------------- KNN
+@pytest.mark.parametrize("n,d,s,r", [(4000, 2, 500, 3), (5000, 3, 333, 3), (3000, 3, 64, 5), (2000, 1, 50, 1),
+                                      (2000, 4, 100, 8), (1000, 3, 40, 32), (1500, 8, 130, 5), (900, 37, 65, 4),
+                                      (600, 784, 100, 5)])
+def test_knn_bitexact(flgp, oracle, n, d, s, r):
+    rng = np.random.default_rng(n + s)
+    X = np.asfortranarray(rng.standard_normal((n, d)))
+    U = np.asfortranarray(X[_init(n, s, 3)] + 0.01 * rng.standard_normal((s, d)))
+    ind, dist = flgp.knn_distances(X, U, r)
+    io, do = oracle.knn(X, U, r, want_dist=True, nthreads=NT)
+    assert np.array_equal(ind, io)
+    assert np.array_equal(dist, do)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    res = flgp.KNN_cpp(X, U, r, "Euclidean", True)
+    assert np.array_equal(res["ind_knn"], io)
+    Zj, Zx = _csr_parts(res["distances_sp"])
+    zj, zx = oracle.knn_csr(io, do)
+    assert np.array_equal(Zj, zj) and np.array_equal(Zx, zx)
+
+
+@pytest.mark.parametrize("d", [2, 3, 6])
+def test_knn_exact_ties_follow_std_partial_sort(flgp, oracle, d):
+    """Lattice points and duplicated anchors: the selected set and its order must match libstdc++."""
+    rng = np.random.default_rng(d)
+    X = np.asfortranarray(rng.integers(-3, 4, (3000, d)).astype(np.float64))
+    U = np.asfortranarray(rng.integers(-3, 4, (90, d)).astype(np.float64))
+    U[40:50] = U[10:20]  # exact duplicates
+    for r in (1, 3, 4, 7):
+        ind = flgp.KNN_cpp(X, U, r)["ind_knn"]
+        assert np.array_equal(ind, oracle.knn(X, U, r, nthreads=NT))
+
+
+def test_knn_errors(flgp):
+    X, _ = spiral(100, 1)
+    with pytest.raises(flgp.FlgpError):
+        flgp.KNN_cpp(X, X[:3], 4)
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.KNN_cpp(X, X[:30], 3, distance="cosine")
+
+
+# ------------------------------------------------------------------------------------------- LAE
+def test_v_to_z_and_single_point(flgp, oracle):
+    rng = np.random.default_rng(0)
+    for r in (1, 2, 3, 7, 40):
+        v = rng.standard_normal(r) * 3
+        assert np.array_equal(flgp.v_to_z_cpp(v), oracle.simplex_project(v))
+    for r, d in ((3, 3), (5, 2), (4, 9), (16, 3)):
+        U = rng.standard_normal((r, d))
+        x = U.mean(0) + 0.2 * rng.standard_normal(d)
+        assert np.array_equal(flgp.local_anchor_embedding_cpp(x, U), oracle.lae_point(x, U))
+
+
+@pytest.mark.parametrize("n,d,s,r", [(4000, 2, 500, 3), (6000, 3, 300, 3), (3000, 3, 100, 5), (2000, 2, 80, 2),
+                                      (2000, 3, 80, 4), (1500, 6, 60, 3), (1200, 3, 50, 7), (400, 784, 50, 5)])
+def test_lae_bitexact(flgp, oracle, n, d, s, r):
+    rng = np.random.default_rng(n + r)
+    if d == 2:
+        X, _ = spiral(n, 5)
+    elif d == 3:
+        X, _ = swiss(n, 5)
+    else:
+        X = np.asfortranarray(rng.standard_normal((n, d)))
+    U = np.asfortranarray(X[_init(n, s, 4)] + 0.05 * rng.standard_normal((s, d)))
+    Z, stats = flgp.LAE_cpp(X, U, r, return_stats=True)
+    Zj, Zx = _csr_parts(Z)
+    zj, zx, _, st = oracle.lae(X, U, r, nthreads=NT, want_stats=True)
+    assert np.array_equal(Zj, zj)
+    assert np.array_equal(Zx, zx)  # bit-exact weights: same operation order, no FMA contraction
+    assert tuple(stats) == tuple(st)
+    assert Z.nnz == n * r  # explicit zeros are stored
+
+
+# ------------------------------------------------------------------------------------------- Z, GL
+@pytest.mark.parametrize("gl", ["rw", "normalized", "cluster-normalized"])
+def test_graph_laplacian_and_cross_similarity(flgp, oracle, gl):
+    X, _ = swiss(5000, 6)
+    s, r = 120, 3
+    U, _, _ = oracle.kmeans_lloyd(X, s, _init(5000, s, 5), 100, NT)
+    zj, zx, _ = oracle.lae(X, U[:, :3], r, nthreads=NT)
+    Z0 = flgp.LAE_cpp(X, U[:, :3], r)
+    want = oracle.graph_laplacian(zj, zx, s, gl, U[:, 3], 1)
+    got = flgp.graphLaplacian_cpp(Z0, gl, U[:, 3])
+    assert np.array_equal(_csr_parts(got)[1], want)  # fixed-point column sums: bit-exact
+    Zc = flgp.cross_similarity_lae_cpp(X, U, r, gl)
+    assert np.array_equal(_csr_parts(Zc)[0], zj) and np.array_equal(_csr_parts(Zc)[1], want)
+    # the reference's sequential fp64 sums agree far inside the 1e-8 contract
+    seq = oracle.graph_laplacian(zj, zx, s, gl, U[:, 3], 0)
+    np.testing.assert_allclose(_csr_parts(got)[1], seq, rtol=1e-12, atol=1e-300)
+    # SE weights: exp() differs by an ulp between libm and CUDA
+    Zs = flgp.cross_similarity_se_cpp(X, U, r, gl, 0.7)
+    sj, sx = oracle.cross_similarity_se(X, U, r, gl, 0.7, 1, NT)
+    assert np.array_equal(_csr_parts(Zs)[0], sj)
+    np.testing.assert_allclose(_csr_parts(Zs)[1], sx, rtol=1e-12, atol=1e-300)
+
+
+def test_gl_errors(flgp):
+    X, _ = spiral(300, 1)
+    Z = flgp.LAE_cpp(X, X[:20], 3)
+    with pytest.raises(flgp.FlgpError, match="graph Laplacian is not supported"):
+        flgp.graphLaplacian_cpp(Z, "bogus")
+    with pytest.raises(flgp.FlgpError):
+        flgp.cross_similarity_lae_cpp(X, X[:20], 3, "cluster-normalized")  # no size column
+
+
+# ------------------------------------------------------------------------------------------- spectrum
+def _check_spectrum(flgp, oracle, ep, values_o, V_o, K, t=2.0, tol=1e-8):
+    values = ep.values
+    np.testing.assert_allclose(values, values_o, rtol=tol, atol=tol * 1e-3)
+    n = ep.n_local
+    idx0 = np.arange(0, n, max(1, n // 97), dtype=np.int32)
+    idx1 = np.arange(0, n, max(1, n // 61), dtype=np.int32)
+    H = flgp.HK_from_spectrum_cpp(ep, K, t, idx0, idx1)
+    Ho = oracle.hk_from_spectrum(V_o, values_o, K, t, idx0, idx1, NT)
+    assert np.abs(H - Ho).max() <= tol * np.abs(Ho).max()
+    return H
+
+
+@pytest.mark.parametrize("root", [True, False])
+def test_spectrum_from_Z(flgp, oracle, root):
+    X, _ = swiss(8000, 7)
+    s, r, K = 150, 3, 40
+    U, _, _ = oracle.kmeans_lloyd(X, s, _init(8000, s, 6), 100, NT)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, r, "cluster-normalized", 1, NT)
+    import scipy.sparse as sp
+
+    Z = sp.csr_matrix((Zx.reshape(-1), Zj.reshape(-1), np.arange(0, 8000 * r + 1, r)), shape=(8000, s))
+    ep = flgp.spectrum_from_Z_cpp(Z, K, root)
+    vo, Vo, I = oracle.spectrum_from_Z(Zj, Zx, s, K, root, 1, NT, True)
+    _check_spectrum(flgp, oracle, ep, vo, Vo, K)
+    V = ep.vectors
+    np.testing.assert_allclose(V.T @ V / 8000, np.eye(K), atol=1e-9)
+    # eigenvectors up to sign where the eigenvalue is isolated
+    gaps = np.minimum(np.abs(np.diff(I["lam"], prepend=np.inf)), np.abs(np.diff(I["lam"], append=-np.inf)))
+    for k in np.nonzero(gaps > 1e-4)[0]:
+        c = np.dot(V[:, k], Vo[:, k]) / 8000
+        assert abs(abs(c) - 1) < 1e-8
+    np.testing.assert_allclose(ep.rows([5, 17, 4000]), V[[5, 17, 4000]], rtol=0, atol=0)
+
+
+def test_spectrum_full_K_equals_s(flgp, oracle):
+    X, _ = spiral(3000, 8)
+    s, r = 40, 3
+    U, _, _ = oracle.kmeans_lloyd(X, s, _init(3000, s, 7), 100, NT)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, r, "rw", 1, NT)
+    ep = flgp.spectrum_from_Z_cpp((Zj, Zx, s), -1, True)
+    vo, Vo = oracle.spectrum_from_Z(Zj, Zx, s, -1, True, 1, NT)
+    assert ep.K == s
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-9)
+
+
+def test_heat_kernel_spectrum_rings_degenerate(flgp, oracle):
+    """C1: six disconnected rings => eigenvalue 1 with multiplicity 6; compare eigenvalues and H, never vectors."""
+    from flgp_b200.datasets import make
+
+    X, Y, cfg = make("C1")
+    m, s, r, K = cfg["m"], cfg["s"], cfg["r"], cfg["K"]
+    init = _init(len(X), s, 8)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init)
+    vo, Vo, I = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init, nthreads=NT, want_internals=True)
+    assert ep.kmeans_iters == I["iters"]
+    assert np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    assert np.sum(np.abs(vo - 1) < 1e-9) >= 2  # the spectrum really is degenerate
+    # keep the K cut away from a cluster: compare on the largest K' <= K with a clear gap below it
+    lam = I["lam"]
+    Kc = max(k for k in range(10, K) if lam[k - 1] - lam[k] > 1e-6)
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
+    idx0 = np.arange(0, len(X), 37, dtype=np.int32)
+    idx1 = np.arange(m, dtype=np.int32)
+    H = flgp.HK_from_spectrum_cpp(ep, Kc, 5.0, idx0, idx1)
+    Ho = oracle.hk_from_spectrum(Vo, vo, Kc, 5.0, idx0, idx1, NT)
+    assert np.abs(H - Ho).max() <= 1e-8 * np.abs(Ho).max()
+
+
+def test_exports_eigenmap_and_covariance(flgp, oracle):
+    X, _ = spiral(2500, 9)
+    s, r, ndim = 60, 3, 8
+    init = _init(2500, s, 9)
+    res = flgp.lae_eigenmap(X, s, r, ndim, "kmeans", "normalized", init_idx=init)
+    evo, Vo = oracle.lae_eigenmap(X, s, r, ndim, init, "normalized", nthreads=NT)
+    np.testing.assert_allclose(res["eigenvalues"], evo, rtol=1e-7, atol=1e-9)
+    P = res["eigenvectors"] @ res["eigenvectors"].T[:, :50]
+    Po = Vo @ Vo.T[:, :50]
+    assert np.abs(P - Po).max() <= 1e-7 * np.abs(Po).max()
+    m = 80
+    H = flgp.heat_kernel_covariance_rcpp(X[:m], X[m:], s, r, 3.0, 20, init_idx=init)
+    vo, Vv = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, 20, init, nthreads=NT)
+    Ho = oracle.hk_from_spectrum(Vv, vo, 20, 3.0, np.arange(2500, dtype=np.int32), np.arange(m, dtype=np.int32), NT)
+    assert H.shape == (2500, m)
+    assert np.abs(H - Ho).max() <= 1e-8 * np.abs(Ho).max()
+
+
+# ------------------------------------------------------------------------------------------- GPR tail
+@pytest.mark.parametrize("m,K", [(60, 80), (400, 50)])
+def test_fit_lae_regression_fixed_pars(flgp, oracle, m, K):
+    X, Y = spiral(4000, 10)
+    s, r = 120, 3
+    init = _init(4000, s, 10)
+    pars, sigma = (4.0, 0.05), 1e-3
+    res = flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, sigma, pars=pars, init_idx=init)
+    ref = oracle.fit_lae_regression_fixed(X[:m], Y[:m], X[m:], s, r, K, pars, init, sigma, nthreads=NT)
+    sc = np.abs(ref["test"]).max()
+    assert np.abs(res["Y_pred"]["train"] - ref["train"]).max() <= 1e-8 * sc
+    assert np.abs(res["Y_pred"]["test"] - ref["test"]).max() <= 1e-8 * sc
+    assert np.abs(res["posterior"]["cov"] - ref["cov"]).max() <= 1e-8 * np.abs(ref["cov"]).max()
+    assert np.all(res["posterior"]["cov"] > 0)
+
+
+def test_errors_mirror_rcpp_stop(flgp):
+    X, Y = spiral(300, 1)
+    with pytest.raises(flgp.FlgpError, match="kernel type is not supported"):
+        flgp.heat_kernel_spectrum_cpp(X[:50], X[50:], 20, 3, 5, models=dict(kernel="bogus"))
+    with pytest.raises(flgp.FlgpError, match="subsample method is not supported"):
+        flgp.heat_kernel_spectrum_cpp(X[:50], X[50:], 20, 3, 5, models=dict(subsample="bogus"))
+    with pytest.raises(flgp.FlgpError, match="cluster-normalized"):
+        flgp.heat_kernel_spectrum_cpp(X[:50], X[50:], 20, 3, 5, models=dict(subsample="random"))
+    with pytest.raises(flgp.FlgpError):
+        flgp.heat_kernel_spectrum_cpp(X[:50], X[50:], 20, 3, 21)  # K > s
+    with pytest.raises(flgp.FlgpError, match="noise"):
+        flgp.fit_lae_regression_gp_rcpp(X[:50], Y[:50], X[50:], 20, 3, 5, noise="bogus", pars=(1, 1))
+
+
+# ------------------------------------------------------------------------------------------- full-size properties
+def test_c4_scale_properties(flgp):
+    """BASELINE config 4 shape at n = 2e6 (full s, r, K): size-independent properties through the C ABI."""
+    from flgp_b200.datasets import make
+
+    n, m = 2_000_000, 5000
+    X, Y, cfg = make("C4", n=n)
+    s, r, K = cfg["s"], cfg["r"], cfg["K"]
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, seed=1, iter_max=10)
+    U = ep.anchors()
+    assert U[:, 3].sum() == n and ep.kmeans_iters == 10
+    Z = ep.Z()
+    Zj, Zx = _csr_parts(Z)
+    assert np.all(np.diff(Zj, axis=1) > 0) and Zj.min() >= 0 and Zj.max() < s
+    np.testing.assert_allclose(Zx.sum(1), 1.0, rtol=1e-6)
+    vals = ep.values
+    assert abs(vals[0] - 1) < 1e-6 and np.all(np.diff(vals) <= 1e-12) and vals[-1] > 0
+    idx = np.arange(0, n, n // 300, dtype=np.int32)
+    H = flgp.HK_from_spectrum_cpp(ep, K, 10.0, idx, idx)
+    np.testing.assert_allclose(H, H.T, rtol=1e-10, atol=1e-12)
+    assert np.linalg.eigvalsh(H).min() > -1e-8
+    V = ep.rows(idx)
+    assert np.abs(V[:, 0]).std() < 1e-6 * np.abs(V[:, 0]).mean()  # top eigenvector of a row-stochastic Z is constant
+    y, cov = flgp.regression_fixed(ep, Y[:m], m, K, (10.0, 0.01), 1e-5)
+    assert np.sqrt(np.mean((y[m:] - Y[m:]) ** 2)) < 0.5 and np.all(cov[m:] > 0)

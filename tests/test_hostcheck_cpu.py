@@ -1,0 +1,128 @@
+"""The kernels' per-thread arithmetic (flgp_b200/csrc/core_math.cuh), compiled for the host by the
+test-only shim, against the oracle — bit for bit.  Proves the CUDA source's LOGIC on the CPU box; the
+-m gpu tests then prove the device build."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+P = C.POINTER
+
+
+def _pd(a):
+    return a.ctypes.data_as(P(C.c_double))
+
+
+def _topr(hc, row, r):
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    ind = np.zeros(r, np.int32)
+    key = np.zeros(r)
+    hc.hc_topr(_pd(row), row.size, r, ind.ctypes.data_as(P(C.c_int32)), _pd(key))
+    return ind, key
+
+
+def _partial_sort_ref(oracle, row, r):
+    """std::partial_sort through the oracle's KNN on a 1-D embedding that reproduces `row` exactly:
+    x = 0, u_j = sqrt-free trick is not exact, so instead build distances directly with d=1, x=0:
+    D_j = ((-2*0*u) + 0) + u_j^2 — only squares.  Use the dedicated row entry point instead."""
+    raise NotImplementedError
+
+
+def test_heap_emulation_matches_std_partial_sort_with_ties(hostcheck, oracle):
+    """Lattice data: many exactly equal distances.  The oracle calls the literal std::partial_sort."""
+    rng = np.random.default_rng(0)
+    # integer lattice points and anchors -> exactly representable, heavily tied distances
+    for trial in range(30):
+        s = int(rng.integers(5, 60))
+        r = int(rng.integers(1, min(s, 9) + 1))
+        d = int(rng.integers(1, 4))
+        X = np.asfortranarray(rng.integers(-3, 4, (40, d)).astype(np.float64))
+        U = np.asfortranarray(rng.integers(-3, 4, (s, d)).astype(np.float64))
+        ind, dist = oracle.knn(X, U, r, want_dist=True)
+        D = ((-2 * (X @ U.T)) + (X ** 2).sum(1)[:, None]) + (U ** 2).sum(1)[None, :]  # exact in integers
+        ties = 0
+        for i in range(len(X)):
+            gi, gk = _topr(hostcheck, D[i], r)
+            assert np.array_equal(gi, ind[i]), (trial, i, gi, ind[i])
+            assert np.array_equal(gk, dist[i])
+            ties += len(np.unique(D[i])) < s
+        assert ties > 0
+
+
+def test_heap_emulation_random_rows(hostcheck, oracle):
+    rng = np.random.default_rng(1)
+    X = np.asfortranarray(rng.standard_normal((200, 3)))
+    U = np.asfortranarray(rng.standard_normal((300, 3)))
+    for r in (1, 2, 3, 5, 8, 16, 32):
+        ind, dist = oracle.knn(X, U, r, want_dist=True)
+        xn = ((X[:, 0] * X[:, 0] + X[:, 1] * X[:, 1]) + X[:, 2] * X[:, 2])
+        un = ((U[:, 0] * U[:, 0] + U[:, 1] * U[:, 1]) + U[:, 2] * U[:, 2])
+        for i in range(0, 200, 7):
+            acc = (X[i, 0] * U[:, 0] + X[i, 1] * U[:, 1]) + X[i, 2] * U[:, 2]
+            row = ((-2.0 * acc) + xn[i]) + un
+            gi, gk = _topr(hostcheck, row, r)
+            assert np.array_equal(gi, ind[i]) and np.array_equal(gk, dist[i])
+
+
+def test_simplex_bitexact(hostcheck, oracle):
+    rng = np.random.default_rng(2)
+    for r in (1, 2, 3, 4, 5, 8, 16, 40):
+        for _ in range(100):
+            v = rng.standard_normal(r) * rng.choice([1e-3, 1, 50])
+            if rng.random() < 0.3:
+                v[rng.integers(0, r)] = v[rng.integers(0, r)]  # duplicates
+            z = np.zeros(r)
+            hostcheck.hc_simplex(_pd(np.ascontiguousarray(v)), r, _pd(z))
+            assert np.array_equal(z, oracle.simplex_project(v))
+
+
+@pytest.mark.parametrize("fixed", [0, 1])
+def test_lae_solver_bitexact(hostcheck, oracle, fixed):
+    rng = np.random.default_rng(3)
+    shapes = [(3, 3), (3, 2), (5, 3), (2, 2)] if fixed else [(3, 3), (4, 7), (1, 2), (6, 2), (16, 5), (5, 30)]
+    n_iter = 0
+    for r, d in shapes:
+        for _ in range(150):
+            U = np.asfortranarray(rng.standard_normal((r, d)) * rng.choice([0.3, 2.0, 20.0]))
+            x = U.mean(0) + rng.standard_normal(d) * rng.choice([0.01, 0.5, 5.0])
+            z = np.zeros(r)
+            it, bt = C.c_int(), C.c_int()
+            rc = hostcheck.hc_lae(_pd(np.ascontiguousarray(x)), d, _pd(U), r, fixed, _pd(z), C.byref(it), C.byref(bt))
+            assert rc == 0
+            zo, ito, bto = oracle.lae_point(x, U, want_stats=True)
+            assert np.array_equal(z, zo), (r, d, z, zo)
+            assert (it.value, bt.value) == (ito, bto)
+            n_iter += ito
+    assert n_iter > 0
+
+
+def test_fx_codec_bitexact(hostcheck, oracle):
+    rng = np.random.default_rng(4)
+    x = np.concatenate([rng.standard_normal(2000) * 1e3, rng.standard_normal(2000) * 1e-6, [0.0, -0.0, 1e3, -1e3]])
+    for count in (1, 1000, 10 ** 7, 10 ** 9):
+        maxabs = np.abs(x).max()
+        hi = np.zeros(x.size, np.int64)
+        lo = np.zeros(x.size, np.int64)
+        back = np.zeros(x.size)
+        rc = hostcheck.hc_fx_roundtrip(C.c_double(maxabs), C.c_int64(count), _pd(x), C.c_int64(x.size),
+                                       hi.ctypes.data_as(P(C.c_longlong)), lo.ctypes.data_as(P(C.c_longlong)),
+                                       _pd(back))
+        assert rc == 0
+        ohi, olo = oracle.fx_encode(x, maxabs, count)
+        assert np.array_equal(hi, ohi) and np.array_equal(lo, olo)
+        assert np.array_equal(back, oracle.fx_decode(ohi, olo, maxabs, count))
+        assert np.max(np.abs(back - x)) <= maxabs * 2.0 ** -60
+
+
+def test_sturm_count_matches_eigenvalues(hostcheck):
+    rng = np.random.default_rng(5)
+    n = 60
+    d = rng.standard_normal(n)
+    e = rng.standard_normal(n - 1)
+    T = np.diag(d) + np.diag(e, 1) + np.diag(e, -1)
+    lam = np.linalg.eigvalsh(T)
+    e2 = np.ascontiguousarray(np.r_[e * e, 0.0])
+    hostcheck.hc_sturm.restype = C.c_int
+    for x in np.r_[lam[:-1] + np.diff(lam) / 2, lam.min() - 1, lam.max() + 1]:
+        got = hostcheck.hc_sturm(_pd(np.ascontiguousarray(d)), _pd(e2), n, C.c_double(x), C.c_double(1e-300))
+        assert got == int((lam < x).sum())

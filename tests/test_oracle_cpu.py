@@ -1,0 +1,255 @@
+"""CPU tests of the oracle itself: each C++ stage against an independent numpy twin, the properties the
+domain offers, and the committed golden fixtures.  (The reference ships no tests or vectors: SURVEY §4.)"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import spiral, swiss
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_fixed_point_roundtrip_and_order_independence(oracle):
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(5000) * 17.0
+    hi, lo = oracle.fx_encode(x, np.abs(x).max(), x.size)
+    back = oracle.fx_decode(hi, lo, np.abs(x).max(), x.size)
+    assert np.max(np.abs(back - x)) <= 1e-18 * 32  # dropped bits are ~2^-70 of the scale
+    perm = rng.permutation(x.size)
+    assert hi.sum() == hi[perm].sum() and lo.sum() == lo[perm].sum()
+    s = oracle.fx_decode(np.array([hi.sum()]), np.array([lo.sum()]), np.abs(x).max(), x.size)[0]
+    import math
+
+    assert abs(s - math.fsum(x)) <= 1e-12 * abs(math.fsum(x)) + 1e-12
+
+
+def test_kmeans_matches_numpy_lloyd(oracle):
+    X, _ = spiral(1500, 3)
+    s = 40
+    rng = np.random.default_rng(0)
+    init = np.sort(rng.choice(len(X), s, replace=False))
+    U, assign, iters = oracle.kmeans_lloyd(X, s, init, 100)
+    # numpy twin (plain fp64 means): same partition unless a point sits on a bisector to 1e-12
+    C = X[init].copy()
+    a_prev = None
+    for _ in range(100):
+        D = (C ** 2).sum(1)[None, :] - 2 * X @ C.T
+        a = D.argmin(1)
+        if a_prev is not None and np.array_equal(a, a_prev):
+            break
+        a_prev = a
+        for j in range(s):
+            if (a == j).any():
+                C[j] = X[a == j].mean(0)
+    assert np.mean(a == assign) > 0.999
+    assert U[:, 2].sum() == len(X)
+    assert np.array_equal(np.bincount(assign, minlength=s), U[:, 2].astype(int))
+    # centres are the means of their members
+    for j in range(0, s, 7):
+        np.testing.assert_allclose(U[j, :2], X[assign == j].mean(0), rtol=1e-12)
+    assert 1 <= iters <= 100
+
+
+def test_kmeans_thread_invariance(oracle):
+    X, _ = swiss(4000, 5)
+    init = np.arange(0, 4000, 80, dtype=np.int32)
+    U1, a1, i1 = oracle.kmeans_lloyd(X, len(init), init, 100, nthreads=1)
+    U4, a4, i4 = oracle.kmeans_lloyd(X, len(init), init, 100, nthreads=4)
+    assert i1 == i4 and np.array_equal(a1, a4) and np.array_equal(U1, U4)  # bit-exact: integer limbs
+
+
+def test_knn_matches_argsort_and_is_sorted(oracle):
+    X, _ = swiss(2000, 7)
+    U = X[::20].copy()
+    ind, dist = oracle.knn(X, U, 4, want_dist=True, nthreads=3)
+    D = ((-2 * (X @ U.T)) + (X ** 2).sum(1)[:, None]) + (U ** 2).sum(1)[None, :]
+    ref = np.argsort(D, axis=1, kind="stable")[:, :4]
+    assert np.array_equal(ind, ref)
+    assert np.all(np.diff(dist, axis=1) >= 0)
+    np.testing.assert_allclose(dist, np.take_along_axis(D, ref, 1), rtol=1e-12, atol=1e-12)
+
+
+def test_knn_errors(oracle):
+    X, _ = spiral(10)
+    with pytest.raises(ValueError):
+        oracle.knn(X, X[:3], 4)
+
+
+def test_simplex_projection_properties(oracle):
+    rng = np.random.default_rng(2)
+    for r in (1, 2, 3, 5, 9):
+        for _ in range(50):
+            v = rng.standard_normal(r) * rng.choice([0.1, 1, 10])
+            z = oracle.simplex_project(v)
+            assert np.all(z >= 0) and abs(z.sum() - 1) < 1e-12
+            # optimality: z = max(v - theta, 0) for a single theta
+            th = (v - z)[z > 0]
+            assert np.ptp(th) < 1e-12
+            # idempotent on the simplex
+            np.testing.assert_allclose(oracle.simplex_project(z), z, atol=1e-15)
+
+
+def _lae_numpy(x, U, T=100, tol=1e-5):
+    """Independent numpy restatement of src/lae.cpp:76-133 (vectorised ops, same control flow)."""
+    r = U.shape[0]
+    zp = np.full(r, 1.0 / r)
+    zc = zp.copy()
+    dp, dc, bc = 0.0, 1.0, 1.0
+    UUt = U @ U.T
+
+    def proj(v):
+        vd = np.sort(v)[::-1]
+        cs = np.cumsum(vd)
+        vs = vd - (cs - 1) / np.arange(1, r + 1)
+        rho = np.nonzero(vs > 0)[0].max() + 1
+        th = (vd[:rho].sum() - 1.0) / rho
+        return np.maximum(v - th, 0)
+
+    for _ in range(T):
+        al = (dp - 1) / dc
+        v = zc + al * (zc - zp)
+        gv = ((x - v @ U) ** 2).sum() / 2
+        g = v @ UUt - x @ U.T
+        j = 0
+        while True:
+            b = 2.0 ** j * bc
+            z = proj(v - g / b)
+            gz = ((x - z @ U) ** 2).sum() / 2
+            gt = gv + g @ (z - v) + b * ((z - v) ** 2).sum() / 2
+            if gz <= gt:
+                bc = b
+                zp, zc = zc, z
+                break
+            j += 1
+        dp, dc = dc, (1 + np.sqrt(1 + 4 * dc * dc)) / 2
+        if ((zc - zp) ** 2).sum() < tol:
+            break
+    return zc
+
+
+def test_lae_point_matches_numpy_twin(oracle):
+    rng = np.random.default_rng(4)
+    worst = 0.0
+    for _ in range(200):
+        r, d = rng.choice([2, 3, 5]), rng.choice([2, 3, 6])
+        U = rng.standard_normal((r, d)) * rng.choice([0.5, 3.0])
+        x = U.mean(0) + 0.3 * rng.standard_normal(d)
+        z = oracle.lae_point(x, U)
+        zn = _lae_numpy(x, U)
+        assert np.all(z >= 0) and abs(z.sum() - 1) < 1e-12
+        worst = max(worst, np.abs(z - zn).max())
+    # summation order differs (numpy pairwise/BLAS vs sequential) so borderline branch flips are possible;
+    # they are rare and small
+    assert worst < 1e-6
+
+
+def test_lae_reconstruction_improves_on_uniform(oracle):
+    X, _ = swiss(500, 8)
+    U = X[::10].copy()
+    Zj, Zx, W = oracle.lae(X, U, 3)
+    assert np.allclose(Zx.sum(1), 1.0) and np.all(Zx >= 0)
+    assert np.all(np.diff(Zj, axis=1) > 0)  # rows sorted by column, distinct
+    rec = np.einsum("ij,ijk->ik", Zx, U[Zj])
+    uni = U[Zj].mean(1)
+    assert (np.linalg.norm(X - rec, axis=1) <= np.linalg.norm(X - uni, axis=1) + 1e-9).mean() > 0.95
+
+
+def _dense(Zj, Zx, s):
+    n, r = Zj.shape
+    Z = np.zeros((n, s))
+    np.put_along_axis(Z, Zj, Zx, 1)
+    return Z
+
+
+@pytest.mark.parametrize("mode", ["rw", "normalized", "cluster-normalized"])
+def test_graph_laplacian_matches_dense_numpy(oracle, mode):
+    X, _ = spiral(800, 2)
+    U = X[::16].copy()
+    s = len(U)
+    Zj, Zx, _ = oracle.lae(X, U, 3)
+    nc = np.arange(1, s + 1, dtype=float)
+    Z = _dense(Zj, Zx, s)
+    if mode != "rw":
+        Z = Z * (1.0 / (Z.sum(0) + 1e-9))
+    if mode == "cluster-normalized":
+        Z = Z * nc
+    Z = (1.0 / (Z.sum(1) + 1e-9))[:, None] * Z
+    for exact in (0, 1):
+        got = oracle.graph_laplacian(Zj, Zx, s, mode, nc, exact)
+        np.testing.assert_allclose(_dense(Zj, got, s), Z, rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(got.sum(1), 1.0, rtol=1e-6)  # the +1e-9 regulariser is visible after scaling
+    with pytest.raises(ValueError):
+        oracle.graph_laplacian(Zj, Zx, s, "bogus")
+
+
+def test_spectrum_against_dense_svd_and_properties(oracle):
+    X, _ = spiral(1200, 6)
+    rng = np.random.default_rng(0)
+    s, r, K = 60, 3, 12
+    init = np.sort(rng.choice(len(X), s, replace=False))
+    U, _, _ = oracle.kmeans_lloyd(X, s, init)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, r, "cluster-normalized")
+    values, V, I = oracle.spectrum_from_Z(Zj, Zx, s, K, root=True, want_internals=True)
+    Z = _dense(Zj, Zx, s)
+    A = Z * (1.0 / np.sqrt(np.abs(Z.sum(0)) + 1e-9))
+    u, sv, _ = np.linalg.svd(A, full_matrices=False)
+    np.testing.assert_allclose(values, sv[:K], rtol=1e-10)
+    assert abs(values[0] - 1.0) < 1e-6  # row-stochastic Z: top singular value 1
+    # lifted vectors: sqrt(n) * left singular vectors, up to sign
+    for k in range(K):
+        c = abs(np.dot(V[:, k], u[:, k])) / np.sqrt(len(X))
+        assert abs(c - 1) < 1e-8
+    np.testing.assert_allclose(V.T @ V / len(X), np.eye(K), atol=1e-9)
+    # exact (fixed-point) and sequential sums agree far below the 1e-8 contract
+    v0, V0 = oracle.spectrum_from_Z(Zj, Zx, s, K, root=True, exact=0)
+    np.testing.assert_allclose(v0, values, rtol=1e-12)
+    # heat kernel: symmetric PSD on a subset
+    idx = np.arange(50, dtype=np.int32)
+    H = oracle.hk_from_spectrum(V, values, K, 2.0, idx, idx)
+    np.testing.assert_allclose(H, H.T, atol=1e-12)
+    assert np.linalg.eigvalsh(H).min() > -1e-10
+    Hn = (V[idx] * np.exp(-2.0 * (1 - values))) @ V[idx].T
+    np.testing.assert_allclose(H, Hn, rtol=1e-12, atol=1e-12)
+
+
+def test_regression_tail_branches_agree_with_direct_gp(oracle):
+    """Both branches of predict_regression_cpp / posterior_covariance_regression equal the textbook GP."""
+    X, Y = spiral(900, 9)
+    rng = np.random.default_rng(1)
+    s, r = 50, 3
+    init = np.sort(rng.choice(len(X), s, replace=False))
+    for m, K in ((30, 40), (120, 25)):  # m <= K and m > K
+        values, V = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init)
+        idx0 = np.arange(m, dtype=np.int32)
+        idx1 = np.arange(m, len(X), dtype=np.int32)
+        pars, sigma = (3.0, 0.05), 1e-3
+        mean = oracle.predict_regression(V, values, Y[:m], idx0, idx1, K, pars, sigma)
+        cov = oracle.posterior_covariance_regression(V, values, idx0, idx1, K, pars, sigma)
+        lam = np.exp(-pars[0] * (1 - values[:K]))
+        C = (V[:, :K] * lam) @ V[:, :K].T
+        Kvv = C[:m, :m] + (pars[1] + sigma) * np.eye(m)
+        ref_mean = C[m:, :m] @ np.linalg.solve(Kvv, Y[:m])
+        ref_cov = np.diag(C)[m:] + pars[1] + sigma - np.einsum("ij,ji->i", C[m:, :m], np.linalg.solve(Kvv, C[:m, m:]))
+        np.testing.assert_allclose(mean, ref_mean, rtol=1e-7, atol=1e-9)
+        np.testing.assert_allclose(cov, ref_cov, rtol=1e-7, atol=1e-9)
+
+
+def test_golden_fixture(oracle):
+    """Oracle outputs pinned by the committed fixture (generated by tests/golden/make_golden.py from THIS oracle;
+    the reference cannot run here, so this guards against drift, not against the reference)."""
+    path = os.path.join(GOLD, "oracle_small.npz")
+    g = np.load(path)
+    meta = json.loads(str(g["meta"]))
+    X, Y = spiral(meta["n"], meta["seed"])
+    init = g["init"]
+    U, assign, iters = oracle.kmeans_lloyd(X, meta["s"], init)
+    assert iters == meta["iters"]
+    assert np.array_equal(assign, g["assign"]) and np.array_equal(U, g["U"])
+    ind = oracle.knn(X, U[:, :2], meta["r"])
+    assert np.array_equal(ind, g["ind"])
+    Zj, Zx = oracle.cross_similarity_lae(X, U, meta["r"], "cluster-normalized")
+    assert np.array_equal(Zj, g["Zj"]) and np.array_equal(Zx, g["Zx"])
+    values, V = oracle.spectrum_from_Z(Zj, Zx, meta["s"], meta["K"], True)
+    np.testing.assert_allclose(values, g["values"], rtol=1e-11)
