@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py — FLGP fit+predict points/sec on BASELINE config 4 (n=10M Swiss roll, d=3, m=5000, s=2000, r=3, K=200).
+
+    python bench.py --gpus 1 --steps 3 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores, bounded sample
+
+One "step" = one full pass of the hot path over the whole synthetic matrix: Lloyd k-means (iter.max=100)
+-> KNN -> LAE -> graph-Laplacian scaling -> Gram -> top-K eigensolve -> GPR tail (posterior mean of every row +
+posterior variance) at fixed hyper-parameters (the nlopt optimiser is outside the path).
+The n rows are sharded over the ranks in contiguous blocks (strong scaling: n is fixed at 10M).
+
+`value`   : n / (device-timed seconds per step), inputs resident in HBM.
+`e2e`     : the same through the host-buffer C ABI (H2D of the shard, D2H of mean+variance inside the timed region).
+`roofline`: the dominant kernel (k-means assign+accumulate, FP64-FMA bound) against the FP64 FMA throughput measured
+            in-process (MEASURED_PEAKS.json has HBM and bf16 only); `roofline_hbm` for the Z-streaming kernels
+            against the measured HBM copy bandwidth.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PARS = (10.0, 0.01)   # (t, noise variance): fixed hyper-parameters
+SIGMA = 1e-5
+SEED = 1234
+KM_SEED = 1
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=None, help="override the number of rows (debug only; invalidates the line)")
+    ap.add_argument("--iter-max", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=100_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                pw.append(float(r[3]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+def cpu_pipeline(X, Y, cfg, init, iter_max, nthreads):
+    """The CPU path: the oracle restatement of the reference (oracle/), all stages, threaded."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+
+    m = cfg["m"]
+    t0 = time.perf_counter()
+    res = O.fit_lae_regression_fixed(X[:m], Y[:m], X[m:], cfg["s"], cfg["r"], cfg["K"], PARS, init, SIGMA,
+                                     iter_max=iter_max, nthreads=nthreads)
+    return time.perf_counter() - t0, res
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  The R package cannot be built or run
+    here (no R/Rcpp/Eigen/TBB), so this is the oracle port on all host cores, on a bounded sample
+    of the same workload (same d, s, r, K, iter.max; fewer rows)."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from flgp_b200.datasets import make
+    from flgp_b200 import default_init
+
+    n = args.cpu_sample
+    X, Y, cfg = make("C4", SEED, n=n)
+    init = default_init(n, cfg["s"], KM_SEED)
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup and 1):  # one warm-up pass is enough for a CPU code (page-in, thread pool)
+        cpu_pipeline(X[: max(cfg["m"] + 1000, n // 10)], Y[: max(cfg["m"] + 1000, n // 10)], cfg,
+                     default_init(max(cfg["m"] + 1000, n // 10), cfg["s"], KM_SEED), 3, cores)
+    times = []
+    for _ in range(max(1, args.steps)):
+        dt, _ = cpu_pipeline(X, Y, cfg, init, args.iter_max, cores)
+        times.append(dt)
+    T = sum(times) / len(times)
+    val = n / T
+    sample = "oracle port, %d of 10M rows (same d=3, s=%d, r=%d, K=%d, iter.max=%d), %d threads" % (
+        n, cfg["s"], cfg["r"], cfg["K"], args.iter_max, cores)
+    line = {"impl": "reference", "metric": "flgp_fit_predict_points_per_sec", "value": val, "unit": "points/s",
+            "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup, "ms_per_step": T * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 swiss-roll n=10M d=3 m=5000 s=2000 r=3 K=200 (bounded CPU sample)",
+                       "sample_rows": n},
+            "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import flgp_b200 as F
+    from flgp_b200.datasets import make, shard_bounds, CONFIGS
+    from flgp_b200.sharding import init_context_comm
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+
+    cfg = dict(CONFIGS["C4"])
+    n = args.n or cfg["n"]
+    m, s, r, K, d = cfg["m"], cfg["s"], cfg["r"], cfg["K"], cfg["d"]
+    lo, hi = shard_bounds(n, world, rank)
+    n_local = hi - lo
+    X_host, Y_host, _ = make("C4", SEED, lo, hi, n=n)          # this rank's rows, column-major
+    m_local = max(0, min(n_local, m - lo))
+    init = F.default_init(n, s, KM_SEED)
+
+    ctx = F.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)                      # a real (non-default) stream shared with the library
+    ctx.set_stream(stream.cuda_stream)                          # CUDA events below see the library's launches
+    init_context_comm(ctx, rank, world)
+
+    # device-resident inputs / outputs for `value`
+    Xd = torch.from_numpy(np.ascontiguousarray(X_host.T)).to(dev)      # (d, n_local) C-order == column-major n_local x d
+    Yd = torch.from_numpy(Y_host[:max(m_local, 1)].copy()).to(dev)
+    yd = torch.empty(max(n_local, 1), dtype=torch.float64, device=dev)
+    cd = torch.empty(max(n_local, 1), dtype=torch.float64, device=dev)
+    # pinned host buffers for `e2e`
+    Xp = torch.from_numpy(np.ascontiguousarray(X_host.T)).pin_memory()
+    Yp = torch.from_numpy(Y_host[:max(m_local, 1)].copy()).pin_memory()
+    yp = torch.empty(max(n_local, 1), dtype=torch.float64).pin_memory()
+    cp = torch.empty(max(n_local, 1), dtype=torch.float64).pin_memory()
+    Xp_np = Xp.numpy().T                                          # F-ordered view (n_local, d)
+    models = dict(subsample="kmeans", kernel="lae", gl="cluster-normalized", root=True)
+    lib = ctx._lib
+    import ctypes as C
+    from flgp_b200._lib import check
+
+    def step_device():
+        ep = F.heat_kernel_spectrum_sharded(None, n, lo, s, r, K, models, init_idx=init, iter_max=args.iter_max,
+                                            ctx=ctx, device_ptr=Xd.data_ptr(), n_local=n_local, d=d)
+        check(lib.flgp_regression_fixed_dev(ep._h, C.c_void_p(Yd.data_ptr()), m, K, PARS[0], PARS[1], SIGMA,
+                                            C.c_void_p(yd.data_ptr()), C.c_void_p(cd.data_ptr())))
+        return ep
+
+    def step_e2e():
+        ep = F.heat_kernel_spectrum_sharded(Xp_np, n, lo, s, r, K, models, init_idx=init, iter_max=args.iter_max,
+                                            ctx=ctx)
+        check(lib.flgp_regression_fixed(ep._h, Yp.numpy().ctypes.data_as(F._lib.p_f64), m, K, PARS[0], PARS[1], SIGMA,
+                                        yp.numpy().ctypes.data_as(F._lib.p_f64),
+                                        cp.numpy().ctypes.data_as(F._lib.p_f64)))
+        return ep
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        e0.record(stream)
+        ep = None
+        for _ in range(steps):
+            if ep is not None:
+                ep.close()
+            ep = fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0]) / steps, ctx.launch_count - l0, ep
+
+    dfma_peak = ctx.dfma_peak_tflops() if rank == 0 else None
+    for _ in range(max(args.warmup, 0)):
+        step_device().close()
+    # --- timed region: device-resident (value), with per-stage events and clock sampling
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ctx.set_timing(True)
+    ctx.stage_reset()
+    ms_step, launches, ep = timed(step_device, args.steps)
+    ctx.set_timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    stages = ctx.stages()
+    info = dict(kmeans_iters=ep.kmeans_iters, lae_iters_per_point=ep.lae_iters / max(n_local, 1),
+                lae_backtracks_per_point=ep.lae_backtracks / max(n_local, 1))
+    y_dev = yd[:n_local].cpu().numpy()
+    ep.close()
+    # --- e2e through the host-buffer C ABI
+    step_e2e().close()
+    ms_e2e, _, ep2 = timed(step_e2e, max(1, min(args.steps, 2)))
+    ep2.close()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # sanity of the result (not timed): the fit must actually predict the held-out rows
+    test = slice(m_local, n_local)
+    rmse = float(np.sqrt(np.mean((y_dev[test] - Y_host[test]) ** 2)))
+
+    # --- per-stage summary and rooflines
+    agg = {}
+    for st in stages:
+        a = agg.setdefault(st["name"], dict(ms=0.0, launches=0, flops=0.0, bytes=0.0, calls=0))
+        a["ms"] += st["ms"]
+        a["launches"] += st["launches"]
+        a["flops"] += st["flops"]
+        a["bytes"] += st["bytes"]
+        a["calls"] += 1
+    per_step = {k: dict(ms=v["ms"] / args.steps, launches=v["launches"] / args.steps,
+                        gflops=(v["flops"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["flops"] else None,
+                        gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None)
+                for k, v in agg.items()}
+    peaks = measured_peaks()
+    ka = agg.get("kmeans_assign_kernel")
+    roof = None
+    if ka and ka["ms"] > 0:
+        ach = ka["flops"] / (ka["ms"] * 1e-3) / 1e12
+        roof = {"bound": "fp64", "kernel": "kmeans_assign_small<3,4>", "achieved": ach, "peak": dfma_peak,
+                "unit": "TFLOP/s", "frac": ach / dfma_peak if dfma_peak else None, "traffic": None,
+                "launch_ms": ka["ms"] / ka["calls"],
+                "algorithmic_flops_per_launch": ka["flops"] / ka["calls"],
+                "peak_source": "FP64 FMA throughput measured in-process by flgp_dfma_peak (register-resident DFMA "
+                               "loop); MEASURED_PEAKS.json carries no fp64 figure, the kernel is FP64-pipe bound, "
+                               "neither HBM- nor tensor-bound",
+                "share_of_step": ka["ms"] / args.steps / ms_step}
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    hb = {}
+    for nm in ("lae", "graph_laplacian", "gram"):
+        if nm in agg and agg[nm]["ms"] > 0 and agg[nm]["bytes"]:
+            g = agg[nm]["bytes"] / (agg[nm]["ms"] * 1e-3) / 1e9
+            hb[nm] = {"achieved": g, "frac": g / hbm_peak, "ms": agg[nm]["ms"] / args.steps}
+    roof_hbm = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s",
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst copy)" if peaks else "fallback 6650 GB/s",
+                "stages": hb}
+
+    line = {"metric": "flgp_fit_predict_points_per_sec", "value": n / (ms_step * 1e-3), "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C4 swiss-roll n=%d d=3 m=5000 s=2000 r=3 K=200, fit_lae_regression (kmeans, "
+                                   "cluster-normalized, root), fixed pars t=%g noise=%g" % (n, PARS[0], PARS[1]),
+                       "iter_max": args.iter_max, "parallelism": "rows sharded over %d GPU(s)" % world,
+                       "l2_policy": "inputs (%.0f MB per rank) larger than the 126 MB L2" % (n_local * d * 8 / 1e6),
+                       "optimizer": "excluded (fixed hyper-parameters), SURVEY.md 8d"},
+            "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(n_local * d * 8 + m_local * 8), "d2h_bytes_per_step": int(n_local * 16)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof,
+            "roofline_hbm": roof_hbm,
+            "stages_ms_per_step": per_step,
+            "path_info": info,
+            "test_rmse": rmse}
+    if not args.no_cpu_baseline:
+        ncpu = args.cpu_sample
+        Xc, Yc, _ = make("C4", SEED, n=ncpu)
+        cores = os.cpu_count() or 1
+        dt, _ = cpu_pipeline(Xc, Yc, cfg, F.default_init(ncpu, s, KM_SEED), args.iter_max, cores)
+        line["cpu_baseline"] = {"value": ncpu / dt, "unit": "points/s", "cores": cores, "kind": "port",
+                                "seconds": dt,
+                                "sample": "oracle port of the reference path, all stages, %d of 10M rows (same d, s, r, "
+                                          "K, iter.max), %d threads; the R package itself cannot run here" %
+                                          (ncpu, cores)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -467,12 +467,17 @@ int flgp_ctx_create(int device, flgp_ctx** out) {
     FLGP_CUDA(cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking));
     h->c.own_stream = true;
     FLGP_CUDA(cudaMallocHost(&h->c.pinned, 64 * sizeof(int64_t)));
+    pool_ctx_count(+1);
     *out = h.release();
   });
 }
 
 void flgp_ctx_destroy(flgp_ctx* ctx) {
   if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaDeviceSynchronize();
+  pool_ctx_count(-1);
+  pool_trim();
   comm_destroy(&ctx->c);
   for (auto& s : ctx->c.stages) {
     cudaEventDestroy(s.beg);
@@ -487,6 +492,7 @@ int flgp_ctx_set_stream(flgp_ctx* ctx, void* cuda_stream) {
   return guard([&] {
     need(ctx != nullptr, "null context");
     FLGP_CUDA(cudaSetDevice(ctx->c.device));
+    FLGP_CUDA(cudaDeviceSynchronize());  // pooled blocks are ordered by the stream: drain before switching
     if (ctx->c.own_stream && ctx->c.stream) {
       FLGP_CUDA(cudaStreamSynchronize(ctx->c.stream));
       cudaStreamDestroy(ctx->c.stream);

@@ -68,6 +68,16 @@ struct Ctx {
     FLGP_CUDA(cudaGetLastError());                                                               \
   } while (0)
 
+// ---- device memory pool ----------------------------------------------------------------------------
+// cudaMalloc/cudaFree synchronise the device and cost milliseconds for the 30-250 MB work buffers of a
+// fit; a repeated fit asks for exactly the same sizes, so freed blocks are kept and handed back by size.
+// All work of a process runs on one stream, which orders reuse; with more than one live context the pool
+// is bypassed.  (capi.cu owns the singleton.)
+void* pool_alloc(size_t bytes);
+void pool_free(void* p, size_t bytes);
+void pool_trim();
+void pool_ctx_count(int delta);
+
 // ---- RAII device buffer ---------------------------------------------------------------------------
 template <class T>
 struct DevBuf {
@@ -92,10 +102,10 @@ struct DevBuf {
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) FLGP_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    if (count) p = static_cast<T*>(pool_alloc(count * sizeof(T)));
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) pool_free(p, n * sizeof(T));
     p = nullptr;
     n = 0;
   }
@@ -129,12 +139,14 @@ struct StageScope {
     c->stages.push_back(r);
     idx = (int)c->stages.size() - 1;
   }
-  ~StageScope() {
+  void stop() {
     if (idx < 0) return;
     StageRec& r = c->stages[idx];
     cudaEventRecord(r.end, c->stream);
     r.launches = c->launches - r.launches;
+    idx = -1;
   }
+  ~StageScope() { stop(); }
 };
 
 // ---- collectives (comm.cu): no-ops when nranks == 1 ---------------------------------------------

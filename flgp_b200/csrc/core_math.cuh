@@ -190,12 +190,17 @@ constexpr int LAE_RMAX = 16;
 constexpr int LAE_T = 100;
 constexpr int LAE_JCAP = 1100;
 
+struct LaeStats {
+  int iters, backtracks;
+};
+
 template <int RT, int DT, class XAcc, class UAcc>
-FLGP_HD void lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out, int* iters, int* bts) {
+FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out) {
   constexpr int RA = RT ? RT : LAE_RMAX;
   const int r = RT ? RT : r_in;
   const int d = DT ? DT : d_in;
-  double UUt[RA * RA], xUt[RA], zp[RA], zc[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
+  double UUt[RA * RA], xUt[RA], zp[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
+  double* zc = z_out;  // the caller's array IS the current iterate (no copy at exit; see DESIGN.md §7 note on nvcc)
 #pragma unroll
   for (int a = 0; a < r; ++a) {
 #pragma unroll
@@ -282,10 +287,10 @@ FLGP_HD void lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double*
       break;
     }
   }
-#pragma unroll
-  for (int a = 0; a < r; ++a) z_out[a] = zc[a];
-  if (iters) *iters = t;
-  if (bts) *bts = nbt;
+  LaeStats st;
+  st.iters = t;
+  st.backtracks = nbt;
+  return st;
 }
 
 // ---------------------------------------------------------------------------------------------

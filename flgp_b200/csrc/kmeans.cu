@@ -318,8 +318,12 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   while (it < iter_max) {
     ++it;
     acc.zero(c->stream);
+    if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, rec.p);
+    else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, C2.p, cn.p);
+    // when timing is on, the assign+accumulate kernel gets its own CUDA-event pair per iteration:
+    // this is the dominant kernel whose roofline bench.py reports
+    StageScope kst(c, "kmeans_assign_kernel", 2.0 * s * d * (double)n_local, (8.0 * d + 4.0) * (double)n_local);
     if (small) {
-      FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, rec.p);
       switch (d) {
         case 1: launch_small<1>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
         case 2: launch_small<2>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
@@ -327,11 +331,11 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
         default: launch_small<4>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
       }
     } else {
-      FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, C2.p, cn.p);
       int grid = ceil_div(n_local, KT_TP);
       if (grid > 0)
         FLGP_LAUNCH(c, kmeans_assign_tiled, grid, 256, 0, X, n_local, ldx, d, C2.p, cn.p, s, fx, assign, uacc);
     }
+    kst.stop();
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(acc.p), words);
     FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s * d, 256), 256, 0, acc.p, s, d, fx, C, sizes);
     FLGP_CUDA(cudaMemcpyAsync(c->pinned, acc.p + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost,

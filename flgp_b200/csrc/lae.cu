@@ -105,7 +105,9 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
       for (int k = 0; k < D; ++k) Ur.u[a][k] = U[col[a] + ldu * k];
     }
     double z[R];
-    lae_solve<R, D>(R, D, x, Ur, z, &it, &bt);
+    const LaeStats ls = lae_solve<R, D>(R, D, x, Ur, z);
+    it = ls.iters;
+    bt = ls.backtracks;
     write_row<R>(R, col, z, i, n, Zj, Zx, Wd);
   }
   add_stats(stats, it, bt);
@@ -124,7 +126,9 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
     Ur.ldu = ldu;
     for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
     double z[LAE_RMAX];
-    lae_solve<0, 0>(r, d, x, Ur, z, &it, &bt);
+    const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z);
+    it = ls.iters;
+    bt = ls.backtracks;
     write_row<LAE_RMAX>(r, Ur.c, z, i, n, Zj, Zx, Wd);
   }
   add_stats(stats, it, bt);
@@ -156,7 +160,7 @@ __global__ void lae_point_kernel(const double* x, int d, const double* Ur, int r
   ua.ldu = r;
   for (int a = 0; a < r; ++a) ua.c[a] = a;
   double zz[LAE_RMAX];
-  lae_solve<0, 0>(r, d, xa, ua, zz, nullptr, nullptr);
+  lae_solve<0, 0>(r, d, xa, ua, zz);
   for (int a = 0; a < r; ++a) z[a] = zz[a];
 }
 

@@ -24,7 +24,9 @@ template <int R, int D>
 void lae_fixed(const double* x, const double* U, double* z, int* it, int* bt) {
   PtrX xa{x};
   PtrU ua{U, R};
-  lae_solve<R, D>(R, D, xa, ua, z, it, bt);
+  LaeStats st = lae_solve<R, D>(R, D, xa, ua, z);
+  *it = st.iters;
+  *bt = st.backtracks;
 }
 }  // namespace
 
@@ -74,7 +76,9 @@ int hc_lae(const double* x, int d, const double* Ur, int r, int fixed, double* z
   PtrX xa{x};
   PtrU ua{Ur, r};
   double zz[LAE_RMAX];
-  lae_solve<0, 0>(r, d, xa, ua, zz, it, bt);
+  LaeStats st = lae_solve<0, 0>(r, d, xa, ua, zz);
+  *it = st.iters;
+  *bt = st.backtracks;
   for (int a = 0; a < r; ++a) z[a] = zz[a];
   return 0;
 }
