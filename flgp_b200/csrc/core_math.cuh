@@ -129,6 +129,81 @@ FLGP_HD void heap_sort(double* hk, int* hi, int r) {
   }
 }
 
+// The same three primitives over an accessor (getk/geti/set by index) instead of arrays, so that a heap
+// of compile-time size can live entirely in registers (RegHeap below): every index is resolved by an
+// unrolled compare-select chain, never by an address.
+template <class H>
+FLGP_HD void heap_adjust_acc(H& h, int hole, int len, double vk, int vi) {
+  const int top = hole;
+  int child = hole;
+  while (child < (len - 1) / 2) {
+    child = 2 * (child + 1);
+    if (h.getk(child) < h.getk(child - 1)) child--;
+    h.set(hole, h.getk(child), h.geti(child));
+    hole = child;
+  }
+  if ((len & 1) == 0 && child == (len - 2) / 2) {
+    child = 2 * (child + 1);
+    h.set(hole, h.getk(child - 1), h.geti(child - 1));
+    hole = child - 1;
+  }
+  int parent = (hole - 1) / 2;
+  while (hole > top && h.getk(parent) < vk) {
+    h.set(hole, h.getk(parent), h.geti(parent));
+    hole = parent;
+    parent = (hole - 1) / 2;
+  }
+  h.set(hole, vk, vi);
+}
+template <class H>
+FLGP_HD void heap_make_acc(H& h, int len) {
+  if (len < 2) return;
+  int parent = (len - 2) / 2;
+  while (true) {
+    double vk = h.getk(parent);
+    int vi = h.geti(parent);
+    heap_adjust_acc(h, parent, len, vk, vi);
+    if (parent == 0) return;
+    parent--;
+  }
+}
+template <class H>
+FLGP_HD void heap_sort_acc(H& h, int r) {
+  int last = r;
+  while (last > 1) {
+    --last;
+    double vk = h.getk(last);
+    int vi = h.geti(last);
+    h.set(last, h.getk(0), h.geti(0));
+    heap_adjust_acc(h, 0, last, vk, vi);
+  }
+}
+template <int R>
+struct RegHeap {
+  double k[R];
+  int id[R];
+  FLGP_HD double getk(int i) const {
+    double v = k[0];
+#pragma unroll
+    for (int u = 1; u < R; ++u) v = (i == u) ? k[u] : v;
+    return v;
+  }
+  FLGP_HD int geti(int i) const {
+    int v = id[0];
+#pragma unroll
+    for (int u = 1; u < R; ++u) v = (i == u) ? id[u] : v;
+    return v;
+  }
+  FLGP_HD void set(int i, double kv, int iv) {
+#pragma unroll
+    for (int u = 0; u < R; ++u)
+      if (i == u) {
+        k[u] = kv;
+        id[u] = iv;
+      }
+  }
+};
+
 // ---------------------------------------------------------------------------------------------
 // v_to_z_cpp (src/lae.cpp:137-153): projection of v (length r) onto the simplex.
 // `vd` is scratch of length r.  Sequential cumulative sum, as std::partial_sum.

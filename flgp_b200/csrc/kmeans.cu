@@ -38,7 +38,7 @@ __global__ void maxabs_kernel(const double* __restrict__ X, int64_t n, int64_t l
 }
 
 // centres -> records [ -2c_0 .. -2c_{d-1}, |c|^2, pad ]  (stride STR = even(d+1))
-__global__ void kmeans_prep_kernel(const double* __restrict__ C, int s, int d, int str, double* rec) {
+__global__ void kmeans_prep_kernel(const double* __restrict__ C, int s, int d, int str, double M, double* rec) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= s) return;
   double a = 0.0;
@@ -47,12 +47,12 @@ __global__ void kmeans_prep_kernel(const double* __restrict__ C, int s, int d, i
     a = fma(c, c, a);
     rec[(size_t)j * str + k] = -2.0 * c;
   }
-  rec[(size_t)j * str + d] = a;
+  rec[(size_t)j * str + d] = __dadd_rn(a, M);  // M keeps every score positive (see the contract in the oracle)
   for (int k = d + 1; k < str; ++k) rec[(size_t)j * str + k] = 0.0;
 }
 
 // split records into the tiled kernel's operands: C2 (s x d col-major) and cn (s)
-__global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, int d, double* C2, double* cn) {
+__global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, int d, double M, double* C2, double* cn) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= s) return;
   double a = 0.0;
@@ -61,7 +61,7 @@ __global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, in
     a = fma(c, c, a);
     C2[j + (size_t)s * k] = -2.0 * c;
   }
-  cn[j] = a;
+  cn[j] = __dadd_rn(a, M);
 }
 
 __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, const double* x, int32_t* assign,
@@ -81,20 +81,29 @@ __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, co
 template <int D, int P>
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_assign_small(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s,
-                    Fx fx, int32_t* __restrict__ assign, unsigned long long* __restrict__ acc, int chunk) {
+                    Fx fx, int32_t* __restrict__ assign, unsigned long long* __restrict__ acc, int chunk, int one) {
   constexpr int STR = (D + 2) / 2 * 2;
   extern __shared__ __align__(16) double srec[];
   const int tid = threadIdx.x;
   const int64_t base = (int64_t)blockIdx.x * (KM_THREADS * P);
   double x[P][D], best[P];
-  int bj[P];
+  int bj[P], bh[P];  // bh = high word of best: scores are positive, so they order like their high words
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     int64_t i = base + (int64_t)p * KM_THREADS + tid;
 #pragma unroll
     for (int k = 0; k < D; ++k) x[p][k] = (i < n) ? X[i + ldx * k] : 0.0;
-    best[p] = INFINITY;
-    bj[p] = 0;
+    // seed with the centre this point had last iteration (centre 0 on the first): the running best is
+    // then almost always final already, so the exact-compare path below is hardly ever entered
+    int seed = (i < n) ? assign[i] : 0;
+    if (seed < 0) seed = 0;
+    const double* rs = rec + (size_t)seed * STR;
+    double e = rs[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) e = fma(x[p][k], rs[k], e);
+    best[p] = e;
+    bh[p] = __double2hiint(e);
+    bj[p] = seed;
   }
   for (int c0 = 0; c0 < s; c0 += chunk) {
     const int cnt = min(chunk, s - c0);
@@ -111,14 +120,28 @@ kmeans_assign_small(const double* __restrict__ X, int64_t n, int64_t ldx, const 
         cr[2 * q] = t.x;
         cr[2 * q + 1] = t.y;
       }
+      double e[P];
+      bool cand = false;
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        double e = cr[D];
+        e[p] = cr[D];
 #pragma unroll
-        for (int k = 0; k < D; ++k) e = fma(x[p][k], cr[k], e);
-        if (e < best[p]) {
-          best[p] = e;
-          bj[p] = c0 + j;
+        for (int k = 0; k < D; ++k) e[p] = fma(x[p][k], cr[k], e[p]);
+        // integer pre-filter on the ALU pipe: for positive doubles a < b implies hi(a) <= hi(b) (a
+        // non-positive score has a negative high word and always passes); the fp64 pipe keeps the FMAs
+        cand |= (__double2hiint(e[p]) <= bh[p]);
+      }
+      if (cand) {
+#pragma unroll 1
+        for (int q = 0; q < one; ++q) {  // `one` == 1: a loop cannot be if-converted => one real, rare branch
+          const int jj = c0 + j;
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            if (e[p] < best[p] || (e[p] == best[p] && jj < bj[p])) {  // lowest index among equal minima
+              best[p] = e[p];
+              bh[p] = __double2hiint(e[p]);
+              bj[p] = jj;
+            }
         }
       }
     }
@@ -264,7 +287,7 @@ void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double*
   size_t smem = (size_t)chunk * STR * sizeof(double);
   int grid = ceil_div(n, (int64_t)KM_THREADS * P);
   if (grid < 1) return;
-  FLGP_LAUNCH(c, (kmeans_assign_small<D, P>), grid, KM_THREADS, smem, X, n, ldx, rec, s, fx, assign, acc, chunk);
+  FLGP_LAUNCH(c, (kmeans_assign_small<D, P>), grid, KM_THREADS, smem, X, n, ldx, rec, s, fx, assign, acc, chunk, 1);
 }
 
 }  // namespace
@@ -292,6 +315,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   double maxabs = maxabs_run(c, X, n_local, ldx, d);
   Fx fx;
   if (fx_make(maxabs, n_total, &fx)) fail(2, "kmeans: non-finite input");
+  const double Moff = (2.0 * d) * (maxabs * maxabs);  // score offset of the k-means contract
 
   const size_t words = (size_t)2 * s * d + s + 1;
   DevBuf<long long> acc(words);
@@ -318,8 +342,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   while (it < iter_max) {
     ++it;
     acc.zero(c->stream);
-    if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, rec.p);
-    else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, C2.p, cn.p);
+    if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
+    else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
     // when timing is on, the assign+accumulate kernel gets its own CUDA-event pair per iteration:
     // this is the dominant kernel whose roofline bench.py reports
     StageScope kst(c, "kmeans_assign_kernel", 2.0 * s * d * (double)n_local, (8.0 * d + 4.0) * (double)n_local);

@@ -73,33 +73,99 @@ struct TopR {
   }
 };
 
-// ---- small d: one thread per point, anchor records broadcast from shared memory -------------------
-template <int D>
+// ---- small d: thread-per-point(s), anchor records broadcast from shared memory ----------------------
+// R > 0: the r-entry heap is a RegHeap<R> (registers only, compile-time r); R == 0: run-time r, local arrays.
+// Hot loop per (point, anchor): 8 fp64-pipe ops for the reference's distance expression, then an INTEGER
+// compare of the high word against the heap top's (for non-negative doubles a < b implies hi(a) <= hi(b);
+// a negative distance has a negative high word and always passes; a negative top disables the filter).
+// Only the rare candidate pays the exact fp64 compare and the heap update.
+template <int R>
+struct HeapState {
+  RegHeap<R> h;
+  __device__ __forceinline__ void fill(int j, double d) { h.set(j, d, j); }
+  __device__ __forceinline__ void make(int) { heap_make_acc(h, R); }
+  __device__ __forceinline__ double top() const { return h.k[0]; }
+  __device__ __forceinline__ void replace(int, double d, int j) { heap_adjust_acc(h, 0, R, d, j); }
+  __device__ __forceinline__ void finish(int, int64_t i, int64_t n, int32_t* ind, double* dist) {
+    heap_sort_acc(h, R);
+#pragma unroll
+    for (int a = 0; a < R; ++a) {
+      ind[i + n * a] = h.id[a];
+      if (dist) dist[i + n * a] = h.k[a];
+    }
+  }
+};
+template <>
+struct HeapState<0> {
+  double hk[KNN_RMAX];
+  int hi[KNN_RMAX];
+  __device__ __forceinline__ void fill(int j, double d) {
+    hk[j] = d;
+    hi[j] = j;
+  }
+  __device__ __forceinline__ void make(int r) { heap_make(hk, hi, r); }
+  __device__ __forceinline__ double top() const { return hk[0]; }
+  __device__ __forceinline__ void replace(int r, double d, int j) { heap_adjust(hk, hi, 0, r, d, j); }
+  __device__ __forceinline__ void finish(int r, int64_t i, int64_t n, int32_t* ind, double* dist) {
+    heap_sort(hk, hi, r);
+    for (int a = 0; a < r; ++a) {
+      ind[i + n * a] = hi[a];
+      if (dist) dist[i + n * a] = hk[a];
+    }
+  }
+};
+
+__device__ __forceinline__ int top_filter(double top) { return top < 0.0 ? 0x7fffffff : __double2hiint(top); }
+
+template <int D, int R, int P>
 __global__ void __launch_bounds__(256)
-knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s, int r,
-                 int32_t* __restrict__ ind, double* __restrict__ dist, int chunk) {
+knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s, int r_in,
+                 int32_t* __restrict__ ind, double* __restrict__ dist, int chunk, int one) {
   constexpr int STR = (D + 2) / 2 * 2;
+  const int r = R ? R : r_in;
   extern __shared__ __align__(16) double srec[];
   const int tid = threadIdx.x;
-  const int64_t i = (int64_t)blockIdx.x * 256 + tid;
-  const bool valid = i < n;
-  double x[D], xn = 0.0;
+  const int64_t base = (int64_t)blockIdx.x * (256 * P);
+  double x[P][D], xn[P];
+  HeapState<R> hs[P];
+  int th[P];
 #pragma unroll
-  for (int k = 0; k < D; ++k) {
-    x[k] = valid ? X[i + ldx * k] : 0.0;
-    xn = __dadd_rn(xn, __dmul_rn(x[k], x[k]));
+  for (int p = 0; p < P; ++p) {
+    const int64_t i = base + (int64_t)p * 256 + tid;
+    xn[p] = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      x[p][k] = (i < n) ? X[i + ldx * k] : 0.0;
+      xn[p] = __dadd_rn(xn[p], __dmul_rn(x[p][k], x[p][k]));
+    }
+    th[p] = 0x7fffffff;
   }
-  TopR h;
-  h.r = r;
-  h.top = INFINITY;
   for (int c0 = 0; c0 < s; c0 += chunk) {
     const int cnt = min(chunk, s - c0);
     __syncthreads();
     for (int t = tid; t < cnt * STR; t += 256) srec[t] = rec[(size_t)c0 * STR + t];
     __syncthreads();
-    if (!valid) continue;
+    int j = 0;
+    if (c0 == 0) {
+      // the first r anchors are the heap range [first, middle) of std::partial_sort
+      for (; j < r; ++j) {
+        const double* ur = srec + (size_t)j * STR;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+          double acc = 0.0;
+#pragma unroll
+          for (int k = 0; k < D; ++k) acc = __dadd_rn(acc, __dmul_rn(x[p][k], ur[k]));
+          hs[p].fill(j, __dadd_rn(__dadd_rn(__dmul_rn(-2.0, acc), xn[p]), ur[D]));
+        }
+      }
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        hs[p].make(r);
+        th[p] = top_filter(hs[p].top());
+      }
+    }
 #pragma unroll 2
-    for (int j = 0; j < cnt; ++j) {
+    for (; j < cnt; ++j) {
       double ur[STR];
       const double2* rj = reinterpret_cast<const double2*>(srec + (size_t)j * STR);
 #pragma unroll
@@ -108,14 +174,34 @@ knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
         ur[2 * q] = t.x;
         ur[2 * q + 1] = t.y;
       }
-      double acc = 0.0;
+      double dd[P];
+      bool cand = false;
 #pragma unroll
-      for (int k = 0; k < D; ++k) acc = __dadd_rn(acc, __dmul_rn(x[k], ur[k]));
-      double dd = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, acc), xn), ur[D]);
-      h.push(dd, c0 + j);
+      for (int p = 0; p < P; ++p) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) acc = __dadd_rn(acc, __dmul_rn(x[p][k], ur[k]));
+        dd[p] = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, acc), xn[p]), ur[D]);
+        cand |= (__double2hiint(dd[p]) <= th[p]);
+      }
+      if (cand) {
+#pragma unroll 1
+        for (int q = 0; q < one; ++q) {  // `one` == 1: keeps this a real, rarely taken branch
+#pragma unroll
+          for (int p = 0; p < P; ++p)
+            if (dd[p] < hs[p].top()) {
+              hs[p].replace(r, dd[p], c0 + j);
+              th[p] = top_filter(hs[p].top());
+            }
+        }
+      }
     }
   }
-  if (valid) h.finish(i, n, ind, dist);
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int64_t i = base + (int64_t)p * 256 + tid;
+    if (i < n) hs[p].finish(r, i, n, ind, dist);
+  }
 }
 
 // ---- any d: 64 x 64 distance tiles in shared memory, scanned in anchor order ----------------------
@@ -183,14 +269,27 @@ knn_tiled_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, co
   if (tid < NT_TP && iscan < n) h.finish(iscan, n, ind, dist);
 }
 
+template <int D, int R>
+void launch_small_r(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, int s, int r,
+                    int32_t* ind, double* dist) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  constexpr int P = R ? 2 : 1;
+  int chunk = std::min(s, 1024);
+  size_t smem = (size_t)chunk * STR * sizeof(double);
+  int grid = ceil_div(n, 256 * P);
+  FLGP_LAUNCH(c, (knn_small_kernel<D, R, P>), grid, 256, smem, X, n, ldx, rec, s, r, ind, dist, chunk, 1);
+}
 template <int D>
 void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, int s, int r,
                   int32_t* ind, double* dist) {
-  constexpr int STR = (D + 2) / 2 * 2;
-  int chunk = std::min(s, 1024);
-  size_t smem = (size_t)chunk * STR * sizeof(double);
-  int grid = ceil_div(n, 256);
-  FLGP_LAUNCH(c, (knn_small_kernel<D>), grid, 256, smem, X, n, ldx, rec, s, r, ind, dist, chunk);
+  switch (r) {
+    case 1: launch_small_r<D, 1>(c, X, n, ldx, rec, s, r, ind, dist); break;
+    case 2: launch_small_r<D, 2>(c, X, n, ldx, rec, s, r, ind, dist); break;
+    case 3: launch_small_r<D, 3>(c, X, n, ldx, rec, s, r, ind, dist); break;
+    case 4: launch_small_r<D, 4>(c, X, n, ldx, rec, s, r, ind, dist); break;
+    case 5: launch_small_r<D, 5>(c, X, n, ldx, rec, s, r, ind, dist); break;
+    default: launch_small_r<D, 0>(c, X, n, ldx, rec, s, r, ind, dist); break;
+  }
 }
 
 }  // namespace

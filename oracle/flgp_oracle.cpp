@@ -137,8 +137,11 @@ int orc_fx_decode(double maxabs, int64_t count, const int64_t* hi, const int64_t
 
 // =========================================================================================
 // k-means (Lloyd).  Contract replacing stats::kmeans at src/Utils.cpp:37-45.
-//   score(i,j) = fma(x_{d-1}, -2c_{j,d-1}, ... fma(x_0, -2c_{j,0}, |c_j|^2))   (= |x-c|^2 - |x|^2)
+//   score(i,j) = fma(x_{d-1}, -2c_{j,d-1}, ... fma(x_0, -2c_{j,0}, |c_j|^2 + M))   (= |x-c|^2 - |x|^2 + M)
 //   |c_j|^2    = fma chain over k ascending starting from 0
+//   M          = (2 d) maxabs^2 >= 2 |x|^2: a data-wide constant that keeps every score positive (the
+//                arg-min is unchanged; positive doubles order like their high words, which the CUDA
+//                kernel uses to keep the compare off the fp64 pipe)
 //   assign(i)  = argmin_j score, lowest j wins ties (strict <, j ascending)
 //   centroid   = decode(sum of fixed-point encodings) / count   (empty cluster keeps its centre)
 // acc layout (int64): hi[s*d] (j + s*k), lo[s*d], cnt[s], changed[1]  => 2*s*d + s + 1 words.
@@ -155,7 +158,7 @@ int orc_kmeans_step(const double* X, int64_t n, int64_t ldx, int d, const double
       a = std::fma(c, c, a);
       c2[(size_t)j * d + k] = -2.0 * c;
     }
-    cn[j] = a;
+    cn[j] = a + (2.0 * d) * (maxabs * maxabs);
   }
   const size_t words = (size_t)2 * s * d + s + 1;
   int T = std::max(1, nthreads);

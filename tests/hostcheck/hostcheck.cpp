@@ -30,6 +30,25 @@ void lae_fixed(const double* x, const double* U, double* z, int* it, int* bt) {
 }
 }  // namespace
 
+// the register-heap variant used by the small-d KNN kernel (compile-time r)
+template <int R>
+static void topr_reg(const double* row, int s, int32_t* ind, double* key) {
+  RegHeap<R> h;
+  for (int j = 0; j < R; ++j) h.set(j, row[j], j);
+  heap_make_acc(h, R);
+  double top = h.getk(0);
+  for (int j = R; j < s; ++j)
+    if (row[j] < top) {
+      heap_adjust_acc(h, 0, R, row[j], j);
+      top = h.getk(0);
+    }
+  heap_sort_acc(h, R);
+  for (int a = 0; a < R; ++a) {
+    ind[a] = h.geti(a);
+    key[a] = h.getk(a);
+  }
+}
+
 extern "C" {
 
 // the TopR state machine of knn.cu, fed a precomputed distance row in anchor order
@@ -56,6 +75,20 @@ void hc_topr(const double* row, int s, int r, int32_t* ind, double* key) {
     ind[a] = hi[a];
     key[a] = hk[a];
   }
+}
+
+int hc_topr_reg(const double* row, int s, int r, int32_t* ind, double* key) {
+  switch (r) {
+    case 1: topr_reg<1>(row, s, ind, key); return 0;
+    case 2: topr_reg<2>(row, s, ind, key); return 0;
+    case 3: topr_reg<3>(row, s, ind, key); return 0;
+    case 4: topr_reg<4>(row, s, ind, key); return 0;
+    case 5: topr_reg<5>(row, s, ind, key); return 0;
+    case 6: topr_reg<6>(row, s, ind, key); return 0;
+    case 7: topr_reg<7>(row, s, ind, key); return 0;
+    case 8: topr_reg<8>(row, s, ind, key); return 0;
+  }
+  return 1;
 }
 
 void hc_simplex(const double* v, int r, double* z) {

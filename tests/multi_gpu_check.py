@@ -1,0 +1,69 @@
+"""Multi-GPU invariance check, launched by torchrun (one process per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+
+Every rank runs its shard through the sharded C ABI; rank 0 also runs the whole matrix on one GPU (no
+communicator) and checks: k-means centres/sizes, Z pattern and values BIT-EXACT for any rank count (integer
+limb all-reduces); eigenvalues and predictions to 1e-10 (fp64 K x K all-reduce order differs)."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import flgp_b200 as F  # noqa: E402
+from flgp_b200.datasets import make, shard_bounds  # noqa: E402
+from flgp_b200.sharding import init_context_comm  # noqa: E402
+
+
+def main():
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n, m, s, r, K = 200_003, 700, 300, 3, 40
+    X, Y, _ = make("C4", 77, n=n)
+    lo, hi = shard_bounds(n, world, rank)
+    init = F.default_init(n, s, 5)
+    ctx = F.Context(local)
+    init_context_comm(ctx, rank, world)
+    ep = F.heat_kernel_spectrum_sharded(np.asfortranarray(X[lo:hi]), n, lo, s, r, K, init_idx=init, iter_max=30, ctx=ctx)
+    m_local = max(0, min(hi - lo, m - lo))
+    y, cov = F.regression_fixed(ep, Y[lo:lo + m_local], m, K, (10.0, 0.01), 1e-5)
+    U = ep.anchors()
+    Z = ep.Z()
+    vals = ep.values
+    iters = ep.kmeans_iters
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(lo=lo, hi=hi, U=U, Zj=Z.indices, Zx=Z.data, vals=vals, y=y, cov=cov,
+                                          iters=iters))
+    ok = True
+    if rank == 0:
+        ctx1 = F.Context(local)  # a second context in this process: no communicator, whole matrix
+        ep1 = F.heat_kernel_spectrum_sharded(X, n, 0, s, r, K, init_idx=init, iter_max=30, ctx=ctx1)
+        y1, cov1 = F.regression_fixed(ep1, Y[:m], m, K, (10.0, 0.01), 1e-5)
+        U1, Z1, v1 = ep1.anchors(), ep1.Z(), ep1.values
+        for g in gathered:
+            ok &= g["iters"] == ep1.kmeans_iters
+            ok &= np.array_equal(g["U"], U1)
+            ok &= np.allclose(g["vals"], v1, rtol=1e-10, atol=0)
+        Zj = np.concatenate([g["Zj"] for g in gathered])
+        Zx = np.concatenate([g["Zx"] for g in gathered])
+        ok &= np.array_equal(Zj, Z1.indices) and np.array_equal(Zx, Z1.data)
+        yy = np.concatenate([g["y"] for g in gathered])
+        cc = np.concatenate([g["cov"] for g in gathered])
+        e_y = np.abs(yy - y1).max() / np.abs(y1).max()
+        e_c = np.abs(cc - cov1).max() / max(1.0, np.abs(cov1).max())
+        ok &= e_y < 1e-9 and e_c < 1e-9
+        print("multi_gpu_check world=%d: iters=%d U/Z bit-exact=%s, dy=%.2e dcov=%.2e -> %s" %
+              (world, ep1.kmeans_iters, np.array_equal(Zx, Z1.data), e_y, e_c, "OK" if ok else "FAIL"))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -21,6 +21,14 @@ def _topr(hc, row, r):
     return ind, key
 
 
+def _topr_reg(hc, row, r):
+    row = np.ascontiguousarray(row, dtype=np.float64)
+    ind = np.zeros(r, np.int32)
+    key = np.zeros(r)
+    assert hc.hc_topr_reg(_pd(row), row.size, r, ind.ctypes.data_as(P(C.c_int32)), _pd(key)) == 0
+    return ind, key
+
+
 def _partial_sort_ref(oracle, row, r):
     """std::partial_sort through the oracle's KNN on a 1-D embedding that reproduces `row` exactly:
     x = 0, u_j = sqrt-free trick is not exact, so instead build distances directly with d=1, x=0:
@@ -45,6 +53,9 @@ def test_heap_emulation_matches_std_partial_sort_with_ties(hostcheck, oracle):
             gi, gk = _topr(hostcheck, D[i], r)
             assert np.array_equal(gi, ind[i]), (trial, i, gi, ind[i])
             assert np.array_equal(gk, dist[i])
+            if r <= 8:  # the register-resident heap of the small-d kernel
+                ri, rk = _topr_reg(hostcheck, D[i], r)
+                assert np.array_equal(ri, ind[i]) and np.array_equal(rk, dist[i])
             ties += len(np.unique(D[i])) < s
         assert ties > 0
 
