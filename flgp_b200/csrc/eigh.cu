@@ -42,25 +42,35 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // ---- 1. tridiagonalisation -----------------------------------------------------------------------
 // A: s x s symmetric, full storage (row i contiguous).  Vh: s x s, row k receives the Householder
 // vector of column k (v[0] = 1 at index 0, length s-k-1).  d (s), e (s-1), tau (s-1).
+//
+// One pass over the trailing matrix and ONE grid barrier per column: the rank-2 update of column k-1
+// (v_{k-1}, w_{k-1}, kept in shared memory by every CTA) is applied while the product A v_k of column k is
+// accumulated from the freshly updated values.  Column k itself is formed redundantly by every CTA from
+// row k in memory minus the pending update, so no barrier is needed between the Householder vector and
+// the pass.  pbuf is double-buffered by the parity of k.
 __global__ void __launch_bounds__(TD_THREADS)
 tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* __restrict__ dd, double* __restrict__ ee,
                double* __restrict__ tau_out, double* __restrict__ pbuf) {
   cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) double sm[];
-  double* vs = sm;           // s
-  double* ws = sm + s;       // s
-  double* red = sm + 2 * s;  // 32
+  double* vp = sm;           // s: pending v_{k-1}; entry q <-> global index k + q
+  double* wp = sm + s;       // s: pending w_{k-1}
+  double* vs = sm + 2 * s;   // s: current  v_k;     entry q <-> global index k + 1 + q
+  double* red = sm + 3 * s;  // 32
   const int tid = threadIdx.x, lane = tid & 31;
   const int gwarp = (blockIdx.x * TD_THREADS + tid) >> 5;
   const int nwarp = (gridDim.x * TD_THREADS) >> 5;
+  bool pending = false;      // is there an update (vp, wp) not yet applied to memory?
 
   for (int k = 0; k < s - 1; ++k) {
-    const int m = s - k - 1;                      // length of the column below the diagonal
-    const double* xrow = A + (size_t)k * s + (k + 1);
-    // --- phase A (redundant in every CTA): Householder vector of column k
+    const int m = s - k - 1;  // length of column k below the diagonal
+    const double* arow = A + (size_t)k * s;
+    // --- column k of the up-to-date matrix: memory row k minus the pending rank-2 update (redundant per CTA)
+    const double v0 = pending ? vp[0] : 0.0, w0 = pending ? wp[0] : 0.0;
     double part = 0.0;
     for (int j = tid; j < m; j += TD_THREADS) {
-      double x = xrow[j];
+      double x = arow[k + 1 + j];
+      if (pending) x = __dsub_rn(x, __dadd_rn(__dmul_rn(v0, wp[j + 1]), __dmul_rn(w0, vp[j + 1])));
       vs[j] = x;
       if (j > 0) part = fma(x, x, part);
     }
@@ -82,45 +92,50 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
     __syncthreads();
     if (blockIdx.x == 0) {
       if (tid == 0) {
-        dd[k] = A[(size_t)k * s + k];
+        double dk = arow[k];
+        if (pending) dk = __dsub_rn(dk, __dadd_rn(__dmul_rn(v0, w0), __dmul_rn(w0, v0)));
+        dd[k] = dk;
         ee[k] = beta;
         tau_out[k] = tau;
-        if (k == s - 2) dd[s - 1] = A[(size_t)(s - 1) * s + (s - 1)];
       }
       for (int j = tid; j < m; j += TD_THREADS) Vh[(size_t)k * s + j] = vs[j];
     }
-    if (tau == 0.0) continue;  // uniform across the grid: H = I, nothing to update
-    // --- phase B: p = tau * A22 v, one warp per row
+    // --- fused pass: apply the pending update to rows k+1.., accumulate p = tau * A22 v_k (one warp per row)
+    double* pk = pbuf + (size_t)(k & 1) * s;
     for (int row = gwarp; row < m; row += nwarp) {
-      const double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
+      double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
+      const double vi = pending ? vp[row + 1] : 0.0, wi = pending ? wp[row + 1] : 0.0;
       double acc = 0.0;
-      for (int j = lane; j < m; j += 32) acc = fma(ar[j], vs[j], acc);
+      for (int j = lane; j < m; j += 32) {
+        double a = ar[j];
+        if (pending) {
+          a = __dsub_rn(a, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
+          ar[j] = a;
+        }
+        acc = fma(a, vs[j], acc);
+      }
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) pbuf[row] = tau * acc;
+      if (lane == 0) pk[row] = tau * acc;
     }
     grid.sync();
-    // --- phase C (redundant): w = p - (tau/2)(p.v) v
+    // --- w_k = p - (tau/2)(p.v) v ; (v_k, w_k) become the pending update
     part = 0.0;
     for (int j = tid; j < m; j += TD_THREADS) {
-      double p = pbuf[j];
-      ws[j] = p;
+      double p = pk[j];
+      wp[j] = p;
       part = fma(p, vs[j], part);
     }
     const double pv = block_sum(part, red);
     const double a2 = -0.5 * tau * pv;
-    for (int j = tid; j < m; j += TD_THREADS) ws[j] = fma(a2, vs[j], ws[j]);
-    __syncthreads();
-    // --- phase D: A22 -= v w^T + w v^T (symmetric rounding: separate products, one add)
-    for (int row = gwarp; row < m; row += nwarp) {
-      double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
-      const double vi = vs[row], wi = ws[row];
-      for (int j = lane; j < m; j += 32) {
-        double t = __dadd_rn(__dmul_rn(vi, ws[j]), __dmul_rn(wi, vs[j]));
-        ar[j] = __dsub_rn(ar[j], t);
-      }
+    for (int j = tid; j < m; j += TD_THREADS) {
+      wp[j] = fma(a2, vs[j], wp[j]);
+      vp[j] = vs[j];
     }
-    grid.sync();
+    pending = true;
+    __syncthreads();
   }
+  // the last pending update has tau == 0 (a 1 x 1 column): memory already holds the final corner
+  if (blockIdx.x == 0 && tid == 0) dd[s - 1] = A[(size_t)(s - 1) * s + (s - 1)];
 }
 
 // ---- 2. eigenvalues: multisection on the Sturm count ------------------------------------------------
@@ -252,18 +267,34 @@ invit_solve_kernel(int s, int K, const double* __restrict__ dg, const double* __
   const int kk = blockIdx.x * blockDim.x + threadIdx.x;
   if (kk >= K) return;
 #define AT(i) ((size_t)(i) * K + kk)
+  // Both sweeps are sequential recurrences; their operands are fetched eight steps ahead so that the chain
+  // waits on arithmetic, not on L2 round trips.
+  constexpr int PF = 8;
   // forward: L with interchanges
   double bi = X[AT(0)];
   double nrm = 0.0;
-  for (int i = 0; i < s - 1; ++i) {
-    double bn = X[AT(i + 1)];
-    if (piv[AT(i)]) {
-      X[AT(i)] = bn;
-      bi = bi - dl[AT(i)] * bn;
-    } else {
-      X[AT(i)] = bi;
-      bi = bn - dl[AT(i)] * bi;
-    }
+  for (int i0 = 0; i0 < s - 1; i0 += PF) {
+    const int cnt = min(PF, s - 1 - i0);
+    double l[PF], xn[PF];
+    unsigned char pv[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < cnt) {
+        l[u] = dl[AT(i0 + u)];
+        pv[u] = piv[AT(i0 + u)];
+        xn[u] = X[AT(i0 + u + 1)];
+      }
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < cnt) {
+        if (pv[u]) {
+          X[AT(i0 + u)] = xn[u];
+          bi = bi - l[u] * xn[u];
+        } else {
+          X[AT(i0 + u)] = bi;
+          bi = xn[u] - l[u] * bi;
+        }
+      }
   }
   X[AT(s - 1)] = bi;
   // backward: U with two super-diagonals
@@ -271,12 +302,26 @@ invit_solve_kernel(int s, int K, const double* __restrict__ dg, const double* __
   X[AT(s - 1)] = x1;
   nrm = fma(x1, x1, nrm);
   double x2 = 0.0;
-  for (int i = s - 2; i >= 0; --i) {
-    double xi = (X[AT(i)] - du[AT(i)] * x1 - du2[AT(i)] * x2) / dg[AT(i)];
-    X[AT(i)] = xi;
-    nrm = fma(xi, xi, nrm);
-    x2 = x1;
-    x1 = xi;
+  for (int i0 = s - 2; i0 >= 0; i0 -= PF) {
+    const int cnt = min(PF, i0 + 1);
+    double g[PF], u1[PF], u2[PF], b[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < cnt) {
+        g[u] = dg[AT(i0 - u)];
+        u1[u] = du[AT(i0 - u)];
+        u2[u] = du2[AT(i0 - u)];
+        b[u] = X[AT(i0 - u)];
+      }
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (u < cnt) {
+        double xi = (b[u] - u1[u] * x1 - u2[u] * x2) / g[u];
+        X[AT(i0 - u)] = xi;
+        nrm = fma(xi, xi, nrm);
+        x2 = x1;
+        x1 = xi;
+      }
   }
   // normalise (guards against overflow in the next solve); clusters are re-orthogonalised next
   const double inv = 1.0 / sqrt(nrm);
@@ -342,7 +387,7 @@ backtransform_kernel(int s, int K, const double* __restrict__ Vh, const double* 
 
 void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   if (K < 1 || K > s) fail(2, "eigh: need 1 <= K <= s (K=%d, s=%d)", K, s);
-  DevBuf<double> dd(s), ee(s), tau(s), pbuf(s), tnorm(1);
+  DevBuf<double> dd(s), ee(s), tau(s), pbuf((size_t)2 * s), tnorm(1);
   ee.zero(c->stream);
   tau.zero(c->stream);
   if (s == 1) {
@@ -355,7 +400,7 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   DevBuf<double> Vh((size_t)s * s);
   // 1. tridiagonalisation (cooperative, persistent)
   {
-    size_t smem = (size_t)(2 * s + 32) * sizeof(double);
+    size_t smem = (size_t)(3 * s + 32) * sizeof(double);
     FLGP_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, TD_THREADS, smem));

@@ -11,6 +11,7 @@
 // (SURVEY.md §8d); bytes 8d + 4 per point (negligible: intensity = s/4 flop/byte).
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 
 #include "kernels.cuh"
 
@@ -278,6 +279,142 @@ __global__ void kmeans_init_kernel(const double* __restrict__ X, int64_t n_local
   if (i >= 0 && i < n_local) Cbits[j + (size_t)s * k] = __double_as_longlong(X[i + ldx * k]);
 }
 
+// ---- exact pruned iterations (small d) ------------------------------------------------------------------
+// After the first brute-force pass every point knows a centre a (its previous assignment).  With
+// ub >= |x - c_a| (true distance), a centre j with |c_a - c_j| >= 2 ub + eta satisfies
+//   |x - c_j| >= |c_a - c_j| - |x - c_a| >= |x - c_a| + eta   =>   score_j - score_a >= eta^2 > 2 Delta,
+// where Delta bounds the rounding error of a computed score, so the COMPUTED score of j is strictly larger
+// than that of a: j can neither win nor tie.  Scanning only {a} + {j : |c_a - c_j| < 2 R_a + eta}
+// (R_a = max ub over the members of a) therefore returns exactly the arg-min of the brute-force scan,
+// including its lowest-index tie rule.  Sums are integer limbs, so a reassignment is an exact -x / +x.
+constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster falls back to the full scan
+
+template <int D>
+__global__ void __launch_bounds__(256)
+kmeans_radius_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec,
+                     const int32_t* __restrict__ assign, double M, double delta2, unsigned long long* __restrict__ Rbits) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int a = assign[i];
+  const double* ra = rec + (size_t)a * STR;
+  double e = ra[D], xn = 0.0;
+#pragma unroll
+  for (int k = 0; k < D; ++k) {
+    const double x = X[i + ldx * k];
+    e = fma(x, ra[k], e);
+    xn = fma(x, x, xn);
+  }
+  const double d2 = fmax((e - M) + xn, 0.0) + delta2;    // >= true squared distance
+  const double ub = sqrt(d2) * (1.0 + 1e-14);
+  atomicMax(&Rbits[a], (unsigned long long)__double_as_longlong(ub));  // non-negative doubles order like their bits
+}
+
+__global__ void __launch_bounds__(128)
+kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned long long* __restrict__ Rbits, double eta,
+                    int32_t* __restrict__ list, int32_t* __restrict__ len) {
+  __shared__ int count;
+  const int a = blockIdx.x;
+  if (threadIdx.x == 0) count = 0;
+  __syncthreads();
+  const double Ra = __longlong_as_double((long long)Rbits[a]);
+  const double thr = (2.0 * Ra + eta) * (1.0 + 1e-9);   // inflated: keeping more centres is always safe
+  for (int j = threadIdx.x; j < s; j += 128) {
+    if (j == a) continue;
+    double cc = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
+      cc = fma(df, df, cc);
+    }
+    if (sqrt(cc) < thr) {
+      const int pos = atomicAdd(&count, 1);
+      if (pos < KM_LMAX) list[(size_t)a * KM_LMAX + pos] = j;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) len[a] = (count <= KM_LMAX) ? count : -1;
+}
+
+template <int D>
+__global__ void __launch_bounds__(256)
+kmeans_assign_pruned(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s, Fx fx,
+                     int32_t* __restrict__ assign, unsigned long long* __restrict__ acc,
+                     const int32_t* __restrict__ list, const int32_t* __restrict__ len) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  int changed = 0;
+  if (i < n) {
+    double x[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = X[i + ldx * k];
+    const int a = assign[i];
+    auto score = [&](int j) {
+      const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
+      double cr[STR];
+#pragma unroll
+      for (int q = 0; q < STR / 2; ++q) {
+        double2 t = rj[q];
+        cr[2 * q] = t.x;
+        cr[2 * q + 1] = t.y;
+      }
+      double e = cr[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) e = fma(x[k], cr[k], e);
+      return e;
+    };
+    double best = score(a);
+    int bj = a;
+    const int L = len[a];
+    if (L >= 0) {
+      const int32_t* la = list + (size_t)a * KM_LMAX;
+      for (int q = 0; q < L; ++q) {
+        const int j = la[q];
+        const double e = score(j);
+        if (e < best || (e == best && j < bj)) {
+          best = e;
+          bj = j;
+        }
+      }
+    } else {  // list overflow: full scan for this cluster's members (rare)
+      for (int j = 0; j < s; ++j) {
+        const double e = score(j);
+        if (e < best || (e == best && j < bj)) {
+          best = e;
+          bj = j;
+        }
+      }
+    }
+    if (bj != a) {
+      changed = 1;
+      assign[i] = bj;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        long long h, l;
+        fx_encode(fx, x[k], &h, &l);
+        atomicAdd(&acc[a + (size_t)s * k], (unsigned long long)(-h));
+        atomicAdd(&acc[(size_t)s * D + a + (size_t)s * k], (unsigned long long)(-l));
+        atomicAdd(&acc[bj + (size_t)s * k], (unsigned long long)h);
+        atomicAdd(&acc[(size_t)s * D + bj + (size_t)s * k], (unsigned long long)l);
+      }
+      atomicAdd(&acc[(size_t)2 * s * D + a], (unsigned long long)(-1ll));
+      atomicAdd(&acc[(size_t)2 * s * D + bj], 1ull);
+    }
+  }
+  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  if ((threadIdx.x & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
+}
+
+template <int D>
+void launch_pruned(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, const double* C, int s,
+                   const Fx& fx, int32_t* assign, unsigned long long* acc, double M, double delta2, double eta,
+                   unsigned long long* Rbits, int32_t* list, int32_t* len) {
+  FLGP_CUDA(cudaMemsetAsync(Rbits, 0, sizeof(unsigned long long) * s, c->stream));
+  const int grid = ceil_div(n, 256);
+  if (grid > 0) FLGP_LAUNCH(c, (kmeans_radius_kernel<D>), grid, 256, 0, X, n, ldx, rec, assign, M, delta2, Rbits);
+  FLGP_LAUNCH(c, kmeans_lists_kernel, s, 128, 0, C, s, D, Rbits, eta, list, len);
+  if (grid > 0) FLGP_LAUNCH(c, (kmeans_assign_pruned<D>), grid, 256, 0, X, n, ldx, rec, s, fx, assign, acc, list, len);
+}
+
 template <int D>
 void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, int s, const Fx& fx,
                   int32_t* assign, unsigned long long* acc) {
@@ -338,16 +475,40 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     cn.alloc(s);
   }
   unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc.p);
+  // pruned iterations (small d): persistent local accumulators + neighbour lists; see the proof above
+  const bool pruned = small && n_total >= 2;
+  const double bound = Moff + 4.0 * d * (maxabs * maxabs);                    // >= |score| terms
+  const double Delta = 8.0 * (d + 4) * 1.1102230246251565e-16 * bound;        // generous bound on a score's rounding error
+  const double delta2 = 4.0 * Delta;                                          // slack added to squared distances
+  const double eta = 2.0 * std::sqrt(2.0 * Delta) + 1e-12 * maxabs;           // eta^2 > 2 Delta with room to spare
+  DevBuf<unsigned long long> Rbits;
+  DevBuf<int32_t> nlist, nlen;
+  DevBuf<long long> acc_red;  // all-reduced copy of the local accumulators (multi-GPU)
+  if (pruned) {
+    Rbits.alloc(s);
+    nlist.alloc((size_t)s * KM_LMAX);
+    nlen.alloc(s);
+    if (c->nranks > 1) acc_red.alloc(words);
+  }
   int it = 0;
   while (it < iter_max) {
     ++it;
-    acc.zero(c->stream);
+    const bool brute = !pruned || it == 1;
+    if (brute) acc.zero(c->stream);
+    else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
-    // when timing is on, the assign+accumulate kernel gets its own CUDA-event pair per iteration:
-    // this is the dominant kernel whose roofline bench.py reports
-    StageScope kst(c, "kmeans_assign_kernel", 2.0 * s * d * (double)n_local, (8.0 * d + 4.0) * (double)n_local);
-    if (small) {
+    // when timing is on, the assign+accumulate work gets its own CUDA-event pair per iteration
+    StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_iteration", 2.0 * s * d * (double)n_local,
+                   (8.0 * d + 4.0) * (double)n_local);
+    if (!brute) {
+      switch (d) {
+        case 1: launch_pruned<1>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
+        case 2: launch_pruned<2>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
+        case 3: launch_pruned<3>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
+        default: launch_pruned<4>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
+      }
+    } else if (small) {
       switch (d) {
         case 1: launch_small<1>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
         case 2: launch_small<2>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
@@ -360,10 +521,14 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
         FLGP_LAUNCH(c, kmeans_assign_tiled, grid, 256, 0, X, n_local, ldx, d, C2.p, cn.p, s, fx, assign, uacc);
     }
     kst.stop();
-    comm_allreduce_i64(c, reinterpret_cast<int64_t*>(acc.p), words);
-    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s * d, 256), 256, 0, acc.p, s, d, fx, C, sizes);
-    FLGP_CUDA(cudaMemcpyAsync(c->pinned, acc.p + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost,
-                              c->stream));
+    long long* red = acc.p;
+    if (pruned && c->nranks > 1) {  // keep the local sums intact; reduce a copy
+      FLGP_CUDA(cudaMemcpyAsync(acc_red.p, acc.p, sizeof(long long) * words, cudaMemcpyDeviceToDevice, c->stream));
+      red = acc_red.p;
+    }
+    comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
+    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s * d, 256), 256, 0, red, s, d, fx, C, sizes);
+    FLGP_CUDA(cudaMemcpyAsync(c->pinned, red + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     sync(c);
     if (c->pinned[0] == 0) break;  // no assignment changed anywhere
   }
