@@ -1,0 +1,188 @@
+// flgp_shim.cpp — Rcpp glue that a maintainer of junhuihe2000/FLGP drops into the R package's src/
+// directory IN PLACE OF the bodies of the spectral-core functions, keeping every [[Rcpp::export]] signature
+// (and therefore R/RcppExports.R, NAMESPACE, man/, R/Fit.R) unchanged.  Each function marshals R's
+// column-major REALSXP / INTSXP buffers straight into the C ABI of include/flgp.h (no copies on the way in:
+// Eigen::Map aliases R memory exactly as the reference does at src/Fit.cpp:29-32) and turns a non-zero
+// status into Rcpp::stop, the reference's own error convention (src/Utils.cpp:64,123,207).
+//
+// NOT COMPILED IN THIS REPOSITORY: the build environment has no R, Rcpp or RcppEigen.  It
+// is kept deliberately thin so that review suffices; the same entry points are exercised through ctypes by
+// flgp_b200/api.py and the -m gpu tests.  Link with: PKG_LIBS += -L<dir> -lflgp_b200  (see INTEGRATION.md).
+//
+// Replaces (file:line in the reference):
+//   subsample_cpp                 src/Utils.cpp:32-68          -> flgp_subsample
+//   KNN_cpp                       src/Utils.cpp:102-192        -> flgp_knn
+//   graphLaplacian_cpp            src/Utils.cpp:195-212        -> flgp_graph_laplacian
+//   LAE_cpp / local_anchor_embedding_cpp / v_to_z_cpp  src/lae.cpp:48-153 -> flgp_lae / flgp_lae_point / flgp_simplex_project
+//   cross_similarity_{lae,se}_cpp src/Spectrum.cpp:101-142     -> flgp_cross_similarity_{lae,se}
+//   spectrum_from_Z_cpp           src/Spectrum.cpp:146-161     -> flgp_spectrum_from_z
+//   heat_kernel_spectrum_cpp      src/Spectrum.cpp:48-76       -> flgp_heat_kernel_spectrum
+//   HK_from_spectrum_cpp          src/Spectrum.cpp:83-94       -> flgp_hk_from_spectrum (handle) or Eigen as before
+//   lae_eigenmap                  src/Spectrum.cpp:17-25       -> flgp_lae_eigenmap
+//   heat_kernel_covariance_cpp    src/Spectrum.cpp:28-43       -> flgp_heat_kernel_covariance
+// [[Rcpp::depends(RcppEigen)]]
+#include <RcppEigen.h>
+
+#include "Spectrum.h"
+#include "Utils.h"
+#include "flgp.h"
+#include "lae.h"
+
+namespace {
+
+flgp_ctx* ctx() {  // one context per R session, created on first use
+  static flgp_ctx* c = nullptr;
+  if (!c && flgp_ctx_create(0, &c)) Rcpp::stop(flgp_last_error());
+  return c;
+}
+inline void ok(int rc) {
+  if (rc) Rcpp::stop(flgp_last_error());
+}
+int gl_code(const std::string& gl) {
+  if (gl == "rw") return FLGP_GL_RW;
+  if (gl == "normalized") return FLGP_GL_NORMALIZED;
+  if (gl == "cluster-normalized") return FLGP_GL_CLUSTER_NORMALIZED;
+  Rcpp::stop("Error: the type of graph Laplacian is not supported!");
+}
+// k-means needs explicit start rows (the reference lets stats::kmeans draw them from R's RNG):
+// draw them from R's RNG here too, so set.seed() keeps governing reproducibility.
+std::vector<int32_t> r_init(int n, int s) {
+  Rcpp::IntegerVector idx = Rcpp::sample(n, s);  // 1-based, without replacement
+  std::vector<int32_t> out(idx.begin(), idx.end());
+  for (auto& v : out) v -= 1;
+  std::sort(out.begin(), out.end());
+  return out;
+}
+// fixed-r CSR (Zj, Zx) -> Eigen row-major sparse matrix (the dgRMatrix the reference returns)
+Eigen::SparseMatrix<double, Eigen::RowMajor> to_sparse(int n, int s, int r, const std::vector<int32_t>& Zj,
+                                                       const std::vector<double>& Zx) {
+  Eigen::SparseMatrix<double, Eigen::RowMajor> Z(n, s);
+  Z.reserve(Eigen::VectorXi::Constant(n, r));
+  for (int i = 0; i < n; ++i)
+    for (int a = 0; a < r; ++a) Z.insert(i, Zj[(size_t)i * r + a]) = Zx[(size_t)i * r + a];
+  return Z;
+}
+
+}  // namespace
+
+Eigen::MatrixXd subsample_cpp(const Eigen::MatrixXd& X, int s, std::string method, int nstart) {
+  const int n = X.rows(), d = X.cols();
+  std::vector<int32_t> init = r_init(n, s);
+  Eigen::MatrixXd U(s, method == "kmeans" ? d + 1 : d);
+  ok(flgp_subsample(ctx(), X.data(), n, d, s, method.c_str(), 100, nstart, init.data(), 0, U.data(), nullptr, nullptr));
+  return U;
+}
+
+Rcpp::List KNN_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& U, int r, std::string distance, bool output,
+                   int /*batch: bounded the reference's working set only*/) {
+  if (distance != "Euclidean") Rcpp::stop("The distance method of KNN is not supported!\n");
+  const int n = X.rows(), d = X.cols(), s = U.rows();
+  Eigen::MatrixXi ind(n, r);
+  if (!output) {
+    ok(flgp_knn(ctx(), X.data(), n, d, U.data(), s, r, ind.data(), nullptr, nullptr, nullptr));
+    return Rcpp::List::create(Rcpp::Named("ind_knn") = ind);
+  }
+  std::vector<int32_t> Zj((size_t)n * r);
+  std::vector<double> Zx((size_t)n * r);
+  ok(flgp_knn(ctx(), X.data(), n, d, U.data(), s, r, ind.data(), nullptr, Zj.data(), Zx.data()));
+  return Rcpp::List::create(Rcpp::Named("ind_knn") = ind, Rcpp::Named("distances_sp") = to_sparse(n, s, r, Zj, Zx));
+}
+
+Eigen::RowVectorXd v_to_z_cpp(const Eigen::RowVectorXd& v) {
+  Eigen::RowVectorXd z(v.size());
+  ok(flgp_simplex_project(ctx(), v.data(), (int)v.size(), z.data()));
+  return z;
+}
+
+Eigen::RowVectorXd local_anchor_embedding_cpp(const Eigen::RowVectorXd& x, const Eigen::MatrixXd& U) {
+  Eigen::RowVectorXd z(U.rows());
+  ok(flgp_lae_point(ctx(), x.data(), (int)U.cols(), U.data(), (int)U.rows(), z.data()));
+  return z;
+}
+
+Eigen::SparseMatrix<double, Eigen::RowMajor> LAE_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& U, int r) {
+  const int n = X.rows(), s = U.rows();
+  std::vector<int32_t> Zj((size_t)n * r);
+  std::vector<double> Zx((size_t)n * r);
+  ok(flgp_lae(ctx(), X.data(), n, (int)X.cols(), U.data(), s, r, Zj.data(), Zx.data(), nullptr));
+  return to_sparse(n, s, r, Zj, Zx);
+}
+
+void graphLaplacian_cpp(Eigen::SparseMatrix<double, Eigen::RowMajor>& Z, std::string gl, const Eigen::VectorXd& num_class) {
+  Z.makeCompressed();
+  const int n = Z.rows(), s = Z.cols(), r = n ? Z.nonZeros() / n : 0;
+  ok(flgp_graph_laplacian(ctx(), n, s, r, Z.innerIndexPtr(), Z.valuePtr(), gl_code(gl),
+                          num_class.size() ? num_class.data() : nullptr));
+}
+
+static Eigen::SparseMatrix<double, Eigen::RowMajor> cross_similarity(const Eigen::MatrixXd& X, const Eigen::MatrixXd& U, int r,
+                                                                    const std::string& gl, bool se, double epsilon) {
+  const int n = X.rows(), d = X.cols(), s = U.rows();
+  std::vector<int32_t> Zj((size_t)n * r);
+  std::vector<double> Zx((size_t)n * r);
+  ok(se ? flgp_cross_similarity_se(ctx(), X.data(), n, d, U.data(), s, (int)U.cols(), r, gl_code(gl), epsilon, Zj.data(), Zx.data())
+        : flgp_cross_similarity_lae(ctx(), X.data(), n, d, U.data(), s, (int)U.cols(), r, gl_code(gl), Zj.data(), Zx.data()));
+  return to_sparse(n, s, r, Zj, Zx);
+}
+Eigen::SparseMatrix<double, Eigen::RowMajor> cross_similarity_lae_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& U, int r,
+                                                                     Rcpp::String gl) {
+  return cross_similarity(X, U, r, gl, false, 0.1);
+}
+Eigen::SparseMatrix<double, Eigen::RowMajor> cross_similarity_se_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& U, int r,
+                                                                    Rcpp::String gl, double epsilon) {
+  return cross_similarity(X, U, r, gl, true, epsilon);
+}
+
+// EigenPair keeps its reference layout {values, vectors}; the n x K block is materialised once so that
+// train.cpp / Predict.cpp (out of scope) keep working unchanged.  Large-n callers use the handle API.
+static EigenPair from_handle(flgp_spectrum* h) {
+  int64_t info[10];
+  ok(flgp_spectrum_info(h, info));
+  Eigen::VectorXd values(info[6]);
+  Eigen::MatrixXd vectors(info[0], info[6]);
+  int rc = flgp_spectrum_values(h, values.data());
+  if (!rc) rc = flgp_spectrum_vectors(h, vectors.data());
+  flgp_spectrum_free(h);
+  ok(rc);
+  return EigenPair(values, vectors);
+}
+
+EigenPair spectrum_from_Z_cpp(const Eigen::SparseMatrix<double, Eigen::RowMajor>& Zin, int K, bool root) {
+  Eigen::SparseMatrix<double, Eigen::RowMajor> Z = Zin;
+  Z.makeCompressed();
+  const int n = Z.rows(), s = Z.cols(), r = n ? Z.nonZeros() / n : 0;
+  flgp_spectrum* h = nullptr;
+  ok(flgp_spectrum_from_z(ctx(), n, s, r, Z.innerIndexPtr(), Z.valuePtr(), K, root, nullptr, nullptr, &h));
+  return from_handle(h);
+}
+
+EigenPair heat_kernel_spectrum_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& X_new, int s, int r, int K,
+                                   const Rcpp::List& models, int nstart, double epsilon) {
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]), ker = Rcpp::as<std::string>(models["kernel"]);
+  std::vector<int32_t> init = r_init(X.rows() + X_new.rows(), s);
+  flgp_spectrum* h = nullptr;
+  ok(flgp_heat_kernel_spectrum(ctx(), X.data(), X.rows(), X_new.data(), X_new.rows(), (int)X.cols(), s, r, K, sub.c_str(),
+                               ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]),
+                               nstart, epsilon, 100, init.data(), 0, &h));
+  return from_handle(h);
+}
+
+Rcpp::List lae_eigenmap(const Eigen::MatrixXd& X, int s, int r, int ndim, std::string subsample, std::string norm, int nstart) {
+  std::vector<int32_t> init = r_init(X.rows(), s);
+  Eigen::VectorXd ev(ndim);
+  Eigen::MatrixXd V(X.rows(), ndim);
+  ok(flgp_lae_eigenmap(ctx(), X.data(), X.rows(), (int)X.cols(), s, r, ndim, subsample.c_str(), gl_code(norm), nstart, 100,
+                       init.data(), 0, ev.data(), V.data()));
+  return Rcpp::List::create(Rcpp::Named("eigenvalues") = ev, Rcpp::Named("eigenvectors") = V);
+}
+
+Eigen::MatrixXd heat_kernel_covariance_cpp(const Eigen::MatrixXd& X, const Eigen::MatrixXd& X_new, int s, int r, double t, int K,
+                                           Rcpp::List models, int nstart, double epsilon) {
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]), ker = Rcpp::as<std::string>(models["kernel"]);
+  std::vector<int32_t> init = r_init(X.rows() + X_new.rows(), s);
+  Eigen::MatrixXd H(X.rows() + X_new.rows(), X.rows());
+  ok(flgp_heat_kernel_covariance(ctx(), X.data(), X.rows(), X_new.data(), X_new.rows(), (int)X.cols(), s, r, t, K, sub.c_str(),
+                                 ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]),
+                                 nstart, epsilon, 100, init.data(), 0, H.data()));
+  return H;
+}
