@@ -8,9 +8,20 @@ namespace flgp {
 // ---- kmeans.cu -------------------------------------------------------------------------------
 // Lloyd iterations on this rank's rows; centroid sums are all-reduced (int64 limbs).
 // U: s x (d+1) column-major (centres, sizes).  assign: n_local (scratch/out).
+// Cluster-sorted layout left behind by the pruned passes (d <= 4): position p holds original row perm[p];
+// as[p] is a centre close to that row (its final assignment), Rbits[a] + move[a] bounds |x - U_a| over the
+// rows with as == a.  The KNN stage reuses it for exact candidate pruning.
+struct KMeansSorted {
+  bool valid = false;
+  DevBuf<double> Xs;                 // n_local x d, column-major, ld n_local
+  DevBuf<int32_t> perm, as;
+  DevBuf<unsigned long long> Rbits;  // bit patterns of non-negative doubles
+  DevBuf<double> move;
+  double eta = 0.0;
+};
 void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, int s, int64_t n_total,
                 int64_t row_offset, const int32_t* init_idx_h, int iter_max, double* U, int32_t* assign,
-                int* iters_out);
+                int* iters_out, KMeansSorted* sorted_out = nullptr);
 double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);  // all-reduced, host value
 
 // ---- knn.cu ----------------------------------------------------------------------------------

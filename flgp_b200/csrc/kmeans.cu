@@ -65,6 +65,14 @@ __global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, in
   cn[j] = __dadd_rn(a, M);
 }
 
+// upper bound on the true distance |x - c_j| from a computed score (score = |x-c|^2 - |x|^2 + M up to rounding)
+__device__ __forceinline__ double km_ub(double score, double M, double xn, double delta2) {
+  return sqrt(fmax((score - M) + xn, 0.0) + delta2) * (1.0 + 1e-14);
+}
+__device__ __forceinline__ void km_radius(unsigned long long* Rbits, int a, double ub) {
+  atomicMax(&Rbits[a], (unsigned long long)__double_as_longlong(ub));  // non-negative doubles order like their bits
+}
+
 __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, const double* x, int32_t* assign,
                                           int64_t i, unsigned long long* acc, int& changed) {
   if (assign[i] != bj) ++changed;
@@ -82,7 +90,8 @@ __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, co
 template <int D, int P>
 __global__ void __launch_bounds__(KM_THREADS)
 kmeans_assign_small(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s,
-                    Fx fx, int32_t* __restrict__ assign, unsigned long long* __restrict__ acc, int chunk, int one) {
+                    Fx fx, int32_t* __restrict__ assign, unsigned long long* __restrict__ acc, int chunk, int one,
+                    unsigned long long* __restrict__ Rbits, double M, double delta2) {
   constexpr int STR = (D + 2) / 2 * 2;
   extern __shared__ __align__(16) double srec[];
   const int tid = threadIdx.x;
@@ -151,7 +160,15 @@ kmeans_assign_small(const double* __restrict__ X, int64_t n, int64_t ldx, const 
 #pragma unroll
   for (int p = 0; p < P; ++p) {
     int64_t i = base + (int64_t)p * KM_THREADS + tid;
-    if (i < n) km_commit(fx, s, D, bj[p], x[p], assign, i, acc, changed);
+    if (i < n) {
+      km_commit(fx, s, D, bj[p], x[p], assign, i, acc, changed);
+      if (Rbits) {  // cluster radius for the pruned passes that follow
+        double xn = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) xn = fma(x[p][k], x[p][k], xn);
+        km_radius(Rbits, bj[p], km_ub(best[p], M, xn, delta2));
+      }
+    }
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
   if ((tid & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
@@ -257,16 +274,24 @@ kmeans_assign_tiled(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
   if ((tid & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * d + s], (unsigned long long)changed);
 }
 
-__global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, int d, Fx fx, double* C,
-                                     double* sizes) {
-  int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= s * d) return;
-  int j = e % s, k = e / s;
+// centroid update, one thread per centre; move[j] >= |c_new - c_old| (for the pruned passes' radius bound)
+__global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, int d, Fx fx, double* C, double* sizes,
+                                     double* move) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= s) return;
   long long cnt = acc[(size_t)2 * s * d + j];
-  if (k == 0) sizes[j] = (double)cnt;
-  if (cnt == 0) return;  // empty cluster keeps its centre
-  double sum = fx_decode(fx, acc[j + (size_t)s * k], acc[(size_t)s * d + j + (size_t)s * k]);
-  C[j + (size_t)s * k] = sum / (double)cnt;
+  sizes[j] = (double)cnt;
+  double mv = 0.0;
+  if (cnt != 0) {  // an empty cluster keeps its centre
+    for (int k = 0; k < d; ++k) {
+      double sum = fx_decode(fx, acc[j + (size_t)s * k], acc[(size_t)s * d + j + (size_t)s * k]);
+      double cnew = sum / (double)cnt;
+      double df = cnew - C[j + (size_t)s * k];
+      mv = fma(df, df, mv);
+      C[j + (size_t)s * k] = cnew;
+    }
+  }
+  if (move) move[j] = sqrt(mv) * (1.0 + 1e-12);
 }
 
 // rows of X that this rank owns -> bit patterns in the (zeroed) centre buffer
@@ -279,75 +304,109 @@ __global__ void kmeans_init_kernel(const double* __restrict__ X, int64_t n_local
   if (i >= 0 && i < n_local) Cbits[j + (size_t)s * k] = __double_as_longlong(X[i + ldx * k]);
 }
 
-// ---- exact pruned iterations (small d) ------------------------------------------------------------------
+// ---- exact pruned passes on cluster-sorted points (small d) -------------------------------------------
 // After the first brute-force pass every point knows a centre a (its previous assignment).  With
 // ub >= |x - c_a| (true distance), a centre j with |c_a - c_j| >= 2 ub + eta satisfies
 //   |x - c_j| >= |c_a - c_j| - |x - c_a| >= |x - c_a| + eta   =>   score_j - score_a >= eta^2 > 2 Delta,
 // where Delta bounds the rounding error of a computed score, so the COMPUTED score of j is strictly larger
-// than that of a: j can neither win nor tie.  Scanning only {a} + {j : |c_a - c_j| < 2 R_a + eta}
-// (R_a = max ub over the members of a) therefore returns exactly the arg-min of the brute-force scan,
-// including its lowest-index tie rule.  Sums are integer limbs, so a reassignment is an exact -x / +x.
-constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster falls back to the full scan
+// than that of a: j can neither win nor tie.  Scanning {a} + {j : |c_a - c_j| < 2 ub + eta} therefore returns
+// exactly the arg-min of the brute-force scan, including its lowest-index tie rule.
+//   * per centre: candidates within 2 R_a + eta, SORTED by centre-centre distance (R_a >= every member's ub:
+//     max ub of the previous pass + how far the centre has moved since);
+//   * per point: walk that list until the centre-centre distance exceeds 2 ub_i + eta (its own bound);
+//   * points are kept sorted by cluster (a permutation + a gathered copy of X), so a warp walks ONE list and
+//     every list / record load is a broadcast; the order is refreshed when enough points have moved;
+//   * sums are integer limbs, so a reassignment is an exact -x / +x on persistent accumulators.
+constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster's members scan everything
 
-template <int D>
 __global__ void __launch_bounds__(256)
-kmeans_radius_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec,
-                     const int32_t* __restrict__ assign, double M, double delta2, unsigned long long* __restrict__ Rbits) {
-  constexpr int STR = (D + 2) / 2 * 2;
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int a = assign[i];
-  const double* ra = rec + (size_t)a * STR;
-  double e = ra[D], xn = 0.0;
-#pragma unroll
-  for (int k = 0; k < D; ++k) {
-    const double x = X[i + ldx * k];
-    e = fma(x, ra[k], e);
-    xn = fma(x, x, xn);
-  }
-  const double d2 = fmax((e - M) + xn, 0.0) + delta2;    // >= true squared distance
-  const double ub = sqrt(d2) * (1.0 + 1e-14);
-  atomicMax(&Rbits[a], (unsigned long long)__double_as_longlong(ub));  // non-negative doubles order like their bits
-}
-
-__global__ void __launch_bounds__(128)
-kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned long long* __restrict__ Rbits, double eta,
-                    int32_t* __restrict__ list, int32_t* __restrict__ len) {
+kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned long long* __restrict__ Rprev,
+                    const double* __restrict__ move, double eta, int32_t* __restrict__ list_j,
+                    double* __restrict__ list_cc, int32_t* __restrict__ len) {
+  __shared__ double kcc[KM_LMAX];
+  __shared__ int kj[KM_LMAX];
   __shared__ int count;
-  const int a = blockIdx.x;
-  if (threadIdx.x == 0) count = 0;
+  const int a = blockIdx.x, tid = threadIdx.x;
+  if (tid == 0) count = 0;
+  for (int t = tid; t < KM_LMAX; t += 256) {
+    kcc[t] = INFINITY;
+    kj[t] = 0x7fffffff;
+  }
   __syncthreads();
-  const double Ra = __longlong_as_double((long long)Rbits[a]);
-  const double thr = (2.0 * Ra + eta) * (1.0 + 1e-9);   // inflated: keeping more centres is always safe
-  for (int j = threadIdx.x; j < s; j += 128) {
+  const double Ra = __longlong_as_double((long long)Rprev[a]) + move[a];
+  const double thr = (2.0 * Ra + eta) * (1.0 + 1e-9);  // inflated: keeping more centres is always safe
+  for (int j = tid; j < s; j += 256) {
     if (j == a) continue;
     double cc = 0.0;
     for (int k = 0; k < d; ++k) {
       const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
       cc = fma(df, df, cc);
     }
-    if (sqrt(cc) < thr) {
+    cc = sqrt(cc);
+    if (cc < thr) {
       const int pos = atomicAdd(&count, 1);
-      if (pos < KM_LMAX) list[(size_t)a * KM_LMAX + pos] = j;
+      if (pos < KM_LMAX) {
+        kcc[pos] = cc;
+        kj[pos] = j;
+      }
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) len[a] = (count <= KM_LMAX) ? count : -1;
+  const int cnt = count;
+  if (cnt > KM_LMAX) {
+    if (tid == 0) len[a] = -1;
+    return;
+  }
+  // bitonic sort of (cc, j) ascending; padding is (+inf, INT_MAX); ties broken by j => deterministic lists
+  int npow = 1;
+  while (npow < cnt) npow <<= 1;
+  for (int k2 = 2; k2 <= npow; k2 <<= 1)
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = tid; t < npow; t += 256) {
+        const int u = t ^ j2;
+        if (u > t) {
+          const bool up = (t & k2) == 0;
+          const double c0 = kcc[t], c1 = kcc[u];
+          const int i0 = kj[t], i1 = kj[u];
+          const bool gt = (c0 > c1) || (c0 == c1 && i0 > i1);
+          if (gt == up) {
+            kcc[t] = c1;
+            kcc[u] = c0;
+            kj[t] = i1;
+            kj[u] = i0;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int t = tid; t < cnt; t += 256) {
+    list_j[(size_t)a * KM_LMAX + t] = kj[t];
+    list_cc[(size_t)a * KM_LMAX + t] = kcc[t];
+  }
+  if (tid == 0) len[a] = cnt;
 }
 
 template <int D>
 __global__ void __launch_bounds__(256)
-kmeans_assign_pruned(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s, Fx fx,
-                     int32_t* __restrict__ assign, unsigned long long* __restrict__ acc,
-                     const int32_t* __restrict__ list, const int32_t* __restrict__ len) {
+kmeans_assign_pruned(const double* __restrict__ Xs, int64_t n, const double* __restrict__ rec, int s, Fx fx,
+                     int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
+                     const double* __restrict__ list_cc, const int32_t* __restrict__ len, double M, double delta2,
+                     double eta, unsigned long long* __restrict__ Rcur, const int32_t* __restrict__ strag,
+                     const int* __restrict__ nstrag) {
+  // generic path: one thread per straggler (a point that left its sorted segment, or whose staged list was
+  // too short); walks its own list from global memory
   constexpr int STR = (D + 2) / 2 * 2;
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   int changed = 0;
-  if (i < n) {
-    double x[D];
+  const int total = *nstrag;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int64_t p = strag[idx];
+    double x[D], xn = 0.0;
 #pragma unroll
-    for (int k = 0; k < D; ++k) x[k] = X[i + ldx * k];
-    const int a = assign[i];
+    for (int k = 0; k < D; ++k) {
+      x[k] = Xs[p + n * k];
+      xn = fma(x[k], x[k], xn);
+    }
+    const int a = as[p];
     auto score = [&](int j) {
       const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
       double cr[STR];
@@ -364,18 +423,21 @@ kmeans_assign_pruned(const double* __restrict__ X, int64_t n, int64_t ldx, const
     };
     double best = score(a);
     int bj = a;
+    const double thr = (2.0 * km_ub(best, M, xn, delta2) + eta) * (1.0 + 1e-9);
     const int L = len[a];
     if (L >= 0) {
-      const int32_t* la = list + (size_t)a * KM_LMAX;
+      const int32_t* lj = list_j + (size_t)a * KM_LMAX;
+      const double* lc = list_cc + (size_t)a * KM_LMAX;
       for (int q = 0; q < L; ++q) {
-        const int j = la[q];
+        if (lc[q] >= thr) break;  // sorted by centre-centre distance: nothing further can win or tie
+        const int j = lj[q];
         const double e = score(j);
         if (e < best || (e == best && j < bj)) {
           best = e;
           bj = j;
         }
       }
-    } else {  // list overflow: full scan for this cluster's members (rare)
+    } else {  // list overflow: this cluster's members scan every centre (rare)
       for (int j = 0; j < s; ++j) {
         const double e = score(j);
         if (e < best || (e == best && j < bj)) {
@@ -385,8 +447,8 @@ kmeans_assign_pruned(const double* __restrict__ X, int64_t n, int64_t ldx, const
       }
     }
     if (bj != a) {
-      changed = 1;
-      assign[i] = bj;
+      ++changed;
+      as[p] = bj;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         long long h, l;
@@ -399,32 +461,183 @@ kmeans_assign_pruned(const double* __restrict__ X, int64_t n, int64_t ldx, const
       atomicAdd(&acc[(size_t)2 * s * D + a], (unsigned long long)(-1ll));
       atomicAdd(&acc[(size_t)2 * s * D + bj], 1ull);
     }
+    km_radius(Rcur, bj, km_ub(best, M, xn, delta2));  // radius of the (new) cluster for the next pass
   }
-  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
-  if ((threadIdx.x & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
+  if (changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
 }
 
+// fast path: one CTA per sorted segment (= the members of one cluster at the last sort).  The cluster's
+// candidate records are staged in shared memory once; every member then runs the brute-force kernel's inner
+// loop over them (broadcast LDS, DFMA chain), stopping at its own 2 ub + eta.  Points that have left the
+// cluster since the sort, or whose bound reaches past the staged part of the list, go to the straggler list.
+constexpr int KM_LS = 192;
+
 template <int D>
-void launch_pruned(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, const double* C, int s,
-                   const Fx& fx, int32_t* assign, unsigned long long* acc, double M, double delta2, double eta,
-                   unsigned long long* Rbits, int32_t* list, int32_t* len) {
-  FLGP_CUDA(cudaMemsetAsync(Rbits, 0, sizeof(unsigned long long) * s, c->stream));
-  const int grid = ceil_div(n, 256);
-  if (grid > 0) FLGP_LAUNCH(c, (kmeans_radius_kernel<D>), grid, 256, 0, X, n, ldx, rec, assign, M, delta2, Rbits);
-  FLGP_LAUNCH(c, kmeans_lists_kernel, s, 128, 0, C, s, D, Rbits, eta, list, len);
-  if (grid > 0) FLGP_LAUNCH(c, (kmeans_assign_pruned<D>), grid, 256, 0, X, n, ldx, rec, s, fx, assign, acc, list, len);
+__global__ void __launch_bounds__(256)
+kmeans_assign_segment(const double* __restrict__ Xs, int64_t n, const double* __restrict__ rec, int s, Fx fx,
+                      int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
+                      const double* __restrict__ list_cc, const int32_t* __restrict__ len,
+                      const int* __restrict__ seg_start, double M, double delta2, double eta,
+                      unsigned long long* __restrict__ Rcur, int32_t* __restrict__ strag, int* __restrict__ nstrag) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  __shared__ __align__(16) double srec[(KM_LS + 1) * STR];
+  __shared__ double scc[KM_LS];
+  __shared__ int sj[KM_LS];
+  __shared__ double sred[8];
+  const int a = blockIdx.x, tid = threadIdx.x;
+  const int beg = seg_start[a], end = seg_start[a + 1];
+  if (beg == end) return;
+  const int L = len[a];
+  const int Ls = (L < 0) ? 0 : min(L, KM_LS);
+  const bool whole = (L >= 0 && L <= KM_LS);
+  for (int t = tid; t < STR; t += 256) srec[t] = rec[(size_t)a * STR + t];
+  for (int q = tid; q < Ls; q += 256) {
+    const int j = list_j[(size_t)a * KM_LMAX + q];
+    sj[q] = j;
+    scc[q] = list_cc[(size_t)a * KM_LMAX + q];
+  }
+  __syncthreads();
+  for (int t = tid; t < Ls * STR; t += 256) srec[STR + t] = rec[(size_t)sj[t / STR] * STR + (t % STR)];
+  __syncthreads();
+  int changed = 0;
+  double rmax = 0.0;
+  for (int p = beg + tid; p < end; p += 256) {
+    bool straggler = (as[p] != a);
+    double x[D], xn = 0.0, best = 0.0;
+    int bj = a;
+    if (!straggler) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        x[k] = Xs[p + n * k];
+        xn = fma(x[k], x[k], xn);
+      }
+      best = srec[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) best = fma(x[k], srec[k], best);
+      const double thr = (2.0 * km_ub(best, M, xn, delta2) + eta) * (1.0 + 1e-9);
+      bool done = false;
+      for (int q = 0; q < Ls; ++q) {
+        if (scc[q] >= thr) {  // sorted by centre-centre distance: nothing further can win or tie
+          done = true;
+          break;
+        }
+        const double* rj = srec + (size_t)(q + 1) * STR;
+        double e = rj[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) e = fma(x[k], rj[k], e);
+        const int j = sj[q];
+        if (e < best || (e == best && j < bj)) {
+          best = e;
+          bj = j;
+        }
+      }
+      if (!done && !whole) straggler = true;  // the bound reaches past the staged part of the list
+    }
+    if (straggler) {  // warp-aggregated append
+      const unsigned act = __activemask();
+      const int lane = tid & 31, lead = __ffs(act) - 1;
+      int base = 0;
+      if (lane == lead) base = atomicAdd(nstrag, __popc(act));
+      base = __shfl_sync(act, base, lead);
+      strag[base + __popc(act & ((1u << lane) - 1))] = p;
+      continue;
+    }
+    const double ub = km_ub(best, M, xn, delta2);
+    if (bj != a) {
+      ++changed;
+      as[p] = bj;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        long long h, l;
+        fx_encode(fx, x[k], &h, &l);
+        atomicAdd(&acc[a + (size_t)s * k], (unsigned long long)(-h));
+        atomicAdd(&acc[(size_t)s * D + a + (size_t)s * k], (unsigned long long)(-l));
+        atomicAdd(&acc[bj + (size_t)s * k], (unsigned long long)h);
+        atomicAdd(&acc[(size_t)s * D + bj + (size_t)s * k], (unsigned long long)l);
+      }
+      atomicAdd(&acc[(size_t)2 * s * D + a], (unsigned long long)(-1ll));
+      atomicAdd(&acc[(size_t)2 * s * D + bj], 1ull);
+      km_radius(Rcur, bj, ub);
+    } else {
+      rmax = fmax(rmax, ub);
+    }
+  }
+  // one radius atomic and one `changed` atomic per CTA
+  for (int o = 16; o; o >>= 1) {
+    rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  }
+  __shared__ int schg[8];
+  if ((tid & 31) == 0) {
+    sred[tid >> 5] = rmax;
+    schg[tid >> 5] = changed;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double m = sred[0];
+    int cgd = schg[0];
+    for (int w = 1; w < 8; ++w) {
+      m = fmax(m, sred[w]);
+      cgd += schg[w];
+    }
+    if (m > 0.0) km_radius(Rcur, a, m);
+    if (cgd) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)cgd);
+  }
+}
+
+// ---- cluster-sorted layout: counting sort by assignment -------------------------------------------------
+__global__ void kmeans_offsets_kernel(const long long* __restrict__ cnt, int s, int* __restrict__ cursor,
+                                      int* __restrict__ seg_start) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {  // s is a few thousand: a serial scan is a few microseconds
+    int run = 0;
+    for (int j = 0; j < s; ++j) {
+      cursor[j] = run;
+      seg_start[j] = run;
+      run += (int)cnt[j];
+    }
+    seg_start[s] = run;
+  }
+}
+
+// src_perm == nullptr: source is the original order (row i <-> index i)
+__global__ void __launch_bounds__(256)
+kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc, int d, const int32_t* __restrict__ asrc,
+                      const int32_t* __restrict__ src_perm, int* __restrict__ cursor, double* __restrict__ Xdst,
+                      int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int a = asrc[i];
+  // one atomic per group of equal keys in the warp
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, a);
+  const int lane = threadIdx.x & 31;
+  const int leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(&cursor[a], __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const int pos = base + __popc(peers & ((1u << lane) - 1));
+  dst_perm[pos] = src_perm ? src_perm[i] : (int32_t)i;
+  adst[pos] = a;
+  for (int k = 0; k < d; ++k) Xdst[pos + n * k] = Xsrc[i + ldsrc * k];
+}
+
+__global__ void kmeans_unpermute_kernel(const int32_t* __restrict__ as, const int32_t* __restrict__ perm, int64_t n,
+                                        int32_t* __restrict__ assign) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) assign[perm[p]] = as[p];
 }
 
 template <int D>
 void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, int s, const Fx& fx,
-                  int32_t* assign, unsigned long long* acc) {
+                  int32_t* assign, unsigned long long* acc, unsigned long long* Rbits, double M, double delta2) {
   constexpr int P = 4;
   constexpr int STR = (D + 2) / 2 * 2;
   int chunk = std::min(s, 1024);
   size_t smem = (size_t)chunk * STR * sizeof(double);
   int grid = ceil_div(n, (int64_t)KM_THREADS * P);
   if (grid < 1) return;
-  FLGP_LAUNCH(c, (kmeans_assign_small<D, P>), grid, KM_THREADS, smem, X, n, ldx, rec, s, fx, assign, acc, chunk, 1);
+  FLGP_LAUNCH(c, (kmeans_assign_small<D, P>), grid, KM_THREADS, smem, X, n, ldx, rec, s, fx, assign, acc, chunk, 1,
+              Rbits, M, delta2);
 }
 
 }  // namespace
@@ -445,7 +658,7 @@ double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d) 
 
 void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, int s, int64_t n_total,
                 int64_t row_offset, const int32_t* init_idx_h, int iter_max, double* U, int32_t* assign,
-                int* iters_out) {
+                int* iters_out, KMeansSorted* sorted_out) {
   if (s < 1 || s > n_total || d < 1) fail(2, "kmeans: need 1 <= s <= n (s=%d, n=%lld)", s, (long long)n_total);
   for (int j = 0; j < s; ++j)
     if (init_idx_h[j] < 0 || init_idx_h[j] >= n_total) fail(2, "kmeans: initial index out of range");
@@ -475,22 +688,59 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     cn.alloc(s);
   }
   unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc.p);
-  // pruned iterations (small d): persistent local accumulators + neighbour lists; see the proof above
+  // pruned passes (small d): persistent local accumulators, neighbour lists, cluster-sorted points
   const bool pruned = small && n_total >= 2;
-  const double bound = Moff + 4.0 * d * (maxabs * maxabs);                    // >= |score| terms
+  const double bound = Moff + 4.0 * d * (maxabs * maxabs);                    // >= the magnitude of every score term
   const double Delta = 8.0 * (d + 4) * 1.1102230246251565e-16 * bound;        // generous bound on a score's rounding error
   const double delta2 = 4.0 * Delta;                                          // slack added to squared distances
   const double eta = 2.0 * std::sqrt(2.0 * Delta) + 1e-12 * maxabs;           // eta^2 > 2 Delta with room to spare
-  DevBuf<unsigned long long> Rbits;
-  DevBuf<int32_t> nlist, nlen;
+  DevBuf<unsigned long long> Rbits[2];
+  DevBuf<int32_t> nlist, nlen, perm[2], as[2];
+  DevBuf<double> ncc, move, Xs[2];
+  DevBuf<int> cursor, seg_start, nstrag;
+  DevBuf<int32_t> strag;
   DevBuf<long long> acc_red;  // all-reduced copy of the local accumulators (multi-GPU)
   if (pruned) {
-    Rbits.alloc(s);
+    Rbits[0].alloc(s);
+    Rbits[1].alloc(s);
     nlist.alloc((size_t)s * KM_LMAX);
+    ncc.alloc((size_t)s * KM_LMAX);
     nlen.alloc(s);
+    move.alloc(s);
+    cursor.alloc(s);
+    seg_start.alloc(s + 1);
+    nstrag.alloc(1);
+    strag.alloc(std::max<int64_t>(n_local, 1));
+    for (int b = 0; b < 2; ++b) {
+      perm[b].alloc(std::max<int64_t>(n_local, 1));
+      as[b].alloc(std::max<int64_t>(n_local, 1));
+      Xs[b].alloc(std::max<int64_t>(n_local * d, 1));
+    }
     if (c->nranks > 1) acc_red.alloc(words);
+    Rbits[0].zero(c->stream);
   }
-  int it = 0;
+  int cur = 0;              // which sorted buffer is live
+  bool have_sorted = false;
+  int64_t moved_since_sort = 0, last_strag = 0;
+  auto resort = [&]() {
+    // counting sort by cluster of the current assignment (local counts live in acc)
+    StageScope st(c, "kmeans_sort");
+    FLGP_LAUNCH(c, kmeans_offsets_kernel, 1, 32, 0, acc.p + (size_t)2 * s * d, s, cursor.p, seg_start.p);
+    const int nxt = have_sorted ? 1 - cur : 0;
+    if (n_local > 0) {
+      if (have_sorted)
+        FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, Xs[cur].p, n_local, n_local, d, as[cur].p,
+                    perm[cur].p, cursor.p, Xs[nxt].p, as[nxt].p, perm[nxt].p);
+      else
+        FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, X, n_local, ldx, d, assign,
+                    (const int32_t*)nullptr, cursor.p, Xs[nxt].p, as[nxt].p, perm[nxt].p);
+    }
+    cur = nxt;
+    have_sorted = true;
+    moved_since_sort = 0;
+    last_strag = 0;
+  };
+  int it = 0, rsel = 0;  // Rbits[rsel]: radii gathered during the previous pass
   while (it < iter_max) {
     ++it;
     const bool brute = !pruned || it == 1;
@@ -498,22 +748,39 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
-    // when timing is on, the assign+accumulate work gets its own CUDA-event pair per iteration
-    StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_iteration", 2.0 * s * d * (double)n_local,
+    if (!brute && (!have_sorted || last_strag * 16 > n_local)) resort();
+    // when timing is on, the assign+accumulate work gets its own CUDA-event pair per pass
+    StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_pass", 2.0 * s * d * (double)n_local,
                    (8.0 * d + 4.0) * (double)n_local);
     if (!brute) {
-      switch (d) {
-        case 1: launch_pruned<1>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
-        case 2: launch_pruned<2>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
-        case 3: launch_pruned<3>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
-        default: launch_pruned<4>(c, X, n_local, ldx, rec.p, C, s, fx, assign, uacc, Moff, delta2, eta, Rbits.p, nlist.p, nlen.p); break;
+      unsigned long long* Rprev = Rbits[rsel].p;
+      unsigned long long* Rcur = Rbits[1 - rsel].p;
+      FLGP_CUDA(cudaMemsetAsync(Rcur, 0, sizeof(unsigned long long) * s, c->stream));
+      FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p);
+      FLGP_CUDA(cudaMemsetAsync(nstrag.p, 0, sizeof(int), c->stream));
+      if (n_local > 0) {
+        const int sgrid = c->sm_count * 8;
+#define FLGP_PRUNED(D_)                                                                                          \
+  FLGP_LAUNCH(c, (kmeans_assign_segment<D_>), s, 256, 0, Xs[cur].p, n_local, rec.p, s, fx, as[cur].p, uacc,       \
+              nlist.p, ncc.p, nlen.p, seg_start.p, Moff, delta2, eta, Rcur, strag.p, nstrag.p);                   \
+  FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs[cur].p, n_local, rec.p, s, fx, as[cur].p, uacc,    \
+              nlist.p, ncc.p, nlen.p, Moff, delta2, eta, Rcur, strag.p, nstrag.p)
+        switch (d) {
+          case 1: FLGP_PRUNED(1); break;
+          case 2: FLGP_PRUNED(2); break;
+          case 3: FLGP_PRUNED(3); break;
+          default: FLGP_PRUNED(4); break;
+        }
+#undef FLGP_PRUNED
       }
+      rsel = 1 - rsel;
     } else if (small) {
+      unsigned long long* R0 = pruned ? Rbits[rsel].p : nullptr;
       switch (d) {
-        case 1: launch_small<1>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
-        case 2: launch_small<2>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
-        case 3: launch_small<3>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
-        default: launch_small<4>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc); break;
+        case 1: launch_small<1>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
+        case 2: launch_small<2>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
+        case 3: launch_small<3>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
+        default: launch_small<4>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
       }
     } else {
       int grid = ceil_div(n_local, KT_TP);
@@ -527,12 +794,31 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       red = acc_red.p;
     }
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
-    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s * d, 256), 256, 0, red, s, d, fx, C, sizes);
+    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr);
     FLGP_CUDA(cudaMemcpyAsync(c->pinned, red + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    if (!brute) FLGP_CUDA(cudaMemcpyAsync(c->pinned + 1, nstrag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     sync(c);
+    moved_since_sort += c->pinned[0];
+    last_strag = brute ? 0 : (int64_t)(*reinterpret_cast<int*>(c->pinned + 1));
     if (c->pinned[0] == 0) break;  // no assignment changed anywhere
   }
+  if (have_sorted && n_local > 0)
+    FLGP_LAUNCH(c, kmeans_unpermute_kernel, ceil_div(n_local, 256), 256, 0, as[cur].p, perm[cur].p, n_local, assign);
   if (iters_out) *iters_out = it;
+  if (sorted_out) {
+    sorted_out->valid = have_sorted;
+    if (have_sorted) {
+      // hand the cluster-sorted layout to the next stage (KNN): radii are those of the last pass; the centres
+      // have moved by at most move[] since (zero when the loop stopped because nothing changed)
+      sorted_out->Xs = std::move(Xs[cur]);
+      sorted_out->perm = std::move(perm[cur]);
+      sorted_out->as = std::move(as[cur]);
+      sorted_out->Rbits = std::move(Rbits[rsel]);
+      sorted_out->move = std::move(move);
+      sorted_out->eta = eta;
+    }
+  }
+  sync(c);
 }
 
 }  // namespace flgp
