@@ -36,6 +36,7 @@ struct flgp_spectrum {
   std::vector<double> values;  // K, as exported (sigma or sigma^2)
   int kmeans_iters = 0;
   long long lae_iters = 0, lae_bts = 0;
+  KMeansSorted sorted;  // cluster-sorted rows left by k-means; consumed (and released) by the KNN stage
 };
 
 namespace {
@@ -164,7 +165,7 @@ void stage_subsample(Ctx* c, flgp_spectrum* sp, const double* X, const Models& m
     }
     StageScope st(c, "kmeans");
     kmeans_run(c, X, sp->n_local, sp->n_local, d, s, sp->n_total, sp->row_offset, init_idx, mo.iter_max, sp->U.p, ap,
-               &sp->kmeans_iters);
+               &sp->kmeans_iters, &sp->sorted);
     if (st.idx >= 0) {
       c->stages[st.idx].flops = 2.0 * s * d * (double)sp->n_local * sp->kmeans_iters;
       c->stages[st.idx].bytes = (8.0 * d + 4.0) * (double)sp->n_local * sp->kmeans_iters;
@@ -196,8 +197,9 @@ void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const do
   if (kernel == "lae") {
     {
       StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 4.0 * r) * (double)n);
-      knn_run(c, X, n, n, d, U, s, s, r, ind.p, nullptr);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, nullptr, &sp->sorted);
     }
+    sp->sorted = KMeansSorted();
     DevBuf<long long> stats(2);
     stats.zero(c->stream);
     {
@@ -213,8 +215,9 @@ void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const do
     DevBuf<double> dist(std::max<int64_t>(n * r, 1));
     {
       StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 12.0 * r) * (double)n);
-      knn_run(c, X, n, n, d, U, s, s, r, ind.p, dist.p);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, dist.p, &sp->sorted);
     }
+    sp->sorted = KMeansSorted();
     StageScope st(c, "se_weights", 0.0, 36.0 * r * (double)n);
     knn_to_csr_run(c, n, r, ind.p, dist.p, sp->Zj.p, sp->Zx.p);
     se_weights_run(c, sp->Zx.p, n * r, 4.0 * epsilon * epsilon, sp->Zx.p);

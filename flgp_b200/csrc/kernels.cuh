@@ -17,7 +17,9 @@ struct KMeansSorted {
   DevBuf<int32_t> perm, as;
   DevBuf<unsigned long long> Rbits;  // bit patterns of non-negative doubles
   DevBuf<double> move;
+  DevBuf<int> seg_start;             // s + 1: positions [seg_start[a], seg_start[a+1]) were in cluster a at the last sort
   double eta = 0.0;
+  double maxabs = 0.0;               // max |X| over all ranks
 };
 void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, int s, int64_t n_total,
                 int64_t row_offset, const int32_t* init_idx_h, int iter_max, double* U, int32_t* assign,
@@ -26,8 +28,10 @@ double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);
 
 // ---- knn.cu ----------------------------------------------------------------------------------
 // ind: n x r (ld n), ascending distance, libstdc++ partial_sort tie behaviour.  dist: optional.
+// sorted (optional): the cluster-sorted layout of the SAME rows left by kmeans_run; with it (d <= 4, r <= 5) every
+// point scans only the anchors that can reach its top r (exact: see knn.cu), everything else is unchanged.
 void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, int32_t* ind, double* dist);
+             int r, int32_t* ind, double* dist, const KMeansSorted* sorted = nullptr);
 
 // ---- lae.cu ----------------------------------------------------------------------------------
 // Zj/Zx: n*r CSR (row i at i*r), rows sorted by column.  Wd: optional dense n x r weights (ld n)

@@ -815,7 +815,9 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       sorted_out->as = std::move(as[cur]);
       sorted_out->Rbits = std::move(Rbits[rsel]);
       sorted_out->move = std::move(move);
+      sorted_out->seg_start = std::move(seg_start);
       sorted_out->eta = eta;
+      sorted_out->maxabs = maxabs;
     }
   }
   sync(c);

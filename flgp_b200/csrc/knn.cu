@@ -10,6 +10,7 @@
 //
 // Roofline: FP64 pipe (2*s*d flop per point); bytes 8d read + 4r (+8r) written.
 #include <algorithm>
+#include <cmath>
 
 #include "kernels.cuh"
 
@@ -117,25 +118,34 @@ struct HeapState<0> {
 
 __device__ __forceinline__ int top_filter(double top) { return top < 0.0 ? 0x7fffffff : __double2hiint(top); }
 
+// sel / nsel / perm (all or none): the kernel processes the *nsel source rows sel[0..), row q of X, and writes
+// the result to output row perm[q] (the pruned path's fallback for the few points it cannot decide, below).
 template <int D, int R, int P>
 __global__ void __launch_bounds__(256)
 knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ rec, int s, int r_in,
-                 int32_t* __restrict__ ind, double* __restrict__ dist, int chunk, int one) {
+                 int32_t* __restrict__ ind, double* __restrict__ dist, int chunk, int one,
+                 const int32_t* __restrict__ sel, const int* __restrict__ nsel, const int32_t* __restrict__ perm,
+                 int64_t n_out) {
   constexpr int STR = (D + 2) / 2 * 2;
   const int r = R ? R : r_in;
   extern __shared__ __align__(16) double srec[];
   const int tid = threadIdx.x;
   const int64_t base = (int64_t)blockIdx.x * (256 * P);
+  const int64_t count = sel ? (int64_t)*nsel : n;
+  if (base >= count) return;
   double x[P][D], xn[P];
   HeapState<R> hs[P];
   int th[P];
+  int64_t orow[P];
 #pragma unroll
   for (int p = 0; p < P; ++p) {
-    const int64_t i = base + (int64_t)p * 256 + tid;
+    const int64_t q = base + (int64_t)p * 256 + tid;
+    const int64_t i = (q < count) ? (sel ? (int64_t)sel[q] : q) : -1;
+    orow[p] = (i < 0) ? -1 : (sel ? (int64_t)perm[i] : i);
     xn[p] = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      x[p][k] = (i < n) ? X[i + ldx * k] : 0.0;
+      x[p][k] = (i >= 0) ? X[i + ldx * k] : 0.0;
       xn[p] = __dadd_rn(xn[p], __dmul_rn(x[p][k], x[p][k]));
     }
     th[p] = 0x7fffffff;
@@ -198,9 +208,251 @@ knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
     }
   }
 #pragma unroll
-  for (int p = 0; p < P; ++p) {
-    const int64_t i = base + (int64_t)p * 256 + tid;
-    if (i < n) hs[p].finish(r, i, n, ind, dist);
+  for (int p = 0; p < P; ++p)
+    if (orow[p] >= 0) hs[p].finish(r, orow[p], n_out, ind, dist);
+}
+
+// ---- exact pruning on the cluster-sorted layout that k-means leaves behind (small d) -----------------------
+// Rows are grouped in segments; segment a holds rows that are close to anchor a (its k-means cluster at the last
+// sort - but correctness below does not depend on that).  For a row x of segment a let
+//   ub   >= |x - U_a|                       (computed from the row's own distance to U_a, plus rounding slack)
+//   rho_a = |U_a - its r-th nearest anchor|, U_a itself counted first (so r anchors lie within rho_a of U_a).
+// Those r anchors are within ub + rho_a of x, hence x's r-th smallest distance is <= ub + rho_a, and an anchor j with
+//   |U_a - U_j| >= 2 ub + rho_a + eta   has   |x - U_j| >= ub + rho_a + eta,
+// i.e. its true distance exceeds that of r other anchors by eta, and its COMPUTED squared distance (rounding error
+// <= Delta, eta^2 > 2 Delta) is strictly larger than theirs: j is neither among the r nearest nor tied with them.
+// Scanning {j : |U_a - U_j| < 2 ub + rho_a + eta} therefore yields the same r smallest values as the full scan.
+// std::partial_sort's answer is unique when those r values and the next one are pairwise distinct; if the row sees
+// an exact tie among its r+1 smallest, or its bound reaches past the staged list, it is handed to the brute-force
+// kernel above (libstdc++ heap emulation over all anchors).  Lists are sorted by anchor-anchor distance so that a
+// row stops at its own bound.
+constexpr int KNN_LMAX = 256;
+
+template <int R>
+struct TopSorted {  // the R + 1 smallest (key, id) pairs seen, ascending, ties by id: registers only
+  double k[R + 1];
+  int id[R + 1];
+  __device__ __forceinline__ void init() {
+#pragma unroll
+    for (int a = 0; a <= R; ++a) {
+      k[a] = INFINITY;
+      id[a] = 0x7fffffff;
+    }
+  }
+  __device__ __forceinline__ void insert(double d, int j) {
+    if (d < k[R] || (d == k[R] && j < id[R])) {
+      k[R] = d;
+      id[R] = j;
+#pragma unroll
+      for (int u = R; u > 0; --u) {
+        const bool lt = k[u] < k[u - 1] || (k[u] == k[u - 1] && id[u] < id[u - 1]);
+        const double tk = k[u];
+        const int ti = id[u];
+        if (lt) {
+          k[u] = k[u - 1];
+          id[u] = id[u - 1];
+          k[u - 1] = tk;
+          id[u - 1] = ti;
+        }
+      }
+    }
+  }
+  __device__ __forceinline__ bool tie() const {
+    bool t = false;
+#pragma unroll
+    for (int a = 0; a < R; ++a) t |= (k[a] == k[a + 1]);  // +inf padding never equals a finite key
+    return t;
+  }
+};
+
+// per anchor: rho_a, then the anchors within thr = 2 R_a + rho_a + eta sorted by distance (a itself first);
+// if more than KNN_LMAX qualify the radius is halved until they fit.  lrad[a] = the radius the list is complete to.
+__global__ void __launch_bounds__(256)
+knn_lists_kernel(const double* __restrict__ U, int s, int64_t ldu, int d, int r,
+                 const unsigned long long* __restrict__ Rbits, const double* __restrict__ move, double eta,
+                 int32_t* __restrict__ list_j, double* __restrict__ list_cc, int32_t* __restrict__ len,
+                 double* __restrict__ lrad, double* __restrict__ rho_out) {
+  __shared__ double kcc[KNN_LMAX];
+  __shared__ int kj[KNN_LMAX];
+  __shared__ double rk[8];
+  __shared__ int rj[8];
+  __shared__ int count;
+  const int a = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double ua[4];
+  for (int k = 0; k < d; ++k) ua[k] = U[a + ldu * k];
+  auto ccof = [&](int j) {
+    double cc = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double df = ua[k] - U[j + ldu * k];
+      cc = fma(df, df, cc);
+    }
+    return sqrt(cc);
+  };
+  // r rounds of "smallest (cc, j) above the previous one": the last is rho_a
+  double pk = -1.0;
+  int pj = -1;
+  for (int round = 0; round < r; ++round) {
+    double bk = INFINITY;
+    int bj = 0x7fffffff;
+    for (int j = tid; j < s; j += 256) {
+      const double cc = ccof(j);
+      const bool above = cc > pk || (cc == pk && j > pj);
+      if (above && (cc < bk || (cc == bk && j < bj))) {
+        bk = cc;
+        bj = j;
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (ok < bk || (ok == bk && oj < bj)) {
+        bk = ok;
+        bj = oj;
+      }
+    }
+    __syncthreads();
+    if (lane == 0) {
+      rk[wid] = bk;
+      rj[wid] = bj;
+    }
+    __syncthreads();
+    bk = rk[0];
+    bj = rj[0];
+    for (int w = 1; w < 8; ++w)
+      if (rk[w] < bk || (rk[w] == bk && rj[w] < bj)) {
+        bk = rk[w];
+        bj = rj[w];
+      }
+    pk = bk;
+    pj = bj;
+  }
+  const double rho = pk * (1.0 + 1e-9);
+  const double Ra = Rbits ? __longlong_as_double((long long)Rbits[a]) + move[a] : 0.0;
+  double thr = (2.0 * Ra + rho + eta) * (1.0 + 1e-9);
+  int cnt;
+  while (true) {
+    __syncthreads();
+    if (tid == 0) count = 0;
+    __syncthreads();
+    for (int j = tid; j < s; j += 256) {
+      const double cc = ccof(j);
+      if (cc < thr) {
+        const int pos = atomicAdd(&count, 1);
+        if (pos < KNN_LMAX) {
+          kcc[pos] = cc;
+          kj[pos] = j;
+        }
+      }
+    }
+    __syncthreads();
+    cnt = count;
+    if (cnt <= KNN_LMAX) break;
+    thr *= 0.5;  // too many: a shorter list is still exact for the rows whose bound fits (the others fall back)
+  }
+  int npow = 1;
+  while (npow < cnt) npow <<= 1;
+  for (int t = cnt + tid; t < npow; t += 256) {
+    kcc[t] = INFINITY;
+    kj[t] = 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k2 = 2; k2 <= npow; k2 <<= 1)
+    for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+      for (int t = tid; t < npow; t += 256) {
+        const int u = t ^ j2;
+        if (u > t) {
+          const bool up = (t & k2) == 0;
+          const double c0 = kcc[t], c1 = kcc[u];
+          const int i0 = kj[t], i1 = kj[u];
+          const bool gt = (c0 > c1) || (c0 == c1 && i0 > i1);
+          if (gt == up) {
+            kcc[t] = c1;
+            kcc[u] = c0;
+            kj[t] = i1;
+            kj[u] = i0;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int t = tid; t < cnt; t += 256) {
+    list_j[(size_t)a * KNN_LMAX + t] = kj[t];
+    list_cc[(size_t)a * KNN_LMAX + t] = kcc[t];
+  }
+  if (tid == 0) {
+    len[a] = cnt;
+    lrad[a] = thr;
+    rho_out[a] = rho;
+  }
+}
+
+template <int D, int R>
+__global__ void __launch_bounds__(256)
+knn_segment_kernel(const double* __restrict__ Xs, int64_t n, const double* __restrict__ rec,
+                   const int32_t* __restrict__ perm, const int* __restrict__ seg_start,
+                   const int32_t* __restrict__ list_j, const double* __restrict__ list_cc,
+                   const int32_t* __restrict__ len, const double* __restrict__ lrad, const double* __restrict__ rho,
+                   double delta2, double eta, int32_t* __restrict__ ind, double* __restrict__ dist,
+                   int32_t* __restrict__ strag, int* __restrict__ nstrag) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  __shared__ __align__(16) double srec[KNN_LMAX * STR];
+  __shared__ double scc[KNN_LMAX];
+  __shared__ int sj[KNN_LMAX];
+  const int a = blockIdx.x, tid = threadIdx.x;
+  const int beg = seg_start[a], end = seg_start[a + 1];
+  if (beg == end) return;
+  const int L = len[a];
+  for (int q = tid; q < L; q += 256) {
+    sj[q] = list_j[(size_t)a * KNN_LMAX + q];
+    scc[q] = list_cc[(size_t)a * KNN_LMAX + q];
+  }
+  __syncthreads();
+  for (int t = tid; t < L * STR; t += 256) srec[t] = rec[(size_t)sj[t / STR] * STR + (t % STR)];
+  __syncthreads();
+  const double radius = lrad[a], rho_a = rho[a];
+  for (int p = beg + tid; p < end; p += 256) {
+    double x[D], xn = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      x[k] = Xs[p + n * k];
+      xn = __dadd_rn(xn, __dmul_rn(x[k], x[k]));
+    }
+    auto sqdist = [&](int q) {  // the reference's expression, src/Utils.cpp:121
+      const double* ur = srec + (size_t)q * STR;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc = __dadd_rn(acc, __dmul_rn(x[k], ur[k]));
+      return __dadd_rn(__dadd_rn(__dmul_rn(-2.0, acc), xn), ur[D]);
+    };
+    TopSorted<R> top;
+    top.init();
+    const double d0 = sqdist(0);  // entry 0 is anchor a itself
+    top.insert(d0, sj[0]);
+    const double ub = sqrt(fmax(d0, 0.0) + delta2) * (1.0 + 1e-14);
+    const double thr = (2.0 * ub + rho_a + eta) * (1.0 + 1e-9);
+    bool fallback = !(thr <= radius) || L < 1;
+    if (!fallback) {
+      for (int q = 1; q < L; ++q) {
+        if (scc[q] >= thr) break;  // sorted by anchor-anchor distance: nothing further can reach the top r
+        top.insert(sqdist(q), sj[q]);
+      }
+      fallback = top.tie();
+    }
+    if (fallback) {  // warp-aggregated append
+      const unsigned act = __activemask();
+      const int lane = tid & 31, lead = __ffs(act) - 1;
+      int base = 0;
+      if (lane == lead) base = atomicAdd(nstrag, __popc(act));
+      base = __shfl_sync(act, base, lead);
+      strag[base + __popc(act & ((1u << lane) - 1))] = p;
+      continue;
+    }
+    const int64_t i = perm[p];
+#pragma unroll
+    for (int q = 0; q < R; ++q) {
+      ind[i + n * q] = top.id[q];
+      if (dist) dist[i + n * q] = top.k[q];
+    }
   }
 }
 
@@ -277,7 +529,46 @@ void launch_small_r(Ctx* c, const double* X, int64_t n, int64_t ldx, const doubl
   int chunk = std::min(s, 1024);
   size_t smem = (size_t)chunk * STR * sizeof(double);
   int grid = ceil_div(n, 256 * P);
-  FLGP_LAUNCH(c, (knn_small_kernel<D, R, P>), grid, 256, smem, X, n, ldx, rec, s, r, ind, dist, chunk, 1);
+  FLGP_LAUNCH(c, (knn_small_kernel<D, R, P>), grid, 256, smem, X, n, ldx, rec, s, r, ind, dist, chunk, 1,
+              (const int32_t*)nullptr, (const int*)nullptr, (const int32_t*)nullptr, n);
+}
+
+// pruned scan over the cluster-sorted layout + brute-force fallback for the undecided rows
+template <int D, int R>
+void launch_pruned_r(Ctx* c, const KMeansSorted& so, int64_t n, const double* rec, const double* U, int s, int64_t ldu,
+                     int32_t* ind, double* dist) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  constexpr int P = 2;
+  const double m = so.maxabs;
+  const double Delta = 8.0 * (D + 4) * 1.1102230246251565e-16 * (4.0 * D * m * m);  // rounding of one computed distance
+  const double delta2 = 4.0 * Delta;
+  const double eta = 2.0 * std::sqrt(2.0 * Delta) + 1e-12 * m;  // eta^2 > 2 Delta
+  DevBuf<int32_t> lj((size_t)s * KNN_LMAX), llen(s), strag((size_t)n);
+  DevBuf<double> lcc((size_t)s * KNN_LMAX), lrad(s), rho(s);
+  DevBuf<int> nstrag(1);
+  nstrag.zero(c->stream);
+  FLGP_LAUNCH(c, knn_lists_kernel, s, 256, 0, U, s, ldu, D, R, so.Rbits.p, so.move.p, eta, lj.p, lcc.p, llen.p, lrad.p,
+              rho.p);
+  FLGP_LAUNCH(c, (knn_segment_kernel<D, R>), s, 256, 0, so.Xs.p, n, rec, so.perm.p, so.seg_start.p, lj.p, lcc.p, llen.p,
+              lrad.p, rho.p, delta2, eta, ind, dist, strag.p, nstrag.p);
+  int chunk = std::min(s, 1024);
+  size_t smem = (size_t)chunk * STR * sizeof(double);
+  int grid = ceil_div(n, 256 * P);  // blocks beyond *nstrag exit at once
+  FLGP_LAUNCH(c, (knn_small_kernel<D, R, P>), grid, 256, smem, so.Xs.p, n, n, rec, s, R, ind, dist, chunk, 1, strag.p,
+              nstrag.p, so.perm.p, n);
+  sync(c);  // the work buffers are freed on return
+}
+template <int D>
+bool launch_pruned(Ctx* c, const KMeansSorted& so, int64_t n, const double* rec, const double* U, int s, int64_t ldu,
+                   int r, int32_t* ind, double* dist) {
+  switch (r) {
+    case 1: launch_pruned_r<D, 1>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    case 2: launch_pruned_r<D, 2>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    case 3: launch_pruned_r<D, 3>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    case 4: launch_pruned_r<D, 4>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    case 5: launch_pruned_r<D, 5>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    default: return false;
+  }
 }
 template <int D>
 void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double* rec, int s, int r,
@@ -295,7 +586,7 @@ void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double*
 }  // namespace
 
 void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, int32_t* ind, double* dist) {
+             int r, int32_t* ind, double* dist, const KMeansSorted* sorted) {
   if (r < 1 || r > s) fail(2, "KNN: need 1 <= r <= s (r=%d, s=%d)", r, s);
   if (r > KNN_RMAX) fail(2, "KNN: r=%d exceeds the supported maximum %d", r, KNN_RMAX);
   if (n <= 0) return;
@@ -303,6 +594,16 @@ void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
     const int str = (d + 2) / 2 * 2;
     DevBuf<double> rec((size_t)s * str);
     FLGP_LAUNCH(c, knn_prep_kernel, ceil_div(s, 128), 128, 0, U, s, ldu, d, str, rec.p);
+    if (sorted && sorted->valid && r <= 5 && n < ((int64_t)1 << 31)) {
+      bool done = false;
+      switch (d) {
+        case 1: done = launch_pruned<1>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
+        case 2: done = launch_pruned<2>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
+        case 3: done = launch_pruned<3>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
+        default: done = launch_pruned<4>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
+      }
+      if (done) return;
+    }
     switch (d) {
       case 1: launch_small<1>(c, X, n, ldx, rec.p, s, r, ind, dist); break;
       case 2: launch_small<2>(c, X, n, ldx, rec.p, s, r, ind, dist); break;

@@ -92,6 +92,54 @@ def test_knn_exact_ties_follow_std_partial_sort(flgp, oracle, d):
         assert np.array_equal(ind, oracle.knn(X, U, r, nthreads=NT))
 
 
+@pytest.mark.parametrize("n,d,s,r,kernel", [(6000, 2, 300, 3, "lae"), (5000, 3, 200, 5, "lae"), (4000, 1, 40, 2, "se"),
+                                             (5000, 4, 150, 4, "se"), (3000, 3, 30, 1, "lae"), (2500, 2, 64, 6, "se")])
+def test_pipeline_knn_pruned_bitexact(flgp, oracle, n, d, s, r, kernel):
+    """Inside heat_kernel_spectrum the KNN runs on the cluster-sorted rows with exact candidate pruning
+    (r <= 5; r = 6 takes the full scan): the neighbour sets, their order (through the LAE weights) and the SE
+    distances must still be the oracle's bit for bit."""
+    rng = np.random.default_rng(n + 7 * s + r)
+    X = np.asfortranarray(rng.standard_normal((n, d)) * rng.uniform(0.5, 3.0, d))
+    init = _init(n, s, 11)
+    K = min(s, 10)
+    mo = dict(kernel=kernel, gl="rw")
+    ep = flgp.heat_kernel_spectrum_cpp(X[:100], X[100:], s, r, K, models=mo, init_idx=init, iter_max=7)
+    _, _, I = oracle.heat_kernel_spectrum(X[:100], X[100:], s, r, K, init, kernel=kernel, gl="rw", nthreads=NT,
+                                          want_internals=True, iter_max=7)
+    assert np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"])
+    if kernel == "lae":
+        assert np.array_equal(Zx, I["Zx"])
+    else:  # exp() of the device and of glibc differ in the last bit
+        np.testing.assert_allclose(Zx, I["Zx"], rtol=1e-12, atol=1e-300)
+
+
+def test_pipeline_knn_pruned_duplicate_anchors_fall_back(flgp, oracle):
+    """Identical start rows tie for ever: the lowest index takes the points and moves, the others stay empty and
+    keep their (identical) centre - one is peeled off per pass.  Six copies and four passes leave a duplicated pair
+    of anchors: every point near it sees an exact tie inside its r + 1 smallest distances and must take the
+    libstdc++ emulation path."""
+    rng = np.random.default_rng(5)
+    n, d, s, r = 4000, 2, 60, 3
+    X = np.asfortranarray(rng.standard_normal((n, d)))
+    init = _init(n, s, 2)
+    for t in (5, 20, 41):  # six identical rows among the start rows, three times
+        for q in range(1, 6):
+            X[init[t + q]] = X[init[t]]
+    ep = flgp.heat_kernel_spectrum_cpp(X[:50], X[50:], s, r, 8, models=dict(gl="rw"), init_idx=init, iter_max=4)
+    _, _, I = oracle.heat_kernel_spectrum(X[:50], X[50:], s, r, 8, init, gl="rw", nthreads=NT, want_internals=True,
+                                          iter_max=4)
+    U = ep.anchors()
+    assert np.array_equal(U, I["U"])
+    assert len(np.unique(U[:, :d], axis=0)) < s  # the duplicated anchors really are there
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    # rows that hold a duplicated pair exist (so the tie path was taken)
+    dup = [j for j in range(s) if np.sum(np.all(U[:, :d] == U[j, :d], axis=1)) > 1]
+    assert np.isin(Zj, dup).any()
+
+
 def test_knn_errors(flgp):
     X, _ = spiral(100, 1)
     with pytest.raises(flgp.FlgpError):
@@ -308,3 +356,6 @@ def test_c4_scale_properties(flgp):
     assert np.abs(V[:, 0]).std() < 1e-6 * np.abs(V[:, 0]).mean()  # top eigenvector of a row-stochastic Z is constant
     y, cov = flgp.regression_fixed(ep, Y[:m], m, K, (10.0, 0.01), 1e-5)
     assert np.sqrt(np.mean((y[m:] - Y[m:]) ** 2)) < 0.5 and np.all(cov[m:] > 0)
+    # the pipeline's pruned KNN against the exported full-scan KNN on the same anchors (two different kernels)
+    ind = flgp.KNN_cpp(X, np.asfortranarray(U[:, :3]), r)["ind_knn"]
+    assert np.array_equal(np.sort(ind, axis=1), Zj)
