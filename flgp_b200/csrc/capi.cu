@@ -346,48 +346,28 @@ void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total
     ls[k] = std::exp(-0.5 * t * ev) + 0.0;
   }
   const double ns = noise + sigma;
-  std::vector<double> coef(KK, 0.0), M((size_t)KK * KK, 0.0);  // padded to the handle's K with zeros
   // training rows of the lifted eigenvectors, row-major m_local x KK
   DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
   lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  DevBuf<double> dcoef(KK), dM((size_t)KK * KK);
   if (m_total > K) {
-    // Woodbury branch (src/Predict.cpp:61-74, src/Utils.cpp:237-244)
-    DevBuf<double> Gg((size_t)KK * KK + KK);
+    // Woodbury branch (src/Predict.cpp:61-74, src/Utils.cpp:237-244): the K x K algebra stays on the device (tail.cu)
+    DevBuf<double> Gg((size_t)KK * KK + KK), dls(K), dlam(K);
+    DevBuf<int> flag(1);
     gram_small_run(c, V1.p, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
     comm_allreduce_f64(c, Gg.p, (size_t)KK * KK + KK);
-    std::vector<double> Gh((size_t)KK * KK + KK);
-    Gg.download(Gh.data(), Gh.size(), c->stream);
+    dls.upload(ls.data(), K, c->stream);
+    dlam.upload(lam.data(), K, c->stream);
+    tail_woodbury_run(c, Gg.p, KK, K, dls.p, dlam.p, ns, dcoef.p, dM.p, flag.p);
+    int bad = 0;
+    flag.download(&bad, 1, c->stream);
     sync(c);
-    auto G1 = [&](int i, int j) { return Gh[i + (size_t)KK * j]; };
-    const double* g1 = Gh.data() + (size_t)KK * KK;
-    std::vector<double> Q((size_t)K * K);
-    for (int j = 0; j < K; ++j)
-      for (int i = 0; i < K; ++i) Q[i + (size_t)K * j] = ls[i] * G1(i, j) * ls[j] + (i == j ? ns : 0.0);
-    if (!chol_lower(Q, K)) fail(2, "regression: K x K system is not positive definite");
-    // q = Q^-1 (ls o g1);  V1^T alpha = (g1 - G1 (ls o q)) / ns;  coef = lam o V1^T alpha
-    std::vector<double> q(K);
-    for (int k = 0; k < K; ++k) q[k] = ls[k] * g1[k];
-    chol_solve(Q, K, q.data(), 1);
-    for (int i = 0; i < K; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < K; ++j) acc += G1(i, j) * (ls[j] * q[j]);
-      coef[i] = lam[i] * ((g1[i] - acc) / ns);
-    }
-    // alphaM = (1/ns) Lam (G1 - G1 Ls Q^-1 Ls G1) Lam ;  M = Lam - alphaM
-    std::vector<double> R((size_t)K * K);
-    for (int j = 0; j < K; ++j)
-      for (int i = 0; i < K; ++i) R[i + (size_t)K * j] = ls[i] * G1(i, j);
-    chol_solve(Q, K, R.data(), K);  // Q^-1 Ls G1
-    for (int j = 0; j < K; ++j)
-      for (int i = 0; i < K; ++i) {
-        double acc = 0.0;
-        for (int k = 0; k < K; ++k) acc += G1(i, k) * ls[k] * R[k + (size_t)K * j];
-        double am = lam[i] * (G1(i, j) - acc) * lam[j] / ns;
-        M[i + (size_t)KK * j] = (i == j ? lam[i] : 0.0) - am;
-      }
+    if (bad) fail(2, "regression: K x K system is not positive definite");
   } else {
-    // direct branch (src/Predict.cpp:47-59, src/Utils.cpp:228-236): every rank needs all m rows
+    // direct branch (src/Predict.cpp:47-59, src/Utils.cpp:228-236): every rank needs all m rows; m <= K is small,
+    // the m x m system is solved on the host
     const int m = (int)m_total;
+    std::vector<double> coef(KK, 0.0), M((size_t)KK * KK, 0.0);  // padded to the handle's K with zeros
     DevBuf<double> Vall((size_t)m * KK + m);
     Vall.zero(c->stream);
     if (m_local > 0) {
@@ -429,11 +409,12 @@ void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total
         for (int i = 0; i < m; ++i) acc += S[i + (size_t)m * a] * S2[i + (size_t)m * b];
         M[a + (size_t)KK * b] = (a == b ? lam[a] : 0.0) - acc;
       }
+    dcoef.upload(coef.data(), KK, c->stream);
+    dM.upload(M.data(), (size_t)KK * KK, c->stream);
+    sync(c);  // coef / M are host temporaries of this branch
   }
   // fold through the lift operator Wm (s x KK row-major)
-  DevBuf<double> dcoef(KK), dM((size_t)KK * KK), wv(s), T((size_t)s * KK), B((size_t)s * s);
-  dcoef.upload(coef.data(), KK, c->stream);
-  dM.upload(M.data(), (size_t)KK * KK, c->stream);
+  DevBuf<double> wv(s), T((size_t)s * KK), B((size_t)s * s);
   gemv_run(c, sp->Wm.p, dcoef.p, s, KK, wv.p);
   sparse_rowdot_run(c, sp->n_local, r, sp->Zj.p, sp->Zx.p, sp->w.p, wv.p, y_pred);
   if (cov) {

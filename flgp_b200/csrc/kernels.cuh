@@ -75,6 +75,12 @@ void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double
 // G(K x K, col-major) = V^T V and g = V^T y over n_rows rows of V (row-major n_rows x K); deterministic
 void gram_small_run(Ctx* c, const double* V, const double* y, int64_t n_rows, int K, double* G, double* g);
 
+// ---- tail.cu ---------------------------------------------------------------------------------
+// m > K branch of the GPR tail: from Gg = [G1 (K_ld x K_ld col-major) | g1 (K_ld)] to coef (K_ld) and M (K_ld x K_ld),
+// both zero padded beyond K; *flag = 1 if Q is not positive definite.  All pointers on the device.
+void tail_woodbury_run(Ctx* c, const double* Gg, int K_ld, int K, const double* ls, const double* lam, double ns,
+                       double* coef, double* M, int* flag);
+
 // ---- eigh.cu ---------------------------------------------------------------------------------
 // Top-K eigenpairs (descending) of the symmetric s x s matrix G (full storage; destroyed).
 // lam: K.  Y: s x K column-major, orthonormal columns.
