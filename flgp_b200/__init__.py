@@ -6,7 +6,7 @@ libflgp_b200.so and fails loudly when it is absent; there is no CPU or PyTorch f
 """
 from .api import (  # noqa: F401
     Context, EigenPair, FlgpError, HK_from_spectrum_cpp, KNN_cpp, LAE_cpp, cross_similarity_lae_cpp,
-    cross_similarity_se_cpp, default_ctx, default_init, fit_lae_regression_gp_rcpp, graphLaplacian_cpp,
+    cross_similarity_se_cpp, default_ctx, default_init, eigs_sym, fit_lae_regression_gp_rcpp, graphLaplacian_cpp,
     heat_kernel_covariance_rcpp, heat_kernel_spectrum_cpp, heat_kernel_spectrum_sharded, knn_distances,
     lae_eigenmap, local_anchor_embedding_cpp, regression_fixed, spectrum_from_Z_cpp, subsample_cpp, v_to_z_cpp,
 )

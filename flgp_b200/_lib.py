@@ -56,6 +56,7 @@ def _declare(lib):
                                                C.c_double, p_i32, p_f64]),
         "flgp_spectrum_from_z": (C.c_int, [H, c_i64, C.c_int, C.c_int, p_i32, p_f64, C.c_int, C.c_int, p_f64, p_f64,
                                            C.POINTER(H)]),
+        "flgp_eigs_sym": (C.c_int, [H, p_f64, C.c_int, C.c_int, p_f64, p_f64]),
         "flgp_heat_kernel_spectrum": (C.c_int, [H, p_f64, c_i64, p_f64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int,
                                                 C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                                                 p_i32, c_u64, C.POINTER(H)]),

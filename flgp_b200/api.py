@@ -350,6 +350,20 @@ def spectrum_from_Z_cpp(Z, K: int, root: bool = False, *, ctx: Optional[Context]
     return EigenPair(ctx, h)
 
 
+def eigs_sym(A, k: int, *, ctx: Optional[Context] = None):
+    """RSpectra::eigs_sym(A, k) as the Nystrom / GLGP drivers call it (src/Fit.cpp:262-278): the k algebraically
+    largest eigenpairs of the dense symmetric matrix A, values descending, orthonormal vectors (signs arbitrary)."""
+    ctx = ctx or default_ctx()
+    A = _f64(A)
+    s = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != s:
+        raise FlgpError("eigs_sym: A must be square")
+    values = np.zeros(k)
+    vectors = np.zeros((s, k), order="F")
+    check(ctx._lib.flgp_eigs_sym(ctx._h, _pf(A), s, k, _pf(values), _pf(vectors)))
+    return {"values": values, "vectors": vectors}
+
+
 def heat_kernel_spectrum_cpp(X, X_new, s: int, r: int, K: int, models=None, nstart: int = 1, epsilon: float = 0.1, *,
                              init_idx=None, seed: int = 0, iter_max: int = 100,
                              ctx: Optional[Context] = None) -> EigenPair:

@@ -749,6 +749,23 @@ int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* 
   });
 }
 
+int flgp_eigs_sym(flgp_ctx* ctx, const double* A, int s, int K, double* values, double* vectors) {
+  return guard([&] {
+    need(ctx && A && values, "null argument");
+    need(s >= 1 && K >= 1 && K <= s, "need 1 <= K <= s");
+    Ctx* c = &ctx->c;
+    DevBuf<double> G((size_t)s * s), lam(K), Y((size_t)s * K);
+    G.upload(A, (size_t)s * s, c->stream);
+    {
+      StageScope st(c, "eigh", (4.0 / 3.0) * s * (double)s * s + 2.0 * s * (double)s * K, 8.0 * s * (double)s * s);
+      eigh_topk_run(c, G.p, s, K, lam.p, Y.p);
+    }
+    lam.download(values, K, c->stream);
+    if (vectors) Y.download(vectors, (size_t)s * K, c->stream);
+    sync(c);
+  });
+}
+
 int flgp_heat_kernel_spectrum_dev(flgp_ctx* ctx, const double* X_local_dev, int64_t n_local, int64_t n_total,
                                   int64_t row_offset, int d, int s, int r, int K, const char* subsample,
                                   const char* kernel, int gl, int root, int nstart, double epsilon, int iter_max,

@@ -16,6 +16,8 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -25,7 +27,9 @@ namespace flgp {
 
 namespace {
 
-constexpr int TD_THREADS = 512;
+constexpr int TD_THREADS = 1024;
+constexpr int TD_MAXSEG = 16;  // a row of the trailing matrix is split over up to this many warps
+constexpr int TD_U = 4;        // loads in flight per lane in the fused pass
 
 // deterministic block-wide sum; every thread receives the result.  red: >= 32 doubles of shared memory.
 __device__ __forceinline__ double block_sum(double v, double* red) {
@@ -39,6 +43,45 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
+// All-to-all flag barrier for a co-resident grid (cooperative launch): every CTA publishes its epoch with one
+// release store and polls everybody else's slot.  No atomic is serialised on one L2 address (148 arrivals on one
+// counter cost more than the rest of a column step), and no L1 state is relied on: every datum that crosses SMs
+// inside the kernel is read with ld.global.cg.
+constexpr int FLAG_PER = 8;      // slots watched per lane of the polling warp: grids of up to 256 CTAs
+constexpr int FLAG_STRIDE = 32;  // one 128-byte line per CTA: polls of different flags go to different L2 slices
+__device__ __forceinline__ void st_release(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void flag_barrier(unsigned* flags, unsigned epoch) {
+  __syncthreads();  // this CTA's stores are all issued
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release(flags + (size_t)blockIdx.x * FLAG_STRIDE, epoch);
+  }
+  if (threadIdx.x < 32) {
+    // every lane watches up to FLAG_PER slots and keeps all its polls in flight together: one round trip per try
+    bool done;
+    do {
+      unsigned seen[FLAG_PER];
+#pragma unroll
+      for (int q = 0; q < FLAG_PER; ++q) {
+        const unsigned b = threadIdx.x + 32 * q;
+        seen[q] = (b < gridDim.x) ? ld_relaxed(flags + (size_t)b * FLAG_STRIDE) : epoch;
+      }
+      done = true;
+#pragma unroll
+      for (int q = 0; q < FLAG_PER; ++q) done &= (seen[q] >= epoch);
+    } while (!__all_sync(0xffffffffu, done));
+    __threadfence();  // acquire side: the polls above are ordered before everything that follows
+  }
+  __syncthreads();
+}
+
 // ---- 1. tridiagonalisation -----------------------------------------------------------------------
 // A: s x s symmetric, full storage (row i contiguous).  Vh: s x s, row k receives the Householder
 // vector of column k (v[0] = 1 at index 0, length s-k-1).  d (s), e (s-1), tau (s-1).
@@ -50,8 +93,16 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
 // the pass.  pbuf is double-buffered by the parity of k.
 __global__ void __launch_bounds__(TD_THREADS)
 tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* __restrict__ dd, double* __restrict__ ee,
-               double* __restrict__ tau_out, double* __restrict__ pbuf) {
-  cg::grid_group grid = cg::this_grid();
+               double* __restrict__ tau_out, double* __restrict__ pbuf, unsigned* __restrict__ flags,
+               long long* __restrict__ prof) {
+  long long t0 = 0, tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  const bool timing = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+#define TD_TICK(i)            \
+  if (timing) {               \
+    long long t_ = clock64(); \
+    tacc[i] += t_ - t0;       \
+    t0 = t_;                  \
+  }
   extern __shared__ __align__(16) double sm[];
   double* vp = sm;           // s: pending v_{k-1}; entry q <-> global index k + q
   double* wp = sm + s;       // s: pending w_{k-1}
@@ -61,20 +112,46 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
   const int gwarp = (blockIdx.x * TD_THREADS + tid) >> 5;
   const int nwarp = (gridDim.x * TD_THREADS) >> 5;
   bool pending = false;      // is there an update (vp, wp) not yet applied to memory?
+  constexpr int PER = (4096 + TD_THREADS - 1) / TD_THREADS;  // row k is prefetched into registers (s <= 4096)
+  double xpre[PER];
+  const bool use_pre = s <= PER * TD_THREADS;
+  if (use_pre) {
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int j = tid + q * TD_THREADS;
+      xpre[q] = (j < s - 1) ? __ldcg(A + 1 + j) : 0.0;  // row 0, columns 1..
+    }
+  }
 
   for (int k = 0; k < s - 1; ++k) {
     const int m = s - k - 1;  // length of column k below the diagonal
     const double* arow = A + (size_t)k * s;
+    if (timing) t0 = clock64();
     // --- column k of the up-to-date matrix: memory row k minus the pending rank-2 update (redundant per CTA)
     const double v0 = pending ? vp[0] : 0.0, w0 = pending ? wp[0] : 0.0;
     double part = 0.0;
-    for (int j = tid; j < m; j += TD_THREADS) {
-      double x = arow[k + 1 + j];
-      if (pending) x = __dsub_rn(x, __dadd_rn(__dmul_rn(v0, wp[j + 1]), __dmul_rn(w0, vp[j + 1])));
-      vs[j] = x;
-      if (j > 0) part = fma(x, x, part);
+    if (use_pre) {
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int j = tid + q * TD_THREADS;
+        if (j < m) {
+          double x = xpre[q];
+          if (pending) x = __dsub_rn(x, __dadd_rn(__dmul_rn(v0, wp[j + 1]), __dmul_rn(w0, vp[j + 1])));
+          vs[j] = x;
+          if (j > 0) part = fma(x, x, part);
+        }
+      }
+    } else {
+      for (int j = tid; j < m; j += TD_THREADS) {
+        double x = __ldcg(arow + k + 1 + j);
+        if (pending) x = __dsub_rn(x, __dadd_rn(__dmul_rn(v0, wp[j + 1]), __dmul_rn(w0, vp[j + 1])));
+        vs[j] = x;
+        if (j > 0) part = fma(x, x, part);
+      }
     }
+    TD_TICK(0);
     const double xnorm2 = block_sum(part, red);  // also orders the vs[] writes
+    TD_TICK(1);
     const double alpha = vs[0];
     double beta, tau, scale;
     if (xnorm2 == 0.0) {
@@ -88,44 +165,87 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
       scale = 1.0 / (alpha - beta);
     }
     __syncthreads();
-    for (int j = tid; j < m; j += TD_THREADS) vs[j] = (j == 0) ? 1.0 : vs[j] * scale;
-    __syncthreads();
-    if (blockIdx.x == 0) {
-      if (tid == 0) {
-        double dk = arow[k];
-        if (pending) dk = __dsub_rn(dk, __dadd_rn(__dmul_rn(v0, w0), __dmul_rn(w0, v0)));
-        dd[k] = dk;
-        ee[k] = beta;
-        tau_out[k] = tau;
-      }
-      for (int j = tid; j < m; j += TD_THREADS) Vh[(size_t)k * s + j] = vs[j];
+    TD_TICK(2);
+    for (int j = tid; j < m; j += TD_THREADS) {
+      const double v = (j == 0) ? 1.0 : vs[j] * scale;
+      vs[j] = v;
+      if ((j >> 5) % gridDim.x == blockIdx.x) Vh[(size_t)k * s + j] = v;  // every CTA stores its share of v_k
     }
-    // --- fused pass: apply the pending update to rows k+1.., accumulate p = tau * A22 v_k (one warp per row)
-    double* pk = pbuf + (size_t)(k & 1) * s;
-    for (int row = gwarp; row < m; row += nwarp) {
+    __syncthreads();
+    TD_TICK(3);
+    if (blockIdx.x == (unsigned)(k % gridDim.x) && tid == 0) {
+      double dk = __ldcg(arow + k);
+      if (pending) dk = __dsub_rn(dk, __dadd_rn(__dmul_rn(v0, w0), __dmul_rn(w0, v0)));
+      dd[k] = dk;
+      ee[k] = beta;
+      tau_out[k] = tau;
+    }
+    TD_TICK(4);
+    // --- fused pass: apply the pending update to rows k+1.., accumulate the products (A22 v_k).  Work item =
+    // (row, segment): a row is split over nseg warps when there are more warps than rows, so that the longest
+    // dependent chain of the step stays short; loads are issued TD_U at a time before any store.
+    int nseg = 1;
+    while (nseg < TD_MAXSEG && (nseg * 2) * m <= nwarp) nseg *= 2;
+    const int seglen = ((m + nseg - 1) / nseg + 31) & ~31;
+    double* pk = pbuf + (size_t)(k & 1) * TD_MAXSEG * s;
+    for (int item = gwarp; item < m * nseg; item += nwarp) {
+      const int row = item / nseg, seg = item - row * nseg;
+      const int c0 = seg * seglen, c1 = min(m, c0 + seglen);
       double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
       const double vi = pending ? vp[row + 1] : 0.0, wi = pending ? wp[row + 1] : 0.0;
       double acc = 0.0;
-      for (int j = lane; j < m; j += 32) {
-        double a = ar[j];
-        if (pending) {
-          a = __dsub_rn(a, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
-          ar[j] = a;
+      for (int j0 = c0 + lane; j0 < c1; j0 += 32 * TD_U) {
+        double a[TD_U];
+#pragma unroll
+        for (int u = 0; u < TD_U; ++u) {
+          const int j = j0 + 32 * u;
+          a[u] = (j < c1) ? __ldcg(ar + j) : 0.0;
         }
-        acc = fma(a, vs[j], acc);
+#pragma unroll
+        for (int u = 0; u < TD_U; ++u) {
+          const int j = j0 + 32 * u;
+          if (j < c1) {
+            double av = a[u];
+            if (pending) {
+              av = __dsub_rn(av, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
+              __stcg(ar + j, av);
+            }
+            acc = fma(av, vs[j], acc);
+          }
+        }
       }
       for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) pk[row] = tau * acc;
+      if (lane == 0) __stcg(pk + (size_t)seg * s + row, acc);
     }
-    grid.sync();
-    // --- w_k = p - (tau/2)(p.v) v ; (v_k, w_k) become the pending update
+    TD_TICK(5);
+    flag_barrier(flags, (unsigned)(k + 1));
+    TD_TICK(6);
+    // --- next column's row from memory (row k+1 now carries every update but (v_k, w_k)): issued together with
+    // the loads of the products so that the two L2 round trips overlap
+    if (use_pre) {
+      const double* anext = A + (size_t)(k + 1) * s + (k + 2);
+#pragma unroll
+      for (int q = 0; q < PER; ++q) {
+        const int j = tid + q * TD_THREADS;
+        xpre[q] = (j < m - 1) ? __ldcg(anext + j) : 0.0;
+      }
+    }
+    // --- w_k = p - (tau/2)(p.v) v with p = tau A22 v; (v_k, w_k) become the pending update
     part = 0.0;
     for (int j = tid; j < m; j += TD_THREADS) {
-      double p = pk[j];
+      double pg[TD_MAXSEG];
+#pragma unroll
+      for (int g = 0; g < TD_MAXSEG; ++g) pg[g] = (g < nseg) ? __ldcg(pk + (size_t)g * s + j) : 0.0;  // all in flight
+      double p = 0.0;
+#pragma unroll
+      for (int g = 0; g < TD_MAXSEG; ++g) p += pg[g];  // fixed order: deterministic
+      p *= tau;
       wp[j] = p;
       part = fma(p, vs[j], part);
     }
+    TD_TICK(7);
     const double pv = block_sum(part, red);
+    TD_TICK(8);
     const double a2 = -0.5 * tau * pv;
     for (int j = tid; j < m; j += TD_THREADS) {
       wp[j] = fma(a2, vs[j], wp[j]);
@@ -133,9 +253,13 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
     }
     pending = true;
     __syncthreads();
+    TD_TICK(9);
   }
+  if (timing)
+    for (int i = 0; i < 12; ++i) prof[i] = tacc[i];
+#undef TD_TICK
   // the last pending update has tau == 0 (a 1 x 1 column): memory already holds the final corner
-  if (blockIdx.x == 0 && tid == 0) dd[s - 1] = A[(size_t)(s - 1) * s + (s - 1)];
+  if (blockIdx.x == 0 && tid == 0) dd[s - 1] = __ldcg(A + (size_t)(s - 1) * s + (s - 1));
 }
 
 // ---- 2. eigenvalues: multisection on the Sturm count ------------------------------------------------
@@ -387,7 +511,7 @@ backtransform_kernel(int s, int K, const double* __restrict__ Vh, const double* 
 
 void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   if (K < 1 || K > s) fail(2, "eigh: need 1 <= K <= s (K=%d, s=%d)", K, s);
-  DevBuf<double> dd(s), ee(s), tau(s), pbuf((size_t)2 * s), tnorm(1);
+  DevBuf<double> dd(s), ee(s), tau(s), pbuf((size_t)2 * TD_MAXSEG * s), tnorm(1);
   ee.zero(c->stream);
   tau.zero(c->stream);
   if (s == 1) {
@@ -405,10 +529,23 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     int per_sm = 0;
     FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, TD_THREADS, smem));
     if (per_sm < 1) fail(2, "eigh: s=%d needs more shared memory than one SM has", s);
-    int grid = c->sm_count;  // one CTA per SM
-    void* args[] = {&G, &s, &Vh.p, &dd.p, &ee.p, &tau.p, &pbuf.p};
+    int grid = std::min(c->sm_count, 32 * FLAG_PER);  // one CTA per SM
+    const bool prof_on = std::getenv("FLGP_EIGH_PROF") != nullptr;
+    DevBuf<long long> prof(12);
+    long long* profp = prof_on ? prof.p : nullptr;
+    DevBuf<unsigned> flags((size_t)grid * FLAG_STRIDE);
+    flags.zero(c->stream);
+    void* args[] = {&G, &s, &Vh.p, &dd.p, &ee.p, &tau.p, &pbuf.p, &flags.p, &profp};
     FLGP_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(TD_THREADS), args, smem, c->stream));
     c->launches++;
+    if (prof_on) {
+      long long h[12];
+      prof.download(h, 12, c->stream);
+      sync(c);
+      fprintf(stderr, "[flgp eigh prof] tridiag s=%d, cycles per column (CTA 0):", s);
+      for (int i = 0; i < 10; ++i) fprintf(stderr, " %d:%.0f", i, (double)h[i] / (s - 1));
+      fprintf(stderr, "\n");
+    }
   }
   // 2. eigenvalues
   {

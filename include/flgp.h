@@ -98,6 +98,12 @@ int flgp_cross_similarity_se(flgp_ctx* ctx, const double* X, int64_t n, int d, c
 int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int K,
                          int root, double* values, double* vectors, flgp_spectrum** handle);
 
+/* Dense symmetric top-K eigensolver: the RSpectra::eigs_sym(A, k = K) call sites of the Nystrom / GLGP drivers
+ * (src/Fit.cpp:262-278, 410-428) and the engine behind flgp_spectrum_from_z.  A is s x s symmetric (full storage,
+ * column- or row-major alike); values (K) are the K algebraically largest eigenvalues, descending; vectors is
+ * s x K column-major with orthonormal columns (signs arbitrary).  No host LAPACK, no cuSOLVER. */
+int flgp_eigs_sym(flgp_ctx* ctx, const double* A, int s, int K, double* values, double* vectors);
+
 /* heat_kernel_spectrum_cpp (src/Spectrum.cpp:48-76): X (m x d) and X_new (m_new x d, may be NULL with
  * m_new = 0) are concatenated, training rows first.  models = {subsample, kernel, gl, root}. */
 int flgp_heat_kernel_spectrum(flgp_ctx* ctx, const double* X, int64_t m, const double* X_new, int64_t m_new, int d,

@@ -359,3 +359,37 @@ def test_c4_scale_properties(flgp):
     # the pipeline's pruned KNN against the exported full-scan KNN on the same anchors (two different kernels)
     ind = flgp.KNN_cpp(X, np.asfortranarray(U[:, :3]), r)["ind_knn"]
     assert np.array_equal(np.sort(ind, axis=1), Zj)
+
+
+# ------------------------------------------------------------------------------------------- dense eigensolver
+def _sym(rng, s, kind):
+    Q, _ = np.linalg.qr(rng.standard_normal((s, s)))
+    if kind == "decay":          # graph-like: eigenvalues 1, then slowly decaying towards 0
+        lam = 1.0 / (1.0 + 0.05 * np.arange(s)) ** 2
+    elif kind == "clustered":    # exact multiplicities and tight clusters at the top
+        lam = np.sort(np.r_[np.ones(5), np.full(4, 0.9), 0.9 - 1e-9 * np.arange(3), rng.uniform(0, 0.8, s - 12)])[::-1]
+    elif kind == "indefinite":
+        lam = np.sort(rng.uniform(-1, 1, s))[::-1]
+    else:                         # graded over 12 orders of magnitude
+        lam = 10.0 ** (-12.0 * np.arange(s) / s)
+    A = (Q * lam) @ Q.T
+    return np.asfortranarray((A + A.T) / 2), lam
+
+
+@pytest.mark.parametrize("s,K,kind", [(300, 40, "decay"), (257, 257, "decay"), (500, 60, "clustered"), (64, 5, "graded"),
+                                       (400, 30, "indefinite"), (2, 1, "decay"), (1, 1, "decay"), (1000, 120, "decay")])
+def test_eigs_sym_matches_lapack(flgp, s, K, kind):
+    """The eigensolver behind spectrum_from_Z / the eigs_sym seam against LAPACK on dense symmetric matrices."""
+    rng = np.random.default_rng(s + K)
+    A, _ = _sym(rng, s, kind)
+    res = flgp.eigs_sym(A, K)
+    w, V = np.linalg.eigh(A)
+    w, V = w[::-1][:K], V[:, ::-1][:, :K]
+    scale = np.abs(w).max()
+    assert np.abs(res["values"] - w).max() <= 1e-12 * max(scale, 1.0) * s
+    Y = res["vectors"]
+    assert np.abs(Y.T @ Y - np.eye(K)).max() < 1e-10
+    assert np.abs(A @ Y - Y * res["values"]).max() <= 1e-10 * max(scale, 1.0)
+    # invariant subspaces agree wherever the K cut does not split a cluster
+    if K < s and w[-1] - np.linalg.eigvalsh(A)[::-1][K] > 1e-6:
+        assert np.abs(Y @ Y.T - V @ V.T).max() < 1e-8
