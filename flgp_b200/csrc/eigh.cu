@@ -27,7 +27,8 @@ namespace flgp {
 
 namespace {
 
-constexpr int TD_THREADS = 1024;
+constexpr int TD_THREADS_STREAM = 1024;  // streaming pass: as many warps in flight as possible
+constexpr int TD_THREADS_RES = 512;      // resident pass: fewer, fatter threads (cheaper reductions and barriers)
 constexpr int TD_MAXSEG = 16;  // a row of the trailing matrix is split over up to this many warps
 constexpr int TD_U = 4;        // loads in flight per lane in the fused pass
 
@@ -59,10 +60,7 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
 }
 __device__ __forceinline__ void flag_barrier(unsigned* flags, unsigned epoch) {
   __syncthreads();  // this CTA's stores are all issued
-  if (threadIdx.x == 0) {
-    __threadfence();
-    st_release(flags + (size_t)blockIdx.x * FLAG_STRIDE, epoch);
-  }
+  if (threadIdx.x == 0) st_release(flags + (size_t)blockIdx.x * FLAG_STRIDE, epoch);  // cumulative over the bar.sync
   if (threadIdx.x < 32) {
     // every lane watches up to FLAG_PER slots and keeps all its polls in flight together: one round trip per try
     bool done;
@@ -89,12 +87,25 @@ __device__ __forceinline__ void flag_barrier(unsigned* flags, unsigned epoch) {
 // One pass over the trailing matrix and ONE grid barrier per column: the rank-2 update of column k-1
 // (v_{k-1}, w_{k-1}, kept in shared memory by every CTA) is applied while the product A v_k of column k is
 // accumulated from the freshly updated values.  Column k itself is formed redundantly by every CTA from
-// row k in memory minus the pending update, so no barrier is needed between the Householder vector and
-// the pass.  pbuf is double-buffered by the parity of k.
+// row k (published by the pass of column k-1, prefetched across the barrier) minus the pending update, so no
+// barrier is needed between the Householder vector and the pass.  Buffers are double-buffered by parity of k.
+//
+// Two pass modes, columns [k_begin, k_end) per launch:
+//   RESIDENT = false  the trailing matrix streams through L2 (read-modify-write, 16 bytes per element and column:
+//                     L2-bandwidth bound); a row is split over several warps.  On exit the last pending update is
+//                     applied to memory, so that the next launch starts from an up-to-date matrix.
+//   RESIDENT = true   once the trailing matrix fits in the shared memory of the grid (rows dealt round-robin to the
+//                     CTAs, <= TD_RPMAX rows each), every CTA keeps its rows on chip for the rest of the
+//                     factorisation: per column it touches only its own shared memory, publishes |rows| products
+//                     and one row; L2 only carries the vectors.
+constexpr int TD_RPMAX = 12;  // rows per CTA in resident mode (shared-memory capacity)
+constexpr int TD_RACC = 16;   // accumulators per lane, padded to a power of two for the butterfly reduction
+
+template <bool RESIDENT, int TD_THREADS>
 __global__ void __launch_bounds__(TD_THREADS)
-tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* __restrict__ dd, double* __restrict__ ee,
-               double* __restrict__ tau_out, double* __restrict__ pbuf, unsigned* __restrict__ flags,
-               long long* __restrict__ prof) {
+tridiag_kernel(double* __restrict__ A, int s, int k_begin, int k_end, double* __restrict__ Vh, double* __restrict__ dd,
+               double* __restrict__ ee, double* __restrict__ tau_out, double* __restrict__ pbuf,
+               double* __restrict__ rowbuf, unsigned* __restrict__ flags, long long* __restrict__ prof) {
   long long t0 = 0, tacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const bool timing = prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
 #define TD_TICK(i)            \
@@ -104,30 +115,44 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
     t0 = t_;                  \
   }
   extern __shared__ __align__(16) double sm[];
-  double* vp = sm;           // s: pending v_{k-1}; entry q <-> global index k + q
-  double* wp = sm + s;       // s: pending w_{k-1}
-  double* vs = sm + 2 * s;   // s: current  v_k;     entry q <-> global index k + 1 + q
-  double* red = sm + 3 * s;  // 32
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int gwarp = (blockIdx.x * TD_THREADS + tid) >> 5;
-  const int nwarp = (gridDim.x * TD_THREADS) >> 5;
-  bool pending = false;      // is there an update (vp, wp) not yet applied to memory?
-  constexpr int PER = (4096 + TD_THREADS - 1) / TD_THREADS;  // row k is prefetched into registers (s <= 4096)
+  const int M0 = s - k_begin;  // order of the trailing matrix this launch starts from
+  double* vp = sm;             // M0: pending v_{k-1}; entry q <-> global index k + q
+  double* wp = sm + M0;        // M0: pending w_{k-1}
+  double* vs = sm + 2 * M0;    // M0: current  v_k;     entry q <-> global index k + 1 + q
+  double* red = sm + 3 * M0;   // 32
+  double* scratch = red + 32;  // TD_RACC x 32 (RESIDENT)
+  double* As = scratch + TD_RACC * 32;  // RP x LD (RESIDENT): own rows, column c <-> global column k_begin + c
+  const int LD = (M0 + 1) & ~1;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int G = gridDim.x, b = blockIdx.x;
+  const int gwarp = (b * TD_THREADS + tid) >> 5;
+  const int nwarp = (G * TD_THREADS) >> 5;
+  const int RP = (M0 + G - 1) / G;  // rows per CTA (RESIDENT)
+  bool pending = false;             // is there an update (vp, wp) not yet applied to the matrix?
+  constexpr int PER = 4;  // the next column's row is prefetched into registers when it fits PER per thread
   double xpre[PER];
-  const bool use_pre = s <= PER * TD_THREADS;
+  const bool use_pre = M0 <= PER * TD_THREADS;
+  if (RESIDENT) {
+    for (int l = 0; l < RP; ++l) {
+      const int i = k_begin + b + l * G;
+      if (i < s)
+        for (int c = tid; c < M0; c += TD_THREADS) As[(size_t)l * LD + c] = __ldcg(A + (size_t)i * s + k_begin + c);
+    }
+  }
   if (use_pre) {
 #pragma unroll
     for (int q = 0; q < PER; ++q) {
       const int j = tid + q * TD_THREADS;
-      xpre[q] = (j < s - 1) ? __ldcg(A + 1 + j) : 0.0;  // row 0, columns 1..
+      xpre[q] = (j < M0 - 1) ? __ldcg(A + (size_t)k_begin * s + k_begin + 1 + j) : 0.0;  // row k_begin
     }
   }
+  __syncthreads();
 
-  for (int k = 0; k < s - 1; ++k) {
+  for (int k = k_begin; k < k_end; ++k) {
     const int m = s - k - 1;  // length of column k below the diagonal
     const double* arow = A + (size_t)k * s;
     if (timing) t0 = clock64();
-    // --- column k of the up-to-date matrix: memory row k minus the pending rank-2 update (redundant per CTA)
+    // --- column k of the up-to-date matrix: its row minus the pending rank-2 update (redundant per CTA)
     const double v0 = pending ? vp[0] : 0.0, w0 = pending ? wp[0] : 0.0;
     double part = 0.0;
     if (use_pre) {
@@ -169,65 +194,113 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
     for (int j = tid; j < m; j += TD_THREADS) {
       const double v = (j == 0) ? 1.0 : vs[j] * scale;
       vs[j] = v;
-      if ((j >> 5) % gridDim.x == blockIdx.x) Vh[(size_t)k * s + j] = v;  // every CTA stores its share of v_k
+      if ((j >> 5) % G == b) Vh[(size_t)k * s + j] = v;  // every CTA stores its share of v_k
     }
     __syncthreads();
     TD_TICK(3);
-    if (blockIdx.x == (unsigned)(k % gridDim.x) && tid == 0) {
-      double dk = __ldcg(arow + k);
+    if (b == (RESIDENT ? (k - k_begin) % G : k % G) && tid == 0) {  // RESIDENT: the owner of row k
+      double dk = RESIDENT ? As[(size_t)((k - k_begin) / G) * LD + (k - k_begin)] : __ldcg(arow + k);
       if (pending) dk = __dsub_rn(dk, __dadd_rn(__dmul_rn(v0, w0), __dmul_rn(w0, v0)));
       dd[k] = dk;
       ee[k] = beta;
       tau_out[k] = tau;
     }
     TD_TICK(4);
-    // --- fused pass: apply the pending update to rows k+1.., accumulate the products (A22 v_k).  Work item =
-    // (row, segment): a row is split over nseg warps when there are more warps than rows, so that the longest
-    // dependent chain of the step stays short; loads are issued TD_U at a time before any store.
-    int nseg = 1;
-    while (nseg < TD_MAXSEG && (nseg * 2) * m <= nwarp) nseg *= 2;
-    const int seglen = ((m + nseg - 1) / nseg + 31) & ~31;
     double* pk = pbuf + (size_t)(k & 1) * TD_MAXSEG * s;
-    for (int item = gwarp; item < m * nseg; item += nwarp) {
-      const int row = item / nseg, seg = item - row * nseg;
-      const int c0 = seg * seglen, c1 = min(m, c0 + seglen);
-      double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
-      const double vi = pending ? vp[row + 1] : 0.0, wi = pending ? wp[row + 1] : 0.0;
-      double acc = 0.0;
-      for (int j0 = c0 + lane; j0 < c1; j0 += 32 * TD_U) {
-        double a[TD_U];
+    double* rnext = rowbuf + (size_t)((k + 1) & 1) * s;  // row k+1 as the next column needs it
+    int nseg = 1;
+    if (RESIDENT) {
+      // --- resident pass: a thread owns column strips, walks this CTA's live rows, keeps one partial product per row
+      const int cbase = (k + 1) - k_begin;
+      double acc[TD_RACC];
 #pragma unroll
-        for (int u = 0; u < TD_U; ++u) {
-          const int j = j0 + 32 * u;
-          a[u] = (j < c1) ? __ldcg(ar + j) : 0.0;
-        }
+      for (int l = 0; l < TD_RACC; ++l) acc[l] = 0.0;
+      for (int j = tid; j < m; j += TD_THREADS) {
+        const double wpj = pending ? wp[j + 1] : 0.0, vpj = pending ? vp[j + 1] : 0.0, vsj = vs[j];
 #pragma unroll
-        for (int u = 0; u < TD_U; ++u) {
-          const int j = j0 + 32 * u;
-          if (j < c1) {
-            double av = a[u];
+        for (int l = 0; l < TD_RPMAX; ++l) {
+          const int i = k_begin + b + l * G;
+          if (l < RP && i > k && i < s) {  // uniform over the CTA
+            const int row = i - (k + 1);
+            double* ap = As + (size_t)l * LD + cbase + j;
+            double av = *ap;
             if (pending) {
-              av = __dsub_rn(av, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
-              __stcg(ar + j, av);
+              av = __dsub_rn(av, __dadd_rn(__dmul_rn(vp[row + 1], wpj), __dmul_rn(wp[row + 1], vpj)));
+              *ap = av;
             }
-            acc = fma(av, vs[j], acc);
+            acc[l] = fma(av, vsj, acc[l]);
+            if (row == 0 && j > 0) __stcg(rnext + (j - 1), av);  // publish row k+1 for the next column
           }
         }
       }
-      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) __stcg(pk + (size_t)seg * s + row, acc);
+      // 16 partial products per lane -> one per lane pair: butterfly that halves the live values at every step
+      // (16 exchanges instead of 60; the shuffle unit, not the fp64 pipe, was the limiter), then across warps
+#pragma unroll
+      for (int half = TD_RACC / 2, o = 16; half >= 1; half >>= 1, o >>= 1) {
+        const bool upper = (lane & o) != 0;
+#pragma unroll
+        for (int q = 0; q < half; ++q) {
+          const double send = upper ? acc[q] : acc[q + half];
+          const double keep = upper ? acc[q + half] : acc[q];
+          acc[q] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], 1);
+      if ((lane & 1) == 0) scratch[(lane >> 1) * 32 + wid] = acc[0];  // row slot lane/2, this warp's column share
+      __syncthreads();
+      if (wid < RP) {
+        double v = (lane < TD_THREADS / 32) ? scratch[wid * 32 + lane] : 0.0;
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const int i = k_begin + b + wid * G;
+        if (lane == 0 && i > k && i < s) __stcg(pk + (i - (k + 1)), v);
+      }
+    } else {
+      // --- streaming pass: apply the pending update to rows k+1.., accumulate the products (A22 v_k).  Work item =
+      // (row, segment): a row is split over nseg warps when there are more warps than rows, so that the longest
+      // dependent chain of the step stays short; loads are issued TD_U at a time before any store.
+      while (nseg < TD_MAXSEG && (nseg * 2) * m <= nwarp) nseg *= 2;
+      const int seglen = ((m + nseg - 1) / nseg + 31) & ~31;
+      for (int item = gwarp; item < m * nseg; item += nwarp) {
+        const int row = item / nseg, seg = item - row * nseg;
+        const int c0 = seg * seglen, c1 = min(m, c0 + seglen);
+        double* ar = A + (size_t)(k + 1 + row) * s + (k + 1);
+        const double vi = pending ? vp[row + 1] : 0.0, wi = pending ? wp[row + 1] : 0.0;
+        double acc = 0.0;
+        for (int j0 = c0 + lane; j0 < c1; j0 += 32 * TD_U) {
+          double a[TD_U];
+#pragma unroll
+          for (int u = 0; u < TD_U; ++u) {
+            const int j = j0 + 32 * u;
+            a[u] = (j < c1) ? __ldcg(ar + j) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < TD_U; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < c1) {
+              double av = a[u];
+              if (pending) {
+                av = __dsub_rn(av, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
+                __stcg(ar + j, av);
+              }
+              acc = fma(av, vs[j], acc);
+              if (row == 0 && j > 0) __stcg(rnext + (j - 1), av);  // publish row k+1 for the next column
+            }
+          }
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) __stcg(pk + (size_t)seg * s + row, acc);
+      }
     }
     TD_TICK(5);
     flag_barrier(flags, (unsigned)(k + 1));
     TD_TICK(6);
-    // --- next column's row from memory (row k+1 now carries every update but (v_k, w_k)): issued together with
-    // the loads of the products so that the two L2 round trips overlap
+    // --- the next column's row (it carries every update but (v_k, w_k)): issued together with the loads of the
+    // products so that the two L2 round trips overlap
     if (use_pre) {
-      const double* anext = A + (size_t)(k + 1) * s + (k + 2);
 #pragma unroll
       for (int q = 0; q < PER; ++q) {
         const int j = tid + q * TD_THREADS;
-        xpre[q] = (j < m - 1) ? __ldcg(anext + j) : 0.0;
+        xpre[q] = (j < m - 1) ? __ldcg(rnext + j) : 0.0;
       }
     }
     // --- w_k = p - (tau/2)(p.v) v with p = tau A22 v; (v_k, w_k) become the pending update
@@ -258,22 +331,47 @@ tridiag_kernel(double* __restrict__ A, int s, double* __restrict__ Vh, double* _
   if (timing)
     for (int i = 0; i < 12; ++i) prof[i] = tacc[i];
 #undef TD_TICK
-  // the last pending update has tau == 0 (a 1 x 1 column): memory already holds the final corner
-  if (blockIdx.x == 0 && tid == 0) dd[s - 1] = __ldcg(A + (size_t)(s - 1) * s + (s - 1));
+  if (k_end >= s - 1) {
+    // the last pending update has tau == 0 (a 1 x 1 column): the matrix already holds the final corner
+    if (RESIDENT) {
+      const int o = (s - 1) - k_begin;
+      if (b == o % G && tid == 0) dd[s - 1] = As[(size_t)(o / G) * LD + o];
+    } else if (b == 0 && tid == 0) {
+      dd[s - 1] = __ldcg(A + (size_t)(s - 1) * s + (s - 1));
+    }
+  } else if (!RESIDENT && pending) {
+    // hand-over: apply the pending update (entries q <-> global index k_end + q) to the rest of the matrix
+    const int mr = s - k_end;
+    for (int row = gwarp; row < mr; row += nwarp) {
+      double* ar = A + (size_t)(k_end + row) * s + k_end;
+      const double vi = vp[row], wi = wp[row];
+      for (int j = lane; j < mr; j += 32)
+        __stcg(ar + j, __dsub_rn(__ldcg(ar + j), __dadd_rn(__dmul_rn(vi, wp[j]), __dmul_rn(wi, vp[j]))));
+    }
+  }
 }
 
+constexpr int BI_WARPS = 4;  // warps per eigenvalue: 128 probes per pass
+// 1/q to ~1 ulp: hardware seed (20 bits) + two Newton steps; |q| >= pivmin (normal), so no special cases arise.
+// The division is the whole dependent chain of a Sturm step; the IEEE sequence is ~3x longer.
+__device__ __forceinline__ double fast_rcp(double q) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+  r = fma(fma(-q, r, 1.0), r, r);
+  r = fma(fma(-q, r, 1.0), r, r);
+  return r;
+}
 // ---- 2. eigenvalues: multisection on the Sturm count ------------------------------------------------
-// one warp per wanted eigenvalue; lam_out[kk], kk = 0..K-1 descending  <=>  ascending index s-1-kk.
-__global__ void __launch_bounds__(256)
+// one CTA per wanted eigenvalue; lam_out[kk], kk = 0..K-1 descending  <=>  ascending index s-1-kk.
+__global__ void __launch_bounds__(BI_WARPS * 32)
 bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee, int s, int K, double* __restrict__ lam_out,
               double* __restrict__ tnorm_out) {
   extern __shared__ __align__(16) double sm[];
   double* d = sm;       // s
   double* e2 = sm + s;  // s
-  __shared__ double red[32];
   const int tid = threadIdx.x, lane = tid & 31;
   double gl = DBL_MAX, gu = -DBL_MAX, emax = 0.0;
-  for (int i = tid; i < s; i += 256) {
+  for (int i = tid; i < s; i += BI_WARPS * 32) {
     double di = dd[i];
     double el = (i > 0) ? fabs(ee[i - 1]) : 0.0, er = (i < s - 1) ? fabs(ee[i]) : 0.0;
     d[i] = di;
@@ -288,7 +386,7 @@ bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee, int 
     gu = fmax(gu, __shfl_xor_sync(0xffffffffu, gu, o));
     emax = fmax(emax, __shfl_xor_sync(0xffffffffu, emax, o));
   }
-  __shared__ double rgl[8], rgu[8], rem[8];
+  __shared__ double rgl[BI_WARPS], rgu[BI_WARPS], rem[BI_WARPS];
   if (lane == 0) {
     rgl[tid >> 5] = gl;
     rgu[tid >> 5] = gu;
@@ -298,12 +396,11 @@ bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee, int 
   gl = rgl[0];
   gu = rgu[0];
   emax = rem[0];
-  for (int w = 1; w < 8; ++w) {
+  for (int w = 1; w < BI_WARPS; ++w) {
     gl = fmin(gl, rgl[w]);
     gu = fmax(gu, rgu[w]);
     emax = fmax(emax, rem[w]);
   }
-  (void)red;
   const double ulp = DBL_EPSILON, safemin = DBL_MIN;
   const double pivmin = safemin * fmax(1.0, emax);
   const double tnorm = fmax(fabs(gl), fabs(gu));
@@ -311,24 +408,33 @@ bisect_kernel(const double* __restrict__ dd, const double* __restrict__ ee, int 
   gu = gu + 2.1 * tnorm * ulp * s + 2.1 * pivmin;
   if (blockIdx.x == 0 && tid == 0 && tnorm_out) *tnorm_out = tnorm;
 
-  const int kk = blockIdx.x * 8 + (tid >> 5);
-  if (kk >= K) return;
-  const int t = s - 1 - kk;  // ascending index of the wanted eigenvalue
-  double lo = gl, hi = gu;   // count(lo) <= t < count(hi)
+  const int kk = blockIdx.x;  // one CTA per wanted eigenvalue
+  const int t = s - 1 - kk;   // ascending index of the wanted eigenvalue
+  double lo = gl, hi = gu;    // count(lo) <= t < count(hi)
+  // (NP + 1)-way multisection, one probe per thread: the Sturm recurrence is a pure latency chain (reciprocal,
+  // multiply, subtract, clamp), so the probes of a pass run on different warps rather than interleaved in one
+  constexpr int NP = BI_WARPS * 32;
   for (int pass = 0; pass < 40; ++pass) {
     const double width = hi - lo;
     const double tol = fmax(2.0 * ulp * fmax(fabs(lo), fabs(hi)), pivmin);
-    if (width <= tol) break;
-    const double x = lo + width * ((double)(lane + 1) / 33.0);
-    const int cnt = sturm_count(d, e2, s, x, pivmin);
-    const unsigned ball = __ballot_sync(0xffffffffu, cnt >= t + 1);
-    const int f = ball ? (__ffs(ball) - 1) : 32;  // first lane whose point is above lambda_t
-    const double xhi = __shfl_sync(0xffffffffu, x, f & 31);
-    const double xlo = __shfl_sync(0xffffffffu, x, (f - 1) & 31);
-    if (f < 32) hi = xhi;
+    if (width <= tol) break;  // uniform over the CTA
+    const double x = lo + width * ((double)(tid + 1) / (double)(NP + 1));
+    double q = 1.0;
+    int cnt = 0;
+    for (int i = 0; i < s; ++i) {
+      const double ei = (i > 0) ? e2[i - 1] : 0.0;
+      double qq = (d[i] - x) - ei * fast_rcp(q);  // the recurrence of sturm_count (core_math.cuh)
+      qq = (fabs(qq) < pivmin) ? -pivmin : qq;
+      cnt += (qq < 0.0);
+      q = qq;
+    }
+    const int f = __syncthreads_count(cnt < t + 1);  // probes 0..f-1 lie below lambda_t, f.. above
+    const double xlo = lo + width * ((double)f / (double)(NP + 1));
+    const double xhi = lo + width * ((double)(f + 1) / (double)(NP + 1));
+    if (f < NP) hi = xhi;
     if (f > 0) lo = xlo;
   }
-  if (lane == 0) lam_out[kk] = 0.5 * (lo + hi);
+  if (tid == 0) lam_out[kk] = 0.5 * (lo + hi);
 }
 
 // ---- 3. inverse iteration ------------------------------------------------------------------------
@@ -341,7 +447,7 @@ __device__ __forceinline__ double hash_uniform(unsigned i, unsigned kk) {
   return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;  // (-1, 1)
 }
 
-// factor T - lam*I = P L U  (dgttrf recurrence);  dg: U diagonal, du: U first super-diagonal,
+// factor T - lam*I = P L U  (dgttrf recurrence);  dg: RECIPROCAL of the U diagonal, du: U first super-diagonal,
 // du2: second super-diagonal, dl: multipliers, piv: 1 where rows i,i+1 were interchanged.
 __global__ void __launch_bounds__(64)
 invit_factor_kernel(const double* __restrict__ dd, const double* __restrict__ ee, int s, int K,
@@ -360,7 +466,7 @@ invit_factor_kernel(const double* __restrict__ dd, const double* __restrict__ ee
     if (fabs(dcur) >= fabs(sub)) {
       if (fabs(dcur) < tiny) dcur = (dcur < 0.0) ? -tiny : tiny;
       const double fact = sub / dcur;
-      dg[AT(i)] = dcur;
+      dg[AT(i)] = 1.0 / dcur;  // the solves multiply by the reciprocal: no division on their dependent chain
       du[AT(i)] = ucur;
       du2[AT(i)] = 0.0;
       dl[AT(i)] = fact;
@@ -369,7 +475,7 @@ invit_factor_kernel(const double* __restrict__ dd, const double* __restrict__ ee
       ucur = unext;
     } else {
       const double fact = dcur / sub;
-      dg[AT(i)] = sub;
+      dg[AT(i)] = 1.0 / sub;
       du[AT(i)] = dnext;
       du2[AT(i)] = unext;
       dl[AT(i)] = fact;
@@ -379,7 +485,7 @@ invit_factor_kernel(const double* __restrict__ dd, const double* __restrict__ ee
     }
   }
   if (fabs(dcur) < tiny) dcur = (dcur < 0.0) ? -tiny : tiny;
-  dg[AT(s - 1)] = dcur;
+  dg[AT(s - 1)] = 1.0 / dcur;
   for (int i = 0; i < s; ++i) X[AT(i)] = hash_uniform((unsigned)i, (unsigned)kk);
 #undef AT
 }
@@ -422,7 +528,7 @@ invit_solve_kernel(int s, int K, const double* __restrict__ dg, const double* __
   }
   X[AT(s - 1)] = bi;
   // backward: U with two super-diagonals
-  double x1 = X[AT(s - 1)] / dg[AT(s - 1)];
+  double x1 = X[AT(s - 1)] * dg[AT(s - 1)];
   X[AT(s - 1)] = x1;
   nrm = fma(x1, x1, nrm);
   double x2 = 0.0;
@@ -440,7 +546,7 @@ invit_solve_kernel(int s, int K, const double* __restrict__ dg, const double* __
 #pragma unroll
     for (int u = 0; u < PF; ++u)
       if (u < cnt) {
-        double xi = (b[u] - u1[u] * x1 - u2[u] * x2) / g[u];
+        double xi = (b[u] - u1[u] * x1 - u2[u] * x2) * g[u];
         X[AT(i0 - u)] = xi;
         nrm = fma(xi, xi, nrm);
         x2 = x1;
@@ -449,7 +555,15 @@ invit_solve_kernel(int s, int K, const double* __restrict__ dg, const double* __
   }
   // normalise (guards against overflow in the next solve); clusters are re-orthogonalised next
   const double inv = 1.0 / sqrt(nrm);
-  for (int i = 0; i < s; ++i) X[AT(i)] *= inv;
+  for (int i0 = 0; i0 < s; i0 += PF) {  // loads batched ahead of the stores: one L2 round trip per PF rows
+    double t[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (i0 + u < s) t[u] = X[AT(i0 + u)];
+#pragma unroll
+    for (int u = 0; u < PF; ++u)
+      if (i0 + u < s) X[AT(i0 + u)] = t[u] * inv;
+  }
 #undef AT
 }
 
@@ -484,27 +598,162 @@ invit_mgs_kernel(int s, int K, const int* __restrict__ cstart, double* __restric
 }
 
 // ---- 4. back-transformation ----------------------------------------------------------------------
+// Y = H_0 H_1 ... H_{s-2} X with the reflectors grouped WY_NB at a time (compact WY, LAPACK dlarft/dlarfb):
+//   H_{k0} ... H_{k0+nb-1} = I - V T V^T,  T upper triangular, T(i,i) = tau_i,
+//   T(0:i, i) = -tau_i T(0:i, 0:i) (V(:, 0:i)^T v_i).
+// The sequential depth drops from s reflectors (one reduction each) to s / WY_NB blocks (two streamed passes over
+// the block's reflectors each); columns of X are independent, so CTAs never synchronise with each other.
+// Block b, reflector i <-> column k0 + i; row offset t <-> global row k0 + 1 + t; V(t, i) = Vh[(k0+i) s + t - i], t >= i.
+constexpr int WY_NB = 32;
+
 __global__ void __launch_bounds__(256)
-backtransform_kernel(int s, int K, const double* __restrict__ Vh, const double* __restrict__ tau,
-                     const double* __restrict__ X, double* __restrict__ Y) {
-  extern __shared__ __align__(16) double sm[];
-  double* x = sm;  // s
-  __shared__ double red[32];
-  const int kk = blockIdx.x, tid = threadIdx.x;
-  for (int i = tid; i < s; i += 256) x[i] = X[(size_t)i * K + kk];
-  __syncthreads();
-  for (int k = s - 2; k >= 0; --k) {
-    const double tk = tau[k];
-    if (tk == 0.0) continue;
-    const int m = s - k - 1;
-    const double* v = Vh + (size_t)k * s;
-    double part = 0.0;
-    for (int j = tid; j < m; j += 256) part = fma(v[j], x[k + 1 + j], part);
-    const double dot = block_sum(part, red) * tk;
-    for (int j = tid; j < m; j += 256) x[k + 1 + j] = fma(-dot, v[j], x[k + 1 + j]);
-    __syncthreads();  // the next reflector reads elements other threads just wrote
+wy_T_kernel(int s, const double* __restrict__ Vh, const double* __restrict__ tau, double* __restrict__ Tg) {
+  constexpr int RT = 64;
+  __shared__ double Vs[RT][WY_NB + 1];
+  __shared__ double Gs[WY_NB][WY_NB + 1];
+  __shared__ double Ts[WY_NB][WY_NB + 1];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * WY_NB;
+  const int nbk = min(WY_NB, (s - 1) - k0);
+  const int mb = s - 1 - k0;
+  const int a2 = (tid >> 4) * 2, b2 = (tid & 15) * 2;  // this thread's 2 x 2 tile of G = V^T V
+  double g00 = 0.0, g01 = 0.0, g10 = 0.0, g11 = 0.0;
+  for (int t0 = 0; t0 < mb; t0 += RT) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < RT * WY_NB / 256; ++q) {
+      const int e = tid + q * 256, i = e / RT, tt = e % RT, t = t0 + tt;
+      Vs[tt][i] = (i < nbk && t < mb && t >= i) ? Vh[(size_t)(k0 + i) * s + (t - i)] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int tt = 0; tt < RT; ++tt) {
+      const double va0 = Vs[tt][a2], va1 = Vs[tt][a2 + 1], vb0 = Vs[tt][b2], vb1 = Vs[tt][b2 + 1];
+      g00 = fma(va0, vb0, g00);
+      g01 = fma(va0, vb1, g01);
+      g10 = fma(va1, vb0, g10);
+      g11 = fma(va1, vb1, g11);
+    }
   }
-  for (int i = tid; i < s; i += 256) Y[(size_t)i + (size_t)s * kk] = x[i];
+  Gs[a2][b2] = g00;
+  Gs[a2][b2 + 1] = g01;
+  Gs[a2 + 1][b2] = g10;
+  Gs[a2 + 1][b2 + 1] = g11;
+  for (int e = tid; e < WY_NB * WY_NB; e += 256) Ts[e / WY_NB][e % WY_NB] = 0.0;
+  __syncthreads();
+  // column i of T from columns 0..i-1 (one warp; row r per lane)
+  if (tid < 32) {
+    for (int i = 0; i < nbk; ++i) {
+      const double ti = tau[k0 + i];
+      double acc = 0.0;
+      if (tid < i)
+        for (int cc = tid; cc < i; ++cc) acc = fma(Ts[tid][cc], Gs[cc][i], acc);
+      __syncwarp();
+      if (tid < i) Ts[tid][i] = -ti * acc;
+      if (tid == i) Ts[i][i] = ti;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < WY_NB * WY_NB; e += 256) Tg[(size_t)blockIdx.x * WY_NB * WY_NB + e] = Ts[e / WY_NB][e % WY_NB];
+}
+
+constexpr int WY_NC = 2;         // eigenvector columns per CTA
+constexpr int WY_THREADS = 512;
+constexpr int WY_U = 8;          // loads in flight per thread
+
+__global__ void __launch_bounds__(WY_THREADS)
+wy_apply_kernel(int s, int K, const double* __restrict__ Vh, const double* __restrict__ Tg,
+                const double* __restrict__ X, double* __restrict__ Y) {
+  extern __shared__ __align__(16) double sm[];
+  double* Xs = sm;                      // WY_NC x s
+  double* Ts = Xs + (size_t)WY_NC * s;  // WY_NB x WY_NB
+  double* Ws = Ts + WY_NB * WY_NB;      // WY_NB x WY_NC : V^T x
+  double* W2 = Ws + WY_NB * WY_NC;      // WY_NB x WY_NC : T V^T x
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int c0 = blockIdx.x * WY_NC;
+  for (int e = tid; e < WY_NC * s; e += WY_THREADS) {
+    const int c = e / s, i = e - c * s;
+    Xs[e] = (c0 + c < K) ? X[(size_t)i * K + c0 + c] : 0.0;
+  }
+  const int nblocks = (s - 1 + WY_NB - 1) / WY_NB;
+  for (int blk = nblocks - 1; blk >= 0; --blk) {
+    const int k0 = blk * WY_NB;
+    const int nbk = min(WY_NB, (s - 1) - k0);
+    const int mb = s - 1 - k0;
+    __syncthreads();  // Xs of the previous block is final; Ts / Ws may be overwritten
+    for (int e = tid; e < WY_NB * WY_NB; e += WY_THREADS) Ts[e] = Tg[(size_t)blk * WY_NB * WY_NB + e];
+    // phase 1: Ws(i, c) = v_i . x_c ; a warp per reflector, lanes along the rows
+    for (int i = wid; i < WY_NB; i += WY_THREADS / 32) {
+      double acc[WY_NC];
+#pragma unroll
+      for (int c = 0; c < WY_NC; ++c) acc[c] = 0.0;
+      if (i < nbk) {
+        const int k = k0 + i, mi = s - k - 1;
+        const double* v = Vh + (size_t)k * s;
+        for (int j0 = lane; j0 < mi; j0 += 32 * WY_U) {
+          double vv[WY_U];
+#pragma unroll
+          for (int u = 0; u < WY_U; ++u) {
+            const int j = j0 + 32 * u;
+            vv[u] = (j < mi) ? v[j] : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < WY_U; ++u) {
+            const int j = j0 + 32 * u;
+            if (j < mi) {
+#pragma unroll
+              for (int c = 0; c < WY_NC; ++c) acc[c] = fma(vv[u], Xs[(size_t)c * s + k + 1 + j], acc[c]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < WY_NC; ++c) {
+        double a = acc[c];
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) Ws[i * WY_NC + c] = a;
+      }
+    }
+    __syncthreads();
+    // W2 = T Ws (T upper triangular)
+    if (tid < WY_NB * WY_NC) {
+      const int i = tid / WY_NC, c = tid % WY_NC;
+      double a = 0.0;
+      for (int ip = i; ip < nbk; ++ip) a = fma(Ts[i * WY_NB + ip], Ws[ip * WY_NC + c], a);
+      W2[tid] = a;
+    }
+    __syncthreads();
+    // phase 2: x_c(t) -= sum_i V(t, i) W2(i, c) ; a thread per row, reflectors in batches
+    for (int t = tid; t < mb; t += WY_THREADS) {
+      double xa[WY_NC];
+#pragma unroll
+      for (int c = 0; c < WY_NC; ++c) xa[c] = Xs[(size_t)c * s + k0 + 1 + t];
+      for (int i0 = 0; i0 < nbk; i0 += WY_U) {
+        double vv[WY_U];
+#pragma unroll
+        for (int u = 0; u < WY_U; ++u) {
+          const int i = i0 + u;
+          vv[u] = (i < nbk && t >= i) ? Vh[(size_t)(k0 + i) * s + (t - i)] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < WY_U; ++u) {
+          const int i = i0 + u;
+          if (i < nbk) {
+#pragma unroll
+            for (int c = 0; c < WY_NC; ++c) xa[c] = fma(-vv[u], W2[i * WY_NC + c], xa[c]);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < WY_NC; ++c) Xs[(size_t)c * s + k0 + 1 + t] = xa[c];
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < WY_NC * s; e += WY_THREADS) {
+    const int c = e / s, i = e - c * s;
+    if (c0 + c < K) Y[(size_t)i + (size_t)s * (c0 + c)] = Xs[e];
+  }
 }
 
 }  // namespace
@@ -522,29 +771,61 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     return;
   }
   DevBuf<double> Vh((size_t)s * s);
-  // 1. tridiagonalisation (cooperative, persistent)
+  // 1. tridiagonalisation (cooperative, persistent): streaming launch while the trailing matrix is larger than the
+  //    grid's shared memory, resident launch for the rest
   {
-    size_t smem = (size_t)(3 * s + 32) * sizeof(double);
-    FLGP_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, TD_THREADS, smem));
-    if (per_sm < 1) fail(2, "eigh: s=%d needs more shared memory than one SM has", s);
-    int grid = std::min(c->sm_count, 32 * FLAG_PER);  // one CTA per SM
+    const int grid = std::min(c->sm_count, 32 * FLAG_PER);  // one CTA per SM
+    int smem_max = 0;
+    FLGP_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+    auto smem_need = [&](int M0, bool resident) {
+      size_t words = (size_t)3 * M0 + 32 + TD_RACC * 32;
+      if (resident) words += (size_t)((M0 + grid - 1) / grid) * ((M0 + 1) & ~1);
+      return words * sizeof(double);
+    };
+    int M_res = 0;  // largest trailing order that can be kept resident
+    for (int M0 = std::min(s, 4 * TD_THREADS_RES); M0 >= 2; --M0)
+      if ((M0 + grid - 1) / grid <= TD_RPMAX && smem_need(M0, true) + 1024 <= (size_t)smem_max) {
+        M_res = M0;
+        break;
+      }
+    if (std::getenv("FLGP_EIGH_NO_RESIDENT")) M_res = 0;
+    const int k_switch = (M_res >= 2) ? std::max(0, s - M_res) : s - 1;  // columns [0, k_switch) stream through L2
     const bool prof_on = std::getenv("FLGP_EIGH_PROF") != nullptr;
-    DevBuf<long long> prof(12);
-    long long* profp = prof_on ? prof.p : nullptr;
+    DevBuf<long long> prof(24);
     DevBuf<unsigned> flags((size_t)grid * FLAG_STRIDE);
+    DevBuf<double> rowbuf((size_t)2 * s);
     flags.zero(c->stream);
-    void* args[] = {&G, &s, &Vh.p, &dd.p, &ee.p, &tau.p, &pbuf.p, &flags.p, &profp};
-    FLGP_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(TD_THREADS), args, smem, c->stream));
-    c->launches++;
+    if (prof_on) prof.zero(c->stream);
+    auto launch = [&](bool resident, int kb, int ke, long long* profp) {
+      const size_t smem = smem_need(s - kb, resident);
+      if (smem + 1024 > (size_t)smem_max) fail(2, "eigh: s=%d needs more shared memory than one SM has", s);
+      const void* fn = resident ? (const void*)tridiag_kernel<true, TD_THREADS_RES>
+                                : (const void*)tridiag_kernel<false, TD_THREADS_STREAM>;
+      const int threads = resident ? TD_THREADS_RES : TD_THREADS_STREAM;
+      FLGP_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      int per_sm = 0;
+      FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+      if (per_sm < 1) fail(2, "eigh: the tridiagonalisation kernel does not fit on an SM (s=%d)", s);
+      int s_ = s, kb_ = kb, ke_ = ke;
+      void* args[] = {&G, &s_, &kb_, &ke_, &Vh.p, &dd.p, &ee.p, &tau.p, &pbuf.p, &rowbuf.p, &flags.p, &profp};
+      FLGP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, c->stream));
+      c->launches++;
+    };
+    if (k_switch > 0) launch(false, 0, std::min(k_switch, s - 1), prof_on ? prof.p : nullptr);
+    if (k_switch < s - 1) launch(true, k_switch, s - 1, prof_on ? prof.p + 12 : nullptr);
     if (prof_on) {
-      long long h[12];
-      prof.download(h, 12, c->stream);
+      long long h[24];
+      prof.download(h, 24, c->stream);
       sync(c);
-      fprintf(stderr, "[flgp eigh prof] tridiag s=%d, cycles per column (CTA 0):", s);
-      for (int i = 0; i < 10; ++i) fprintf(stderr, " %d:%.0f", i, (double)h[i] / (s - 1));
-      fprintf(stderr, "\n");
+      fprintf(stderr, "[flgp eigh prof] tridiag s=%d, streaming columns [0,%d), resident [%d,%d); cycles per column (CTA 0)\n",
+              s, k_switch, k_switch, s - 1);
+      for (int ph = 0; ph < 2; ++ph) {
+        const int cols = ph == 0 ? std::min(k_switch, s - 1) : (s - 1 - k_switch);
+        if (cols <= 0) continue;
+        fprintf(stderr, "  %s:", ph == 0 ? "streaming" : "resident ");
+        for (int i = 0; i < 10; ++i) fprintf(stderr, " %d:%.0f", i, (double)h[12 * ph + i] / cols);
+        fprintf(stderr, "\n");
+      }
     }
   }
   // 2. eigenvalues
@@ -552,7 +833,7 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     size_t smem = (size_t)2 * s * sizeof(double);
     if (smem > 48 * 1024)
       FLGP_CUDA(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLGP_LAUNCH(c, bisect_kernel, ceil_div(K, 8), 256, smem, dd.p, ee.p, s, K, lam, tnorm.p);
+    FLGP_LAUNCH(c, bisect_kernel, K, BI_WARPS * 32, smem, dd.p, ee.p, s, K, lam, tnorm.p);
   }
   // clusters of close eigenvalues (host decides; K doubles)
   std::vector<double> lam_h(K);
@@ -577,12 +858,16 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     FLGP_LAUNCH(c, invit_solve_kernel, ceil_div(K, 64), 64, 0, s, K, dg.p, du.p, du2.p, dl.p, piv.p, X.p);
     FLGP_LAUNCH(c, invit_mgs_kernel, K, 256, 0, s, K, cs.p, X.p);
   }
-  // 4. back-transformation
+  // 4. back-transformation (blocked compact WY)
   {
-    size_t smem = (size_t)s * sizeof(double);
+    const int nblocks = (s - 1 + WY_NB - 1) / WY_NB;
+    DevBuf<double> Tg((size_t)nblocks * WY_NB * WY_NB);
+    FLGP_LAUNCH(c, wy_T_kernel, nblocks, 256, 0, s, Vh.p, tau.p, Tg.p);
+    size_t smem = ((size_t)WY_NC * s + WY_NB * WY_NB + 2 * WY_NB * WY_NC) * sizeof(double);
     if (smem > 48 * 1024)
-      FLGP_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    FLGP_LAUNCH(c, backtransform_kernel, K, 256, smem, s, K, Vh.p, tau.p, X.p, Y);
+      FLGP_CUDA(cudaFuncSetAttribute(wy_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    FLGP_LAUNCH(c, wy_apply_kernel, ceil_div(K, WY_NC), WY_THREADS, smem, s, K, Vh.p, Tg.p, X.p, Y);
+    sync(c);  // Tg is released on return
   }
   sync(c);
 }
