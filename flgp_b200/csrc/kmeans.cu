@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -69,8 +71,24 @@ __global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, in
 __device__ __forceinline__ double km_ub(double score, double M, double xn, double delta2) {
   return sqrt(fmax((score - M) + xn, 0.0) + delta2) * (1.0 + 1e-14);
 }
+// The same two bounds through a single-precision square root (a handful of instructions instead of ~35): they only
+// steer the pruning, so being 2^-21 looser costs nothing; outside the float range the fp64 root is used.
+__device__ __forceinline__ double km_ub_fast(double score, double M, double xn, double delta2) {
+  const double v = fmax((score - M) + xn, 0.0) + delta2;
+  if (!(v > 1e-30 && v < 1e30)) return sqrt(v) * (1.0 + 1e-14);
+  return (double)sqrtf((float)v) * (1.0 + 4.8e-7);  // float conversion and root: 2 half-ulp errors of 6e-8 each
+}
+__device__ __forceinline__ double km_lb_fast(double score, double M, double xn, double delta2) {
+  const double v = fmax(((score - M) + xn) - delta2, 0.0);
+  if (!(v > 1e-30 && v < 1e30)) return (v < 1e30 || v != v) ? 0.0 : sqrt(v) * (1.0 - 1e-14);
+  return (double)sqrtf((float)v) * (1.0 - 4.8e-7);
+}
 __device__ __forceinline__ void km_radius(unsigned long long* Rbits, int a, double ub) {
-  atomicMax(&Rbits[a], (unsigned long long)__double_as_longlong(ub));  // non-negative doubles order like their bits
+  // non-negative doubles order like their bits.  The radius usually covers the point already (a possibly stale,
+  // i.e. smaller, cached value only costs a redundant atomic): one atomic per point on 2000 addresses is the
+  // difference between a compute-bound and an atomics-bound pass.
+  const unsigned long long b = (unsigned long long)__double_as_longlong(ub);
+  if (b > Rbits[a]) atomicMax(&Rbits[a], b);
 }
 
 __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, const double* x, int32_t* assign,
@@ -276,7 +294,7 @@ kmeans_assign_tiled(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
 
 // centroid update, one thread per centre; move[j] >= |c_new - c_old| (for the pruned passes' radius bound)
 __global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, int d, Fx fx, double* C, double* sizes,
-                                     double* move) {
+                                     double* move, unsigned long long* maxmove_bits) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= s) return;
   long long cnt = acc[(size_t)2 * s * d + j];
@@ -291,7 +309,11 @@ __global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, i
       C[j + (size_t)s * k] = cnew;
     }
   }
-  if (move) move[j] = sqrt(mv) * (1.0 + 1e-12);
+  if (move) {
+    const double mj = sqrt(mv) * (1.0 + 1e-12);
+    move[j] = mj;
+    atomicMax(maxmove_bits, (unsigned long long)__double_as_longlong(mj));  // non-negative doubles order like their bits
+  }
 }
 
 // rows of X that this rank owns -> bit patterns in the (zeroed) centre buffer
@@ -322,7 +344,9 @@ constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster'
 __global__ void __launch_bounds__(256)
 kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned long long* __restrict__ Rprev,
                     const double* __restrict__ move, double eta, int32_t* __restrict__ list_j,
-                    double* __restrict__ list_cc, int32_t* __restrict__ len) {
+                    double* __restrict__ list_cc, int32_t* __restrict__ len, double* __restrict__ lthr,
+                    double4* __restrict__ cl, const unsigned long long* __restrict__ maxmove_bits,
+                    unsigned long long* __restrict__ Rcur) {
   __shared__ double kcc[KM_LMAX];
   __shared__ int kj[KM_LMAX];
   __shared__ int count;
@@ -334,7 +358,15 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   }
   __syncthreads();
   const double Ra = __longlong_as_double((long long)Rprev[a]) + move[a];
-  const double thr = (2.0 * Ra + eta) * (1.0 + 1e-9);  // inflated: keeping more centres is always safe
+  // A member's freshly computed bound ub0 can exceed the carried radius by the rounding slack of a score
+  // (sqrt(5 Delta) < eta): the list is made complete to 2 (Ra + eta) + eta, so that no member ever reaches past it
+  // (a full scan over all centres would stall its whole warp).  Keeping more centres is always safe.
+  const double thr = (2.0 * (Ra + eta) + eta) * (1.0 + 1e-9);
+  if (tid == 0) {
+    lthr[a] = thr;  // every centre outside the list is at least this far from centre a
+    // members that keep centre a are within Ra of it (their bound grew by move[a]); evaluated points add theirs
+    Rcur[a] = (unsigned long long)__double_as_longlong(Ra * (1.0 + 1e-15));
+  }
   for (int j = tid; j < s; j += 256) {
     if (j == a) continue;
     double cc = 0.0;
@@ -353,8 +385,11 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   }
   __syncthreads();
   const int cnt = count;
-  if (cnt > KM_LMAX) {
-    if (tid == 0) len[a] = -1;
+  if (cnt > KM_LMAX) {  // no list: every centre counts as a neighbour
+    if (tid == 0) {
+      len[a] = -1;
+      cl[a] = make_double4(move[a], __longlong_as_double((long long)*maxmove_bits), INFINITY, 0.0);
+    }
     return;
   }
   // bitonic sort of (cc, j) ascending; padding is (+inf, INT_MAX); ties broken by j => deterministic lists
@@ -379,34 +414,54 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
       }
       __syncthreads();
     }
+  double mv = 0.0;  // largest displacement among the listed centres (lower-bound decay of this cluster's points)
   for (int t = tid; t < cnt; t += 256) {
     list_j[(size_t)a * KM_LMAX + t] = kj[t];
     list_cc[(size_t)a * KM_LMAX + t] = kcc[t];
+    mv = fmax(mv, move[kj[t]]);
   }
-  if (tid == 0) len[a] = cnt;
+  for (int o = 16; o; o >>= 1) mv = fmax(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+  __shared__ double smv[8];
+  if ((tid & 31) == 0) smv[tid >> 5] = mv;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) mv = fmax(mv, smv[w]);
+    cl[a] = make_double4(move[a], mv, thr, 0.0);
+    len[a] = cnt;
+  }
 }
 
+struct __align__(16) KmWork {
+  int p, a;  // position in the sorted layout, current centre
+  double l;  // lower bound after this pass's centre moves
+};
+
+// Evaluation of the points on the work list, one thread per point: walks the neighbour list of the point's centre
+// (sorted by centre-centre distance) up to the point's own 2 ub + eta and leaves new bounds behind.  Sums are integer
+// limbs, so a reassignment is an exact -x / +x on the persistent accumulators.
 template <int D>
 __global__ void __launch_bounds__(256)
-kmeans_assign_pruned(const double* __restrict__ Xs, int64_t n, const double* __restrict__ rec, int s, Fx fx,
+kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__ rec, int s, Fx fx,
                      int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
                      const double* __restrict__ list_cc, const int32_t* __restrict__ len, double M, double delta2,
-                     double eta, unsigned long long* __restrict__ Rcur, const int32_t* __restrict__ strag,
-                     const int* __restrict__ nstrag) {
-  // generic path: one thread per straggler (a point that left its sorted segment, or whose staged list was
-  // too short); walks its own list from global memory
+                     double eta, unsigned long long* __restrict__ Rcur, const KmWork* __restrict__ work,
+                     const int* __restrict__ nwork, const double* __restrict__ lthr, double2* __restrict__ UL,
+                     unsigned long long* __restrict__ nfull) {
   constexpr int STR = (D + 2) / 2 * 2;
   int changed = 0;
-  const int total = *nstrag;
+  const int total = *nwork;
   for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-    const int64_t p = strag[idx];
+    const KmWork wr = work[idx];  // coalesced 16-byte records: position, centre, moved lower bound
+    const int64_t p = wr.p;
+    const int a = wr.a;
+    const double4 xv = Xs4[p];  // one 32-byte sector per point
+    const double xa[4] = {xv.x, xv.y, xv.z, xv.w};
     double x[D], xn = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-      x[k] = Xs[p + n * k];
+      x[k] = xa[k];
       xn = fma(x[k], x[k], xn);
     }
-    const int a = as[p];
     auto score = [&](int j) {
       const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
       double cr[STR];
@@ -421,31 +476,53 @@ kmeans_assign_pruned(const double* __restrict__ Xs, int64_t n, const double* __r
       for (int k = 0; k < D; ++k) e = fma(x[k], cr[k], e);
       return e;
     };
-    double best = score(a);
+    double best = score(a), sec = INFINITY;  // sec: second smallest score seen
     int bj = a;
-    const double thr = (2.0 * km_ub(best, M, xn, delta2) + eta) * (1.0 + 1e-9);
+    const double ub0 = km_ub_fast(best, M, xn, delta2);
+    if (ub0 + eta <= wr.l) {  // the tightened upper bound is enough: nothing can beat or tie centre a
+      UL[p] = make_double2(ub0, wr.l);
+      continue;
+    }
+    const double thr = (2.0 * ub0 + eta) * (1.0 + 1e-9);
     const int L = len[a];
-    if (L >= 0) {
+    double ccb = lthr[a];             // every centre that was NOT scanned is at least this far from centre a
+    bool full = (L < 0) || !(thr <= ccb);  // no list, or the bound reaches past the radius the list is complete to
+    if (!full) {
       const int32_t* lj = list_j + (size_t)a * KM_LMAX;
       const double* lc = list_cc + (size_t)a * KM_LMAX;
       for (int q = 0; q < L; ++q) {
-        if (lc[q] >= thr) break;  // sorted by centre-centre distance: nothing further can win or tie
+        if (lc[q] >= thr) {  // sorted by centre-centre distance: nothing further can win or tie
+          ccb = lc[q];
+          break;
+        }
         const int j = lj[q];
         const double e = score(j);
         if (e < best || (e == best && j < bj)) {
+          sec = best;
           best = e;
           bj = j;
+        } else if (e < sec) {
+          sec = e;
         }
       }
-    } else {  // list overflow: this cluster's members scan every centre (rare)
+    } else {  // scan every centre (list overflow; otherwise excluded by the slack in the list radius)
+      if (nfull) atomicAdd(nfull, 1ull);
+      ccb = INFINITY;
       for (int j = 0; j < s; ++j) {
+        if (j == a) continue;
         const double e = score(j);
         if (e < best || (e == best && j < bj)) {
+          sec = best;
           best = e;
           bj = j;
+        } else if (e < sec) {
+          sec = e;
         }
       }
     }
+    // bounds for the passes that follow: u >= |x - c_bj|, l <= distance to every other centre
+    const double ub = (bj == a) ? ub0 : km_ub_fast(best, M, xn, delta2);
+    UL[p] = make_double2(ub, fmin(km_lb_fast(sec, M, xn, delta2), (ccb - ub0) * (1.0 - 1e-14)));
     if (bj != a) {
       ++changed;
       as[p] = bj;
@@ -461,127 +538,81 @@ kmeans_assign_pruned(const double* __restrict__ Xs, int64_t n, const double* __r
       atomicAdd(&acc[(size_t)2 * s * D + a], (unsigned long long)(-1ll));
       atomicAdd(&acc[(size_t)2 * s * D + bj], 1ull);
     }
-    km_radius(Rcur, bj, km_ub(best, M, xn, delta2));  // radius of the (new) cluster for the next pass
+    km_radius(Rcur, bj, ub);  // radius of the (new) cluster for the next pass
   }
   if (changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
 }
 
-// fast path: one CTA per sorted segment (= the members of one cluster at the last sort).  The cluster's
-// candidate records are staged in shared memory once; every member then runs the brute-force kernel's inner
-// loop over them (broadcast LDS, DFMA chain), stopping at its own 2 ub + eta.  Points that have left the
-// cluster since the sort, or whose bound reaches past the staged part of the list, go to the straggler list.
-constexpr int KM_LS = 192;
+// Bound test, one streaming pass over the points (any order; the cluster-sorted order makes the per-cluster lookups
+// and the survivors' list walks coherent).  Hamerly-style bounds carried from pass to pass: u >= |x - c_a| and
+// l <= |x - c_j| for every j != a.  The centres have moved since they were taken: c_a by move[a]; the centres of a's
+// current neighbour list by at most nbmove[a]; a centre outside the list is at least lthr[a] from c_a, hence
+// lthr[a] - u from x.  If u + eta <= l still holds, every other centre is farther than c_a by eta, its COMPUTED
+// score is strictly larger (eta^2 > 2 Delta) and the point keeps its centre - without its coordinates being read.
+// The points that fail are compacted (per CTA in shared memory, one global atomic per CTA) into the work list that
+// kmeans_assign_pruned evaluates.  cl[a] = {move, nbmove, lthr, -}.
+constexpr int KM_BT = 256, KM_BQ = 8;  // threads per CTA, points per thread
 
-template <int D>
-__global__ void __launch_bounds__(256)
-kmeans_assign_segment(const double* __restrict__ Xs, int64_t n, const double* __restrict__ rec, int s, Fx fx,
-                      int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
-                      const double* __restrict__ list_cc, const int32_t* __restrict__ len,
-                      const int* __restrict__ seg_start, double M, double delta2, double eta,
-                      unsigned long long* __restrict__ Rcur, int32_t* __restrict__ strag, int* __restrict__ nstrag) {
-  constexpr int STR = (D + 2) / 2 * 2;
-  __shared__ __align__(16) double srec[(KM_LS + 1) * STR];
-  __shared__ double scc[KM_LS];
-  __shared__ int sj[KM_LS];
-  __shared__ double sred[8];
-  const int a = blockIdx.x, tid = threadIdx.x;
-  const int beg = seg_start[a], end = seg_start[a + 1];
-  if (beg == end) return;
-  const int L = len[a];
-  const int Ls = (L < 0) ? 0 : min(L, KM_LS);
-  const bool whole = (L >= 0 && L <= KM_LS);
-  for (int t = tid; t < STR; t += 256) srec[t] = rec[(size_t)a * STR + t];
-  for (int q = tid; q < Ls; q += 256) {
-    const int j = list_j[(size_t)a * KM_LMAX + q];
-    sj[q] = j;
-    scc[q] = list_cc[(size_t)a * KM_LMAX + q];
+__global__ void __launch_bounds__(KM_BT)
+kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* __restrict__ cl, double eta,
+                     double2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
+                     unsigned long long* __restrict__ nskip) {
+  __shared__ KmWork wl[KM_BT * KM_BQ];
+  __shared__ int wcount, wbase;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t c0 = (int64_t)blockIdx.x * (KM_BT * KM_BQ);
+  if (tid == 0) wcount = 0;
+  __syncthreads();
+  double2 ul_in[KM_BQ];
+  int as_in[KM_BQ];
+#pragma unroll
+  for (int q = 0; q < KM_BQ; ++q) {  // everything is requested before the first value is looked at
+    const int64_t p = c0 + q * KM_BT + tid;
+    const bool valid = p < n;
+    as_in[q] = valid ? as[p] : 0;
+    ul_in[q] = valid ? UL[p] : make_double2(0.0, 0.0);
   }
-  __syncthreads();
-  for (int t = tid; t < Ls * STR; t += 256) srec[STR + t] = rec[(size_t)sj[t / STR] * STR + (t % STR)];
-  __syncthreads();
-  int changed = 0;
-  double rmax = 0.0;
-  for (int p = beg + tid; p < end; p += 256) {
-    bool straggler = (as[p] != a);
-    double x[D], xn = 0.0, best = 0.0;
-    int bj = a;
-    if (!straggler) {
+  int skipped = 0;
 #pragma unroll
-      for (int k = 0; k < D; ++k) {
-        x[k] = Xs[p + n * k];
-        xn = fma(x[k], x[k], xn);
+  for (int q = 0; q < KM_BQ; ++q) {  // uniform trip count: the ballot sees whole warps
+    const int64_t p = c0 + q * KM_BT + tid;
+    const bool valid = p < n;
+    bool need = false;
+    double l = 0.0;
+    if (valid) {
+      const double4 ca = cl[as_in[q]];
+      const double u = (ul_in[q].x + ca.x) * (1.0 + 1e-15);
+      l = fmin((ul_in[q].y - ca.y) * (1.0 - 1e-15) - 1e-300, (ca.z - u) * (1.0 - 1e-15));
+      if (u + eta <= l) {
+        UL[p] = make_double2(u, l);
+        ++skipped;
+      } else {
+        need = true;  // the evaluation receives the moved lower bound in its work record and rewrites UL[p]
       }
-      best = srec[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) best = fma(x[k], srec[k], best);
-      const double thr = (2.0 * km_ub(best, M, xn, delta2) + eta) * (1.0 + 1e-9);
-      bool done = false;
-      for (int q = 0; q < Ls; ++q) {
-        if (scc[q] >= thr) {  // sorted by centre-centre distance: nothing further can win or tie
-          done = true;
-          break;
-        }
-        const double* rj = srec + (size_t)(q + 1) * STR;
-        double e = rj[D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) e = fma(x[k], rj[k], e);
-        const int j = sj[q];
-        if (e < best || (e == best && j < bj)) {
-          best = e;
-          bj = j;
-        }
-      }
-      if (!done && !whole) straggler = true;  // the bound reaches past the staged part of the list
     }
-    if (straggler) {  // warp-aggregated append
-      const unsigned act = __activemask();
-      const int lane = tid & 31, lead = __ffs(act) - 1;
+    const unsigned mw = __ballot_sync(0xffffffffu, need);
+    if (mw) {
+      const int lead = __ffs(mw) - 1;
       int base = 0;
-      if (lane == lead) base = atomicAdd(nstrag, __popc(act));
-      base = __shfl_sync(act, base, lead);
-      strag[base + __popc(act & ((1u << lane) - 1))] = p;
-      continue;
-    }
-    const double ub = km_ub(best, M, xn, delta2);
-    if (bj != a) {
-      ++changed;
-      as[p] = bj;
-#pragma unroll
-      for (int k = 0; k < D; ++k) {
-        long long h, l;
-        fx_encode(fx, x[k], &h, &l);
-        atomicAdd(&acc[a + (size_t)s * k], (unsigned long long)(-h));
-        atomicAdd(&acc[(size_t)s * D + a + (size_t)s * k], (unsigned long long)(-l));
-        atomicAdd(&acc[bj + (size_t)s * k], (unsigned long long)h);
-        atomicAdd(&acc[(size_t)s * D + bj + (size_t)s * k], (unsigned long long)l);
+      if (lane == lead) base = atomicAdd(&wcount, __popc(mw));
+      base = __shfl_sync(0xffffffffu, base, lead);
+      if (need) {
+        KmWork wr;
+        wr.p = (int)p;
+        wr.a = as_in[q];
+        wr.l = l;
+        wl[base + __popc(mw & ((1u << lane) - 1))] = wr;
       }
-      atomicAdd(&acc[(size_t)2 * s * D + a], (unsigned long long)(-1ll));
-      atomicAdd(&acc[(size_t)2 * s * D + bj], 1ull);
-      km_radius(Rcur, bj, ub);
-    } else {
-      rmax = fmax(rmax, ub);
     }
-  }
-  // one radius atomic and one `changed` atomic per CTA
-  for (int o = 16; o; o >>= 1) {
-    rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
-    changed += __shfl_xor_sync(0xffffffffu, changed, o);
-  }
-  __shared__ int schg[8];
-  if ((tid & 31) == 0) {
-    sred[tid >> 5] = rmax;
-    schg[tid >> 5] = changed;
   }
   __syncthreads();
-  if (tid == 0) {
-    double m = sred[0];
-    int cgd = schg[0];
-    for (int w = 1; w < 8; ++w) {
-      m = fmax(m, sred[w]);
-      cgd += schg[w];
-    }
-    if (m > 0.0) km_radius(Rcur, a, m);
-    if (cgd) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)cgd);
+  const int nw = wcount;
+  if (tid == 0 && nw) wbase = atomicAdd(nwork, nw);
+  __syncthreads();
+  for (int w = tid; w < nw; w += KM_BT) work[wbase + w] = wl[w];
+  if (nskip) {
+    for (int o = 16; o; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+    if (lane == 0 && skipped) atomicAdd(nskip, (unsigned long long)skipped);
   }
 }
 
@@ -602,8 +633,9 @@ __global__ void kmeans_offsets_kernel(const long long* __restrict__ cnt, int s, 
 // src_perm == nullptr: source is the original order (row i <-> index i)
 __global__ void __launch_bounds__(256)
 kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc, int d, const int32_t* __restrict__ asrc,
-                      const int32_t* __restrict__ src_perm, int* __restrict__ cursor, double* __restrict__ Xdst,
-                      int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm) {
+                      const int32_t* __restrict__ src_perm, int* __restrict__ cursor, double4* __restrict__ Xdst,
+                      int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm, const double2* __restrict__ ULsrc,
+                      double2* __restrict__ ULdst, const double4* __restrict__ X4src) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int a = asrc[i];
@@ -618,7 +650,24 @@ kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc,
   const int pos = base + __popc(peers & ((1u << lane) - 1));
   dst_perm[pos] = src_perm ? src_perm[i] : (int32_t)i;
   adst[pos] = a;
-  for (int k = 0; k < d; ++k) Xdst[pos + n * k] = Xsrc[i + ldsrc * k];
+  if (X4src) {
+    Xdst[pos] = X4src[i];
+  } else {  // first sort: from the caller's column-major matrix to one 32-byte record per point
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < d; ++k) v[k] = Xsrc[i + ldsrc * k];
+    Xdst[pos] = make_double4(v[0], v[1], v[2], v[3]);
+  }
+  // bounds travel with the point; before the first sort there are none: u = inf, l = 0 force a full evaluation
+  ULdst[pos] = ULsrc ? ULsrc[i] : make_double2(INFINITY, 0.0);
+}
+
+// the KNN stage reads the sorted rows column-major
+__global__ void kmeans_x4_to_colmajor_kernel(const double4* __restrict__ X4, int64_t n, int d, double* __restrict__ Xs) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const double4 v = X4[p];
+  const double a[4] = {v.x, v.y, v.z, v.w};
+  for (int k = 0; k < d; ++k) Xs[p + n * k] = a[k];
 }
 
 __global__ void kmeans_unpermute_kernel(const int32_t* __restrict__ as, const int32_t* __restrict__ perm, int64_t n,
@@ -696,9 +745,14 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   const double eta = 2.0 * std::sqrt(2.0 * Delta) + 1e-12 * maxabs;           // eta^2 > 2 Delta with room to spare
   DevBuf<unsigned long long> Rbits[2];
   DevBuf<int32_t> nlist, nlen, perm[2], as[2];
-  DevBuf<double> ncc, move, Xs[2];
+  DevBuf<double> ncc, move, lthr;
+  DevBuf<double4> Xs4[2];
+  DevBuf<double2> UL[2];
+  DevBuf<KmWork> work;
+  DevBuf<double4> cl;
+  const bool prof_skip = std::getenv("FLGP_KMEANS_PROF") != nullptr;
+  DevBuf<unsigned long long> maxmove, nskip;
   DevBuf<int> cursor, seg_start, nstrag;
-  DevBuf<int32_t> strag;
   DevBuf<long long> acc_red;  // all-reduced copy of the local accumulators (multi-GPU)
   if (pruned) {
     Rbits[0].alloc(s);
@@ -710,12 +764,19 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     cursor.alloc(s);
     seg_start.alloc(s + 1);
     nstrag.alloc(1);
-    strag.alloc(std::max<int64_t>(n_local, 1));
+    work.alloc(std::max<int64_t>(n_local, 1));
     for (int b = 0; b < 2; ++b) {
       perm[b].alloc(std::max<int64_t>(n_local, 1));
       as[b].alloc(std::max<int64_t>(n_local, 1));
-      Xs[b].alloc(std::max<int64_t>(n_local * d, 1));
+      Xs4[b].alloc(std::max<int64_t>(n_local, 1));
+      UL[b].alloc(std::max<int64_t>(n_local, 1));
     }
+    lthr.alloc(s);
+    cl.alloc(s);
+    maxmove.alloc(1);
+    nskip.alloc(2);
+    maxmove.zero(c->stream);
+    nskip.zero(c->stream);
     if (c->nranks > 1) acc_red.alloc(words);
     Rbits[0].zero(c->stream);
   }
@@ -729,11 +790,13 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     const int nxt = have_sorted ? 1 - cur : 0;
     if (n_local > 0) {
       if (have_sorted)
-        FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, Xs[cur].p, n_local, n_local, d, as[cur].p,
-                    perm[cur].p, cursor.p, Xs[nxt].p, as[nxt].p, perm[nxt].p);
+        FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, (const double*)nullptr, n_local, n_local, d,
+                    as[cur].p, perm[cur].p, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, UL[cur].p, UL[nxt].p,
+                    Xs4[cur].p);
       else
         FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, X, n_local, ldx, d, assign,
-                    (const int32_t*)nullptr, cursor.p, Xs[nxt].p, as[nxt].p, perm[nxt].p);
+                    (const int32_t*)nullptr, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, (const double2*)nullptr,
+                    UL[nxt].p, (const double4*)nullptr);
     }
     cur = nxt;
     have_sorted = true;
@@ -748,23 +811,24 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
-    if (!brute && (!have_sorted || last_strag * 16 > n_local)) resort();
+    if (!brute && (!have_sorted || moved_since_sort * 8 > n_local)) resort();
     // when timing is on, the assign+accumulate work gets its own CUDA-event pair per pass
     StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_pass", 2.0 * s * d * (double)n_local,
                    (8.0 * d + 4.0) * (double)n_local);
     if (!brute) {
       unsigned long long* Rprev = Rbits[rsel].p;
       unsigned long long* Rcur = Rbits[1 - rsel].p;
-      FLGP_CUDA(cudaMemsetAsync(Rcur, 0, sizeof(unsigned long long) * s, c->stream));
-      FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p);
+      FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p, lthr.p, cl.p,
+                  maxmove.p, Rcur);
       FLGP_CUDA(cudaMemsetAsync(nstrag.p, 0, sizeof(int), c->stream));
       if (n_local > 0) {
         const int sgrid = c->sm_count * 8;
+        FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, cl.p, eta,
+                    UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr);
 #define FLGP_PRUNED(D_)                                                                                          \
-  FLGP_LAUNCH(c, (kmeans_assign_segment<D_>), s, 256, 0, Xs[cur].p, n_local, rec.p, s, fx, as[cur].p, uacc,       \
-              nlist.p, ncc.p, nlen.p, seg_start.p, Moff, delta2, eta, Rcur, strag.p, nstrag.p);                   \
-  FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs[cur].p, n_local, rec.p, s, fx, as[cur].p, uacc,    \
-              nlist.p, ncc.p, nlen.p, Moff, delta2, eta, Rcur, strag.p, nstrag.p)
+  FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs4[cur].p, rec.p, s, fx, as[cur].p, uacc,            \
+              nlist.p, ncc.p, nlen.p, Moff, delta2, eta, Rcur, work.p, nstrag.p, lthr.p, UL[cur].p,               \
+              prof_skip ? nskip.p + 1 : nullptr)
         switch (d) {
           case 1: FLGP_PRUNED(1); break;
           case 2: FLGP_PRUNED(2); break;
@@ -794,7 +858,9 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       red = acc_red.p;
     }
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
-    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr);
+    if (pruned) maxmove.zero(c->stream);
+    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
+                pruned ? maxmove.p : nullptr);
     FLGP_CUDA(cudaMemcpyAsync(c->pinned, red + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
     if (!brute) FLGP_CUDA(cudaMemcpyAsync(c->pinned + 1, nstrag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     sync(c);
@@ -804,13 +870,23 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   }
   if (have_sorted && n_local > 0)
     FLGP_LAUNCH(c, kmeans_unpermute_kernel, ceil_div(n_local, 256), 256, 0, as[cur].p, perm[cur].p, n_local, assign);
+  if (pruned && std::getenv("FLGP_KMEANS_PROF")) {
+    unsigned long long h[2] = {0, 0};
+    nskip.download(h, 2, c->stream);
+    sync(c);
+    fprintf(stderr, "[flgp kmeans prof] %d passes, %.1f%% of the point-passes after the first skipped by their bounds, "
+            "%llu full scans\n", it, it > 1 ? 100.0 * (double)h[0] / ((double)n_local * (it - 1)) : 0.0, h[1]);
+  }
   if (iters_out) *iters_out = it;
   if (sorted_out) {
     sorted_out->valid = have_sorted;
     if (have_sorted) {
       // hand the cluster-sorted layout to the next stage (KNN): radii are those of the last pass; the centres
       // have moved by at most move[] since (zero when the loop stopped because nothing changed)
-      sorted_out->Xs = std::move(Xs[cur]);
+      sorted_out->Xs.alloc(std::max<int64_t>(n_local * d, 1));
+      if (n_local > 0)
+        FLGP_LAUNCH(c, kmeans_x4_to_colmajor_kernel, ceil_div(n_local, 256), 256, 0, Xs4[cur].p, n_local, d,
+                    sorted_out->Xs.p);
       sorted_out->perm = std::move(perm[cur]);
       sorted_out->as = std::move(as[cur]);
       sorted_out->Rbits = std::move(Rbits[rsel]);
