@@ -13,9 +13,9 @@ The n rows are sharded over the ranks in contiguous blocks (strong scaling: n is
 
 `value`   : n / (device-timed seconds per step), inputs resident in HBM.
 `e2e`     : the same through the host-buffer C ABI (H2D of the shard, D2H of mean+variance inside the timed region).
-`roofline`: the dominant kernel (k-means assign+accumulate, FP64-FMA bound) against the FP64 FMA throughput measured
-            in-process (MEASURED_PEAKS.json has HBM and bf16 only); `roofline_hbm` for the Z-streaming kernels
-            against the measured HBM copy bandwidth.
+`roofline`: the kernel with the largest share of the step, against the FP64 FMA throughput measured in-process
+            (MEASURED_PEAKS.json has HBM and bf16 only); `roofline_kernels` lists the other single-launch kernels the
+            same way; `roofline_hbm` rates the Z-streaming stages against the measured HBM copy bandwidth.
 """
 from __future__ import annotations
 
@@ -32,6 +32,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the ncu --set full captures committed under profiles/
+NCU_TRAFFIC = {}
 
 PARS = (10.0, 0.01)   # (t, noise variance): fixed hyper-parameters
 SIGMA = 1e-5
@@ -154,7 +157,7 @@ def run_reference(args):
                        "sample_rows": n},
             "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------ ours
@@ -286,18 +289,33 @@ def run_ours(args):
                         gbs=(v["bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 and v["bytes"] else None)
                 for k, v in agg.items()}
     peaks = measured_peaks()
-    ka = agg.get("kmeans_assign_kernel")
-    roof = None
-    if ka and ka["ms"] > 0:
-        ach = ka["flops"] / (ka["ms"] * 1e-3) / 1e12
-        roof = {"bound": "fp64", "kernel": "kmeans_assign_small<3,4>", "achieved": ach, "peak": dfma_peak,
-                "unit": "TFLOP/s", "frac": ach / dfma_peak if dfma_peak else None, "traffic": None,
-                "launch_ms": ka["ms"] / ka["calls"],
-                "algorithmic_flops_per_launch": ka["flops"] / ka["calls"],
-                "peak_source": "FP64 FMA throughput measured in-process by flgp_dfma_peak (register-resident DFMA "
-                               "loop); MEASURED_PEAKS.json carries no fp64 figure, the kernel is FP64-pipe bound, "
-                               "neither HBM- nor tensor-bound",
-                "share_of_step": ka["ms"] / args.steps / ms_step}
+    # single-launch stages = kernels; each against the roofline that bounds it.  fp64 peak: measured
+    # in-process (MEASURED_PEAKS.json carries HBM and bf16 only); traffic: dram bytes of one launch from the committed
+    # `ncu --set full` capture named in `traffic_source` (None where no capture exists).
+    fp64_src = ("FP64 FMA throughput measured in-process by flgp_dfma_peak (register-resident DFMA loop); "
+                "MEASURED_PEAKS.json carries no fp64 figure")
+    kernels = {
+        "kmeans_assign_kernel": ("kmeans_assign_small<3,4>", "fp64", NCU_TRAFFIC.get("kmeans_assign_small")),
+        "eigh_tridiag_resident": ("tridiag_kernel<true,512>", "fp64", NCU_TRAFFIC.get("tridiag_resident")),
+        "eigh_tridiag_streaming": ("tridiag_kernel<false,1024>", "fp64", NCU_TRAFFIC.get("tridiag_streaming")),
+    }
+    roofs = []
+    for st_name, (kname, bound, traffic) in kernels.items():
+        a = agg.get(st_name)
+        if not a or a["ms"] <= 0 or not a["flops"]:
+            continue
+        ach = a["flops"] / (a["ms"] * 1e-3) / 1e12
+        roofs.append({"bound": bound, "kernel": kname, "achieved": ach, "peak": dfma_peak, "unit": "TFLOP/s",
+                      "frac": ach / dfma_peak if dfma_peak else None,
+                      "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
+                      "launch_ms": a["ms"] / a["calls"], "algorithmic_flops_per_launch": a["flops"] / a["calls"],
+                      "peak_source": fp64_src, "share_of_step": a["ms"] / args.steps / ms_step})
+    roofs.sort(key=lambda r: -r["share_of_step"])
+    roof = roofs[0] if roofs else None
+    if roof and roof["kernel"].startswith("tridiag"):
+        roof["note"] = ("latency bound, not pipe bound: s-1 dependent column steps, each = on-chip symmetric product + one "
+                        "grid-wide flag barrier (~2 us) + two block reductions; cycle breakdown per column in "
+                        "profiles/README.md")
     hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
     hb = {}
     for nm in ("lae", "graph_laplacian", "gram"):
@@ -321,6 +339,7 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
+            "roofline_kernels": roofs,
             "roofline_hbm": roof_hbm,
             "stages_ms_per_step": per_step,
             "path_info": info,
@@ -335,12 +354,21 @@ def run_ours(args):
                                 "sample": "oracle port of the reference path, all stages, %d of 10M rows (same d, s, r, "
                                           "K, iter.max), %d threads; the R package itself cannot run here" %
                                           (ncpu, cores)}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else this process (or NCCL) prints went to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # libraries (NCCL prints its version banner on stdout) must not pollute the one-line contract
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)

@@ -886,18 +886,10 @@ int flgp_hk_from_spectrum(flgp_spectrum* h, int K, double t, const int32_t* idx0
     dl.upload(lam.data(), K, c->stream);
     lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, KK, d0.p, n0, V0.p, KK, false);
     lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, KK, d1.p, n1, V1.p, KK, false);
-    // rows are KK long but only the first K columns enter: strided operands with ld = KK
-    // gemm_nt_run assumes ld == K, so when K < KK compact through the general kernel below
-    if (K == KK) {
-      gemm_nt_run(c, V0.p, V1.p, dl.p, n0, n1, K, dH.p, n0);
-    } else {
-      DevBuf<double> A0((size_t)n0 * K), A1((size_t)n1 * K);
-      FLGP_CUDA(cudaMemcpy2DAsync(A0.p, K * sizeof(double), V0.p, KK * sizeof(double), K * sizeof(double), n0,
-                                  cudaMemcpyDeviceToDevice, c->stream));
-      FLGP_CUDA(cudaMemcpy2DAsync(A1.p, K * sizeof(double), V1.p, KK * sizeof(double), K * sizeof(double), n1,
-                                  cudaMemcpyDeviceToDevice, c->stream));
-      gemm_nt_run(c, A0.p, A1.p, dl.p, n0, n1, K, dH.p, n0);
-      sync(c);
+    // rows are KK long but only the first K columns enter: the tensor maps carry the pitch KK, no compaction
+    {
+      StageScope sg(c, "hk_gemm", 2.0 * K * (double)n0 * n1, 8.0 * (double)n0 * n1);
+      gemm_nt_ld_run(c, V0.p, KK, V1.p, KK, dl.p, n0, n1, K, dH.p, n0);
     }
     dH.download(H, (size_t)n0 * n1, c->stream);
     sync(c);

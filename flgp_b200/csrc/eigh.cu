@@ -811,8 +811,21 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
       FLGP_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(threads), args, smem, c->stream));
       c->launches++;
     };
-    if (k_switch > 0) launch(false, 0, std::min(k_switch, s - 1), prof_on ? prof.p : nullptr);
-    if (k_switch < s - 1) launch(true, k_switch, s - 1, prof_on ? prof.p + 12 : nullptr);
+    // flops of columns [a, b): sum over k of 4 (s-k-1)^2  (symmetric product + rank-2 update)
+    auto td_flops = [&](int a, int b) {
+      double f = 0.0;
+      for (int k = a; k < b; ++k) f += 4.0 * (double)(s - k - 1) * (double)(s - k - 1);
+      return f;
+    };
+    if (k_switch > 0) {
+      const int ke = std::min(k_switch, s - 1);
+      StageScope st(c, "eigh_tridiag_streaming", td_flops(0, ke), 4.0 * td_flops(0, ke));  // 16 B per element and column
+      launch(false, 0, ke, prof_on ? prof.p : nullptr);
+    }
+    if (k_switch < s - 1) {
+      StageScope st(c, "eigh_tridiag_resident", td_flops(k_switch, s - 1), 0.0);
+      launch(true, k_switch, s - 1, prof_on ? prof.p + 12 : nullptr);
+    }
     if (prof_on) {
       long long h[24];
       prof.download(h, 24, c->stream);
@@ -833,6 +846,7 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     size_t smem = (size_t)2 * s * sizeof(double);
     if (smem > 48 * 1024)
       FLGP_CUDA(cudaFuncSetAttribute(bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    StageScope st(c, "eigh_bisect");
     FLGP_LAUNCH(c, bisect_kernel, K, BI_WARPS * 32, smem, dd.p, ee.p, s, K, lam, tnorm.p);
   }
   // clusters of close eigenvalues (host decides; K doubles)
@@ -852,14 +866,18 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   DevBuf<double> dg(sk), du(sk), du2(sk), dl(sk), X(sk);
   DevBuf<unsigned char> piv(sk);
   const double tiny = DBL_EPSILON * std::max(tn, DBL_MIN / DBL_EPSILON);
-  FLGP_LAUNCH(c, invit_factor_kernel, ceil_div(K, 64), 64, 0, dd.p, ee.p, s, K, lam, tiny, dg.p, du.p, du2.p, dl.p,
-              piv.p, X.p);
-  for (int it = 0; it < 3; ++it) {
-    FLGP_LAUNCH(c, invit_solve_kernel, ceil_div(K, 64), 64, 0, s, K, dg.p, du.p, du2.p, dl.p, piv.p, X.p);
-    FLGP_LAUNCH(c, invit_mgs_kernel, K, 256, 0, s, K, cs.p, X.p);
+  {
+    StageScope st(c, "eigh_inverse_iteration");
+    FLGP_LAUNCH(c, invit_factor_kernel, ceil_div(K, 64), 64, 0, dd.p, ee.p, s, K, lam, tiny, dg.p, du.p, du2.p, dl.p,
+                piv.p, X.p);
+    for (int it = 0; it < 3; ++it) {
+      FLGP_LAUNCH(c, invit_solve_kernel, ceil_div(K, 64), 64, 0, s, K, dg.p, du.p, du2.p, dl.p, piv.p, X.p);
+      FLGP_LAUNCH(c, invit_mgs_kernel, K, 256, 0, s, K, cs.p, X.p);
+    }
   }
   // 4. back-transformation (blocked compact WY)
   {
+    StageScope st(c, "eigh_backtransform", 4.0 * s * (double)s * K / 2.0, 0.0);
     const int nblocks = (s - 1 + WY_NB - 1) / WY_NB;
     DevBuf<double> Tg((size_t)nblocks * WY_NB * WY_NB);
     FLGP_LAUNCH(c, wy_T_kernel, nblocks, 256, 0, s, Vh.p, tau.p, Tg.p);

@@ -3,11 +3,157 @@
 // the K x K blocks of the GPR tail and the folds W M W^T.  One strided, shared-memory tiled FMA
 // kernel (64 x 64 tile, 4 x 4 per thread, ascending-k accumulation => deterministic).
 // The diagonal scaling is fused into the A-operand load, as the reference scales V0's columns first.
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint (no -lcuda)
+
 #include "kernels.cuh"
 
 namespace flgp {
 
 namespace {
+
+// ---- FP64 tensor-core GEMM, operands staged by TMA ---------------------------------------------------------------
+// C(i, j) = sum_k A(i,k) sc[k] B(j,k), A: M x K and B: N x K, both row-major (k contiguous) = the "row.col" operand
+// layout of mma.sync.m8n8k4.f64 (tcgen05 has no fp64 kind; DMMA is the fp64 tensor path of sm_100a).
+// CTA tile 64 x 64, K step 16: one TMA box of 64 rows x 128 bytes per operand and stage, SWIZZLE_128B so that the
+// fragment loads (8 rows x 4 k) are bank-conflict free; DG_STAGES-deep mbarrier pipeline, one producer thread.
+// 4 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA tiles (32 accumulator registers per thread).
+constexpr int DG_T = 64, DG_K = 16, DG_STAGES = 4;
+constexpr uint32_t DG_STAGE_BYTES = 2u * DG_T * DG_K * sizeof(double);  // A box + B box
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+// element (row, k) of a 64 x 16 box stored with the 128-byte swizzle: 16-byte chunk index XOR (row mod 8)
+__device__ __forceinline__ double box_at(const double* box, int row, int k) {
+  return box[row * DG_K + ((((k >> 1) ^ (row & 7)) << 1) | (k & 1))];
+}
+
+__global__ void __launch_bounds__(128)
+dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const double* __restrict__ sc, int64_t M, int64_t N, int K, double* __restrict__ C, int64_t ldc) {
+  extern __shared__ __align__(1024) unsigned char dsm_raw[];
+  // 1024-byte alignment of every box is what SWIZZLE_128B requires
+  double* boxes = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t full[DG_STAGES];
+  __shared__ double scs[1024];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wm = (wid >> 1) * 32, wn = (wid & 1) * 32;  // this warp's corner inside the CTA tile
+  const int i0 = blockIdx.y * DG_T, j0 = blockIdx.x * DG_T;
+  const int nk = (K + DG_K - 1) / DG_K;
+  if (tid == 0) {
+    for (int st = 0; st < DG_STAGES; ++st) mbar_init(&full[st], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int kt) {
+    const int st = kt % DG_STAGES;
+    double* a = boxes + (size_t)st * 2 * DG_T * DG_K;
+    mbar_expect_tx(&full[st], DG_STAGE_BYTES);
+    tma_load_2d(a, &mapA, kt * DG_K, i0, &full[st]);                  // rows i0.., columns kt*16.. (zero filled outside)
+    tma_load_2d(a + DG_T * DG_K, &mapB, kt * DG_K, j0, &full[st]);
+  };
+  if (tid == 0)
+    for (int kt = 0; kt < DG_STAGES - 1 && kt < nk; ++kt) issue(kt);
+  double acc[4][4][2];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int fr = lane >> 2, fk = lane & 3;  // fragment coordinates: row (or column) within the 8, k within the 4
+  for (int kt = 0; kt < nk; ++kt) {
+    const int st = kt % DG_STAGES;
+    // the scale factors of this K slab (block-uniform, tiny)
+    if (sc) {
+      __syncthreads();
+      if (tid < DG_K) scs[tid] = (kt * DG_K + tid < K) ? sc[kt * DG_K + tid] : 0.0;
+    }
+    mbar_wait(&full[st], (kt / DG_STAGES) & 1);
+    if (sc) __syncthreads();
+    const double* As = boxes + (size_t)st * 2 * DG_T * DG_K;
+    const double* Bs = As + DG_T * DG_K;
+#pragma unroll
+    for (int ks = 0; ks < DG_K; ks += 4) {
+      double af[4], bf[4];
+      const double sk = sc ? scs[ks + fk] : 1.0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) af[a] = box_at(As, wm + a * 8 + fr, ks + fk) * sk;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = box_at(Bs, wn + b * 8 + fr, ks + fk);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+    }
+    __syncthreads();  // everyone is done with stage st-of-(kt): the producer may refill the slot freed one step ago
+    if (tid == 0 && kt + DG_STAGES - 1 < nk) issue(kt + DG_STAGES - 1);
+  }
+  // epilogue: thread holds C(row = lane/4, cols = 2 (lane%4) + {0,1}) of every 8 x 8 tile
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t i = i0 + wm + a * 8 + fr, j = j0 + wn + b * 8 + 2 * fk;
+      if (i < M && j < N) C[i + ldc * j] = acc[a][b][0];
+      if (i < M && j + 1 < N) C[i + ldc * (j + 1)] = acc[a][b][1];
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    FLGP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) fail(3, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// rows x K matrix, row-major with leading dimension ld (elements): box = 64 rows x 16 columns, 128-byte swizzle
+CUtensorMap make_map(const double* base, int64_t rows, int K, int64_t ld) {
+  CUtensorMap m;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+  cuuint32_t box[2] = {DG_K, DG_T};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fail(3, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return m;
+}
 
 constexpr int GT = 64, GK = 16, GPAD = 66;
 
@@ -80,7 +226,24 @@ void gemm_strided(Ctx* c, const double* A, int64_t ars, int64_t acs, const doubl
 
 void gemm_nt_run(Ctx* c, const double* A, const double* B, const double* sc, int64_t M, int64_t N, int K,
                  double* C, int64_t ldc) {
-  gemm_strided(c, A, K, 1, B, 1, K, sc, M, N, K, C, 1, ldc);
+  gemm_nt_ld_run(c, A, K, B, K, sc, M, N, K, C, ldc);
+}
+
+void gemm_nt_ld_run(Ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, const double* sc, int64_t M,
+                    int64_t N, int K, double* C, int64_t ldc) {
+  if (M <= 0 || N <= 0) return;
+  // TMA needs 16-byte aligned bases and row pitches; anything else (odd leading dimensions) takes the FMA kernel
+  const bool tma_ok = (lda % 2 == 0) && (ldb % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(B) % 16 == 0) && K >= 1 && M * (int64_t)N >= 64 * 64;
+  if (!tma_ok) {
+    gemm_strided(c, A, lda, 1, B, 1, ldb, sc, M, N, K, C, 1, ldc);
+    return;
+  }
+  const CUtensorMap mapA = make_map(A, M, K, lda), mapB = make_map(B, N, K, ldb);
+  const size_t smem = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024;
+  FLGP_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(N, DG_T), ceil_div(M, DG_T));
+  FLGP_LAUNCH(c, dmma_gemm_nt_kernel, grid, 128, smem, mapA, mapB, sc, M, N, K, C, ldc);
 }
 
 void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C) {

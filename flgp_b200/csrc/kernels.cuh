@@ -68,6 +68,9 @@ void sparse_quadform_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, con
 // sc may be null.  fp64 FMA accumulation in ascending k.
 void gemm_nt_run(Ctx* c, const double* A, const double* B, const double* sc, int64_t M, int64_t N, int K,
                  double* C, int64_t ldc);
+// the same with explicit leading dimensions (elements) of the row-major operands; FP64 tensor cores (DMMA) fed by TMA
+void gemm_nt_ld_run(Ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, const double* sc, int64_t M,
+                    int64_t N, int K, double* C, int64_t ldc);
 // C(M x N row-major) = A(M x K row-major) * B(K x N row-major)
 void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C);
 // small: y(M) = A(M x K row-major) x(K)

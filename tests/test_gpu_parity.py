@@ -393,3 +393,25 @@ def test_eigs_sym_matches_lapack(flgp, s, K, kind):
     # invariant subspaces agree wherever the K cut does not split a cluster
     if K < s and w[-1] - np.linalg.eigvalsh(A)[::-1][K] > 1e-6:
         assert np.abs(Y @ Y.T - V @ V.T).max() < 1e-8
+
+
+# ------------------------------------------------------------------------------------------- heat kernel GEMM
+@pytest.mark.parametrize("n0,n1,K", [(64, 64, 16), (333, 257, 30), (1000, 700, 200), (70, 5, 9), (129, 640, 37)])
+def test_hk_from_spectrum_tensor_core_gemm(flgp, oracle, n0, n1, K):
+    """HK_from_spectrum_cpp through the DMMA + TMA GEMM (and its FMA fallback for small / odd shapes) against the
+    oracle's plain triple loop on the same lifted eigenvectors."""
+    X, _ = spiral(3000, 21)
+    s, r, KK = 150, 3, 40 if K <= 40 else 200
+    if KK > s:
+        s = 260
+    init = _init(3000, s, 4)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:100], X[100:], s, r, KK, init_idx=init, iter_max=15)
+    rng = np.random.default_rng(n0 + n1)
+    idx0 = rng.integers(0, 3000, n0).astype(np.int32)
+    idx1 = rng.integers(0, 3000, n1).astype(np.int32)
+    H = flgp.HK_from_spectrum_cpp(ep, K, 3.0, idx0, idx1)
+    V = ep.vectors
+    lam = np.exp(-3.0 * (1.0 - ep.values[:K]))
+    Ho = (V[idx0, :K] * lam) @ V[idx1, :K].T
+    assert H.shape == (n0, n1)
+    assert np.abs(H - Ho).max() <= 1e-12 * max(1.0, np.abs(Ho).max())
