@@ -34,7 +34,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch, from the ncu --set full captures committed under profiles/
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    "kmeans_assign_small": (311.2e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_kmeans_assign_small.ncu-rep)"),
+    "tridiag_resident": (25.3e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_resident.ncu-rep)"),
+    "tridiag_streaming": (37.6e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_streaming.ncu-rep)"),
+}
 
 PARS = (10.0, 0.01)   # (t, noise variance): fixed hyper-parameters
 SIGMA = 1e-5

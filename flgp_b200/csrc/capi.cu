@@ -194,18 +194,24 @@ void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const do
   sp->Zj.alloc(std::max<int64_t>(n * r, 1));
   sp->Zx.alloc(std::max<int64_t>(n * r, 1));
   DevBuf<int32_t> ind(std::max<int64_t>(n * r, 1));
+  bool srt = false;  // are ind / dist in cluster-sorted order?
   if (kernel == "lae") {
     {
       StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 4.0 * r) * (double)n);
-      knn_run(c, X, n, n, d, U, s, s, r, ind.p, nullptr, &sp->sorted);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, nullptr, &sp->sorted, &srt);
     }
-    sp->sorted = KMeansSorted();
     DevBuf<long long> stats(2);
     stats.zero(c->stream);
     {
+      // after a pruned KNN the neighbours are in cluster-sorted order: the solver runs in that order too (coalesced
+      // reads, warps whose points share anchors and converge alike) and writes each CSR row at its original place
       StageScope st(c, "lae", 0.0, (8.0 * d + 4.0 * r + 12.0 * r) * (double)n);
-      lae_run(c, X, n, n, d, U, s, s, r, ind.p, sp->Zj.p, sp->Zx.p, nullptr, stats.p);
+      if (srt) lae_run(c, sp->sorted.Xs.p, n, n, d, U, s, s, r, ind.p, sp->Zj.p, sp->Zx.p, nullptr, stats.p,
+                       sp->sorted.perm.p);
+      else lae_run(c, X, n, n, d, U, s, s, r, ind.p, sp->Zj.p, sp->Zx.p, nullptr, stats.p);
     }
+    sync(c);
+    sp->sorted = KMeansSorted();
     long long h[2];
     stats.download(h, 2, c->stream);
     sync(c);
@@ -215,11 +221,12 @@ void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const do
     DevBuf<double> dist(std::max<int64_t>(n * r, 1));
     {
       StageScope st(c, "knn", 2.0 * s * d * (double)n, (8.0 * d + 12.0 * r) * (double)n);
-      knn_run(c, X, n, n, d, U, s, s, r, ind.p, dist.p, &sp->sorted);
+      knn_run(c, X, n, n, d, U, s, s, r, ind.p, dist.p, &sp->sorted, &srt);
     }
-    sp->sorted = KMeansSorted();
     StageScope st(c, "se_weights", 0.0, 36.0 * r * (double)n);
-    knn_to_csr_run(c, n, r, ind.p, dist.p, sp->Zj.p, sp->Zx.p);
+    knn_to_csr_run(c, n, r, ind.p, dist.p, sp->Zj.p, sp->Zx.p, srt ? sp->sorted.perm.p : nullptr);
+    sync(c);
+    sp->sorted = KMeansSorted();
     se_weights_run(c, sp->Zx.p, n * r, 4.0 * epsilon * epsilon, sp->Zx.p);
     sync(c);
   } else {

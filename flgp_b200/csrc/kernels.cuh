@@ -30,15 +30,20 @@ double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);
 // ind: n x r (ld n), ascending distance, libstdc++ partial_sort tie behaviour.  dist: optional.
 // sorted (optional): the cluster-sorted layout of the SAME rows left by kmeans_run; with it (d <= 4, r <= 5) every
 // point scans only the anchors that can reach its top r (exact: see knn.cu), everything else is unchanged.
+// out_sorted (optional, with sorted): when the pruned path runs, row p of ind/dist describes sorted position p
+// (= original row sorted->perm[p]) and *out_sorted is set; the consumer un-permutes when it writes its own output.
 void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, int32_t* ind, double* dist, const KMeansSorted* sorted = nullptr);
+             int r, int32_t* ind, double* dist, const KMeansSorted* sorted = nullptr, bool* out_sorted = nullptr);
 
 // ---- lae.cu ----------------------------------------------------------------------------------
 // Zj/Zx: n*r CSR (row i at i*r), rows sorted by column.  Wd: optional dense n x r weights (ld n)
 // in KNN order.  stats: optional 2 x int64 on device (iterations, back-tracks), accumulated.
+// perm (optional): input row i (of X and ind) is written as output row perm[i].
 void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats);
-void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx);
+             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats,
+             const int32_t* perm = nullptr);
+void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx,
+                    const int32_t* perm = nullptr);
 void se_weights_run(Ctx* c, const double* dist, int64_t len, double denom, double* out);
 // one point / one vector, for the exported helpers
 void lae_point_run(Ctx* c, const double* x, int d, const double* Ur, int r, double* z);

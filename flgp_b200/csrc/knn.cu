@@ -141,7 +141,7 @@ knn_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
   for (int p = 0; p < P; ++p) {
     const int64_t q = base + (int64_t)p * 256 + tid;
     const int64_t i = (q < count) ? (sel ? (int64_t)sel[q] : q) : -1;
-    orow[p] = (i < 0) ? -1 : (sel ? (int64_t)perm[i] : i);
+    orow[p] = (i < 0) ? -1 : ((sel && perm) ? (int64_t)perm[i] : i);
     xn[p] = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -447,7 +447,7 @@ knn_segment_kernel(const double* __restrict__ Xs, int64_t n, const double* __res
       strag[base + __popc(act & ((1u << lane) - 1))] = p;
       continue;
     }
-    const int64_t i = perm[p];
+    const int64_t i = perm ? (int64_t)perm[p] : (int64_t)p;
 #pragma unroll
     for (int q = 0; q < R; ++q) {
       ind[i + n * q] = top.id[q];
@@ -536,7 +536,8 @@ void launch_small_r(Ctx* c, const double* X, int64_t n, int64_t ldx, const doubl
 // pruned scan over the cluster-sorted layout + brute-force fallback for the undecided rows
 template <int D, int R>
 void launch_pruned_r(Ctx* c, const KMeansSorted& so, int64_t n, const double* rec, const double* U, int s, int64_t ldu,
-                     int32_t* ind, double* dist) {
+                     int32_t* ind, double* dist, bool keep_sorted) {
+  const int32_t* perm = keep_sorted ? nullptr : so.perm.p;  // null: output row = sorted position
   constexpr int STR = (D + 2) / 2 * 2;
   constexpr int P = 2;
   const double m = so.maxabs;
@@ -549,24 +550,24 @@ void launch_pruned_r(Ctx* c, const KMeansSorted& so, int64_t n, const double* re
   nstrag.zero(c->stream);
   FLGP_LAUNCH(c, knn_lists_kernel, s, 256, 0, U, s, ldu, D, R, so.Rbits.p, so.move.p, eta, lj.p, lcc.p, llen.p, lrad.p,
               rho.p);
-  FLGP_LAUNCH(c, (knn_segment_kernel<D, R>), s, 256, 0, so.Xs.p, n, rec, so.perm.p, so.seg_start.p, lj.p, lcc.p, llen.p,
+  FLGP_LAUNCH(c, (knn_segment_kernel<D, R>), s, 256, 0, so.Xs.p, n, rec, perm, so.seg_start.p, lj.p, lcc.p, llen.p,
               lrad.p, rho.p, delta2, eta, ind, dist, strag.p, nstrag.p);
   int chunk = std::min(s, 1024);
   size_t smem = (size_t)chunk * STR * sizeof(double);
   int grid = ceil_div(n, 256 * P);  // blocks beyond *nstrag exit at once
   FLGP_LAUNCH(c, (knn_small_kernel<D, R, P>), grid, 256, smem, so.Xs.p, n, n, rec, s, R, ind, dist, chunk, 1, strag.p,
-              nstrag.p, so.perm.p, n);
+              nstrag.p, perm, n);
   sync(c);  // the work buffers are freed on return
 }
 template <int D>
 bool launch_pruned(Ctx* c, const KMeansSorted& so, int64_t n, const double* rec, const double* U, int s, int64_t ldu,
-                   int r, int32_t* ind, double* dist) {
+                   int r, int32_t* ind, double* dist, bool ks) {
   switch (r) {
-    case 1: launch_pruned_r<D, 1>(c, so, n, rec, U, s, ldu, ind, dist); return true;
-    case 2: launch_pruned_r<D, 2>(c, so, n, rec, U, s, ldu, ind, dist); return true;
-    case 3: launch_pruned_r<D, 3>(c, so, n, rec, U, s, ldu, ind, dist); return true;
-    case 4: launch_pruned_r<D, 4>(c, so, n, rec, U, s, ldu, ind, dist); return true;
-    case 5: launch_pruned_r<D, 5>(c, so, n, rec, U, s, ldu, ind, dist); return true;
+    case 1: launch_pruned_r<D, 1>(c, so, n, rec, U, s, ldu, ind, dist, ks); return true;
+    case 2: launch_pruned_r<D, 2>(c, so, n, rec, U, s, ldu, ind, dist, ks); return true;
+    case 3: launch_pruned_r<D, 3>(c, so, n, rec, U, s, ldu, ind, dist, ks); return true;
+    case 4: launch_pruned_r<D, 4>(c, so, n, rec, U, s, ldu, ind, dist, ks); return true;
+    case 5: launch_pruned_r<D, 5>(c, so, n, rec, U, s, ldu, ind, dist, ks); return true;
     default: return false;
   }
 }
@@ -586,7 +587,8 @@ void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double*
 }  // namespace
 
 void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, int32_t* ind, double* dist, const KMeansSorted* sorted) {
+             int r, int32_t* ind, double* dist, const KMeansSorted* sorted, bool* out_sorted) {
+  if (out_sorted) *out_sorted = false;
   if (r < 1 || r > s) fail(2, "KNN: need 1 <= r <= s (r=%d, s=%d)", r, s);
   if (r > KNN_RMAX) fail(2, "KNN: r=%d exceeds the supported maximum %d", r, KNN_RMAX);
   if (n <= 0) return;
@@ -597,12 +599,15 @@ void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
     if (sorted && sorted->valid && r <= 5 && n < ((int64_t)1 << 31)) {
       bool done = false;
       switch (d) {
-        case 1: done = launch_pruned<1>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
-        case 2: done = launch_pruned<2>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
-        case 3: done = launch_pruned<3>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
-        default: done = launch_pruned<4>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist); break;
+        case 1: done = launch_pruned<1>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist, out_sorted != nullptr); break;
+        case 2: done = launch_pruned<2>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist, out_sorted != nullptr); break;
+        case 3: done = launch_pruned<3>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist, out_sorted != nullptr); break;
+        default: done = launch_pruned<4>(c, *sorted, n, rec.p, U, s, ldu, r, ind, dist, out_sorted != nullptr); break;
       }
-      if (done) return;
+      if (done) {
+        if (out_sorted) *out_sorted = true;
+        return;
+      }
     }
     switch (d) {
       case 1: launch_small<1>(c, X, n, ldx, rec.p, s, r, ind, dist); break;

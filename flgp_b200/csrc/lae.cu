@@ -89,7 +89,7 @@ template <int R, int D>
 __global__ void __launch_bounds__(128)
 lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const double* __restrict__ U, int64_t ldu,
                  const int32_t* __restrict__ ind, int32_t* __restrict__ Zj, double* __restrict__ Zx,
-                 double* __restrict__ Wd, long long* stats) {
+                 double* __restrict__ Wd, long long* stats, const int32_t* __restrict__ perm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int it = 0, bt = 0;
   if (i < n) {
@@ -108,7 +108,7 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
     const LaeStats ls = lae_solve<R, D>(R, D, x, Ur, z);
     it = ls.iters;
     bt = ls.backtracks;
-    write_row<R>(R, col, z, i, n, Zj, Zx, Wd);
+    write_row<R>(R, col, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);  // perm: input row i is output row perm[i]
   }
   add_stats(stats, it, bt);
 }
@@ -116,7 +116,8 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
 __global__ void __launch_bounds__(128)
 lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ U,
                    int64_t ldu, int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj,
-                   double* __restrict__ Zx, double* __restrict__ Wd, long long* stats) {
+                   double* __restrict__ Zx, double* __restrict__ Wd, long long* stats,
+                   const int32_t* __restrict__ perm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int it = 0, bt = 0;
   if (i < n) {
@@ -129,13 +130,13 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
     const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z);
     it = ls.iters;
     bt = ls.backtracks;
-    write_row<LAE_RMAX>(r, Ur.c, z, i, n, Zj, Zx, Wd);
+    write_row<LAE_RMAX>(r, Ur.c, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
   }
   add_stats(stats, it, bt);
 }
 
 __global__ void knn_to_csr_kernel(int64_t n, int r, const int32_t* __restrict__ ind, const double* __restrict__ dist,
-                                  int32_t* __restrict__ Zj, double* __restrict__ Zx) {
+                                  int32_t* __restrict__ Zj, double* __restrict__ Zx, const int32_t* __restrict__ perm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int col[32];
@@ -144,7 +145,7 @@ __global__ void knn_to_csr_kernel(int64_t n, int r, const int32_t* __restrict__ 
     col[a] = ind[i + n * a];
     v[a] = dist[i + n * a];
   }
-  write_row<32>(r, col, v, i, n, Zj, Zx, nullptr);
+  write_row<32>(r, col, v, perm ? (int64_t)perm[i] : i, n, Zj, Zx, nullptr);
 }
 
 __global__ void se_weights_kernel(const double* __restrict__ dist, int64_t len, double denom, double* out) {
@@ -172,26 +173,28 @@ __global__ void simplex_project_kernel(const double* v, int r, double* z, double
 }  // namespace
 
 void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
-             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats) {
+             int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats, const int32_t* perm) {
   (void)s;
   if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
   if (n <= 0) return;
   const int grid = ceil_div(n, 128);
 #define LAE_CASE(R_, D_)                                                                                  \
   if (r == R_ && d == D_) {                                                                               \
-    FLGP_LAUNCH(c, (lae_small_kernel<R_, D_>), grid, 128, 0, X, n, ldx, U, ldu, ind, Zj, Zx, Wd, stats);  \
+    FLGP_LAUNCH(c, (lae_small_kernel<R_, D_>), grid, 128, 0, X, n, ldx, U, ldu, ind, Zj, Zx, Wd, stats,   \
+                perm);                                                                                    \
     return;                                                                                               \
   }
   LAE_CASE(2, 2) LAE_CASE(3, 2) LAE_CASE(4, 2) LAE_CASE(5, 2)
   LAE_CASE(2, 3) LAE_CASE(3, 3) LAE_CASE(4, 3) LAE_CASE(5, 3)
 #undef LAE_CASE
-  FLGP_LAUNCH(c, lae_generic_kernel, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats);
+  FLGP_LAUNCH(c, lae_generic_kernel, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats, perm);
 }
 
-void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx) {
+void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx,
+                    const int32_t* perm) {
   if (r < 1 || r > 32) fail(2, "r=%d outside 1..32", r);
   if (n <= 0) return;
-  FLGP_LAUNCH(c, knn_to_csr_kernel, ceil_div(n, 128), 128, 0, n, r, ind, dist, Zj, Zx);
+  FLGP_LAUNCH(c, knn_to_csr_kernel, ceil_div(n, 128), 128, 0, n, r, ind, dist, Zj, Zx, perm);
 }
 
 void se_weights_run(Ctx* c, const double* dist, int64_t len, double denom, double* out) {
