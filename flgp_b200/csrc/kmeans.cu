@@ -293,9 +293,17 @@ kmeans_assign_tiled(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
 }
 
 // centroid update, one thread per centre; move[j] >= |c_new - c_old| (for the pruned passes' radius bound)
+// kstate[0]: first pass in which no assignment changed (0 = none yet); kstate[1]: assignments changed so far.
+// The host reads them every few passes only: a pass after convergence changes nothing (same sums, same centres), so
+// running ahead of the check is harmless and the reported iteration count is still the exact one.
 __global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, int d, Fx fx, double* C, double* sizes,
-                                     double* move, unsigned long long* maxmove_bits) {
+                                     double* move, unsigned long long* maxmove_bits, int it, long long* kstate) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0) {
+    const long long ch = acc[(size_t)2 * s * d + s];
+    if (ch == 0 && kstate[0] == 0) kstate[0] = it;
+    kstate[1] += ch;
+  }
   if (j >= s) return;
   long long cnt = acc[(size_t)2 * s * d + j];
   sizes[j] = (double)cnt;
@@ -339,6 +347,7 @@ __global__ void kmeans_init_kernel(const double* __restrict__ X, int64_t n_local
 //   * points are kept sorted by cluster (a permutation + a gathered copy of X), so a warp walks ONE list and
 //     every list / record load is a broadcast; the order is refreshed when enough points have moved;
 //   * sums are integer limbs, so a reassignment is an exact -x / +x on persistent accumulators.
+constexpr int KM_CHECK = 8;   // passes between two host checks of the convergence flag
 constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster's members scan everything
 
 __global__ void __launch_bounds__(256)
@@ -782,7 +791,9 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   }
   int cur = 0;              // which sorted buffer is live
   bool have_sorted = false;
-  int64_t moved_since_sort = 0, last_strag = 0;
+  int64_t moved_since_sort = 0, moved_base = 0;  // assignments changed (all ranks) since the last sort
+  DevBuf<long long> kstate(2);
+  kstate.zero(c->stream);
   auto resort = [&]() {
     // counting sort by cluster of the current assignment (local counts live in acc)
     StageScope st(c, "kmeans_sort");
@@ -800,8 +811,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     cur = nxt;
     have_sorted = true;
+    moved_base += moved_since_sort;
     moved_since_sort = 0;
-    last_strag = 0;
   };
   int it = 0, rsel = 0;  // Rbits[rsel]: radii gathered during the previous pass
   while (it < iter_max) {
@@ -811,7 +822,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
-    if (!brute && (!have_sorted || moved_since_sort * 8 > n_local)) resort();
+    if (!brute && (!have_sorted || moved_since_sort * 8 > n_total)) resort();
     // when timing is on, the assign+accumulate work gets its own CUDA-event pair per pass
     StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_pass", 2.0 * s * d * (double)n_local,
                    (8.0 * d + 4.0) * (double)n_local);
@@ -860,13 +871,17 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
     if (pruned) maxmove.zero(c->stream);
     FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
-                pruned ? maxmove.p : nullptr);
-    FLGP_CUDA(cudaMemcpyAsync(c->pinned, red + (words - 1), sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
-    if (!brute) FLGP_CUDA(cudaMemcpyAsync(c->pinned + 1, nstrag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    sync(c);
-    moved_since_sort += c->pinned[0];
-    last_strag = brute ? 0 : (int64_t)(*reinterpret_cast<int*>(c->pinned + 1));
-    if (c->pinned[0] == 0) break;  // no assignment changed anywhere
+                pruned ? maxmove.p : nullptr, it, kstate.p);
+    // one host round trip per KM_CHECK passes (and after the first, which decides about the sorted layout)
+    if (it == 1 || it % KM_CHECK == 0 || it == iter_max) {
+      FLGP_CUDA(cudaMemcpyAsync(c->pinned, kstate.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+      sync(c);
+      moved_since_sort = c->pinned[1] - moved_base;
+      if (c->pinned[0] != 0) {  // no assignment changed anywhere in pass pinned[0]
+        it = (int)c->pinned[0];
+        break;
+      }
+    }
   }
   if (have_sorted && n_local > 0)
     FLGP_LAUNCH(c, kmeans_unpermute_kernel, ceil_div(n_local, 256), 256, 0, as[cur].p, perm[cur].p, n_local, assign);

@@ -55,3 +55,20 @@ def test_product_never_imports_the_oracle():
                              t, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm) must put exactly one JSON line on stdout, whatever libraries print."""
+    import json
+    import subprocess
+    import sys
+
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--cpu-sample", "6000", "--iter-max", "3"], capture_output=True, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] == 0

@@ -415,3 +415,21 @@ def test_hk_from_spectrum_tensor_core_gemm(flgp, oracle, n0, n1, K):
     Ho = (V[idx0, :K] * lam) @ V[idx1, :K].T
     assert H.shape == (n0, n1)
     assert np.abs(H - Ho).max() <= 1e-12 * max(1.0, np.abs(Ho).max())
+
+
+# ------------------------------------------------------------------------------------------- large d (config 3 shape)
+def test_c3_shape_pipeline_large_d(flgp, oracle):
+    """BASELINE config 3's shape at reduced n: d = 784, r = 5 through the tiled (any-d) k-means / KNN / LAE kernels."""
+    rng = np.random.default_rng(33)
+    n, d, s, r, K, m = 2500, 784, 80, 5, 20, 200
+    means = 3.0 * rng.standard_normal((10, d))
+    lab = rng.integers(0, 10, n)
+    X = np.asfortranarray(means[lab] + rng.standard_normal((n, d)))
+    init = _init(n, s, 6)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=12)
+    vo, Vo, I = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init, nthreads=NT, want_internals=True, iter_max=12)
+    assert ep.kmeans_iters == I["iters"]
+    assert np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
