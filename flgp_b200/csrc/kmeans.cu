@@ -95,6 +95,7 @@ __device__ __forceinline__ void km_commit(const Fx& fx, int s, int d, int bj, co
                                           int64_t i, unsigned long long* acc, int& changed) {
   if (assign[i] != bj) ++changed;
   assign[i] = bj;
+  if (!acc) return;  // pre-pass against the pivot centres: only the label and the radius are wanted
   for (int k = 0; k < d; ++k) {
     long long h, l;
     fx_encode(fx, x[k], &h, &l);
@@ -189,7 +190,220 @@ kmeans_assign_small(const double* __restrict__ X, int64_t n, int64_t ldx, const 
     }
   }
   for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  if ((tid & 31) == 0 && changed && acc) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
+}
+
+// ---- first pass through pivots (small d) ---------------------------------------------------------------------------
+// A brute-force pass costs 2 s d flop per point.  Instead: (1) label every point with the nearest of np << s PIVOT
+// centres (a subset of the centres; the kernel above with acc == nullptr) and record each pivot group's radius R_p;
+// (2) sort the points by pivot; (3) per pivot list the centres within 2 R_p + eta of the pivot centre: a member at
+// distance ub <= R_p from the pivot centre has its nearest centre within ub, hence within 2 ub of the pivot centre,
+// and every unlisted centre is at least ub + eta away, so its COMPUTED score is strictly larger than the pivot
+// centre's (eta^2 > 2 Delta) - it can neither win nor tie; (4) run the brute-force inner loop of the kernel above
+// over that list only (kmeans_assign_listed).  The arg-min, its lowest-index tie rule, the sums and the radii are
+// exactly those of the full scan.
+template <int D, int P>
+__global__ void __launch_bounds__(KM_THREADS)
+kmeans_assign_listed(const double4* __restrict__ Xs4, const int32_t* __restrict__ perm, const int* __restrict__ items,
+                     const int* __restrict__ n_items, const double* __restrict__ rec, const int32_t* __restrict__ list_j,
+                     const int32_t* __restrict__ len, int lmax, int s, Fx fx, int32_t* __restrict__ assign,
+                     unsigned long long* __restrict__ acc, unsigned long long* __restrict__ Rbits, double M,
+                     double delta2) {
+  constexpr int STR = (D + 2) / 2 * 2;
+  extern __shared__ __align__(16) double srec[];  // lmax records, then lmax indices
+  if ((int)blockIdx.x >= *n_items) return;
+  const int tid = threadIdx.x;
+  const int pv = items[3 * blockIdx.x], beg = items[3 * blockIdx.x + 1], end = items[3 * blockIdx.x + 2];
+  int* sj = reinterpret_cast<int*>(srec + (size_t)lmax * STR);
+  const int L0 = len[pv];
+  const int L = (L0 < 0) ? 0 : L0;
+  for (int q = tid; q < L; q += KM_THREADS) sj[q] = list_j[(size_t)pv * lmax + q];
+  __syncthreads();
+  for (int t = tid; t < L * STR; t += KM_THREADS) srec[t] = rec[(size_t)sj[t / STR] * STR + (t % STR)];
+  __syncthreads();
+  double x[P][D], best[P];
+  int bj[P], bh[P];
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int q = beg + p * KM_THREADS + tid;
+    double4 v = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (q < end) v = Xs4[q];
+    const double xa[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[p][k] = xa[k];
+    best[p] = INFINITY;
+    bh[p] = 0x7fffffff;
+    bj[p] = 0x7fffffff;
+  }
+  auto scan = [&](const double* cr, int jj) {
+    double e[P];
+    bool cand = false;
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+      e[p] = cr[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) e[p] = fma(x[p][k], cr[k], e[p]);
+      cand |= (__double2hiint(e[p]) <= bh[p]);  // integer pre-filter: scores are positive (see kmeans_assign_small)
+    }
+    if (cand) {
+#pragma unroll
+      for (int p = 0; p < P; ++p)
+        if (e[p] < best[p] || (e[p] == best[p] && jj < bj[p])) {  // lowest index among equal minima, any scan order
+          best[p] = e[p];
+          bh[p] = __double2hiint(e[p]);
+          bj[p] = jj;
+        }
+    }
+  };
+  if (L0 >= 0) {
+#pragma unroll 2
+    for (int j = 0; j < L; ++j) {
+      double cr[STR];
+      const double2* rj = reinterpret_cast<const double2*>(srec + (size_t)j * STR);
+#pragma unroll
+      for (int q = 0; q < STR / 2; ++q) {
+        double2 t = rj[q];
+        cr[2 * q] = t.x;
+        cr[2 * q + 1] = t.y;
+      }
+      scan(cr, sj[j]);
+    }
+  } else {  // list overflow: this pivot's members scan every centre (records from global memory; rare)
+    for (int j = 0; j < s; ++j) {
+      double cr[STR];
+      const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
+#pragma unroll
+      for (int q = 0; q < STR / 2; ++q) {
+        double2 t = rj[q];
+        cr[2 * q] = t.x;
+        cr[2 * q + 1] = t.y;
+      }
+      scan(cr, j);
+    }
+  }
+  int changed = 0;
+#pragma unroll
+  for (int p = 0; p < P; ++p) {
+    const int q = beg + p * KM_THREADS + tid;
+    if (q < end) {
+      assign[perm[q]] = -1;  // the label written by the pre-pass was a pivot number
+      km_commit(fx, s, D, bj[p], x[p], assign, perm[q], acc, changed);
+      double xn = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) xn = fma(x[p][k], x[p][k], xn);
+      km_radius(Rbits, bj[p], km_ub(best[p], M, xn, delta2));
+    }
+  }
+  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
   if ((tid & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
+}
+
+// per pivot: every centre within 2 R_p + eta of the pivot centre (unsorted; the pivot centre itself included)
+__global__ void __launch_bounds__(256)
+kmeans_pivot_lists_kernel(const double* __restrict__ C, int s, int d, const int32_t* __restrict__ pivots,
+                          const unsigned long long* __restrict__ Rp, double eta, int lmax, int32_t* __restrict__ list_j,
+                          int32_t* __restrict__ len) {
+  __shared__ int count;
+  const int pv = blockIdx.x, tid = threadIdx.x, a = pivots[pv];
+  if (tid == 0) count = 0;
+  __syncthreads();
+  const double thr = (2.0 * (__longlong_as_double((long long)Rp[pv]) + eta) + eta) * (1.0 + 1e-9);
+  for (int j = tid; j < s; j += 256) {
+    double cc = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
+      cc = fma(df, df, cc);
+    }
+    if (sqrt(cc) < thr) {
+      const int pos = atomicAdd(&count, 1);
+      if (pos < lmax) list_j[(size_t)pv * lmax + pos] = j;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) len[pv] = (count <= lmax) ? count : -1;
+}
+
+// pivot records = the centre records of the chosen centres
+__global__ void kmeans_pivot_rec_kernel(const double* __restrict__ rec, int str, const int32_t* __restrict__ pivots, int np,
+                                        double* __restrict__ prec) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < np * str) prec[e] = rec[(size_t)pivots[e / str] * str + (e % str)];
+}
+
+__global__ void kmeans_hist_kernel(const int32_t* __restrict__ label, int64_t n, int nb, long long* __restrict__ cnt) {
+  extern __shared__ int hs[];
+  for (int t = threadIdx.x; t < nb; t += blockDim.x) hs[t] = 0;
+  __syncthreads();
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&hs[label[i]], 1);
+  __syncthreads();
+  for (int t = threadIdx.x; t < nb; t += blockDim.x)
+    if (hs[t]) atomicAdd(reinterpret_cast<unsigned long long*>(&cnt[t]), (unsigned long long)hs[t]);
+}
+
+// segment offsets and work items of at most chunk points (item = segment, first, last + 1); one thread per segment
+__global__ void kmeans_items_kernel(const long long* __restrict__ cnt, int nb, int chunk, int* __restrict__ cursor,
+                                    int* __restrict__ items, int* __restrict__ n_items) {
+  extern __shared__ int sh[];  // nb segment starts, nb item starts
+  int* seg0 = sh;
+  int* it0 = sh + nb;
+  if (threadIdx.x == 0) {
+    int run = 0, ni = 0;
+    for (int j = 0; j < nb; ++j) {
+      seg0[j] = run;
+      it0[j] = ni;
+      run += (int)cnt[j];
+      ni += ((int)cnt[j] + chunk - 1) / chunk;
+    }
+    *n_items = ni;
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    cursor[j] = seg0[j];
+    const int end = seg0[j] + (int)cnt[j];
+    int ni = it0[j];
+    for (int b = seg0[j]; b < end; b += chunk, ++ni) {
+      items[3 * ni] = j;
+      items[3 * ni + 1] = b;
+      items[3 * ni + 2] = min(end, b + chunk);
+    }
+  }
+}
+
+// counting-sort scatter for FEW keys (the pivot groups): a CTA counts its 2048 points per key in shared memory,
+// reserves one range per key with one global atomic each, and places its points inside those ranges
+constexpr int KM_FK_PTS = 8;
+__global__ void __launch_bounds__(256)
+kmeans_scatter_fewkeys_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const int32_t* __restrict__ key,
+                              int nkeys, int* __restrict__ cursor, double4* __restrict__ Xdst,
+                              int32_t* __restrict__ dst_perm) {
+  extern __shared__ int sh[];  // nkeys counts, nkeys bases
+  int* cntk = sh;
+  int* base = sh + nkeys;
+  const int tid = threadIdx.x;
+  const int64_t c0 = (int64_t)blockIdx.x * (256 * KM_FK_PTS);
+  for (int t = tid; t < nkeys; t += 256) cntk[t] = 0;
+  __syncthreads();
+  int k[KM_FK_PTS], rank[KM_FK_PTS];
+#pragma unroll
+  for (int q = 0; q < KM_FK_PTS; ++q) {
+    const int64_t i = c0 + q * 256 + tid;
+    k[q] = (i < n) ? key[i] : -1;
+    if (k[q] >= 0) rank[q] = atomicAdd(&cntk[k[q]], 1);
+  }
+  __syncthreads();
+  for (int t = tid; t < nkeys; t += 256) base[t] = cntk[t] ? atomicAdd(&cursor[t], cntk[t]) : 0;
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < KM_FK_PTS; ++q) {
+    const int64_t i = c0 + q * 256 + tid;
+    if (k[q] < 0) continue;
+    const int pos = base[k[q]] + rank[q];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int kk = 0; kk < d; ++kk) v[kk] = X[i + ldx * kk];
+    Xdst[pos] = make_double4(v[0], v[1], v[2], v[3]);
+    dst_perm[pos] = (int32_t)i;
+  }
 }
 
 // ---- any d: 64 points x 64 centres register-tiled FMA kernel ------------------------------------
@@ -347,6 +561,9 @@ __global__ void kmeans_init_kernel(const double* __restrict__ X, int64_t n_local
 //   * points are kept sorted by cluster (a permutation + a gathered copy of X), so a warp walks ONE list and
 //     every list / record load is a broadcast; the order is refreshed when enough points have moved;
 //   * sums are integer limbs, so a reassignment is an exact -x / +x on persistent accumulators.
+constexpr int KM_NPIVOT = 128;        // pivot centres of the first pass
+constexpr int KM_PIVOT_LMAX = 1024;   // longest candidate list of a pivot group
+constexpr int KM_PIVOT_MIN_S = 512;   // below this many centres the plain full scan is as fast
 constexpr int KM_CHECK = 8;   // passes between two host checks of the convergence flag
 constexpr int KM_LMAX = 512;  // longest neighbour list; longer => that cluster's members scan everything
 
@@ -644,7 +861,8 @@ __global__ void __launch_bounds__(256)
 kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc, int d, const int32_t* __restrict__ asrc,
                       const int32_t* __restrict__ src_perm, int* __restrict__ cursor, double4* __restrict__ Xdst,
                       int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm, const double2* __restrict__ ULsrc,
-                      double2* __restrict__ ULdst, const double4* __restrict__ X4src) {
+                      double2* __restrict__ ULdst, const double4* __restrict__ X4src,
+                      unsigned long long* __restrict__ Rnew) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int a = asrc[i];
@@ -667,7 +885,21 @@ kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc,
     Xdst[pos] = make_double4(v[0], v[1], v[2], v[3]);
   }
   // bounds travel with the point; before the first sort there are none: u = inf, l = 0 force a full evaluation
-  ULdst[pos] = ULsrc ? ULsrc[i] : make_double2(INFINITY, 0.0);
+  const double2 ul = ULsrc ? ULsrc[i] : make_double2(INFINITY, 0.0);
+  ULdst[pos] = ul;
+  // the cluster radii are re-tightened at every sort (between sorts they only grow: R += move): one atomic per
+  // group of equal keys in the warp
+  if (Rnew) {
+    double m = ul.x;
+    // max over the peers of this key: every lane scans the peer mask (at most 32 steps, usually one group per warp)
+    unsigned rest = peers;
+    while (rest) {
+      const int src = __ffs(rest) - 1;
+      rest &= rest - 1;
+      m = fmax(m, __shfl_sync(peers, ul.x, src));
+    }
+    if (lane == leader) atomicMax(&Rnew[a], (unsigned long long)__double_as_longlong(m));
+  }
 }
 
 // the KNN stage reads the sorted rows column-major
@@ -760,6 +992,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   DevBuf<KmWork> work;
   DevBuf<double4> cl;
   const bool prof_skip = std::getenv("FLGP_KMEANS_PROF") != nullptr;
+  DevBuf<int> prof_hist(128);
+  prof_hist.zero(c->stream);
   DevBuf<unsigned long long> maxmove, nskip;
   DevBuf<int> cursor, seg_start, nstrag;
   DevBuf<long long> acc_red;  // all-reduced copy of the local accumulators (multi-GPU)
@@ -794,27 +1028,29 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   int64_t moved_since_sort = 0, moved_base = 0;  // assignments changed (all ranks) since the last sort
   DevBuf<long long> kstate(2);
   kstate.zero(c->stream);
+  int rsel = 0;  // Rbits[rsel]: radii gathered during the previous pass
   auto resort = [&]() {
     // counting sort by cluster of the current assignment (local counts live in acc)
     StageScope st(c, "kmeans_sort");
     FLGP_LAUNCH(c, kmeans_offsets_kernel, 1, 32, 0, acc.p + (size_t)2 * s * d, s, cursor.p, seg_start.p);
     const int nxt = have_sorted ? 1 - cur : 0;
     if (n_local > 0) {
+      if (have_sorted) FLGP_CUDA(cudaMemsetAsync(Rbits[rsel].p, 0, sizeof(unsigned long long) * s, c->stream));
       if (have_sorted)
         FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, (const double*)nullptr, n_local, n_local, d,
                     as[cur].p, perm[cur].p, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, UL[cur].p, UL[nxt].p,
-                    Xs4[cur].p);
+                    Xs4[cur].p, Rbits[rsel].p);
       else
         FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, X, n_local, ldx, d, assign,
                     (const int32_t*)nullptr, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, (const double2*)nullptr,
-                    UL[nxt].p, (const double4*)nullptr);
+                    UL[nxt].p, (const double4*)nullptr, (unsigned long long*)nullptr);
     }
     cur = nxt;
     have_sorted = true;
     moved_base += moved_since_sort;
     moved_since_sort = 0;
   };
-  int it = 0, rsel = 0;  // Rbits[rsel]: radii gathered during the previous pass
+  int it = 0;
   while (it < iter_max) {
     ++it;
     const bool brute = !pruned || it == 1;
@@ -848,7 +1084,54 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
         }
 #undef FLGP_PRUNED
       }
+      if (prof_skip && it < 128)
+        FLGP_CUDA(cudaMemcpyAsync(prof_hist.p + it, nstrag.p, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
       rsel = 1 - rsel;
+    } else if (small && pruned && s >= KM_PIVOT_MIN_S && n_local > 0) {
+      // first pass through pivots (see kmeans_assign_listed): np pivot centres, then each pivot group against the
+      // centres that can reach it
+      const int np = KM_NPIVOT, lmax = KM_PIVOT_LMAX, chunk = KM_THREADS * 4;
+      std::vector<int32_t> pv_h(np);
+      for (int q = 0; q < np; ++q) pv_h[q] = (int32_t)((int64_t)q * s / np);
+      DevBuf<int32_t> pv(np), plist((size_t)np * lmax), plen(np);
+      DevBuf<double> prec((size_t)np * str);
+      DevBuf<unsigned long long> Rp(np);
+      DevBuf<long long> pcnt(np);
+      const int max_items = (int)(n_local / chunk) + np + 1;
+      DevBuf<int> items((size_t)3 * max_items), n_items(1);
+      pv.upload(pv_h.data(), np, c->stream);
+      Rp.zero(c->stream);
+      pcnt.zero(c->stream);
+      FLGP_LAUNCH(c, kmeans_pivot_rec_kernel, ceil_div(np * str, 128), 128, 0, rec.p, str, pv.p, np, prec.p);
+      switch (d) {  // labels (pivot numbers) into `assign`, group radii into Rp; nothing is accumulated
+        case 1: launch_small<1>(c, X, n_local, ldx, prec.p, np, fx, assign, nullptr, Rp.p, Moff, delta2); break;
+        case 2: launch_small<2>(c, X, n_local, ldx, prec.p, np, fx, assign, nullptr, Rp.p, Moff, delta2); break;
+        case 3: launch_small<3>(c, X, n_local, ldx, prec.p, np, fx, assign, nullptr, Rp.p, Moff, delta2); break;
+        default: launch_small<4>(c, X, n_local, ldx, prec.p, np, fx, assign, nullptr, Rp.p, Moff, delta2); break;
+      }
+      FLGP_LAUNCH(c, kmeans_hist_kernel, c->sm_count * 4, 256, np * sizeof(int), assign, n_local, np, pcnt.p);
+      FLGP_LAUNCH(c, kmeans_items_kernel, 1, 128, 2 * np * sizeof(int), pcnt.p, np, chunk, cursor.p, items.p,
+                  n_items.p);
+      FLGP_LAUNCH(c, kmeans_scatter_fewkeys_kernel, ceil_div(n_local, 256 * KM_FK_PTS), 256, 2 * np * sizeof(int), X,
+                  n_local, ldx, d, assign, np, cursor.p, Xs4[1].p, perm[1].p);
+      FLGP_LAUNCH(c, kmeans_pivot_lists_kernel, np, 256, 0, C, s, d, pv.p, Rp.p, eta, lmax, plist.p, plen.p);
+      const size_t lsm = (size_t)lmax * (str * sizeof(double) + sizeof(int));
+#define FLGP_LISTED(D_)                                                                                             \
+  do {                                                                                                              \
+    if (lsm > 48 * 1024)                                                                                            \
+      FLGP_CUDA(cudaFuncSetAttribute((kmeans_assign_listed<D_, 4>), cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                     (int)lsm));                                                                    \
+    FLGP_LAUNCH(c, (kmeans_assign_listed<D_, 4>), max_items, KM_THREADS, lsm, Xs4[1].p, perm[1].p, items.p,         \
+                n_items.p, rec.p, plist.p, plen.p, lmax, s, fx, assign, uacc, Rbits[rsel].p, Moff, delta2);         \
+  } while (0)
+      switch (d) {
+        case 1: FLGP_LISTED(1); break;
+        case 2: FLGP_LISTED(2); break;
+        case 3: FLGP_LISTED(3); break;
+        default: FLGP_LISTED(4); break;
+      }
+#undef FLGP_LISTED
+      sync(c);  // the pivot work buffers are released here
     } else if (small) {
       unsigned long long* R0 = pruned ? Rbits[rsel].p : nullptr;
       switch (d) {
@@ -891,6 +1174,12 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     sync(c);
     fprintf(stderr, "[flgp kmeans prof] %d passes, %.1f%% of the point-passes after the first skipped by their bounds, "
             "%llu full scans\n", it, it > 1 ? 100.0 * (double)h[0] / ((double)n_local * (it - 1)) : 0.0, h[1]);
+    int hist[128];
+    prof_hist.download(hist, 128, c->stream);
+    sync(c);
+    fprintf(stderr, "[flgp kmeans prof] survivors of the bound test per pass (%% of points):");
+    for (int q = 2; q <= it && q < 128; ++q) fprintf(stderr, " %.0f", 100.0 * hist[q] / (double)std::max<int64_t>(n_local, 1));
+    fprintf(stderr, "\n");
   }
   if (iters_out) *iters_out = it;
   if (sorted_out) {

@@ -23,7 +23,9 @@ def _csr_parts(Z):
 
 # ------------------------------------------------------------------------------------------- k-means
 @pytest.mark.parametrize("n,d,s", [(4000, 2, 500), (20000, 3, 200), (1500, 1, 20), (3000, 4, 64),
-                                    (3000, 5, 70), (2500, 16, 100), (700, 37, 33)])
+                                    (3000, 5, 70), (2500, 16, 100), (700, 37, 33),
+                                    # s >= 512: the first pass goes through pivot groups
+                                    (40000, 3, 600), (30000, 2, 1024), (9000, 4, 513), (5000, 1, 700)])
 def test_kmeans_bitexact(flgp, oracle, n, d, s):
     rng = np.random.default_rng(n + d)
     if d == 2:
@@ -39,6 +41,21 @@ def test_kmeans_bitexact(flgp, oracle, n, d, s):
     assert np.array_equal(assign, ao)
     assert np.array_equal(U, Uo)  # centres AND sizes, bit for bit
     assert U[:, d].sum() == n
+
+
+def test_kmeans_pivot_first_pass_with_duplicates_and_lattice(flgp, oracle):
+    """The pivot-pruned first pass on adversarial input: lattice points (exact score ties between centres) and
+    duplicated start rows (identical centres, one of them left empty)."""
+    rng = np.random.default_rng(12)
+    n, s = 20000, 640
+    X = np.asfortranarray(rng.integers(-20, 21, (n, 2)).astype(np.float64))
+    init = _init(n, s, 4)
+    X[init[7]] = X[init[3]]
+    X[init[300]] = X[init[3]]
+    for iter_max in (1, 2, 9):
+        U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=iter_max, return_info=True)
+        Uo, ao, io = oracle.kmeans_lloyd(X, s, init, iter_max, NT)
+        assert iters == io and np.array_equal(assign, ao) and np.array_equal(U, Uo)
 
 
 def test_kmeans_iter_cap_and_default_init(flgp, oracle):
