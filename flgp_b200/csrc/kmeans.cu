@@ -657,6 +657,9 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   }
 }
 
+__device__ __forceinline__ float2 km_pack(double u, double l) {  // u rounded up, l rounded down
+  return make_float2(__double2float_ru(u), __double2float_rd(l));
+}
 struct __align__(16) KmWork {
   int p, a;  // position in the sorted layout, current centre
   double l;  // lower bound after this pass's centre moves
@@ -671,7 +674,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
                      int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
                      const double* __restrict__ list_cc, const int32_t* __restrict__ len, double M, double delta2,
                      double eta, unsigned long long* __restrict__ Rcur, const KmWork* __restrict__ work,
-                     const int* __restrict__ nwork, const double* __restrict__ lthr, double2* __restrict__ UL,
+                     const int* __restrict__ nwork, const double* __restrict__ lthr, float2* __restrict__ UL,
                      unsigned long long* __restrict__ nfull) {
   constexpr int STR = (D + 2) / 2 * 2;
   int changed = 0;
@@ -706,7 +709,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
     int bj = a;
     const double ub0 = km_ub_fast(best, M, xn, delta2);
     if (ub0 + eta <= wr.l) {  // the tightened upper bound is enough: nothing can beat or tie centre a
-      UL[p] = make_double2(ub0, wr.l);
+      UL[p] = km_pack(ub0, wr.l);
       continue;
     }
     const double thr = (2.0 * ub0 + eta) * (1.0 + 1e-9);
@@ -748,7 +751,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
     }
     // bounds for the passes that follow: u >= |x - c_bj|, l <= distance to every other centre
     const double ub = (bj == a) ? ub0 : km_ub_fast(best, M, xn, delta2);
-    UL[p] = make_double2(ub, fmin(km_lb_fast(sec, M, xn, delta2), (ccb - ub0) * (1.0 - 1e-14)));
+    UL[p] = km_pack(ub, fmin(km_lb_fast(sec, M, xn, delta2), (ccb - ub0) * (1.0 - 1e-14)));
     if (bj != a) {
       ++changed;
       as[p] = bj;
@@ -781,7 +784,7 @@ constexpr int KM_BT = 256, KM_BQ = 8;  // threads per CTA, points per thread
 
 __global__ void __launch_bounds__(KM_BT)
 kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* __restrict__ cl, double eta,
-                     double2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
+                     float2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
                      unsigned long long* __restrict__ nskip) {
   __shared__ KmWork wl[KM_BT * KM_BQ];
   __shared__ int wcount, wbase;
@@ -789,14 +792,14 @@ kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* _
   const int64_t c0 = (int64_t)blockIdx.x * (KM_BT * KM_BQ);
   if (tid == 0) wcount = 0;
   __syncthreads();
-  double2 ul_in[KM_BQ];
+  float2 ul_in[KM_BQ];
   int as_in[KM_BQ];
 #pragma unroll
   for (int q = 0; q < KM_BQ; ++q) {  // everything is requested before the first value is looked at
     const int64_t p = c0 + q * KM_BT + tid;
     const bool valid = p < n;
     as_in[q] = valid ? as[p] : 0;
-    ul_in[q] = valid ? UL[p] : make_double2(0.0, 0.0);
+    ul_in[q] = valid ? UL[p] : make_float2(0.f, 0.f);
   }
   int skipped = 0;
 #pragma unroll
@@ -807,10 +810,14 @@ kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* _
     double l = 0.0;
     if (valid) {
       const double4 ca = cl[as_in[q]];
-      const double u = (ul_in[q].x + ca.x) * (1.0 + 1e-15);
-      l = fmin((ul_in[q].y - ca.y) * (1.0 - 1e-15) - 1e-300, (ca.z - u) * (1.0 - 1e-15));
-      if (u + eta <= l) {
-        UL[p] = make_double2(u, l);
+      // stored bounds are floats rounded outwards (u up, l down): half the traffic of this HBM-bound kernel; the
+      // decision is taken on the values as they will be stored
+      const float2 nb = km_pack(((double)ul_in[q].x + ca.x) * (1.0 + 1e-15),
+                                fmin(((double)ul_in[q].y - ca.y) * (1.0 - 1e-15) - 1e-300,
+                                     (ca.z - ((double)ul_in[q].x + ca.x) * (1.0 + 1e-7)) * (1.0 - 1e-15)));
+      l = (double)nb.y;
+      if ((double)nb.x + eta <= l) {
+        UL[p] = nb;
         ++skipped;
       } else {
         need = true;  // the evaluation receives the moved lower bound in its work record and rewrites UL[p]
@@ -860,8 +867,8 @@ __global__ void kmeans_offsets_kernel(const long long* __restrict__ cnt, int s, 
 __global__ void __launch_bounds__(256)
 kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc, int d, const int32_t* __restrict__ asrc,
                       const int32_t* __restrict__ src_perm, int* __restrict__ cursor, double4* __restrict__ Xdst,
-                      int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm, const double2* __restrict__ ULsrc,
-                      double2* __restrict__ ULdst, const double4* __restrict__ X4src,
+                      int32_t* __restrict__ adst, int32_t* __restrict__ dst_perm, const float2* __restrict__ ULsrc,
+                      float2* __restrict__ ULdst, const double4* __restrict__ X4src,
                       unsigned long long* __restrict__ Rnew) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
@@ -885,18 +892,18 @@ kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc,
     Xdst[pos] = make_double4(v[0], v[1], v[2], v[3]);
   }
   // bounds travel with the point; before the first sort there are none: u = inf, l = 0 force a full evaluation
-  const double2 ul = ULsrc ? ULsrc[i] : make_double2(INFINITY, 0.0);
+  const float2 ul = ULsrc ? ULsrc[i] : make_float2(INFINITY, 0.f);
   ULdst[pos] = ul;
   // the cluster radii are re-tightened at every sort (between sorts they only grow: R += move): one atomic per
   // group of equal keys in the warp
   if (Rnew) {
-    double m = ul.x;
+    double m = (double)ul.x;
     // max over the peers of this key: every lane scans the peer mask (at most 32 steps, usually one group per warp)
     unsigned rest = peers;
     while (rest) {
       const int src = __ffs(rest) - 1;
       rest &= rest - 1;
-      m = fmax(m, __shfl_sync(peers, ul.x, src));
+      m = fmax(m, (double)__shfl_sync(peers, ul.x, src));
     }
     if (lane == leader) atomicMax(&Rnew[a], (unsigned long long)__double_as_longlong(m));
   }
@@ -988,7 +995,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   DevBuf<int32_t> nlist, nlen, perm[2], as[2];
   DevBuf<double> ncc, move, lthr;
   DevBuf<double4> Xs4[2];
-  DevBuf<double2> UL[2];
+  DevBuf<float2> UL[2];
   DevBuf<KmWork> work;
   DevBuf<double4> cl;
   const bool prof_skip = std::getenv("FLGP_KMEANS_PROF") != nullptr;
@@ -1042,7 +1049,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
                     Xs4[cur].p, Rbits[rsel].p);
       else
         FLGP_LAUNCH(c, kmeans_scatter_kernel, ceil_div(n_local, 256), 256, 0, X, n_local, ldx, d, assign,
-                    (const int32_t*)nullptr, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, (const double2*)nullptr,
+                    (const int32_t*)nullptr, cursor.p, Xs4[nxt].p, as[nxt].p, perm[nxt].p, (const float2*)nullptr,
                     UL[nxt].p, (const double4*)nullptr, (unsigned long long*)nullptr);
     }
     cur = nxt;
