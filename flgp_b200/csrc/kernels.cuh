@@ -35,6 +35,19 @@ double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);
 void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
              int r, int32_t* ind, double* dist, const KMeansSorted* sorted = nullptr, bool* out_sorted = nullptr);
 
+// ---- distsel.cu ------------------------------------------------------------------------------
+// Large-d distance stages on the FP64 tensor cores (DMMA) with exact, certified selection.
+// to_rowmajor: column-major n x d (ld ldx) -> row-major n x dp, zero padded (dp even: 16-byte row pitch for TMA).
+void to_rowmajor_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, int dp, double* Xr);
+bool dist_select_supported(int64_t n, int s, int r);
+// For every row i of Xr (n x dp): the r+1 smallest of  add[j] - 2 <Xr_i, Cr_j>  over the s rows of Cr (s x dp).
+// out_idx(i, 0..r-1) (ld ldo) = their indices in ascending order of value; rows whose r+1 smallest values are not
+// pairwise more than thr (= thr_row[i] if given, else thr0) apart are appended to und_list (*und_count entries;
+// the caller zeroes the counter) and must be re-done in the oracle's summation order.
+void dist_select_run(Ctx* c, const double* Xr, int64_t n, const double* Cr, int s, int dp, const double* add, int r,
+                     double thr0, const double* thr_row, int32_t* out_idx, int64_t ldo, int* und_count,
+                     int32_t* und_list);
+
 // ---- lae.cu ----------------------------------------------------------------------------------
 // Zj/Zx: n*r CSR (row i at i*r), rows sorted by column.  Wd: optional dense n x r weights (ld n)
 // in KNN order.  stats: optional 2 x int64 on device (iterations, back-tracks), accumulated.

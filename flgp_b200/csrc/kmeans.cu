@@ -506,6 +506,87 @@ kmeans_assign_tiled(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
   if ((tid & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * d + s], (unsigned long long)changed);
 }
 
+// ---- large d on the tensor cores (distsel.cu): rows the DMMA selection could not certify, and the commit ---------
+// One CTA per listed row: every score in the oracle's order (cn[j], then fma over ascending k), lowest value then
+// lowest index.  dynamic shared memory: d doubles.
+__global__ void __launch_bounds__(256)
+kmeans_exact_rows_kernel(const double* __restrict__ X, int64_t ldx, int d, const double* __restrict__ C2,
+                         const double* __restrict__ cn, int s, const int* __restrict__ und_count,
+                         const int32_t* __restrict__ und_list, int32_t* __restrict__ newa) {
+  extern __shared__ double xs[];
+  __shared__ double rv[8];
+  __shared__ int rj[8];
+  const int tid = threadIdx.x, cnt = *und_count;
+  for (int u = blockIdx.x; u < cnt; u += gridDim.x) {
+    const int64_t i = und_list[u];
+    __syncthreads();
+    for (int k = tid; k < d; k += 256) xs[k] = X[i + ldx * k];
+    __syncthreads();
+    double lv = INFINITY;
+    int lj = 0x7fffffff;
+    for (int j = tid; j < s; j += 256) {
+      double e = cn[j];
+      for (int k = 0; k < d; ++k) e = fma(xs[k], C2[j + (size_t)s * k], e);
+      if (e < lv) {  // ascending j per thread: the first minimum is the lowest index
+        lv = e;
+        lj = j;
+      }
+    }
+    for (int o = 16; o; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, lv, o);
+      const int oj = __shfl_xor_sync(0xffffffffu, lj, o);
+      if (ov < lv || (ov == lv && oj < lj)) {
+        lv = ov;
+        lj = oj;
+      }
+    }
+    if ((tid & 31) == 0) {
+      rv[tid >> 5] = lv;
+      rj[tid >> 5] = lj;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (rv[w] < lv || (rv[w] == lv && rj[w] < lj)) {
+          lv = rv[w];
+          lj = rj[w];
+        }
+      newa[i] = (lj < s) ? lj : 0;  // all-NaN row: centre 0, like the scan kernels
+    }
+  }
+}
+
+// One warp per row: a changed assignment is an exact -enc(x) / +enc(x) on the persistent integer accumulators.
+__global__ void __launch_bounds__(256)
+kmeans_commit_rows_kernel(const double* __restrict__ Xr, int64_t n, int d, int dp, const int32_t* __restrict__ newa,
+                          int32_t* __restrict__ assign, int s, Fx fx, unsigned long long* __restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int changed = 0;
+  for (int64_t i = w0; i < n; i += nw) {
+    const int a_old = assign[i], a_new = newa[i];
+    if (a_old == a_new) continue;
+    for (int k = lane; k < d; k += 32) {
+      long long h, l;
+      fx_encode(fx, Xr[i * dp + k], &h, &l);
+      atomicAdd(&acc[a_new + (size_t)s * k], (unsigned long long)h);
+      atomicAdd(&acc[(size_t)s * d + a_new + (size_t)s * k], (unsigned long long)l);
+      if (a_old >= 0) {
+        atomicAdd(&acc[a_old + (size_t)s * k], (unsigned long long)(-h));
+        atomicAdd(&acc[(size_t)s * d + a_old + (size_t)s * k], (unsigned long long)(-l));
+      }
+    }
+    if (lane == 0) {
+      atomicAdd(&acc[(size_t)2 * s * d + a_new], 1ull);
+      if (a_old >= 0) atomicAdd(&acc[(size_t)2 * s * d + a_old], ~0ull);
+      assign[i] = a_new;
+      ++changed;
+    }
+  }
+  if (changed) atomicAdd(&acc[(size_t)2 * s * d + s], (unsigned long long)changed);
+}
+
 // centroid update, one thread per centre; move[j] >= |c_new - c_old| (for the pruned passes' radius bound)
 // kstate[0]: first pass in which no assignment changed (0 = none yet); kstate[1]: assignments changed so far.
 // The host reads them every few passes only: a pass after convergence changes nothing (same sums, same centres), so
@@ -984,9 +1065,30 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     C2.alloc((size_t)s * d);
     cn.alloc(s);
   }
+  // large d: assignment on the FP64 tensor cores (distsel.cu) over row-major copies, certified rows only; the rest
+  // in the oracle's order.  Accumulators are persistent (exact integer -x / +x per changed row).
+  const bool dmma = !small && dist_select_supported(n_local, s, 1) && n_local < ((int64_t)1 << 31) &&
+                    std::getenv("FLGP_NO_DMMA_DIST") == nullptr;
+  const int dp = (d + 1) / 2 * 2;
+  DevBuf<double> Xr, Cr;
+  DevBuf<int32_t> newa, und_list;
+  DevBuf<int> und_count;
+  if (dmma) {
+    Xr.alloc((size_t)n_local * dp);
+    Cr.alloc((size_t)s * dp);
+    newa.alloc(n_local);
+    und_list.alloc(n_local);
+    und_count.alloc(1);
+    to_rowmajor_run(c, X, n_local, ldx, d, dp, Xr.p);
+    const size_t xsm = sizeof(double) * d;
+    if (xsm > 200 * 1024) fail(2, "kmeans: d=%d exceeds the supported maximum", d);
+    if (xsm > 40 * 1024)
+      FLGP_CUDA(cudaFuncSetAttribute(kmeans_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+  }
   unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc.p);
   // pruned passes (small d): persistent local accumulators, neighbour lists, cluster-sorted points
   const bool pruned = small && n_total >= 2;
+  const bool persistent = pruned || dmma;  // local accumulators survive the pass; a copy is all-reduced
   const double bound = Moff + 4.0 * d * (maxabs * maxabs);                    // >= the magnitude of every score term
   const double Delta = 8.0 * (d + 4) * 1.1102230246251565e-16 * bound;        // generous bound on a score's rounding error
   const double delta2 = 4.0 * Delta;                                          // slack added to squared distances
@@ -1027,9 +1129,9 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     nskip.alloc(2);
     maxmove.zero(c->stream);
     nskip.zero(c->stream);
-    if (c->nranks > 1) acc_red.alloc(words);
     Rbits[0].zero(c->stream);
   }
+  if (persistent && c->nranks > 1) acc_red.alloc(words);
   int cur = 0;              // which sorted buffer is live
   bool have_sorted = false;
   int64_t moved_since_sort = 0, moved_base = 0;  // assignments changed (all ranks) since the last sort
@@ -1061,7 +1163,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   while (it < iter_max) {
     ++it;
     const bool brute = !pruned || it == 1;
-    if (brute) acc.zero(c->stream);
+    if (brute && !(dmma && it > 1)) acc.zero(c->stream);
     else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
@@ -1147,6 +1249,15 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
         case 3: launch_small<3>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
         default: launch_small<4>(c, X, n_local, ldx, rec.p, s, fx, assign, uacc, R0, Moff, delta2); break;
       }
+    } else if (dmma) {
+      to_rowmajor_run(c, C, s, s, d, dp, Cr.p);
+      und_count.zero(c->stream);
+      dist_select_run(c, Xr.p, n_local, Cr.p, s, dp, cn.p, 1, 4.0 * Delta, nullptr, newa.p, n_local, und_count.p,
+                      und_list.p);
+      FLGP_LAUNCH(c, kmeans_exact_rows_kernel, c->sm_count * 4, 256, sizeof(double) * d, X, ldx, d, C2.p, cn.p, s,
+                  und_count.p, und_list.p, newa.p);
+      FLGP_LAUNCH(c, kmeans_commit_rows_kernel, c->sm_count * 8, 256, 0, Xr.p, n_local, d, dp, newa.p, assign, s, fx,
+                  uacc);
     } else {
       int grid = ceil_div(n_local, KT_TP);
       if (grid > 0)
@@ -1154,7 +1265,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     kst.stop();
     long long* red = acc.p;
-    if (pruned && c->nranks > 1) {  // keep the local sums intact; reduce a copy
+    if (persistent && c->nranks > 1) {  // keep the local sums intact; reduce a copy
       FLGP_CUDA(cudaMemcpyAsync(acc_red.p, acc.p, sizeof(long long) * words, cudaMemcpyDeviceToDevice, c->stream));
       red = acc_red.p;
     }

@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cmath>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace flgp {
@@ -583,6 +585,65 @@ void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double*
     default: launch_small_r<D, 0>(c, X, n, ldx, rec, s, r, ind, dist); break;
   }
 }
+// ---- large d on the tensor cores (distsel.cu): thresholds, exact re-scoring, uncertified rows ------------------
+__global__ void knn_maxbits_kernel(const double* __restrict__ v, int n, unsigned long long* out) {
+  double m = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmax(m, v[i]);
+  for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));  // m >= 0
+}
+// thr_i = coef * (|x_i|^2 + max_j |u_j|^2): twice the distance between an oracle-order and a tensor-core value
+__global__ void knn_thr_kernel(const double* __restrict__ xn, int64_t n, const unsigned long long* __restrict__ unmax,
+                               double coef, double* __restrict__ thr) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) thr[i] = coef * (xn[i] + __longlong_as_double((long long)*unmax));
+}
+// distances of the selected anchors in the reference's own order: ((-2 * sum_k x_k u_k) + |x|^2) + |u|^2
+__global__ void knn_rescore_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
+                                   const double* __restrict__ U, int s, int64_t ldu, const double* __restrict__ xn,
+                                   const double* __restrict__ un, int r, const int32_t* __restrict__ ind,
+                                   double* __restrict__ dist) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= n * r) return;
+  const int64_t i = e % n;
+  const int j = ind[e];
+  if (j < 0 || j >= s) return;
+  double dot = 0.0;
+  for (int k = 0; k < d; ++k) dot = __dadd_rn(dot, __dmul_rn(X[i + ldx * k], U[j + ldu * k]));
+  dist[e] = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), xn[i]), un[j]);
+}
+// One CTA per uncertified row: all s distances in the reference's order, then the literal heap selection.
+// dynamic shared memory: d + s doubles.
+__global__ void __launch_bounds__(256)
+knn_exact_rows_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ U, int s,
+                      int64_t ldu, const double* __restrict__ xn, const double* __restrict__ un, int r,
+                      const int* __restrict__ und_count, const int32_t* __restrict__ und_list,
+                      int32_t* __restrict__ ind, double* __restrict__ dist) {
+  extern __shared__ double sm[];
+  double* xs = sm;
+  double* Ds = sm + d;
+  const int tid = threadIdx.x, cnt = *und_count;
+  for (int u = blockIdx.x; u < cnt; u += gridDim.x) {
+    const int64_t i = und_list[u];
+    __syncthreads();
+    for (int k = tid; k < d; k += 256) xs[k] = X[i + ldx * k];
+    __syncthreads();
+    const double my_xn = xn[i];
+    for (int j = tid; j < s; j += 256) {
+      double dot = 0.0;
+      for (int k = 0; k < d; ++k) dot = __dadd_rn(dot, __dmul_rn(xs[k], U[j + ldu * k]));
+      Ds[j] = __dadd_rn(__dadd_rn(__dmul_rn(-2.0, dot), my_xn), un[j]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      TopR h;
+      h.r = r;
+      h.top = INFINITY;
+      for (int j = 0; j < s; ++j) h.push(Ds[j], j);
+      h.finish(i, n, ind, dist);
+    }
+  }
+}
 
 }  // namespace
 
@@ -620,6 +681,34 @@ void knn_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
     DevBuf<double> xn(n), un(s);
     FLGP_LAUNCH(c, rownorm_kernel, ceil_div(n, 256), 256, 0, X, n, ldx, d, xn.p);
     FLGP_LAUNCH(c, rownorm_kernel, ceil_div(s, 256), 256, 0, U, (int64_t)s, ldu, d, un.p);
+    const size_t xsm = sizeof(double) * ((size_t)d + s);
+    if (dist_select_supported(n, s, r) && n < ((int64_t)1 << 31) && xsm <= 200 * 1024 &&
+        std::getenv("FLGP_NO_DMMA_DIST") == nullptr) {
+      // tensor-core inner products + certified selection (distsel.cu); uncertified rows in the reference's order
+      const int dp = (d + 1) / 2 * 2;
+      DevBuf<double> Xr((size_t)n * dp), Ur((size_t)s * dp), thr(n);
+      DevBuf<unsigned long long> unmax(1);
+      DevBuf<int> und_count(1);
+      DevBuf<int32_t> und_list(n);
+      to_rowmajor_run(c, X, n, ldx, d, dp, Xr.p);
+      to_rowmajor_run(c, U, s, ldu, d, dp, Ur.p);
+      unmax.zero(c->stream);
+      und_count.zero(c->stream);
+      FLGP_LAUNCH(c, knn_maxbits_kernel, 8, 256, 0, un.p, s, unmax.p);
+      // |oracle value - true| and |tensor value - true| are each below 2^-53 (4d + 10)(|x|^2 + |u|^2): see distsel.cu
+      const double coef = 4.0 * (4.0 * d + 10.0) * 1.1102230246251565e-16;
+      FLGP_LAUNCH(c, knn_thr_kernel, ceil_div(n, 256), 256, 0, xn.p, n, unmax.p, coef, thr.p);
+      dist_select_run(c, Xr.p, n, Ur.p, s, dp, un.p, r, 0.0, thr.p, ind, n, und_count.p, und_list.p);
+      if (dist)
+        FLGP_LAUNCH(c, knn_rescore_kernel, ceil_div(n * r, 256), 256, 0, X, n, ldx, d, U, s, ldu, xn.p, un.p, r, ind,
+                    dist);
+      if (xsm > 40 * 1024)
+        FLGP_CUDA(cudaFuncSetAttribute(knn_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+      FLGP_LAUNCH(c, knn_exact_rows_kernel, c->sm_count * 4, 256, xsm, X, n, ldx, d, U, s, ldu, xn.p, un.p, r,
+                  und_count.p, und_list.p, ind, dist);
+      sync(c);
+      return;
+    }
     FLGP_LAUNCH(c, knn_tiled_kernel, ceil_div(n, NT_TP), 256, 0, X, n, ldx, d, U, s, ldu, xn.p, un.p, r, ind,
                 dist);
     sync(c);

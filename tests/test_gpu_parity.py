@@ -434,6 +434,55 @@ def test_hk_from_spectrum_tensor_core_gemm(flgp, oracle, n0, n1, K):
     assert np.abs(H - Ho).max() <= 1e-12 * max(1.0, np.abs(Ho).max())
 
 
+# ------------------------------------------------------------------------------------------- large d: tensor-core path
+@pytest.mark.parametrize("n,d,s", [(1200, 37, 70), (900, 784, 64), (3000, 6, 200)])
+def test_kmeans_large_d_tensor_core_bitexact(flgp, oracle, n, d, s, monkeypatch):
+    """d > 4, n >= 64, s >= 64: the assignment runs as DMMA inner products + certified arg-min (distsel.cu); the
+    result must be the oracle's bit for bit, and identical to the oracle-order FMA kernel (FLGP_NO_DMMA_DIST)."""
+    rng = np.random.default_rng(n + d + s)
+    X = np.asfortranarray(rng.standard_normal((n, d)) * rng.uniform(0.2, 4.0, d) + rng.integers(0, 3, (n, 1)))
+    init = _init(n, s, 8)
+    U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=15, return_info=True)
+    Uo, ao, io = oracle.kmeans_lloyd(X, s, init, 15, NT)
+    assert iters == io and np.array_equal(assign, ao) and np.array_equal(U, Uo)
+    monkeypatch.setenv("FLGP_NO_DMMA_DIST", "1")
+    U2, a2, it2 = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=15, return_info=True)
+    assert it2 == iters and np.array_equal(a2, assign) and np.array_equal(U2, U)
+
+
+def test_large_d_ties_take_the_exact_fallback(flgp, oracle):
+    """Lattice data in d = 6 with duplicated centres / anchors: no row can be certified by the tensor-core
+    selection (exact ties), every one is re-done in the oracle's order; results still bit-exact."""
+    rng = np.random.default_rng(66)
+    n, d, s = 2500, 6, 96
+    X = np.asfortranarray(rng.integers(-3, 4, (n, d)).astype(np.float64))
+    init = _init(n, s, 5)
+    X[init[9]] = X[init[2]]
+    X[init[70]] = X[init[2]]
+    for iter_max in (1, 4):
+        U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=iter_max, return_info=True)
+        Uo, ao, io = oracle.kmeans_lloyd(X, s, init, iter_max, NT)
+        assert iters == io and np.array_equal(assign, ao) and np.array_equal(U, Uo)
+    A = np.asfortranarray(X[init])
+    for r in (1, 2, 3, 5):
+        ind, dist = flgp.knn_distances(X, A, r)
+        io_, do_ = oracle.knn(X, A, r, want_dist=True, nthreads=NT)
+        assert np.array_equal(ind, io_) and np.array_equal(dist, do_)
+
+
+@pytest.mark.parametrize("n,d,s,r", [(5000, 16, 300, 5), (700, 101, 64, 2), (2000, 9, 257, 3), (333, 50, 70, 1)])
+def test_knn_large_d_tensor_core_bitexact(flgp, oracle, n, d, s, r, monkeypatch):
+    rng = np.random.default_rng(n + d)
+    X = np.asfortranarray(rng.standard_normal((n, d)) * 5.0)
+    U = np.asfortranarray(X[_init(n, s, 3)] + 0.3 * rng.standard_normal((s, d)))
+    ind, dist = flgp.knn_distances(X, U, r)
+    io_, do_ = oracle.knn(X, U, r, want_dist=True, nthreads=NT)
+    assert np.array_equal(ind, io_) and np.array_equal(dist, do_)
+    monkeypatch.setenv("FLGP_NO_DMMA_DIST", "1")
+    ind2, dist2 = flgp.knn_distances(X, U, r)
+    assert np.array_equal(ind2, ind) and np.array_equal(dist2, dist)
+
+
 # ------------------------------------------------------------------------------------------- large d (config 3 shape)
 def test_c3_shape_pipeline_large_d(flgp, oracle):
     """BASELINE config 3's shape at reduced n: d = 784, r = 5 through the tiled (any-d) k-means / KNN / LAE kernels."""
