@@ -61,7 +61,9 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------ helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  The timed
+    region lasts ~0.2 s, shorter than one nvidia-smi start-up, so the samples come from NVML in-process (pynvml, the
+    library nvidia-smi itself reads) every 5 ms; nvidia-smi -lms is the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -69,10 +71,31 @@ class ClockSampler:
 
     def __init__(self, gpu_index: int):
         self.idx = gpu_index
-        self.rows = []
+        self.rows = []   # (sm_mhz, max_mhz, watts, [reasons])
         self.p = None
+        self.nv = None
+        self.run = False
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.idx
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.idx])
+                except Exception:
+                    pass
+            self.h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.nv = nv
+            self.run = True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
                                        "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
@@ -82,32 +105,62 @@ class ClockSampler:
         except Exception:
             self.p = None
 
-    def _read(self):
-        for line in self.p.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
-
-    def stop(self):
-        if not self.p:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+    def _poll(self):
+        nv = self.nv
+        bits = []
+        for nm, attr in (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+                         ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+                         ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+                         ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap")):
+            v = getattr(nv, attr, None)
+            if v is None:
+                v = getattr(nv, attr.replace("ClocksEventReason", "ClocksThrottleReason"), None)
+            if v is not None:
+                bits.append((nm, int(v)))
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while self.run:
             try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                pw.append(float(r[3]))
-                for nm, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = int(get_reasons(self.h)) if get_reasons else 0
+                self.rows.append((sm, self.mx, pw, [nm for nm, b in bits if mask & b]))
             except Exception:
                 pass
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+            time.sleep(0.005)
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.p.stdout:
+            r = [x.strip() for x in line.split(",")]
+            try:
+                self.rows.append((float(r[1]), float(r[2]), float(r[3]),
+                                  [nm for nm, v in zip(names, r[4:8]) if v.lower().startswith("active")]))
+            except Exception:
+                pass
+
+    def stop(self):
+        if self.nv is None and not self.p:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml / nvidia-smi unavailable"]}
+        if self.nv is not None:
+            self.run = False
+            self.t.join(timeout=2)
+            src = "nvml, 5 ms period"
+        else:
+            self.p.terminate()
+            try:
+                self.p.wait(timeout=5)
+            except Exception:
+                self.p.kill()
+            src = "nvidia-smi -lms 200"
+        sm = [r[0] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons.update(r[3])
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None,
+                "power_w_max": max(r[2] for r in self.rows) if self.rows else None, "samples": len(sm),
+                "source": src, "reasons": sorted(reasons)}
 
 
 def measured_peaks():

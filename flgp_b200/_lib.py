@@ -18,6 +18,8 @@ p_i32 = C.POINTER(C.c_int32)
 p_i64 = C.POINTER(C.c_int64)
 p_void = C.c_void_p
 
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.c_uint, p_f64, p_f64, p_void)  # nlopt-style: f(n, x, grad, data)
+
 _lib = None
 
 
@@ -87,6 +89,18 @@ def _declare(lib):
                                                     C.c_int, C.c_double, C.c_double, C.c_double, C.c_char_p,
                                                     C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, p_i32, c_u64,
                                                     p_f64, p_f64, p_f64]),
+        "flgp_regression_objective": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, p_f64, p_f64, p_f64]),
+        "flgp_train_regression": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, p_f64, p_f64,
+                                            C.POINTER(C.c_int)]),
+        "flgp_mma_minimize": (C.c_int, [C.c_int, OBJECTIVE_FN, p_void, p_f64, p_f64, p_f64, p_f64, C.c_double, C.c_int,
+                                        C.POINTER(C.c_int)]),
+        "flgp_fit_lae_regression": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_double, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, p_i32, c_u64, p_f64, p_f64, p_f64, p_f64, p_f64]),
+        "flgp_fit_se_regression": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int,
+                                             C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, p_i32, c_u64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64,
+                                             p_f64, C.POINTER(H)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

@@ -464,16 +464,66 @@ def regression_fixed(eigenpair: EigenPair, Y_local, m_total: int, K: int, pars: 
     return y, cov
 
 
+def regression_objective(eigenpair: EigenPair, Y_local, m_total: int, K: int, pars: Sequence[float],
+                         sigma: float = 1e-5, approach: str = "posterior"):
+    """negative_marginal_likelihood_regression_cpp / negative_log_posterior_regression_cpp at pars = (t, noise)
+    (src/train.cpp:333-436, noise="same").  Returns (objective, grad[2])."""
+    Y_local = np.ascontiguousarray(Y_local, dtype=np.float64).reshape(-1)
+    x = np.ascontiguousarray(pars, dtype=np.float64)
+    obj = C.c_double()
+    grad = np.zeros(2)
+    check(eigenpair.ctx._lib.flgp_regression_objective(eigenpair._h, _pf(Y_local), m_total, K, sigma, _b(approach),
+                                                       _pf(x), C.byref(obj), _pf(grad)))
+    return obj.value, grad
+
+
+def train_regression_gp(eigenpair: EigenPair, Y_local, m_total: int, K: int, sigma: float = 1e-5,
+                        approach: str = "posterior", x0: Optional[Sequence[float]] = None):
+    """train_regression_gp_cpp, noise="same" (src/train.cpp:557-671).  Returns (pars, obj, evaluations)."""
+    Y_local = np.ascontiguousarray(Y_local, dtype=np.float64).reshape(-1)
+    x = np.array(x0 if x0 is not None else (np.nan, np.nan), dtype=np.float64)
+    obj = C.c_double()
+    nev = C.c_int()
+    check(eigenpair.ctx._lib.flgp_train_regression(eigenpair._h, _pf(Y_local), m_total, K, sigma, _b(approach), _pf(x),
+                                                   C.byref(obj), C.byref(nev)))
+    return x, obj.value, nev.value
+
+
+def mma_minimize(f, x0, lb, ub, xtol_rel: float = 1e-5, maxeval: int = 1000):
+    """The library's NLOPT_LD_MMA restatement on a Python objective f(x) -> (value, grad).  Host only."""
+    from ._lib import OBJECTIVE_FN, load
+
+    x = np.array(x0, dtype=np.float64)
+    n = x.size
+
+    def cb(nn, xp, gp, _):
+        xx = np.array([xp[i] for i in range(nn)])
+        v, g = f(xx)
+        if gp:
+            for i in range(nn):
+                gp[i] = float(g[i])
+        return float(v)
+
+    cfn = OBJECTIVE_FN(cb)
+    lbv = np.ascontiguousarray(lb, dtype=np.float64)
+    ubv = np.ascontiguousarray(ub, dtype=np.float64)
+    minf = C.c_double()
+    nev = C.c_int()
+    check(load().flgp_mma_minimize(n, cfn, None, _pf(lbv), _pf(ubv), _pf(x), C.byref(minf), xtol_rel, maxeval,
+                                   C.byref(nev)))
+    return x, minf.value, nev.value
+
+
 def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, approach="posterior",
                                noise="same", models=None, output_cov: bool = False, nstart: int = 1, *,
-                               pars: Sequence[float], init_idx=None, seed: int = 0, iter_max: int = 100,
-                               ctx: Optional[Context] = None):
-    """fit_lae_regression_gp_rcpp (R/Fit.R:56-69 -> src/Fit.cpp:20-99) with the hyper-parameters
-    pars = (t, noise variance) SUPPLIED: the nlopt optimiser of the reference (src/train.cpp:557-671) is
-    outside the hot path."""
+                               pars: Optional[Sequence[float]] = None, init_idx=None, seed: int = 0,
+                               iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_lae_regression_gp_rcpp (R/Fit.R:56-69 -> src/Fit.cpp:20-99).  pars = (t, noise variance) given: used as
+    is; pars = None: trained by empirical Bayes as the reference does (src/train.cpp:557-671; the optimiser is a
+    restatement of NLopt's MMA, so trained pars agree with the reference to optimiser tolerance)."""
     if noise != "same":
         raise FlgpError("The noise setting is illegal!" if noise != "different"
-                        else "noise=\"different\" needs the optimiser; not part of the fixed-parameter path")
+                        else "noise=\"different\" (one variance per training point) is not part of this path")
     if approach not in ("posterior", "marginal"):
         raise FlgpError("This model selection approach is not supported!")
     ctx = ctx or default_ctx()
@@ -487,12 +537,61 @@ def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: 
     train = np.zeros(m)
     test = np.zeros(m_new)
     cov = np.zeros(m_new)
-    check(ctx._lib.flgp_fit_lae_regression_fixed(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma,
-                                                 pars[0], pars[1], _b(mo["subsample"]), _b(mo["kernel"]),
-                                                 _gl(mo["gl"]), int(bool(mo["root"])), nstart, iter_max,
-                                                 _pi(_idx(init_idx)), seed, _pf(train), _pf(test), _pf(cov)))
-    res = {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(pars)}
+    x = np.array(pars if pars is not None else (np.nan, np.nan), dtype=np.float64)
+    obj = C.c_double()
+    check(ctx._lib.flgp_fit_lae_regression(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma,
+                                           _b(approach), _b(mo["subsample"]), _b(mo["kernel"]), _gl(mo["gl"]),
+                                           int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed, _pf(x),
+                                           _pf(train), _pf(test), _pf(cov), C.byref(obj)))
+    res = {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(x),
+           "obj": obj.value}
     if output_cov:
-        res["C"] = heat_kernel_covariance_rcpp(X, X_new, s, r, pars[0], K, mo, nstart, init_idx=init_idx, seed=seed,
+        res["C"] = heat_kernel_covariance_rcpp(X, X_new, s, r, x[0], K, mo, nstart, init_idx=init_idx, seed=seed,
                                                iter_max=iter_max, ctx=ctx)
+    return res
+
+
+def fit_se_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, a2s=None,
+                              approach="posterior", noise="same", models=None, output_cov: bool = False,
+                              nstart: int = 1, *, pars: Optional[Sequence[float]] = None, init_idx=None, seed: int = 0,
+                              iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_se_regression_gp_rcpp (R/Fit.R:119-136 -> src/Fit.cpp:102-219): squared-exponential weights on the KNN
+    graph with a grid search over the bandwidth a2 (default exp(seq(log 0.1, log 10, length 10))); one k-means and one
+    KNN serve the whole grid.  models["kernel"] is ignored, as in the reference."""
+    if noise != "same":
+        raise FlgpError("The noise setting is illegal!" if noise != "different"
+                        else "noise=\"different\" (one variance per training point) is not part of this path")
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    if a2s is None:
+        a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    a2s = np.ascontiguousarray(a2s, dtype=np.float64)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    train = np.zeros(m)
+    test = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    xo = np.zeros(2)
+    fixed = np.ascontiguousarray(pars, dtype=np.float64) if pars is not None else None
+    a2 = C.c_double()
+    obj = C.c_double()
+    h = C.c_void_p()
+    check(ctx._lib.flgp_fit_se_regression(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma, _pf(a2s),
+                                          a2s.size, _b(approach), _b(mo["subsample"]), _gl(mo["gl"]),
+                                          int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed,
+                                          _pf(fixed), _pf(train), _pf(test), _pf(cov), _pf(xo), C.byref(a2),
+                                          C.byref(obj), C.byref(h)))
+    ep = EigenPair(ctx, h)
+    res = {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(xo),
+           "a2": a2.value, "obj": obj.value, "eigenpair": ep}
+    if output_cov:
+        n = m + m_new
+        Kk = s if K < 0 else K
+        res["C"] = HK_from_spectrum_cpp(ep, Kk, xo[0], np.arange(n, dtype=np.int32), np.arange(m, dtype=np.int32))
     return res

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <memory>
 #include <unordered_set>
 
@@ -117,6 +118,28 @@ void chol_solve(const std::vector<double>& L, int n, double* B, int nrhs) {
       b[i] = v / L[i + (size_t)n * i];
     }
   }
+}
+
+#include "train.inl"
+
+// deterministic sum of len doubles: fixed grid, per-thread sequential partial sums, fixed-order tree
+__global__ void __launch_bounds__(256) sum_partial_kernel(const double* __restrict__ v, int64_t len, double* part) {
+  __shared__ double sh[256];
+  double a = 0.0;
+  for (int64_t e = blockIdx.x * 256 + threadIdx.x; e < len; e += (int64_t)gridDim.x * 256) a += v[e];
+  sh[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+__global__ void sum_final_kernel(const double* __restrict__ part, int np, double* out) {
+  if (threadIdx.x || blockIdx.x) return;
+  double a = 0.0;
+  for (int q = 0; q < np; ++q) a += part[q];
+  *out = a;
 }
 
 __global__ void build_lift_kernel(const double* __restrict__ Y, int s, int K, const double* __restrict__ scale,
@@ -431,6 +454,101 @@ void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total
     sparse_quadform_run(c, sp->n_local, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, B.p, ns, cov);
   }
   sync(c);
+}
+
+// ---- fit_se_regression_gp_cpp's grid search (src/Fit.cpp:126-178) ------------------------------------------
+// One k-means and one KNN; per bandwidth a2: Z = exp(-dist / (a2 * mean dist)) -> graph Laplacian -> spectrum ->
+// training objective.  Returns the handle of the best a2 (largest objective).
+template <class T>
+void dev_copy(Ctx* c, DevBuf<T>& dst, const DevBuf<T>& src) {
+  dst.alloc(src.n);
+  if (src.n) FLGP_CUDA(cudaMemcpyAsync(dst.p, src.p, sizeof(T) * src.n, cudaMemcpyDeviceToDevice, c->stream));
+}
+
+std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int64_t n_local, int64_t n_total,
+                                                int64_t row_offset, int d, int s, int r, int K, const Models& mo,
+                                                const int32_t* init_idx, uint64_t seed, const double* Ydev,
+                                                int64_t m_total, double sigma, bool posterior, const double* a2s,
+                                                int n_a2, const double* fixed_pars, double* pars_out, double* best_a2,
+                                                double* best_obj) {
+  need(n_local >= 0 && n_total >= 1 && d >= 1, "bad matrix shape");
+  need(s >= 1 && s <= n_total, "need 1 <= s <= n");
+  need(r >= 1 && r <= s, "need 1 <= r <= s");
+  need(n_total < ((int64_t)1 << 31), "n must fit in int32 indices per process API");
+  need(n_a2 >= 1 && a2s, "empty bandwidth grid");
+  parse_gl(mo.gl);
+  if (K < 0) K = s;
+  flgp_spectrum base;
+  base.c = c;
+  base.n_local = n_local;
+  base.n_total = n_total;
+  base.row_offset = row_offset;
+  base.d = d;
+  base.s = s;
+  base.r = r;
+  stage_subsample(c, &base, Xdev, mo, init_idx, seed, nullptr);
+  const int64_t nr = std::max<int64_t>(n_local * r, 1);
+  DevBuf<int32_t> ind(nr), Zj(nr);
+  DevBuf<double> dist(nr), D(nr);
+  bool srt = false;
+  {
+    StageScope st(c, "knn", 2.0 * s * d * (double)n_local, (8.0 * d + 12.0 * r) * (double)n_local);
+    knn_run(c, Xdev, n_local, n_local, d, base.U.p, s, s, r, ind.p, dist.p, &base.sorted, &srt);
+  }
+  knn_to_csr_run(c, n_local, r, ind.p, dist.p, Zj.p, D.p, srt ? base.sorted.perm.p : nullptr);
+  sync(c);
+  base.sorted = KMeansSorted();
+  // distances_mean = distances_sp.coeffs().sum() / (n r)   (src/Fit.cpp:131)
+  const int np = 256;
+  DevBuf<double> part(np + 1);
+  part.zero(c->stream);
+  if (n_local > 0) FLGP_LAUNCH(c, sum_partial_kernel, np, 256, 0, D.p, n_local * r, part.p);
+  FLGP_LAUNCH(c, sum_final_kernel, 1, 32, 0, part.p, np, part.p + np);
+  comm_allreduce_f64(c, part.p + np, 1);
+  double dsum = 0.0;
+  FLGP_CUDA(cudaMemcpyAsync(&dsum, part.p + np, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  sync(c);
+  const double dmean = dsum / ((double)n_total * r);
+  std::unique_ptr<flgp_spectrum> best;
+  double max_obj = -std::numeric_limits<double>::infinity();
+  for (int q = 0; q < n_a2; ++q) {
+    std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
+    sp->c = c;
+    sp->n_local = n_local;
+    sp->n_total = n_total;
+    sp->row_offset = row_offset;
+    sp->d = d;
+    sp->s = s;
+    sp->r = r;
+    sp->ucols = base.ucols;
+    sp->kmeans_iters = base.kmeans_iters;
+    dev_copy(c, sp->U, base.U);
+    dev_copy(c, sp->Zj, Zj);
+    sp->Zx.alloc(nr);
+    se_weights_run(c, D.p, n_local * r, a2s[q] * dmean, sp->Zx.p);  // src/Fit.cpp:150
+    const double* nc = (mo.gl == FLGP_GL_CLUSTER_NORMALIZED) ? sp->U.p + (size_t)s * d : nullptr;
+    stage_graph_laplacian(c, n_local, s, r, sp->Zj.p, sp->Zx.p, mo.gl, nc, n_total);
+    stage_spectrum(c, sp.get(), K, mo.root);
+    const RegTrain T = reg_train_prepare(sp.get(), Ydev, m_total, K, sigma);
+    double x[2] = {std::nan(""), std::nan("")};
+    double obj;
+    if (fixed_pars) {
+      x[0] = fixed_pars[0];
+      x[1] = fixed_pars[1];
+      obj = -reg_objective(T, x, nullptr, posterior);
+    } else {
+      obj = train_regression(T, posterior, x, nullptr);
+    }
+    if (obj > max_obj || !best) {  // src/Fit.cpp:169-174 (first candidate kept even when every objective is -inf)
+      max_obj = obj;
+      pars_out[0] = x[0];
+      pars_out[1] = x[1];
+      if (best_a2) *best_a2 = a2s[q];
+      best = std::move(sp);
+    }
+  }
+  if (best_obj) *best_obj = max_obj;
+  return best;
 }
 
 }  // namespace
@@ -982,6 +1100,126 @@ int flgp_fit_lae_regression_fixed(flgp_ctx* ctx, const double* X, const double* 
     std::memcpy(train, y.data(), sizeof(double) * m);
     if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
     if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
+static int approach_flag(const char* approach, bool* posterior) {
+  const std::string a = approach ? approach : "posterior";
+  if (a == "posterior") *posterior = true;
+  else if (a == "marginal") *posterior = false;
+  else return 1;
+  return 0;
+}
+
+int flgp_regression_objective(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double sigma,
+                              const char* approach, const double* pars, double* obj, double* grad) {
+  return guard([&] {
+    need(h && Y_local && pars && obj, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = h->c;
+    const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
+    DevBuf<double> dY(std::max<int64_t>(m_local, 1));
+    if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
+    const RegTrain T = reg_train_prepare(h, dY.p, m_total, K, sigma);
+    *obj = reg_objective(T, pars, grad, post);
+  });
+}
+
+int flgp_train_regression(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double sigma,
+                          const char* approach, double* pars_io, double* obj, int* nevals) {
+  return guard([&] {
+    need(h && Y_local && pars_io, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = h->c;
+    const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
+    DevBuf<double> dY(std::max<int64_t>(m_local, 1));
+    if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
+    const RegTrain T = reg_train_prepare(h, dY.p, m_total, K, sigma);
+    const double o = train_regression(T, post, pars_io, nevals);
+    if (obj) *obj = o;
+  });
+}
+
+int flgp_mma_minimize(int n, flgp_objective_fn f, void* data, const double* lb, const double* ub, double* x,
+                      double* minf, double xtol_rel, int maxeval, int* nevals) {
+  return guard([&] {
+    need(n >= 1 && f && lb && ub && x && minf, "null argument");
+    const int nev = mma_minimize(n, [&](const double* xx, double* g) { return f((unsigned)n, xx, g, data); }, lb, ub, x,
+                                 minf, xtol_rel, maxeval > 0 ? maxeval : 1000);
+    if (nevals) *nevals = nev;
+  });
+}
+
+int flgp_fit_lae_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                            int64_t m_new, int d, int s, int r, int K, double sigma, const char* approach,
+                            const char* subsample, const char* kernel, int gl, int root, int nstart, int iter_max,
+                            const int32_t* init_idx, uint64_t seed, double* pars_io, double* train, double* test,
+                            double* cov, double* obj) {
+  if (K < 0) K = s;  // src/Fit.cpp:37-39
+  bool post = true;
+  if (approach_flag(approach, &post)) {
+    g_err = "This model selection approach is not supported!";
+    return 2;
+  }
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, m, X_new, m_new, d, s, r, K, subsample, kernel, gl, root, nstart, 0.1,
+                                     iter_max, init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  return guard([&] {
+    need(Y && train && pars_io, "null argument");
+    if (!(pars_io[0] == pars_io[0] && pars_io[1] == pars_io[1])) {  // NaN: train (src/Fit.cpp:45-62)
+      int rc1 = flgp_train_regression(h, Y, m, K, sigma, approach, pars_io, obj, nullptr);
+      if (rc1) fail(rc1, "%s", g_err.c_str());
+    } else if (obj) {
+      int rc1 = flgp_regression_objective(h, Y, m, K, sigma, approach, pars_io, obj, nullptr);
+      if (rc1) fail(rc1, "%s", g_err.c_str());
+      *obj = -*obj;
+    }
+    const int64_t n = m + m_new;
+    std::vector<double> y(n), cv(n);
+    int rc2 = flgp_regression_fixed(h, Y, m, K, pars_io[0], pars_io[1], sigma, y.data(), cv.data());
+    if (rc2) fail(rc2, "%s", g_err.c_str());
+    std::memcpy(train, y.data(), sizeof(double) * m);
+    if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
+    if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
+int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                           int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,
+                           const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,
+                           const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
+                           double* test, double* cov, double* pars_out, double* best_a2, double* best_obj,
+                           flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && X && Y && train && pars_out, "null argument");
+    need(m >= 1 && m_new >= 0, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = &ctx->c;
+    need(c->nranks == 1, "flgp_fit_se_regression is the single-process entry point");
+    const int64_t n = m + m_new;
+    DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+    DevBuf<double> dY(m);
+    dY.upload(Y, m, c->stream);
+    const Models mo = make_models(subsample, "se", gl, root, nstart, 0.1, iter_max);
+    std::unique_ptr<flgp_spectrum> sp = se_grid_pipeline(c, dX.p, n, n, 0, d, s, r, K, mo, init_idx, seed, dY.p, m,
+                                                         sigma, post, a2s, n_a2, fixed_pars, pars_out, best_a2,
+                                                         best_obj);
+    const int Kk = K < 0 ? s : K;
+    DevBuf<double> dy(n), dc(n);
+    regression_fixed_dev(sp.get(), dY.p, m, Kk, pars_out[0], pars_out[1], sigma, dy.p, dc.p);
+    std::vector<double> y(n), cv(n);
+    dy.download(y.data(), n, c->stream);
+    dc.download(cv.data(), n, c->stream);
+    sync(c);
+    std::memcpy(train, y.data(), sizeof(double) * m);
+    if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
+    if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+    if (out) *out = sp.release();
   });
 }
 

@@ -10,6 +10,8 @@
 // Roofline: HBM (8d + 4r bytes read, 12r written per point); the solver itself is latency /
 // divergence bound (data-dependent 1..100 outer iterations) and is reported with its iteration
 // count, as SURVEY.md §8d asks.
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace flgp {
@@ -31,6 +33,13 @@ struct GlobU {  // anchors read in place (large d): U(c_a, k)
   int64_t ldu;
   int c[LAE_RMAX];
   __device__ __forceinline__ double operator()(int a, int k) const { return U[c[a] + ldu * k]; }
+};
+struct GlobURow {  // the same from a row-major copy (k contiguous): a thread streams its r anchor rows, so every
+                   // 32-byte sector it fetches is used four times instead of once
+  const double* U;
+  int64_t off[LAE_RMAX];
+  int c[LAE_RMAX];
+  __device__ __forceinline__ double operator()(int a, int k) const { return U[off[a] + k]; }
 };
 struct GlobX {
   const double* X;
@@ -113,6 +122,7 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
   add_stats(stats, it, bt);
 }
 
+template <bool ROWMAJOR>
 __global__ void __launch_bounds__(128)
 lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ U,
                    int64_t ldu, int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj,
@@ -122,10 +132,17 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
   int it = 0, bt = 0;
   if (i < n) {
     GlobX x{X + i, ldx};
-    GlobU Ur;
+    typename std::conditional<ROWMAJOR, GlobURow, GlobU>::type Ur;
     Ur.U = U;
-    Ur.ldu = ldu;
-    for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
+    if constexpr (ROWMAJOR) {
+      for (int a = 0; a < r; ++a) {
+        Ur.c[a] = ind[i + n * a];
+        Ur.off[a] = (int64_t)Ur.c[a] * ldu;  // ldu = row pitch of the row-major copy
+      }
+    } else {
+      Ur.ldu = ldu;
+      for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
+    }
     double z[LAE_RMAX];
     const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z);
     it = ls.iters;
@@ -174,7 +191,6 @@ __global__ void simplex_project_kernel(const double* v, int r, double* z, double
 
 void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
              int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats, const int32_t* perm) {
-  (void)s;
   if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
   if (n <= 0) return;
   const int grid = ceil_div(n, 128);
@@ -187,7 +203,15 @@ void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
   LAE_CASE(2, 2) LAE_CASE(3, 2) LAE_CASE(4, 2) LAE_CASE(5, 2)
   LAE_CASE(2, 3) LAE_CASE(3, 3) LAE_CASE(4, 3) LAE_CASE(5, 3)
 #undef LAE_CASE
-  FLGP_LAUNCH(c, lae_generic_kernel, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats, perm);
+  if (d >= 8) {  // long rows: read the anchors from a row-major copy (sector reuse through L1)
+    DevBuf<double> Ur((size_t)s * d);
+    to_rowmajor_run(c, U, s, ldu, d, d, Ur.p);
+    FLGP_LAUNCH(c, lae_generic_kernel<true>, grid, 128, 0, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats,
+                perm);
+    sync(c);  // Ur is released on return
+    return;
+  }
+  FLGP_LAUNCH(c, lae_generic_kernel<false>, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats, perm);
 }
 
 void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx,

@@ -1,0 +1,287 @@
+// train.inl — empirical-Bayes training of the GP regression hyper-parameters (t, noise variance) on a spectrum handle
+// (included by capi.cu inside its anonymous namespace).
+//
+//   reg_objective   negative_marginal_likelihood_regression_cpp / negative_log_posterior_regression_cpp, noise="same"
+//                   (/root/reference/src/train.cpp:333-436; priors of PostOFDataReg, src/train.h:144-156)
+//   mma_minimize    the optimiser behind nlopt_create(NLOPT_LD_MMA, 2) of train_regression_gp_cpp
+//                   (src/train.cpp:557-671).  nloptr / NLopt is an un-vendored dependency of the reference (version
+//                   unpinned, DESCRIPTION): restated from the published algorithm — Svanberg's CCSA with MMA
+//                   approximations (SIAM J. Optim. 12, 2002) in NLopt's arrangement for bound constraints only.
+//                   Parity with the reference is therefore to optimiser tolerance (xtol_rel = 1e-5), not bitwise.
+//
+// Everything n- and m-sized stays on the device: the objective needs only V1^T V1 (K x K), V1^T Y (K) and Y^T Y of the
+// m training rows of the lifted eigenvectors (m > K, the Woodbury branch), or the m x K block itself (m <= K).
+// What remains per evaluation is K x K (or m x m) dense algebra, K <= a few hundred: host C++ (the reference: Eigen LLT).
+
+struct RegTrain {
+  int m = 0, K = 0;
+  double sigma = 1e-5;
+  std::vector<double> ev;   // 1 - values[:K]
+  std::vector<double> VtV;  // K x K (m > K)
+  std::vector<double> b;    // V1^T Y (m > K)
+  double yty = 0.0;
+  std::vector<double> V;    // m x K row-major (m <= K)
+  std::vector<double> Y;    // m (m <= K)
+};
+
+RegTrain reg_train_prepare(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double sigma) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total && m_total < INT32_MAX, "bad number of training rows");
+  const int r = sp->r, KK = sp->K;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  RegTrain T;
+  T.m = (int)m_total;
+  T.K = K;
+  T.sigma = sigma;
+  T.ev.resize(K);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - sp->values[k];
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
+  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  if (m_total > K) {
+    const size_t words = (size_t)KK * KK + KK + 1;
+    DevBuf<double> Gg(words);
+    Gg.zero(c->stream);
+    gram_small_run(c, V1.p, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
+    if (m_local > 0) gemv_run(c, Ydev, Ydev, 1, (int)m_local, Gg.p + (size_t)KK * KK + KK);
+    comm_allreduce_f64(c, Gg.p, words);
+    std::vector<double> h(words);
+    Gg.download(h.data(), words, c->stream);
+    sync(c);
+    T.VtV.resize((size_t)K * K);
+    T.b.resize(K);
+    for (int j = 0; j < K; ++j) {
+      for (int i = 0; i < K; ++i) T.VtV[i + (size_t)K * j] = h[i + (size_t)KK * j];
+      T.b[j] = h[(size_t)KK * KK + j];
+    }
+    T.yty = h[(size_t)KK * KK + KK];
+  } else {
+    const int m = (int)m_total;
+    DevBuf<double> Vall((size_t)m * KK + m);
+    Vall.zero(c->stream);
+    if (m_local > 0) {
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+                                cudaMemcpyDeviceToDevice, c->stream));
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + sp->row_offset, Ydev, sizeof(double) * m_local,
+                                cudaMemcpyDeviceToDevice, c->stream));
+    }
+    comm_allreduce_f64(c, Vall.p, (size_t)m * KK + m);
+    std::vector<double> h((size_t)m * KK + m);
+    Vall.download(h.data(), h.size(), c->stream);
+    sync(c);
+    T.V.resize((size_t)m * K);
+    for (int i = 0; i < m; ++i)
+      for (int k = 0; k < K; ++k) T.V[(size_t)i * K + k] = h[(size_t)i * KK + k];
+    T.Y.assign(h.begin() + (size_t)m * KK, h.end());
+  }
+  return T;
+}
+
+// inverse from a lower Cholesky factor (column-major n x n): returns A^-1 (full, symmetric)
+std::vector<double> chol_inverse(const std::vector<double>& L, int n) {
+  std::vector<double> I((size_t)n * n, 0.0);
+  for (int i = 0; i < n; ++i) I[i + (size_t)n * i] = 1.0;
+  chol_solve(L, n, I.data(), n);
+  return I;
+}
+
+// objective value and gradient at x = (t, noise); posterior adds the priors.  Returns +inf when the system is not
+// positive definite (the reference's LLT would silently produce NaN there).
+double reg_objective(const RegTrain& T, const double* x, double* grad, bool posterior) {
+  const int m = T.m, K = T.K;
+  const double t = x[0], noise = x[1], ns = noise + T.sigma;
+  double g0 = 0.0, g1 = 0.0, nmll = 0.0;
+  if (m <= K) {
+    // C = V diag(exp(-t ev)) V^T + (sigma + noise) I     (src/train.cpp:347-372)
+    std::vector<double> C((size_t)m * m), lam(K), dlam(K);
+    for (int k = 0; k < K; ++k) {
+      lam[k] = std::exp(-t * T.ev[k]);
+      dlam[k] = -T.ev[k] * lam[k];
+    }
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0;
+        for (int k = 0; k < K; ++k) a += (T.V[(size_t)i * K + k] * lam[k]) * T.V[(size_t)j * K + k];
+        C[i + (size_t)m * j] = a + (i == j ? (T.sigma + noise) : 0.0);
+      }
+    std::vector<double> L = C;
+    if (!chol_lower(L, m)) return INFINITY;
+    std::vector<double> alpha = T.Y;
+    chol_solve(L, m, alpha.data(), 1);
+    if (grad) {
+      const std::vector<double> Ci = chol_inverse(L, m);
+      // U = alpha alpha^T - C^-1;  grad_t = V diag(dlam) V^T
+      double s0 = 0.0, tr = 0.0;
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+          double gt = 0.0;
+          for (int k = 0; k < K; ++k) gt += (T.V[(size_t)j * K + k] * dlam[k]) * T.V[(size_t)i * K + k];  // grad_t(j, i)
+          s0 += (alpha[i] * alpha[j] - Ci[i + (size_t)m * j]) * gt;
+        }
+      for (int i = 0; i < m; ++i) tr += alpha[i] * alpha[i] - Ci[i + (size_t)m * i];
+      g0 = -0.5 * s0;
+      g1 = -0.5 * tr;
+    }
+    double ya = 0.0, ld = 0.0;
+    for (int i = 0; i < m; ++i) {
+      ya += T.Y[i] * alpha[i];
+      ld += std::log(L[i + (size_t)m * i] + 1e-9);
+    }
+    nmll = 0.5 * ya + ld;
+  } else {
+    // Woodbury branch (src/train.cpp:373-417) through the K-sized statistics:
+    //   Q = ls VtV ls + ns I,  w = ls Q^-1 ls b,  V^T alpha = (b - VtV w) / ns,  Y^T alpha = (yty - b.w) / ns,
+    //   alpha^T alpha = (yty - 2 b.w + w^T VtV w) / ns^2
+    std::vector<double> ls(K), A(K), Q((size_t)K * K);
+    for (int k = 0; k < K; ++k) {
+      ls[k] = std::exp(-0.5 * t * T.ev[k]) + 0.0;
+      A[k] = -T.ev[k] * (std::exp(-t * T.ev[k]) + 0.0) + 0.0;
+    }
+    for (int j = 0; j < K; ++j)
+      for (int i = 0; i < K; ++i) Q[i + (size_t)K * j] = (ls[i] * T.VtV[i + (size_t)K * j]) * ls[j] + (i == j ? ns : 0.0);
+    std::vector<double> L = Q;
+    if (!chol_lower(L, K)) return INFINITY;
+    std::vector<double> w(K), Gw(K);
+    for (int k = 0; k < K; ++k) w[k] = ls[k] * T.b[k];
+    chol_solve(L, K, w.data(), 1);
+    for (int k = 0; k < K; ++k) w[k] *= ls[k];
+    double bw = 0.0, wGw = 0.0;
+    for (int i = 0; i < K; ++i) {
+      double a = 0.0;
+      for (int j = 0; j < K; ++j) a += T.VtV[i + (size_t)K * j] * w[j];
+      Gw[i] = a;
+      bw += T.b[i] * w[i];
+      wGw += w[i] * a;
+    }
+    if (grad) {
+      const std::vector<double> Qi = chol_inverse(L, K);
+      double s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+      for (int k = 0; k < K; ++k) {
+        const double vta = (T.b[k] - Gw[k]) / ns;
+        s1 += vta * A[k] * vta;
+        s2 += A[k] * T.VtV[k + (size_t)K * k];
+      }
+      // s3 = sum_ij (Qi ls VtV)(i,j) (A VtV ls)(j,i);  s4 = sum_ij Qi(i,j) (ls VtV ls)(j,i)
+      std::vector<double> P((size_t)K * K);  // P = Qi * (ls VtV)
+      for (int j = 0; j < K; ++j)
+        for (int i = 0; i < K; ++i) {
+          double a = 0.0;
+          for (int k = 0; k < K; ++k) a += Qi[k + (size_t)K * i] * (ls[k] * T.VtV[k + (size_t)K * j]);  // Qi symmetric
+          P[i + (size_t)K * j] = a;
+        }
+      for (int j = 0; j < K; ++j)
+        for (int i = 0; i < K; ++i) {
+          s3 += P[i + (size_t)K * j] * ((A[j] * T.VtV[j + (size_t)K * i]) * ls[i]);
+          s4 += Qi[i + (size_t)K * j] * ((ls[j] * T.VtV[j + (size_t)K * i]) * ls[i]);
+        }
+      g0 = -0.5 * s1 + 0.5 / ns * s2 - 0.5 / ns * s3;
+      const double aa = (T.yty - 2.0 * bw + wGw) / (ns * ns);
+      g1 = -0.5 * aa + 0.5 / ns * ((double)m - s4);
+    }
+    double ld = 0.0;
+    for (int i = 0; i < K; ++i) ld += std::log(L[i + (size_t)K * i] + 1e-9);
+    nmll = 0.5 * (T.yty - bw) / ns + ld + 0.5 * (double)(m - K) * std::log(ns);
+  }
+  if (grad) {
+    if (std::fabs(g1) >= 10.0) g1 = g1 / std::fabs(g1) * 10.0;  // the reference's gradient clipping
+    grad[0] = g0;
+    grad[1] = g1;
+  }
+  if (posterior) {  // src/train.cpp:333-350, PostOFDataReg defaults
+    const double p = 1.0, q = 10.0, tau = 2.0, al = 1e-1, be = 1e-3;
+    nmll += p * std::log(t + 1e-9) + std::pow(t / tau, -q);
+    nmll += (al + 1.0) * std::log(ns) + be / ns;
+    if (grad) {
+      grad[0] += p / (t + 1e-9) - (q / tau) * std::pow(t / tau, -q - 1.0);
+      grad[1] += (al + 1.0) / ns - be / (ns * ns);
+    }
+  }
+  return nmll;
+}
+
+// CCSA-MMA, bound constraints only.  f(x, grad) -> value.  Returns the number of evaluations.
+template <class Fn>
+int mma_minimize(int n, Fn&& f, const double* lb, const double* ub, double* x, double* minf_out, double xtol_rel,
+                 int maxeval) {
+  std::vector<double> sigma(n), dfdx(n), dcur(n), xcur(x, x + n), xprev(x, x + n), xprevprev(x, x + n);
+  for (int j = 0; j < n; ++j) sigma[j] = (std::isinf(ub[j]) || std::isinf(lb[j])) ? 1.0 : 0.5 * (ub[j] - lb[j]);
+  double rho = 1.0;
+  double minf = f(x, dfdx.data());
+  int nev = 1, k = 0;
+  while (true) {
+    ++k;
+    if (k > 1) xprevprev = xprev;
+    xprev = xcur;
+    while (true) {
+      double gval = minf, wval = 0.0;
+      for (int j = 0; j < n; ++j) {
+        xcur[j] = x[j];
+        if (sigma[j] == 0.0) continue;
+        const double s2 = sigma[j] * sigma[j];
+        const double v = std::fabs(dfdx[j]) * sigma[j] + 0.5 * rho;
+        const double u = dfdx[j] * s2;
+        const double q = u / (v * sigma[j]);
+        double dx = (u / v) / (-1.0 - std::sqrt(std::fabs(1.0 - q * q)));
+        double xj = x[j] + dx;
+        if (xj > ub[j]) xj = ub[j];
+        else if (xj < lb[j]) xj = lb[j];
+        if (xj > x[j] + 0.9 * sigma[j]) xj = x[j] + 0.9 * sigma[j];
+        else if (xj < x[j] - 0.9 * sigma[j]) xj = x[j] - 0.9 * sigma[j];
+        xcur[j] = xj;
+        dx = xj - x[j];
+        const double dx2 = dx * dx, den = 1.0 / (s2 - dx2);
+        gval += (dfdx[j] * s2 * dx + v * dx2) * den;
+        wval += 0.5 * dx2 * den;
+      }
+      const double fcur = f(xcur.data(), dcur.data());
+      ++nev;
+      const bool inner_done = gval >= fcur;
+      if (fcur < minf) {
+        minf = fcur;
+        for (int j = 0; j < n; ++j) {
+          x[j] = xcur[j];
+          dfdx[j] = dcur[j];
+        }
+      }
+      if (nev >= maxeval) {
+        *minf_out = minf;
+        return nev;
+      }
+      if (inner_done) break;
+      if (fcur > gval) rho = std::min(10.0 * rho, 1.1 * (rho + (fcur - gval) / wval));
+      else if (!(fcur == fcur)) rho = 10.0 * rho;  // NaN objective: shrink the step
+    }
+    double dn = 0.0, xn = 0.0;
+    for (int j = 0; j < n; ++j) {
+      dn += std::fabs(xcur[j] - xprev[j]);
+      xn += std::fabs(xcur[j]);
+    }
+    if (dn <= xtol_rel * xn) break;
+    rho = std::max(0.1 * rho, 1e-5);
+    if (k > 1)
+      for (int j = 0; j < n; ++j) {
+        const double dx2 = (xcur[j] - xprev[j]) * (xprev[j] - xprevprev[j]);
+        sigma[j] *= dx2 < 0 ? 0.7 : (dx2 > 0 ? 1.2 : 1.0);
+        if (!std::isinf(ub[j]) && !std::isinf(lb[j])) {
+          sigma[j] = std::min(sigma[j], 10.0 * (ub[j] - lb[j]));
+          sigma[j] = std::max(sigma[j], 0.01 * (ub[j] - lb[j]));
+        }
+      }
+  }
+  *minf_out = minf;
+  return nev;
+}
+
+// train_regression_gp_cpp, noise="same": x0 = (10, 1), lb = (1e-3, 1e-4), ub = +inf, xtol_rel = 1e-5.
+// pars_io: in = start (or the defaults when NaN), out = optimum.  Returns obj = -minimum.
+double train_regression(const RegTrain& T, bool posterior, double* pars_io, int* nevals) {
+  double x[2] = {pars_io[0] == pars_io[0] ? pars_io[0] : 10.0, pars_io[1] == pars_io[1] ? pars_io[1] : 1.0};
+  const double lb[2] = {1e-3, 1e-4}, ub[2] = {INFINITY, INFINITY};
+  double minf = 0.0;
+  const int nev = mma_minimize(2, [&](const double* xx, double* g) { return reg_objective(T, xx, g, posterior); }, lb, ub,
+                               x, &minf, 1e-5, 1000);
+  pars_io[0] = x[0];
+  pars_io[1] = x[1];
+  if (nevals) *nevals = nev;
+  return -minf;
+}

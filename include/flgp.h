@@ -165,6 +165,41 @@ int flgp_fit_lae_regression_fixed(flgp_ctx* ctx, const double* X, const double* 
                                   int iter_max, const int32_t* init_idx, uint64_t seed, double* train, double* test,
                                   double* cov);
 
+/* ---- hyper-parameter training of the GP regression ---------------- */
+/* Objective of train_regression_gp_cpp with noise = "same": negative_marginal_likelihood_regression_cpp
+ * (approach "marginal") or negative_log_posterior_regression_cpp ("posterior"), src/train.cpp:333-436, at
+ * pars = (t, noise variance); grad (2, may be NULL) carries the reference's clipping of grad[1] to +-10.
+ * Y_local: labels of the training rows this rank owns (first m_total rows of X_all are the training rows). */
+int flgp_regression_objective(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double sigma,
+                              const char* approach, const double* pars, double* obj, double* grad);
+/* train_regression_gp_cpp, noise = "same" (src/train.cpp:557-671): NLopt's LD_MMA from x0 = (10, 1) (or pars_io when
+ * not NaN), lb = (1e-3, 1e-4), ub = +inf, xtol_rel = 1e-5.  pars_io <- optimum, *obj <- -(minimum).  NLopt is an
+ * un-vendored dependency of the reference: the optimiser is a restatement of the published CCSA/MMA algorithm, so
+ * parity with the reference is to optimiser tolerance. */
+int flgp_train_regression(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double sigma,
+                          const char* approach, double* pars_io, double* obj, int* nevals);
+/* The optimiser itself behind an nlopt-style callback (value = f(n, x, grad, data)); host only, no GPU needed. */
+typedef double (*flgp_objective_fn)(unsigned n, const double* x, double* grad, void* data);
+int flgp_mma_minimize(int n, flgp_objective_fn f, void* data, const double* lb, const double* ub, double* x,
+                      double* minf, double xtol_rel, int maxeval, int* nevals);
+/* fit_lae_regression_gp_cpp (src/Fit.cpp:20-99) including the training: pars_io = (NaN, NaN) trains, finite values
+ * are used as given; *obj (may be NULL) <- the objective (sign as the reference prints it: larger is better). */
+int flgp_fit_lae_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                            int64_t m_new, int d, int s, int r, int K, double sigma, const char* approach,
+                            const char* subsample, const char* kernel, int gl, int root, int nstart, int iter_max,
+                            const int32_t* init_idx, uint64_t seed, double* pars_io, double* train, double* test,
+                            double* cov, double* obj);
+/* fit_se_regression_gp_cpp (src/Fit.cpp:102-219): one k-means + KNN, then per a2 of the grid
+ * Z = exp(-dist / (a2 * mean dist)) -> graph Laplacian -> spectrum -> training; the a2 with the largest objective
+ * wins.  fixed_pars (may be NULL): evaluate the objective at these (t, noise) instead of training.
+ * out (may be NULL): the winning spectrum handle (caller frees). */
+int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                           int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,
+                           const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,
+                           const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
+                           double* test, double* cov, double* pars_out, double* best_a2, double* best_obj,
+                           flgp_spectrum** out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -426,3 +426,170 @@ def fit_lae_regression_fixed(X, Y, X_new, s, r, K, pars, init_idx, sigma=1e-5, g
     test = predict_regression(V, values, Y, idx0, idx1, K, pars, sigma)
     cov = posterior_covariance_regression(V, values, idx0, idx1, K, pars, sigma)
     return dict(train=train, test=test, cov=cov, values=values, vectors=V)
+
+
+# ------------------------------------------------------------------ hyper-parameter training (regression)
+def regression_objective(V, values, Y, idx, K, x, sigma=1e-5, approach="marginal", prior=(1.0, 10.0, 2.0, 0.1, 1e-3)):
+    """negative_marginal_likelihood_regression_cpp / negative_log_posterior_regression_cpp, noise="same"
+    (src/train.cpp:333-436), on the materialised eigenvectors V.  Returns (objective, grad[2]) with the reference's
+    gradient clipping of grad[1] to +-10.  prior = (p, q, tau, alpha, beta) of PostOFDataReg (src/train.h:144-156)."""
+    import scipy.linalg as sla
+
+    t, noise = float(x[0]), float(x[1])
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+    m, q = Y.shape
+    ev = 1.0 - values[:K]
+    Vm = V[np.asarray(idx), :K]
+    grad = np.zeros(2)
+    if m <= K:
+        C = (Vm * np.exp(-t * ev)) @ Vm.T
+        C[np.diag_indices(m)] += sigma
+        C[np.diag_indices(m)] += noise
+        L = sla.cholesky(C, lower=True)
+        alpha = sla.cho_solve((L, True), Y)
+        C_inv = sla.cho_solve((L, True), np.eye(m))
+        U = alpha @ alpha.T / q - C_inv
+        grad_t = (Vm * (-ev * np.exp(-t * ev))) @ Vm.T
+        grad[0] = -0.5 * (U * grad_t.T).sum()
+        grad[1] = -0.5 * np.trace(U)
+        nmll = 0.5 * (Y * alpha).sum() / q + np.log(np.diag(L) + 1e-9).sum()
+    else:
+        ls = np.exp(-0.5 * t * ev) + 0.0
+        VtV = Vm.T @ Vm
+        Q = (ls[:, None] * VtV) * ls[None, :]
+        Q[np.diag_indices(K)] += noise + sigma
+        L = sla.cholesky(Q, lower=True)
+        ns = noise + sigma
+        alpha = 1.0 / ns * (Y - (Vm * ls) @ sla.cho_solve((L, True), ls[:, None] * (Vm.T @ Y)))
+        Q_inv = sla.cho_solve((L, True), np.eye(K))
+        A = -ev * (np.exp(-t * ev) + 0.0) + 0.0
+        Vta = Vm.T @ alpha
+        grad[0] = -0.5 * (Vta * (A[:, None] * Vta)).sum() / q
+        grad[0] += 0.5 / ns * np.trace(A[:, None] * VtV)
+        grad[0] += -0.5 / ns * ((Q_inv @ (ls[:, None] * VtV)) * ((A[:, None] * VtV) * ls[None, :]).T).sum()
+        grad[1] = -0.5 * (alpha * alpha).sum() / q
+        grad[1] += 0.5 / ns * (m - (Q_inv * ((ls[:, None] * VtV) * ls[None, :]).T).sum())
+        nmll = 0.5 * (Y * alpha).sum() / q + np.log(np.diag(L) + 1e-9).sum() + 0.5 * (m - K) * np.log(ns)
+    if abs(grad[1]) >= 10.0:
+        grad[1] = grad[1] / abs(grad[1]) * 10.0
+    if approach == "posterior":
+        p, qq, tau, al, be = prior
+        nmll += p * np.log(t + 1e-9) + (t / tau) ** (-qq)
+        nmll += (al + 1) * np.log(noise + sigma) + be / (noise + sigma)
+        grad[0] += p / (t + 1e-9) - (qq / tau) * (t / tau) ** (-qq - 1)
+        grad[1] += (al + 1) / (noise + sigma) - be / (noise + sigma) ** 2
+    elif approach != "marginal":
+        raise ValueError("This model selection approach is not supported!")
+    return float(nmll), grad
+
+
+def mma_minimize(f, x0, lb, ub, xtol_rel=1e-5, maxeval=1000):
+    """Svanberg's CCSA with MMA approximations for bound constraints only, as NLopt's NLOPT_LD_MMA runs it
+    (nloptr is an un-vendored dependency of the reference, version unpinned: DESCRIPTION; call site
+    src/train.cpp:621-650 with xtol_rel = 1e-5, x0 = (10, 1), lb = (1e-3, 1e-4), ub = +inf).  Restated from the
+    published algorithm (K. Svanberg, SIAM J. Optim. 12, 2002) in NLopt's arrangement: per-coordinate asymptote
+    widths sigma (1 when a bound is infinite, else half the box), conservative inner iterations that raise rho,
+    0.7 / 1.2 sigma adaptation from the sign pattern of successive steps.  f(x) -> (value, grad).
+    Returns (x, minf, nevals)."""
+    x = np.array(x0, dtype=np.float64)
+    n = x.size
+    lb = np.asarray(lb, dtype=np.float64)
+    ub = np.asarray(ub, dtype=np.float64)
+    sigma = np.where(np.isinf(ub) | np.isinf(lb), 1.0, 0.5 * (ub - lb))
+    rho = 1.0
+    minf, dfdx = f(x)
+    dfdx = np.array(dfdx, dtype=np.float64)
+    nev = 1
+    xcur = x.copy()
+    xprev = x.copy()
+    xprevprev = x.copy()
+    k = 0
+    while True:
+        k += 1
+        if k > 1:
+            xprevprev = xprev.copy()
+        xprev = xcur.copy()
+        while True:
+            gval, wval = minf, 0.0
+            xcur = x.copy()
+            for j in range(n):
+                if sigma[j] == 0:
+                    continue
+                s2 = sigma[j] * sigma[j]
+                v = abs(dfdx[j]) * sigma[j] + 0.5 * rho
+                u = dfdx[j] * s2
+                dx = (u / v) / (-1.0 - np.sqrt(abs(1.0 - (u / (v * sigma[j])) ** 2)))
+                xj = x[j] + dx
+                xj = min(max(xj, lb[j]), ub[j])
+                xj = min(max(xj, x[j] - 0.9 * sigma[j]), x[j] + 0.9 * sigma[j])
+                xcur[j] = xj
+                dx = xj - x[j]
+                dx2 = dx * dx
+                den = 1.0 / (s2 - dx2)
+                gval += (dfdx[j] * s2 * dx + v * dx2) * den
+                wval += 0.5 * dx2 * den
+            fcur, dcur = f(xcur)
+            nev += 1
+            inner_done = gval >= fcur
+            if fcur < minf:
+                minf = fcur
+                x = xcur.copy()
+                dfdx = np.array(dcur, dtype=np.float64)
+            if nev >= maxeval:
+                return x, minf, nev
+            if inner_done:
+                break
+            if fcur > gval:
+                rho = min(10.0 * rho, 1.1 * (rho + (fcur - gval) / wval))
+        if np.abs(xcur - xprev).sum() <= xtol_rel * np.abs(xcur).sum():
+            return x, minf, nev
+        rho = max(0.1 * rho, 1e-5)
+        if k > 1:
+            for j in range(n):
+                dx2 = (xcur[j] - xprev[j]) * (xprev[j] - xprevprev[j])
+                sigma[j] *= 0.7 if dx2 < 0 else (1.2 if dx2 > 0 else 1.0)
+                if not (np.isinf(ub[j]) or np.isinf(lb[j])):
+                    sigma[j] = max(min(sigma[j], 10.0 * (ub[j] - lb[j])), 0.01 * (ub[j] - lb[j]))
+
+
+def train_regression(V, values, Y, idx, K, sigma=1e-5, approach="posterior", x0=(10.0, 1.0), lb=(1e-3, 1e-4),
+                     ub=(np.inf, np.inf)):
+    """train_regression_gp_cpp, noise="same" (src/train.cpp:557-671): returns (pars, obj = -minimum)."""
+    x, minf, _ = mma_minimize(lambda x: regression_objective(V, values, Y, idx, K, x, sigma, approach), x0, lb, ub)
+    return x, -minf
+
+
+def fit_se_regression(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-5, approach="posterior",
+                      gl="cluster-normalized", root=True, iter_max=100, nthreads=1, pars=None):
+    """fit_se_regression_gp_cpp (src/Fit.cpp:102-219): one k-means + KNN, then for every a2 of the grid
+    Z = exp(-dist / (a2 * mean dist)), graph Laplacian, spectrum, empirical-Bayes training; the a2 with the largest
+    objective wins.  pars: fixed (t, noise) instead of training (then the objective is evaluated at pars)."""
+    m = len(X)
+    X_all = np.asfortranarray(np.vstack([X, X_new]))
+    n = len(X_all)
+    if K < 0:
+        K = s
+    U, assign, iters = kmeans_lloyd(X_all, s, init_idx, iter_max, nthreads)
+    ind, dist = knn(X_all, np.asfortranarray(U[:, :-1]), r, want_dist=True, nthreads=nthreads)
+    Zj, Dx = knn_csr(ind, dist)
+    dmean = Dx.sum() / (n * r)
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n, dtype=np.int32)
+    best = None
+    for a2 in a2s:
+        Zx = se_weights(Dx, a2 * dmean)
+        nc = U[:, -1].copy() if gl == "cluster-normalized" else None
+        Zx = graph_laplacian(Zj, Zx, s, gl, nc)
+        values, V = spectrum_from_Z(Zj, Zx, s, K, root, nthreads=nthreads)
+        if pars is None:
+            x, obj = train_regression(V, values, Y, idx0, K, sigma, approach)
+        else:
+            x = np.asarray(pars, dtype=np.float64)
+            obj = -regression_objective(V, values, Y, idx0, K, x, sigma, approach)[0]
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, pars=x, a2=a2, values=values, V=V)
+    V, values, x = best["V"], best["values"], best["pars"]
+    best["train"] = predict_regression(V, values, Y, idx0, idx0, K, x, sigma)
+    best["test"] = predict_regression(V, values, Y, idx0, idx1, K, x, sigma)
+    best["cov"] = posterior_covariance_regression(V, values, idx0, idx1, K, x, sigma)
+    return best

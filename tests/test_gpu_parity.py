@@ -499,3 +499,84 @@ def test_c3_shape_pipeline_large_d(flgp, oracle):
     Zj, Zx = _csr_parts(ep.Z())
     assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
     np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------- training (§8f rows 2, 3)
+@pytest.mark.parametrize("m,K", [(300, 40), (30, 40)])
+@pytest.mark.parametrize("approach", ["marginal", "posterior"])
+def test_regression_objective_matches_oracle(flgp, oracle, m, K, approach):
+    """The training objective and its gradient on a spectrum handle (K-sized statistics gathered on the device)
+    against the oracle's literal restatement on the materialised eigenvectors; both branches of the reference."""
+    X, Y = spiral(2500, 5)
+    s, r = 120, 3
+    init = _init(len(X), s, 2)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=20)
+    V, values = ep.vectors, ep.values
+    idx = np.arange(m, dtype=np.int32)
+    for pars in [(10.0, 1.0), (2.0, 0.05), (40.0, 3.0)]:
+        f, g = flgp.regression_objective(ep, Y[:m], m, K, pars, 1e-5, approach)
+        fo, go = oracle.regression_objective(V, values, Y[:m], idx, K, pars, 1e-5, approach)
+        np.testing.assert_allclose(f, fo, rtol=1e-8, atol=1e-8)
+        np.testing.assert_allclose(g, go, rtol=1e-6, atol=1e-6 * max(1.0, np.abs(go).max()))
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.regression_objective(ep, Y[:m], m, K, (10.0, 1.0), 1e-5, "bayes")
+
+
+def test_train_regression_matches_oracle_optimiser(flgp, oracle):
+    """train_regression_gp_cpp: the library's MMA run on the device-side statistics lands where the oracle's twin
+    lands on the materialised eigenvectors (to optimiser tolerance), improving on the start x0 = (10, 1)."""
+    X, Y = spiral(3000, 8)
+    m, s, r, K = 200, 150, 3, 50
+    init = _init(len(X), s, 3)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=20)
+    idx = np.arange(m, dtype=np.int32)
+    for approach in ("posterior", "marginal"):
+        x, obj, nev = flgp.train_regression_gp(ep, Y[:m], m, K, 1e-5, approach)
+        xo, objo = oracle.train_regression(ep.vectors, ep.values, Y[:m], idx, K, 1e-5, approach)
+        assert x[0] >= 1e-3 and x[1] >= 1e-4 and nev >= 2
+        f0, _ = flgp.regression_objective(ep, Y[:m], m, K, (10.0, 1.0), 1e-5, approach)
+        assert -obj <= f0
+        np.testing.assert_allclose(obj, objo, rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(x, xo, rtol=1e-3)
+
+
+def test_fit_lae_regression_trains_when_pars_missing(flgp, oracle):
+    X, Y = swiss(3000, 4)
+    m, s, r, K = 250, 100, 3, 30
+    init = _init(len(X), s, 9)
+    res = flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, init_idx=init, iter_max=15)
+    ref = oracle.fit_lae_regression_fixed(X[:m], Y[:m], X[m:], s, r, K, res["pars"], init, iter_max=15, nthreads=NT)
+    np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-7, atol=1e-9)
+    xo, objo = oracle.train_regression(ref["vectors"], ref["values"], Y[:m], np.arange(m, dtype=np.int32), K)
+    np.testing.assert_allclose(res["pars"], xo, rtol=1e-3)
+    np.testing.assert_allclose(res["obj"], objo, rtol=1e-5, atol=1e-5)
+
+
+def test_fit_se_regression_config2_grid(flgp, oracle):
+    """BASELINE config 2 (README GPR spiral: n=4000, d=2, m=200, s=500, r=3, K=100, fit_se_regression_gp_rcpp):
+    one k-means + KNN, ten bandwidths.  With fixed (t, noise) the whole path is deterministic: same winning a2,
+    predictions and variances to 1e-8; with training, to optimiser tolerance."""
+    X, Y = spiral(4000, 2)
+    m, s, r, K = 200, 500, 3, 100
+    init = _init(len(X), s, 1)
+    a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    pars = (8.0, 0.5)
+    res = flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, pars=pars, init_idx=init)
+    ref = oracle.fit_se_regression(X[:m], Y[:m], X[m:], s, r, K, init, a2s, pars=pars, nthreads=NT)
+    assert res["a2"] == ref["a2"]
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-8)
+    np.testing.assert_allclose(res["eigenpair"].values, ref["values"], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res["Y_pred"]["train"], ref["train"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-7, atol=1e-9)
+    # trained
+    res = flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, init_idx=init, output_cov=True)
+    ref = oracle.fit_se_regression(X[:m], Y[:m], X[m:], s, r, K, init, a2s, nthreads=NT)
+    assert res["a2"] == ref["a2"]
+    np.testing.assert_allclose(res["pars"], ref["pars"], rtol=1e-3)
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-5)
+    np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-3, atol=1e-3)
+    assert res["C"].shape == (4000, m)
+    rmse = np.sqrt(np.mean((res["Y_pred"]["test"] - Y[m:]) ** 2))
+    assert rmse < 2.0   # labels carry N(0,1) noise on a signal of amplitude ~10
