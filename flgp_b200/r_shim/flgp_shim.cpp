@@ -20,6 +20,9 @@
 //   HK_from_spectrum_cpp          src/Spectrum.cpp:83-94       -> flgp_hk_from_spectrum (handle) or Eigen as before
 //   lae_eigenmap                  src/Spectrum.cpp:17-25       -> flgp_lae_eigenmap
 //   heat_kernel_covariance_cpp    src/Spectrum.cpp:28-43       -> flgp_heat_kernel_covariance
+//   fit_lae_regression_gp_cpp     src/Fit.cpp:20-99            -> flgp_fit_lae_regression (spectrum + MMA training + GPR tail)
+//   fit_se_regression_gp_cpp      src/Fit.cpp:102-219          -> flgp_fit_se_regression  (one k-means/KNN, bandwidth grid)
+//   train_regression_gp_cpp       src/train.cpp:557-671        -> flgp_train_regression   (noise = "same")
 // [[Rcpp::depends(RcppEigen)]]
 #include <RcppEigen.h>
 
@@ -185,4 +188,76 @@ Eigen::MatrixXd heat_kernel_covariance_cpp(const Eigen::MatrixXd& X, const Eigen
                                  ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]),
                                  nstart, epsilon, 100, init.data(), 0, H.data()));
   return H;
+}
+
+// ---- regression fit drivers (noise = "same"; noise = "different" keeps the reference's nlopt path) -------------
+namespace {
+Rcpp::List pack_fit(const Eigen::VectorXd& train, const Eigen::VectorXd& test, const Eigen::VectorXd& cov,
+                    const std::vector<double>& pars) {
+  Rcpp::List Y_pred = Rcpp::List::create(Rcpp::Named("train") = train, Rcpp::Named("test") = test);
+  Rcpp::List post = Rcpp::List::create(Rcpp::Named("mean") = test, Rcpp::Named("cov") = cov);
+  return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = pars);
+}
+}  // namespace
+
+Rcpp::List fit_lae_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                     int s, int r, int K, double sigma, std::string approach, std::string noise,
+                                     Rcpp::List models, bool output_cov, int nstart) {
+  if (noise != "same") Rcpp::stop("noise=\"different\" is not offloaded; call the reference path");
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows();
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]), ker = Rcpp::as<std::string>(models["kernel"]);
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  std::vector<double> pars = {NA_REAL, NA_REAL};  // NaN: train
+  Eigen::VectorXd train(m), test(m_new), cov(m_new);
+  double obj = 0.0;
+  ok(flgp_fit_lae_regression(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, sigma,
+                             approach.c_str(), sub.c_str(), ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
+                             Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, pars.data(), train.data(),
+                             test.data(), cov.data(), &obj));
+  Rcpp::List res = pack_fit(train, test, cov, pars);
+  if (output_cov) {
+    Eigen::MatrixXd C(m + m_new, m);
+    ok(flgp_heat_kernel_covariance(ctx(), X.data(), m, X_new.data(), m_new, (int)X.cols(), s, r, pars[0], K, sub.c_str(),
+                                   ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
+                                   Rcpp::as<bool>(models["root"]), nstart, 0.1, 100, init.data(), 0, C.data()));
+    res["C"] = C;
+  }
+  return res;
+}
+
+Rcpp::List fit_se_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                    int s, int r, int K, double sigma, std::vector<double> a2s, std::string approach,
+                                    std::string noise, Rcpp::List models, bool output_cov, int nstart) {
+  if (noise != "same") Rcpp::stop("noise=\"different\" is not offloaded; call the reference path");
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows(), n = m + m_new;
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]);
+  std::vector<int32_t> init = r_init(n, s);
+  std::vector<double> pars(2);
+  Eigen::VectorXd train(m), test(m_new), cov(m_new);
+  double a2 = 0.0, obj = 0.0;
+  flgp_spectrum* h = nullptr;
+  ok(flgp_fit_se_regression(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, sigma, a2s.data(),
+                            (int)a2s.size(), approach.c_str(), sub.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
+                            Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, nullptr, train.data(),
+                            test.data(), cov.data(), pars.data(), &a2, &obj, output_cov ? &h : nullptr));
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", t = " << pars[0]
+              << ", sigma = " << std::sqrt(pars[1]) << ", the objective function is " << obj << "\n";
+  Rcpp::List res = pack_fit(train, test, cov, pars);
+  if (output_cov) {
+    std::vector<int32_t> i0(n), i1(m);
+    for (int i = 0; i < n; ++i) i0[i] = i;
+    for (int i = 0; i < m; ++i) i1[i] = i;
+    Eigen::MatrixXd C(n, m);
+    int rc = flgp_hk_from_spectrum(h, K < 0 ? s : K, pars[0], i0.data(), n, i1.data(), m, C.data());
+    flgp_spectrum_free(h);
+    ok(rc);
+    res["C"] = C;
+  }
+  return res;
 }

@@ -60,9 +60,38 @@ def main():
         ok &= e_y < 1e-9 and e_c < 1e-9
         print("multi_gpu_check world=%d: iters=%d U/Z bit-exact=%s, dy=%.2e dcov=%.2e -> %s" %
               (world, ep1.kmeans_iters, np.array_equal(Zx, Z1.data), e_y, e_c, "OK" if ok else "FAIL"))
+    ok &= large_d_case(rank, local, world, ctx)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
+
+
+def large_d_case(rank, local, world, ctx):
+    """d = 16 (config 5's dimension): the tensor-core distance path with persistent integer accumulators, sharded."""
+    n, m, s, r, K, d = 60_001, 300, 128, 5, 30, 16
+    rng = np.random.default_rng(123)
+    a, b = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    T4 = np.c_[np.cos(a), np.sin(a), np.cos(b), np.sin(b)]
+    Q, _ = np.linalg.qr(rng.standard_normal((d, 4)))
+    X = np.asfortranarray(T4 @ Q.T + 0.01 * rng.standard_normal((n, d)))
+    lo, hi = shard_bounds(n, world, rank)
+    init = F.default_init(n, s, 6)
+    ep = F.heat_kernel_spectrum_sharded(np.asfortranarray(X[lo:hi]), n, lo, s, r, K, init_idx=init, iter_max=12, ctx=ctx)
+    Z = ep.Z()
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(U=ep.anchors(), Zj=Z.indices, Zx=Z.data, vals=ep.values, iters=ep.kmeans_iters))
+    ok = True
+    if rank == 0:
+        ctx1 = F.Context(local)
+        ep1 = F.heat_kernel_spectrum_sharded(X, n, 0, s, r, K, init_idx=init, iter_max=12, ctx=ctx1)
+        Z1 = ep1.Z()
+        for g in gathered:
+            ok &= g["iters"] == ep1.kmeans_iters and np.array_equal(g["U"], ep1.anchors())
+            ok &= np.allclose(g["vals"], ep1.values, rtol=1e-10, atol=0)
+        ok &= np.array_equal(np.concatenate([g["Zj"] for g in gathered]), Z1.indices)
+        ok &= np.array_equal(np.concatenate([g["Zx"] for g in gathered]), Z1.data)
+        print("multi_gpu_check world=%d large-d (d=16): U/Z bit-exact -> %s" % (world, "OK" if ok else "FAIL"))
+    return ok
 
 
 if __name__ == "__main__":
