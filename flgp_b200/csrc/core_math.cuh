@@ -269,44 +269,19 @@ struct LaeStats {
   int iters, backtracks;
 };
 
-template <int RT, int DT, class XAcc, class UAcc>
-FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out) {
+// The iteration proper, given UUt (r x r, row stride RA), xUt (r) and the objective w -> |x - w U|^2 / 2 as a callable
+// (sequential per thread in lae_solve; warp-cooperative in lae.cu's large-d kernel: same values, same order).
+template <int RT, class Obj>
+FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj&& objective, double* z_out) {
   constexpr int RA = RT ? RT : LAE_RMAX;
   const int r = RT ? RT : r_in;
-  const int d = DT ? DT : d_in;
-  double UUt[RA * RA], xUt[RA], zp[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
+  double zp[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
   double* zc = z_out;  // the caller's array IS the current iterate (no copy at exit; see DESIGN.md §7 note on nvcc)
 #pragma unroll
   for (int a = 0; a < r; ++a) {
-#pragma unroll
-    for (int b = 0; b < r; ++b) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = 0; k < d; ++k) s = s + U(a, k) * U(b, k);
-      UUt[a * RA + b] = s;
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < r; ++a) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < d; ++k) s = s + x(k) * U(a, k);
-    xUt[a] = s;
     zp[a] = 1.0 / (double)r;
     zc[a] = 1.0 / (double)r;
   }
-  auto objective = [&](const double* w) {
-    double sq = 0.0;
-#pragma unroll
-    for (int k = 0; k < d; ++k) {
-      double wu = 0.0;
-#pragma unroll
-      for (int a = 0; a < r; ++a) wu = wu + w[a] * U(a, k);
-      double df = x(k) - wu;
-      sq = sq + df * df;
-    }
-    return sq / 2.0;
-  };
   double delta_prev = 0.0, delta_curr = 1.0, beta_curr = 1.0;
   int t = 0, nbt = 0;
   for (t = 0; t < LAE_T; ++t) {
@@ -366,6 +341,44 @@ FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, dou
   st.iters = t;
   st.backtracks = nbt;
   return st;
+}
+
+template <int RT, int DT, class XAcc, class UAcc>
+FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out) {
+  constexpr int RA = RT ? RT : LAE_RMAX;
+  const int r = RT ? RT : r_in;
+  const int d = DT ? DT : d_in;
+  double UUt[RA * RA], xUt[RA];
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+#pragma unroll
+    for (int b = 0; b < r; ++b) {
+      double s = 0.0;
+#pragma unroll
+      for (int k = 0; k < d; ++k) s = s + U(a, k) * U(b, k);
+      UUt[a * RA + b] = s;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < r; ++a) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < d; ++k) s = s + x(k) * U(a, k);
+    xUt[a] = s;
+  }
+  auto objective = [&](const double* w) {
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < d; ++k) {
+      double wu = 0.0;
+#pragma unroll
+      for (int a = 0; a < r; ++a) wu = wu + w[a] * U(a, k);
+      double df = x(k) - wu;
+      sq = sq + df * df;
+    }
+    return sq / 2.0;
+  };
+  return lae_iterate<RT>(r, UUt, xUt, objective, z_out);
 }
 
 // ---------------------------------------------------------------------------------------------

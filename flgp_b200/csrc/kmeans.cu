@@ -54,15 +54,28 @@ __global__ void kmeans_prep_kernel(const double* __restrict__ C, int s, int d, i
   for (int k = d + 1; k < str; ++k) rec[(size_t)j * str + k] = 0.0;
 }
 
-// split records into the tiled kernel's operands: C2 (s x d col-major) and cn (s)
-__global__ void kmeans_prep_tiled_kernel(const double* __restrict__ C, int s, int d, double M, double* C2, double* cn) {
+// split records into the tiled kernel's operands: C2 = -2 C (s x d col-major, element-wise) and
+// cn[j] = (sum_k fma(c,c,.)) + M (one thread per centre, ascending k as the oracle; loads batched 8 deep so that the
+// d-long chain waits on arithmetic, not on memory)
+__global__ void kmeans_prep_c2_kernel(const double* __restrict__ C, size_t len, double* __restrict__ C2) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e < len) C2[e] = -2.0 * C[e];
+}
+__global__ void kmeans_prep_cn_kernel(const double* __restrict__ C, int s, int d, double M, double* __restrict__ cn) {
   int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= s) return;
   double a = 0.0;
-  for (int k = 0; k < d; ++k) {
-    double c = C[j + (size_t)s * k];
+  int k = 0;
+  for (; k + 8 <= d; k += 8) {
+    double c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = C[j + (size_t)s * (k + q)];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a = fma(c[q], c[q], a);
+  }
+  for (; k < d; ++k) {
+    const double c = C[j + (size_t)s * k];
     a = fma(c, c, a);
-    C2[j + (size_t)s * k] = -2.0 * c;
   }
   cn[j] = __dadd_rn(a, M);
 }
@@ -619,6 +632,22 @@ __global__ void kmeans_update_kernel(const long long* __restrict__ acc, int s, i
   }
 }
 
+// the same for large d, one thread per (centre, coordinate); no displacement bookkeeping (brute-force passes only)
+__global__ void kmeans_update_wide_kernel(const long long* __restrict__ acc, int s, int d, Fx fx, double* C,
+                                          double* sizes, int it, long long* kstate) {
+  const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (e == 0) {
+    const long long ch = acc[(size_t)2 * s * d + s];
+    if (ch == 0 && kstate[0] == 0) kstate[0] = it;
+    kstate[1] += ch;
+  }
+  if (e >= (size_t)s * d) return;
+  const int j = (int)(e % s);
+  const long long cnt = acc[(size_t)2 * s * d + j];
+  if (e < (size_t)s) sizes[j] = (double)cnt;
+  if (cnt != 0) C[e] = fx_decode(fx, acc[e], acc[(size_t)s * d + e]) / (double)cnt;  // an empty cluster keeps its centre
+}
+
 // rows of X that this rank owns -> bit patterns in the (zeroed) centre buffer
 __global__ void kmeans_init_kernel(const double* __restrict__ X, int64_t n_local, int64_t ldx, int d, int s,
                                    int64_t row_offset, const int32_t* __restrict__ init_idx, long long* Cbits) {
@@ -1166,7 +1195,10 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     if (brute && !(dmma && it > 1)) acc.zero(c->stream);
     else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
     if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
-    else FLGP_LAUNCH(c, kmeans_prep_tiled_kernel, ceil_div(s, 128), 128, 0, C, s, d, Moff, C2.p, cn.p);
+    else {
+      FLGP_LAUNCH(c, kmeans_prep_c2_kernel, ceil_div((int64_t)s * d, 256), 256, 0, C, (size_t)s * d, C2.p);
+      FLGP_LAUNCH(c, kmeans_prep_cn_kernel, ceil_div(s, 64), 64, 0, C, s, d, Moff, cn.p);
+    }
     if (!brute && (!have_sorted || moved_since_sort * 8 > n_total)) resort();
     // when timing is on, the assign+accumulate work gets its own CUDA-event pair per pass
     StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_pass", 2.0 * s * d * (double)n_local,
@@ -1271,8 +1303,12 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
     if (pruned) maxmove.zero(c->stream);
-    FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
-                pruned ? maxmove.p : nullptr, it, kstate.p);
+    if (small)
+      FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
+                  pruned ? maxmove.p : nullptr, it, kstate.p);
+    else
+      FLGP_LAUNCH(c, kmeans_update_wide_kernel, ceil_div((int64_t)s * d, 256), 256, 0, red, s, d, fx, C, sizes, it,
+                  kstate.p);
     // one host round trip per KM_CHECK passes (and after the first, which decides about the sorted layout)
     if (it == 1 || it % KM_CHECK == 0 || it == iter_max) {
       FLGP_CUDA(cudaMemcpyAsync(c->pinned, kstate.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));

@@ -10,6 +10,7 @@
 // Roofline: HBM (8d + 4r bytes read, 12r written per point); the solver itself is latency /
 // divergence bound (data-dependent 1..100 outer iterations) and is reported with its iteration
 // count, as SURVEY.md §8d asks.
+#include <algorithm>
 #include <type_traits>
 
 #include "kernels.cuh"
@@ -152,6 +153,115 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
   add_stats(stats, it, bt);
 }
 
+// ---- large d: one WARP per point ------------------------------------------------------------------------------
+// With d in the hundreds the per-thread solver is a chain of d-long dependent sums per objective evaluation and the
+// kernel's time is that latency (58 ms at n = 70000, d = 784).  Here a warp owns the point: the d products of a sum
+// are formed by the 32 lanes in parallel (coalesced reads of the anchors' row-major rows) into shared memory, then
+// every lane adds them up in the oracle's order (k = 0, 1, 2, ...: an LDS broadcast + DADD per term, the same value
+// in all lanes, so control flow stays warp-uniform).  The r x r and r chains of the set-up run one chain per lane.
+// Dynamic shared memory per warp: x (d) + products (d) + UUt / xUt (LAE_RMAX^2 + LAE_RMAX).
+constexpr int LW_EXTRA = LAE_RMAX * LAE_RMAX + LAE_RMAX;
+
+__global__ void __launch_bounds__(256)
+lae_warp_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ Ur, int64_t ldu,
+                int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj, double* __restrict__ Zx,
+                double* __restrict__ Wd, long long* stats, const int32_t* __restrict__ perm) {
+  extern __shared__ double lw_sm[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  double* xs = lw_sm + (size_t)wid * (2 * (size_t)d + LW_EXTRA);
+  double* ps = xs + d;
+  double* uu = ps + d;          // UUt, row stride LAE_RMAX
+  double* xu = uu + LAE_RMAX * LAE_RMAX;
+  int it_tot = 0, bt_tot = 0;
+  for (int64_t i = (int64_t)blockIdx.x * nw + wid; i < n; i += (int64_t)gridDim.x * nw) {
+    int col[LAE_RMAX];
+    const double* row[LAE_RMAX];
+    for (int a = 0; a < r; ++a) {
+      col[a] = ind[i + n * a];
+      row[a] = Ur + (int64_t)col[a] * ldu;
+    }
+    __syncwarp();
+    for (int k = lane; k < d; k += 32) xs[k] = X[i + ldx * k];
+    __syncwarp();
+    // set-up chains: (a, b) with a <= b (the product commutes: UUt is exactly symmetric), then x.U_a
+    const int npair = r * (r + 1) / 2, nchain = npair + r;
+    for (int c0 = 0; c0 < nchain; c0 += 32) {
+      const int ch = c0 + lane;
+      if (ch < nchain) {
+        int a = 0, b = 0;
+        const double* pa;
+        const double* pb;
+        if (ch < npair) {
+          int q = ch;
+          while (q >= r - a) {
+            q -= r - a;
+            ++a;
+          }
+          b = a + q;
+          pa = row[a];
+          pb = row[b];
+        } else {
+          a = ch - npair;
+          pa = xs;
+          pb = row[a];
+        }
+        double sacc = 0.0;
+        int k = 0;
+        for (; k + 4 <= d; k += 4) {
+          const double p0 = pa[k] * pb[k], p1 = pa[k + 1] * pb[k + 1], p2 = pa[k + 2] * pb[k + 2],
+                       p3 = pa[k + 3] * pb[k + 3];
+          sacc = sacc + p0;
+          sacc = sacc + p1;
+          sacc = sacc + p2;
+          sacc = sacc + p3;
+        }
+        for (; k < d; ++k) sacc = sacc + pa[k] * pb[k];
+        if (ch < npair) {
+          uu[a * LAE_RMAX + b] = sacc;
+          uu[b * LAE_RMAX + a] = sacc;
+        } else {
+          xu[a] = sacc;
+        }
+      }
+    }
+    __syncwarp();
+    double UUt[LAE_RMAX * LAE_RMAX], xUt[LAE_RMAX];
+    for (int a = 0; a < r; ++a) {
+      xUt[a] = xu[a];
+      for (int b = 0; b < r; ++b) UUt[a * LAE_RMAX + b] = uu[a * LAE_RMAX + b];
+    }
+    auto objective = [&](const double* w) {
+      __syncwarp();
+      for (int k = lane; k < d; k += 32) {
+        double wu = 0.0;
+        for (int a = 0; a < r; ++a) wu = wu + w[a] * row[a][k];
+        const double df = xs[k] - wu;
+        ps[k] = df * df;
+      }
+      __syncwarp();
+      double sq = 0.0;
+      int k = 0;
+      for (; k + 4 <= d; k += 4) {
+        const double p0 = ps[k], p1 = ps[k + 1], p2 = ps[k + 2], p3 = ps[k + 3];
+        sq = sq + p0;
+        sq = sq + p1;
+        sq = sq + p2;
+        sq = sq + p3;
+      }
+      for (; k < d; ++k) sq = sq + ps[k];
+      return sq / 2.0;
+    };
+    double z[LAE_RMAX];
+    const LaeStats ls = lae_iterate<0>(r, UUt, xUt, objective, z);
+    if (lane == 0) {
+      it_tot += ls.iters;
+      bt_tot += ls.backtracks;
+      write_row<LAE_RMAX>(r, col, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
+    }
+  }
+  add_stats(stats, it_tot, bt_tot);
+}
+
 __global__ void knn_to_csr_kernel(int64_t n, int r, const int32_t* __restrict__ ind, const double* __restrict__ dist,
                                   int32_t* __restrict__ Zj, double* __restrict__ Zx, const int32_t* __restrict__ perm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,7 +313,23 @@ void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
   LAE_CASE(2, 2) LAE_CASE(3, 2) LAE_CASE(4, 2) LAE_CASE(5, 2)
   LAE_CASE(2, 3) LAE_CASE(3, 3) LAE_CASE(4, 3) LAE_CASE(5, 3)
 #undef LAE_CASE
-  if (d >= 8) {  // long rows: read the anchors from a row-major copy (sector reuse through L1)
+  if (d >= 32) {  // long rows: one warp per point over a row-major copy of the anchors
+    const size_t per_warp = (2 * (size_t)d + LW_EXTRA) * sizeof(double);
+    int warps = (int)std::min<size_t>(8, (100 * 1024) / per_warp);
+    if (warps >= 1) {
+      DevBuf<double> Ur((size_t)s * d);
+      to_rowmajor_run(c, U, s, ldu, d, d, Ur.p);
+      const size_t smem = per_warp * warps;
+      if (smem > 40 * 1024)
+        FLGP_CUDA(cudaFuncSetAttribute(lae_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      const int wgrid = (int)std::min<int64_t>(ceil_div(n, warps), (int64_t)c->sm_count * 16);
+      FLGP_LAUNCH(c, lae_warp_kernel, wgrid, warps * 32, smem, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats,
+                  perm);
+      sync(c);  // Ur is released on return
+      return;
+    }
+  }
+  if (d >= 8) {  // medium rows: read the anchors from a row-major copy (sector reuse through L1)
     DevBuf<double> Ur((size_t)s * d);
     to_rowmajor_run(c, U, s, ldu, d, d, Ur.p);
     FLGP_LAUNCH(c, lae_generic_kernel<true>, grid, 128, 0, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats,

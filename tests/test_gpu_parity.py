@@ -178,7 +178,8 @@ def test_v_to_z_and_single_point(flgp, oracle):
 
 
 @pytest.mark.parametrize("n,d,s,r", [(4000, 2, 500, 3), (6000, 3, 300, 3), (3000, 3, 100, 5), (2000, 2, 80, 2),
-                                      (2000, 3, 80, 4), (1500, 6, 60, 3), (1200, 3, 50, 7), (400, 784, 50, 5)])
+                                      (2000, 3, 80, 4), (1500, 6, 60, 3), (1200, 3, 50, 7), (400, 784, 50, 5),
+                                      (900, 33, 40, 8), (700, 100, 30, 1), (500, 257, 64, 16), (800, 16, 64, 5)])
 def test_lae_bitexact(flgp, oracle, n, d, s, r):
     rng = np.random.default_rng(n + r)
     if d == 2:
@@ -385,6 +386,8 @@ def _sym(rng, s, kind):
         lam = 1.0 / (1.0 + 0.05 * np.arange(s)) ** 2
     elif kind == "clustered":    # exact multiplicities and tight clusters at the top
         lam = np.sort(np.r_[np.ones(5), np.full(4, 0.9), 0.9 - 1e-9 * np.arange(3), rng.uniform(0, 0.8, s - 12)])[::-1]
+    elif kind == "bigcluster":   # 50-fold eigenvalue 1 and a 30-member cluster 1e-10 apart (CGS2 re-orthogonalisation)
+        lam = np.sort(np.r_[np.ones(50), 0.7 - 1e-10 * np.arange(30), rng.uniform(0, 0.6, s - 80)])[::-1]
     elif kind == "indefinite":
         lam = np.sort(rng.uniform(-1, 1, s))[::-1]
     else:                         # graded over 12 orders of magnitude
@@ -394,7 +397,8 @@ def _sym(rng, s, kind):
 
 
 @pytest.mark.parametrize("s,K,kind", [(300, 40, "decay"), (257, 257, "decay"), (500, 60, "clustered"), (64, 5, "graded"),
-                                       (400, 30, "indefinite"), (2, 1, "decay"), (1, 1, "decay"), (1000, 120, "decay")])
+                                       (400, 30, "indefinite"), (2, 1, "decay"), (1, 1, "decay"), (1000, 120, "decay"),
+                                       (600, 100, "bigcluster"), (300, 65, "bigcluster")])
 def test_eigs_sym_matches_lapack(flgp, s, K, kind):
     """The eigensolver behind spectrum_from_Z / the eigs_sym seam against LAPACK on dense symmetric matrices."""
     rng = np.random.default_rng(s + K)
