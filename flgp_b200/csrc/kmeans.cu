@@ -1210,7 +1210,20 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
                   maxmove.p, Rcur);
       FLGP_CUDA(cudaMemsetAsync(nstrag.p, 0, sizeof(int), c->stream));
       if (n_local > 0) {
-        const int sgrid = c->sm_count * 8;
+        // a grid-stride kernel over a device-side item count: exactly one resident wave (a partial second wave
+        // would run with most SMs idle; ncu: 1.6 waves at the former sm_count * 8)
+        static int pruned_per_sm[5] = {0, 0, 0, 0, 0};
+        if (!pruned_per_sm[d]) {
+          int nb = 0;
+          switch (d) {
+            case 1: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<1>, 256, 0)); break;
+            case 2: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<2>, 256, 0)); break;
+            case 3: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<3>, 256, 0)); break;
+            default: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<4>, 256, 0)); break;
+          }
+          pruned_per_sm[d] = std::max(nb, 1);
+        }
+        const int sgrid = c->sm_count * pruned_per_sm[d];
         FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, cl.p, eta,
                     UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr);
 #define FLGP_PRUNED(D_)                                                                                          \
