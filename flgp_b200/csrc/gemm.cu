@@ -3,6 +3,8 @@
 // the K x K blocks of the GPR tail and the folds W M W^T.  One strided, shared-memory tiled FMA
 // kernel (64 x 64 tile, 4 x 4 per thread, ascending-k accumulation => deterministic).
 // The diagonal scaling is fused into the A-operand load, as the reference scales V0's columns first.
+#include <algorithm>
+
 #include "kernels.cuh"
 #include "tma_dmma.cuh"
 
@@ -92,7 +94,11 @@ constexpr int GT = 64, GK = 16, GPAD = 66;
 __global__ void __launch_bounds__(256)
 gemm_strided_kernel(const double* __restrict__ A, int64_t ars, int64_t acs, const double* __restrict__ B,
                     int64_t brs, int64_t bcs, const double* __restrict__ sc, int64_t M, int64_t N, int K,
-                    double* __restrict__ C, int64_t crs, int64_t ccs) {
+                    double* __restrict__ C, int64_t crs, int64_t ccs, int kchunk, int64_t csplit) {
+  // blockIdx.z = K slab (split-K for short-and-wide products: partial results csplit apart, summed in slab order by
+  // splitk_reduce_kernel, so the result does not depend on the schedule)
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  C += (int64_t)blockIdx.z * csplit;
   __shared__ __align__(16) double As[GK][GPAD];
   __shared__ __align__(16) double Bs[GK][GPAD];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -103,7 +109,7 @@ gemm_strided_kernel(const double* __restrict__ A, int64_t ars, int64_t acs, cons
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
   const bool a_kfast = (acs == 1), b_kfast = (brs == 1);
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
     __syncthreads();
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -112,7 +118,7 @@ gemm_strided_kernel(const double* __restrict__ A, int64_t ars, int64_t acs, cons
       int k = k0 + kk;
       int64_t i = i0 + m;
       double v = 0.0;
-      if (k < K && i < M) {
+      if (k < kend && i < M) {
         v = A[i * ars + k * acs];
         if (sc) v = __dmul_rn(v, sc[k]);
       }
@@ -121,7 +127,7 @@ gemm_strided_kernel(const double* __restrict__ A, int64_t ars, int64_t acs, cons
       m = b_kfast ? (e >> 4) : (e & 63);
       k = k0 + kk;
       int64_t j = j0 + m;
-      Bs[kk][m] = (k < K && j < N) ? B[k * brs + j * bcs] : 0.0;
+      Bs[kk][m] = (k < kend && j < N) ? B[k * brs + j * bcs] : 0.0;
     }
     __syncthreads();
 #pragma unroll
@@ -146,11 +152,40 @@ gemm_strided_kernel(const double* __restrict__ A, int64_t ars, int64_t acs, cons
     }
 }
 
+__global__ void splitk_reduce_kernel(const double* __restrict__ part, int64_t len, int nsplit, double* __restrict__ out) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  double a = 0.0;
+  for (int z = 0; z < nsplit; ++z) a += part[(int64_t)z * len + e];
+  out[e] = a;
+}
+
 void gemm_strided(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs, int64_t bcs,
                   const double* sc, int64_t M, int64_t N, int K, double* C, int64_t crs, int64_t ccs) {
   if (M <= 0 || N <= 0) return;
   dim3 grid(ceil_div(N, GT), ceil_div(M, GT));
-  FLGP_LAUNCH(c, gemm_strided_kernel, grid, 256, 0, A, ars, acs, B, brs, bcs, sc, M, N, K, C, crs, ccs);
+  FLGP_LAUNCH(c, gemm_strided_kernel, grid, 256, 0, A, ars, acs, B, brs, bcs, sc, M, N, K, C, crs, ccs, K > 0 ? K : 1,
+              (int64_t)0);
+}
+// the same with the contraction split over up to 64 slabs when the output is too small to fill the GPU
+// (dense column-major M x N output, ld M)
+void gemm_strided_splitk(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs, int64_t bcs,
+                         int64_t M, int64_t N, int K, double* C) {
+  if (M <= 0 || N <= 0) return;
+  const int tiles = ceil_div(N, GT) * ceil_div(M, GT);
+  int nsplit = std::min(64, std::max(1, std::min(K / 128, (2 * c->sm_count) / tiles)));
+  if (nsplit <= 1) {
+    gemm_strided(c, A, ars, acs, B, brs, bcs, nullptr, M, N, K, C, 1, M);
+    return;
+  }
+  const int kchunk = ceil_div(ceil_div(K, nsplit), GK) * GK;
+  nsplit = ceil_div(K, kchunk);
+  DevBuf<double> part((size_t)nsplit * M * N);
+  dim3 grid(ceil_div(N, GT), ceil_div(M, GT), nsplit);
+  FLGP_LAUNCH(c, gemm_strided_kernel, grid, 256, 0, A, ars, acs, B, brs, bcs, (const double*)nullptr, M, N, K, part.p,
+              (int64_t)1, M, kchunk, M * N);
+  FLGP_LAUNCH(c, splitk_reduce_kernel, ceil_div(M * N, 256), 256, 0, part.p, M * N, nsplit, C);
+  sync(c);  // part is released on return
 }
 
 }  // namespace
@@ -188,8 +223,8 @@ void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double
 void gram_small_run(Ctx* c, const double* V, const double* y, int64_t n_rows, int K, double* G, double* g) {
   // G = V^T V : A(i,k) = V[k*K + i], B(k,j) = V[k*K + j]
   if (n_rows > INT32_MAX) fail(2, "too many training rows");
-  gemm_strided(c, V, 1, K, V, K, 1, nullptr, K, K, (int)n_rows, G, 1, K);
-  if (y && g) gemm_strided(c, V, 1, K, y, 1, 0, nullptr, K, 1, (int)n_rows, g, 1, 0);
+  gemm_strided_splitk(c, V, 1, K, V, K, 1, K, K, (int)n_rows, G);
+  if (y && g) gemm_strided_splitk(c, V, 1, K, y, 1, 0, K, 1, (int)n_rows, g);
 }
 
 }  // namespace flgp
