@@ -352,7 +352,10 @@ def run_ours(args):
     fp64_src = ("FP64 FMA throughput measured in-process by flgp_dfma_peak (register-resident DFMA loop); "
                 "MEASURED_PEAKS.json carries no fp64 figure")
     kernels = {
-        "kmeans_assign_kernel": ("kmeans_assign_small<3,4>", "fp64", NCU_TRAFFIC.get("kmeans_assign_small")),
+        "kmeans_assign_kernel": ("k-means pass 1, pivot-pruned (kmeans_assign_small<3,4> on 128 pivots + "
+                                 "kmeans_assign_listed<3,4>)", "fp64", None),
+        "kmeans_pruned_pass": ("k-means passes 2.., bound-pruned (kmeans_lists + kmeans_bounds + kmeans_assign_pruned<3> "
+                               "+ kmeans_update, per pass)", "fp64", None),
         "eigh_tridiag_resident": ("tridiag_kernel<true,512>", "fp64", NCU_TRAFFIC.get("tridiag_resident")),
         "eigh_tridiag_streaming": ("tridiag_kernel<false,1024>", "fp64", NCU_TRAFFIC.get("tridiag_streaming")),
     }
@@ -367,8 +370,14 @@ def run_ours(args):
                       "traffic": traffic[0] if traffic else None, "traffic_source": traffic[1] if traffic else None,
                       "launch_ms": a["ms"] / a["calls"], "algorithmic_flops_per_launch": a["flops"] / a["calls"],
                       "peak_source": fp64_src, "share_of_step": a["ms"] / args.steps / ms_step})
+    for r_ in roofs:
+        if "pruned" in r_["kernel"]:
+            r_["note"] = ("EXACT PRUNING: `achieved` counts the brute-force 2*s*d flop per point and pass (SURVEY.md 8d "
+                          "denominator) although most (point, centre) pairs are never scored, so frac may exceed 1; the "
+                          "kernels that remain are HBM / latency bound (profiles/README.md: bound test 5.05 TB/s = 0.78 "
+                          "of the HBM copy peak)")
     roofs.sort(key=lambda r: -r["share_of_step"])
-    roof = roofs[0] if roofs else None
+    roof = next((r_ for r_ in roofs if "pruned" not in r_["kernel"]), None)  # dominant SINGLE kernel
     if roof and roof["kernel"].startswith("tridiag"):
         roof["note"] = ("latency bound, not pipe bound: s-1 dependent column steps, each = on-chip symmetric product + one "
                         "grid-wide flag barrier (~2 us) + two block reductions; cycle breakdown per column in "
