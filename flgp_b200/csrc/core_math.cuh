@@ -224,18 +224,17 @@ FLGP_HD void simplex_project(const double* v, int r_in, double* z, double* vd) {
     }
     vd[b + 1] = key;
   }
-  double cs = 0.0, cs_rho = 0.0;
-  int rho = 0;
+  double cs = 0.0;
+  // theta = (cs_rho - 1) / rho is the very quotient formed at a = rho - 1 (same operands): it is kept instead of
+  // divided again (an IEEE fp64 division is ~30 instructions on the fp64 pipe); rho == 0 -> (0 - 1) / 0 = -inf
+  double theta = -INFINITY;
 #pragma unroll
   for (int a = 0; a < r; ++a) {
     cs = (a == 0) ? vd[0] : cs + vd[a];
-    double vstar = vd[a] - (cs - 1.0) / (double)(a + 1);
-    if (vstar > 0) {  // the reference scans from r down and stops at the LAST index with v* > 0
-      rho = a + 1;
-      cs_rho = cs;
-    }
+    const double qv = (cs - 1.0) / (double)(a + 1);
+    double vstar = vd[a] - qv;
+    if (vstar > 0) theta = qv;  // the reference scans from r down and stops at the LAST index with v* > 0
   }
-  double theta = (cs_rho - 1.0) / (double)rho;  // rho == 0 -> -inf, as the reference
 #pragma unroll
   for (int a = 0; a < r; ++a) {
     double t = v[a] - theta;
@@ -269,10 +268,36 @@ struct LaeStats {
   int iters, backtracks;
 };
 
+// 1 / beta for the back-tracking step size.  beta = 2^j * beta_curr with beta_curr = 1 initially, so beta is always
+// an exact power of two >= 1 (or +inf): its reciprocal is an exponent flip, bit-identical to the IEEE division.
+// Anything else (unreachable) takes the division.
+FLGP_HD double lae_recip(double beta) {
+#if defined(__CUDA_ARCH__)
+  const int hi = __double2hiint(beta), lo = __double2loint(beta);
+  const int e = (hi >> 20) & 0x7ff;
+  if (lo == 0 && (hi & 0x800fffff) == 0 && e >= 1023 && e <= 2045) return __hiloint2double((2046 - e) << 20, 0);
+#endif
+  return 1.0 / beta;
+}
+
+// The momentum ratio alpha_t = (delta_{t-1} - 1) / delta_t of iteration t depends on t only
+// (delta_0 = 0, delta_1 = 1, delta_{t+1} = (1 + sqrt(1 + 4 delta_t^2)) / 2): a table of LAE_T correctly rounded
+// values replaces one division and one square root per iteration and point.  IEEE sqrt and division are correctly
+// rounded on the host and on sm_100a alike, so the table equals the on-the-fly values bit for bit.
+inline void lae_alpha_table(double* tab) {
+  double delta_prev = 0.0, delta_curr = 1.0;
+  for (int t = 0; t < 100; ++t) {
+    tab[t] = (delta_prev - 1.0) / delta_curr;
+    delta_prev = delta_curr;
+    delta_curr = (1.0 + std::sqrt(1.0 + 4.0 * delta_curr * delta_curr)) / 2.0;
+  }
+}
+
 // The iteration proper, given UUt (r x r, row stride RA), xUt (r) and the objective w -> |x - w U|^2 / 2 as a callable
 // (sequential per thread in lae_solve; warp-cooperative in lae.cu's large-d kernel: same values, same order).
 template <int RT, class Obj>
-FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj&& objective, double* z_out) {
+FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj&& objective, double* z_out,
+                             const double* alpha_tab = nullptr) {
   constexpr int RA = RT ? RT : LAE_RMAX;
   const int r = RT ? RT : r_in;
   double zp[RA], v[RA], g[RA], vt[RA], z[RA], scratch[RA];
@@ -285,7 +310,7 @@ FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj
   double delta_prev = 0.0, delta_curr = 1.0, beta_curr = 1.0;
   int t = 0, nbt = 0;
   for (t = 0; t < LAE_T; ++t) {
-    const double alpha = (delta_prev - 1.0) / delta_curr;
+    const double alpha = alpha_tab ? alpha_tab[t] : (delta_prev - 1.0) / delta_curr;
 #pragma unroll
     for (int a = 0; a < r; ++a) v[a] = zc[a] + alpha * (zc[a] - zp[a]);
     const double g_v = objective(v);
@@ -299,7 +324,7 @@ FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj
     int j = 0;
     while (true) {
       const double beta = pow2i(j) * beta_curr;
-      const double ib = 1.0 / beta;
+      const double ib = lae_recip(beta);
 #pragma unroll
       for (int a = 0; a < r; ++a) vt[a] = v[a] - ib * g[a];
       simplex_project<RT>(vt, r, z, scratch);
@@ -324,8 +349,10 @@ FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj
       ++j;
       ++nbt;
     }
-    delta_prev = delta_curr;
-    delta_curr = (1.0 + sqrt(1.0 + 4.0 * delta_curr * delta_curr)) / 2.0;
+    if (!alpha_tab) {
+      delta_prev = delta_curr;
+      delta_curr = (1.0 + sqrt(1.0 + 4.0 * delta_curr * delta_curr)) / 2.0;
+    }
     double sq = 0.0;
 #pragma unroll
     for (int a = 0; a < r; ++a) {
@@ -344,7 +371,8 @@ FLGP_HD LaeStats lae_iterate(int r_in, const double* UUt, const double* xUt, Obj
 }
 
 template <int RT, int DT, class XAcc, class UAcc>
-FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out) {
+FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, double* z_out,
+                           const double* alpha_tab = nullptr) {
   constexpr int RA = RT ? RT : LAE_RMAX;
   const int r = RT ? RT : r_in;
   const int d = DT ? DT : d_in;
@@ -378,7 +406,7 @@ FLGP_HD LaeStats lae_solve(int r_in, int d_in, const XAcc& x, const UAcc& U, dou
     }
     return sq / 2.0;
   };
-  return lae_iterate<RT>(r, UUt, xUt, objective, z_out);
+  return lae_iterate<RT>(r, UUt, xUt, objective, z_out, alpha_tab);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1199,7 +1199,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       FLGP_LAUNCH(c, kmeans_prep_c2_kernel, ceil_div((int64_t)s * d, 256), 256, 0, C, (size_t)s * d, C2.p);
       FLGP_LAUNCH(c, kmeans_prep_cn_kernel, ceil_div(s, 64), 64, 0, C, s, d, Moff, cn.p);
     }
-    if (!brute && (!have_sorted || moved_since_sort * 8 > n_total)) resort();
+    static const int resort_div = std::getenv("FLGP_KM_RESORT") ? std::atoi(std::getenv("FLGP_KM_RESORT")) : 4;
+    if (!brute && (!have_sorted || moved_since_sort * resort_div > n_total)) resort();
     // when timing is on, the assign+accumulate work gets its own CUDA-event pair per pass
     StageScope kst(c, brute ? "kmeans_assign_kernel" : "kmeans_pruned_pass", 2.0 * s * d * (double)n_local,
                    (8.0 * d + 4.0) * (double)n_local);

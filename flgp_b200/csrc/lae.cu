@@ -19,6 +19,9 @@ namespace flgp {
 
 namespace {
 
+// momentum ratios alpha_t of the Nesterov iteration (core_math.cuh lae_alpha_table), filled once per process
+__device__ double g_lae_alpha[LAE_T];
+
 template <int R, int D>
 struct RegU {
   double u[R][D];
@@ -115,7 +118,7 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
       for (int k = 0; k < D; ++k) Ur.u[a][k] = U[col[a] + ldu * k];
     }
     double z[R];
-    const LaeStats ls = lae_solve<R, D>(R, D, x, Ur, z);
+    const LaeStats ls = lae_solve<R, D>(R, D, x, Ur, z, g_lae_alpha);
     it = ls.iters;
     bt = ls.backtracks;
     write_row<R>(R, col, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);  // perm: input row i is output row perm[i]
@@ -145,7 +148,7 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
       for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
     }
     double z[LAE_RMAX];
-    const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z);
+    const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z, g_lae_alpha);
     it = ls.iters;
     bt = ls.backtracks;
     write_row<LAE_RMAX>(r, Ur.c, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
@@ -252,7 +255,7 @@ lae_warp_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, con
       return sq / 2.0;
     };
     double z[LAE_RMAX];
-    const LaeStats ls = lae_iterate<0>(r, UUt, xUt, objective, z);
+    const LaeStats ls = lae_iterate<0>(r, UUt, xUt, objective, z, g_lae_alpha);
     if (lane == 0) {
       it_tot += ls.iters;
       bt_tot += ls.backtracks;
@@ -288,7 +291,7 @@ __global__ void lae_point_kernel(const double* x, int d, const double* Ur, int r
   ua.ldu = r;
   for (int a = 0; a < r; ++a) ua.c[a] = a;
   double zz[LAE_RMAX];
-  lae_solve<0, 0>(r, d, xa, ua, zz);
+  lae_solve<0, 0>(r, d, xa, ua, zz, g_lae_alpha);
   for (int a = 0; a < r; ++a) z[a] = zz[a];
 }
 
@@ -297,12 +300,24 @@ __global__ void simplex_project_kernel(const double* v, int r, double* z, double
   simplex_project<0>(v, r, z, scratch);
 }
 
+void lae_tables_init(Ctx* c) {
+  static bool done_dev[64] = {false};  // the table is a per-device symbol
+  bool& done = done_dev[c->device & 63];
+  if (done) return;
+  double tab[LAE_T];
+  lae_alpha_table(tab);
+  FLGP_CUDA(cudaMemcpyToSymbolAsync(g_lae_alpha, tab, sizeof tab, 0, cudaMemcpyHostToDevice, c->stream));
+  sync(c);  // tab is a stack array
+  done = true;
+}
+
 }  // namespace
 
 void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const double* U, int s, int64_t ldu,
              int r, const int32_t* ind, int32_t* Zj, double* Zx, double* Wd, long long* stats, const int32_t* perm) {
   if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
   if (n <= 0) return;
+  lae_tables_init(c);
   const int grid = ceil_div(n, 128);
 #define LAE_CASE(R_, D_)                                                                                  \
   if (r == R_ && d == D_) {                                                                               \
@@ -354,6 +369,7 @@ void se_weights_run(Ctx* c, const double* dist, int64_t len, double denom, doubl
 
 void lae_point_run(Ctx* c, const double* x, int d, const double* Ur, int r, double* z) {
   if (r < 1 || r > LAE_RMAX) fail(2, "LAE: r=%d outside the supported range 1..%d", r, LAE_RMAX);
+  lae_tables_init(c);
   FLGP_LAUNCH(c, lae_point_kernel, 1, 32, 0, x, d, Ur, r, z);
 }
 

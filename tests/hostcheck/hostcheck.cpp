@@ -24,7 +24,10 @@ template <int R, int D>
 void lae_fixed(const double* x, const double* U, double* z, int* it, int* bt) {
   PtrX xa{x};
   PtrU ua{U, R};
-  LaeStats st = lae_solve<R, D>(R, D, xa, ua, z);
+  static double tab[100];
+  static bool init = (lae_alpha_table(tab), true);
+  (void)init;
+  LaeStats st = lae_solve<R, D>(R, D, xa, ua, z, tab);
   *it = st.iters;
   *bt = st.backtracks;
 }
