@@ -6,7 +6,8 @@ libflgp_b200.so and fails loudly when it is absent; there is no CPU or PyTorch f
 """
 from .api import (  # noqa: F401
     Context, EigenPair, FlgpError, HK_from_spectrum_cpp, KNN_cpp, LAE_cpp, cross_similarity_lae_cpp,
-    cross_similarity_se_cpp, default_ctx, default_init, eigs_sym, fit_lae_regression_gp_rcpp, fit_se_regression_gp_rcpp,
+    cross_similarity_se_cpp, default_ctx, default_init, eigs_sym, fit_lae_regression_gp_rcpp, fit_nystrom_regression_gp_rcpp,
+    fit_se_regression_gp_rcpp,
     graphLaplacian_cpp,
     heat_kernel_covariance_rcpp, heat_kernel_spectrum_cpp, heat_kernel_spectrum_sharded, knn_distances,
     lae_eigenmap, local_anchor_embedding_cpp, mma_minimize, regression_fixed, regression_objective, spectrum_from_Z_cpp, subsample_cpp, train_regression_gp,

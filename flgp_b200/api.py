@@ -595,3 +595,41 @@ def fit_se_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: f
         Kk = s if K < 0 else K
         res["C"] = HK_from_spectrum_cpp(ep, Kk, xo[0], np.arange(n, dtype=np.int32), np.arange(m, dtype=np.int32))
     return res
+
+
+def fit_nystrom_regression_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: float = 1e-5, a2s=None,
+                                   approach="posterior", noise="same", subsample="kmeans", output_cov: bool = False,
+                                   nstart: int = 1, *, pars: Optional[Sequence[float]] = None, init_idx=None,
+                                   seed: int = 0, iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_nystrom_regression_gp_rcpp (R/Fit.R:177-195 -> src/Fit.cpp:222-357): the Nystrom-extension baseline —
+    dense SE kernel on the s anchors, top-K eigenpairs, extension of the eigenvectors to every row (an n x s x K
+    product on the FP64 tensor cores, in row blocks), bandwidth grid, training, GPR tail."""
+    if noise != "same":
+        raise FlgpError("The noise setting is illegal!" if noise != "different"
+                        else "noise=\"different\" (one variance per training point) is not part of this path")
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    if output_cov:
+        raise FlgpError("output_cov is not offloaded for the Nystrom driver")
+    ctx = ctx or default_ctx()
+    if a2s is None:
+        a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    a2s = np.ascontiguousarray(a2s, dtype=np.float64)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    train = np.zeros(m)
+    test = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    xo = np.zeros(2)
+    fixed = np.ascontiguousarray(pars, dtype=np.float64) if pars is not None else None
+    a2 = C.c_double()
+    obj = C.c_double()
+    check(ctx._lib.flgp_fit_nystrom_regression(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, K, sigma, _pf(a2s),
+                                               a2s.size, _b(approach), _b(subsample), nstart, iter_max,
+                                               _pi(_idx(init_idx)), seed, _pf(fixed), _pf(train), _pf(test), _pf(cov),
+                                               _pf(xo), C.byref(a2), C.byref(obj)))
+    return {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(xo),
+            "a2": a2.value, "obj": obj.value}

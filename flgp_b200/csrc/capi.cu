@@ -361,30 +361,26 @@ Models make_models(const char* subsample, const char* kernel, int gl, int root, 
 // Everything n-sized is folded through the r non-zeros of each row of A:
 //   mean_i = a_i . (Wm coef),   var_i = add + a_i^T (Wm M Wm^T) a_i,
 // coef (K) and M (K x K) come from the K x K (m > K, Woodbury) or m x m (m <= K) system on the host.
-void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double t, double noise,
-                          double sigma, double* y_pred, double* cov) {
-  Ctx* c = sp->c;
-  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
-  need(m_total >= 1 && m_total <= sp->n_total, "bad number of training rows");
-  const int s = sp->s, r = sp->r, KK = sp->K;
-  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
-  StageScope st(c, "gpr_tail", 2.0 * r * (double)sp->n_local * (1 + r), 24.0 * r * (double)sp->n_local);
+// coef (KK, zero padded beyond K) and M (KK x KK) of the GPR tail from the training rows V1 (row-major
+// m_local x KK on the device; this rank's share, starting at global row row_offset):
+//   mean_i = V_i . coef,   var_i = (noise + sigma) + V_i^T M V_i      (src/Predict.cpp:40-75, src/Utils.cpp:215-249)
+void gpr_tail_system(Ctx* c, const double* V1, int KK, int64_t m_local, int64_t row_offset, const double* Ydev,
+                     int64_t m_total, int K, const std::vector<double>& values, double t, double noise, double sigma,
+                     DevBuf<double>& dcoef, DevBuf<double>& dM) {
   std::vector<double> lam(K), ls(K);
   for (int k = 0; k < K; ++k) {
-    double ev = 1.0 - sp->values[k];
+    double ev = 1.0 - values[k];
     lam[k] = std::exp(-t * ev);
     ls[k] = std::exp(-0.5 * t * ev) + 0.0;
   }
   const double ns = noise + sigma;
-  // training rows of the lifted eigenvectors, row-major m_local x KK
-  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
-  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
-  DevBuf<double> dcoef(KK), dM((size_t)KK * KK);
+  dcoef.alloc(KK);
+  dM.alloc((size_t)KK * KK);
   if (m_total > K) {
     // Woodbury branch (src/Predict.cpp:61-74, src/Utils.cpp:237-244): the K x K algebra stays on the device (tail.cu)
     DevBuf<double> Gg((size_t)KK * KK + KK), dls(K), dlam(K);
     DevBuf<int> flag(1);
-    gram_small_run(c, V1.p, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
+    gram_small_run(c, V1, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
     comm_allreduce_f64(c, Gg.p, (size_t)KK * KK + KK);
     dls.upload(ls.data(), K, c->stream);
     dlam.upload(lam.data(), K, c->stream);
@@ -401,9 +397,9 @@ void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total
     DevBuf<double> Vall((size_t)m * KK + m);
     Vall.zero(c->stream);
     if (m_local > 0) {
-      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)row_offset * KK, V1, sizeof(double) * m_local * KK,
                                 cudaMemcpyDeviceToDevice, c->stream));
-      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + sp->row_offset, Ydev, sizeof(double) * m_local,
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + row_offset, Ydev, sizeof(double) * m_local,
                                 cudaMemcpyDeviceToDevice, c->stream));
     }
     comm_allreduce_f64(c, Vall.p, (size_t)m * KK + m);
@@ -443,6 +439,22 @@ void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total
     dM.upload(M.data(), (size_t)KK * KK, c->stream);
     sync(c);  // coef / M are host temporaries of this branch
   }
+}
+
+void regression_fixed_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double t, double noise,
+                          double sigma, double* y_pred, double* cov) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total, "bad number of training rows");
+  const int s = sp->s, r = sp->r, KK = sp->K;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  StageScope st(c, "gpr_tail", 2.0 * r * (double)sp->n_local * (1 + r), 24.0 * r * (double)sp->n_local);
+  const double ns = noise + sigma;
+  // training rows of the lifted eigenvectors, row-major m_local x KK
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
+  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  DevBuf<double> dcoef, dM;
+  gpr_tail_system(c, V1.p, KK, m_local, sp->row_offset, Ydev, m_total, K, sp->values, t, noise, sigma, dcoef, dM);
   // fold through the lift operator Wm (s x KK row-major)
   DevBuf<double> wv(s), T((size_t)s * KK), B((size_t)s * s);
   gemv_run(c, sp->Wm.p, dcoef.p, s, KK, wv.p);
@@ -1220,6 +1232,113 @@ int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, cons
     if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
     if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
     if (out) *out = sp.release();
+  });
+}
+
+int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
+                                const char* approach, const char* subsample, int nstart, int iter_max,
+                                const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
+                                double* test, double* cov, double* pars_out, double* best_a2, double* best_obj) {
+  return guard([&] {
+    need(ctx && X && Y && train && pars_out && a2s, "null argument");
+    need(m >= 1 && m_new >= 0 && d >= 1 && n_a2 >= 1, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = &ctx->c;
+    need(c->nranks == 1, "flgp_fit_nystrom_regression is the single-process entry point");
+    const int64_t n = m + m_new;
+    need(s >= 1 && s <= n && n < ((int64_t)1 << 31), "need 1 <= s <= n");
+    if (K < 0) K = s;  // R/Fit.R:183-185
+    need(K >= 1 && K <= s, "need 1 <= K <= s");
+    DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+    DevBuf<double> dY(m);
+    dY.upload(Y, m, c->stream);
+    // anchors (src/Fit.cpp:242): subsample_cpp(...).leftCols(d)
+    flgp_spectrum base;
+    base.c = c;
+    base.n_local = base.n_total = n;
+    base.d = d;
+    base.s = s;
+    base.r = 1;
+    const Models mo = make_models(subsample, "se", FLGP_GL_RW, 1, nstart, 0.1, iter_max);
+    stage_subsample(c, &base, dX.p, mo, init_idx, seed, nullptr);
+    base.sorted = KMeansSorted();
+    const double* U = base.U.p;
+    DevBuf<double> un(s), D((size_t)s * s);
+    double dmean = 0.0;
+    nys_anchor_distances_run(c, U, s, s, d, un.p, D.p, &dmean);
+    // row blocks: the n_b x s weight block stays below ~512 MB
+    const int64_t nb_max = std::max<int64_t>(256, std::min<int64_t>(n, ((int64_t)64 << 20) / s));
+    DevBuf<double> Wx((size_t)std::min<int64_t>(nb_max, n) * s);
+    DevBuf<double> V1((size_t)m * K);
+    struct Cand {
+      DevBuf<double> rs, Bt;
+      std::vector<double> lam;
+      double denom = 0.0;
+    } best;
+    double max_obj = -std::numeric_limits<double>::infinity();
+    bool have = false;
+    for (int q = 0; q < n_a2; ++q) {  // grid search (src/Fit.cpp:262-312)
+      Cand cd;
+      cd.rs.alloc(s);
+      cd.Bt.alloc((size_t)K * s);
+      cd.denom = a2s[q] * dmean;
+      DevBuf<double> lam(K);
+      nys_anchor_operator_run(c, D.p, s, K, cd.denom, cd.rs.p, lam.p, cd.Bt.p);
+      cd.lam.resize(K);
+      lam.download(cd.lam.data(), K, c->stream);
+      sync(c);
+      for (int64_t r0 = 0; r0 < m; r0 += nb_max) {
+        const int64_t nb = std::min<int64_t>(nb_max, m - r0);
+        nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, cd.rs.p, cd.denom, cd.Bt.p, K, Wx.p,
+                            V1.p + (size_t)r0 * K);
+      }
+      const RegTrain T = reg_train_from_rows(c, V1.p, K, m, 0, dY.p, m, K, sigma, cd.lam);
+      double x[2] = {std::nan(""), std::nan("")};
+      double obj;
+      if (fixed_pars) {
+        x[0] = fixed_pars[0];
+        x[1] = fixed_pars[1];
+        obj = -reg_objective(T, x, nullptr, post);
+      } else {
+        obj = train_regression(T, post, x, nullptr);
+      }
+      if (obj > max_obj || !have) {
+        max_obj = obj;
+        pars_out[0] = x[0];
+        pars_out[1] = x[1];
+        if (best_a2) *best_a2 = a2s[q];
+        best = std::move(cd);
+        have = true;
+      }
+    }
+    if (best_obj) *best_obj = max_obj;
+    // predictions with the winning bandwidth (src/Fit.cpp:318-340)
+    for (int64_t r0 = 0; r0 < m; r0 += nb_max) {
+      const int64_t nb = std::min<int64_t>(nb_max, m - r0);
+      nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p,
+                          V1.p + (size_t)r0 * K);
+    }
+    DevBuf<double> dcoef, dM;
+    gpr_tail_system(c, V1.p, K, m, 0, dY.p, m, K, best.lam, pars_out[0], pars_out[1], sigma, dcoef, dM);
+    const double ns = pars_out[1] + sigma;
+    const int64_t nbv = std::min<int64_t>(nb_max, n);
+    DevBuf<double> Vb((size_t)nbv * K), Tb((size_t)nbv * K), dy(n), dc(n);
+    for (int64_t r0 = 0; r0 < n; r0 += nb_max) {
+      const int64_t nb = std::min<int64_t>(nb_max, n - r0);
+      nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p, Vb.p);
+      gemv_run(c, Vb.p, dcoef.p, nb, K, dy.p + r0);
+      gemm_nn_run(c, Vb.p, dM.p, nb, K, K, Tb.p);  // M symmetric: row-major image = column-major image
+      nys_rowdot_run(c, Tb.p, Vb.p, nb, K, ns, dc.p + r0);
+    }
+    std::vector<double> y(n), cv(n);
+    dy.download(y.data(), n, c->stream);
+    dc.download(cv.data(), n, c->stream);
+    sync(c);
+    std::memcpy(train, y.data(), sizeof(double) * m);
+    if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
+    if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
   });
 }
 

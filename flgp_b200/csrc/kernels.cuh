@@ -96,6 +96,19 @@ void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double
 // G(K x K, col-major) = V^T V and g = V^T y over n_rows rows of V (row-major n_rows x K); deterministic
 void gram_small_run(Ctx* c, const double* V, const double* y, int64_t n_rows, int K, double* G, double* g);
 
+// ---- nystrom.cu ------------------------------------------------------------------------------
+// Nystrom extension (fit_nystrom_regression_gp_cpp, src/Fit.cpp:222-357).  U: s x d column-major (ld ldu).
+// un (s): |u|^2;  D (s x s): squared distances between anchors;  *mean_h: their mean (host).
+void nys_anchor_distances_run(Ctx* c, const double* U, int s, int64_t ldu, int d, double* un, double* D, double* mean_h);
+// for one bandwidth (denom = a2 * mean): rs (s) = rowsums of Z_UU + 1e-9, lam (K) = top eigenvalues of W_UU,
+// Bt (K x s row-major) = rescaled anchor eigenvectors divided by (|lam| + 1e-9)
+void nys_anchor_operator_run(Ctx* c, const double* D, int s, int K, double denom, double* rs, double* lam, double* Bt);
+// rows row0 .. row0+nb-1 of X (column-major, ld ldx): Wx (nb x s row-major scratch), V (nb x K row-major) = extension
+void nys_extend_rows_run(Ctx* c, const double* X, int64_t ldx, int64_t row0, int64_t nb, int d, const double* U, int s,
+                         int64_t ldu, const double* un, const double* rs, double denom, const double* Bt, int K,
+                         double* Wx, double* V);
+void nys_rowdot_run(Ctx* c, const double* T, const double* V, int64_t n, int K, double add, double* out);
+
 // ---- tail.cu ---------------------------------------------------------------------------------
 // m > K branch of the GPR tail: from Gg = [G1 (K_ld x K_ld col-major) | g1 (K_ld)] to coef (K_ld) and M (K_ld x K_ld),
 // both zero padded beyond K; *flag = 1 if Q is not positive definite.  All pointers on the device.

@@ -24,25 +24,23 @@ struct RegTrain {
   std::vector<double> Y;    // m (m <= K)
 };
 
-RegTrain reg_train_prepare(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double sigma) {
-  Ctx* c = sp->c;
-  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
-  need(m_total >= 1 && m_total <= sp->n_total && m_total < INT32_MAX, "bad number of training rows");
-  const int r = sp->r, KK = sp->K;
-  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+// statistics from the training rows V1 (row-major m_local x KK on the device, this rank's share from global row
+// row_offset), eigenvalues `values` (as exported: the Laplacian spectrum is 1 - values)
+RegTrain reg_train_from_rows(Ctx* c, const double* V1, int KK, int64_t m_local, int64_t row_offset, const double* Ydev,
+                             int64_t m_total, int K, double sigma, const std::vector<double>& values) {
+  need(K >= 1 && K <= KK, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total < INT32_MAX, "bad number of training rows");
   RegTrain T;
   T.m = (int)m_total;
   T.K = K;
   T.sigma = sigma;
   T.ev.resize(K);
-  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - sp->values[k];
-  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
-  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - values[k];
   if (m_total > K) {
     const size_t words = (size_t)KK * KK + KK + 1;
     DevBuf<double> Gg(words);
     Gg.zero(c->stream);
-    gram_small_run(c, V1.p, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
+    gram_small_run(c, V1, Ydev, m_local, KK, Gg.p, Gg.p + (size_t)KK * KK);
     if (m_local > 0) gemv_run(c, Ydev, Ydev, 1, (int)m_local, Gg.p + (size_t)KK * KK + KK);
     comm_allreduce_f64(c, Gg.p, words);
     std::vector<double> h(words);
@@ -60,9 +58,9 @@ RegTrain reg_train_prepare(flgp_spectrum* sp, const double* Ydev, int64_t m_tota
     DevBuf<double> Vall((size_t)m * KK + m);
     Vall.zero(c->stream);
     if (m_local > 0) {
-      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)row_offset * KK, V1, sizeof(double) * m_local * KK,
                                 cudaMemcpyDeviceToDevice, c->stream));
-      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + sp->row_offset, Ydev, sizeof(double) * m_local,
+      FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + row_offset, Ydev, sizeof(double) * m_local,
                                 cudaMemcpyDeviceToDevice, c->stream));
     }
     comm_allreduce_f64(c, Vall.p, (size_t)m * KK + m);
@@ -75,6 +73,17 @@ RegTrain reg_train_prepare(flgp_spectrum* sp, const double* Ydev, int64_t m_tota
     T.Y.assign(h.begin() + (size_t)m * KK, h.end());
   }
   return T;
+}
+
+RegTrain reg_train_prepare(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double sigma) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total && m_total < INT32_MAX, "bad number of training rows");
+  const int r = sp->r, KK = sp->K;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
+  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  return reg_train_from_rows(c, V1.p, KK, m_local, sp->row_offset, Ydev, m_total, K, sigma, sp->values);
 }
 
 // inverse from a lower Cholesky factor (column-major n x n): returns A^-1 (full, symmetric)

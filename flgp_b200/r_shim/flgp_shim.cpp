@@ -23,6 +23,7 @@
 //   fit_lae_regression_gp_cpp     src/Fit.cpp:20-99            -> flgp_fit_lae_regression (spectrum + MMA training + GPR tail)
 //   fit_se_regression_gp_cpp      src/Fit.cpp:102-219          -> flgp_fit_se_regression  (one k-means/KNN, bandwidth grid)
 //   train_regression_gp_cpp       src/train.cpp:557-671        -> flgp_train_regression   (noise = "same")
+//   fit_nystrom_regression_gp_cpp src/Fit.cpp:222-357          -> flgp_fit_nystrom_regression
 // [[Rcpp::depends(RcppEigen)]]
 #include <RcppEigen.h>
 
@@ -260,4 +261,24 @@ Rcpp::List fit_se_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVe
     res["C"] = C;
   }
   return res;
+}
+
+Rcpp::List fit_nystrom_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                         int s, int K, double sigma, std::vector<double> a2s, std::string approach,
+                                         std::string noise, std::string subsample, bool output_cov, int nstart) {
+  if (noise != "same" || output_cov) Rcpp::stop("noise=\"different\" / output_cov are not offloaded; call the reference path");
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows();
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  std::vector<double> pars(2);
+  Eigen::VectorXd train(m), test(m_new), cov(m_new);
+  double a2 = 0.0, obj = 0.0;
+  ok(flgp_fit_nystrom_regression(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, K, sigma, a2s.data(),
+                                 (int)a2s.size(), approach.c_str(), subsample.c_str(), nstart, 100, init.data(), 0, nullptr,
+                                 train.data(), test.data(), cov.data(), pars.data(), &a2, &obj));
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", t = " << pars[0]
+              << ", sigma = " << std::sqrt(pars[1]) << ", the objective function is " << obj << "\n";
+  return pack_fit(train, test, cov, pars);
 }

@@ -199,6 +199,15 @@ int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, cons
                            const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
                            double* test, double* cov, double* pars_out, double* best_a2, double* best_obj,
                            flgp_spectrum** out);
+/* fit_nystrom_regression_gp_cpp (src/Fit.cpp:222-357; R wrapper R/Fit.R:177-195), SURVEY.md §8f row 4: anchors by
+ * subsample_cpp, dense SE kernel on the anchors (bandwidth a2 * mean anchor distance), doubly normalised; its top-K
+ * eigenpairs (the RSpectra::eigs_sym callback) are extended to every row by the Nystrom formula; training and GPR
+ * tail as in the other drivers.  Single process.  fixed_pars (may be NULL): skip the training. */
+int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
+                                const char* approach, const char* subsample, int nstart, int iter_max,
+                                const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
+                                double* test, double* cov, double* pars_out, double* best_a2, double* best_obj);
 
 #ifdef __cplusplus
 }

@@ -593,3 +593,69 @@ def fit_se_regression(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-5, approach=
     best["test"] = predict_regression(V, values, Y, idx0, idx1, K, x, sigma)
     best["cov"] = posterior_covariance_regression(V, values, idx0, idx1, K, x, sigma)
     return best
+
+
+# ------------------------------------------------------------------ Nystrom extension
+def _sqdist(A, B):
+    """((-2 A B^T) + |a|^2) + |b|^2 with sequential, separately rounded sums (the contract for every distance)."""
+    A = _f(A)
+    B = _f(B)
+    na, d = A.shape
+    dot = np.zeros((na, B.shape[0]))
+    an = np.zeros(na)
+    bn = np.zeros(B.shape[0])
+    for k in range(d):
+        dot = dot + np.outer(A[:, k], B[:, k])
+        an = an + A[:, k] * A[:, k]
+        bn = bn + B[:, k] * B[:, k]
+    return ((-2.0 * dot) + an[:, None]) + bn[None, :]
+
+
+def fit_nystrom_regression(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-5, approach="posterior", iter_max=100,
+                           nthreads=1, pars=None):
+    """fit_nystrom_regression_gp_cpp (src/Fit.cpp:222-357), dense and literal; RSpectra::eigs_sym replaced by LAPACK
+    (top-K algebraic: W_UU is positive semi-definite, so largest magnitude = largest algebraic)."""
+    m = len(X)
+    X_all = np.asfortranarray(np.vstack([X, X_new]))
+    n = len(X_all)
+    if K < 0:
+        K = s
+    U = kmeans_lloyd(X_all, s, init_idx, iter_max, nthreads)[0][:, :-1]
+    D_UU = _sqdist(U, U)
+    D_all = _sqdist(X_all, U)
+    dmean = D_UU.sum() / (s * s)
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n, dtype=np.int32)
+    best = None
+    for a2 in a2s:
+        Z_UU = np.exp(-D_UU / (a2 * dmean))
+        rs = Z_UU.sum(axis=1) + 1e-9
+        A_UU = (1.0 / rs)[:, None] * Z_UU * (1.0 / rs)[None, :]
+        sdi = 1.0 / np.sqrt(A_UU.sum(axis=1) + 1e-9)
+        W_UU = sdi[:, None] * A_UU * sdi[None, :]
+        w, Q = np.linalg.eigh((W_UU + W_UU.T) / 2)
+        values, vecs = w[::-1][:K].copy(), Q[:, ::-1][:, :K].copy()
+        vecs = sdi[:, None] * vecs
+        vecs = np.sqrt(s) * vecs * (1.0 / (np.linalg.norm(vecs, axis=0) + 1e-9))[None, :]
+
+        def extend(Dx, a2=a2, rs=rs, vecs=vecs, values=values):  # bound now: the closure outlives the loop
+            Zx = np.exp(-Dx / (a2 * dmean))
+            Ax = (1.0 / (Zx.sum(axis=1) + 1e-9))[:, None] * Zx * (1.0 / rs)[None, :]
+            Wx = (1.0 / (Ax.sum(axis=1) + 1e-9))[:, None] * Ax
+            return Wx @ vecs * (1.0 / (np.abs(values) + 1e-9))[None, :]
+
+        Vm = extend(D_all[:m])
+        if pars is None:
+            x, obj = train_regression(Vm, values, Y, idx0, K, sigma, approach)
+        else:
+            x = np.asarray(pars, dtype=np.float64)
+            obj = -regression_objective(Vm, values, Y, idx0, K, x, sigma, approach)[0]
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, pars=x, a2=a2, values=values, extend=extend)
+    V = best["extend"](D_all)
+    values, x = best["values"], best["pars"]
+    best["train"] = predict_regression(V, values, Y, idx0, idx0, K, x, sigma)
+    best["test"] = predict_regression(V, values, Y, idx0, idx1, K, x, sigma)
+    best["cov"] = posterior_covariance_regression(V, values, idx0, idx1, K, x, sigma)
+    del best["extend"]
+    return best

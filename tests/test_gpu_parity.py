@@ -584,3 +584,38 @@ def test_fit_se_regression_config2_grid(flgp, oracle):
     assert res["C"].shape == (4000, m)
     rmse = np.sqrt(np.mean((res["Y_pred"]["test"] - Y[m:]) ** 2))
     assert rmse < 2.0   # labels carry N(0,1) noise on a signal of amplitude ~10
+
+
+# ------------------------------------------------------------------------------------------- Nystrom (§8f row 4)
+@pytest.mark.parametrize("n,d,m,s,K", [(3000, 2, 200, 300, 60), (1500, 3, 40, 128, 50), (2000, 16, 150, 100, 100)])
+def test_fit_nystrom_regression(flgp, oracle, n, d, m, s, K):
+    """fit_nystrom_regression_gp_rcpp against the oracle's dense literal restatement: same winning bandwidth, objective
+    to 1e-7, predictions and variances to 1e-6 at fixed (t, noise) (the dense s x s normalisation and the n x s x K
+    extension accumulate in different orders); trained parameters to optimiser tolerance."""
+    if d == 2:
+        X, Y = spiral(n, 6)
+    elif d == 3:
+        X, Y = swiss(n, 6)
+    else:
+        rng = np.random.default_rng(6)
+        a, b = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+        Q, _ = np.linalg.qr(rng.standard_normal((d, 4)))
+        X = np.asfortranarray(np.c_[np.cos(a), np.sin(a), np.cos(b), np.sin(b)] @ Q.T + 0.01 * rng.standard_normal((n, d)))
+        Y = np.sin(a) + np.cos(2 * b) + 0.1 * rng.standard_normal(n)
+    init = _init(n, s, 4)
+    a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 5))
+    pars = (6.0, 0.3)
+    res = flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, K, a2s=a2s, pars=pars, init_idx=init, iter_max=25)
+    ref = oracle.fit_nystrom_regression(X[:m], Y[:m], X[m:], s, K, init, a2s, pars=pars, iter_max=25, nthreads=NT)
+    assert res["a2"] == ref["a2"]
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-7, atol=1e-7)
+    scale = max(1.0, np.abs(ref["test"]).max())
+    np.testing.assert_allclose(res["Y_pred"]["train"], ref["train"], rtol=1e-6, atol=1e-6 * scale)
+    np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-6, atol=1e-6 * scale)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-6, atol=1e-8)
+    if d == 2:  # with training
+        res = flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, K, a2s=a2s, init_idx=init, iter_max=25)
+        ref = oracle.fit_nystrom_regression(X[:m], Y[:m], X[m:], s, K, init, a2s, iter_max=25, nthreads=NT)
+        assert res["a2"] == ref["a2"]
+        np.testing.assert_allclose(res["pars"], ref["pars"], rtol=1e-3)
+        np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-3, atol=1e-3 * scale)

@@ -253,3 +253,17 @@ def test_golden_fixture(oracle):
     assert np.array_equal(Zj, g["Zj"]) and np.array_equal(Zx, g["Zx"])
     values, V = oracle.spectrum_from_Z(Zj, Zx, meta["s"], meta["K"], True)
     np.testing.assert_allclose(values, g["values"], rtol=1e-11)
+
+
+def test_nystrom_oracle_is_a_sane_regressor(oracle):
+    """The dense restatement of fit_nystrom_regression_gp_cpp (oracle.fit_nystrom_regression) on the README spiral:
+    extension rows are convex-like weights, predictions track the signal."""
+    from conftest import spiral
+
+    X, Y = spiral(1200, 9)
+    m, s, K = 150, 100, 40
+    init = np.sort(np.random.default_rng(1).choice(1200, s, replace=False)).astype(np.int32)
+    res = oracle.fit_nystrom_regression(X[:m], Y[:m], X[m:], s, K, init, [0.5, 2.0], pars=(2.0, 1.0), iter_max=15)
+    assert res["a2"] in (0.5, 2.0) and np.isfinite(res["obj"])
+    assert np.all(np.isfinite(res["test"])) and np.all(res["cov"] > 0)
+    assert np.sqrt(np.mean((res["test"] - Y[m:]) ** 2)) < 0.7 * np.std(Y[m:])  # labels carry N(0,1) noise
