@@ -67,7 +67,15 @@ __global__ void __launch_bounds__(128)
 dist_select_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapC,
                    const double* __restrict__ add, int64_t n, int s, int nk, double thr0,
                    const double* __restrict__ thr_row, int r, int32_t* __restrict__ out_idx, int64_t ldo,
-                   int* __restrict__ und_count, int32_t* __restrict__ und_list) {
+                   int* __restrict__ und_count, int32_t* __restrict__ und_list, const int* __restrict__ n_rows_dev,
+                   double* __restrict__ out_val) {
+  // n_rows_dev (optional): only the first *n_rows_dev rows are live (a device-side count, e.g. the survivors of a
+  // bound test); CTAs beyond it leave at once, so the launch needs no host round trip
+  if (n_rows_dev) {
+    const int64_t live = *n_rows_dev;
+    if ((int64_t)blockIdx.x * DG_T >= live) return;
+    n = n < live ? n : live;
+  }
   extern __shared__ __align__(1024) unsigned char dsm_raw[];
   double* boxes = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t full[DG_STAGES];
@@ -196,6 +204,10 @@ dist_select_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 #pragma unroll
       for (int t = 0; t < R1 - 1; ++t)
         if (t < r) out_idx[i + ldo * t] = (ix[a][t] < s) ? ix[a][t] : 0;
+      if (out_val) {  // the two smallest values (k-means bounds: best and runner-up)
+        out_val[2 * i] = v[a][0];
+        out_val[2 * i + 1] = v[a][1];
+      }
       if (!ok) und_list[atomicAdd(und_count, 1)] = (int32_t)i;
     }
   }
@@ -204,11 +216,11 @@ dist_select_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
 template <int R1>
 void launch_select(Ctx* c, const CUtensorMap& mapX, const CUtensorMap& mapC, const double* add, int64_t n, int s,
                    int nk, double thr0, const double* thr_row, int r, int32_t* out_idx, int64_t ldo, int* und_count,
-                   int32_t* und_list) {
+                   int32_t* und_list, const int* n_rows_dev, double* out_val) {
   const size_t smem = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024;
   FLGP_CUDA(cudaFuncSetAttribute(dist_select_kernel<R1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   FLGP_LAUNCH(c, dist_select_kernel<R1>, ceil_div(n, DG_T), 128, smem, mapX, mapC, add, n, s, nk, thr0, thr_row, r,
-              out_idx, ldo, und_count, und_list);
+              out_idx, ldo, und_count, und_list, n_rows_dev, out_val);
 }
 
 }  // namespace
@@ -223,15 +235,19 @@ bool dist_select_supported(int64_t n, int s, int r) { return n >= DG_T && s >= D
 
 void dist_select_run(Ctx* c, const double* Xr, int64_t n, const double* Cr, int s, int dp, const double* add, int r,
                      double thr0, const double* thr_row, int32_t* out_idx, int64_t ldo, int* und_count,
-                     int32_t* und_list) {
+                     int32_t* und_list, const int* n_rows_dev, double* out_val) {
   if (!dist_select_supported(n, s, r)) fail(2, "dist_select: unsupported shape (n=%lld, s=%d, r=%d)", (long long)n, s, r);
   if (dp % 2) fail(2, "dist_select: the row pitch must be even");
   const CUtensorMap mapX = make_map(Xr, n, dp, dp), mapC = make_map(Cr, s, dp, dp);
   const int nk = (dp + DG_K - 1) / DG_K;
-  if (r == 1) launch_select<2>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list);
-  else if (r == 2) launch_select<3>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list);
-  else if (r == 3) launch_select<4>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list);
-  else launch_select<6>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list);
+  if (r == 1) launch_select<2>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list, n_rows_dev,
+                          out_val);
+  else if (r == 2) launch_select<3>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list, n_rows_dev,
+                          out_val);
+  else if (r == 3) launch_select<4>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list, n_rows_dev,
+                          out_val);
+  else launch_select<6>(c, mapX, mapC, add, n, s, nk, thr0, thr_row, r, out_idx, ldo, und_count, und_list, n_rows_dev,
+                          out_val);
 }
 
 }  // namespace flgp

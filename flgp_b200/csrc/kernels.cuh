@@ -46,7 +46,9 @@ bool dist_select_supported(int64_t n, int s, int r);
 // the caller zeroes the counter) and must be re-done in the oracle's summation order.
 void dist_select_run(Ctx* c, const double* Xr, int64_t n, const double* Cr, int s, int dp, const double* add, int r,
                      double thr0, const double* thr_row, int32_t* out_idx, int64_t ldo, int* und_count,
-                     int32_t* und_list);
+                     int32_t* und_list, const int* n_rows_dev = nullptr, double* out_val = nullptr);
+// n_rows_dev (optional, device): only the first *n_rows_dev rows are live.  out_val (optional): 2 doubles per row, the
+// smallest and second smallest value (r + 1 >= 2 always).
 
 // ---- lae.cu ----------------------------------------------------------------------------------
 // Zj/Zx: n*r CSR (row i at i*r), rows sorted by column.  Wd: optional dense n x r weights (ld n)

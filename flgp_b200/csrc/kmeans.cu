@@ -519,70 +519,212 @@ kmeans_assign_tiled(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
   if ((tid & 31) == 0 && changed) atomicAdd(&acc[(size_t)2 * s * d + s], (unsigned long long)changed);
 }
 
-// ---- large d on the tensor cores (distsel.cu): rows the DMMA selection could not certify, and the commit ---------
-// One CTA per listed row: every score in the oracle's order (cn[j], then fma over ascending k), lowest value then
-// lowest index.  dynamic shared memory: d doubles.
+// ---- large d, passes 2..: Hamerly bounds around the tensor-core evaluation -----------------------------------------
+// Every point carries u >= |x - c_a| and l <= |x - c_j| for all j != a.  After the centres move: u += move[a],
+// l -= (largest move of any OTHER centre).  u + eta <= l  =>  the oracle's computed scores keep c_a strictly first
+// (eta^2 > 2 Delta, as in the small-d path), so the point is skipped without touching its coordinates; the rest first
+// tighten u with one exact score (d flops), and only what still fails is gathered and re-evaluated against all centres
+// by dist_select_kernel, which also returns the two smallest values for the new bounds.
+__global__ void kmeans_xnorm_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, double* __restrict__ xn) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int k = 0; k < d; ++k) {
+    const double x = X[i + ldx * k];
+    a = fma(x, x, a);
+  }
+  xn[i] = a;
+}
+// move[j] >= |c_new - c_old|, one warp per centre
+__global__ void kmeans_move_kernel(const double* __restrict__ C, const double* __restrict__ Cold, int s, int d,
+                                   double* __restrict__ move) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= s) return;
+  double a = 0.0;
+  for (int k = lane; k < d; k += 32) {
+    const double df = C[j + (size_t)s * k] - Cold[j + (size_t)s * k];
+    a = fma(df, df, a);
+  }
+  for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) move[j] = sqrt(a) * (1.0 + 1e-12) * (1.0 + 1e-12);  // summation-order slack
+}
+// mm = {largest move, second largest move, index of the largest}
+__global__ void kmeans_move_max_kernel(const double* __restrict__ move, int s, double* __restrict__ mm,
+                                       unsigned long long* __restrict__ maxbits) {
+  __shared__ double v1[256], v2[256];
+  __shared__ int i1[256];
+  const int tid = threadIdx.x;
+  double a = -1.0, b = -1.0;
+  int ia = -1;
+  for (int j = tid; j < s; j += 256) {
+    const double m = move[j];
+    if (m > a) {
+      b = a;
+      a = m;
+      ia = j;
+    } else if (m > b) {
+      b = m;
+    }
+  }
+  v1[tid] = a;
+  v2[tid] = b;
+  i1[tid] = ia;
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 1; t < 256; ++t) {
+      if (v1[t] > a) {
+        b = fmax(a, v2[t]);
+        a = v1[t];
+        ia = i1[t];
+      } else {
+        b = fmax(b, v1[t]);
+      }
+    }
+    mm[0] = fmax(a, 0.0);
+    mm[1] = fmax(b, 0.0);
+    mm[2] = (double)ia;
+    *maxbits = (unsigned long long)__double_as_longlong(fmax(a, 0.0));
+  }
+}
 __global__ void __launch_bounds__(256)
-kmeans_exact_rows_kernel(const double* __restrict__ X, int64_t ldx, int d, const double* __restrict__ C2,
-                         const double* __restrict__ cn, int s, const int* __restrict__ und_count,
-                         const int32_t* __restrict__ und_list, int32_t* __restrict__ newa) {
+kmeans_hbounds_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ C2,
+                      const double* __restrict__ cn, int s, const int32_t* __restrict__ assign,
+                      const double4* __restrict__ cl, double eta, double M,
+                      double delta2, const double* __restrict__ xn, double* __restrict__ UB, double* __restrict__ LB,
+                      int32_t* __restrict__ surv, int* __restrict__ nsurv) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t i0 = (int64_t)blockIdx.x * 256; i0 < n; i0 += (int64_t)gridDim.x * 256) {  // uniform per warp
+    const int64_t i = i0 + threadIdx.x;
+    bool need = false;
+    if (i < n) {
+      const int a = assign[i];
+      // cl[a] = {move of c_a, largest move among the centres of a's neighbour list, radius the list is complete to}
+      const double4 ca = cl[a];
+      const double u = (UB[i] + ca.x) * (1.0 + 1e-15);
+      const double l = fmin((LB[i] - ca.y) * (1.0 - 1e-15) - 1e-300, (ca.z - u * (1.0 + 1e-15)) * (1.0 - 1e-15));
+      if (u + eta <= l) {
+        UB[i] = u;
+        LB[i] = l;
+      } else {
+        double e = cn[a];
+        for (int k = 0; k < d; ++k) e = fma(X[i + ldx * k], C2[a + (size_t)s * k], e);
+        const double ub0 = km_ub_fast(e, M, xn[i], delta2);
+        if (ub0 + eta <= l) {
+          UB[i] = ub0;
+          LB[i] = l;
+        } else {
+          need = true;  // the evaluation rewrites both bounds
+        }
+      }
+    }
+    const unsigned mw = __ballot_sync(0xffffffffu, need);
+    if (mw) {
+      const int lead = __ffs(mw) - 1;
+      int base = 0;
+      if (lane == lead) base = atomicAdd(nsurv, __popc(mw));
+      base = __shfl_sync(0xffffffffu, base, lead);
+      if (need) surv[base + __popc(mw & ((1u << lane) - 1))] = (int32_t)i;
+    }
+  }
+}
+// survivors' rows, row-major dp pitch, one warp per row
+__global__ void kmeans_gather_rows_kernel(const double* __restrict__ Xr, int dp, const int32_t* __restrict__ surv,
+                                          const int* __restrict__ nsurv, double* __restrict__ Xs) {
+  const int lane = threadIdx.x & 31, cnt = *nsurv;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < cnt; q += nw) {
+    const double* src = Xr + (int64_t)surv[q] * dp;
+    for (int k = lane; k < dp; k += 32) Xs[q * dp + k] = src[k];
+  }
+}
+// rows the selection could not certify (positions in the survivor list): every score in the oracle's order; best
+// (lowest index on ties) and the runner-up value.  dynamic shared memory: d doubles.
+__global__ void __launch_bounds__(256)
+kmeans_exact_rows2_kernel(const double* __restrict__ X, int64_t ldx, int d, const double* __restrict__ C2,
+                          const double* __restrict__ cn, int s, const int* __restrict__ und_count,
+                          const int32_t* __restrict__ und_list, const int32_t* __restrict__ surv,
+                          int32_t* __restrict__ sidx, double* __restrict__ svals) {
   extern __shared__ double xs[];
-  __shared__ double rv[8];
+  __shared__ double rv[8], rs2[8];
   __shared__ int rj[8];
   const int tid = threadIdx.x, cnt = *und_count;
   for (int u = blockIdx.x; u < cnt; u += gridDim.x) {
-    const int64_t i = und_list[u];
+    const int q = und_list[u];
+    const int64_t i = surv ? surv[q] : q;
     __syncthreads();
     for (int k = tid; k < d; k += 256) xs[k] = X[i + ldx * k];
     __syncthreads();
-    double lv = INFINITY;
+    double lv = INFINITY, ls = INFINITY;
     int lj = 0x7fffffff;
     for (int j = tid; j < s; j += 256) {
       double e = cn[j];
       for (int k = 0; k < d; ++k) e = fma(xs[k], C2[j + (size_t)s * k], e);
-      if (e < lv) {  // ascending j per thread: the first minimum is the lowest index
+      if (e < lv) {
+        ls = lv;
         lv = e;
         lj = j;
+      } else if (e < ls) {
+        ls = e;
       }
     }
     for (int o = 16; o; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, lv, o);
+      const double ov = __shfl_xor_sync(0xffffffffu, lv, o), os = __shfl_xor_sync(0xffffffffu, ls, o);
       const int oj = __shfl_xor_sync(0xffffffffu, lj, o);
       if (ov < lv || (ov == lv && oj < lj)) {
+        ls = fmin(lv, os);
         lv = ov;
         lj = oj;
+      } else {
+        ls = fmin(ls, ov);
       }
     }
     if ((tid & 31) == 0) {
       rv[tid >> 5] = lv;
+      rs2[tid >> 5] = ls;
       rj[tid >> 5] = lj;
     }
     __syncthreads();
     if (tid == 0) {
-      for (int w = 1; w < 8; ++w)
+      for (int w = 1; w < 8; ++w) {
         if (rv[w] < lv || (rv[w] == lv && rj[w] < lj)) {
+          ls = fmin(lv, rs2[w]);
           lv = rv[w];
           lj = rj[w];
+        } else {
+          ls = fmin(ls, rv[w]);
         }
-      newa[i] = (lj < s) ? lj : 0;  // all-NaN row: centre 0, like the scan kernels
+      }
+      sidx[q] = (lj < s) ? lj : 0;
+      svals[2 * (size_t)q] = lv;
+      svals[2 * (size_t)q + 1] = ls;
     }
   }
 }
-
-// One warp per row: a changed assignment is an exact -enc(x) / +enc(x) on the persistent integer accumulators.
+// evaluated rows: new bounds from the two smallest values; a changed assignment is an exact -enc(x) / +enc(x).
+// One warp per evaluated row q (row surv[q] of the matrix; Xrows holds row q at pitch dp).
 __global__ void __launch_bounds__(256)
-kmeans_commit_rows_kernel(const double* __restrict__ Xr, int64_t n, int d, int dp, const int32_t* __restrict__ newa,
-                          int32_t* __restrict__ assign, int s, Fx fx, unsigned long long* __restrict__ acc) {
-  const int lane = threadIdx.x & 31;
-  const int64_t w0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+kmeans_hcommit_kernel(const double* __restrict__ Xrows, int d, int dp, const int32_t* __restrict__ surv,
+                      const int* __restrict__ nsurv, const int32_t* __restrict__ sidx, const double* __restrict__ svals,
+                      const double* __restrict__ xn, int32_t* __restrict__ assign, int s, Fx fx,
+                      unsigned long long* __restrict__ acc, double M, double delta2, double* __restrict__ UB,
+                      double* __restrict__ LB, unsigned long long* __restrict__ Rcur) {
+  const int lane = threadIdx.x & 31, cnt = *nsurv;
   const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
   int changed = 0;
-  for (int64_t i = w0; i < n; i += nw) {
-    const int a_old = assign[i], a_new = newa[i];
+  for (int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < cnt; q += nw) {
+    const int64_t i = surv ? surv[q] : q;
+    const int a_old = assign[i], a_new = sidx[q];
+    if (lane == 0) {
+      const double x2 = xn[i];
+      const double ub = km_ub_fast(svals[2 * q], M, x2, delta2);
+      UB[i] = ub;
+      LB[i] = km_lb_fast(svals[2 * q + 1], M, x2, delta2);
+      if (Rcur) km_radius(Rcur, a_new, ub);  // radius of the (new) cluster for the next pass's neighbour lists
+    }
     if (a_old == a_new) continue;
     for (int k = lane; k < d; k += 32) {
       long long h, l;
-      fx_encode(fx, Xr[i * dp + k], &h, &l);
+      fx_encode(fx, Xrows[q * dp + k], &h, &l);
       atomicAdd(&acc[a_new + (size_t)s * k], (unsigned long long)h);
       atomicAdd(&acc[(size_t)s * d + a_new + (size_t)s * k], (unsigned long long)l);
       if (a_old >= 0) {
@@ -1099,20 +1241,36 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   const bool dmma = !small && dist_select_supported(n_local, s, 1) && n_local < ((int64_t)1 << 31) &&
                     std::getenv("FLGP_NO_DMMA_DIST") == nullptr;
   const int dp = (d + 1) / 2 * 2;
-  DevBuf<double> Xr, Cr;
-  DevBuf<int32_t> newa, und_list;
-  DevBuf<int> und_count;
+  DevBuf<double> Xr, Cr, Xsv, hxn, hUB, hLB, hvals, Cold, hmove, hmm;
+  DevBuf<int32_t> newa, und_list, hsurv;
+  DevBuf<int> und_count, hnsurv;
+  const bool hamerly = dmma && std::getenv("FLGP_NO_HAMERLY") == nullptr;
   if (dmma) {
     Xr.alloc((size_t)n_local * dp);
     Cr.alloc((size_t)s * dp);
     newa.alloc(n_local);
     und_list.alloc(n_local);
     und_count.alloc(1);
+    hnsurv.alloc(1);
+    hvals.alloc((size_t)2 * n_local);
+    hxn.alloc(n_local);
+    hUB.alloc(n_local);
+    hLB.alloc(n_local);
+    if (hamerly) {
+      Xsv.alloc((size_t)n_local * dp);
+      hsurv.alloc(n_local);
+      Cold.alloc((size_t)s * d);
+      hmove.alloc(s);
+      hmm.alloc(4);
+      hmove.zero(c->stream);
+    }
+    FLGP_LAUNCH(c, kmeans_xnorm_kernel, ceil_div(n_local, 256), 256, 0, X, n_local, ldx, d, hxn.p);
     to_rowmajor_run(c, X, n_local, ldx, d, dp, Xr.p);
     const size_t xsm = sizeof(double) * d;
     if (xsm > 200 * 1024) fail(2, "kmeans: d=%d exceeds the supported maximum", d);
-    if (xsm > 40 * 1024)
-      FLGP_CUDA(cudaFuncSetAttribute(kmeans_exact_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+    if (xsm > 40 * 1024) {
+      FLGP_CUDA(cudaFuncSetAttribute(kmeans_exact_rows2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)xsm));
+    }
   }
   unsigned long long* uacc = reinterpret_cast<unsigned long long*>(acc.p);
   // pruned passes (small d): persistent local accumulators, neighbour lists, cluster-sorted points
@@ -1161,12 +1319,26 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     Rbits[0].zero(c->stream);
   }
   if (persistent && c->nranks > 1) acc_red.alloc(words);
+  if (hamerly) {  // neighbour lists of the centres, as in the small-d pruned passes
+    Rbits[0].alloc(s);
+    Rbits[1].alloc(s);
+    nlist.alloc((size_t)s * KM_LMAX);
+    ncc.alloc((size_t)s * KM_LMAX);
+    nlen.alloc(s);
+    lthr.alloc(s);
+    cl.alloc(s);
+    maxmove.alloc(1);
+    maxmove.zero(c->stream);
+    Rbits[0].zero(c->stream);
+  }
   int cur = 0;              // which sorted buffer is live
   bool have_sorted = false;
   int64_t moved_since_sort = 0, moved_base = 0;  // assignments changed (all ranks) since the last sort
   DevBuf<long long> kstate(2);
   kstate.zero(c->stream);
   int rsel = 0;  // Rbits[rsel]: radii gathered during the previous pass
+  int filt_pause = 0, filt_backoff = KM_CHECK;  // large-d bound filter: passes left without it / next pause length
+  bool last_filtered = false;
   auto resort = [&]() {
     // counting sort by cluster of the current assignment (local counts live in acc)
     StageScope st(c, "kmeans_sort");
@@ -1298,12 +1470,38 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     } else if (dmma) {
       to_rowmajor_run(c, C, s, s, d, dp, Cr.p);
       und_count.zero(c->stream);
-      dist_select_run(c, Xr.p, n_local, Cr.p, s, dp, cn.p, 1, 4.0 * Delta, nullptr, newa.p, n_local, und_count.p,
-                      und_list.p);
-      FLGP_LAUNCH(c, kmeans_exact_rows_kernel, c->sm_count * 4, 256, sizeof(double) * d, X, ldx, d, C2.p, cn.p, s,
-                  und_count.p, und_list.p, newa.p);
-      FLGP_LAUNCH(c, kmeans_commit_rows_kernel, c->sm_count * 8, 256, 0, Xr.p, n_local, d, dp, newa.p, assign, s, fx,
-                  uacc);
+      // pass 1 evaluates every row; so does a pass while the filter is paused (it is paused, with doubling back-off,
+      // whenever more than half of the rows survive it: on data without low-dimensional structure the bound test,
+      // the tightening and the gather then cost more than they save).  A full evaluation refreshes every bound, so
+      // the filter can resume at any pass.
+      const bool filtered = hamerly && it > 1 && filt_pause == 0;
+      if (filt_pause > 0) --filt_pause;
+      last_filtered = filtered;
+      const double* rows = Xr.p;
+      const int32_t* surv = nullptr;
+      if (filtered) {
+        hnsurv.zero(c->stream);
+        FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rbits[rsel].p, hmove.p, eta, nlist.p, ncc.p, nlen.p,
+                    lthr.p, cl.p, maxmove.p, Rbits[1 - rsel].p);
+        FLGP_LAUNCH(c, kmeans_hbounds_kernel, c->sm_count * 8, 256, 0, X, n_local, ldx, d, C2.p, cn.p, s, assign, cl.p,
+                    eta, Moff, delta2, hxn.p, hUB.p, hLB.p, hsurv.p, hnsurv.p);
+        FLGP_LAUNCH(c, kmeans_gather_rows_kernel, c->sm_count * 8, 256, 0, Xr.p, dp, hsurv.p, hnsurv.p, Xsv.p);
+        rows = Xsv.p;
+        surv = hsurv.p;
+      } else {
+        const int all = (int)n_local;
+        FLGP_CUDA(cudaMemcpyAsync(hnsurv.p, &all, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if (hamerly) FLGP_CUDA(cudaMemsetAsync(Rbits[rsel].p, 0, sizeof(unsigned long long) * s, c->stream));
+      }
+      dist_select_run(c, rows, n_local, Cr.p, s, dp, cn.p, 1, 4.0 * Delta, nullptr, newa.p, n_local, und_count.p,
+                      und_list.p, filtered ? hnsurv.p : nullptr, hvals.p);
+      FLGP_LAUNCH(c, kmeans_exact_rows2_kernel, c->sm_count * 4, 256, sizeof(double) * d, X, ldx, d, C2.p, cn.p, s,
+                  und_count.p, und_list.p, surv, newa.p, hvals.p);
+      // radii: pass 1 collects them into Rbits[rsel]; a filtered pass into the buffer its lists kernel initialised
+      unsigned long long* Rw = hamerly ? (filtered ? Rbits[1 - rsel].p : Rbits[rsel].p) : nullptr;
+      FLGP_LAUNCH(c, kmeans_hcommit_kernel, c->sm_count * 8, 256, 0, rows, d, dp, surv, hnsurv.p, newa.p, hvals.p, hxn.p,
+                  assign, s, fx, uacc, Moff, delta2, hUB.p, hLB.p, Rw);
+      if (filtered) rsel = 1 - rsel;
     } else {
       int grid = ceil_div(n_local, KT_TP);
       if (grid > 0)
@@ -1317,16 +1515,31 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
     if (pruned) maxmove.zero(c->stream);
-    if (small)
+    if (small) {
       FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
                   pruned ? maxmove.p : nullptr, it, kstate.p);
-    else
+    } else {
+      if (hamerly)
+        FLGP_CUDA(cudaMemcpyAsync(Cold.p, C, sizeof(double) * (size_t)s * d, cudaMemcpyDeviceToDevice, c->stream));
       FLGP_LAUNCH(c, kmeans_update_wide_kernel, ceil_div((int64_t)s * d, 256), 256, 0, red, s, d, fx, C, sizes, it,
                   kstate.p);
+      if (hamerly) {
+        FLGP_LAUNCH(c, kmeans_move_kernel, ceil_div((int64_t)s * 32, 256), 256, 0, C, Cold.p, s, d, hmove.p);
+        FLGP_LAUNCH(c, kmeans_move_max_kernel, 1, 256, 0, hmove.p, s, hmm.p, maxmove.p);
+      }
+    }
     // one host round trip per KM_CHECK passes (and after the first, which decides about the sorted layout)
-    if (it == 1 || it % KM_CHECK == 0 || it == iter_max) {
+    if (it == 1 || it % KM_CHECK == 0 || it == iter_max || (hamerly && it == 3)) {
       FLGP_CUDA(cudaMemcpyAsync(c->pinned, kstate.p, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+      if (hamerly) FLGP_CUDA(cudaMemcpyAsync(c->pinned + 2, hnsurv.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
       sync(c);
+      if (hamerly && last_filtered) {
+        const int nsv = *reinterpret_cast<const int*>(c->pinned + 2);
+        if ((int64_t)nsv * 2 > n_local) {
+          filt_pause = filt_backoff;
+          filt_backoff = std::min(filt_backoff * 2, 64);
+        }
+      }
       moved_since_sort = c->pinned[1] - moved_base;
       if (c->pinned[0] != 0) {  // no assignment changed anywhere in pass pinned[0]
         it = (int)c->pinned[0];

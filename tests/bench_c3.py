@@ -14,9 +14,14 @@ a = [int(v) for v in sys.argv[1:]]
 n, d, s, r, K, iter_max = (a + [70000, 784, 1000, 5, 200, 20][len(a):])[:6]
 m = 1000
 rng = np.random.default_rng(3)
-means = 3.0 * rng.standard_normal((10, d))
-lab = rng.integers(0, 10, n)
-X = np.asfortranarray(means[lab] + rng.standard_normal((n, d)))
+if d == 16:  # BASELINE config 5's data: a 2-torus embedded in 16 dimensions + N(0, 0.01^2)
+    a_, b_ = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    Q_, _ = np.linalg.qr(rng.standard_normal((d, 4)))
+    X = np.asfortranarray(np.c_[np.cos(a_), np.sin(a_), np.cos(b_), np.sin(b_)] @ Q_.T + 0.01 * rng.standard_normal((n, d)))
+else:  # BASELINE config 3's data: 10 Gaussian classes
+    means = 3.0 * rng.standard_normal((10, d))
+    lab = rng.integers(0, 10, n)
+    X = np.asfortranarray(means[lab] + rng.standard_normal((n, d)))
 init = np.sort(rng.choice(n, s, replace=False)).astype(np.int32)
 ctx = F.default_ctx()
 ctx.set_timing(True)

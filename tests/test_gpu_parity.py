@@ -454,6 +454,25 @@ def test_kmeans_large_d_tensor_core_bitexact(flgp, oracle, n, d, s, monkeypatch)
     assert it2 == iters and np.array_equal(a2, assign) and np.array_equal(U2, U)
 
 
+def test_kmeans_large_d_bound_filter_many_passes(flgp, oracle, monkeypatch):
+    """Config 5's data type (2-torus in 16 dimensions + noise) over many Lloyd passes: from pass 2 on most rows are
+    skipped by their Hamerly bounds (neighbour-list-local decay) and only the survivors reach the tensor-core
+    evaluation; centres, sizes, assignments and the iteration count must stay the brute-force oracle's bit for bit,
+    and equal to the unfiltered run (FLGP_NO_HAMERLY)."""
+    rng = np.random.default_rng(16)
+    n, d, s = 20000, 16, 128
+    a, b = rng.uniform(0, 2 * np.pi, n), rng.uniform(0, 2 * np.pi, n)
+    Q, _ = np.linalg.qr(rng.standard_normal((d, 4)))
+    X = np.asfortranarray(np.c_[np.cos(a), np.sin(a), np.cos(b), np.sin(b)] @ Q.T + 0.01 * rng.standard_normal((n, d)))
+    init = _init(n, s, 12)
+    U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=60, return_info=True)
+    Uo, ao, io = oracle.kmeans_lloyd(X, s, init, 60, NT)
+    assert iters == io and np.array_equal(assign, ao) and np.array_equal(U, Uo)
+    monkeypatch.setenv("FLGP_NO_HAMERLY", "1")
+    U2, a2, it2 = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, iter_max=60, return_info=True)
+    assert it2 == iters and np.array_equal(a2, assign) and np.array_equal(U2, U)
+
+
 def test_large_d_ties_take_the_exact_fallback(flgp, oracle):
     """Lattice data in d = 6 with duplicated centres / anchors: no row can be certified by the tensor-core
     selection (exact ties), every one is re-done in the oracle's order; results still bit-exact."""
