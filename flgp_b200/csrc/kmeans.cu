@@ -824,7 +824,7 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
                     const double* __restrict__ move, double eta, int32_t* __restrict__ list_j,
                     double* __restrict__ list_cc, int32_t* __restrict__ len, double* __restrict__ lthr,
                     double4* __restrict__ cl, const unsigned long long* __restrict__ maxmove_bits,
-                    unsigned long long* __restrict__ Rcur) {
+                    unsigned long long* __restrict__ Rcur, float4* __restrict__ clf = nullptr) {
   __shared__ double kcc[KM_LMAX];
   __shared__ int kj[KM_LMAX];
   __shared__ int count;
@@ -866,7 +866,9 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   if (cnt > KM_LMAX) {  // no list: every centre counts as a neighbour
     if (tid == 0) {
       len[a] = -1;
-      cl[a] = make_double4(move[a], __longlong_as_double((long long)*maxmove_bits), INFINITY, 0.0);
+      const double mm_ = __longlong_as_double((long long)*maxmove_bits);
+      cl[a] = make_double4(move[a], mm_, INFINITY, 0.0);
+      if (clf) clf[a] = make_float4(__double2float_ru(move[a]), __double2float_ru(mm_), INFINITY, 0.f);
     }
     return;
   }
@@ -905,6 +907,8 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   if (tid == 0) {
     for (int w = 1; w < 8; ++w) mv = fmax(mv, smv[w]);
     cl[a] = make_double4(move[a], mv, thr, 0.0);
+    // the streaming bound test works in single precision with directed rounding (moves up, radius down)
+    if (clf) clf[a] = make_float4(__double2float_ru(move[a]), __double2float_ru(mv), __double2float_rd(thr), 0.f);
     len[a] = cnt;
   }
 }
@@ -1035,7 +1039,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
 constexpr int KM_BT = 256, KM_BQ = 8;  // threads per CTA, points per thread
 
 __global__ void __launch_bounds__(KM_BT)
-kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* __restrict__ cl, double eta,
+kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const float4* __restrict__ cl, float eta_up,
                      float2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
                      unsigned long long* __restrict__ nskip) {
   __shared__ KmWork wl[KM_BT * KM_BQ];
@@ -1061,14 +1065,15 @@ kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const double4* _
     bool need = false;
     double l = 0.0;
     if (valid) {
-      const double4 ca = cl[as_in[q]];
-      // stored bounds are floats rounded outwards (u up, l down): half the traffic of this HBM-bound kernel; the
-      // decision is taken on the values as they will be stored
-      const float2 nb = km_pack(((double)ul_in[q].x + ca.x) * (1.0 + 1e-15),
-                                fmin(((double)ul_in[q].y - ca.y) * (1.0 - 1e-15) - 1e-300,
-                                     (ca.z - ((double)ul_in[q].x + ca.x) * (1.0 + 1e-7)) * (1.0 - 1e-15)));
+      const float4 ca = cl[as_in[q]];  // {move of c_a (rounded up), largest move in a's list (up), list radius (down)}
+      // stored bounds are floats rounded outwards (u up, l down): half the traffic of a double pair; the update is
+      // single-precision arithmetic with directed rounding (every step errs on the safe side) and the decision is
+      // taken on the values as they will be stored
+      float2 nb;
+      nb.x = __fadd_ru(ul_in[q].x, ca.x);
+      nb.y = fminf(__fsub_rd(ul_in[q].y, ca.y), __fsub_rd(ca.z, nb.x));
       l = (double)nb.y;
-      if ((double)nb.x + eta <= l) {
+      if (__fadd_ru(nb.x, eta_up) <= nb.y) {
         UL[p] = nb;
         ++skipped;
       } else {
@@ -1287,6 +1292,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   DevBuf<float2> UL[2];
   DevBuf<KmWork> work;
   DevBuf<double4> cl;
+  DevBuf<float4> clf;
   const bool prof_skip = std::getenv("FLGP_KMEANS_PROF") != nullptr;
   DevBuf<int> prof_hist(128);
   prof_hist.zero(c->stream);
@@ -1312,6 +1318,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     lthr.alloc(s);
     cl.alloc(s);
+    clf.alloc(s);
     maxmove.alloc(1);
     nskip.alloc(2);
     maxmove.zero(c->stream);
@@ -1380,7 +1387,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       unsigned long long* Rprev = Rbits[rsel].p;
       unsigned long long* Rcur = Rbits[1 - rsel].p;
       FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p, lthr.p, cl.p,
-                  maxmove.p, Rcur);
+                  maxmove.p, Rcur, clf.p);
       FLGP_CUDA(cudaMemsetAsync(nstrag.p, 0, sizeof(int), c->stream));
       if (n_local > 0) {
         // a grid-stride kernel over a device-side item count: exactly one resident wave (a partial second wave
@@ -1397,7 +1404,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
           pruned_per_sm[d] = std::max(nb, 1);
         }
         const int sgrid = c->sm_count * pruned_per_sm[d];
-        FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, cl.p, eta,
+        FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, clf.p,
+                    std::nextafterf((float)eta, INFINITY),  // eta rounded up
                     UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr);
 #define FLGP_PRUNED(D_)                                                                                          \
   FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs4[cur].p, rec.p, s, fx, as[cur].p, uacc,            \
