@@ -1036,7 +1036,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
 // score is strictly larger (eta^2 > 2 Delta) and the point keeps its centre - without its coordinates being read.
 // The points that fail are compacted (per CTA in shared memory, one global atomic per CTA) into the work list that
 // kmeans_assign_pruned evaluates.  cl[a] = {move, nbmove, lthr, -}.
-constexpr int KM_BT = 256, KM_BQ = 8;  // threads per CTA, points per thread
+constexpr int KM_BT = 256, KM_BQ = 4;  // threads per CTA, points per thread
 
 __global__ void __launch_bounds__(KM_BT)
 kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const float4* __restrict__ cl, float eta_up,
