@@ -25,3 +25,19 @@ H = O.hk_from_spectrum(V, values, meta["K"], 2.0, np.arange(20, dtype=np.int32),
 np.savez_compressed(os.path.join(os.path.dirname(__file__), "oracle_small.npz"), meta=json.dumps(meta), init=init,
                     U=U, assign=assign, ind=ind, Zj=Zj, Zx=Zx, values=values, H=H)
 print("wrote oracle_small.npz", meta)
+
+# ---- second fixture: training objective, optimiser, SE grid, Nystrom driver (the round's widening rows) -------------
+m = 120
+idx = np.arange(m, dtype=np.int32)
+obj_m, grad_m = O.regression_objective(V, values, Y[:m], idx, meta["K"], (6.0, 0.4), 1e-5, "marginal")
+obj_p, grad_p = O.regression_objective(V, values, Y[:m], idx, meta["K"], (6.0, 0.4), 1e-5, "posterior")
+obj_s, grad_s = O.regression_objective(V, values, Y[:8], idx[:8], meta["K"], (6.0, 0.4), 1e-5, "posterior")  # m <= K
+pars, obj_t = O.train_regression(V, values, Y[:m], idx, meta["K"], 1e-5, "posterior")
+a2s = np.array([0.3, 1.0, 3.0])
+se = O.fit_se_regression(X[:m], Y[:m], X[m:], meta["s"], meta["r"], meta["K"], init, a2s, pars=(6.0, 0.4), iter_max=30)
+ny = O.fit_nystrom_regression(X[:m], Y[:m], X[m:], meta["s"], meta["K"], init, a2s, pars=(6.0, 0.4), iter_max=30)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "oracle_train.npz"), m=m, a2s=a2s,
+                    obj=np.array([obj_m, obj_p, obj_s]), grad=np.array([grad_m, grad_p, grad_s]), pars=pars, obj_t=obj_t,
+                    se_a2=se["a2"], se_obj=se["obj"], se_test=se["test"][:200], se_cov=se["cov"][:200],
+                    ny_a2=ny["a2"], ny_obj=ny["obj"], ny_test=ny["test"][:200], ny_cov=ny["cov"][:200])
+print("wrote oracle_train.npz: pars", pars, "se a2", se["a2"], "nystrom a2", ny["a2"])

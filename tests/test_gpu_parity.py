@@ -638,3 +638,43 @@ def test_fit_nystrom_regression(flgp, oracle, n, d, m, s, K):
         assert res["a2"] == ref["a2"]
         np.testing.assert_allclose(res["pars"], ref["pars"], rtol=1e-3)
         np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-3, atol=1e-3 * scale)
+
+
+# ------------------------------------------------------------------------------------------- committed golden fixtures
+def test_cuda_path_against_golden_fixtures(flgp):
+    """The CUDA path against the committed fixtures of tests/golden/ directly (no oracle call at run time): k-means,
+    KNN, Z, eigenvalues (oracle_small.npz); training objective, trained pars, SE grid and Nystrom driver
+    (oracle_train.npz)."""
+    import json
+    import os
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g0 = np.load(os.path.join(gold, "oracle_small.npz"))
+    g = np.load(os.path.join(gold, "oracle_train.npz"))
+    meta = json.loads(str(g0["meta"]))
+    X, Y = spiral(meta["n"], meta["seed"])
+    init, s, r, K, m = g0["init"], meta["s"], meta["r"], meta["K"], int(g["m"])
+    U, assign, iters = flgp.subsample_cpp(X, s, "kmeans", init_idx=init, return_info=True)
+    assert iters == meta["iters"] and np.array_equal(assign, g0["assign"]) and np.array_equal(U, g0["U"])
+    assert np.array_equal(flgp.KNN_cpp(X, np.asfortranarray(U[:, :2]), r)["ind_knn"], g0["ind"])
+    Zj, Zx = _csr_parts(flgp.cross_similarity_lae_cpp(X, U, r, "cluster-normalized"))
+    assert np.array_equal(Zj, g0["Zj"]) and np.array_equal(Zx, g0["Zx"])
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init)
+    np.testing.assert_allclose(ep.values, g0["values"], rtol=1e-8)
+    for q, (mm, ap) in enumerate([(m, "marginal"), (m, "posterior"), (8, "posterior")]):
+        f, gr = flgp.regression_objective(ep, Y[:mm], mm, K, (6.0, 0.4), 1e-5, ap)
+        np.testing.assert_allclose(f, g["obj"][q], rtol=1e-8)
+        np.testing.assert_allclose(gr, g["grad"][q], rtol=1e-6, atol=1e-7)
+    x, obj, _ = flgp.train_regression_gp(ep, Y[:m], m, K, 1e-5, "posterior")
+    np.testing.assert_allclose(x, g["pars"], rtol=1e-3)
+    np.testing.assert_allclose(obj, g["obj_t"], rtol=1e-6)
+    se = flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, a2s=g["a2s"], pars=(6.0, 0.4), init_idx=init,
+                                        iter_max=30)
+    assert se["a2"] == float(g["se_a2"])
+    np.testing.assert_allclose(se["Y_pred"]["test"][:200], g["se_test"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(se["posterior"]["cov"][:200], g["se_cov"], rtol=1e-7, atol=1e-9)
+    ny = flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, K, a2s=g["a2s"], pars=(6.0, 0.4), init_idx=init,
+                                             iter_max=30)
+    assert ny["a2"] == float(g["ny_a2"])
+    np.testing.assert_allclose(ny["Y_pred"]["test"][:200], g["ny_test"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(ny["posterior"]["cov"][:200], g["ny_cov"], rtol=1e-6, atol=1e-8)

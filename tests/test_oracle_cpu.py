@@ -267,3 +267,33 @@ def test_nystrom_oracle_is_a_sane_regressor(oracle):
     assert res["a2"] in (0.5, 2.0) and np.isfinite(res["obj"])
     assert np.all(np.isfinite(res["test"])) and np.all(res["cov"] > 0)
     assert np.sqrt(np.mean((res["test"] - Y[m:]) ** 2)) < 0.7 * np.std(Y[m:])  # labels carry N(0,1) noise
+
+
+def test_golden_fixture_training_rows(oracle):
+    """The round's widening rows (training objective, MMA optimiser, SE grid, Nystrom driver) pinned by the committed
+    fixture tests/golden/oracle_train.npz (same generator script; guards the oracle against drift)."""
+    g0 = np.load(os.path.join(GOLD, "oracle_small.npz"))
+    g = np.load(os.path.join(GOLD, "oracle_train.npz"))
+    meta = json.loads(str(g0["meta"]))
+    X, Y = spiral(meta["n"], meta["seed"])
+    init, m, K = g0["init"], int(g["m"]), meta["K"]
+    U, _, _ = oracle.kmeans_lloyd(X, meta["s"], init)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, meta["r"], "cluster-normalized")
+    values, V = oracle.spectrum_from_Z(Zj, Zx, meta["s"], K, True)
+    idx = np.arange(m, dtype=np.int32)
+    cases = [(Y[:m], idx, "marginal"), (Y[:m], idx, "posterior"), (Y[:8], idx[:8], "posterior")]
+    for q, (yy, ii, ap) in enumerate(cases):
+        f, gr = oracle.regression_objective(V, values, yy, ii, K, (6.0, 0.4), 1e-5, ap)
+        np.testing.assert_allclose(f, g["obj"][q], rtol=1e-9)
+        np.testing.assert_allclose(gr, g["grad"][q], rtol=1e-7, atol=1e-9)
+    pars, obj_t = oracle.train_regression(V, values, Y[:m], idx, K, 1e-5, "posterior")
+    np.testing.assert_allclose(pars, g["pars"], rtol=1e-6)
+    np.testing.assert_allclose(obj_t, g["obj_t"], rtol=1e-8)
+    se = oracle.fit_se_regression(X[:m], Y[:m], X[m:], meta["s"], meta["r"], K, init, g["a2s"], pars=(6.0, 0.4), iter_max=30)
+    assert se["a2"] == float(g["se_a2"])
+    np.testing.assert_allclose(se["test"][:200], g["se_test"], rtol=1e-8, atol=1e-9)
+    np.testing.assert_allclose(se["cov"][:200], g["se_cov"], rtol=1e-8, atol=1e-10)
+    ny = oracle.fit_nystrom_regression(X[:m], Y[:m], X[m:], meta["s"], K, init, g["a2s"], pars=(6.0, 0.4), iter_max=30)
+    assert ny["a2"] == float(g["ny_a2"])
+    np.testing.assert_allclose(ny["test"][:200], g["ny_test"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(ny["cov"][:200], g["ny_cov"], rtol=1e-7, atol=1e-9)
