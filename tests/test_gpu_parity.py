@@ -678,3 +678,50 @@ def test_cuda_path_against_golden_fixtures(flgp):
     assert ny["a2"] == float(g["ny_a2"])
     np.testing.assert_allclose(ny["Y_pred"]["test"][:200], g["ny_test"], rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(ny["posterior"]["cov"][:200], g["ny_cov"], rtol=1e-6, atol=1e-8)
+
+
+# ------------------------------------------------------------------------------------------- edge shapes of the new paths
+@pytest.mark.parametrize("n,d,s,r,K", [(130, 16, 64, 5, 64), (64, 5, 64, 1, 10), (200, 9, 65, 5, 65), (97, 33, 64, 4, 7)])
+def test_large_d_minimum_shapes(flgp, oracle, n, d, s, r, K):
+    """Smallest shapes that still take the tensor-core path (n >= 64, s >= 64), K = s, r = 1, ragged last tiles."""
+    rng = np.random.default_rng(n + d)
+    X = np.asfortranarray(rng.standard_normal((n, d)) * 2.0 + rng.integers(0, 3, (n, 1)))
+    init = _init(n, s, 2)
+    m = 20
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=6)
+    vo, Vo, I = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init, nthreads=NT, want_internals=True, iter_max=6)
+    assert ep.kmeans_iters == I["iters"] and np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-9)
+
+
+@pytest.mark.parametrize("gl", ["rw", "normalized"])
+def test_fit_se_regression_other_laplacians_and_errors(flgp, oracle, gl):
+    X, Y = spiral(1500, 13)
+    m, s, r, K = 100, 80, 3, 20
+    init = _init(len(X), s, 7)
+    a2s = np.array([0.5, 2.0])
+    res = flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, a2s=a2s, pars=(5.0, 0.3), models=dict(gl=gl),
+                                         init_idx=init, iter_max=20)
+    ref = oracle.fit_se_regression(X[:m], Y[:m], X[m:], s, r, K, init, a2s, gl=gl, pars=(5.0, 0.3), iter_max=20,
+                                   nthreads=NT)
+    assert res["a2"] == ref["a2"]
+    np.testing.assert_allclose(res["Y_pred"]["test"], ref["test"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-7, atol=1e-9)
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, approach="evidence", init_idx=init)
+    with pytest.raises(flgp.FlgpError, match="illegal"):
+        flgp.fit_se_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, noise="none", init_idx=init)
+    with pytest.raises(flgp.FlgpError):
+        flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, s + 1, init_idx=init)   # K > s
+
+
+def test_nystrom_random_anchors_and_K_equals_s(flgp, oracle):
+    """subsample="random" anchors (no k-means) and K = s through the Nystrom driver: finite, positive variances."""
+    X, Y = spiral(900, 3)
+    m, s = 60, 40
+    init = _init(len(X), s, 1)
+    res = flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, -1, a2s=[1.0], pars=(4.0, 0.5), subsample="random",
+                                              init_idx=init)
+    assert np.all(np.isfinite(res["Y_pred"]["test"])) and np.all(res["posterior"]["cov"] > 0)
