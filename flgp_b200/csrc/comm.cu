@@ -99,6 +99,15 @@ void comm_allreduce_i64(Ctx* c, int64_t* d, size_t count) {
   if (c->nranks == 1 || count == 0) return;
   FLGP_NCCL(c->nccl, c->nccl->AllReduce(d, d, count, ncclInt64, ncclSum, c->nccl->comm, c->stream));
 }
+// out of place: dst = sum over ranks of src (src untouched)
+void comm_allreduce_i64_to(Ctx* c, const int64_t* src, int64_t* dst, size_t count) {
+  if (count == 0) return;
+  if (c->nranks == 1) {
+    if (dst != src) FLGP_CUDA(cudaMemcpyAsync(dst, src, sizeof(int64_t) * count, cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
+  FLGP_NCCL(c->nccl, c->nccl->AllReduce(src, dst, count, ncclInt64, ncclSum, c->nccl->comm, c->stream));
+}
 void comm_allreduce_f64(Ctx* c, double* d, size_t count) {
   if (c->nranks == 1 || count == 0) return;
   FLGP_NCCL(c->nccl, c->nccl->AllReduce(d, d, count, ncclFloat64, ncclSum, c->nccl->comm, c->stream));

@@ -151,6 +151,7 @@ struct StageScope {
 
 // ---- collectives (comm.cu): no-ops when nranks == 1 ---------------------------------------------
 void comm_allreduce_i64(Ctx* c, int64_t* dbuf, size_t count);
+void comm_allreduce_i64_to(Ctx* c, const int64_t* src, int64_t* dst, size_t count);  // out of place
 void comm_allreduce_f64(Ctx* c, double* dbuf, size_t count);
 void comm_allreduce_max_f64(Ctx* c, double* dbuf, size_t count);
 void comm_destroy(Ctx* c);

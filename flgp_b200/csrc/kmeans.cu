@@ -824,12 +824,30 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
                     const double* __restrict__ move, double eta, int32_t* __restrict__ list_j,
                     double* __restrict__ list_cc, int32_t* __restrict__ len, double* __restrict__ lthr,
                     double4* __restrict__ cl, const unsigned long long* __restrict__ maxmove_bits,
-                    unsigned long long* __restrict__ Rcur, float4* __restrict__ clf = nullptr) {
+                    unsigned long long* __restrict__ Rcur, float4* __restrict__ clf = nullptr,
+                    double* __restrict__ rec = nullptr, int str = 0, double M = 0.0,
+                    long long* __restrict__ zero_changed = nullptr, int* __restrict__ zero_count = nullptr) {
   __shared__ double kcc[KM_LMAX];
   __shared__ int kj[KM_LMAX];
   __shared__ int count;
   const int a = blockIdx.x, tid = threadIdx.x;
   if (tid == 0) count = 0;
+  // folded into this launch (a pruned pass is ~10 short launches otherwise; at 8 GPUs their host cost shows): the
+  // centre's score record (kmeans_prep_kernel) and the zeroing of the pass's counters
+  if (rec && tid == 32) {
+    double acc2 = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double cc = C[a + (size_t)s * k];
+      acc2 = fma(cc, cc, acc2);
+      rec[(size_t)a * str + k] = -2.0 * cc;
+    }
+    rec[(size_t)a * str + d] = __dadd_rn(acc2, M);
+    for (int k = d + 1; k < str; ++k) rec[(size_t)a * str + k] = 0.0;
+  }
+  if (a == 0 && tid == 64) {
+    if (zero_changed) *zero_changed = 0;
+    if (zero_count) *zero_count = 0;
+  }
   for (int t = tid; t < KM_LMAX; t += 256) {
     kcc[t] = INFINITY;
     kj[t] = 0x7fffffff;
@@ -1041,12 +1059,13 @@ constexpr int KM_BT = 256, KM_BQ = 4;  // threads per CTA, points per thread
 __global__ void __launch_bounds__(KM_BT)
 kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const float4* __restrict__ cl, float eta_up,
                      float2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
-                     unsigned long long* __restrict__ nskip) {
+                     unsigned long long* __restrict__ nskip, unsigned long long* __restrict__ zero_maxmove) {
   __shared__ KmWork wl[KM_BT * KM_BQ];
   __shared__ int wcount, wbase;
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t c0 = (int64_t)blockIdx.x * (KM_BT * KM_BQ);
   if (tid == 0) wcount = 0;
+  if (blockIdx.x == 0 && tid == 1 && zero_maxmove) *zero_maxmove = 0;  // read by the lists kernel before, written by the update after
   __syncthreads();
   float2 ul_in[KM_BQ];
   int as_in[KM_BQ];
@@ -1371,9 +1390,12 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   while (it < iter_max) {
     ++it;
     const bool brute = !pruned || it == 1;
+    const bool fused_pass = small && !brute;  // pruned pass: record, counters are handled inside its own kernels
     if (brute && !(dmma && it > 1)) acc.zero(c->stream);
-    else FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
-    if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
+    else if (!fused_pass)
+      FLGP_CUDA(cudaMemsetAsync(acc.p + (words - 1), 0, sizeof(long long), c->stream));  // the `changed` slot
+    if (fused_pass) {
+    } else if (small) FLGP_LAUNCH(c, kmeans_prep_kernel, ceil_div(s, 128), 128, 0, C, s, d, str, Moff, rec.p);
     else {
       FLGP_LAUNCH(c, kmeans_prep_c2_kernel, ceil_div((int64_t)s * d, 256), 256, 0, C, (size_t)s * d, C2.p);
       FLGP_LAUNCH(c, kmeans_prep_cn_kernel, ceil_div(s, 64), 64, 0, C, s, d, Moff, cn.p);
@@ -1387,8 +1409,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       unsigned long long* Rprev = Rbits[rsel].p;
       unsigned long long* Rcur = Rbits[1 - rsel].p;
       FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p, lthr.p, cl.p,
-                  maxmove.p, Rcur, clf.p);
-      FLGP_CUDA(cudaMemsetAsync(nstrag.p, 0, sizeof(int), c->stream));
+                  maxmove.p, Rcur, clf.p, rec.p, str, Moff, acc.p + (words - 1), nstrag.p);
+      if (n_local == 0) maxmove.zero(c->stream);  // otherwise the bound-test kernel does it
       if (n_local > 0) {
         // a grid-stride kernel over a device-side item count: exactly one resident wave (a partial second wave
         // would run with most SMs idle; ncu: 1.6 waves at the former sm_count * 8)
@@ -1406,7 +1428,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
         const int sgrid = c->sm_count * pruned_per_sm[d];
         FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, clf.p,
                     std::nextafterf((float)eta, INFINITY),  // eta rounded up
-                    UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr);
+                    UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr, maxmove.p);
 #define FLGP_PRUNED(D_)                                                                                          \
   FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs4[cur].p, rec.p, s, fx, as[cur].p, uacc,            \
               nlist.p, ncc.p, nlen.p, Moff, delta2, eta, Rcur, work.p, nstrag.p, lthr.p, UL[cur].p,               \
@@ -1517,12 +1539,13 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     }
     kst.stop();
     long long* red = acc.p;
-    if (persistent && c->nranks > 1) {  // keep the local sums intact; reduce a copy
-      FLGP_CUDA(cudaMemcpyAsync(acc_red.p, acc.p, sizeof(long long) * words, cudaMemcpyDeviceToDevice, c->stream));
+    if (persistent && c->nranks > 1) {  // keep the local sums intact: reduce out of place
       red = acc_red.p;
+      comm_allreduce_i64_to(c, reinterpret_cast<const int64_t*>(acc.p), reinterpret_cast<int64_t*>(red), words);
+    } else {
+      comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
     }
-    comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
-    if (pruned) maxmove.zero(c->stream);
+    if (pruned && brute) maxmove.zero(c->stream);  // a pruned pass zeroes it in its bound-test kernel
     if (small) {
       FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
                   pruned ? maxmove.p : nullptr, it, kstate.p);
