@@ -126,7 +126,8 @@ lae_small_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, const dou
   add_stats(stats, it, bt);
 }
 
-template <bool ROWMAJOR>
+// RT > 0: compile-time r (the solver's r x r state then lives in registers instead of LAE_RMAX-sized local arrays)
+template <bool ROWMAJOR, int RT>
 __global__ void __launch_bounds__(128)
 lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ U,
                    int64_t ldu, int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj,
@@ -147,11 +148,11 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
       Ur.ldu = ldu;
       for (int a = 0; a < r; ++a) Ur.c[a] = ind[i + n * a];
     }
-    double z[LAE_RMAX];
-    const LaeStats ls = lae_solve<0, 0>(r, d, x, Ur, z, g_lae_alpha);
+    double z[RT ? RT : LAE_RMAX];
+    const LaeStats ls = lae_solve<RT, 0>(r, d, x, Ur, z, g_lae_alpha);
     it = ls.iters;
     bt = ls.backtracks;
-    write_row<LAE_RMAX>(r, Ur.c, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
+    write_row<(RT ? RT : LAE_RMAX)>(r, Ur.c, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
   }
   add_stats(stats, it, bt);
 }
@@ -165,6 +166,7 @@ lae_generic_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, 
 // Dynamic shared memory per warp: x (d) + products (d) + UUt / xUt (LAE_RMAX^2 + LAE_RMAX).
 constexpr int LW_EXTRA = LAE_RMAX * LAE_RMAX + LAE_RMAX;
 
+template <int RT>
 __global__ void __launch_bounds__(256)
 lae_warp_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, const double* __restrict__ Ur, int64_t ldu,
                 int r, const int32_t* __restrict__ ind, int32_t* __restrict__ Zj, double* __restrict__ Zx,
@@ -228,11 +230,16 @@ lae_warp_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, con
       }
     }
     __syncwarp();
-    double UUt[LAE_RMAX * LAE_RMAX], xUt[LAE_RMAX];
-    for (int a = 0; a < r; ++a) {
-      xUt[a] = xu[a];
-      for (int b = 0; b < r; ++b) UUt[a * LAE_RMAX + b] = uu[a * LAE_RMAX + b];
-    }
+    constexpr int RA = RT ? RT : LAE_RMAX;  // row stride lae_iterate<RT> expects
+    double UUt[RA * RA], xUt[RA];
+#pragma unroll
+    for (int a = 0; a < RA; ++a)
+      if (a < r) {
+        xUt[a] = xu[a];
+#pragma unroll
+        for (int b = 0; b < RA; ++b)
+          if (b < r) UUt[a * RA + b] = uu[a * LAE_RMAX + b];
+      }
     auto objective = [&](const double* w) {
       __syncwarp();
       for (int k = lane; k < d; k += 32) {
@@ -254,12 +261,12 @@ lae_warp_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, con
       for (; k < d; ++k) sq = sq + ps[k];
       return sq / 2.0;
     };
-    double z[LAE_RMAX];
-    const LaeStats ls = lae_iterate<0>(r, UUt, xUt, objective, z, g_lae_alpha);
+    double z[RA];
+    const LaeStats ls = lae_iterate<RT>(r, UUt, xUt, objective, z, g_lae_alpha);
     if (lane == 0) {
       it_tot += ls.iters;
       bt_tot += ls.backtracks;
-      write_row<LAE_RMAX>(r, col, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
+      write_row<RA>(r, col, z, perm ? (int64_t)perm[i] : i, n, Zj, Zx, Wd);
     }
   }
   add_stats(stats, it_tot, bt_tot);
@@ -335,11 +342,22 @@ void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
       DevBuf<double> Ur((size_t)s * d);
       to_rowmajor_run(c, U, s, ldu, d, d, Ur.p);
       const size_t smem = per_warp * warps;
-      if (smem > 40 * 1024)
-        FLGP_CUDA(cudaFuncSetAttribute(lae_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       const int wgrid = (int)std::min<int64_t>(ceil_div(n, warps), (int64_t)c->sm_count * 16);
-      FLGP_LAUNCH(c, lae_warp_kernel, wgrid, warps * 32, smem, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats,
-                  perm);
+#define LAE_WARP(R_)                                                                                               \
+  do {                                                                                                             \
+    if (smem > 40 * 1024)                                                                                          \
+      FLGP_CUDA(cudaFuncSetAttribute(lae_warp_kernel<R_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    FLGP_LAUNCH(c, lae_warp_kernel<R_>, wgrid, warps * 32, smem, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, \
+                stats, perm);                                                                                      \
+  } while (0)
+      switch (r) {
+        case 2: LAE_WARP(2); break;
+        case 3: LAE_WARP(3); break;
+        case 4: LAE_WARP(4); break;
+        case 5: LAE_WARP(5); break;
+        default: LAE_WARP(0); break;
+      }
+#undef LAE_WARP
       sync(c);  // Ur is released on return
       return;
     }
@@ -347,12 +365,20 @@ void lae_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, const doubl
   if (d >= 8) {  // medium rows: read the anchors from a row-major copy (sector reuse through L1)
     DevBuf<double> Ur((size_t)s * d);
     to_rowmajor_run(c, U, s, ldu, d, d, Ur.p);
-    FLGP_LAUNCH(c, lae_generic_kernel<true>, grid, 128, 0, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats,
-                perm);
+#define LAE_GEN(R_) \
+  FLGP_LAUNCH(c, (lae_generic_kernel<true, R_>), grid, 128, 0, X, n, ldx, d, Ur.p, (int64_t)d, r, ind, Zj, Zx, Wd, stats, perm)
+    switch (r) {
+      case 2: LAE_GEN(2); break;
+      case 3: LAE_GEN(3); break;
+      case 4: LAE_GEN(4); break;
+      case 5: LAE_GEN(5); break;
+      default: LAE_GEN(0); break;
+    }
+#undef LAE_GEN
     sync(c);  // Ur is released on return
     return;
   }
-  FLGP_LAUNCH(c, lae_generic_kernel<false>, grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats, perm);
+  FLGP_LAUNCH(c, (lae_generic_kernel<false, 0>), grid, 128, 0, X, n, ldx, d, U, ldu, r, ind, Zj, Zx, Wd, stats, perm);
 }
 
 void knn_to_csr_run(Ctx* c, int64_t n, int r, const int32_t* ind, const double* dist, int32_t* Zj, double* Zx,

@@ -179,7 +179,8 @@ def test_v_to_z_and_single_point(flgp, oracle):
 
 @pytest.mark.parametrize("n,d,s,r", [(4000, 2, 500, 3), (6000, 3, 300, 3), (3000, 3, 100, 5), (2000, 2, 80, 2),
                                       (2000, 3, 80, 4), (1500, 6, 60, 3), (1200, 3, 50, 7), (400, 784, 50, 5),
-                                      (900, 33, 40, 8), (700, 100, 30, 1), (500, 257, 64, 16), (800, 16, 64, 5)])
+                                      (900, 33, 40, 8), (700, 100, 30, 1), (500, 257, 64, 16), (800, 16, 64, 5),
+                                      (600, 16, 40, 2), (600, 40, 40, 3), (600, 12, 40, 4), (500, 64, 40, 4), (500, 9, 40, 3)])
 def test_lae_bitexact(flgp, oracle, n, d, s, r):
     rng = np.random.default_rng(n + r)
     if d == 2:
