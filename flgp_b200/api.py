@@ -633,3 +633,16 @@ def fit_nystrom_regression_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: floa
                                                _pf(xo), C.byref(a2), C.byref(obj)))
     return {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(xo),
             "a2": a2.value, "obj": obj.value}
+
+
+def posterior_distribution_classification(eigenpair: EigenPair, Y_local, m_total: int, K: int, t: float,
+                                          sigma: float = 1e-3, tol: float = 1e-5, max_iter: int = 100):
+    """posterior_distribution_classification (src/Utils.cpp:252-299) on a spectrum handle at a fixed diffusion time
+    t, as fit_lae_logit_gp_cpp calls it (src/Fit.cpp:563-582): Laplace posterior mean and variance of the latent
+    function at every local row (training rows first).  Returns (mean, cov)."""
+    Y_local = np.ascontiguousarray(Y_local, dtype=np.float64).reshape(-1)
+    mean = np.zeros(eigenpair.n_local)
+    cov = np.zeros(eigenpair.n_local)
+    check(eigenpair.ctx._lib.flgp_classification_posterior_fixed(eigenpair._h, _pf(Y_local), m_total, K, t, sigma, tol,
+                                                                 max_iter, _pf(mean), _pf(cov)))
+    return mean, cov

@@ -563,6 +563,122 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
   return best;
 }
 
+// ---- Laplace posterior of the binary GP classifier (posterior_distribution_classification,
+//      /root/reference/src/Utils.cpp:252-299; GPML algorithms 3.1 / 3.2) -------------------------------------------
+// Newton iterations on the m training points (host, m x m: m is the number of labelled points), from f = 0:
+//   pi = 1 / (1 + exp(-f)), W = pi (1 - pi), B = I + sqrt(W) C11 sqrt(W), b = W f + (Y - pi),
+//   a = b - sqrt(W) B^-1 sqrt(W) (C11 b), f <- C11 a, until |f - f_new|_1 < tol.
+// Returns pi (m) and beta = sqrt(W) B^-1 sqrt(W) (m x m, column-major) at the mode.
+void laplace_mode(const std::vector<double>& C11, const double* Y, int m, double tol, int max_iter,
+                  std::vector<double>& pi, std::vector<double>& beta) {
+  std::vector<double> f(m, 0.0), W(m), sw(m), b(m), cb(m), a(m), fn(m), B((size_t)m * m);
+  pi.assign(m, 0.5);
+  auto refresh = [&]() {
+    for (int i = 0; i < m; ++i) {
+      pi[i] = 1.0 / (1.0 + std::exp(-f[i]));
+      W[i] = pi[i] * (1.0 - pi[i]);
+      sw[i] = std::sqrt(W[i]);
+    }
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) B[i + (size_t)m * j] = (sw[i] * C11[i + (size_t)m * j]) * sw[j] + (i == j ? 1.0 : 0.0);
+    if (!chol_lower(B, m)) fail(2, "classification: the Newton system is not positive definite");
+  };
+  for (int iter = 0; iter < max_iter; ++iter) {
+    refresh();
+    for (int i = 0; i < m; ++i) b[i] = W[i] * f[i] + (Y[i] - pi[i]);
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += C11[i + (size_t)m * j] * b[j];
+      cb[i] = sw[i] * acc;
+    }
+    chol_solve(B, m, cb.data(), 1);
+    for (int i = 0; i < m; ++i) a[i] = b[i] - sw[i] * cb[i];
+    double diff = 0.0;
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += C11[i + (size_t)m * j] * a[j];
+      fn[i] = acc;
+      diff += std::fabs(f[i] - acc);
+    }
+    f = fn;
+    if (diff < tol) break;
+  }
+  refresh();
+  beta.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) beta[i + (size_t)m * i] = 1.0;
+  chol_solve(B, m, beta.data(), m);
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i) beta[i + (size_t)m * j] = (sw[i] * beta[i + (size_t)m * j]) * sw[j];
+}
+
+// The n-sized half on a spectrum handle, folded like the GPR tail (C21 = V2 Lam V1^T is never formed):
+//   mean_i = V_i . (Lam V1^T (Y - pi)),   cov_i = V_i (Lam - Lam V1^T beta V1 Lam) V_i^T + sigma
+void classification_posterior_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double t, double sigma,
+                                  double tol, int max_iter, double* mean, double* cov) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total && m_total <= 8192, "classification: need 1 <= m <= 8192 labelled rows");
+  const int s = sp->s, r = sp->r, KK = sp->K, m = (int)m_total;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1));
+  lift_rows_run(c, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  DevBuf<double> Vall((size_t)m * KK + m);
+  Vall.zero(c->stream);
+  if (m_local > 0) {
+    FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)m * KK + sp->row_offset, Ydev, sizeof(double) * m_local,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  }
+  comm_allreduce_f64(c, Vall.p, (size_t)m * KK + m);
+  std::vector<double> Vh((size_t)m * KK + m);
+  Vall.download(Vh.data(), Vh.size(), c->stream);
+  sync(c);
+  const double* Yh = Vh.data() + (size_t)m * KK;
+  auto V = [&](int i, int k) { return Vh[(size_t)i * KK + k]; };
+  std::vector<double> lam(K);
+  for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * (1.0 - sp->values[k]));
+  std::vector<double> C11((size_t)m * m);
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
+      C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
+    }
+  std::vector<double> pi, beta;
+  laplace_mode(C11, Yh, m, tol, max_iter, pi, beta);
+  std::vector<double> coef(KK, 0.0), Mq((size_t)KK * KK, 0.0), T1((size_t)m * K);
+  for (int k = 0; k < K; ++k) {
+    double acc = 0.0;
+    for (int i = 0; i < m; ++i) acc += V(i, k) * (Yh[i] - pi[i]);
+    coef[k] = lam[k] * acc;
+  }
+  for (int k = 0; k < K; ++k)  // T1 = beta V1 (m x K, column-major)
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += beta[i + (size_t)m * j] * V(j, k);
+      T1[i + (size_t)m * k] = acc;
+    }
+  for (int b2 = 0; b2 < K; ++b2)
+    for (int a2 = 0; a2 < K; ++a2) {
+      double acc = 0.0;
+      for (int i = 0; i < m; ++i) acc += V(i, a2) * T1[i + (size_t)m * b2];
+      Mq[a2 + (size_t)KK * b2] = (a2 == b2 ? lam[a2] : 0.0) - (lam[a2] * acc) * lam[b2];
+    }
+  DevBuf<double> dcoef(KK), dM((size_t)KK * KK);
+  dcoef.upload(coef.data(), KK, c->stream);
+  dM.upload(Mq.data(), (size_t)KK * KK, c->stream);
+  DevBuf<double> wv(s), T((size_t)s * KK), Bq((size_t)s * s);
+  gemv_run(c, sp->Wm.p, dcoef.p, s, KK, wv.p);
+  sparse_rowdot_run(c, sp->n_local, r, sp->Zj.p, sp->Zx.p, sp->w.p, wv.p, mean);
+  if (cov) {
+    gemm_nn_run(c, sp->Wm.p, dM.p, s, KK, KK, T.p);            // Mq is symmetric up to rounding: beta is
+    gemm_nt_run(c, T.p, sp->Wm.p, nullptr, s, s, KK, Bq.p, s);
+    sparse_quadform_run(c, sp->n_local, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, Bq.p, sigma, cov);
+  }
+  sync(c);
+}
+
 }  // namespace
 
 extern "C" {
@@ -1339,6 +1455,25 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
     std::memcpy(train, y.data(), sizeof(double) * m);
     if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
     if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
+int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
+                                        double sigma, double tol, int max_iter, double* mean, double* cov) {
+  return guard([&] {
+    need(h && Y_local && mean, "null argument");
+    Ctx* c = h->c;
+    const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
+    DevBuf<double> dY(std::max<int64_t>(m_local, 1)), dm(std::max<int64_t>(h->n_local, 1)),
+        dc(std::max<int64_t>(h->n_local, 1));
+    if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
+    classification_posterior_dev(h, dY.p, m_total, K, t, sigma, tol, max_iter > 0 ? max_iter : 100, dm.p,
+                                 cov ? dc.p : nullptr);
+    if (h->n_local > 0) {
+      dm.download(mean, h->n_local, c->stream);
+      if (cov) dc.download(cov, h->n_local, c->stream);
+    }
+    sync(c);
   });
 }
 

@@ -208,6 +208,14 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
                                 const char* approach, const char* subsample, int nstart, int iter_max,
                                 const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
                                 double* test, double* cov, double* pars_out, double* best_a2, double* best_obj);
+/* posterior_distribution_classification (src/Utils.cpp:252-299; exported, src/Utils.h:77-80) as the binary logit
+ * drivers call it (fit_lae_logit_gp_cpp, src/Fit.cpp:563-582) at a FIXED diffusion time t: Laplace approximation of
+ * the GP classifier — Newton iterations on the m labelled rows (labels 0/1, f = 0 start, |df|_1 < tol), then the
+ * predictive mean C21 (Y - pi) and variance C22 - rowsum((C21 beta) o C21) of EVERY local row, folded through the
+ * factored eigenvectors (C21 = V2 Lam V1^T is never formed).  Cvv carries + sigma on its diagonal and C22 + sigma, as
+ * in the driver.  The labels' Polya-Gamma sampler (R RNG) and the COBYLA training of t are not part of this path. */
+int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
+                                        double sigma, double tol, int max_iter, double* mean, double* cov);
 
 #ifdef __cplusplus
 }

@@ -659,3 +659,38 @@ def fit_nystrom_regression(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-5, approac
     best["cov"] = posterior_covariance_regression(V, values, idx0, idx1, K, x, sigma)
     del best["extend"]
     return best
+
+
+# ------------------------------------------------------------------ Laplace posterior of the binary classifier
+def posterior_distribution_classification(C11, C21, C22, Y, tol=1e-5, max_iter=100):
+    """posterior_distribution_classification (src/Utils.cpp:252-299), literal: Newton iterations for the posterior
+    mode (GPML algorithm 3.1) from f = 0, then mean = C21 (Y - pi), cov = C22 - rowsum((C21 beta) o C21)."""
+    import scipy.linalg as sla
+
+    C11 = np.asarray(C11, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    m = Y.size
+    f = np.zeros(m)
+
+    def factor(f):
+        pi = 1.0 / (1.0 + np.exp(-f))
+        W = pi * (1.0 - pi)
+        sw = np.sqrt(W)
+        B = sw[:, None] * C11 * sw[None, :]
+        B[np.diag_indices(m)] += 1.0
+        return pi, W, sw, sla.cho_factor(B, lower=True)
+
+    for _ in range(max_iter):
+        pi, W, sw, cf = factor(f)
+        b = W * f + (Y - pi)
+        a = b - sw * sla.cho_solve(cf, sw * (C11 @ b))
+        f_new = C11 @ a
+        done = np.abs(f - f_new).sum() < tol
+        f = f_new
+        if done:
+            break
+    pi, W, sw, cf = factor(f)
+    mean = C21 @ (Y - pi)
+    beta = sw[:, None] * sla.cho_solve(cf, np.eye(m)) * sw[None, :]
+    cov = np.asarray(C22) - ((C21 @ beta) * C21).sum(axis=1)
+    return mean, cov

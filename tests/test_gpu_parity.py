@@ -726,3 +726,31 @@ def test_nystrom_random_anchors_and_K_equals_s(flgp, oracle):
     res = flgp.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, -1, a2s=[1.0], pars=(4.0, 0.5), subsample="random",
                                               init_idx=init)
     assert np.all(np.isfinite(res["Y_pred"]["test"])) and np.all(res["posterior"]["cov"] > 0)
+
+
+# ------------------------------------------------------------------------------------------- Laplace posterior (logit)
+@pytest.mark.parametrize("m,K", [(100, 100), (60, 25)])
+def test_classification_posterior_config1_rings(flgp, oracle, m, K):
+    """BASELINE config 1 (README GPC rings: n=4800, d=2, m=100, s=600, r=3, K=100, fit_lae_logit_gp_rcpp): the
+    deterministic half of the driver at a fixed diffusion time — Laplace posterior mean / variance of every row,
+    folded through the factored eigenvectors, against the oracle's literal posterior_distribution_classification on
+    the dense covariance blocks (src/Fit.cpp:563-582)."""
+    from flgp_b200.datasets import make
+
+    X, lab, cfg = make("C1")  # rows already shuffled: training rows first
+    s, r, t, sigma = cfg["s"], cfg["r"], 10.0, 1e-3
+    init = _init(len(X), s, 1)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=50)
+    mean, cov = flgp.posterior_distribution_classification(ep, lab[:m], m, K, t, sigma)
+    V, values = ep.vectors, ep.values
+    n = len(X)
+    idx0, idx1 = np.arange(m, dtype=np.int32), np.arange(n, dtype=np.int32)
+    C11 = oracle.hk_from_spectrum(V, values, K, t, idx0, idx0)
+    C11[np.diag_indices(m)] += sigma
+    C21 = oracle.hk_from_spectrum(V, values, K, t, idx1, idx0)
+    C22 = ((V[:, :K] * np.exp(-t * (1.0 - values[:K]))) * V[:, :K]).sum(axis=1) + sigma
+    mo, co = oracle.posterior_distribution_classification(C11, C21, C22, lab[:m])
+    np.testing.assert_allclose(mean, mo, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(mo).max()))
+    np.testing.assert_allclose(cov, co, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(co).max()))
+    acc = np.mean((mean[m:] > 0) == (lab[m:] > 0.5))
+    assert acc > 0.8  # six separated rings, untuned t: the Laplace mode classifies most held-out points

@@ -297,3 +297,27 @@ def test_golden_fixture_training_rows(oracle):
     assert ny["a2"] == float(g["ny_a2"])
     np.testing.assert_allclose(ny["test"][:200], g["ny_test"], rtol=1e-7, atol=1e-8)
     np.testing.assert_allclose(ny["cov"][:200], g["ny_cov"], rtol=1e-7, atol=1e-9)
+
+
+def test_laplace_posterior_oracle_against_direct_mode(oracle):
+    """oracle.posterior_distribution_classification (src/Utils.cpp:252-299): its Newton mode satisfies the
+    stationarity condition f = C11 (Y - pi(f)) of the Laplace approximation, and the predictive variance equals the
+    textbook C22 - C21 (C11 + W^-1)^-1 C21^T."""
+    rng = np.random.default_rng(4)
+    m, q = 30, 12
+    A = rng.standard_normal((m + q, 8))
+    Kf = A @ A.T * 0.3 + 1e-3 * np.eye(m + q)
+    C11, C21, C22 = Kf[:m, :m], Kf[m:, :m], np.diag(Kf)[m:]
+    Y = (rng.uniform(size=m) > 0.5).astype(np.float64)
+    mean, cov = oracle.posterior_distribution_classification(C11, C21, C22, Y, tol=1e-12, max_iter=200)
+    # recover the mode from the mean relation on the training block itself
+    f = np.zeros(m)
+    for _ in range(500):
+        pi = 1 / (1 + np.exp(-f))
+        W = pi * (1 - pi)
+        f = np.linalg.solve(np.eye(m) + C11 * W[None, :], C11 @ (W * f + Y - pi))
+    pi = 1 / (1 + np.exp(-f))
+    np.testing.assert_allclose(mean, C21 @ (Y - pi), rtol=1e-8, atol=1e-10)
+    W = pi * (1 - pi)
+    ref = C22 - np.einsum("ij,jk,ik->i", C21, np.linalg.inv(C11 + np.diag(1 / W)), C21)
+    np.testing.assert_allclose(cov, ref, rtol=1e-8, atol=1e-10)
