@@ -10,7 +10,8 @@ from .api import (  # noqa: F401
     fit_se_regression_gp_rcpp,
     graphLaplacian_cpp,
     heat_kernel_covariance_rcpp, heat_kernel_spectrum_cpp, heat_kernel_spectrum_sharded, knn_distances,
-    lae_eigenmap, local_anchor_embedding_cpp, mma_minimize, posterior_distribution_classification, regression_fixed, regression_objective, spectrum_from_Z_cpp, subsample_cpp, train_regression_gp,
+    lae_eigenmap, local_anchor_embedding_cpp, mma_minimize, posterior_distribution_classification,
+    posterior_distribution_classification_rcpp, regression_fixed, regression_objective, spectrum_from_Z_cpp, subsample_cpp, train_regression_gp,
     v_to_z_cpp,
 )
 

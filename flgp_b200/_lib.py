@@ -106,6 +106,8 @@ def _declare(lib):
                                                   p_i32, c_u64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64]),
         "flgp_classification_posterior_fixed": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_double, C.c_double,
                                                           C.c_int, p_f64, p_f64]),
+        "flgp_posterior_distribution_classification": (C.c_int, [H, p_f64, p_f64, p_f64, p_f64, C.c_int, c_i64,
+                                                                 C.c_double, C.c_int, p_f64, p_f64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol

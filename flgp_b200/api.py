@@ -646,3 +646,22 @@ def posterior_distribution_classification(eigenpair: EigenPair, Y_local, m_total
     check(eigenpair.ctx._lib.flgp_classification_posterior_fixed(eigenpair._h, _pf(Y_local), m_total, K, t, sigma, tol,
                                                                  max_iter, _pf(mean), _pf(cov)))
     return mean, cov
+
+
+def posterior_distribution_classification_rcpp(C11, C21, C22, Y, tol: float = 1e-5, max_iter: int = 100, *,
+                                               ctx: Optional[Context] = None):
+    """posterior_distribution_classification(C11, C21, C22, Y, tol, max_iter) — the reference's export on explicit
+    covariance blocks (src/Utils.h:77-80, src/Utils.cpp:252-299) -> {"mean", "cov"}."""
+    ctx = ctx or default_ctx()
+    C11 = _f64(C11)
+    C21 = _f64(C21)
+    C22 = np.ascontiguousarray(C22, dtype=np.float64).reshape(-1)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, m_new = C11.shape[0], C21.shape[0]
+    if C11.shape != (m, m) or C21.shape != (m_new, m) or C22.size != m_new or Y.size != m:
+        raise FlgpError("posterior_distribution_classification: inconsistent shapes")
+    mean = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    check(ctx._lib.flgp_posterior_distribution_classification(ctx._h, _pf(C11), _pf(C21), _pf(C22), _pf(Y), m, m_new,
+                                                              tol, max_iter, _pf(mean), _pf(cov)))
+    return {"mean": mean, "cov": cov}

@@ -563,6 +563,16 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
   return best;
 }
 
+// out[i] = base[i] - sum_k A(k, i) B(k, i) for row-major m x n operands (columns are the test rows)
+__global__ void coldot_sub_kernel(const double* __restrict__ A, const double* __restrict__ B, int m, int64_t n,
+                                  const double* __restrict__ base, double* __restrict__ out) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double a = 0.0;
+  for (int k = 0; k < m; ++k) a = fma(A[(size_t)k * n + i], B[(size_t)k * n + i], a);
+  out[i] = base[i] - a;
+}
+
 // ---- Laplace posterior of the binary GP classifier (posterior_distribution_classification,
 //      /root/reference/src/Utils.cpp:252-299; GPML algorithms 3.1 / 3.2) -------------------------------------------
 // Newton iterations on the m training points (host, m x m: m is the number of labelled points), from f = 0:
@@ -1473,6 +1483,35 @@ int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local,
       dm.download(mean, h->n_local, c->stream);
       if (cov) dc.download(cov, h->n_local, c->stream);
     }
+    sync(c);
+  });
+}
+
+int flgp_posterior_distribution_classification(flgp_ctx* ctx, const double* C11, const double* C21, const double* C22,
+                                               const double* Y, int m, int64_t m_new, double tol, int max_iter,
+                                               double* mean, double* cov) {
+  return guard([&] {
+    need(ctx && C11 && C21 && C22 && Y && mean && cov, "null argument");
+    need(m >= 1 && m <= 8192 && m_new >= 0, "classification: need 1 <= m <= 8192 labelled rows");
+    Ctx* c = &ctx->c;
+    std::vector<double> c11(C11, C11 + (size_t)m * m), pi, beta;
+    laplace_mode(c11, Y, m, tol, max_iter > 0 ? max_iter : 100, pi, beta);
+    if (m_new == 0) return;
+    // C21 (m_new x m, column-major) is the row-major m x m_new matrix R = C21^T:
+    //   mean = (Y - pi)^T R  (1 x m_new),   T^T = beta R  (m x m_new),   cov = C22 - colsum(T^T o R)
+    std::vector<double> ypi(m);
+    for (int i = 0; i < m; ++i) ypi[i] = Y[i] - pi[i];
+    DevBuf<double> dR((size_t)m * m_new), dB((size_t)m * m), dT((size_t)m * m_new), dv(m), d22(m_new), dmean(m_new),
+        dcov(m_new);
+    dR.upload(C21, (size_t)m * m_new, c->stream);
+    dB.upload(beta.data(), (size_t)m * m, c->stream);  // symmetric: row-major image = column-major image
+    dv.upload(ypi.data(), m, c->stream);
+    d22.upload(C22, m_new, c->stream);
+    gemm_nn_run(c, dv.p, dR.p, 1, m_new, m, dmean.p);
+    gemm_nn_run(c, dB.p, dR.p, m, m_new, m, dT.p);
+    FLGP_LAUNCH(c, coldot_sub_kernel, ceil_div(m_new, 256), 256, 0, dT.p, dR.p, m, m_new, d22.p, dcov.p);
+    dmean.download(mean, m_new, c->stream);
+    dcov.download(cov, m_new, c->stream);
     sync(c);
   });
 }

@@ -24,6 +24,7 @@
 //   fit_se_regression_gp_cpp      src/Fit.cpp:102-219          -> flgp_fit_se_regression  (one k-means/KNN, bandwidth grid)
 //   train_regression_gp_cpp       src/train.cpp:557-671        -> flgp_train_regression   (noise = "same")
 //   fit_nystrom_regression_gp_cpp src/Fit.cpp:222-357          -> flgp_fit_nystrom_regression
+//   posterior_distribution_classification src/Utils.cpp:252-299 -> flgp_posterior_distribution_classification
 // [[Rcpp::depends(RcppEigen)]]
 #include <RcppEigen.h>
 
@@ -281,4 +282,14 @@ Rcpp::List fit_nystrom_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::Nume
   Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", t = " << pars[0]
               << ", sigma = " << std::sqrt(pars[1]) << ", the objective function is " << obj << "\n";
   return pack_fit(train, test, cov, pars);
+}
+
+// [[Rcpp::export(posterior_distribution_classification)]]  -- signature unchanged (src/Utils.h:77-80)
+Rcpp::List posterior_distribution_classification(const Eigen::MatrixXd& C11, const Eigen::MatrixXd& C21,
+                                                 const Eigen::VectorXd& C22, const Eigen::VectorXd& Y, double tol,
+                                                 int max_iter) {
+  Eigen::VectorXd mean(C21.rows()), cov(C21.rows());
+  ok(flgp_posterior_distribution_classification(ctx(), C11.data(), C21.data(), C22.data(), Y.data(), (int)C11.rows(),
+                                                C21.rows(), tol, max_iter, mean.data(), cov.data()));
+  return Rcpp::List::create(Rcpp::Named("mean") = mean, Rcpp::Named("cov") = cov);
 }

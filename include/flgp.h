@@ -216,6 +216,12 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
  * in the driver.  The labels' Polya-Gamma sampler (R RNG) and the COBYLA training of t are not part of this path. */
 int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
                                         double sigma, double tol, int max_iter, double* mean, double* cov);
+/* The export itself, posterior_distribution_classification(C11, C21, C22, Y, tol, max_iter) (src/Utils.h:77-80) on
+ * explicit covariance blocks: C11 m x m, C21 m_new x m (column-major), C22 m_new, labels 0/1.  Newton mode on the
+ * host (m x m), the m_new-sized products on the device. */
+int flgp_posterior_distribution_classification(flgp_ctx* ctx, const double* C11, const double* C21, const double* C22,
+                                               const double* Y, int m, int64_t m_new, double tol, int max_iter,
+                                               double* mean, double* cov);
 
 #ifdef __cplusplus
 }

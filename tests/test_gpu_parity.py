@@ -754,3 +754,19 @@ def test_classification_posterior_config1_rings(flgp, oracle, m, K):
     np.testing.assert_allclose(cov, co, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(co).max()))
     acc = np.mean((mean[m:] > 0) == (lab[m:] > 0.5))
     assert acc > 0.8  # six separated rings, untuned t: the Laplace mode classifies most held-out points
+
+
+def test_posterior_distribution_classification_export(flgp, oracle):
+    """The reference's own export on explicit covariance blocks (src/Utils.h:77-80), ragged sizes."""
+    rng = np.random.default_rng(9)
+    for m, q in [(37, 501), (64, 64), (5, 1)]:
+        A = rng.standard_normal((m + q, 11))
+        Kf = A @ A.T * 0.2 + 1e-3 * np.eye(m + q)
+        C11, C21, C22 = np.asfortranarray(Kf[:m, :m]), np.asfortranarray(Kf[m:, :m]), np.diag(Kf)[m:].copy()
+        Y = (rng.uniform(size=m) > 0.4).astype(np.float64)
+        res = flgp.posterior_distribution_classification_rcpp(C11, C21, C22, Y)
+        mo, co = oracle.posterior_distribution_classification(C11, C21, C22, Y)
+        np.testing.assert_allclose(res["mean"], mo, rtol=1e-9, atol=1e-10)
+        np.testing.assert_allclose(res["cov"], co, rtol=1e-9, atol=1e-10)
+    with pytest.raises(flgp.FlgpError, match="inconsistent"):
+        flgp.posterior_distribution_classification_rcpp(C11, C21[:, :1], C22, Y)
