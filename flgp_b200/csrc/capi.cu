@@ -286,7 +286,7 @@ void stage_spectrum(Ctx* c, flgp_spectrum* sp, int K, bool root) {
   DevBuf<double> lam(K), Y((size_t)s * K);
   {
     StageScope st(c, "eigh", (4.0 / 3.0) * s * (double)s * s + 2.0 * s * (double)s * K, 8.0 * s * (double)s * s);
-    eigh_topk_run(c, G.p, s, K, lam.p, Y.p);
+    eigh_topk_run(c, G.p, s, K, lam.p, Y.p, /*psd=*/true);
   }
   std::vector<double> lam_h(K), scale(K);
   lam.download(lam_h.data(), K, c->stream);

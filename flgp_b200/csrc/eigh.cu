@@ -816,7 +816,23 @@ wy_apply_kernel(int s, int K, const double* __restrict__ Vh, const double* __res
 
 }  // namespace
 
-void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
+void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y, bool psd) {
+  if (K < 1 || K > s) fail(2, "eigh: need 1 <= K <= s (K=%d, s=%d)", K, s);
+  // K << s: Chebyshev-filtered subspace iteration on the tensor cores (chfsi.cu); it certifies its own result
+  // (residuals) and leaves G untouched, so anything it declines or fails on takes the direct route below
+  static const bool no_chfsi = std::getenv("FLGP_EIGH_DIRECT") != nullptr;
+  if (!no_chfsi && s >= 1024 && 5 * K <= s) {
+    bool ok;
+    {
+      StageScope st(c, "eigh_chfsi");
+      ok = chfsi_topk_run(c, G, s, K, lam, Y, psd);
+    }
+    if (ok) return;
+  }
+  eigh_direct_run(c, G, s, K, lam, Y);
+}
+
+void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   if (K < 1 || K > s) fail(2, "eigh: need 1 <= K <= s (K=%d, s=%d)", K, s);
   DevBuf<double> dd(s), ee(s), tau(s), pbuf((size_t)2 * TD_MAXSEG * s), tnorm(1);
   ee.zero(c->stream);

@@ -20,7 +20,11 @@ namespace {
 // 4 warps, each a 32 x 32 sub-tile = 4 x 4 DMMA tiles (32 accumulator registers per thread).
 __global__ void __launch_bounds__(128)
 dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
-                    const double* __restrict__ sc, int64_t M, int64_t N, int K, double* __restrict__ C, int64_t ldc) {
+                    const double* __restrict__ sc, int64_t M, int64_t N, int K, double* __restrict__ C, int64_t ldc,
+                    int kchunk, int64_t csplit) {
+  // blockIdx.z = K slab [kbeg, kend) (kchunk is a multiple of 16); partial results csplit apart
+  const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+  C += (int64_t)blockIdx.z * csplit;
   extern __shared__ __align__(1024) unsigned char dsm_raw[];
   // 1024-byte alignment of every box is what SWIZZLE_128B requires
   double* boxes = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(dsm_raw) + 1023) & ~(uintptr_t)1023);
@@ -29,7 +33,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wm = (wid >> 1) * 32, wn = (wid & 1) * 32;  // this warp's corner inside the CTA tile
   const int i0 = blockIdx.y * DG_T, j0 = blockIdx.x * DG_T;
-  const int nk = (K + DG_K - 1) / DG_K;
+  const int nk = (kend - kbeg + DG_K - 1) / DG_K;
   if (tid == 0) {
     for (int st = 0; st < DG_STAGES; ++st) mbar_init(&full[st], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -39,8 +43,8 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int st = kt % DG_STAGES;
     double* a = boxes + (size_t)st * 2 * DG_T * DG_K;
     mbar_expect_tx(&full[st], DG_STAGE_BYTES);
-    tma_load_2d(a, &mapA, kt * DG_K, i0, &full[st]);                  // rows i0.., columns kt*16.. (zero filled outside)
-    tma_load_2d(a + DG_T * DG_K, &mapB, kt * DG_K, j0, &full[st]);
+    tma_load_2d(a, &mapA, kbeg + kt * DG_K, i0, &full[st]);           // rows i0.., columns kbeg+kt*16.. (zero filled outside)
+    tma_load_2d(a + DG_T * DG_K, &mapB, kbeg + kt * DG_K, j0, &full[st]);
   };
   if (tid == 0)
     for (int kt = 0; kt < DG_STAGES - 1 && kt < nk; ++kt) issue(kt);
@@ -55,7 +59,7 @@ dmma_gemm_nt_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // the scale factors of this K slab (block-uniform, tiny)
     if (sc) {
       __syncthreads();
-      if (tid < DG_K) scs[tid] = (kt * DG_K + tid < K) ? sc[kt * DG_K + tid] : 0.0;
+      if (tid < DG_K) scs[tid] = (kbeg + kt * DG_K + tid < kend) ? sc[kbeg + kt * DG_K + tid] : 0.0;
     }
     mbar_wait(&full[st], (kt / DG_STAGES) & 1);
     if (sc) __syncthreads();
@@ -209,11 +213,42 @@ void gemm_nt_ld_run(Ctx* c, const double* A, int64_t lda, const double* B, int64
   const size_t smem = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024;
   FLGP_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(ceil_div(N, DG_T), ceil_div(M, DG_T));
-  FLGP_LAUNCH(c, dmma_gemm_nt_kernel, grid, 128, smem, mapA, mapB, sc, M, N, K, C, ldc);
+  FLGP_LAUNCH(c, dmma_gemm_nt_kernel, grid, 128, smem, mapA, mapB, sc, M, N, K, C, ldc, K > 0 ? ((K + 15) / 16) * 16 : 16,
+              (int64_t)0);
 }
 
 void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C) {
   gemm_strided(c, A, K, 1, B, N, 1, nullptr, M, N, K, C, N, 1);
+}
+
+void gemm_tn_splitk_run(Ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N,
+                        int Kd, double* C) {
+  if (M <= 0 || N <= 0) return;
+  const bool tma_ok = (lda % 2 == 0) && (ldb % 2 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0) &&
+                      (reinterpret_cast<uintptr_t>(B) % 16 == 0) && M * N >= 64 * 64 && Kd >= 256;
+  if (!tma_ok) {
+    gemm_strided_splitk(c, A, lda, 1, B, 1, ldb, M, N, Kd, C);
+    return;
+  }
+  // A^T B with both operands column-major = the NT product of the row-major views (M x Kd) and (N x Kd): FP64 tensor
+  // cores, the contraction split into slabs so that the few output tiles still fill the GPU, slabs summed in order
+  const int tiles = ceil_div(N, DG_T) * ceil_div(M, DG_T);
+  int nsplit = std::max(1, std::min(Kd / 64, (2 * c->sm_count) / tiles));
+  const int kchunk = ceil_div(ceil_div(Kd, nsplit), DG_K) * DG_K;
+  nsplit = ceil_div(Kd, kchunk);
+  const CUtensorMap mapA = make_map(A, M, Kd, lda), mapB = make_map(B, N, Kd, ldb);
+  const size_t smem = (size_t)DG_STAGES * DG_STAGE_BYTES + 1024;
+  FLGP_CUDA(cudaFuncSetAttribute(dmma_gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(ceil_div(N, DG_T), ceil_div(M, DG_T), nsplit);
+  if (nsplit == 1) {
+    FLGP_LAUNCH(c, dmma_gemm_nt_kernel, grid, 128, smem, mapA, mapB, (const double*)nullptr, M, N, Kd, C, M, kchunk,
+                (int64_t)0);
+    return;
+  }
+  DevBuf<double> part((size_t)nsplit * M * N);  // stream-ordered pool: released blocks are only reused on this stream
+  FLGP_LAUNCH(c, dmma_gemm_nt_kernel, grid, 128, smem, mapA, mapB, (const double*)nullptr, M, N, Kd, part.p, M, kchunk,
+              M * N);
+  FLGP_LAUNCH(c, splitk_reduce_kernel, ceil_div(M * N, 256), 256, 0, part.p, M * N, nsplit, C);
 }
 
 void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double* y) {

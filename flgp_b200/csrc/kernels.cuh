@@ -97,6 +97,9 @@ void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N,
 void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double* y);
 // G(K x K, col-major) = V^T V and g = V^T y over n_rows rows of V (row-major n_rows x K); deterministic
 void gram_small_run(Ctx* c, const double* V, const double* y, int64_t n_rows, int K, double* G, double* g);
+// C(M x N, col-major ld M) = A^T B;  A: Kd x M and B: Kd x N column-major (lda, ldb); deterministic split over Kd
+void gemm_tn_splitk_run(Ctx* c, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t M, int64_t N,
+                        int Kd, double* C);
 
 // ---- nystrom.cu ------------------------------------------------------------------------------
 // Nystrom extension (fit_nystrom_regression_gp_cpp, src/Fit.cpp:222-357).  U: s x d column-major (ld ldu).
@@ -120,7 +123,13 @@ void tail_woodbury_run(Ctx* c, const double* Gg, int K_ld, int K, const double* 
 // ---- eigh.cu ---------------------------------------------------------------------------------
 // Top-K eigenpairs (descending) of the symmetric s x s matrix G (full storage; destroyed).
 // lam: K.  Y: s x K column-major, orthonormal columns.
-void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y);
+// psd: the caller knows G is positive semi-definite (a Gram): lower spectral bound 0 for the iterative route.
+void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y, bool psd = false);
+// the direct route: Householder tridiagonalisation, multisection, inverse iteration, blocked back-transformation
+void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y);
+// chfsi.cu: Chebyshev-filtered subspace iteration (K << s, s even); G is only read.  false = not applicable or not
+// converged (outputs undefined).
+bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* Y, bool psd);
 
 // ---- misc ------------------------------------------------------------------------------------
 double dfma_peak_run(Ctx* c, int iters);  // measured fp64 FMA TFLOP/s (roofline denominator)
