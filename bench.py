@@ -4,7 +4,9 @@
     python bench.py --gpus 1 --steps 3 --warmup 3
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
         bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores, bounded sample
+    python bench.py --impl reference ...        # the CPU path (oracle port) on the host cores, same config:
+                                                # every stage timed on a bounded sample and scaled to the full n
+    python bench.py --config C3|C5 ...          # the other named shapes (same JSON; the headline stays C4)
 
 One "step" = one full pass of the hot path over the whole synthetic matrix: Lloyd k-means (iter.max=100)
 -> KNN -> LAE -> graph-Laplacian scaling -> Gram -> top-K eigensolve -> GPR tail (posterior mean of every row +
@@ -13,13 +15,17 @@ The n rows are sharded over the ranks in contiguous blocks (strong scaling: n is
 
 `value`   : n / (device-timed seconds per step), inputs resident in HBM.
 `e2e`     : the same through the host-buffer C ABI (H2D of the shard, D2H of mean+variance inside the timed region).
-`roofline`: the kernel with the largest share of the step, against the FP64 FMA throughput measured in-process
-            (MEASURED_PEAKS.json has HBM and bf16 only); `roofline_kernels` lists the other single-launch kernels the
+`e2e_pageable`: the same from ordinary (pageable) host arrays, as the R shim hands them over.
+`roofline`: the single kernel with the largest share of the step, against the FP64 FMA throughput measured in-process
+            (MEASURED_PEAKS.json has HBM and bf16 only); `roofline_kernels` lists the other instrumented kernels the
             same way; `roofline_hbm` rates the Z-streaming stages against the measured HBM copy bandwidth.
+`result_digest`: sharding-independent digest of the result (anchors, Z, predictions): equal for every rank count.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
+import importlib.util
 import json
 import os
 import statistics
@@ -38,6 +44,7 @@ NCU_TRAFFIC = {
     "kmeans_assign_small": (311.2e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_kmeans_assign_small.ncu-rep)"),
     "tridiag_resident": (25.3e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_resident.ncu-rep)"),
     "tridiag_streaming": (37.6e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_streaming.ncu-rep)"),
+    "cheb_gemm": (40.2e6, "profiles/r2_ncu_full_summary.csv (r2_cheb_gemm_v2.ncu-rep, cheb_gemm_kernel<7>, one launch)"),
 }
 
 PARS = (10.0, 0.01)   # (t, noise variance): fixed hyper-parameters
@@ -54,7 +61,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=None, help="override the number of rows (debug only; invalidates the line)")
     ap.add_argument("--iter-max", type=int, default=100)
-    ap.add_argument("--cpu-sample", type=int, default=100_000, help="rows of the CPU baseline sample")
+    ap.add_argument("--config", default="C4", choices=["C3", "C4", "C5"])
+    ap.add_argument("--cpu-sample", type=int, default=None, help="rows of the CPU sample (default: 1e6, or n if smaller)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -170,49 +178,111 @@ def measured_peaks():
         return None
 
 
-def cpu_pipeline(X, Y, cfg, init, iter_max, nthreads):
-    """The CPU path: the oracle restatement of the reference (oracle/), all stages, threaded."""
+def load_datasets():
+    """flgp_b200/datasets.py as a stand-alone module: the reference arm must not import the product package
+    (importing it maps libflgp_b200.so into the CPU process)."""
+    spec = importlib.util.spec_from_file_location("flgp_datasets", os.path.join(ROOT, "flgp_b200", "datasets.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_config(cfgname, cfg, n, world, iter_max):
+    """The `config` object of the JSON line: identical in the GPU arm and in the reference arm."""
+    return {"workload": "%s %s n=%d d=%d m=%d s=%d r=%d K=%d, fit_lae_regression (kmeans, cluster-normalized, root), "
+                        "fixed pars t=%g noise=%g" % (cfgname, cfg["name"], n, cfg["d"], cfg["m"], cfg["s"], cfg["r"],
+                                                      cfg["K"], PARS[0], PARS[1]),
+            "iter_max": iter_max, "parallelism": "rows sharded over %d GPU(s)" % world,
+            "l2_policy": "inputs (%.0f MB per rank) larger than the 126 MB L2" % (n / world * cfg["d"] * 8 / 1e6),
+            "optimizer": "excluded (fixed hyper-parameters), SURVEY.md 8d"}
+
+
+def cpu_staged(make, cfgname, n_full, n_sample, iter_max, cores):
+    """The reference's CPU path (oracle restatement, oracle/), timed stage by stage on the first n_sample rows of the
+    SAME workload and scaled to n_full rows: the stages that are linear in n (KNN, LAE, graph
+    Laplacian, Gram, lift, GPR tail) are timed in full on the sample and multiplied by n_full / n_sample; Lloyd k-means is
+    timed per pass (2 passes) and multiplied by iter_max passes (the GPU arm runs all iter_max passes at this n:
+    path_info.kmeans_iters) and by n_full / n_sample; the s x s eigensolve (LAPACK) does not depend on n and is timed
+    once.  Returns the per-stage seconds on the sample and the extrapolated seconds of one full step."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle as O
 
-    m = cfg["m"]
-    t0 = time.perf_counter()
-    res = O.fit_lae_regression_fixed(X[:m], Y[:m], X[m:], cfg["s"], cfg["r"], cfg["K"], PARS, init, SIGMA,
-                                     iter_max=iter_max, nthreads=nthreads)
-    return time.perf_counter() - t0, res
+    X, Y, cfg = make(cfgname, SEED, n=n_sample)
+    m, s, r, K, d = cfg["m"], cfg["s"], cfg["r"], cfg["K"], cfg["d"]
+    m = min(m, n_sample // 2)
+    init = np.sort(np.random.default_rng(KM_SEED).choice(n_sample, s, replace=False)).astype(np.int32)
+    t = {}
+    now = time.perf_counter
+    passes = 2
+    t0 = now()
+    U, _, _ = O.kmeans_lloyd(X, s, init, passes, cores)
+    t["kmeans_per_pass"] = (now() - t0) / passes
+    Uc = np.asfortranarray(U[:, :d])
+    t0 = now()
+    ind = O.knn(X, Uc, r, nthreads=cores)
+    t["knn"] = now() - t0
+    t0 = now()
+    Zj, Zx, _ = O.lae(X, Uc, r, ind=ind, nthreads=cores)
+    t["lae"] = now() - t0
+    t0 = now()
+    Zx = O.graph_laplacian(Zj, Zx, s, "cluster-normalized", U[:, d])
+    t["graph_laplacian"] = now() - t0
+    t0 = now()
+    w = O.spectrum_scale(O.colsum(Zj, Zx, s))
+    G = O.gram(Zj, Zx, w, s)
+    t["gram"] = now() - t0
+    t0 = now()
+    lam, Yv = O.gram_eigh(G, K)
+    t["eigh"] = now() - t0
+    t0 = now()
+    sigma = np.sqrt(np.maximum(lam, 0.0))
+    V = O.lift(Zj, Zx, w, Yv, sigma, nthreads=cores)
+    t["lift"] = now() - t0
+    t0 = now()
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n_sample, dtype=np.int32)
+    O.predict_regression(V, sigma, Y[:m], idx0, idx0, K, PARS, SIGMA)
+    O.predict_regression(V, sigma, Y[:m], idx0, idx1, K, PARS, SIGMA)
+    O.posterior_covariance_regression(V, sigma, idx0, idx1, K, PARS, SIGMA)
+    t["gpr_tail"] = now() - t0
+    scale = n_full / float(n_sample)
+    linear = t["knn"] + t["lae"] + t["graph_laplacian"] + t["gram"] + t["lift"] + t["gpr_tail"]
+    full = scale * (iter_max * t["kmeans_per_pass"] + linear) + t["eigh"]
+    sample = ("oracle port of the reference path on %d threads; every stage timed on the first %d of %d rows (same d=%d, "
+              "s=%d, r=%d, K=%d): n-linear stages x %.4g, Lloyd %.3f s per pass x %d passes x %.4g, eigensolve once; the R "
+              "package itself cannot be built here" % (cores, n_sample, n_full, d, s, r, K, scale, t["kmeans_per_pass"],
+                                                        iter_max, scale))
+    return t, full, sample, cfg
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  The R package cannot be built or run
-    here (no R/Rcpp/Eigen/TBB), so this is the oracle port on all host cores, on a bounded sample
-    of the same workload (same d, s, r, K, iter.max; fewer rows)."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores, same config as the GPU
+    arm.  The R package cannot be built or run here (no R/Rcpp/Eigen/TBB), so this is the oracle
+    port with all host threads; each step times every stage on a bounded sample and extrapolates to the full n
+    (cpu_staged above).  Rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    from flgp_b200.datasets import make
-    from flgp_b200 import default_init
-
-    n = args.cpu_sample
-    X, Y, cfg = make("C4", SEED, n=n)
-    init = default_init(n, cfg["s"], KM_SEED)
+    ds = load_datasets()
+    cfg0 = dict(ds.CONFIGS[args.config])
+    n = args.n or cfg0["n"]
+    ns = min(n, args.cpu_sample or 1_000_000)
     cores = os.cpu_count() or 1
-    for _ in range(args.warmup and 1):  # one warm-up pass is enough for a CPU code (page-in, thread pool)
-        cpu_pipeline(X[: max(cfg["m"] + 1000, n // 10)], Y[: max(cfg["m"] + 1000, n // 10)], cfg,
-                     default_init(max(cfg["m"] + 1000, n // 10), cfg["s"], KM_SEED), 3, cores)
-    times = []
+    if args.warmup:  # one small warm-up pass is enough for a CPU code (page-in, thread pool, library build)
+        cpu_staged(ds.make, args.config, n, min(ns, max(20_000, 2 * cfg0["s"] + 2 * cfg0["m"])), args.iter_max, cores)
+    fulls, last = [], None
     for _ in range(max(1, args.steps)):
-        dt, _ = cpu_pipeline(X, Y, cfg, init, args.iter_max, cores)
-        times.append(dt)
-    T = sum(times) / len(times)
+        last = cpu_staged(ds.make, args.config, n, ns, args.iter_max, cores)
+        fulls.append(last[1])
+    T = sum(fulls) / len(fulls)
+    stages, _, sample, cfg = last
     val = n / T
-    sample = "oracle port, %d of 10M rows (same d=3, s=%d, r=%d, K=%d, iter.max=%d), %d threads" % (
-        n, cfg["s"], cfg["r"], cfg["K"], args.iter_max, cores)
     line = {"impl": "reference", "metric": "flgp_fit_predict_points_per_sec", "value": val, "unit": "points/s",
             "n_gpus": args.gpus, "steps": max(1, args.steps), "warmup": args.warmup, "ms_per_step": T * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 swiss-roll n=10M d=3 m=5000 s=2000 r=3 K=200 (bounded CPU sample)",
-                       "sample_rows": n},
-            "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample},
+            "config": workload_config(args.config, cfg0, n, args.gpus, args.iter_max),
+            "cpu_baseline": {"value": val, "unit": "points/s", "cores": cores, "kind": "port", "sample": sample,
+                             "stage_seconds_on_sample": stages, "sample_rows": ns, "extrapolated": ns < n},
             "e2e": {"value": val, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -235,12 +305,12 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
 
-    cfg = dict(CONFIGS["C4"])
+    cfg = dict(CONFIGS[args.config])
     n = args.n or cfg["n"]
     m, s, r, K, d = cfg["m"], cfg["s"], cfg["r"], cfg["K"], cfg["d"]
     lo, hi = shard_bounds(n, world, rank)
     n_local = hi - lo
-    X_host, Y_host, _ = make("C4", SEED, lo, hi, n=n)          # this rank's rows, column-major
+    X_host, Y_host, _ = make(args.config, SEED, lo, hi, n=n)   # this rank's rows, column-major
     m_local = max(0, min(n_local, m - lo))
     init = F.default_init(n, s, KM_SEED)
 
@@ -321,8 +391,55 @@ def run_ours(args):
     ep.close()
     # --- e2e through the host-buffer C ABI
     step_e2e().close()
-    ms_e2e, _, ep2 = timed(step_e2e, max(1, min(args.steps, 2)))
+    ms_e2e, _, ep2 = timed(step_e2e, max(1, args.steps))
     ep2.close()
+    # --- the same from pageable host memory (what the R shim hands over: ordinary R vectors)
+    Yh = Y_host[:max(m_local, 1)].copy()
+    yh = np.empty(max(n_local, 1))
+    ch = np.empty(max(n_local, 1))
+
+    def step_pageable():
+        ep = F.heat_kernel_spectrum_sharded(X_host, n, lo, s, r, K, models, init_idx=init, iter_max=args.iter_max,
+                                            ctx=ctx)
+        check(lib.flgp_regression_fixed(ep._h, Yh.ctypes.data_as(F._lib.p_f64), m, K, PARS[0], PARS[1], SIGMA,
+                                        yh.ctypes.data_as(F._lib.p_f64), ch.ctypes.data_as(F._lib.p_f64)))
+        return ep
+
+    step_pageable().close()
+    ms_page, _, ep3 = timed(step_pageable, max(1, args.steps))
+    # --- result digest (not timed): independent of how the rows are sharded, so that the 1/2/4/8-GPU lines can be
+    # compared.  Z and the predictions enter as a wrap-around sum of per-row 64-bit hashes of (global row, bits).
+    def mix(h, words):
+        h = (h ^ words) * np.uint64(0x9E3779B97F4A7C15)
+        return h ^ (h >> np.uint64(29))
+
+    Z = ep3.Z()
+    rows = np.arange(lo, hi, dtype=np.uint64)
+    hz = rows * np.uint64(0xD6E8FEB86659FD93) + np.uint64(1)
+    zj = Z.indices.reshape(n_local, r).astype(np.uint64)
+    zx = np.ascontiguousarray(Z.data).view(np.uint64).reshape(n_local, r)
+    with np.errstate(over="ignore"):
+        for q in range(r):
+            hz = mix(mix(hz, zj[:, q]), zx[:, q])
+        hp = mix(mix(rows * np.uint64(0xD6E8FEB86659FD93) + np.uint64(2), yh[:n_local].view(np.uint64)),
+                 ch[:n_local].view(np.uint64))
+        sums = np.array([hz.sum(dtype=np.uint64), hp.sum(dtype=np.uint64)], dtype=np.uint64)
+    red = torch.from_numpy(sums.view(np.int64).copy()).to(dev)
+    mx = torch.tensor([float(np.abs(yh[:n_local]).max()) if n_local else 0.0,
+                       float(np.abs(ch[:n_local]).max()) if n_local else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(red, op=dist.ReduceOp.SUM)   # int64 wrap-around: associative
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    anchors = ep3.anchors()
+    digest = {"anchors_sha256": hashlib.sha256(np.ascontiguousarray(anchors).tobytes()).hexdigest(),
+              "Z_rowhash_sum": "%016x" % (int(red[0].item()) & 0xFFFFFFFFFFFFFFFF),
+              "pred_rowhash_sum": "%016x" % (int(red[1].item()) & 0xFFFFFFFFFFFFFFFF),
+              "pred_mean_maxabs": float(mx[0].item()), "pred_var_maxabs": float(mx[1].item()),
+              "values_sha256": hashlib.sha256(np.ascontiguousarray(ep3.values).tobytes()).hexdigest(),
+              "note": "Z / predictions: sum mod 2^64 over rows of a 64-bit hash of (global row index, bit patterns); "
+                      "equal digests at 1, 2, 4, 8 GPUs = bit-identical anchors, Z and predictions"}
+    del Z, zj, zx, hz, hp
+    ep3.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -356,6 +473,9 @@ def run_ours(args):
                                  "kmeans_assign_listed<3,4>)", "fp64", None),
         "kmeans_pruned_pass": ("k-means passes 2.., bound-pruned (kmeans_lists + kmeans_bounds + kmeans_assign_pruned<3> "
                                "+ kmeans_update, per pass)", "fp64", None),
+        "eigh_chfsi_filter": ("cheb_gemm_kernel<H> (DMMA + TMA filter GEMM of the eigensolver, all launches of a step)",
+                              "fp64", NCU_TRAFFIC.get("cheb_gemm")),
+        "eigh_tridiag_cluster": ("tridiag_cluster_kernel (Rayleigh-Ritz problems of order nb)", "fp64", None),
         "eigh_tridiag_resident": ("tridiag_kernel<true,512>", "fp64", NCU_TRAFFIC.get("tridiag_resident")),
         "eigh_tridiag_streaming": ("tridiag_kernel<false,1024>", "fp64", NCU_TRAFFIC.get("tridiag_streaming")),
     }
@@ -378,7 +498,12 @@ def run_ours(args):
                           "of the HBM copy peak)")
     roofs.sort(key=lambda r: -r["share_of_step"])
     roof = next((r_ for r_ in roofs if "pruned" not in r_["kernel"]), None)  # dominant SINGLE kernel
-    if roof and roof["kernel"].startswith("tridiag"):
+    if roof and roof["kernel"].startswith("cheb_gemm"):
+        roof["bound"] = "tensor"
+        roof["note"] = ("FP64 tensor cores (DMMA m8n8k4; tcgen05 has no fp64 kind) fed by TMA; achieved = 2 s^2 x (active "
+                        "columns) flop of every launch of the step / the CUDA-event time of the filter stage; ncu: tensor "
+                        "pipe 83 % active, profiles/r2_ncu_full_summary.csv")
+    if roof and roof["kernel"].startswith("tridiag_kernel"):
         roof["note"] = ("latency bound, not pipe bound: s-1 dependent column steps, each = on-chip symmetric product + one "
                         "grid-wide flag barrier (~2 us) + two block reductions; cycle breakdown per column in "
                         "profiles/README.md")
@@ -395,13 +520,12 @@ def run_ours(args):
     line = {"metric": "flgp_fit_predict_points_per_sec", "value": n / (ms_step * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C4 swiss-roll n=%d d=3 m=5000 s=2000 r=3 K=200, fit_lae_regression (kmeans, "
-                                   "cluster-normalized, root), fixed pars t=%g noise=%g" % (n, PARS[0], PARS[1]),
-                       "iter_max": args.iter_max, "parallelism": "rows sharded over %d GPU(s)" % world,
-                       "l2_policy": "inputs (%.0f MB per rank) larger than the 126 MB L2" % (n_local * d * 8 / 1e6),
-                       "optimizer": "excluded (fixed hyper-parameters), SURVEY.md 8d"},
+            "config": workload_config(args.config, cfg, n, world, args.iter_max),
             "e2e": {"value": n / (ms_e2e * 1e-3), "unit": "points/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(n_local * d * 8 + m_local * 8), "d2h_bytes_per_step": int(n_local * 16)},
+            "e2e_pageable": {"value": n / (ms_page * 1e-3), "unit": "points/s", "ms_per_step": ms_page,
+                             "note": "inputs and outputs in ordinary pageable host arrays (what the R shim passes)"},
+            "result_digest": digest,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof,
@@ -410,16 +534,13 @@ def run_ours(args):
             "stages_ms_per_step": per_step,
             "path_info": info,
             "test_rmse": rmse}
-    if not args.no_cpu_baseline:
-        ncpu = args.cpu_sample
-        Xc, Yc, _ = make("C4", SEED, n=ncpu)
+    if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
-        dt, _ = cpu_pipeline(Xc, Yc, cfg, F.default_init(ncpu, s, KM_SEED), args.iter_max, cores)
-        line["cpu_baseline"] = {"value": ncpu / dt, "unit": "points/s", "cores": cores, "kind": "port",
-                                "seconds": dt,
-                                "sample": "oracle port of the reference path, all stages, %d of 10M rows (same d, s, r, "
-                                          "K, iter.max), %d threads; the R package itself cannot run here" %
-                                          (ncpu, cores)}
+        ns = min(n, args.cpu_sample or 1_000_000)
+        stages_cpu, full_s, sample, _ = cpu_staged(make, args.config, n, ns, args.iter_max, cores)
+        line["cpu_baseline"] = {"value": n / full_s, "unit": "points/s", "cores": cores, "kind": "port",
+                                "sample": sample, "stage_seconds_on_sample": stages_cpu, "sample_rows": ns,
+                                "extrapolated_seconds_per_step": full_s}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -13,7 +13,7 @@
 //      of the columns and the GEMM shrinks (CTA tile height 64/48/32/16 rows keeps ~all SMs busy);
 //   2. Cholesky-QR (Gram GEMM, blocked Cholesky + triangular inverse, rotation GEMM), twice when ill conditioned;
 //   3. Rayleigh-Ritz: W = G X, H = X^T W, small dense eigenproblem (eigh.cu, order nb), X <- X V, W <- W V,
-//      residual norms |W_j - theta_j X_j| decide the next degrees.  Converged when all K residuals <= 3e-13 |G|.
+//      residual norms |W_j - theta_j X_j| decide the next degrees.  Converged when all K residuals <= 1e-13 |G|.
 //
 // The filter never forms anything larger than s x nb; G is only read.  When the iteration does not converge within
 // its budget (clustered spectra whose K-th gap the guards do not cover, K close to s) the caller falls back to the
@@ -112,7 +112,12 @@ cheb_gemm_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
   for (int a = 0; a < MTX; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
-  const int fr = lane >> 2, fk = lane & 3;
+  // Fragment row of a lane: the 8 rows (columns) of an m8n8k4 block may be dealt to the lane groups in any order as
+  // long as the epilogue uses the same order.  A 64-bit shared load is served per half-warp (lanes 0-15 = groups
+  // 0-3); with the 128-byte swizzle rows r and r^1 exchange the same pair of 16-byte chunks, so groups 0-3 must not
+  // hold adjacent rows: group g takes row pr(g) = 0,2,4,6,1,3,5,7 -> every half-warp touches 8 distinct chunks.
+  const int fg = lane >> 2, fk = lane & 3;
+  const int fr = ((fg & 3) << 1) | (fg >> 2);
   // element (row, k) of a swizzled box: row * 128 bytes + 16-byte chunk ((k >> 1) ^ (row & 7)) + (k & 1) * 8;
   // row & 7 == fr for every fragment row of this thread, so the in-row offsets depend on q = k / 4 only
   uint32_t offA[4], offB[4];
@@ -151,12 +156,14 @@ cheb_gemm_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
   for (int a = 0; a < MTX; ++a)
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
-      const int i = i0 + wm + a * 8 + fr, j = j0 + wn + b * 8 + 2 * fk;
+      const int i = i0 + wm + a * 8 + fr;
       if (a >= mtw || i >= s) continue;
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        if (j + q >= jend) continue;
-        const int64_t at = i + ld * (int64_t)(j + q);
+        const int n = 2 * fk + q;  // accumulator column n was fed by lane group n, i.e. physical column pr(n)
+        const int j = j0 + wn + b * 8 + (((n & 3) << 1) | (n >> 2));
+        if (j >= jend) continue;
+        const int64_t at = i + ld * (int64_t)j;
         double v = c1 * acc[a][b][q];
         if (c2 != 0.0) v = fma(c2, X[at], v);
         if (c3 != 0.0) v = fma(c3, P[at], v);
@@ -263,7 +270,15 @@ __device__ __forceinline__ unsigned cluster_rank() {
   return r;
 }
 __global__ void __cluster_dims__(CH_NC, 1, 1) __launch_bounds__(CH_THREADS)
-cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, double* __restrict__ info) {
+cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, double* __restrict__ info,
+                   long long* __restrict__ prof) {
+  long long t0 = clock64(), tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define CH_TICK(i)                                \
+  if (prof && threadIdx.x == 0) {                 \
+    const long long t_ = clock64();               \
+    tacc[i] += t_ - t0;                           \
+    t0 = t_;                                      \
+  }
   extern __shared__ __align__(16) double csm[];
   double* D = csm;                        // 32 x 33: diagonal block, then its Cholesky factor
   double* Di = D + CH_NB * 33;            // 32 x 33: inverse of the factor
@@ -284,6 +299,7 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
     __stcg(M + e, col <= i ? S[col + (size_t)nb * i] : 0.0);
   }
   cluster_sync_all();
+  CH_TICK(0);
   for (int j0 = 0; j0 < nb; j0 += CH_NB) {
     const int jb = min(CH_NB, nb - j0);
     const int r0 = j0 + jb;         // first row below the panel
@@ -295,6 +311,7 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
       Di[i * 33 + j] = 0.0;
     }
     __syncthreads();
+    CH_TICK(1);
     // Cholesky of the block with all threads, one barrier per column: thread (i, j..j+1) owns its entries of the
     // Schur complement, which stays UNSCALED in D (column k of the factor = D(:, k) * invd[k], applied at the end)
     {
@@ -326,6 +343,7 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
       }
       __syncthreads();
     }
+    CH_TICK(2);
     // inverse of the lower-triangular factor, row by row, 16 threads per entry of the row:
     //   Di(r, c) = (delta_rc - sum_{c <= q < r} L(r, q) Di(q, c)) / L(r, r)
     {
@@ -338,6 +356,7 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
         __syncthreads();
       }
     }
+    CH_TICK(3);
     // (b) Y[p, col] = sum_q Di(k, q) R(j0 + q, col) for col < j0: every CTA takes a column range, staged through
     //     smem (Zs is free until the barrier) so that no dependent L2 round trip sits in the inner loop; Y[p, p] = Di
     {
@@ -389,9 +408,23 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
         }
       }
     }
+    CH_TICK(4);
     cluster_sync_all();
+    CH_TICK(5);
     // (d) Z panel -> smem (columns 0 .. nb-1 that exist: Y part [0, r0), L21^T part [r0, nb))
-    for (int e = tid; e < jb * nb; e += CH_THREADS) Zs[e] = __ldcg(Zg + e);
+    for (int e0 = 0; e0 < jb * nb; e0 += 8 * CH_THREADS) {  // 8 loads in flight per thread
+      double t8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * CH_THREADS + tid;
+        t8[u] = (e < jb * nb) ? __ldcg(Zg + e) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = e0 + u * CH_THREADS + tid;
+        if (e < jb * nb) Zs[e] = t8[u];
+      }
+    }
     __syncthreads();
     // rows of the result: M[p rows, 0 .. r0) = Y   (CTA 0; nobody reads these rows again)
     if (rank == 0)
@@ -399,20 +432,27 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
         const int k = e / r0, col = e - k * r0;
         __stcg(M + (size_t)(j0 + k) * nb + col, Zs[(size_t)k * nb + col]);
       }
+    CH_TICK(6);
     // (e) update of this CTA's rows, columns 0 .. i: all (row, column) pairs at once, so that the L2 round trips of
     //     different rows overlap
     for (int e = tid; e < myrows * nb; e += CH_THREADS) {
       const int lr = e / nb, col = e - lr * nb;
       const int i = r0 + rank + lr * CH_NC;
       if (col > i) continue;
-      double acc = (col >= j0 && col < r0) ? 0.0 : __ldcg(M + (size_t)i * nb + col);
+      // the old value is fetched first and consumed last: its L2 round trip hides behind the 32 FMAs
+      const double old = (col >= j0 && col < r0) ? 0.0 : __ldcg(M + (size_t)i * nb + col);
       const double* lrow = Ls + lr * 33;
+      double acc = 0.0;
 #pragma unroll 8
-      for (int k = 0; k < jb; ++k) acc = fma(-lrow[k], Zs[(size_t)k * nb + col], acc);
-      __stcg(M + (size_t)i * nb + col, acc);
+      for (int k = 0; k < jb; ++k) acc = fma(lrow[k], Zs[(size_t)k * nb + col], acc);
+      __stcg(M + (size_t)i * nb + col, old - acc);
     }
     cluster_sync_all();
+    CH_TICK(7);
   }
+  if (prof && rank == 0 && tid == 0)
+    for (int i = 0; i < 8; ++i) prof[i] = tacc[i];
+#undef CH_TICK
   if (rank == 0 && tid == 0) {
     info[0] = (double)bad;
     info[1] = dmin_s;
@@ -463,7 +503,8 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
     }
     return;
   }
-  const int fr = lane >> 2, fk = lane & 3;
+  const int fg = lane >> 2, fk = lane & 3;
+  const int fr = ((fg & 3) << 1) | (fg >> 2);  // conflict-free row order of the fragment loads (see cheb_gemm_kernel)
   uint32_t offA[4], offB[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -499,7 +540,8 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
 #pragma unroll
   for (int q = 0; q < 2; ++q) {
     const double u = q ? acc1 : acc0;
-    const int64_t at = i + (int64_t)s * (2 * fk + q);
+    const int n = 2 * fk + q;
+    const int64_t at = i + (int64_t)s * (((n & 3) << 1) | (n >> 2));
     const double v = (i < s) ? V[at] : 0.0, vp = (i < s) ? Vp[at] : 0.0;
     if (i < s) U[at] = u;
     p[0][q] = (i < s) ? u * v : 0.0;
@@ -514,7 +556,8 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
       x += __shfl_xor_sync(0xffffffffu, x, 4);
       x += __shfl_xor_sync(0xffffffffu, x, 8);
       x += __shfl_xor_sync(0xffffffffu, x, 16);
-      if (fr == 0) wsum[wid][w][2 * fk + q] = x;
+      const int n = 2 * fk + q;
+      if (fg == 0) wsum[wid][w][((n & 3) << 1) | (n >> 2)] = x;
     }
   // the two consumer warps meet on a named barrier (the producer warp has left)
   asm volatile("bar.sync 1, 64;" ::: "memory");
@@ -533,11 +576,14 @@ lanczos_update_kernel(int s, int step, int nparts, const double* __restrict__ pa
                       double* __restrict__ alpha, double* __restrict__ beta) {
   __shared__ double al[LZ_NV], bp[LZ_NV], red[32][LZ_NV], be[LZ_NV];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (tid < LZ_NV) {
+  if (wid < LZ_NV) {  // warp = run: lanes stride over the CTAs' partial sums, then a fixed shuffle tree
     double a = 0.0;
-    for (int cta = 0; cta < nparts; ++cta) a += partial[((size_t)cta * 3) * LZ_NV + tid];
-    al[tid] = a;
-    bp[tid] = step > 0 ? beta[(step - 1) * LZ_NV + tid] : 0.0;
+    for (int cta = lane; cta < nparts; cta += 32) a += partial[((size_t)cta * 3) * LZ_NV + wid];
+    for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) {
+      al[wid] = a;
+      bp[wid] = step > 0 ? beta[(step - 1) * LZ_NV + wid] : 0.0;
+    }
   }
   __syncthreads();
   double n2[LZ_NV];
@@ -771,7 +817,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       fprintf(stderr, "[chfsi] s=%d K=%d nb=%d dos: a=%.5f top=%.5f c0=%.5f (lanczos min %.5f max %.5f)\n", s, K, nb, f.a,
               f.top, f.c, tmin, tmax);
   }
-  const double tol = 3e-13 * gnorm;
+  const double tol = 1e-13 * gnorm;
   int cur = 0;  // buffer that holds X
   FLGP_LAUNCH(c, cf_init_kernel, ceil_div((int64_t)s * nb, 256), 256, 0, Xb[0].p, s, ld, nb, 0u);
 
@@ -816,6 +862,19 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
                                   sizeof(double) * CF_BN * ld, cudaMemcpyDeviceToDevice, c->stream));
     cur = dst;
   };
+  // algorithmic work of one filter call: 2 s^2 flop per active column and degree; G (s^2) + 4 column blocks per launch
+  auto filter_work = [&](const std::vector<int>& deg, double* bytes) {
+    double fl = 0.0, by = 0.0;
+    for (int j = 1; j <= deg[ng - 1]; ++j) {
+      int g0 = 0;
+      while (deg[g0] < j) ++g0;
+      const double ncols = nb - g0 * CF_BN;
+      fl += 2.0 * s * (double)s * ncols;
+      by += 8.0 * (s * (double)s + 4.0 * s * ncols);
+    }
+    *bytes = by;
+    return fl;
+  };
   // Out(s x nb col-major) = In * M with B(j, k) = M(k, j) given row-major (N = nb rows of length nb)
   auto rotate = [&](const double* In, const double* Brm, double* Out) {
     dim3 tg(ceil_div(s, 32), ceil_div(nb, 32));
@@ -834,7 +893,16 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
         FLGP_CUDA(cudaFuncSetAttribute(cf_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
       }
-      FLGP_LAUNCH(c, cf_chol_inv_kernel, CH_NC, CH_THREADS, smem, S.p, nb, Linv.p, Zg.p, info.p);
+      static const bool chprof = std::getenv("FLGP_CHOL_PROF") != nullptr;
+      DevBuf<long long> prof(8);
+      FLGP_LAUNCH(c, cf_chol_inv_kernel, CH_NC, CH_THREADS, smem, S.p, nb, Linv.p, Zg.p, info.p, chprof ? prof.p : nullptr);
+      if (chprof) {
+        long long ph[8];
+        prof.download(ph, 8, c->stream);
+        sync(c);
+        fprintf(stderr, "[chol prof] init %lld | load D %lld, chol %lld, inv %lld, Y+L21 %lld, sync %lld, Z load %lld, update+sync %lld\n",
+                ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6], ph[7]);
+      }
       double ih[3];
       info.download(ih, 3, c->stream);
       sync(c);
@@ -876,7 +944,9 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   std::vector<std::vector<int>> pending;
   for (int it = 1; it <= max_outer && cost < max_cost; ++it) {
     {
-      StageScope st(c, "eigh_chfsi_filter");
+      double by = 0.0;
+      const double fl = filter_work(deg, &by);
+      StageScope st(c, "eigh_chfsi_filter", fl, by);
       filter(deg);
     }
     {
@@ -887,7 +957,9 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       std::vector<int> sg = pending.back();
       pending.pop_back();
       {
-        StageScope st(c, "eigh_chfsi_filter");
+        double by = 0.0;
+        const double fl = filter_work(sg, &by);
+        StageScope st(c, "eigh_chfsi_filter", fl, by);
         filter(sg);
       }
       StageScope st(c, "eigh_chfsi_cholqr");

@@ -351,6 +351,129 @@ tridiag_kernel(double* __restrict__ A, int s, int k_begin, int k_end, double* __
   }
 }
 
+// ---- 1b. tridiagonalisation of a SMALL matrix inside one thread-block cluster ----------------------------------------
+// The Rayleigh-Ritz problems of chfsi.cu (order 256 .. 384) and the small Grams of configs 1 / 2 are too small for the
+// grid-wide kernel above: its per-column cost is the ~2 us flag barrier across 148 CTAs.  Here the whole matrix lives
+// in the shared memory of TDC_NC CTAs (rows dealt round-robin), the products and the next column's row travel through
+// distributed shared memory, and the one barrier per column is the hardware cluster barrier (~0.2 us).  Same
+// algorithm and the same outputs (Vh, d, e, tau) as tridiag_kernel: pending rank-2 update applied inside the pass.
+constexpr int TDC_NC = 8, TDC_THREADS = 512, TDC_SMAX = 416;
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__global__ void __cluster_dims__(TDC_NC, 1, 1) __launch_bounds__(TDC_THREADS)
+tridiag_cluster_kernel(const double* __restrict__ A, int s, double* __restrict__ Vh, double* __restrict__ dd,
+                       double* __restrict__ ee, double* __restrict__ tau_out) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  extern __shared__ __align__(16) double sm[];
+  const int LD = (s + 1) & ~1;
+  const int RP = (s + TDC_NC - 1) / TDC_NC;
+  double* vp = sm;            // pending v_{k-1}; entry q <-> global index k + q
+  double* wp = vp + LD;       // pending w_{k-1}
+  double* vs = wp + LD;       // current v_k; entry q <-> global index k + 1 + q
+  double* xrow = vs + LD;     // 2 x LD: row k of the matrix (columns k+1 ..), written by the owner of the row
+  double* pb = xrow + 2 * LD; // 2 x LD: products A v_k, written by the owners of the rows
+  double* red = pb + 2 * LD;  // 32
+  double* As = red + 32;      // RP x LD: rows rank, rank + NC, ...
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int l = 0; l < RP; ++l) {
+    const int i = rank + l * TDC_NC;
+    if (i < s)
+      for (int c = tid; c < s; c += TDC_THREADS) As[(size_t)l * LD + c] = A[(size_t)i * s + c];
+  }
+  for (int j = tid; j < s - 1; j += TDC_THREADS) xrow[j] = A[1 + j];  // row 0
+  double* xrow_r[TDC_NC];
+#pragma unroll
+  for (int r = 0; r < TDC_NC; ++r) xrow_r[r] = cluster.map_shared_rank(xrow, r);
+  double* pb_mine = cluster.map_shared_rank(pb, lane & (TDC_NC - 1));  // the peer this lane delivers products to
+  __syncthreads();
+  cluster_barrier();  // every CTA of the cluster is resident before the first remote store
+  bool pending = false;
+  for (int k = 0; k < s - 1; ++k) {
+    const int m = s - k - 1, par = k & 1;
+    const double* xr = xrow + par * LD;
+    // --- column k of the up-to-date matrix (redundant per CTA)
+    const double v0 = pending ? vp[0] : 0.0, w0 = pending ? wp[0] : 0.0;
+    double part = 0.0;
+    for (int j = tid; j < m; j += TDC_THREADS) {
+      double x = xr[j];
+      if (pending) x = __dsub_rn(x, __dadd_rn(__dmul_rn(v0, wp[j + 1]), __dmul_rn(w0, vp[j + 1])));
+      vs[j] = x;
+      if (j > 0) part = fma(x, x, part);
+    }
+    const double xnorm2 = block_sum(part, red);
+    const double alpha = vs[0];
+    double beta, tau, scale;
+    if (xnorm2 == 0.0) {
+      beta = alpha;
+      tau = 0.0;
+      scale = 0.0;
+    } else {
+      const double nrm = sqrt(fma(alpha, alpha, xnorm2));
+      beta = (alpha >= 0.0) ? -nrm : nrm;
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += TDC_THREADS) {
+      const double v = (j == 0) ? 1.0 : vs[j] * scale;
+      vs[j] = v;
+      if ((j >> 5) % TDC_NC == rank) Vh[(size_t)k * s + j] = v;
+    }
+    __syncthreads();
+    if (rank == k % TDC_NC && tid == 0) {
+      double dk = As[(size_t)(k / TDC_NC) * LD + k];
+      if (pending) dk = __dsub_rn(dk, __dadd_rn(__dmul_rn(v0, w0), __dmul_rn(w0, v0)));
+      dd[k] = dk;
+      ee[k] = beta;
+      tau_out[k] = tau;
+    }
+    // --- pass over the own rows below k: apply the pending update, accumulate the product with v_k (warp per row)
+    for (int l = wid; l < RP; l += TDC_THREADS / 32) {
+      const int i = rank + l * TDC_NC;
+      if (i <= k || i >= s) continue;  // warp-uniform
+      const int row = i - (k + 1);
+      const double vi = pending ? vp[row + 1] : 0.0, wi = pending ? wp[row + 1] : 0.0;
+      double* ar = As + (size_t)l * LD + (k + 1);
+      double acc = 0.0;
+      for (int j = lane; j < m; j += 32) {
+        double av = ar[j];
+        if (pending) {
+          av = __dsub_rn(av, __dadd_rn(__dmul_rn(vi, wp[j + 1]), __dmul_rn(wi, vp[j + 1])));
+          ar[j] = av;
+        }
+        acc = fma(av, vs[j], acc);
+        if (row == 0 && j > 0) {  // row k+1 as the next column needs it, to every CTA
+#pragma unroll
+          for (int r = 0; r < TDC_NC; ++r) xrow_r[r][(par ^ 1) * LD + (j - 1)] = av;
+        }
+      }
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane < TDC_NC) pb_mine[par * LD + row] = acc;  // lane r delivers the product to CTA r
+    }
+    cluster_barrier();
+    // --- w_k = p - (tau/2)(p.v) v with p = tau A22 v; (v_k, w_k) become the pending update
+    part = 0.0;
+    for (int j = tid; j < m; j += TDC_THREADS) {
+      const double p = pb[par * LD + j] * tau;
+      wp[j] = p;
+      part = fma(p, vs[j], part);
+    }
+    const double pv = block_sum(part, red);
+    const double a2 = -0.5 * tau * pv;
+    for (int j = tid; j < m; j += TDC_THREADS) {
+      wp[j] = fma(a2, vs[j], wp[j]);
+      vp[j] = vs[j];
+    }
+    pending = true;
+    __syncthreads();
+  }
+  // the last pending update has tau == 0 (a 1 x 1 column): the matrix already holds the final corner
+  if (rank == (s - 1) % TDC_NC && tid == 0) dd[s - 1] = As[(size_t)((s - 1) / TDC_NC) * LD + (s - 1)];
+  cluster_barrier();  // nobody leaves while a peer could still address its shared memory
+}
+
 constexpr int BI_WARPS = 4;  // warps per eigenvalue: 128 probes per pass
 // 1/q to ~1 ulp: hardware seed (20 bits) + two Newton steps; |q| >= pivmin (normal), so no special cases arise.
 // The division is the whole dependent chain of a Sturm step; the IEEE sequence is ~3x longer.
@@ -847,7 +970,20 @@ void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   DevBuf<double> Vh((size_t)s * s);
   // 1. tridiagonalisation (cooperative, persistent): streaming launch while the trailing matrix is larger than the
   //    grid's shared memory, resident launch for the rest
-  {
+  static const bool no_cluster = std::getenv("FLGP_EIGH_NO_CLUSTER") != nullptr;
+  if (s <= TDC_SMAX && !no_cluster) {
+    const int LD = (s + 1) & ~1, RP = (s + TDC_NC - 1) / TDC_NC;
+    const size_t smem = ((size_t)7 * LD + 32 + (size_t)RP * LD) * sizeof(double);
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+      FLGP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      smem_set = smem;
+    }
+    double f = 0.0;
+    for (int k = 0; k < s - 1; ++k) f += 4.0 * (double)(s - k - 1) * (double)(s - k - 1);
+    StageScope st(c, "eigh_tridiag_cluster", f, 0.0);
+    FLGP_LAUNCH(c, tridiag_cluster_kernel, TDC_NC, TDC_THREADS, smem, G, s, Vh.p, dd.p, ee.p, tau.p);
+  } else {
     const int grid = std::min(c->sm_count, 32 * FLAG_PER);  // one CTA per SM
     int smem_max = 0;
     FLGP_CUDA(cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));

@@ -1,6 +1,8 @@
 """GPU parity tests proper: every stage through the C ABI (ctypes mirror of the Rcpp exports) against the
 oracle on the same seeded inputs.  Bit-exact: k-means assignments/centres, KNN indices+distances, LAE weights,
 Z pattern and values, Gram-side sums.  1e-8 relative (fp64): eigenvalues, heat kernel, predictions."""
+import os
+
 import numpy as np
 import pytest
 
@@ -770,3 +772,103 @@ def test_posterior_distribution_classification_export(flgp, oracle):
         np.testing.assert_allclose(res["cov"], co, rtol=1e-9, atol=1e-10)
     with pytest.raises(flgp.FlgpError, match="inconsistent"):
         flgp.posterior_distribution_classification_rcpp(C11, C21[:, :1], C22, Y)
+
+
+# ------------------------------------------------------------------------------------------- round 2: iterative eigensolver
+def _chfsi_matrix(rng, s, kind):
+    Q, _ = np.linalg.qr(rng.standard_normal((s, s)))
+    if kind == "graph":          # like the Gram of a row-stochastic Z: top eigenvalue 1, slow decay to a positive floor
+        lam = 0.2 + 0.8 / (1.0 + 0.004 * np.arange(s)) ** 2
+    elif kind == "degenerate":   # exact multiplicities at the top (disconnected anchor graph) and tight clusters
+        lam = np.sort(np.r_[np.ones(6), np.full(4, 0.97), 0.9 - 1e-9 * np.arange(3), rng.uniform(0.0, 0.85, s - 13)])[::-1]
+    elif kind == "indefinite":
+        lam = np.sort(rng.uniform(-1.0, 1.0, s))[::-1]
+    else:                        # "flat": the K-th gap is tiny compared with the spectrum: the iteration must either
+        lam = np.sort(rng.uniform(0.5, 0.5001, s))[::-1]  # converge or hand over to the direct solver
+        lam[:5] = [1.0, 0.9, 0.8, 0.7, 0.6]
+    A = (Q * lam) @ Q.T
+    return np.asfortranarray((A + A.T) / 2), lam
+
+
+@pytest.mark.parametrize("s,K,kind", [(1200, 100, "graph"), (2000, 200, "graph"), (1024, 60, "indefinite"),
+                                       (1500, 150, "degenerate"), (1100, 40, "flat")])
+def test_eigs_sym_iterative_route(flgp, s, K, kind):
+    """s >= 1024 and K <= s / 5 take the Chebyshev-filtered subspace iteration (chfsi.cu) — or fall back to the direct
+    solver when it does not converge; either way the answer must be LAPACK's."""
+    rng = np.random.default_rng(s + K)
+    A, _ = _chfsi_matrix(rng, s, kind)
+    res = flgp.eigs_sym(A, K)
+    w_all, V_all = np.linalg.eigh(A)
+    w, V = w_all[::-1][:K], V_all[:, ::-1][:, :K]
+    scale = max(np.abs(w_all).max(), 1.0)
+    assert np.abs(res["values"] - w).max() <= 1e-12 * scale * s
+    Y = res["vectors"]
+    assert np.abs(Y.T @ Y - np.eye(K)).max() < 1e-10
+    assert np.abs(A @ Y - Y * res["values"]).max() <= 1e-10 * scale
+    gap = w[-1] - w_all[::-1][K]
+    if gap > 1e-4 * scale:
+        assert np.abs(Y @ Y.T - V @ V.T).max() < 1e-8
+
+
+def test_eigs_sym_iterative_equals_direct(flgp, monkeypatch):
+    """The two routes behind one seam on the same matrix: eigenvalues to 1e-12, invariant subspace to 1e-9."""
+    rng = np.random.default_rng(77)
+    A, _ = _chfsi_matrix(rng, 1600, "graph")
+    K = 160
+    it = flgp.eigs_sym(A, K)
+    monkeypatch.setenv("FLGP_EIGH_DIRECT", "1")
+    import subprocess
+    import sys as _sys
+    # the switch is read once per process: the direct route runs in a child process
+    code = ("import sys, numpy as np; sys.path.insert(0, %r); import flgp_b200 as F; A = np.load(sys.argv[1]); "
+            "r = F.eigs_sym(np.asfortranarray(A), %d); np.save(sys.argv[2], r['values']); np.save(sys.argv[3], r['vectors'])"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), K))
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        np.save(os.path.join(td, "A.npy"), A)
+        subprocess.run([_sys.executable, "-c", code, os.path.join(td, "A.npy"), os.path.join(td, "w.npy"),
+                        os.path.join(td, "Y.npy")], check=True, env=dict(os.environ, FLGP_EIGH_DIRECT="1"))
+        wd, Yd = np.load(os.path.join(td, "w.npy")), np.load(os.path.join(td, "Y.npy"))
+    assert np.abs(it["values"] - wd).max() <= 1e-12
+    assert np.abs(it["vectors"] @ it["vectors"].T - Yd @ Yd.T).max() < 1e-9
+
+
+# ------------------------------------------------------------------------------------------- round 2: headline shapes vs the oracle
+def test_c4_headline_shape_against_oracle(flgp, oracle):
+    """BASELINE config 4 at n = 2e6 with the full s = 2000, r = 3, K = 200 and 5 Lloyd passes, against the oracle
+    (about a minute of CPU time): anchors, sizes, Z pattern and Z values bit-exact, eigenvalues 1e-8."""
+    from flgp_b200.datasets import make
+
+    n, m = 2_000_000, 5000
+    X, Y, cfg = make("C4", n=n)
+    s, r, K = cfg["s"], cfg["r"], cfg["K"]
+    init = _init(n, s, 1)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=5)
+    vo, Vo, I = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init, nthreads=NT, want_internals=True, iter_max=5)
+    assert ep.kmeans_iters == I["iters"] == 5
+    assert np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
+    idx = np.arange(0, n, n // 200, dtype=np.int32)
+    H = flgp.HK_from_spectrum_cpp(ep, K, 10.0, idx, idx)
+    lam = np.exp(-10.0 * (1.0 - vo))
+    Ho = (Vo[idx] * lam) @ Vo[idx].T
+    assert np.abs(H - Ho).max() <= 1e-8 * np.abs(Ho).max()
+
+
+def test_c3_headline_shape_against_oracle(flgp, oracle):
+    """BASELINE config 3 at its full shape n = 70000, d = 784, s = 1000, r = 5, K = 200 with 2 Lloyd passes (the
+    tensor-core distance path with certified selection): anchors, sizes, Z bit-exact, eigenvalues 1e-8."""
+    from flgp_b200.datasets import make
+
+    X, Y, cfg = make("C3")
+    n, m, s, r, K = cfg["n"], cfg["m"], cfg["s"], cfg["r"], cfg["K"]
+    init = _init(n, s, 3)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=2)
+    vo, Vo, I = oracle.heat_kernel_spectrum(X[:m], X[m:], s, r, K, init, nthreads=NT, want_internals=True, iter_max=2)
+    assert ep.kmeans_iters == I["iters"]
+    assert np.array_equal(ep.anchors(), I["U"])
+    Zj, Zx = _csr_parts(ep.Z())
+    assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)

@@ -321,3 +321,49 @@ def test_laplace_posterior_oracle_against_direct_mode(oracle):
     W = pi * (1 - pi)
     ref = C22 - np.einsum("ij,jk,ik->i", C21, np.linalg.inv(C11 + np.diag(1 / W)), C21)
     np.testing.assert_allclose(cov, ref, rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------ independent third-party cross-checks
+def test_kmeans_against_sklearn_lloyd(oracle):
+    """The Lloyd contract against scikit-learn's Lloyd (an implementation by other authors) from the same start rows:
+    same partition, same centres, same sizes.  (stats::kmeans itself is Hartigan-Wong with an R-RNG start: unpinned.)"""
+    sk = pytest.importorskip("sklearn.cluster")
+    X, _ = swiss(4000, 7)
+    s = 30
+    init = np.sort(np.random.default_rng(5).choice(len(X), s, replace=False)).astype(np.int32)
+    U, assign, iters = oracle.kmeans_lloyd(X, s, init, 300)
+    assert iters < 300  # converged: no assignment changed in the last pass
+    km = sk.KMeans(n_clusters=s, init=np.ascontiguousarray(X[init]), n_init=1, algorithm="lloyd", max_iter=300, tol=0.0)
+    km.fit(np.ascontiguousarray(X))
+    assert np.array_equal(km.labels_, assign)
+    np.testing.assert_allclose(km.cluster_centers_, U[:, :3], rtol=1e-12, atol=1e-12)
+    assert np.array_equal(np.bincount(km.labels_, minlength=s), U[:, 3].astype(np.int64))
+
+
+def test_spectrum_against_scipy_svds(oracle):
+    """spectrum_from_Z_cpp through the Gram route against ARPACK's svds on A = Z diag(w) (the method family of
+    RSpectra::svds, src/TruncatedSVD.cpp:23-28): singular values to 1e-8, left singular subspace through H."""
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spl
+
+    X, _ = spiral(3000, 11)
+    s, r, K = 120, 3, 20
+    init = np.sort(np.random.default_rng(2).choice(len(X), s, replace=False)).astype(np.int32)
+    U, _, _ = oracle.kmeans_lloyd(X, s, init, 50)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, r, "cluster-normalized")
+    values, V, I = oracle.spectrum_from_Z(Zj, Zx, s, K, root=True, want_internals=True)
+    n = len(X)
+    A = sp.csr_matrix((Zx.reshape(-1) * I["w"][Zj.reshape(-1)], Zj.reshape(-1), np.arange(0, n * r + 1, r)), shape=(n, s))
+    u, sv, _ = spl.svds(A, k=K, tol=1e-12, random_state=0)
+    order = np.argsort(-sv)
+    sv, u = sv[order], u[:, order]
+    np.testing.assert_allclose(values, sv, rtol=1e-8)
+    # heat kernel on a few rows: invariant under the sign / rotation freedom of the singular vectors
+    idx = np.arange(0, n, 97)
+    lam = np.exp(-5.0 * (1.0 - sv))
+    H_arpack = n * (u[idx] * lam) @ u[idx].T
+    H_oracle = (V[idx] * np.exp(-5.0 * (1.0 - values))) @ V[idx].T
+    # the K cut must not split a cluster for the comparison to be meaningful
+    gap = values[K - 1] - np.sqrt(max(np.linalg.eigvalsh(I["G"])[::-1][K], 0.0))
+    if gap > 1e-4:
+        assert np.abs(H_arpack - H_oracle).max() <= 1e-7 * np.abs(H_oracle).max()
