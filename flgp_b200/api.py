@@ -146,13 +146,21 @@ def _from_csr(Z, r=None):
     if isinstance(Z, tuple):
         Zj, Zx, s = Z
         Zj = np.ascontiguousarray(Zj, dtype=np.int32)
+        Zx = np.ascontiguousarray(Zx, dtype=np.float64)
         n, r = Zj.shape
-        return Zj, np.ascontiguousarray(Zx, dtype=np.float64), n, s, r
+        if r > 1 and np.any(np.diff(Zj, axis=1) < 0):  # the library wants column-sorted rows (it rejects others)
+            order = np.argsort(Zj, axis=1, kind="stable")
+            Zj = np.ascontiguousarray(np.take_along_axis(Zj, order, axis=1))
+            Zx = np.ascontiguousarray(np.take_along_axis(Zx.reshape(n, r), order, axis=1))
+        return Zj, Zx, n, s, r
     n, s = Z.shape
     cnt = np.diff(Z.indptr)
     if n == 0 or not np.all(cnt == cnt[0]):
         raise FlgpError("the sparse matrix must store the same number of entries in every row")
     r = int(cnt[0])
+    if not Z.has_sorted_indices:  # scipy does not keep rows column-sorted; dgRMatrix (the R side) does
+        Z = Z.copy()
+        Z.sort_indices()
     return (np.ascontiguousarray(Z.indices, dtype=np.int32).reshape(n, r),
             np.ascontiguousarray(Z.data, dtype=np.float64).reshape(n, r), n, s, r)
 

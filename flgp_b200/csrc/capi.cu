@@ -189,6 +189,31 @@ void stage_subsample(Ctx* c, flgp_spectrum* sp, const double* X, const Models& m
     StageScope st(c, "kmeans");
     kmeans_run(c, X, sp->n_local, sp->n_local, d, s, sp->n_total, sp->row_offset, init_idx, mo.iter_max, sp->U.p, ap,
                &sp->kmeans_iters, &sp->sorted);
+    if (mo.nstart > 1) {
+      // stats::kmeans(nstart = k) (src/Utils.cpp:37-42): k runs from different random starts, the one with the
+      // smallest total within-cluster sum of squares is returned.  Start 0 = init_idx (or the seed's default
+      // rows), start q > 0 = default rows of a seed derived from (seed, q); the comparison is on exact
+      // fixed-point sums, so every rank keeps the same run.
+      double best = kmeans_withinss_run(c, X, sp->n_local, sp->n_local, d, sp->U.p, s, ap, sp->n_total);
+      DevBuf<double> U2((size_t)s * (d + 1));
+      DevBuf<int32_t> a2(std::max<int64_t>(sp->n_local, 1));
+      for (int q = 1; q < mo.nstart; ++q) {
+        const std::vector<int32_t> init_q = default_init(sp->n_total, s, seed * 0x9E3779B97F4A7C15ull + (uint64_t)q);
+        KMeansSorted srt;
+        int iters = 0;
+        kmeans_run(c, X, sp->n_local, sp->n_local, d, s, sp->n_total, sp->row_offset, init_q.data(), mo.iter_max, U2.p,
+                   a2.p, &iters, &srt);
+        const double w = kmeans_withinss_run(c, X, sp->n_local, sp->n_local, d, U2.p, s, a2.p, sp->n_total);
+        if (w < best) {
+          best = w;
+          FLGP_CUDA(cudaMemcpyAsync(sp->U.p, U2.p, sizeof(double) * s * (d + 1), cudaMemcpyDeviceToDevice, c->stream));
+          FLGP_CUDA(cudaMemcpyAsync(ap, a2.p, sizeof(int32_t) * sp->n_local, cudaMemcpyDeviceToDevice, c->stream));
+          sync(c);
+          sp->kmeans_iters = iters;
+          sp->sorted = std::move(srt);
+        }
+      }
+    }
     if (st.idx >= 0) {
       c->stages[st.idx].flops = 2.0 * s * d * (double)sp->n_local * sp->kmeans_iters;
       c->stages[st.idx].bytes = (8.0 * d + 4.0) * (double)sp->n_local * sp->kmeans_iters;
@@ -258,16 +283,17 @@ void stage_cross_similarity(Ctx* c, flgp_spectrum* sp, const double* X, const do
 }
 
 void stage_graph_laplacian(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int gl,
-                           const double* num_class, int64_t n_total) {
+                           const double* num_class, int64_t n_total, double vmax = 1.0) {
   StageScope st(c, "graph_laplacian", 0.0, (gl >= 1 ? 36.0 : 24.0) * r * (double)n);
   DevBuf<double> cs(s);
-  if (gl >= 1) colsum_run(c, n, s, r, Zj, Zx, n_total, cs.p);
+  if (gl >= 1) colsum_run(c, n, s, r, Zj, Zx, n_total, cs.p, vmax);
   gl_apply_run(c, n, s, r, Zj, Zx, gl, cs.p, num_class);
   sync(c);
 }
 
 // spectrum_from_Z_cpp on sp->Zj/Zx: fills w, Wm, values
-void stage_spectrum(Ctx* c, flgp_spectrum* sp, int K, bool root) {
+// zmax > 0: Z came from the caller (any finite values): the fixed-point scales follow max |Z| and max w
+void stage_spectrum(Ctx* c, flgp_spectrum* sp, int K, bool root, double zmax = 0.0) {
   const int s = sp->s, r = sp->r;
   const int64_t n = sp->n_local;
   if (K < 0) K = s;
@@ -279,9 +305,18 @@ void stage_spectrum(Ctx* c, flgp_spectrum* sp, int K, bool root) {
   {
     StageScope st(c, "gram", 2.0 * r * r * (double)n, 24.0 * r * (double)n + 8.0 * s * s);
     DevBuf<double> cs(s);
-    colsum_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->n_total, cs.p);
+    colsum_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->n_total, cs.p, zmax > 0.0 ? zmax : 1.0);
     spectrum_scale_run(c, s, cs.p, sp->w.p);
-    gram_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->n_total, G.p);
+    double pmax = 1.0;
+    if (zmax > 0.0) {
+      std::vector<double> wh(s);
+      sp->w.download(wh.data(), s, c->stream);
+      sync(c);
+      double wmax = 0.0;
+      for (double v : wh) wmax = std::max(wmax, std::fabs(v));
+      pmax = zmax * wmax * zmax * wmax * (1.0 + 1e-12) + 1e-300;
+    }
+    gram_run(c, n, s, r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->n_total, G.p, pmax);
   }
   DevBuf<double> lam(K), Y((size_t)s * K);
   {
@@ -943,7 +978,8 @@ int flgp_graph_laplacian(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* 
     dZj.upload(Zj, (size_t)n * r, c->stream);
     dZx.upload(Zx, (size_t)n * r, c->stream);
     if (num_class) dnc.upload(num_class, s, c->stream);
-    stage_graph_laplacian(c, n, s, r, dZj.p, dZx.p, gl, dnc.p, n);
+    const double zmax = csr_validate_run(c, n, s, r, dZj.p, dZx.p);
+    stage_graph_laplacian(c, n, s, r, dZj.p, dZx.p, gl, dnc.p, n, std::max(zmax, 1e-300));
     dZx.download(Zx, (size_t)n * r, c->stream);
     sync(c);
   });
@@ -1000,7 +1036,8 @@ int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* 
     sp->Zx.alloc((size_t)n * r);
     sp->Zj.upload(Zj, (size_t)n * r, c->stream);
     sp->Zx.upload(Zx, (size_t)n * r, c->stream);
-    stage_spectrum(c, sp.get(), K, root != 0);
+    const double zmax = csr_validate_run(c, n, s, r, sp->Zj.p, sp->Zx.p);
+    stage_spectrum(c, sp.get(), K, root != 0, std::max(zmax, 1e-300));
     if (values) std::memcpy(values, sp->values.data(), sizeof(double) * sp->K);
     if (vectors) {
       DevBuf<double> V((size_t)n * sp->K);

@@ -236,6 +236,29 @@ __global__ void cf_transpose_kernel(const double* __restrict__ X, int s, int64_t
     if (i < s && j < ncols) Xr[(int64_t)i * ncols + j] = t[threadIdx.x][ii];
   }
 }
+// Multi-GPU: the filter is column-parallel, so every rank filters its share of every 64-column group and the blocks are
+// all-gathered.  Rank q owns the cpg = 64 / R columns [g * 64 + q * cpg, ...) of group g; its local block keeps the
+// groups in order (local column g * cpg + j), so the active columns are still a suffix.
+__global__ void cf_pack_kernel(const double* __restrict__ X, int s, int64_t ld, int ng, int cpg, int rank,
+                               double* __restrict__ Xl) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (e >= (int64_t)s * ng * cpg) return;
+  const int lc = (int)(e / s), i = (int)(e - (int64_t)lc * s);
+  const int g = lc / cpg, j = lc - g * cpg;
+  Xl[i + ld * lc] = X[i + ld * (g * CF_BN + rank * cpg + j)];
+}
+// recv: R blocks of (s x ng*cpg), block q from rank q  ->  X (s x nb)
+__global__ void cf_unpack_kernel(const double* __restrict__ recv, int s, int64_t ld, int ng, int cpg, int R,
+                                 double* __restrict__ X) {
+  const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  const int nbl = ng * cpg;
+  if (e >= (int64_t)s * nbl * R) return;
+  const int q = (int)(e / ((int64_t)s * nbl));
+  const int64_t rem = e - (int64_t)q * s * nbl;
+  const int lc = (int)(rem / s), i = (int)(rem - (int64_t)lc * s);
+  const int g = lc / cpg, j = lc - g * cpg;
+  X[i + ld * (g * CF_BN + q * cpg + j)] = recv[(size_t)q * ld * nbl + i + ld * lc];
+}
 // H <- (H + H^T) / 2  (nb x nb column-major)
 __global__ void cf_symmetrize_kernel(double* H, int nb) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
@@ -702,9 +725,38 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   // ---- tensor maps: G with 4 box heights, each vector block as the "col" operand
   CUtensorMap mapG[9];  // index = tile height / 8
   for (int h = 2; h <= 8; ++h) mapG[h] = make_map_box(G, s, s, s, 8 * h);
-  CUtensorMap mapX[3];
-  for (int q = 0; q < 3; ++q) mapX[q] = make_map_box(Xb[q].p, nb, s, ld, CF_BN);
-  auto gemm = [&](int src, const double* P, double* Out, int col0, int ncols, double c1, double c2, double c3) {
+  // a set of three rotating column blocks (the recurrence needs Y_{j-2}, Y_{j-1}, Y_j) with their tensor maps
+  struct BlockSet {
+    CUtensorMap map[3];
+    double* p[3];
+    int ncols;
+  };
+  BlockSet full;
+  full.ncols = nb;
+  for (int q = 0; q < 3; ++q) {
+    full.p[q] = Xb[q].p;
+    full.map[q] = make_map_box(Xb[q].p, nb, s, ld, CF_BN);
+  }
+  // multi-GPU: this rank's columns of every group (see cf_pack_kernel)
+  static const bool no_shard = std::getenv("FLGP_CHFSI_NO_SHARD") != nullptr;
+  const int R = c->nranks;
+  const bool shard = R > 1 && CF_BN % R == 0 && !no_shard;
+  const int cpg = shard ? CF_BN / R : CF_BN, nbl = ng * cpg;
+  DevBuf<double> Xl[3], recv;
+  BlockSet loc;
+  loc.ncols = nbl;
+  if (shard) {
+    recv.alloc(blk);
+    const int nbl_map = std::max(nbl, CF_BN);  // the TMA box is 64 columns wide: keep the tensor at least that wide
+    for (int q = 0; q < 3; ++q) {
+      Xl[q].alloc((size_t)s * nbl_map);
+      if (nbl_map > nbl) Xl[q].zero(c->stream);
+      loc.p[q] = Xl[q].p;
+      loc.map[q] = make_map_box(Xl[q].p, nbl_map, s, ld, CF_BN);
+    }
+  }
+  auto gemm = [&](const BlockSet& bs, int src, const double* P, double* Out, int col0, int ncols, double c1, double c2,
+                  double c3) {
     // tile height: the smallest that still gives at most one CTA per SM (the active block shrinks with the degrees)
     const int ct = ceil_div(ncols, CF_BN);
     int h = 8;
@@ -718,7 +770,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       FLGP_CUDA(cudaFuncSetAttribute(cheb_gemm_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  \
       attr_set = true;                                                                                                \
     }                                                                                                                 \
-    FLGP_LAUNCH(c, cheb_gemm_kernel<HH>, grid, CF_THREADS, smem, mapG[h], mapX[src], s, col0, ncols, Xb[src].p, P,    \
+    FLGP_LAUNCH(c, cheb_gemm_kernel<HH>, grid, CF_THREADS, smem, mapG[h], bs.map[src], s, col0, ncols, bs.p[src], P,  \
                 Out, ld, c1, c2, c3);                                                                                 \
   }
     switch (h) {
@@ -821,30 +873,32 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   int cur = 0;  // buffer that holds X
   FLGP_LAUNCH(c, cf_init_kernel, ceil_div((int64_t)s * nb, 256), 256, 0, Xb[0].p, s, ld, nb, 0u);
 
-  // X <- p(G) X with per-group degrees deg[g] (non-decreasing in g); result back in Xb[cur]
-  auto filter = [&](const std::vector<int>& deg) {
+  // X <- p(G) X with per-group degrees deg[g] (non-decreasing in g); result back in Xb[cur].
+  // The recurrence runs on block set bs with gw columns per group: the full block, or (multi-GPU) this rank's share,
+  // which is packed from / all-gathered back into the full block around it.  Every column is computed by exactly one
+  // rank with the same instruction sequence as in a single-GPU run, so the result does not depend on the rank count.
+  auto recurrence = [&](const BlockSet& bs, int gw, int start, const std::vector<int>& deg) -> int {
     const int mm = deg[ng - 1];
-    if (mm <= 0) return;
     const double e = 0.5 * (f.c - f.a), cen = 0.5 * (f.c + f.a);
     const double sig1 = e / (f.top - cen);
     double sig = sig1;
-    int bj = cur;                      // buffer of Y_{j-1}
-    int bjm = -1;                      // buffer of Y_{j-2}
-    std::vector<int> where(ng, cur);   // buffer holding the final columns of each group
+    int bj = start;                     // buffer of Y_{j-1}
+    int bjm = -1;                       // buffer of Y_{j-2}
+    std::vector<int> where(ng, start);  // buffer holding the final columns of each group
     for (int j = 1; j <= mm; ++j) {
       int g0 = 0;
       while (deg[g0] < j) ++g0;
-      const int col0 = g0 * CF_BN, ncols = nb - col0;
+      const int col0 = g0 * gw, ncols = bs.ncols - col0;
       int bo = 0;
       while (bo == bj || bo == bjm) ++bo;
       if (j == 1) {
-        gemm(bj, nullptr, Xb[bo].p, col0, ncols, sig1 / e, -cen * sig1 / e, 0.0);
+        gemm(bs, bj, nullptr, bs.p[bo], col0, ncols, sig1 / e, -cen * sig1 / e, 0.0);
       } else {
         const double sig2 = 1.0 / (2.0 / sig1 - sig);
-        gemm(bj, Xb[bjm].p, Xb[bo].p, col0, ncols, 2.0 * sig2 / e, -cen * 2.0 * sig2 / e, -sig * sig2);
+        gemm(bs, bj, bs.p[bjm], bs.p[bo], col0, ncols, 2.0 * sig2 / e, -cen * 2.0 * sig2 / e, -sig * sig2);
         sig = sig2;
       }
-      cost += (double)ncols / nb;
+      cost += (double)ncols / bs.ncols / (shard ? R : 1);
       for (int g = g0; g < ng; ++g)
         if (deg[g] == j) where[g] = bo;
       bjm = bj;
@@ -858,9 +912,31 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       if (cnt[q] > cnt[dst]) dst = q;
     for (int g = 0; g < ng; ++g)
       if (where[g] != dst)
-        FLGP_CUDA(cudaMemcpyAsync(Xb[dst].p + (size_t)g * CF_BN * ld, Xb[where[g]].p + (size_t)g * CF_BN * ld,
-                                  sizeof(double) * CF_BN * ld, cudaMemcpyDeviceToDevice, c->stream));
-    cur = dst;
+        FLGP_CUDA(cudaMemcpyAsync(bs.p[dst] + (size_t)g * gw * ld, bs.p[where[g]] + (size_t)g * gw * ld,
+                                  sizeof(double) * gw * ld, cudaMemcpyDeviceToDevice, c->stream));
+    return dst;
+  };
+  auto filter = [&](const std::vector<int>& deg) {
+    if (deg[ng - 1] <= 0) return;
+    if (!shard) {
+      cur = recurrence(full, CF_BN, cur, deg);
+      return;
+    }
+    FLGP_LAUNCH(c, cf_pack_kernel, ceil_div((int64_t)s * nbl, 256), 256, 0, Xb[cur].p, s, ld, ng, cpg, c->rank, Xl[0].p);
+    const int dst = recurrence(loc, cpg, 0, deg);
+    comm_allgather_f64(c, Xl[dst].p, recv.p, (size_t)s * nbl);
+    FLGP_LAUNCH(c, cf_unpack_kernel, ceil_div((int64_t)s * nbl * R, 256), 256, 0, recv.p, s, ld, ng, cpg, R, Xb[cur].p);
+  };
+  // W = G X (Rayleigh-Ritz), the same way
+  auto apply_G = [&](double* W) {
+    if (!shard) {
+      gemm(full, cur, nullptr, W, 0, nb, 1.0, 0.0, 0.0);
+      return;
+    }
+    FLGP_LAUNCH(c, cf_pack_kernel, ceil_div((int64_t)s * nbl, 256), 256, 0, Xb[cur].p, s, ld, ng, cpg, c->rank, Xl[0].p);
+    gemm(loc, 0, nullptr, Xl[1].p, 0, nbl, 1.0, 0.0, 0.0);
+    comm_allgather_f64(c, Xl[1].p, recv.p, (size_t)s * nbl);
+    FLGP_LAUNCH(c, cf_unpack_kernel, ceil_div((int64_t)s * nbl * R, 256), 256, 0, recv.p, s, ld, ng, cpg, R, W);
   };
   // algorithmic work of one filter call: 2 s^2 flop per active column and degree; G (s^2) + 4 column blocks per launch
   auto filter_work = [&](const std::vector<int>& deg, double* bytes) {
@@ -917,8 +993,8 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   std::vector<double> th(nb), rs(nb);
   auto rayleigh_ritz = [&]() {
     double* X = Xb[cur].p;
-    gemm(cur, nullptr, Wb.p, 0, nb, 1.0, 0.0, 0.0);
-    cost += 1.0;
+    apply_G(Wb.p);
+    cost += shard ? 1.0 / R : 1.0;
     gemm_tn_splitk_run(c, X, ld, Wb.p, ld, nb, nb, s, Hs.p);
     FLGP_LAUNCH(c, cf_symmetrize_kernel, ceil_div(nb * nb, 256), 256, 0, Hs.p, nb);
     eigh_direct_run(c, Hs.p, nb, nb, theta.p, Vs.p);

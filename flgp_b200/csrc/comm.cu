@@ -20,6 +20,7 @@ struct Nccl {
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                             cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
@@ -44,6 +45,7 @@ static Nccl* nccl_open() {
   BIND(GetUniqueId, "ncclGetUniqueId");
   BIND(CommInitRank, "ncclCommInitRank");
   BIND(AllReduce, "ncclAllReduce");
+  BIND(AllGather, "ncclAllGather");
   BIND(CommDestroy, "ncclCommDestroy");
   BIND(GetErrorString, "ncclGetErrorString");
 #undef BIND
@@ -111,6 +113,15 @@ void comm_allreduce_i64_to(Ctx* c, const int64_t* src, int64_t* dst, size_t coun
 void comm_allreduce_f64(Ctx* c, double* d, size_t count) {
   if (c->nranks == 1 || count == 0) return;
   FLGP_NCCL(c->nccl, c->nccl->AllReduce(d, d, count, ncclFloat64, ncclSum, c->nccl->comm, c->stream));
+}
+// recv[q * count .. (q+1) * count) = send of rank q (bit copies: the only fp64 data-path exchange besides the K x K tail)
+void comm_allgather_f64(Ctx* c, const double* send, double* recv, size_t count) {
+  if (count == 0) return;
+  if (c->nranks == 1) {
+    if (recv != send) FLGP_CUDA(cudaMemcpyAsync(recv, send, sizeof(double) * count, cudaMemcpyDeviceToDevice, c->stream));
+    return;
+  }
+  FLGP_NCCL(c->nccl, c->nccl->AllGather(send, recv, count, ncclFloat64, c->nccl->comm, c->stream));
 }
 void comm_allreduce_max_f64(Ctx* c, double* d, size_t count) {
   if (c->nranks == 1 || count == 0) return;

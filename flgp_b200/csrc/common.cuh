@@ -154,6 +154,7 @@ void comm_allreduce_i64(Ctx* c, int64_t* dbuf, size_t count);
 void comm_allreduce_i64_to(Ctx* c, const int64_t* src, int64_t* dst, size_t count);  // out of place
 void comm_allreduce_f64(Ctx* c, double* dbuf, size_t count);
 void comm_allreduce_max_f64(Ctx* c, double* dbuf, size_t count);
+void comm_allgather_f64(Ctx* c, const double* send, double* recv, size_t count_per_rank);
 void comm_destroy(Ctx* c);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

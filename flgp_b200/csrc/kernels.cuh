@@ -25,6 +25,9 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
                 int64_t row_offset, const int32_t* init_idx_h, int iter_max, double* U, int32_t* assign,
                 int* iters_out, KMeansSorted* sorted_out = nullptr);
 double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);  // all-reduced, host value
+// tot.withinss of an assignment (exact fixed point, all-reduced): the criterion stats::kmeans ranks its nstart runs by
+double kmeans_withinss_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, const double* U, int s,
+                           const int32_t* assign, int64_t n_total);
 
 // ---- knn.cu ----------------------------------------------------------------------------------
 // ind: n x r (ld n), ascending distance, libstdc++ partial_sort tie behaviour.  dist: optional.
@@ -65,13 +68,17 @@ void lae_point_run(Ctx* c, const double* x, int d, const double* Ur, int r, doub
 void simplex_project_run(Ctx* c, const double* v, int r, double* z);
 
 // ---- sparse.cu -------------------------------------------------------------------------------
+// vmax bounds |Zx| (fixed-point scale); the pipeline's own Z has entries in [0, 1]
 void colsum_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int64_t n_total,
-                double* colsum);  // fixed-point, all-reduced
+                double* colsum, double vmax = 1.0);  // fixed-point, all-reduced
+// caller-supplied CSR: throws unless 0 <= column < s, columns strictly ascending per row, values finite; max |value|
+double csr_validate_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx);
 void gl_apply_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, double* Zx, int mode,
                   const double* colsum, const double* num_class);
 void spectrum_scale_run(Ctx* c, int s, const double* colsum, double* w);
+// pmax bounds |Z(i,p) w(p) Z(i,q) w(q)| (fixed-point scale); <= 1 for the pipeline's own non-negative Z
 void gram_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, const double* w,
-              int64_t n_total, double* G);  // s x s, fixed-point, all-reduced, symmetric
+              int64_t n_total, double* G, double pmax = 1.0);  // s x s, fixed-point, all-reduced, symmetric
 // rows of the lifted eigenvectors: out(a, k) = sum_p Z(i_a, c_p) w(c_p) Wm(c_p, k),  i_a = idx ? idx[a] : a
 // Wm: s x K row-major.  out: n_rows x K, column-major (ld = ldo) if colmajor else row-major (ld = K).
 void lift_rows_run(Ctx* c, int r, const int32_t* Zj, const double* Zx, const double* w, const double* Wm,

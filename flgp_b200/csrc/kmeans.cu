@@ -1215,6 +1215,52 @@ void launch_small(Ctx* c, const double* X, int64_t n, int64_t ldx, const double*
 
 }  // namespace
 
+// total within-cluster sum of squares of an assignment, as exact fixed-point limbs (order independent: the same
+// bits for every thread schedule and every rank count) -- what stats::kmeans compares its nstart runs by
+__global__ void kmeans_withinss_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d,
+                                       const double* __restrict__ U, int s, const int32_t* __restrict__ assign, Fx fx,
+                                       unsigned long long* __restrict__ out) {
+  long long h = 0, l = 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = assign[i];
+    double w = 0.0;
+    for (int k = 0; k < d; ++k) {
+      const double df = X[i + ldx * k] - U[a + (size_t)s * k];
+      w = fma(df, df, w);
+    }
+    long long hh, ll;
+    fx_encode(fx, w, &hh, &ll);
+    h += hh;
+    l += ll;
+  }
+  for (int o = 16; o; o >>= 1) {
+    h += __shfl_xor_sync(0xffffffffu, h, o);
+    l += __shfl_xor_sync(0xffffffffu, l, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&out[0], (unsigned long long)h);
+    atomicAdd(&out[1], (unsigned long long)l);
+  }
+}
+
+double kmeans_withinss_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, const double* U, int s,
+                           const int32_t* assign, int64_t n_total) {
+  const double maxabs = maxabs_run(c, X, n_local, ldx, d);
+  Fx fx;
+  if (fx_make(4.0 * d * maxabs * maxabs + 1e-300, n_total, &fx)) fail(2, "kmeans: non-finite input");
+  DevBuf<unsigned long long> acc(2);
+  acc.zero(c->stream);
+  if (n_local > 0) {
+    const int grid = (int)std::min<int64_t>((n_local + 255) / 256, (int64_t)c->sm_count * 8);
+    FLGP_LAUNCH(c, kmeans_withinss_kernel, grid, 256, 0, X, n_local, ldx, d, U, s, assign, fx, acc.p);
+  }
+  comm_allreduce_i64(c, reinterpret_cast<int64_t*>(acc.p), 2);
+  long long h[2];
+  acc.download(reinterpret_cast<unsigned long long*>(h), 2, c->stream);
+  sync(c);
+  return fx_todouble(h[0]) * fx.q1 + fx_todouble(h[1]) * fx.q2;
+}
+
 double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d) {
   DevBuf<unsigned long long> m(1);
   m.zero(c->stream);

@@ -180,12 +180,64 @@ sparse_quadform_kernel(int64_t n, int s, int r, const int32_t* __restrict__ Zj, 
   q[i] = add + acc;
 }
 
+// caller-supplied CSR (flgp_spectrum_from_z, flgp_graph_laplacian): the kernels above rely on 0 <= column < s, strictly
+// ascending columns inside a row (the Gram writes (c_p, c_q), p <= q, into the upper triangle only) and finite values.
+// flags[0] |= 1 bad column, 2 unsorted / duplicate column, 4 non-finite value;  maxbits = bits of max |value|.
+__global__ void csr_validate_kernel(int64_t n, int s, int r, const int32_t* __restrict__ Zj, const double* __restrict__ Zx,
+                                    int* __restrict__ flags, unsigned long long* __restrict__ maxbits) {
+  int bad = 0;
+  double mx = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int prev = -1;
+    for (int p = 0; p < r; ++p) {
+      const int cj = Zj[i * r + p];
+      const double v = Zx[i * r + p];
+      if (cj < 0 || cj >= s) bad |= 1;
+      if (cj <= prev) bad |= 2;
+      if (!isfinite(v)) bad |= 4;
+      prev = cj;
+      mx = fmax(mx, fabs(v));
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (bad) atomicOr(flags, bad);
+    atomicMax(maxbits, (unsigned long long)__double_as_longlong(mx));  // non-negative doubles order like their bits
+  }
+}
+
+}  // namespace
+
+double csr_validate_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx) {
+  DevBuf<int> flags(1);
+  DevBuf<unsigned long long> mb(1);
+  flags.zero(c->stream);
+  mb.zero(c->stream);
+  if (n > 0) {
+    const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)c->sm_count * 8);
+    FLGP_LAUNCH(c, csr_validate_kernel, grid, 256, 0, n, s, r, Zj, Zx, flags.p, mb.p);
+  }
+  int f = 0;
+  double mx = 0.0;
+  flags.download(&f, 1, c->stream);
+  mb.download(reinterpret_cast<unsigned long long*>(&mx), 1, c->stream);
+  sync(c);
+  if (f & 1) fail(2, "sparse matrix: a column index is outside [0, s)");
+  if (f & 2) fail(2, "sparse matrix: the column indices of a row must be strictly ascending (sorted, no duplicates)");
+  if (f & 4) fail(2, "sparse matrix: non-finite value");
+  return mx;
+}
+
+namespace {
 }  // namespace
 
 void colsum_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, int64_t n_total,
-                double* colsum) {
+                double* colsum, double vmax) {
   Fx fx;
-  if (fx_make(1.0, n_total, &fx)) fail(2, "colsum: bad scale");
+  if (fx_make(vmax, n_total, &fx)) fail(2, "colsum: bad scale");
   DevBuf<long long> acc((size_t)2 * s);
   acc.zero(c->stream);
   const int64_t nnz = n * r;
@@ -220,9 +272,9 @@ void spectrum_scale_run(Ctx* c, int s, const double* colsum, double* w) {
 }
 
 void gram_run(Ctx* c, int64_t n, int s, int r, const int32_t* Zj, const double* Zx, const double* w,
-              int64_t n_total, double* G) {
+              int64_t n_total, double* G, double pmax) {
   Fx fx;
-  if (fx_make(1.0, n_total, &fx)) fail(2, "gram: bad scale");
+  if (fx_make(pmax, n_total, &fx)) fail(2, "gram: bad scale");
   if (r > 32) fail(2, "r=%d exceeds 32", r);
   const size_t ss = (size_t)s * s;
   DevBuf<long long> limbs(2 * ss);

@@ -66,7 +66,13 @@ int flgp_default_init(int64_t n, int s, uint64_t seed, int32_t* init_idx);
 
 /* subsample_cpp (src/Utils.cpp:32-68).  method "kmeans": U is s x (d+1) = [centres, cluster sizes];
  * "random": U is s x d = X[init_idx,] (no size column, as the reference).  assign (n, optional) and
- * iters (optional) report the final assignment and the Lloyd iterations run. */
+ * iters (optional) report the final assignment and the Lloyd iterations run.
+ * nstart > 1 (stats::kmeans's restarts): nstart Lloyd runs, start 0 from init_idx (or the seed's default rows),
+ * start q from the default rows of a seed derived from (seed, q); the run with the smallest total within-cluster
+ * sum of squares (exact fixed-point sum: the same choice on every rank) is returned.
+ * Limits: r <= 16 for the LAE kernel ("lae"), r <= 32 for the SE kernel and KNN; sparse matrices handed in by the
+ * caller (flgp_graph_laplacian, flgp_spectrum_from_z) need 0 <= column < s and strictly ascending columns in every
+ * row (what dgRMatrix stores) -- anything else is rejected with status 2. */
 int flgp_subsample(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, const char* method, int iter_max,
                    int nstart, const int32_t* init_idx, uint64_t seed, double* U, int32_t* assign, int* iters);
 

@@ -61,6 +61,7 @@ def main():
         print("multi_gpu_check world=%d: iters=%d U/Z bit-exact=%s, dy=%.2e dcov=%.2e -> %s" %
               (world, ep1.kmeans_iters, np.array_equal(Zx, Z1.data), e_y, e_c, "OK" if ok else "FAIL"))
     ok &= large_d_case(rank, local, world, ctx)
+    ok &= large_s_case(rank, local, world, ctx)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
@@ -91,6 +92,37 @@ def large_d_case(rank, local, world, ctx):
         ok &= np.array_equal(np.concatenate([g["Zj"] for g in gathered]), Z1.indices)
         ok &= np.array_equal(np.concatenate([g["Zx"] for g in gathered]), Z1.data)
         print("multi_gpu_check world=%d large-d (d=16): U/Z bit-exact -> %s" % (world, "OK" if ok else "FAIL"))
+    return ok
+
+
+def large_s_case(rank, local, world, ctx):
+    """s = 1100, K = 100: the iterative eigensolver (chfsi.cu) with its filter columns sharded over the ranks and
+    all-gathered; every column is computed by one rank with the single-GPU instruction sequence, so eigenvalues and
+    predictions must be BIT-identical to the one-GPU run (only the K x K tail all-reduce can differ in the last bits)."""
+    n, m, s, r, K = 150_001, 900, 1100, 3, 100
+    X, Y, _ = make("C4", 99, n=n)
+    lo, hi = shard_bounds(n, world, rank)
+    init = F.default_init(n, s, 9)
+    ep = F.heat_kernel_spectrum_sharded(np.asfortranarray(X[lo:hi]), n, lo, s, r, K, init_idx=init, iter_max=15, ctx=ctx)
+    m_local = max(0, min(hi - lo, m - lo))
+    y, cov = F.regression_fixed(ep, Y[lo:lo + m_local], m, K, (10.0, 0.01), 1e-5)
+    rows = ep.rows(np.arange(0, hi - lo, 997, dtype=np.int32))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(vals=ep.values, y=y, rows=rows))
+    ok = True
+    if rank == 0:
+        ctx1 = F.Context(local)
+        ep1 = F.heat_kernel_spectrum_sharded(X, n, 0, s, r, K, init_idx=init, iter_max=15, ctx=ctx1)
+        y1, _ = F.regression_fixed(ep1, Y[:m], m, K, (10.0, 0.01), 1e-5)
+        idx1 = np.concatenate([np.arange(lo_, hi_, 997) for lo_, hi_ in (shard_bounds(n, world, q) for q in range(world))])
+        rows1 = ep1.rows(idx1.astype(np.int32))
+        bit_vals = all(np.array_equal(g["vals"], ep1.values) for g in gathered)
+        bit_rows = np.array_equal(np.concatenate([g["rows"] for g in gathered]), rows1)
+        yy = np.concatenate([g["y"] for g in gathered])
+        e_y = np.abs(yy - y1).max() / np.abs(y1).max()
+        ok = bit_vals and bit_rows and e_y < 1e-9
+        print("multi_gpu_check world=%d large-s (s=%d, iterative eigensolver, sharded filter): eigenvalues bit-exact=%s, "
+              "eigenvector rows bit-exact=%s, dy=%.2e -> %s" % (world, s, bit_vals, bit_rows, e_y, "OK" if ok else "FAIL"))
     return ok
 
 

@@ -872,3 +872,50 @@ def test_c3_headline_shape_against_oracle(flgp, oracle):
     Zj, Zx = _csr_parts(ep.Z())
     assert np.array_equal(Zj, I["Zj"]) and np.array_equal(Zx, I["Zx"])
     np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
+
+
+# ------------------------------------------------------------------------------------------- round 2: ADVICE items
+def test_caller_supplied_csr_is_validated_and_scaled(flgp, oracle):
+    """flgp_spectrum_from_z / flgp_graph_laplacian on a caller's sparse matrix: unsorted scipy rows are sorted by the
+    binding, bad indices are rejected by the library, and values far outside [0, 1] keep full accuracy (the
+    fixed-point scale follows max |Z| and max w instead of a constant)."""
+    import scipy.sparse as sp
+
+    rng = np.random.default_rng(8)
+    n, s, r, K = 3000, 60, 4, 12
+    cols = np.stack([rng.choice(s, r, replace=False) for _ in range(n)]).astype(np.int32)   # unsorted rows
+    vals = rng.uniform(0.5, 40.0, (n, r)) * rng.choice([1.0, 1.0, 1.0, -0.2], (n, r))        # large, some negative
+    Z = sp.csr_matrix((vals.reshape(-1), cols.reshape(-1), np.arange(0, n * r + 1, r)), shape=(n, s))
+    res = flgp.spectrum_from_Z_cpp(Z, K, root=False)
+    # dense reference: sigma^2 of A = Z diag(1/sqrt(|colsum| + 1e-9))
+    Zd = Z.toarray()
+    c = Zd.sum(0)
+    A = Zd / np.sqrt(np.abs(c) + 1e-9)
+    sv = np.linalg.svd(A, compute_uv=False)[:K] ** 2
+    np.testing.assert_allclose(res.values if hasattr(res, "values") else res["values"], sv, rtol=1e-9)
+    # a column index outside [0, s) and a duplicated column are rejected
+    bad = cols.copy()
+    bad.sort(axis=1)
+    bad[5, r - 1] = s
+    with pytest.raises(flgp.FlgpError, match="outside"):
+        flgp.spectrum_from_Z_cpp((bad, np.abs(vals), s), K)
+    dup = np.sort(cols, axis=1)
+    dup[7, 1] = dup[7, 0]
+    with pytest.raises(flgp.FlgpError, match="ascending"):
+        flgp.graphLaplacian_cpp((dup, np.abs(vals), s), "rw")
+
+
+def test_kmeans_nstart_keeps_the_best_run(flgp, oracle):
+    """nstart > 1 = stats::kmeans's restarts: the returned run has the smallest total within-cluster sum of squares of
+    the nstart runs (each run is the Lloyd contract from its own start rows)."""
+    X, _ = swiss(5000, 4)
+    s = 25
+    U1 = flgp.subsample_cpp(X, s, "kmeans", nstart=1, seed=11)
+    U4 = flgp.subsample_cpp(X, s, "kmeans", nstart=4, seed=11)
+
+    def wss(U):
+        D = ((X[:, None, :] - U[None, :, :3]) ** 2).sum(-1)
+        return D.min(1).sum()
+
+    assert wss(U4) <= wss(U1) * (1 + 1e-12)
+    assert U4[:, 3].sum() == len(X)
