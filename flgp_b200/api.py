@@ -522,6 +522,81 @@ def mma_minimize(f, x0, lb, ub, xtol_rel: float = 1e-5, maxeval: int = 1000):
     return x, minf.value, nev.value
 
 
+def cobyla_minimize_1d(f, x0: float, lb: float = 1e-3, ub: float = float("inf"), xtol_rel: float = 1e-4,
+                       maxeval: int = 1000):
+    """The library's one-variable restatement of NLOPT_LN_COBYLA (src/train.cpp:38-71) on a Python objective f(t).
+    Host only.  Returns (t, minimum, evaluations)."""
+    from ._lib import OBJECTIVE_FN, load
+
+    def cb(nn, xp, gp, _):
+        return float(f(float(xp[0])))
+
+    cfn = OBJECTIVE_FN(cb)
+    x = np.array([x0], dtype=np.float64)
+    minf = C.c_double()
+    nev = C.c_int()
+    check(load().flgp_cobyla_minimize_1d(cfn, None, lb, ub, _pf(x), C.byref(minf), xtol_rel, maxeval, C.byref(nev)))
+    return float(x[0]), minf.value, nev.value
+
+
+def logit_objective(eigenpair: EigenPair, Y, m_total: int, K: int, t: float, sigma: float = 1e-3,
+                    approach: str = "posterior", N=None) -> float:
+    """negative_marginal_likelihood_logit_cpp / negative_log_posterior_logit_cpp at diffusion time t
+    (src/train.cpp:14-36) on the m labelled rows (labels 0/1, N trials per row)."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    obj = C.c_double()
+    check(eigenpair.ctx._lib.flgp_logit_objective(eigenpair._h, _pf(Y), _pf(Nv), m_total, K, sigma, _b(approach), t,
+                                                  C.byref(obj)))
+    return obj.value
+
+
+def train_lae_logit_gp(eigenpair: EigenPair, Y, m_total: int, K: int, sigma: float = 1e-3,
+                       approach: str = "posterior", t0: Optional[float] = None, N=None):
+    """train_lae_logit_gp_cpp (src/train.cpp:38-71).  Returns (t, obj, evaluations)."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    t = np.array([np.nan if t0 is None else t0], dtype=np.float64)
+    obj = C.c_double()
+    nev = C.c_int()
+    check(eigenpair.ctx._lib.flgp_train_logit(eigenpair._h, _pf(Y), _pf(Nv), m_total, K, sigma, _b(approach), _pf(t),
+                                              C.byref(obj), C.byref(nev)))
+    return float(t[0]), obj.value, nev.value
+
+
+def fit_lae_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma: float = 1e-3, approach="posterior",
+                          models=None, output_cov: bool = False, nstart: int = 1, *, t: Optional[float] = None,
+                          init_idx=None, seed: int = 0, iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_lae_logit_gp_rcpp (R/Fit.R:528-545 -> src/Fit.cpp:521-600): spectrum, empirical-Bayes training of the diffusion
+    time t (COBYLA restatement; t given: used as is), Laplace posterior of the test rows.  The reference's Y_pred comes
+    from a Polya-Gamma Gibbs sampler on R's RNG (stochastic) and is not produced; the
+    deterministic part of the result list is: posterior$mean, posterior$cov, pars (= t), optional C."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    mean = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    Cm = np.zeros((m + m_new, m), order="F") if output_cov else None
+    tt = np.array([np.nan if t is None else t], dtype=np.float64)
+    obj = C.c_double()
+    check(ctx._lib.flgp_fit_lae_logit(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, _pf(Nv), sigma,
+                                      _b(approach), _b(mo["subsample"]), _b(mo["kernel"]), _gl(mo["gl"]),
+                                      int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed, _pf(tt),
+                                      _pf(mean), _pf(cov), _pf(Cm), C.byref(obj)))
+    res = {"posterior": {"mean": mean, "cov": cov}, "pars": float(tt[0]), "obj": obj.value}
+    if output_cov:
+        res["C"] = Cm
+    return res
+
+
 def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, approach="posterior",
                                noise="same", models=None, output_cov: bool = False, nstart: int = 1, *,
                                pars: Optional[Sequence[float]] = None, init_idx=None, seed: int = 0,

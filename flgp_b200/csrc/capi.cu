@@ -1505,6 +1505,123 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
   });
 }
 
+// the m labelled rows of the lifted eigenvectors on the host (m x K row-major), gathered over the ranks
+static LogitTrain logit_train_prepare(flgp_spectrum* sp, const double* Y, const double* N, int64_t m_total, int K,
+                                      double sigma, bool posterior) {
+  Ctx* c = sp->c;
+  need(K >= 1 && K <= sp->K, "K exceeds the number of computed eigenpairs");
+  need(m_total >= 1 && m_total <= sp->n_total && m_total <= 8192, "classification: need 1 <= m <= 8192 labelled rows");
+  const int KK = sp->K, m = (int)m_total;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(sp->n_local, m_total - sp->row_offset));
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local * KK, 1)), Vall((size_t)m * KK);
+  lift_rows_run(c, sp->r, sp->Zj.p, sp->Zx.p, sp->w.p, sp->Wm.p, KK, nullptr, m_local, V1.p, KK, false);
+  Vall.zero(c->stream);
+  if (m_local > 0)
+    FLGP_CUDA(cudaMemcpyAsync(Vall.p + (size_t)sp->row_offset * KK, V1.p, sizeof(double) * m_local * KK,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  comm_allreduce_f64(c, Vall.p, (size_t)m * KK);
+  std::vector<double> Vh((size_t)m * KK);
+  Vall.download(Vh.data(), Vh.size(), c->stream);
+  sync(c);
+  LogitTrain T;
+  T.m = m;
+  T.K = K;
+  T.sigma = sigma;
+  T.posterior = posterior;
+  T.V.resize((size_t)m * K);
+  for (int i = 0; i < m; ++i)
+    for (int k = 0; k < K; ++k) T.V[(size_t)i * K + k] = Vh[(size_t)i * KK + k];
+  T.ev.resize(K);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - sp->values[k];
+  T.Y.assign(Y, Y + m);
+  T.N.assign(m, 1.0);
+  if (N) T.N.assign(N, N + m);
+  return T;
+}
+
+int flgp_logit_objective(flgp_spectrum* h, const double* Y, const double* N, int64_t m_total, int K, double sigma,
+                         const char* approach, double t, double* obj) {
+  return guard([&] {
+    need(h && Y && obj, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const LogitTrain T = logit_train_prepare(h, Y, N, m_total, K, sigma, post);
+    *obj = logit_objective(T, t);
+  });
+}
+
+int flgp_cobyla_minimize_1d(flgp_objective_fn f, void* data, double lb, double ub, double* x, double* minf,
+                            double xtol_rel, int maxeval, int* nevals) {
+  return guard([&] {
+    need(f && x, "null argument");
+    need(lb <= *x && *x <= ub, "the start lies outside the bounds");
+    auto fn = [&](double t) { return f(1, &t, nullptr, data); };
+    *x = cobyla_minimize_1d(fn, *x, lb, ub, xtol_rel > 0 ? xtol_rel : 1e-4, maxeval > 0 ? maxeval : 1000, minf, nevals);
+  });
+}
+
+int flgp_train_logit(flgp_spectrum* h, const double* Y, const double* N, int64_t m_total, int K, double sigma,
+                     const char* approach, double* t_io, double* obj, int* nevals) {
+  return guard([&] {
+    need(h && Y && t_io, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const LogitTrain T = logit_train_prepare(h, Y, N, m_total, K, sigma, post);
+    double t0 = *t_io;
+    if (!(t0 == t0) || t0 < 0.0) t0 = 10.0;  // src/train.cpp:41-43
+    double fmin = 0.0;
+    auto fn = [&](double t) { return logit_objective(T, t); };
+    *t_io = cobyla_minimize_1d(fn, std::max(t0, 1e-3), 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nevals);
+    if (obj) *obj = -fmin;  // ReturnValue(t, -obj), src/train.cpp:70
+  });
+}
+
+int flgp_fit_lae_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m, int64_t m_new,
+                       int d, int s, int r, int K, const double* N, double sigma, const char* approach,
+                       const char* subsample, const char* kernel, int gl, int root, int nstart, int iter_max,
+                       const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
+                       double* C_out, double* obj) {
+  if (K < 0) K = s;  // src/Fit.cpp:538-540
+  bool post = true;
+  if (approach_flag(approach, &post)) {
+    g_err = "This model selection approach is not supported!";
+    return 2;
+  }
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, m, X_new, m_new, d, s, r, K, subsample, kernel, gl, root, nstart, 0.1,
+                                     iter_max, init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  return guard([&] {
+    need(Y && t_io, "null argument");
+    if (!(*t_io == *t_io)) {  // NaN: train t (src/Fit.cpp:548-563)
+      int rc1 = flgp_train_logit(h, Y, N, m, K, sigma, approach, t_io, obj, nullptr);
+      if (rc1) fail(rc1, "%s", g_err.c_str());
+    } else if (obj) {
+      int rc1 = flgp_logit_objective(h, Y, N, m, K, sigma, approach, *t_io, obj);
+      if (rc1) fail(rc1, "%s", g_err.c_str());
+      *obj = -*obj;
+    }
+    const int64_t n = m + m_new;
+    if (post_mean) {  // posterior_distribution_classification on the test rows (src/Fit.cpp:566-582)
+      std::vector<double> mean(n), cov(n);
+      int rc2 = flgp_classification_posterior_fixed(h, Y, m, K, *t_io, sigma, 1e-5, 100, mean.data(),
+                                                    post_cov ? cov.data() : nullptr);
+      if (rc2) fail(rc2, "%s", g_err.c_str());
+      if (m_new) std::memcpy(post_mean, mean.data() + m, sizeof(double) * m_new);
+      if (post_cov && m_new) std::memcpy(post_cov, cov.data() + m, sizeof(double) * m_new);
+    }
+    if (C_out) {  // output_cov: C = [Cvv + sigma I; Cnv], n x m (src/Fit.cpp:566-573)
+      std::vector<int32_t> i0(n), i1(m);
+      for (int64_t i = 0; i < n; ++i) i0[i] = (int32_t)i;
+      for (int64_t i = 0; i < m; ++i) i1[i] = (int32_t)i;
+      int rc3 = flgp_hk_from_spectrum(h, K, *t_io, i0.data(), n, i1.data(), m, C_out);
+      if (rc3) fail(rc3, "%s", g_err.c_str());
+      for (int64_t i = 0; i < m; ++i) C_out[i + n * i] += sigma;
+    }
+  });
+}
+
 int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
                                         double sigma, double tol, int max_iter, double* mean, double* cov) {
   return guard([&] {

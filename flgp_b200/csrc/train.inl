@@ -294,3 +294,143 @@ double train_regression(const RegTrain& T, bool posterior, double* pars_io, int*
   if (nevals) *nevals = nev;
   return -minf;
 }
+
+// ---- binary GP classifier: training of the diffusion time t (second half) -----------------------
+//   laplace_mll       marginal_log_likelihood_logit_la_cpp (/root/reference/src/train.cpp:716-760): Newton iterations for
+//                     the posterior mode (GPML algorithm 3.1) from f = 0, stop when |f - f_new|_1 < tol; the value uses
+//                     `a` and chol(B) of the LAST Newton step, as the reference does.
+//   logit_objective   negative_marginal_likelihood_logit_cpp / negative_log_posterior_logit_cpp (src/train.cpp:14-36):
+//                     C = V1 diag(exp(-t (1 - values))) V1^T + sigma I on the m labelled rows; prior of PostOFData
+//                     (src/train.h:129-141): p log(t + 1e-9) + (t / tau)^(-q), p = 1e-2, q = 10, tau = 2.
+//   cobyla_minimize_1d  the optimiser behind nlopt_create(NLOPT_LN_COBYLA, 1) of train_lae_logit_gp_cpp
+//                     (src/train.cpp:38-71): t0 = 10, lb = 1e-3, ub = +inf, xtol_rel = 1e-4.  NLopt is an un-vendored
+//                     dependency (parity unpinned); this is Powell's COBYLA iteration written out for ONE variable: a
+//                     two-point simplex, the linear model through it, a trust-region step of length rho from the best
+//                     vertex (clipped to the bounds), rho kept while the step pays off and divided by 10 otherwise,
+//                     from rhobeg (NLopt's default initial step: 0.75 (t0 - lb) here) down to rhoend = xtol_rel rhobeg.
+//                     Trained t agrees with NLopt / scipy COBYLA to the optimiser's tolerance on a unimodal objective.
+struct LogitTrain {
+  int m = 0, K = 0;
+  double sigma = 1e-3;
+  bool posterior = true;
+  double p = 1e-2, q = 10.0, tau = 2.0;
+  std::vector<double> V;   // m x K row-major: the labelled rows of the lifted eigenvectors
+  std::vector<double> ev;  // 1 - values[:K]
+  std::vector<double> Y, N;
+};
+
+double laplace_mll(const std::vector<double>& C, const double* Y, const double* N, int m, double tol, int max_iter) {
+  std::vector<double> f(m, 0.0), pi(m), W(m), sw(m), b(m), cb(m), a(m, 0.0), fn(m), B((size_t)m * m);
+  double logdet = 0.0;
+  for (int iter = 0; iter < max_iter; ++iter) {
+    for (int i = 0; i < m; ++i) {
+      pi[i] = 1.0 / (1.0 + std::exp(-f[i]));
+      W[i] = N[i] * pi[i] * (1.0 - pi[i]);
+      sw[i] = std::sqrt(W[i]);
+    }
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) B[i + (size_t)m * j] = (sw[i] * C[i + (size_t)m * j]) * sw[j] + (i == j ? 1.0 : 0.0);
+    if (!chol_lower(B, m)) fail(2, "classification: the Newton system is not positive definite");
+    logdet = 0.0;
+    for (int i = 0; i < m; ++i) logdet += std::log(B[i + (size_t)m * i] + 1e-9);
+    for (int i = 0; i < m; ++i) b[i] = W[i] * f[i] + Y[i] * (1.0 - pi[i]) + (N[i] - Y[i]) * (-pi[i]);
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += C[i + (size_t)m * j] * b[j];
+      cb[i] = sw[i] * acc;
+    }
+    chol_solve(B, m, cb.data(), 1);
+    for (int i = 0; i < m; ++i) a[i] = b[i] - sw[i] * cb[i];
+    double diff = 0.0;
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += C[i + (size_t)m * j] * a[j];
+      fn[i] = acc;
+      diff += std::fabs(f[i] - acc);
+    }
+    f = fn;
+    if (diff < tol) break;
+  }
+  double amll = 0.0;
+  for (int i = 0; i < m; ++i) amll += a[i] * f[i];
+  amll *= -0.5;
+  for (int i = 0; i < m; ++i) {
+    const double p1 = 1.0 / (1.0 + std::exp(-f[i]));
+    amll += Y[i] * std::log(p1) + (N[i] - Y[i]) * std::log(1.0 - p1);
+  }
+  return amll - logdet;
+}
+
+double logit_objective(const LogitTrain& T, double t) {
+  const int m = T.m, K = T.K;
+  std::vector<double> lam(K), C((size_t)m * m);
+  for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * T.ev[k]);
+  for (int j = 0; j < m; ++j)
+    for (int i = j; i < m; ++i) {
+      double acc = 0.0;
+      const double* vi = &T.V[(size_t)i * K];
+      const double* vj = &T.V[(size_t)j * K];
+      for (int k = 0; k < K; ++k) acc += (vi[k] * lam[k]) * vj[k];
+      C[i + (size_t)m * j] = C[j + (size_t)m * i] = acc + (i == j ? T.sigma : 0.0);
+    }
+  const double mll = laplace_mll(C, T.Y.data(), T.N.data(), m, 1e-5, 100);
+  double pr = 0.0;
+  if (T.posterior) pr = T.p * std::log(t + 1e-9) + std::pow(t / T.tau, -T.q);
+  return -mll + pr;
+}
+
+template <class F>
+double cobyla_minimize_1d(F&& f, double x0, double lb, double ub, double xtol_rel, int maxeval, double* fmin_out,
+                          int* nevals_out) {
+  // NLopt's default initial step for one bounded variable (nlopt_set_default_initial_step)
+  double step = HUGE_VAL;
+  if (std::isfinite(ub) && std::isfinite(lb) && (ub - lb) * 0.25 < step && ub > lb) step = (ub - lb) * 0.25;
+  if (std::isfinite(ub) && ub - x0 < step && ub > x0) step = (ub - x0) * 0.75;
+  if (std::isfinite(lb) && x0 - lb < step && x0 > lb) step = (x0 - lb) * 0.75;
+  if (!std::isfinite(step)) step = std::fabs(x0);
+  if (!(step > 0.0)) step = 1.0;
+  const double rhobeg = step, rhoend = xtol_rel * rhobeg;
+  auto clip = [&](double x) { return std::min(ub, std::max(lb, x)); };
+  int nev = 0;
+  double xa = clip(x0), fa = f(xa);
+  ++nev;
+  double xb = (xa + rhobeg <= ub) ? xa + rhobeg : xa - rhobeg, fb = f(clip(xb));
+  xb = clip(xb);
+  ++nev;
+  if (fb < fa) {
+    std::swap(xa, xb);
+    std::swap(fa, fb);
+  }
+  double rho = rhobeg;
+  while (nev < maxeval) {
+    double dir;  // descent direction of the linear model through the simplex
+    if (xb != xa && fb != fa) dir = ((fb - fa) / (xb - xa) > 0.0) ? -1.0 : 1.0;
+    else dir = (xb > xa) ? -1.0 : 1.0;
+    double xt = clip(xa + dir * rho);
+    if (xt == xa) xt = clip(xa - dir * rho);  // pinned at a bound: the only move is inwards
+    bool improved = false;
+    if (xt != xa) {
+      const double ft = f(xt);
+      ++nev;
+      if (ft < fa) {
+        const double predicted = (xb != xa) ? std::fabs((fb - fa) / (xb - xa)) * std::fabs(xt - xa) : 0.0;
+        improved = (fa - ft) >= 0.1 * predicted;  // the model pays off at this radius: keep rho
+        xb = xa;
+        fb = fa;
+        xa = xt;
+        fa = ft;
+      } else {
+        xb = xt;  // the far vertex moves to the trial point: the simplex stays within rho of the best vertex
+        fb = ft;
+      }
+    }
+    if (!improved) {
+      if (rho <= rhoend) break;
+      rho *= 0.1;
+      if (rho <= 1.5 * rhoend) rho = rhoend;
+    }
+  }
+  if (fmin_out) *fmin_out = fa;
+  if (nevals_out) *nevals_out = nev;
+  return xa;
+}

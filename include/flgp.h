@@ -229,6 +229,33 @@ int flgp_posterior_distribution_classification(flgp_ctx* ctx, const double* C11,
                                                const double* Y, int m, int64_t m_new, double tol, int max_iter,
                                                double* mean, double* cov);
 
+/* ---- training of the binary GP classifier (fit_lae_logit_gp_cpp, src/Fit.cpp:521-600) -------- */
+/* negative_marginal_likelihood_logit_cpp ("marginal") / negative_log_posterior_logit_cpp ("posterior"),
+ * src/train.cpp:14-36: minus the Laplace-approximate marginal log-likelihood of the m labelled rows at diffusion time t
+ * (marginal_log_likelihood_logit_la_cpp, src/train.cpp:716-760; N = trials per row, NULL = all 1), plus the prior
+ * p log(t + 1e-9) + (t / tau)^(-q) with the defaults of PostOFData (p = 1e-2, q = 10, tau = 2).  Single process or
+ * every rank with the same Y / N (the labelled rows are gathered). */
+int flgp_logit_objective(flgp_spectrum* h, const double* Y, const double* N, int64_t m_total, int K, double sigma,
+                         const char* approach, double t, double* obj);
+/* train_lae_logit_gp_cpp (src/train.cpp:38-71): NLopt's LN_COBYLA on t from t0 = 10 (or *t_io when finite and >= 0),
+ * lb = 1e-3, ub = +inf, xtol_rel = 1e-4.  *t_io <- optimum, *obj <- -(minimum).  NLopt is an un-vendored dependency:
+ * the optimiser is Powell's COBYLA iteration restated for one variable (flgp_cobyla_minimize_1d), so parity with the
+ * reference is to optimiser tolerance. */
+int flgp_train_logit(flgp_spectrum* h, const double* Y, const double* N, int64_t m_total, int K, double sigma,
+                     const char* approach, double* t_io, double* obj, int* nevals);
+/* The optimiser itself behind an nlopt-style callback (n = 1); host only, no GPU needed. */
+int flgp_cobyla_minimize_1d(flgp_objective_fn f, void* data, double lb, double ub, double* x, double* minf,
+                            double xtol_rel, int maxeval, int* nevals);
+/* fit_lae_logit_gp_cpp (src/Fit.cpp:521-600) without the Polya-Gamma label sampler (R RNG): spectrum, training of t
+ * (*t_io = NaN trains; a finite value is used as given), then posterior_distribution_classification on the m_new test
+ * rows: post_mean / post_cov (m_new each, may be NULL).  C_out (may be NULL): the n x m matrix [Cvv + sigma I; Cnv] of
+ * output_cov = TRUE.  *obj (may be NULL) <- the objective as the reference prints it (larger is better). */
+int flgp_fit_lae_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m, int64_t m_new,
+                       int d, int s, int r, int K, const double* N, double sigma, const char* approach,
+                       const char* subsample, const char* kernel, int gl, int root, int nstart, int iter_max,
+                       const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
+                       double* C_out, double* obj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -694,3 +694,106 @@ def posterior_distribution_classification(C11, C21, C22, Y, tol=1e-5, max_iter=1
     beta = sw[:, None] * sla.cho_solve(cf, np.eye(m)) * sw[None, :]
     cov = np.asarray(C22) - ((C21 @ beta) * C21).sum(axis=1)
     return mean, cov
+
+
+# ------------------------------------------------------------------ binary GP classifier: training of t (TEST ORACLE)
+def laplace_mll(Cm, Y, N=None, tol=1e-5, max_iter=100):
+    """marginal_log_likelihood_logit_la_cpp (src/train.cpp:716-760), literal: Newton from f = 0, value from the LAST
+    Newton step's a and chol(B)."""
+    import scipy.linalg as sla
+
+    Cm = np.asarray(Cm, dtype=np.float64)
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1)
+    m = Y.size
+    N = np.ones(m) if N is None else np.asarray(N, dtype=np.float64).reshape(-1)
+    f = np.zeros(m)
+    a = np.zeros(m)
+    Lb = np.eye(m)
+    for _ in range(max_iter):
+        pi = 1.0 / (1.0 + np.exp(-f))
+        W = N * pi * (1.0 - pi)
+        sw = np.sqrt(W)
+        B = (sw[:, None] * Cm) * sw[None, :]
+        B[np.diag_indices(m)] += 1.0
+        Lb = sla.cholesky(B, lower=True)
+        b = W * f + Y * (1.0 - pi) + (N - Y) * (-pi)
+        a = b - sw * sla.cho_solve((Lb, True), sw * (Cm @ b))
+        f_new = Cm @ a
+        done = np.abs(f - f_new).sum() < tol
+        f = f_new
+        if done:
+            break
+    pi = 1.0 / (1.0 + np.exp(-f))
+    amll = -0.5 * float(a @ f)
+    amll += float((Y * np.log(pi)).sum() + ((N - Y) * np.log(1.0 - pi)).sum())
+    amll -= float(np.log(np.diag(Lb) + 1e-9).sum())
+    return amll
+
+
+def logit_objective(V, values, Y, idx, K, t, sigma=1e-3, approach="posterior", N=None, prior=(1e-2, 10.0, 2.0)):
+    """negative_marginal_likelihood_logit_cpp / negative_log_posterior_logit_cpp (src/train.cpp:14-36)."""
+    Cm = hk_from_spectrum(V, values, K, t, idx, idx)
+    Cm[np.diag_indices(len(idx))] += sigma
+    mll = laplace_mll(Cm, Y, N)
+    if approach == "marginal":
+        return -mll
+    p, q, tau = prior
+    return -mll + p * np.log(t + 1e-9) + (t / tau) ** (-q)
+
+
+def cobyla_minimize_1d(f, x0, lb=1e-3, ub=np.inf, xtol_rel=1e-4, maxeval=1000):
+    """Twin of the library's one-variable restatement of NLOPT_LN_COBYLA (csrc/train.inl: cobyla_minimize_1d): two-point
+    simplex, linear model, trust-region step rho from the best vertex clipped to the bounds, rho / 10 when a step does
+    not pay off, from NLopt's default initial step down to xtol_rel times it.  Returns (x, fmin, evaluations)."""
+    step = np.inf
+    if np.isfinite(ub) and np.isfinite(lb) and (ub - lb) * 0.25 < step and ub > lb:
+        step = (ub - lb) * 0.25
+    if np.isfinite(ub) and ub - x0 < step and ub > x0:
+        step = (ub - x0) * 0.75
+    if np.isfinite(lb) and x0 - lb < step and x0 > lb:
+        step = (x0 - lb) * 0.75
+    if not np.isfinite(step):
+        step = abs(x0)
+    if not step > 0.0:
+        step = 1.0
+    rhobeg, rhoend = step, xtol_rel * step
+    clip = lambda x: min(ub, max(lb, x))  # noqa: E731
+    xa = clip(x0)
+    fa = f(xa)
+    xb = clip(xa + rhobeg if xa + rhobeg <= ub else xa - rhobeg)
+    fb = f(xb)
+    nev = 2
+    if fb < fa:
+        xa, xb, fa, fb = xb, xa, fb, fa
+    rho = rhobeg
+    while nev < maxeval:
+        if xb != xa and fb != fa:
+            direction = -1.0 if (fb - fa) / (xb - xa) > 0.0 else 1.0
+        else:
+            direction = -1.0 if xb > xa else 1.0
+        xt = clip(xa + direction * rho)
+        if xt == xa:
+            xt = clip(xa - direction * rho)
+        improved = False
+        if xt != xa:
+            ft = f(xt)
+            nev += 1
+            if ft < fa:
+                predicted = abs((fb - fa) / (xb - xa)) * abs(xt - xa) if xb != xa else 0.0
+                improved = (fa - ft) >= 0.1 * predicted
+                xb, fb, xa, fa = xa, fa, xt, ft
+            else:
+                xb, fb = xt, ft
+        if not improved:
+            if rho <= rhoend:
+                break
+            rho *= 0.1
+            if rho <= 1.5 * rhoend:
+                rho = rhoend
+    return xa, fa, nev
+
+
+def train_lae_logit(V, values, Y, idx, K, sigma=1e-3, approach="posterior", t0=10.0, N=None):
+    """train_lae_logit_gp_cpp (src/train.cpp:38-71): (t, -minimum, evaluations)."""
+    t, fmin, nev = cobyla_minimize_1d(lambda t: logit_objective(V, values, Y, idx, K, t, sigma, approach, N), t0)
+    return t, -fmin, nev

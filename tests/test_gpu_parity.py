@@ -919,3 +919,43 @@ def test_kmeans_nstart_keeps_the_best_run(flgp, oracle):
 
     assert wss(U4) <= wss(U1) * (1 + 1e-12)
     assert U4[:, 3].sum() == len(X)
+
+
+@pytest.mark.parametrize("approach", ["posterior", "marginal"])
+def test_fit_lae_logit_config1_end_to_end(flgp, oracle, approach):
+    """BASELINE config 1 end to end (README GPC rings: n=4800, d=2, m=100, s=600, r=3, K=100, fit_lae_logit_gp_rcpp):
+    spectrum -> training of the diffusion time t (COBYLA restatement on the Laplace objective) -> Laplace posterior of
+    the test rows, against the oracle twin run on the library's own eigenvectors: the objective to 1e-8, the trained
+    t to the optimiser's tolerance, posterior mean / variance at the trained t to 1e-7."""
+    from flgp_b200.datasets import make
+
+    X, lab, cfg = make("C1")
+    m, s, r, K, sigma = cfg["m"], cfg["s"], cfg["r"], cfg["K"], 1e-3
+    init = _init(len(X), s, 1)
+    res = flgp.fit_lae_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, sigma=sigma, approach=approach, init_idx=init,
+                                     iter_max=50, output_cov=True)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=50)
+    V, values = ep.vectors, ep.values
+    n = len(X)
+    idx0 = np.arange(m, dtype=np.int32)
+    for t in (2.0, 10.0, 40.0):
+        got = flgp.logit_objective(ep, lab[:m], m, K, t, sigma, approach)
+        want = oracle.logit_objective(V, values, lab[:m], idx0, K, t, sigma, approach)
+        assert abs(got - want) <= 1e-8 * max(1.0, abs(want))
+    t_o, obj_o, nev_o = oracle.train_lae_logit(V, values, lab[:m], idx0, K, sigma, approach)
+    t_l, obj_l, nev_l = flgp.train_lae_logit_gp(ep, lab[:m], m, K, sigma, approach)
+    assert abs(t_l - t_o) <= 1e-3 * max(1.0, t_o) and abs(obj_l - obj_o) <= 1e-6 * max(1.0, abs(obj_o))
+    assert abs(res["pars"] - t_l) <= 1e-12 * t_l and abs(res["obj"] - obj_l) <= 1e-9 * max(1.0, abs(obj_l))
+    # posterior of the test rows at the trained t (src/Fit.cpp:563-582)
+    t = res["pars"]
+    idx1 = np.arange(m, n, dtype=np.int32)
+    C11 = oracle.hk_from_spectrum(V, values, K, t, idx0, idx0)
+    C11[np.diag_indices(m)] += sigma
+    C21 = oracle.hk_from_spectrum(V, values, K, t, idx1, idx0)
+    C22 = ((V[m:, :K] * np.exp(-t * (1.0 - values[:K]))) * V[m:, :K]).sum(axis=1) + sigma
+    mo, co = oracle.posterior_distribution_classification(C11, C21, C22, lab[:m])
+    np.testing.assert_allclose(res["posterior"]["mean"], mo, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(mo).max()))
+    np.testing.assert_allclose(res["posterior"]["cov"], co, rtol=1e-7, atol=1e-8 * max(1.0, np.abs(co).max()))
+    np.testing.assert_allclose(res["C"][:m], C11, rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(res["C"][m:], C21, rtol=1e-8, atol=1e-10)
+    assert np.mean((res["posterior"]["mean"] > 0) == (lab[m:] > 0.5)) > 0.9   # README: error rate 0.027 after training

@@ -95,3 +95,56 @@ def test_oracle_train_regression_improves_and_respects_bounds(oracle):
     f, _ = oracle.regression_objective(V, values, Y, idx, K, x, 1e-5, "posterior")
     f0, _ = oracle.regression_objective(V, values, Y, idx, K, (10.0, 1.0), 1e-5, "posterior")
     assert abs(f + obj) < 1e-9 and f < f0 - 50.0
+
+
+# ------------------------------------------------------------------ logit training: COBYLA restatement (host only)
+def _toy_logit_problem(seed=3, m=60, K=25):
+    rng = np.random.default_rng(seed)
+    n = 400
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.2, 1.0, K))[::-1]
+    values[0] = 1.0
+    idx = np.arange(m, dtype=np.int32)
+    f_true = V[:m, 1] * 1.5 + V[:m, 2]
+    Y = (f_true + 0.3 * rng.standard_normal(m) > 0).astype(np.float64)
+    return V, values, Y, idx
+
+
+def test_cobyla_1d_library_matches_python_twin_and_scipy(oracle):
+    """The one-variable COBYLA restatement: library (host code of libflgp_b200.so) == Python twin evaluation for
+    evaluation, and both reach scipy's COBYLA optimum (an independent implementation of Powell's method) to the
+    optimiser's tolerance on the Laplace objective of a small classifier and on two analytic functions."""
+    import scipy.optimize as so
+    import flgp_b200 as F
+
+    V, values, Y, idx = _toy_logit_problem()
+    K = V.shape[1]
+    fobj = lambda t: oracle.logit_objective(V, values, Y, idx, K, t, 1e-3, "posterior")  # noqa: E731
+    for f, x0 in ((fobj, 10.0), (lambda t: (np.log(t) - 1.3) ** 2 + 0.01 * t, 10.0), (lambda t: abs(t - 0.4) + 1.0, 10.0)):
+        t_lib, f_lib, n_lib = F.cobyla_minimize_1d(f, x0)
+        t_py, f_py, n_py = oracle.cobyla_minimize_1d(f, x0)
+        assert n_lib == n_py and t_lib == t_py and f_lib == f_py
+        ref = so.minimize(lambda x: f(float(x[0])), [x0], method="COBYLA", bounds=[(1e-3, None)],
+                          options=dict(rhobeg=0.75 * (x0 - 1e-3), tol=1e-7, maxiter=2000))
+        # xtol_rel = 1e-4 of the initial step (7.5e-4 here) is the resolution the reference asks of the optimiser
+        assert f_lib <= ref.fun + 1e-3 * max(1.0, abs(ref.fun))
+        assert abs(t_lib - float(ref.x[0])) <= 2e-3 * max(1.0, abs(float(ref.x[0])))
+
+
+def test_laplace_mll_matches_direct_newton(oracle):
+    """marginal_log_likelihood_logit_la_cpp restated: at the converged mode the value equals the textbook Laplace
+    approximation log p(y|f) - f^T C^-1 f / 2 - log|I + W^1/2 C W^1/2| / 2 (GPML eq. 3.32)."""
+    V, values, Y, idx = _toy_logit_problem(5, 40, 15)
+    C = oracle.hk_from_spectrum(V, values, 15, 6.0, idx, idx)
+    C[np.diag_indices(40)] += 1e-3
+    got = oracle.laplace_mll(C, Y, tol=1e-12, max_iter=200)
+    f = np.zeros(40)
+    for _ in range(200):  # plain Newton on the log posterior
+        pi = 1 / (1 + np.exp(-f))
+        W = pi * (1 - pi)
+        f = np.linalg.solve(np.eye(40) + C * W[None, :], C @ (W * f + Y - pi))
+    pi = 1 / (1 + np.exp(-f))
+    W = pi * (1 - pi)
+    B = np.eye(40) + np.sqrt(W)[:, None] * C * np.sqrt(W)[None, :]
+    want = (Y * np.log(pi) + (1 - Y) * np.log(1 - pi)).sum() - 0.5 * f @ np.linalg.solve(C, f) - 0.5 * np.linalg.slogdet(B)[1]
+    assert abs(got - want) <= 1e-6 * abs(want)
