@@ -104,6 +104,10 @@ def _declare(lib):
         "flgp_fit_nystrom_regression": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int,
                                                   C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                                   p_i32, c_u64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64]),
+        "flgp_fit_nystrom_regression_sharded": (C.c_int, [H, p_f64, c_i64, c_i64, c_i64, C.c_int, p_f64, c_i64, C.c_int,
+                                                          C.c_int, C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p,
+                                                          C.c_int, C.c_int, p_i32, c_u64, p_f64, p_f64, p_f64, p_f64,
+                                                          p_f64, p_f64]),
         "flgp_logit_objective": (C.c_int, [H, p_f64, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, C.c_double, p_f64]),
         "flgp_train_logit": (C.c_int, [H, p_f64, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, p_f64, p_f64,
                                        C.POINTER(C.c_int)]),

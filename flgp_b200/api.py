@@ -718,6 +718,33 @@ def fit_nystrom_regression_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: floa
             "a2": a2.value, "obj": obj.value}
 
 
+def fit_nystrom_regression_sharded(X_local, n_total: int, row_offset: int, Y_local, m_total: int, s: int, K: int = -1,
+                                   sigma: float = 1e-5, a2s=None, approach="posterior", subsample="kmeans",
+                                   nstart: int = 1, *, pars: Optional[Sequence[float]] = None, init_idx=None,
+                                   seed: int = 0, iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_nystrom_regression_gp_cpp on one contiguous block of rows per rank (multi-GPU; BASELINE config 5's Nystrom
+    variant): returns the posterior mean / variance of the local rows, pars, a2, obj."""
+    ctx = ctx or default_ctx()
+    if a2s is None:
+        a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    a2s = np.ascontiguousarray(a2s, dtype=np.float64)
+    X_local = _f64(X_local)
+    n_local, d = X_local.shape
+    Y_local = np.ascontiguousarray(Y_local, dtype=np.float64).reshape(-1)
+    mean = np.zeros(max(n_local, 1))
+    cov = np.zeros(max(n_local, 1))
+    xo = np.zeros(2)
+    fixed = np.ascontiguousarray(pars, dtype=np.float64) if pars is not None else None
+    a2 = C.c_double()
+    obj = C.c_double()
+    check(ctx._lib.flgp_fit_nystrom_regression_sharded(ctx._h, _pf(X_local), n_local, n_total, row_offset, d,
+                                                       _pf(Y_local) if Y_local.size else None, m_total, s, K, sigma,
+                                                       _pf(a2s), a2s.size, _b(approach), _b(subsample), nstart, iter_max,
+                                                       _pi(_idx(init_idx)), seed, _pf(fixed), _pf(mean), _pf(cov),
+                                                       _pf(xo), C.byref(a2), C.byref(obj)))
+    return {"mean": mean[:n_local], "cov": cov[:n_local], "pars": list(xo), "a2": a2.value, "obj": obj.value}
+
+
 def posterior_distribution_classification(eigenpair: EigenPair, Y_local, m_total: int, K: int, t: float,
                                           sigma: float = 1e-3, tol: float = 1e-5, max_iter: int = 100):
     """posterior_distribution_classification (src/Utils.cpp:252-299) on a spectrum handle at a fixed diffusion time

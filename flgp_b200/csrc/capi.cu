@@ -1398,6 +1398,104 @@ int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, cons
   });
 }
 
+// fit_nystrom_regression_gp_cpp (src/Fit.cpp:222-357) on one contiguous block of rows of X_all (dX: n_local x d on the
+// device, rows row_offset ..; the first m_total rows of X_all are the training rows, dY their labels on this rank).
+// The anchors and the s x s anchor operator are replicated (k-means sums all-reduced as everywhere); the extension is
+// row-parallel; the K x K training statistics and the tail system are all-reduced.  y / cv: n_local on the host.
+static void nystrom_fit(Ctx* c, const double* dX, int64_t n_local, int64_t n_total, int64_t row_offset, int d,
+                        const double* dY, int64_t m_total, int s, int K, double sigma, const double* a2s, int n_a2,
+                        bool post, const char* subsample, int nstart, int iter_max, const int32_t* init_idx,
+                        uint64_t seed, const double* fixed_pars, double* y, double* cv, double* pars_out,
+                        double* best_a2, double* best_obj) {
+  const int64_t n = n_total, m = m_total;
+  const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(n_local, m_total - row_offset));
+  // anchors (src/Fit.cpp:242): subsample_cpp(...).leftCols(d)
+  flgp_spectrum base;
+  base.c = c;
+  base.n_local = n_local;
+  base.n_total = n;
+  base.row_offset = row_offset;
+  base.d = d;
+  base.s = s;
+  base.r = 1;
+  const Models mo = make_models(subsample, "se", FLGP_GL_RW, 1, nstart, 0.1, iter_max);
+  stage_subsample(c, &base, dX, mo, init_idx, seed, nullptr);
+  base.sorted = KMeansSorted();
+  const double* U = base.U.p;
+  DevBuf<double> un(s), D((size_t)s * s);
+  double dmean = 0.0;
+  nys_anchor_distances_run(c, U, s, s, d, un.p, D.p, &dmean);
+  // row blocks: the n_b x s weight block stays below ~512 MB
+  const int64_t nb_max = std::max<int64_t>(256, std::min<int64_t>(std::max<int64_t>(n_local, 1), ((int64_t)64 << 20) / s));
+  DevBuf<double> Wx((size_t)std::min<int64_t>(nb_max, std::max<int64_t>(n_local, 1)) * s);
+  DevBuf<double> V1((size_t)std::max<int64_t>(m_local, 1) * K);
+  struct Cand {
+    DevBuf<double> rs, Bt;
+    std::vector<double> lam;
+    double denom = 0.0;
+  } best;
+  double max_obj = -std::numeric_limits<double>::infinity();
+  bool have = false;
+  for (int q = 0; q < n_a2; ++q) {  // grid search (src/Fit.cpp:262-312)
+    Cand cd;
+    cd.rs.alloc(s);
+    cd.Bt.alloc((size_t)K * s);
+    cd.denom = a2s[q] * dmean;
+    DevBuf<double> lam(K);
+    nys_anchor_operator_run(c, D.p, s, K, cd.denom, cd.rs.p, lam.p, cd.Bt.p);
+    cd.lam.resize(K);
+    lam.download(cd.lam.data(), K, c->stream);
+    sync(c);
+    for (int64_t r0 = 0; r0 < m_local; r0 += nb_max) {
+      const int64_t nb = std::min<int64_t>(nb_max, m_local - r0);
+      nys_extend_rows_run(c, dX, n_local, r0, nb, d, U, s, s, un.p, cd.rs.p, cd.denom, cd.Bt.p, K, Wx.p,
+                          V1.p + (size_t)r0 * K);
+    }
+    const RegTrain T = reg_train_from_rows(c, V1.p, K, m_local, row_offset, dY, m, K, sigma, cd.lam);
+    double x[2] = {std::nan(""), std::nan("")};
+    double obj;
+    if (fixed_pars) {
+      x[0] = fixed_pars[0];
+      x[1] = fixed_pars[1];
+      obj = -reg_objective(T, x, nullptr, post);
+    } else {
+      obj = train_regression(T, post, x, nullptr);
+    }
+    if (obj > max_obj || !have) {
+      max_obj = obj;
+      pars_out[0] = x[0];
+      pars_out[1] = x[1];
+      if (best_a2) *best_a2 = a2s[q];
+      best = std::move(cd);
+      have = true;
+    }
+  }
+  if (best_obj) *best_obj = max_obj;
+  // predictions with the winning bandwidth (src/Fit.cpp:318-340)
+  for (int64_t r0 = 0; r0 < m_local; r0 += nb_max) {
+    const int64_t nb = std::min<int64_t>(nb_max, m_local - r0);
+    nys_extend_rows_run(c, dX, n_local, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p,
+                        V1.p + (size_t)r0 * K);
+  }
+  DevBuf<double> dcoef, dM;
+  gpr_tail_system(c, V1.p, K, m_local, row_offset, dY, m, K, best.lam, pars_out[0], pars_out[1], sigma, dcoef, dM);
+  const double ns = pars_out[1] + sigma;
+  const int64_t nbv = std::min<int64_t>(nb_max, std::max<int64_t>(n_local, 1));
+  DevBuf<double> Vb((size_t)nbv * K), Tb((size_t)nbv * K), dy(std::max<int64_t>(n_local, 1)), dc(std::max<int64_t>(n_local, 1));
+  for (int64_t r0 = 0; r0 < n_local; r0 += nb_max) {
+    const int64_t nb = std::min<int64_t>(nb_max, n_local - r0);
+    nys_extend_rows_run(c, dX, n_local, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p, Vb.p);
+    gemv_run(c, Vb.p, dcoef.p, nb, K, dy.p + r0);
+    gemm_nn_run(c, Vb.p, dM.p, nb, K, K, Tb.p);  // M symmetric: row-major image = column-major image
+    nys_rowdot_run(c, Tb.p, Vb.p, nb, K, ns, dc.p + r0);
+  }
+  if (n_local > 0) {
+    dy.download(y, n_local, c->stream);
+    dc.download(cv, n_local, c->stream);
+  }
+  sync(c);
+}
+
 int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
                                 int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
                                 const char* approach, const char* subsample, int nstart, int iter_max,
@@ -1409,7 +1507,7 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
     Ctx* c = &ctx->c;
-    need(c->nranks == 1, "flgp_fit_nystrom_regression is the single-process entry point");
+    need(c->nranks == 1, "flgp_fit_nystrom_regression is the single-process entry point (see ..._sharded)");
     const int64_t n = m + m_new;
     need(s >= 1 && s <= n && n < ((int64_t)1 << 31), "need 1 <= s <= n");
     if (K < 0) K = s;  // R/Fit.R:183-185
@@ -1417,91 +1515,39 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
     DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
     DevBuf<double> dY(m);
     dY.upload(Y, m, c->stream);
-    // anchors (src/Fit.cpp:242): subsample_cpp(...).leftCols(d)
-    flgp_spectrum base;
-    base.c = c;
-    base.n_local = base.n_total = n;
-    base.d = d;
-    base.s = s;
-    base.r = 1;
-    const Models mo = make_models(subsample, "se", FLGP_GL_RW, 1, nstart, 0.1, iter_max);
-    stage_subsample(c, &base, dX.p, mo, init_idx, seed, nullptr);
-    base.sorted = KMeansSorted();
-    const double* U = base.U.p;
-    DevBuf<double> un(s), D((size_t)s * s);
-    double dmean = 0.0;
-    nys_anchor_distances_run(c, U, s, s, d, un.p, D.p, &dmean);
-    // row blocks: the n_b x s weight block stays below ~512 MB
-    const int64_t nb_max = std::max<int64_t>(256, std::min<int64_t>(n, ((int64_t)64 << 20) / s));
-    DevBuf<double> Wx((size_t)std::min<int64_t>(nb_max, n) * s);
-    DevBuf<double> V1((size_t)m * K);
-    struct Cand {
-      DevBuf<double> rs, Bt;
-      std::vector<double> lam;
-      double denom = 0.0;
-    } best;
-    double max_obj = -std::numeric_limits<double>::infinity();
-    bool have = false;
-    for (int q = 0; q < n_a2; ++q) {  // grid search (src/Fit.cpp:262-312)
-      Cand cd;
-      cd.rs.alloc(s);
-      cd.Bt.alloc((size_t)K * s);
-      cd.denom = a2s[q] * dmean;
-      DevBuf<double> lam(K);
-      nys_anchor_operator_run(c, D.p, s, K, cd.denom, cd.rs.p, lam.p, cd.Bt.p);
-      cd.lam.resize(K);
-      lam.download(cd.lam.data(), K, c->stream);
-      sync(c);
-      for (int64_t r0 = 0; r0 < m; r0 += nb_max) {
-        const int64_t nb = std::min<int64_t>(nb_max, m - r0);
-        nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, cd.rs.p, cd.denom, cd.Bt.p, K, Wx.p,
-                            V1.p + (size_t)r0 * K);
-      }
-      const RegTrain T = reg_train_from_rows(c, V1.p, K, m, 0, dY.p, m, K, sigma, cd.lam);
-      double x[2] = {std::nan(""), std::nan("")};
-      double obj;
-      if (fixed_pars) {
-        x[0] = fixed_pars[0];
-        x[1] = fixed_pars[1];
-        obj = -reg_objective(T, x, nullptr, post);
-      } else {
-        obj = train_regression(T, post, x, nullptr);
-      }
-      if (obj > max_obj || !have) {
-        max_obj = obj;
-        pars_out[0] = x[0];
-        pars_out[1] = x[1];
-        if (best_a2) *best_a2 = a2s[q];
-        best = std::move(cd);
-        have = true;
-      }
-    }
-    if (best_obj) *best_obj = max_obj;
-    // predictions with the winning bandwidth (src/Fit.cpp:318-340)
-    for (int64_t r0 = 0; r0 < m; r0 += nb_max) {
-      const int64_t nb = std::min<int64_t>(nb_max, m - r0);
-      nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p,
-                          V1.p + (size_t)r0 * K);
-    }
-    DevBuf<double> dcoef, dM;
-    gpr_tail_system(c, V1.p, K, m, 0, dY.p, m, K, best.lam, pars_out[0], pars_out[1], sigma, dcoef, dM);
-    const double ns = pars_out[1] + sigma;
-    const int64_t nbv = std::min<int64_t>(nb_max, n);
-    DevBuf<double> Vb((size_t)nbv * K), Tb((size_t)nbv * K), dy(n), dc(n);
-    for (int64_t r0 = 0; r0 < n; r0 += nb_max) {
-      const int64_t nb = std::min<int64_t>(nb_max, n - r0);
-      nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p, Vb.p);
-      gemv_run(c, Vb.p, dcoef.p, nb, K, dy.p + r0);
-      gemm_nn_run(c, Vb.p, dM.p, nb, K, K, Tb.p);  // M symmetric: row-major image = column-major image
-      nys_rowdot_run(c, Tb.p, Vb.p, nb, K, ns, dc.p + r0);
-    }
     std::vector<double> y(n), cv(n);
-    dy.download(y.data(), n, c->stream);
-    dc.download(cv.data(), n, c->stream);
-    sync(c);
+    nystrom_fit(c, dX.p, n, n, 0, d, dY.p, m, s, K, sigma, a2s, n_a2, post, subsample, nstart, iter_max, init_idx, seed,
+                fixed_pars, y.data(), cv.data(), pars_out, best_a2, best_obj);
     std::memcpy(train, y.data(), sizeof(double) * m);
     if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
     if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
+int flgp_fit_nystrom_regression_sharded(flgp_ctx* ctx, const double* X_local, int64_t n_local, int64_t n_total,
+                                        int64_t row_offset, int d, const double* Y_local, int64_t m_total, int s, int K,
+                                        double sigma, const double* a2s, int n_a2, const char* approach,
+                                        const char* subsample, int nstart, int iter_max, const int32_t* init_idx,
+                                        uint64_t seed, const double* fixed_pars, double* mean_local, double* cov_local,
+                                        double* pars_out, double* best_a2, double* best_obj) {
+  return guard([&] {
+    need(ctx && mean_local && cov_local && pars_out && a2s, "null argument");
+    need(n_local >= 0 && n_total >= 1 && d >= 1 && n_a2 >= 1 && m_total >= 1 && m_total <= n_total, "bad matrix shape");
+    need(row_offset >= 0 && row_offset + n_local <= n_total, "shard outside the matrix");
+    need(n_local == 0 || X_local, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = &ctx->c;
+    need(s >= 1 && s <= n_total && n_total < ((int64_t)1 << 31), "need 1 <= s <= n");
+    if (K < 0) K = s;
+    need(K >= 1 && K <= s, "need 1 <= K <= s");
+    const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(n_local, m_total - row_offset));
+    need(m_local == 0 || Y_local, "null argument");
+    DevBuf<double> dX((size_t)std::max<int64_t>(n_local * d, 1)), dY(std::max<int64_t>(m_local, 1));
+    if (n_local > 0) dX.upload(X_local, (size_t)n_local * d, c->stream);
+    if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
+    nystrom_fit(c, dX.p, n_local, n_total, row_offset, d, dY.p, m_total, s, K, sigma, a2s, n_a2, post, subsample, nstart,
+                iter_max, init_idx, seed, fixed_pars, mean_local, cov_local, pars_out, best_a2, best_obj);
   });
 }
 

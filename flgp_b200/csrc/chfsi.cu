@@ -1064,7 +1064,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
     for (int j = 0; j < nb; ++j) rate[j] = std::acosh(std::max(1.0, (th[j] - cen) / e));
     double mw = 0.0, cap = 1e9;
     for (int j = 0; j < K; ++j) {
-      if (rs[j] > tol) need[j] = std::log(rs[j] / tol) / std::max(rate[j], 1e-2) * 1.15 + 2.0;
+      if (rs[j] > tol) need[j] = std::log(rs[j] / tol) / std::max(rate[j], 1e-2) * 1.06 + 1.0;
       mw = std::max(mw, need[j]);
     }
     for (int j = 0; j < nb; ++j) {

@@ -208,12 +208,22 @@ int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, cons
 /* fit_nystrom_regression_gp_cpp (src/Fit.cpp:222-357; R wrapper R/Fit.R:177-195), SURVEY.md §8f row 4: anchors by
  * subsample_cpp, dense SE kernel on the anchors (bandwidth a2 * mean anchor distance), doubly normalised; its top-K
  * eigenpairs (the RSpectra::eigs_sym callback) are extended to every row by the Nystrom formula; training and GPR
- * tail as in the other drivers.  Single process.  fixed_pars (may be NULL): skip the training. */
+ * tail as in the other drivers.  Single process (the sharded form follows).  fixed_pars (may be NULL): skip the training. */
 int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
                                 int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
                                 const char* approach, const char* subsample, int nstart, int iter_max,
                                 const int32_t* init_idx, uint64_t seed, const double* fixed_pars, double* train,
                                 double* test, double* cov, double* pars_out, double* best_a2, double* best_obj);
+/* The same on one contiguous block of rows of X_all per rank (rows row_offset .. row_offset + n_local - 1; the first
+ * m_total rows of X_all are the training rows; Y_local = labels of the training rows this rank owns): anchors and the
+ * s x s anchor operator replicated, the extension row-parallel, the K x K statistics all-reduced.  mean_local /
+ * cov_local: posterior mean and variance of the local rows (BASELINE config 5's "Nystrom variant" over 8 GPUs). */
+int flgp_fit_nystrom_regression_sharded(flgp_ctx* ctx, const double* X_local, int64_t n_local, int64_t n_total,
+                                        int64_t row_offset, int d, const double* Y_local, int64_t m_total, int s, int K,
+                                        double sigma, const double* a2s, int n_a2, const char* approach,
+                                        const char* subsample, int nstart, int iter_max, const int32_t* init_idx,
+                                        uint64_t seed, const double* fixed_pars, double* mean_local, double* cov_local,
+                                        double* pars_out, double* best_a2, double* best_obj);
 /* posterior_distribution_classification (src/Utils.cpp:252-299; exported, src/Utils.h:77-80) as the binary logit
  * drivers call it (fit_lae_logit_gp_cpp, src/Fit.cpp:563-582) at a FIXED diffusion time t: Laplace approximation of
  * the GP classifier — Newton iterations on the m labelled rows (labels 0/1, f = 0 start, |df|_1 < tol), then the

@@ -62,6 +62,7 @@ def main():
               (world, ep1.kmeans_iters, np.array_equal(Zx, Z1.data), e_y, e_c, "OK" if ok else "FAIL"))
     ok &= large_d_case(rank, local, world, ctx)
     ok &= large_s_case(rank, local, world, ctx)
+    ok &= nystrom_case(rank, local, world, ctx)
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
@@ -123,6 +124,35 @@ def large_s_case(rank, local, world, ctx):
         ok = bit_vals and bit_rows and e_y < 1e-9
         print("multi_gpu_check world=%d large-s (s=%d, iterative eigensolver, sharded filter): eigenvalues bit-exact=%s, "
               "eigenvector rows bit-exact=%s, dy=%.2e -> %s" % (world, s, bit_vals, bit_rows, e_y, "OK" if ok else "FAIL"))
+    return ok
+
+
+def nystrom_case(rank, local, world, ctx):
+    """fit_nystrom_regression sharded over the ranks against the single-process entry on the whole matrix (fixed pars:
+    the comparison is of the extension and the tail, not of the optimiser path)."""
+    n, m, s, K = 40_001, 400, 200, 30
+    X, Y, _ = make("C4", 55, n=n)
+    lo, hi = shard_bounds(n, world, rank)
+    init = F.default_init(n, s, 2)
+    a2s = np.array([0.5, 2.0])
+    m_local = max(0, min(hi - lo, m - lo))
+    res = F.fit_nystrom_regression_sharded(np.asfortranarray(X[lo:hi]), n, lo, Y[lo:lo + m_local], m, s, K, a2s=a2s,
+                                           pars=(10.0, 0.05), init_idx=init, iter_max=20, ctx=ctx)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, dict(mean=res["mean"], cov=res["cov"], a2=res["a2"], obj=res["obj"]))
+    ok = True
+    if rank == 0:
+        ctx1 = F.Context(local)
+        one = F.fit_nystrom_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, K, a2s=a2s, pars=(10.0, 0.05), init_idx=init,
+                                               iter_max=20, ctx=ctx1)
+        mean = np.concatenate([g["mean"] for g in gathered])
+        cov = np.concatenate([g["cov"] for g in gathered])
+        ref_mean = np.r_[one["Y_pred"]["train"], one["Y_pred"]["test"]]
+        e_m = np.abs(mean - ref_mean).max() / np.abs(ref_mean).max()
+        e_c = np.abs(cov[m:] - one["posterior"]["cov"]).max() / max(1.0, np.abs(one["posterior"]["cov"]).max())
+        ok = all(g["a2"] == one["a2"] for g in gathered) and e_m < 1e-9 and e_c < 1e-9
+        print("multi_gpu_check world=%d Nystrom sharded: same a2=%s, dmean=%.2e dcov=%.2e -> %s" %
+              (world, all(g["a2"] == one["a2"] for g in gathered), e_m, e_c, "OK" if ok else "FAIL"))
     return ok
 
 
