@@ -335,50 +335,56 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
     }
     __syncthreads();
     CH_TICK(1);
-    // Cholesky of the block with all threads, one barrier per column: thread (i, j..j+1) owns its entries of the
-    // Schur complement, which stays UNSCALED in D (column k of the factor = D(:, k) * invd[k], applied at the end)
-    {
-      const int pi = tid >> 4, pj2 = (tid & 15) * 2;  // 32 x 16 threads, two columns each
-      for (int k = 0; k < jb; ++k) {
-        double dkk = D[k * 33 + k];
-        if (!(dkk > 0.0)) {
-          if (tid == 0) bad = 1;
-          dkk = DBL_MIN;
-        }
-        const double inv = rsqrt(dkk);
-        const double cik = D[pi * 33 + k] * inv;
+    // Cholesky and inverse of the 32 x 32 block by ONE warp, lane = row, the row in registers, loops fully unrolled:
+    // a step is a shuffle (pivot), an rsqrt, and independent shared-memory broadcasts + FMAs - no block barrier inside
+    // the 2 x 32 dependent steps (the all-thread version spent ~520 cycles per step on its barrier and its rsqrt).
+    if (tid < 32) {
+      const int lane = tid;
+      double row[CH_NB];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = pj2 + u;
-          if (pi < jb && j > k && j <= pi) D[pi * 33 + j] = fma(-cik, D[j * 33 + k] * inv, D[pi * 33 + j]);
+      for (int j = 0; j < CH_NB; ++j) row[j] = D[lane * 33 + j];
+      double lmin = DBL_MAX, lmax = 0.0;
+      bool isbad = false;
+#pragma unroll
+      for (int k = 0; k < CH_NB; ++k) {
+        if (k < jb) {  // warp-uniform
+          double dkk = __shfl_sync(0xffffffffu, row[k], k);
+          if (!(dkk > 0.0)) {
+            isbad = true;
+            dkk = DBL_MIN;
+          }
+          const double inv = rsqrt(dkk);
+          const double lik = (lane >= k) ? row[k] * inv : 0.0;  // column k of the factor
+          row[k] = lik;
+          D[lane * 33 + k] = lik;
+          if (lane == 0) invd[k] = inv;
+          lmin = fmin(lmin, dkk * inv);
+          lmax = fmax(lmax, dkk * inv);
+          __syncwarp();
+#pragma unroll
+          for (int j = k + 1; j < CH_NB; ++j)
+            if (lane >= j) row[j] = fma(-lik, D[j * 33 + k], row[j]);
         }
-        if (tid == 0) {
-          invd[k] = inv;
-          const double l = dkk * inv;
-          dmin_s = fmin(dmin_s, l);
-          dmax_s = fmax(dmax_s, l);
-        }
-        __syncthreads();
       }
-      for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-        const int i = e / CH_NB, k = e % CH_NB;
-        if (i < jb && k <= i) D[i * 33 + k] *= invd[k];
+      __syncwarp();
+      // Di(r, c) = (delta_rc - sum_{q < r} L(r, q) Di(q, c)) / L(r, r): lane = column c, the column in registers
+      double colv[CH_NB];
+#pragma unroll
+      for (int r = 0; r < CH_NB; ++r) {
+        double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < r; ++q) v = fma(-D[r * 33 + q], colv[q], v);
+        colv[r] = (r < jb && lane <= r) ? v * invd[r] : 0.0;
+        Di[r * 33 + lane] = colv[r];
       }
-      __syncthreads();
+      if (lane == 0) {
+        if (isbad) bad = 1;
+        dmin_s = fmin(dmin_s, lmin);
+        dmax_s = fmax(dmax_s, lmax);
+      }
     }
     CH_TICK(2);
-    // inverse of the lower-triangular factor, row by row, 16 threads per entry of the row:
-    //   Di(r, c) = (delta_rc - sum_{c <= q < r} L(r, q) Di(q, c)) / L(r, r)
-    {
-      const int cc = tid >> 4, t16 = tid & 15;
-      for (int r = 0; r < jb; ++r) {
-        double v = 0.0;
-        for (int q = cc + t16; q < r; q += 16) v = fma(D[r * 33 + q], Di[q * 33 + cc], v);
-        for (int o = 8; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (t16 == 0 && cc <= r) Di[r * 33 + cc] = (((r == cc) ? 1.0 : 0.0) - v) * invd[r];
-        __syncthreads();
-      }
-    }
+    __syncthreads();
     CH_TICK(3);
     // (b) Y[p, col] = sum_q Di(k, q) R(j0 + q, col) for col < j0: every CTA takes a column range, staged through
     //     smem (Zs is free until the barrier) so that no dependent L2 round trip sits in the inner loop; Y[p, p] = Di
@@ -535,7 +541,11 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
     offA[q] = (uint32_t)(wid * 8 + fr) * 128u + inrow;
     offB[q] = (uint32_t)LZ_BM * 128u + (uint32_t)fr * 128u + inrow;
   }
-  double acc0 = 0.0, acc1 = 0.0;
+  // one accumulator pair per k-slab position: a single pair would chain all 4 ceil(s/16) DMMAs of the row block
+  // through the tensor pipe's latency (the kernel was 2x slower for it); the partial sums are added in a fixed order
+  double acc[LZ_SUB][2];
+#pragma unroll
+  for (int u = 0; u < LZ_SUB; ++u) acc[u][0] = acc[u][1] = 0.0;
   for (int t = 0; t < nst; ++t) {
     const int st = t % LZ_STAGES;
     mbar_wait(&full[st], (t / LZ_STAGES) & 1);
@@ -553,10 +563,13 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[st]);
 #pragma unroll
-    for (int u = 0; u < LZ_SUB; ++u)
+    for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) dmma_m8n8k4(acc0, acc1, af[u][q], bf[u][q]);
+      for (int u = 0; u < LZ_SUB; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[u][q], bf[u][q]);
   }
+  const double acc0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+  const double acc1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+  static_assert(LZ_SUB == 4, "the final sum is written out for four partial accumulators");
   // epilogue: u(i, run) for run = 2 fk, 2 fk + 1; inner products over this warp's 8 rows, then over the two warps
   const int i = i0 + wid * 8 + fr;
   double p[3][2];
@@ -589,61 +602,46 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
     partial[((size_t)blockIdx.x * 3 + w) * LZ_NV + run] = wsum[0][w][run] + wsum[1][w][run];
   }
 }
-// finish one Lanczos step of all runs from U = G V and the per-CTA inner products u.v:
+// finish one Lanczos step from U = G V and the per-CTA inner products u.v, one CTA per run:
 //   alpha = u.v;  w = u - alpha v - beta_prev vp;  beta = |w|;  v_new = w / beta  (the caller rotates vp <- v <- v_new).
-// Every CTA sums the partials and forms |w|^2 over ALL rows itself (same fixed order everywhere: identical results,
-// no second grid-wide reduction), then writes its own rows.
+// Fixed reduction orders: the result does not depend on the schedule.
 __global__ void __launch_bounds__(1024)
 lanczos_update_kernel(int s, int step, int nparts, const double* __restrict__ partial, const double* __restrict__ V,
                       const double* __restrict__ Vp, const double* __restrict__ U, double* __restrict__ Vnew,
                       double* __restrict__ alpha, double* __restrict__ beta) {
-  __shared__ double al[LZ_NV], bp[LZ_NV], red[32][LZ_NV], be[LZ_NV];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  if (wid < LZ_NV) {  // warp = run: lanes stride over the CTAs' partial sums, then a fixed shuffle tree
+  __shared__ double red[32];
+  __shared__ double al_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, run = blockIdx.x;
+  if (wid == 0) {  // lanes stride over the CTAs' partial sums, then a fixed shuffle tree
     double a = 0.0;
-    for (int cta = lane; cta < nparts; cta += 32) a += partial[((size_t)cta * 3) * LZ_NV + wid];
+    for (int cta = lane; cta < nparts; cta += 32) a += partial[((size_t)cta * 3) * LZ_NV + run];
     for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0) {
-      al[wid] = a;
-      bp[wid] = step > 0 ? beta[(step - 1) * LZ_NV + wid] : 0.0;
-    }
+    if (lane == 0) al_s = a;
   }
   __syncthreads();
-  double n2[LZ_NV];
+  const double al = al_s, bp = step > 0 ? beta[(step - 1) * LZ_NV + run] : 0.0;
+  const double* v = V + (size_t)s * run;
+  const double* vp = Vp + (size_t)s * run;
+  const double* u = U + (size_t)s * run;
+  constexpr int PER = 4;  // s <= 4096: a thread keeps its elements of w in registers
+  double w[PER];
+  double n2 = 0.0;
 #pragma unroll
-  for (int run = 0; run < LZ_NV; ++run) n2[run] = 0.0;
-  for (int i = tid; i < s; i += 1024) {
-#pragma unroll
-    for (int run = 0; run < LZ_NV; ++run) {
-      const int64_t at = i + (int64_t)s * run;
-      const double w = fma(-bp[run], Vp[at], fma(-al[run], V[at], U[at]));
-      n2[run] = fma(w, w, n2[run]);
-    }
+  for (int q = 0; q < PER; ++q) {
+    const int i = tid + q * 1024;
+    w[q] = (i < s) ? fma(-bp, vp[i], fma(-al, v[i], u[i])) : 0.0;
+    n2 = fma(w[q], w[q], n2);
   }
+  const double be = sqrt(cf_block_sum(n2, red));
+  const double inv = be > 0.0 ? 1.0 / be : 0.0;
 #pragma unroll
-  for (int run = 0; run < LZ_NV; ++run) {
-    for (int o = 16; o; o >>= 1) n2[run] += __shfl_xor_sync(0xffffffffu, n2[run], o);
-    if (lane == 0) red[wid][run] = n2[run];
+  for (int q = 0; q < PER; ++q) {
+    const int i = tid + q * 1024;
+    if (i < s) Vnew[(size_t)s * run + i] = w[q] * inv;
   }
-  __syncthreads();
-  if (tid < LZ_NV) {
-    double t = 0.0;
-    for (int w = 0; w < 32; ++w) t += red[w][tid];
-    be[tid] = sqrt(t);
-    if (blockIdx.x == 0) {
-      alpha[step * LZ_NV + tid] = al[tid];
-      beta[step * LZ_NV + tid] = sqrt(t);
-    }
-  }
-  __syncthreads();
-  const int i = blockIdx.x * 1024 + tid;
-  if (i >= s) return;
-  // the new vectors go to a third buffer: V and Vp of all rows are still being read by the other CTAs
-#pragma unroll
-  for (int run = 0; run < LZ_NV; ++run) {
-    const int64_t at = i + (int64_t)s * run;
-    const double w = fma(-bp[run], Vp[at], fma(-al[run], V[at], U[at]));
-    Vnew[at] = be[run] > 0.0 ? w / be[run] : 0.0;
+  if (tid == 0) {
+    alpha[step * LZ_NV + run] = al;
+    beta[step * LZ_NV + run] = be;
   }
 }
 
@@ -715,7 +713,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   static const int env_guard = std::getenv("FLGP_CHFSI_NB") ? std::atoi(std::getenv("FLGP_CHFSI_NB")) : 0;
   int nb = ((K + std::max(32, K / 4) + CF_BN - 1) / CF_BN) * CF_BN;
   if (env_guard > 0) nb = ((std::max(env_guard, K + 8) + CF_BN - 1) / CF_BN) * CF_BN;
-  if (nb > 512 || nb * 3 > s) return false;
+  if (nb > 512 || nb * 3 > s || s > 4096) return false;  // s <= 4096: lanczos_update_kernel keeps a run in registers
   const int ng = nb / CF_BN;
   const int64_t ld = s;
   const size_t blk = (size_t)s * nb;
@@ -810,7 +808,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
     for (int j = 0; j < kl; ++j) {
       const int ip = j % 3, iv = (j + 1) % 3, in = (j + 2) % 3;
       FLGP_LAUNCH(c, lanczos_symv_kernel, nparts, 96, lz_smem, mapG[2], mapV[iv], s, Vb[iv].p, Vb[ip].p, W.p, part.p);
-      FLGP_LAUNCH(c, lanczos_update_kernel, ceil_div(s, 1024), 1024, 0, s, j, nparts, part.p, Vb[iv].p, Vb[ip].p, W.p,
+      FLGP_LAUNCH(c, lanczos_update_kernel, LZ_NV, 1024, 0, s, j, nparts, part.p, Vb[iv].p, Vb[ip].p, W.p,
                   Vb[in].p, al.p, be.p);
     }
     std::vector<double> alh((size_t)kl * LZ_NV), beh((size_t)kl * LZ_NV);
@@ -958,6 +956,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
     gemm_nt_ld_run(c, Xr.p, nb, Brm, nb, nullptr, s, nb, nb, Out, ld);
   };
   // Cholesky-QR of Xb[cur]; returns false when the Gram is numerically singular
+  double last_ratio = 1.0;
   auto cholqr = [&]() -> bool {
     FLGP_LAUNCH(c, cf_normalize_kernel, nb, 256, 0, Xb[cur].p, s, ld);
     for (int pass = 0; pass < 3; ++pass) {
@@ -986,7 +985,10 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       rotate(Xb[cur].p, Linv.p, Xb[cur].p);
       const double ratio = ih[1] / ih[2];
       if (g_cf_debug) fprintf(stderr, "[chfsi]   cholqr pass %d: min/max diag(L) = %.2e\n", pass, ratio);
-      if (ratio > 0.3) break;
+      last_ratio = ratio;
+      // one pass leaves |X^T X - I| ~ eps / ratio^2: enough for the next filter segment or a rough Rayleigh-Ritz
+      // step as long as that stays below ~1e-8; the pass before an accepted result must have ratio >= 0.05
+      if (ratio > 2e-4) break;
     }
     return true;
   };
@@ -1051,7 +1053,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       fprintf(stderr, "[chfsi] it %d: cut %.5f theta[0] %.6f theta[K-1] %.6f theta[nb-1] %.6f max res(K) %.2e cost %.1f\n",
               it, f.c, th[0], th[K - 1], th[nb - 1], rmaxK, cost);
     if (!std::isfinite(rmaxK)) return false;
-    if (rmaxK <= tol) {
+    if (rmaxK <= tol && last_ratio >= 0.05) {  // accepted only on a basis that one Cholesky-QR pass made orthonormal
       converged = true;
       break;
     }
@@ -1091,7 +1093,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       }
       segs.push_back(sg);
     }
-    if (segs.empty()) return false;
+    if (segs.empty()) segs.push_back(std::vector<int>(ng, 0));  // residuals are there: only re-orthonormalise + RR
     deg = segs[0];
     for (size_t q = segs.size(); q-- > 1;) pending.push_back(segs[q]);
     if (g_cf_debug) {

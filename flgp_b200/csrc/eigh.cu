@@ -354,14 +354,17 @@ tridiag_kernel(double* __restrict__ A, int s, int k_begin, int k_end, double* __
 // ---- 1b. tridiagonalisation of a SMALL matrix inside one thread-block cluster ----------------------------------------
 // The Rayleigh-Ritz problems of chfsi.cu (order 256 .. 384) and the small Grams of configs 1 / 2 are too small for the
 // grid-wide kernel above: its per-column cost is the ~2 us flag barrier across 148 CTAs.  Here the whole matrix lives
-// in the shared memory of TDC_NC CTAs (rows dealt round-robin), the products and the next column's row travel through
+// in the shared memory of 8 or 16 CTAs (rows dealt round-robin), the products and the next column's row travel through
 // distributed shared memory, and the one barrier per column is the hardware cluster barrier (~0.2 us).  Same
 // algorithm and the same outputs (Vh, d, e, tau) as tridiag_kernel: pending rank-2 update applied inside the pass.
-constexpr int TDC_NC = 8, TDC_THREADS = 512, TDC_SMAX = 416;
+constexpr int TDC_THREADS = 512;
+constexpr int TDC_SMAX8 = 416;   // 8 CTAs (portable cluster size): 52 rows x 416 doubles + vectors per CTA
+constexpr int TDC_SMAX16 = 832;  // 16 CTAs (non-portable size, B200 allows it): 52 rows x 832 doubles per CTA
 __device__ __forceinline__ void cluster_barrier() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__global__ void __cluster_dims__(TDC_NC, 1, 1) __launch_bounds__(TDC_THREADS)
+template <int TDC_NC>
+__global__ void __launch_bounds__(TDC_THREADS)
 tridiag_cluster_kernel(const double* __restrict__ A, int s, double* __restrict__ Vh, double* __restrict__ dd,
                        double* __restrict__ ee, double* __restrict__ tau_out) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -971,18 +974,35 @@ void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
   // 1. tridiagonalisation (cooperative, persistent): streaming launch while the trailing matrix is larger than the
   //    grid's shared memory, resident launch for the rest
   static const bool no_cluster = std::getenv("FLGP_EIGH_NO_CLUSTER") != nullptr;
-  if (s <= TDC_SMAX && !no_cluster) {
-    const int LD = (s + 1) & ~1, RP = (s + TDC_NC - 1) / TDC_NC;
+  if (s <= TDC_SMAX16 && !no_cluster) {
+    const int nc = s <= TDC_SMAX8 ? 8 : 16;
+    const int LD = (s + 1) & ~1, RP = (s + nc - 1) / nc;
     const size_t smem = ((size_t)7 * LD + 32 + (size_t)RP * LD) * sizeof(double);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
-      FLGP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      smem_set = smem;
-    }
     double f = 0.0;
     for (int k = 0; k < s - 1; ++k) f += 4.0 * (double)(s - k - 1) * (double)(s - k - 1);
     StageScope st(c, "eigh_tridiag_cluster", f, 0.0);
-    FLGP_LAUNCH(c, tridiag_cluster_kernel, TDC_NC, TDC_THREADS, smem, G, s, Vh.p, dd.p, ee.p, tau.p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(nc);
+    cfg.blockDim = dim3(TDC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = nc;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    const double* Gc = G;
+    if (nc == 8) {
+      FLGP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FLGP_CUDA(cudaLaunchKernelEx(&cfg, tridiag_cluster_kernel<8>, Gc, s, Vh.p, dd.p, ee.p, tau.p));
+    } else {
+      FLGP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      FLGP_CUDA(cudaFuncSetAttribute(tridiag_cluster_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      FLGP_CUDA(cudaLaunchKernelEx(&cfg, tridiag_cluster_kernel<16>, Gc, s, Vh.p, dd.p, ee.p, tau.p));
+    }
+    c->launches++;
   } else {
     const int grid = std::min(c->sm_count, 32 * FLAG_PER);  // one CTA per SM
     int smem_max = 0;

@@ -11,6 +11,7 @@
 // divergence bound (data-dependent 1..100 outer iterations) and is reported with its iteration
 // count, as SURVEY.md §8d asks.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.cuh"
