@@ -8,6 +8,8 @@
 #include <cstring>
 #include <limits>
 #include <memory>
+#include <string>
+#include <thread>
 #include <unordered_set>
 
 #include "../../include/flgp.h"
@@ -556,8 +558,12 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
   FLGP_CUDA(cudaMemcpyAsync(&dsum, part.p + np, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   sync(c);
   const double dmean = dsum / ((double)n_total * r);
-  std::unique_ptr<flgp_spectrum> best;
-  double max_obj = -std::numeric_limits<double>::infinity();
+  // The grid points are independent.  Their device work (weights, graph Laplacian, Gram, eigensolve, training
+  // statistics) runs back to back on the stream; the empirical-Bayes trainings are pure host work on K x K statistics
+  // (hundreds of objective evaluations each: 70 ms at config 2, against 3 ms of device work per grid point) and run
+  // concurrently, one thread per grid point, so the grid costs about one training instead of n_a2 of them.
+  std::vector<std::unique_ptr<flgp_spectrum>> sps(n_a2);
+  std::vector<RegTrain> Ts(n_a2);
   for (int q = 0; q < n_a2; ++q) {
     std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
     sp->c = c;
@@ -576,22 +582,50 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
     const double* nc = (mo.gl == FLGP_GL_CLUSTER_NORMALIZED) ? sp->U.p + (size_t)s * d : nullptr;
     stage_graph_laplacian(c, n_local, s, r, sp->Zj.p, sp->Zx.p, mo.gl, nc, n_total);
     stage_spectrum(c, sp.get(), K, mo.root);
-    const RegTrain T = reg_train_prepare(sp.get(), Ydev, m_total, K, sigma);
-    double x[2] = {std::nan(""), std::nan("")};
-    double obj;
-    if (fixed_pars) {
-      x[0] = fixed_pars[0];
-      x[1] = fixed_pars[1];
-      obj = -reg_objective(T, x, nullptr, posterior);
-    } else {
-      obj = train_regression(T, posterior, x, nullptr);
+    Ts[q] = reg_train_prepare(sp.get(), Ydev, m_total, K, sigma);
+    sps[q] = std::move(sp);
+  }
+  std::vector<double> objs(n_a2), xs((size_t)2 * n_a2);
+  std::vector<std::string> errs(n_a2);
+  std::vector<int> codes(n_a2, 0);
+  auto train_one = [&](int q) {
+    try {
+      double x[2] = {std::nan(""), std::nan("")};
+      if (fixed_pars) {
+        x[0] = fixed_pars[0];
+        x[1] = fixed_pars[1];
+        objs[q] = -reg_objective(Ts[q], x, nullptr, posterior);
+      } else {
+        objs[q] = train_regression(Ts[q], posterior, x, nullptr);
+      }
+      xs[2 * q] = x[0];
+      xs[2 * q + 1] = x[1];
+    } catch (const Error& e) {
+      codes[q] = e.code;
+      errs[q] = e.what();
+    } catch (const std::exception& e) {
+      codes[q] = 3;
+      errs[q] = e.what();
     }
-    if (obj > max_obj || !best) {  // src/Fit.cpp:169-174 (first candidate kept even when every objective is -inf)
-      max_obj = obj;
-      pars_out[0] = x[0];
-      pars_out[1] = x[1];
+  };
+  if (n_a2 > 1 && !fixed_pars) {
+    std::vector<std::thread> th;
+    for (int q = 0; q < n_a2; ++q) th.emplace_back(train_one, q);
+    for (auto& t : th) t.join();
+  } else {
+    for (int q = 0; q < n_a2; ++q) train_one(q);
+  }
+  for (int q = 0; q < n_a2; ++q)
+    if (codes[q]) fail(codes[q], "%s", errs[q].c_str());
+  std::unique_ptr<flgp_spectrum> best;
+  double max_obj = -std::numeric_limits<double>::infinity();
+  for (int q = 0; q < n_a2; ++q) {
+    if (objs[q] > max_obj || !best) {  // src/Fit.cpp:169-174 (first candidate kept even when every objective is -inf)
+      max_obj = objs[q];
+      pars_out[0] = xs[2 * q];
+      pars_out[1] = xs[2 * q + 1];
       if (best_a2) *best_a2 = a2s[q];
-      best = std::move(sp);
+      best = std::move(sps[q]);
     }
   }
   if (best_obj) *best_obj = max_obj;

@@ -35,7 +35,9 @@ namespace {
 
 constexpr int CF_BN = 64;      // vector columns per CTA tile = column group of the degree schedule
 constexpr int CF_K = DG_K;     // 16: one 128-byte TMA row per k step
-constexpr int CF_STAGES = 6;
+// ring depth by tile height (stage = (8 H + 64) x 128 bytes): as deep as ~190 KB of shared memory allow; the short tiles
+// of a sharded / mostly converged block move little data per stage and need the depth to cover the L2 latency
+__host__ __device__ constexpr int cf_stages(int H) { return H <= 4 ? 16 : 12; }
 constexpr int CF_CONSUMERS = 16;                  // consumer warps; one more warp feeds the TMA ring
 constexpr int CF_THREADS = 32 * (CF_CONSUMERS + 1);
 
@@ -73,6 +75,7 @@ cheb_gemm_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant
                  int64_t ld, double c1, double c2, double c3) {
   constexpr int BM = 8 * H;
   constexpr int MTX = (H + 3) / 4;  // most 8-row blocks any warp row owns
+  constexpr int CF_STAGES = cf_stages(H);
   constexpr uint32_t STAGE_BYTES = (uint32_t)(BM + CF_BN) * CF_K * sizeof(double);
   extern __shared__ __align__(1024) unsigned char dsm_raw[];
   const uint32_t boxes = (smem_u32(dsm_raw) + 1023u) & ~1023u;  // SWIZZLE_128B: boxes on 1024-byte boundaries
@@ -759,7 +762,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
     const int ct = ceil_div(ncols, CF_BN);
     int h = 8;
     while (h > 2 && ceil_div(s, 8 * (h - 1)) * ct <= c->sm_count) --h;
-    const size_t smem = (size_t)CF_STAGES * (8 * h + CF_BN) * CF_K * sizeof(double) + 1024;
+    const size_t smem = (size_t)cf_stages(h) * (8 * h + CF_BN) * CF_K * sizeof(double) + 1024;
     dim3 grid(ct, ceil_div(s, 8 * h));
 #define CF_LAUNCH(HH)                                                                                                 \
   {                                                                                                                   \

@@ -947,7 +947,7 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y, bool
   // K << s: Chebyshev-filtered subspace iteration on the tensor cores (chfsi.cu); it certifies its own result
   // (residuals) and leaves G untouched, so anything it declines or fails on takes the direct route below
   static const bool no_chfsi = std::getenv("FLGP_EIGH_DIRECT") != nullptr;
-  if (!no_chfsi && s >= 1024 && 5 * K <= s) {
+  if (!no_chfsi && s >= 1000 && 5 * K <= s) {
     bool ok;
     {
       StageScope st(c, "eigh_chfsi");

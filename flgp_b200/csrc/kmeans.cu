@@ -890,7 +890,29 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
     }
     return;
   }
-  // bitonic sort of (cc, j) ascending; padding is (+inf, INT_MAX); ties broken by j => deterministic lists
+  // sort of (cc, j) ascending, ties broken by j => deterministic lists.  Short lists (the usual case: a few dozen
+  // neighbours) by ranking: entry t goes to position #{u : key_u < key_t}, one pass over the list per thread and two
+  // barriers instead of the ~log^2 barriers of the bitonic network below (the sort was most of this kernel's time).
+  if (cnt <= 256) {
+    double ct = 0.0;
+    int jt = 0, rank = 0;
+    if (tid < cnt) {
+      ct = kcc[tid];
+      jt = kj[tid];
+      for (int u = 0; u < cnt; ++u) {
+        const double cu = kcc[u];
+        const int ju = kj[u];
+        rank += (cu < ct) || (cu == ct && ju < jt);
+      }
+    }
+    __syncthreads();
+    if (tid < cnt) {
+      kcc[rank] = ct;
+      kj[rank] = jt;
+    }
+    __syncthreads();
+  } else {
+  // bitonic sort of (cc, j) ascending; padding is (+inf, INT_MAX)
   int npow = 1;
   while (npow < cnt) npow <<= 1;
   for (int k2 = 2; k2 <= npow; k2 <<= 1)
@@ -912,6 +934,7 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
       }
       __syncthreads();
     }
+  }
   double mv = 0.0;  // largest displacement among the listed centres (lower-bound decay of this cluster's points)
   for (int t = tid; t < cnt; t += 256) {
     list_j[(size_t)a * KM_LMAX + t] = kj[t];
