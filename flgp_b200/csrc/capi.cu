@@ -60,6 +60,12 @@ int guard(F f) {
   }
 }
 
+// every entry point works on its context's device, whatever device the calling thread had current
+Ctx* on_device(Ctx* c) {
+  FLGP_CUDA(cudaSetDevice(c->device));
+  return c;
+}
+
 void need(bool ok, const char* msg) {
   if (!ok) fail(2, "%s", msg);
 }
@@ -899,7 +905,7 @@ int flgp_subsample(flgp_ctx* ctx, const double* X, int64_t n, int d, int s, cons
   return guard([&] {
     need(ctx && X && U, "null argument");
     need(n >= 1 && d >= 1, "bad matrix shape");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     need(c->nranks == 1, "flgp_subsample is single-process; use the sharded spectrum entry for multi-GPU");
     DevBuf<double> dX((size_t)n * d);
     dX.upload(X, (size_t)n * d, c->stream);
@@ -924,7 +930,7 @@ int flgp_knn(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, 
     need(ctx && X && U && ind, "null argument");
     need(n >= 0 && d >= 1 && s >= 1, "bad matrix shape");
     need((Zj == nullptr) == (Zx == nullptr), "Zj and Zx go together");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     const bool want_dist = dist || Zj;
     DevBuf<double> dX((size_t)std::max<int64_t>(n * d, 1)), dU((size_t)s * d), ddist;
     DevBuf<int32_t> dind((size_t)std::max<int64_t>(n * r, 1));
@@ -951,7 +957,7 @@ int flgp_knn(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, 
 int flgp_simplex_project(flgp_ctx* ctx, const double* v, int r, double* z) {
   return guard([&] {
     need(ctx && v && z && r >= 1, "bad argument");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<double> dv(r), dz(r);
     dv.upload(v, r, c->stream);
     simplex_project_run(c, dv.p, r, dz.p);
@@ -963,7 +969,7 @@ int flgp_simplex_project(flgp_ctx* ctx, const double* v, int r, double* z) {
 int flgp_lae_point(flgp_ctx* ctx, const double* x, int d, const double* Ur, int r, double* z) {
   return guard([&] {
     need(ctx && x && Ur && z && d >= 1, "bad argument");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<double> dx(d), dU((size_t)r * d), dz(r);
     dx.upload(x, d, c->stream);
     dU.upload(Ur, (size_t)r * d, c->stream);
@@ -978,7 +984,7 @@ int flgp_lae(flgp_ctx* ctx, const double* X, int64_t n, int d, const double* U, 
   return guard([&] {
     need(ctx && X && U && Zj && Zx, "null argument");
     need(n >= 1 && d >= 1 && s >= 1, "bad matrix shape");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<double> dX((size_t)n * d), dU((size_t)s * d), dZx((size_t)n * r);
     DevBuf<int32_t> dind((size_t)n * r), dZj((size_t)n * r);
     DevBuf<long long> dst(2);
@@ -1006,7 +1012,7 @@ int flgp_graph_laplacian(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* 
     need(n >= 1 && s >= 1 && r >= 1, "bad shape");
     parse_gl(gl);
     need(gl != FLGP_GL_CLUSTER_NORMALIZED || num_class, "cluster-normalized needs the cluster sizes");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<int32_t> dZj((size_t)n * r);
     DevBuf<double> dZx((size_t)n * r), dnc(s);
     dZj.upload(Zj, (size_t)n * r, c->stream);
@@ -1028,7 +1034,7 @@ static int cross_similarity(flgp_ctx* ctx, const double* X, int64_t n, int d, co
     parse_gl(gl);
     if (gl == FLGP_GL_CLUSTER_NORMALIZED && ucols != d + 1)
       fail(2, "gl=\"cluster-normalized\" needs the cluster-size column of U (SURVEY Appendix A.1)");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     flgp_spectrum sp;
     sp.c = c;
     sp.n_local = sp.n_total = n;
@@ -1060,7 +1066,7 @@ int flgp_spectrum_from_z(flgp_ctx* ctx, int64_t n, int s, int r, const int32_t* 
   return guard([&] {
     need(ctx && Zj && Zx, "null argument");
     need(n >= 1 && s >= 1 && r >= 1 && r <= s, "bad shape");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
     sp->c = c;
     sp->n_local = sp->n_total = n;
@@ -1087,7 +1093,7 @@ int flgp_eigs_sym(flgp_ctx* ctx, const double* A, int s, int K, double* values, 
   return guard([&] {
     need(ctx && A && values, "null argument");
     need(s >= 1 && K >= 1 && K <= s, "need 1 <= K <= s");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<double> G((size_t)s * s), lam(K), Y((size_t)s * K);
     G.upload(A, (size_t)s * s, c->stream);
     {
@@ -1119,7 +1125,7 @@ int flgp_heat_kernel_spectrum_sharded(flgp_ctx* ctx, const double* X_local, int6
   return guard([&] {
     need(ctx && out && (X_local || n_local == 0), "null argument");
     need(n_local >= 0 && d >= 1, "bad matrix shape");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     DevBuf<double> dX((size_t)std::max<int64_t>(n_local * d, 1));
     if (n_local) dX.upload(X_local, (size_t)n_local * d, c->stream);
     Models mo = make_models(subsample, kernel, gl, root, nstart, epsilon, iter_max);
@@ -1134,7 +1140,7 @@ int flgp_heat_kernel_spectrum(flgp_ctx* ctx, const double* X, int64_t m, const d
   return guard([&] {
     need(ctx && out && X, "null argument");
     need(m >= 1 && m_new >= 0 && d >= 1 && (X_new || m_new == 0), "bad matrix shape");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     need(c->nranks == 1, "use flgp_heat_kernel_spectrum_sharded for multi-GPU runs");
     DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
     Models mo = make_models(subsample, kernel, gl, root, nstart, epsilon, iter_max);
@@ -1178,7 +1184,7 @@ int flgp_spectrum_z(const flgp_spectrum* h, int32_t* Zj, double* Zx) {
 int flgp_spectrum_vectors(flgp_spectrum* h, double* vectors) {
   return guard([&] {
     need(h && vectors, "null argument");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     DevBuf<double> V((size_t)std::max<int64_t>(h->n_local * h->K, 1));
     lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, h->K, nullptr, h->n_local, V.p, h->n_local, true);
     if (h->n_local) V.download(vectors, (size_t)h->n_local * h->K, c->stream);
@@ -1190,7 +1196,7 @@ int flgp_spectrum_gather_rows(flgp_spectrum* h, const int32_t* idx, int64_t n_id
   return guard([&] {
     need(h && idx && V && n_idx >= 1, "bad argument");
     for (int64_t a = 0; a < n_idx; ++a) need(idx[a] >= 0 && idx[a] < h->n_local, "row index out of range");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     DevBuf<int32_t> di((size_t)n_idx);
     DevBuf<double> dV((size_t)n_idx * h->K);
     di.upload(idx, n_idx, c->stream);
@@ -1208,7 +1214,7 @@ int flgp_hk_from_spectrum(flgp_spectrum* h, int K, double t, const int32_t* idx0
     need(K >= 1 && K <= h->K, "K exceeds the number of computed eigenpairs");
     for (int64_t a = 0; a < n0; ++a) need(idx0[a] >= 0 && idx0[a] < h->n_local, "row index out of range");
     for (int64_t a = 0; a < n1; ++a) need(idx1[a] >= 0 && idx1[a] < h->n_local, "row index out of range");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     const int KK = h->K;
     StageScope st(c, "hk_from_spectrum", 2.0 * K * (double)n0 * n1, 8.0 * (double)n0 * n1);
     DevBuf<int32_t> d0((size_t)n0), d1((size_t)n1);
@@ -1275,7 +1281,7 @@ int flgp_regression_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_tot
   return guard([&] {
     need(h && y_pred, "null argument");
     if (K < 0) K = h->K;
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
     need(Y_local || m_local == 0, "labels missing");
     DevBuf<double> dY((size_t)std::max<int64_t>(m_local, 1)), dy((size_t)std::max<int64_t>(h->n_local, 1)),
@@ -1326,7 +1332,7 @@ int flgp_regression_objective(flgp_spectrum* h, const double* Y_local, int64_t m
     need(h && Y_local && pars && obj, "null argument");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
     DevBuf<double> dY(std::max<int64_t>(m_local, 1));
     if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
@@ -1341,7 +1347,7 @@ int flgp_train_regression(flgp_spectrum* h, const double* Y_local, int64_t m_tot
     need(h && Y_local && pars_io, "null argument");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
     DevBuf<double> dY(std::max<int64_t>(m_local, 1));
     if (m_local > 0) dY.upload(Y_local, m_local, c->stream);
@@ -1408,7 +1414,7 @@ int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, cons
     need(m >= 1 && m_new >= 0, "bad matrix shape");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     need(c->nranks == 1, "flgp_fit_se_regression is the single-process entry point");
     const int64_t n = m + m_new;
     DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
@@ -1540,7 +1546,7 @@ int flgp_fit_nystrom_regression(flgp_ctx* ctx, const double* X, const double* Y,
     need(m >= 1 && m_new >= 0 && d >= 1 && n_a2 >= 1, "bad matrix shape");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     need(c->nranks == 1, "flgp_fit_nystrom_regression is the single-process entry point (see ..._sharded)");
     const int64_t n = m + m_new;
     need(s >= 1 && s <= n && n < ((int64_t)1 << 31), "need 1 <= s <= n");
@@ -1571,7 +1577,7 @@ int flgp_fit_nystrom_regression_sharded(flgp_ctx* ctx, const double* X_local, in
     need(n_local == 0 || X_local, "null argument");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     need(s >= 1 && s <= n_total && n_total < ((int64_t)1 << 31), "need 1 <= s <= n");
     if (K < 0) K = s;
     need(K >= 1 && K <= s, "need 1 <= K <= s");
@@ -1706,7 +1712,7 @@ int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local,
                                         double sigma, double tol, int max_iter, double* mean, double* cov) {
   return guard([&] {
     need(h && Y_local && mean, "null argument");
-    Ctx* c = h->c;
+    Ctx* c = on_device(h->c);
     const int64_t m_local = std::max<int64_t>(0, std::min<int64_t>(h->n_local, m_total - h->row_offset));
     DevBuf<double> dY(std::max<int64_t>(m_local, 1)), dm(std::max<int64_t>(h->n_local, 1)),
         dc(std::max<int64_t>(h->n_local, 1));
@@ -1727,7 +1733,7 @@ int flgp_posterior_distribution_classification(flgp_ctx* ctx, const double* C11,
   return guard([&] {
     need(ctx && C11 && C21 && C22 && Y && mean && cov, "null argument");
     need(m >= 1 && m <= 8192 && m_new >= 0, "classification: need 1 <= m <= 8192 labelled rows");
-    Ctx* c = &ctx->c;
+    Ctx* c = on_device(&ctx->c);
     std::vector<double> c11(C11, C11 + (size_t)m * m), pi, beta;
     laplace_mode(c11, Y, m, tol, max_iter > 0 ? max_iter : 100, pi, beta);
     if (m_new == 0) return;

@@ -1,17 +1,22 @@
-// eigh.cu — on-device top-K symmetric eigensolver for the s x s Gram A^T A
+// eigh.cu — on-device top-K symmetric eigensolver for the s x s Gram A^T A: dispatcher + the direct route
 // (replaces the RSpectra::svds / Eigen::BDCSVD call of truncated_SVD_cpp,
 //  /root/reference/src/TruncatedSVD.cpp:9-34; sigma^2 = eigenvalues of the Gram, right vectors lifted
 //  later by sparse.cu).  No host LAPACK, no cuSOLVER: everything stays in HBM/L2.
 //
-//   1. Householder tridiagonalisation  Q^T G Q = T      one persistent cooperative kernel; the
-//      trailing matrix (<= 32 MB at s = 2000) stays L2-resident; 2 grid barriers per column.
-//   2. top-K eigenvalues of T by warp-wide multisection of the Sturm count (33-way per pass).
-//   3. eigenvectors of T by inverse iteration (pivoted tridiagonal LU per eigenvalue, one thread
-//      each, interleaved storage) with modified Gram-Schmidt inside clusters of close eigenvalues.
-//   4. back-transformation Y = Q X, one CTA per eigenvector, vector resident in shared memory.
+// eigh_topk_run: K <= s/5 and s >= 1000 -> Chebyshev-filtered subspace iteration on the FP64 tensor cores (chfsi.cu);
+// anything else, and whatever that route declines or does not converge on -> the direct route below:
+//   1. Householder tridiagonalisation  Q^T G Q = T, ONE barrier and one pass over the trailing matrix per column
+//      (the rank-2 update of column k-1 is applied while A v_k is accumulated):
+//        s <= 832   one thread-block cluster (8 or 16 CTAs), matrix resident in distributed shared memory,
+//                   hardware cluster barrier (tridiag_cluster_kernel);
+//        larger     cooperative grid, all-to-all flag barrier: streaming through L2 until the trailing matrix fits
+//                   the grid's shared memory, resident after that (tridiag_kernel<false|true>).
+//   2. top-K eigenvalues of T: one CTA per eigenvalue, 129-way multisection of the Sturm count.
+//   3. eigenvectors of T by inverse iteration (pivoted tridiagonal LU per eigenvalue, one thread each, interleaved
+//      storage) with modified Gram-Schmidt inside clusters of close eigenvalues, CGS2 for clusters > 12.
+//   4. back-transformation Y = Q X with compact-WY blocks of 32 reflectors.
 //
-// Work: (4/3) s^3 flop for step 1 (BLAS-2, L2-bandwidth bound: 24 bytes per trailing element per
-// column => 8 s^3 bytes), 2 s^2 K flop for step 4.
+// Work: (4/3) s^3 flop for step 1 (BLAS-2; latency bound: s-1 dependent steps), 2 s^2 K flop for step 4.
 #include <cooperative_groups.h>
 
 #include <algorithm>

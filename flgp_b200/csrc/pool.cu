@@ -1,6 +1,8 @@
-// pool.cu — size-keyed cache of device blocks (declared in common.cuh).
+// pool.cu — cache of device blocks keyed by (device, size) (declared in common.cuh): a block is only ever handed
+// back on the device it was allocated on.
 #include <map>
 #include <mutex>
+#include <utility>
 
 #include "common.cuh"
 
@@ -8,20 +10,26 @@ namespace flgp {
 namespace {
 struct Pool {
   std::mutex mu;
-  std::multimap<size_t, void*> free_blocks;
+  std::multimap<std::pair<int, size_t>, void*> free_blocks;  // (device, bytes)
   size_t cached = 0;
   int live_ctx = 0;
   static constexpr size_t kLimit = (size_t)48 << 30;  // bytes kept at most
 } g_pool;
 size_t round_up(size_t b) { return (b + 511) & ~(size_t)511; }
+int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
 }  // namespace
 
 void* pool_alloc(size_t bytes) {
   bytes = round_up(bytes);
+  const int dev = current_device();
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     if (g_pool.live_ctx <= 1) {
-      auto it = g_pool.free_blocks.find(bytes);
+      auto it = g_pool.free_blocks.find(std::make_pair(dev, bytes));
       if (it != g_pool.free_blocks.end()) {
         void* p = it->second;
         g_pool.free_blocks.erase(it);
@@ -42,10 +50,13 @@ void* pool_alloc(size_t bytes) {
 
 void pool_free(void* p, size_t bytes) {
   bytes = round_up(bytes);
+  cudaPointerAttributes at;
+  int dev = current_device();
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess) dev = at.device;  // the device that owns the block
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     if (g_pool.live_ctx <= 1 && g_pool.cached + bytes <= Pool::kLimit) {
-      g_pool.free_blocks.emplace(bytes, p);
+      g_pool.free_blocks.emplace(std::make_pair(dev, bytes), p);
       g_pool.cached += bytes;
       return;
     }
@@ -59,7 +70,7 @@ void pool_ctx_count(int delta) {
 }
 
 void pool_trim() {
-  std::multimap<size_t, void*> blocks;
+  std::multimap<std::pair<int, size_t>, void*> blocks;
   {
     std::lock_guard<std::mutex> lk(g_pool.mu);
     blocks.swap(g_pool.free_blocks);

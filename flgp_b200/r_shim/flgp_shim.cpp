@@ -284,6 +284,36 @@ Rcpp::List fit_nystrom_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::Nume
   return pack_fit(train, test, cov, pars);
 }
 
+// fit_lae_logit_gp_cpp (src/Fit.cpp:521-600), signature unchanged (src/Fit.h).  Spectrum, COBYLA training of t and the
+// Laplace posterior of the test rows run behind the C ABI; the labels still come from the reference's Polya-Gamma Gibbs
+// sampler (test_pgbinary_cpp, src/Predict.cpp:11-26: R's RNG) on the covariance block C the library returns.
+Rcpp::List test_pgbinary_cpp(const Eigen::MatrixXd& Cvv, const Eigen::VectorXd& Y, const Eigen::MatrixXd& C);  // reference
+Rcpp::List fit_lae_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                int s, int r, int K, Rcpp::NumericVector N_train, double sigma, std::string approach,
+                                Rcpp::List models, bool output_cov, int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const Eigen::Map<Eigen::VectorXd> N(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(N_train));
+  const int m = X.rows(), m_new = X_new.rows();
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]), ker = Rcpp::as<std::string>(models["kernel"]);
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  double t = NA_REAL, obj = 0.0;  // NaN: train
+  Eigen::VectorXd mean(m_new), cov(m_new);
+  Eigen::MatrixXd C(m + m_new, m);
+  ok(flgp_fit_lae_logit(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, N.data(), sigma,
+                        approach.c_str(), sub.c_str(), ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
+                        Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, &t, mean.data(), cov.data(),
+                        C.data(), &obj));
+  Eigen::VectorXd label = Rcpp::as<Eigen::VectorXd>(test_pgbinary_cpp(C.topRows(m), Y, C)["Y_pred"]);
+  Rcpp::List Y_pred = Rcpp::List::create(Rcpp::Named("train") = label.head(m), Rcpp::Named("test") = label.tail(m_new));
+  Rcpp::List post = Rcpp::List::create(Rcpp::Named("mean") = mean, Rcpp::Named("cov") = cov);
+  if (output_cov)
+    return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("C") = C, Rcpp::Named("posterior") = post,
+                              Rcpp::Named("pars") = t);
+  return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
+}
+
 // [[Rcpp::export(posterior_distribution_classification)]]  -- signature unchanged (src/Utils.h:77-80)
 Rcpp::List posterior_distribution_classification(const Eigen::MatrixXd& C11, const Eigen::MatrixXd& C21,
                                                  const Eigen::VectorXd& C22, const Eigen::VectorXd& Y, double tol,

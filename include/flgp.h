@@ -229,7 +229,9 @@ int flgp_fit_nystrom_regression_sharded(flgp_ctx* ctx, const double* X_local, in
  * the GP classifier — Newton iterations on the m labelled rows (labels 0/1, f = 0 start, |df|_1 < tol), then the
  * predictive mean C21 (Y - pi) and variance C22 - rowsum((C21 beta) o C21) of EVERY local row, folded through the
  * factored eigenvectors (C21 = V2 Lam V1^T is never formed).  Cvv carries + sigma on its diagonal and C22 + sigma, as
- * in the driver.  The labels' Polya-Gamma sampler (R RNG) and the COBYLA training of t are not part of this path. */
+ * in the driver.  The labels' Polya-Gamma sampler (R RNG) is not part of this path (training of t: flgp_train_logit).
+ * The Newton mode is m x m dense algebra on the host (as in the reference: Eigen LLT): O(m^3) per Newton step, meant
+ * for the m of the reference's use (hundreds to a few thousand labelled rows; m <= 8192 is accepted). */
 int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
                                         double sigma, double tol, int max_iter, double* mean, double* cov);
 /* The export itself, posterior_distribution_classification(C11, C21, C22, Y, tol, max_iter) (src/Utils.h:77-80) on
