@@ -3,7 +3,7 @@
 //  /root/reference/src/TruncatedSVD.cpp:9-34; sigma^2 = eigenvalues of the Gram, right vectors lifted
 //  later by sparse.cu).  No host LAPACK, no cuSOLVER: everything stays in HBM/L2.
 //
-// eigh_topk_run: K <= s/5 and s >= 1000 -> Chebyshev-filtered subspace iteration on the FP64 tensor cores (chfsi.cu);
+// eigh_topk_run: K <= s/5 and s >= 1024 -> Chebyshev-filtered subspace iteration on the FP64 tensor cores (chfsi.cu);
 // anything else, and whatever that route declines or does not converge on -> the direct route below:
 //   1. Householder tridiagonalisation  Q^T G Q = T, ONE barrier and one pass over the trailing matrix per column
 //      (the rank-2 update of column k-1 is applied while A v_k is accumulated):
@@ -952,7 +952,7 @@ void eigh_topk_run(Ctx* c, double* G, int s, int K, double* lam, double* Y, bool
   // K << s: Chebyshev-filtered subspace iteration on the tensor cores (chfsi.cu); it certifies its own result
   // (residuals) and leaves G untouched, so anything it declines or fails on takes the direct route below
   static const bool no_chfsi = std::getenv("FLGP_EIGH_DIRECT") != nullptr;
-  if (!no_chfsi && s >= 1000 && 5 * K <= s) {
+  if (!no_chfsi && s >= 1024 && 5 * K <= s) {
     bool ok;
     {
       StageScope st(c, "eigh_chfsi");
