@@ -708,6 +708,24 @@ const bool g_cf_debug = std::getenv("FLGP_CHFSI_DEBUG") != nullptr;
 
 }  // namespace
 
+bool chol_inv_run(Ctx* c, const double* S, int nb, double* Linv, double* ratio) {
+  if (nb < 1 || nb > 512) fail(2, "chol_inv: order %d outside 1..512", nb);
+  DevBuf<double> Zg((size_t)CH_NB * nb), info(4);
+  const int rows_cta = ceil_div(nb, CH_NC);
+  const size_t smem = ((size_t)2 * CH_NB * 33 + (size_t)CH_NB * nb + (size_t)rows_cta * 33) * sizeof(double);
+  static bool attr = false;
+  if (!attr) {
+    FLGP_CUDA(cudaFuncSetAttribute(cf_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  FLGP_LAUNCH(c, cf_chol_inv_kernel, CH_NC, CH_THREADS, smem, S, nb, Linv, Zg.p, info.p, (long long*)nullptr);
+  double ih[3];
+  info.download(ih, 3, c->stream);
+  sync(c);
+  if (ratio) *ratio = ih[2] > 0.0 ? ih[1] / ih[2] : 0.0;
+  return ih[0] == 0.0 && ih[1] > 0.0;
+}
+
 // Top-K eigenpairs of G (s x s, symmetric, full storage, only read).  lam (K, descending) and Y (s x K column-major,
 // orthonormal) on the device.  psd: the caller knows G is positive semi-definite (a Gram).  Returns false when the
 // iteration is not applicable or did not converge (outputs then undefined; G untouched).

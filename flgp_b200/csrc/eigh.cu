@@ -23,6 +23,8 @@
 #include <cfloat>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 
 #include "kernels.cuh"
 
@@ -737,7 +739,7 @@ invit_mgs_kernel(int s, int K, const int* __restrict__ cstart, double* __restric
 constexpr int CGS_MIN = 12, CGS_THREADS = 1024;
 
 __global__ void __launch_bounds__(CGS_THREADS)
-invit_cgs2_kernel(int s, int K, const int* __restrict__ cstart, double* __restrict__ X) {
+invit_cgs2_kernel(int s, int K, const int* __restrict__ cstart, double* __restrict__ X, int min_size) {
   extern __shared__ double cg_sm[];  // part[32][mc] then coef[mc]
   __shared__ double red[32];
   const int k0 = blockIdx.x;
@@ -745,7 +747,7 @@ invit_cgs2_kernel(int s, int K, const int* __restrict__ cstart, double* __restri
   int k1 = k0 + 1;
   while (k1 < K && cstart[k1] == k0) ++k1;
   const int mc = k1 - k0;
-  if (mc <= CGS_MIN) return;  // small clusters: invit_mgs_kernel
+  if (mc <= CGS_MIN || mc < min_size) return;  // small clusters: invit_mgs_kernel; mid-sized: Cholesky-QR (host loop)
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   double* part = cg_sm;                    // 32 x mc
   double* coef = cg_sm + (size_t)32 * mc;  // mc
@@ -1114,10 +1116,43 @@ void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y) {
     StageScope st(c, "eigh_inverse_iteration");
     FLGP_LAUNCH(c, invit_factor_kernel, ceil_div(K, 64), 64, 0, dd.p, ee.p, s, K, lam, tiny, dg.p, du.p, du2.p, dl.p,
                 piv.p, X.p);
+    // clusters of 13 .. 512 close eigenvalues: Cholesky-QR (Gram + cluster Cholesky + rotation: GEMM-shaped, all SMs)
+    // instead of Gram-Schmidt by one CTA, which was 67 of the 87 ms of the Nystrom anchor eigensolve (150-member
+    // cluster of an exponentially decaying spectrum).  Any orthonormal basis of the cluster's span serves inverse
+    // iteration; a Gram that is numerically singular falls back to the Gram-Schmidt kernel.
+    std::vector<std::pair<int, int>> mid;  // (first column, size)
+    for (int k = 0; k < K;) {
+      int e = k + 1;
+      while (e < K && cstart[e] == k) ++e;
+      if (e - k > CGS_MIN && e - k <= 512) mid.emplace_back(k, e - k);
+      k = e;
+    }
+    int mid_max = 0;
+    for (auto& m_ : mid) mid_max = std::max(mid_max, m_.second);
+    DevBuf<double> Sc((size_t)std::max(mid_max, 1) * std::max(mid_max, 1)), Lc((size_t)std::max(mid_max, 1) * std::max(mid_max, 1)),
+        Tc((size_t)s * std::max(mid_max, 1));
+    auto cluster_cholqr = [&](int k0, int mc) -> bool {
+      for (int pass = 0; pass < 2; ++pass) {
+        // S = Xc^T Xc (Xc = columns k0 .. k0+mc-1 of the row-major s x K array X)
+        gemm_general_splitk_run(c, X.p + k0, 1, K, X.p + k0, K, 1, mc, mc, s, Sc.p);
+        double ratio = 0.0;
+        if (!chol_inv_run(c, Sc.p, mc, Lc.p, &ratio)) return false;
+        // Xc <- Xc L^-T : T(q, j) = sum_i Xc(q, i) Linv(j, i)
+        gemm_general_run(c, X.p + k0, K, 1, Lc.p, 1, mc, s, mc, mc, Tc.p, mc, 1);
+        FLGP_CUDA(cudaMemcpy2DAsync(X.p + k0, sizeof(double) * K, Tc.p, sizeof(double) * mc, sizeof(double) * mc, s,
+                                    cudaMemcpyDeviceToDevice, c->stream));
+        if (ratio > 0.3) break;
+      }
+      return true;
+    };
     for (int it = 0; it < 3; ++it) {
       FLGP_LAUNCH(c, invit_solve_kernel, ceil_div(K, 64), 64, 0, s, K, dg.p, du.p, du2.p, dl.p, piv.p, X.p);
       FLGP_LAUNCH(c, invit_mgs_kernel, K, 256, 0, s, K, cs.p, X.p, cgs_ok ? CGS_MIN : K);
-      if (cgs_ok) FLGP_LAUNCH(c, invit_cgs2_kernel, K, CGS_THREADS, cgs_smem, s, K, cs.p, X.p);
+      bool chol_ok = true;
+      for (auto& m_ : mid) chol_ok = chol_ok && cluster_cholqr(m_.first, m_.second);
+      // clusters beyond 512 members, and everything mid-sized when a Gram was singular: Gram-Schmidt kernel
+      if (cgs_ok && (max_cluster > 512 || !chol_ok))
+        FLGP_LAUNCH(c, invit_cgs2_kernel, K, CGS_THREADS, cgs_smem, s, K, cs.p, X.p, chol_ok ? 513 : 0);
     }
   }
   // 4. back-transformation (blocked compact WY)

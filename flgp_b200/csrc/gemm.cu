@@ -217,6 +217,15 @@ void gemm_nt_ld_run(Ctx* c, const double* A, int64_t lda, const double* B, int64
               (int64_t)0);
 }
 
+void gemm_general_run(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs, int64_t bcs,
+                      int64_t M, int64_t N, int K, double* C, int64_t crs, int64_t ccs) {
+  gemm_strided(c, A, ars, acs, B, brs, bcs, nullptr, M, N, K, C, crs, ccs);
+}
+void gemm_general_splitk_run(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs,
+                             int64_t bcs, int64_t M, int64_t N, int K, double* C) {
+  gemm_strided_splitk(c, A, ars, acs, B, brs, bcs, M, N, K, C);
+}
+
 void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C) {
   gemm_strided(c, A, K, 1, B, N, 1, nullptr, M, N, K, C, N, 1);
 }

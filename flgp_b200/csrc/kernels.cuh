@@ -100,6 +100,12 @@ void gemm_nt_ld_run(Ctx* c, const double* A, int64_t lda, const double* B, int64
                     int64_t N, int K, double* C, int64_t ldc);
 // C(M x N row-major) = A(M x K row-major) * B(K x N row-major)
 void gemm_nn_run(Ctx* c, const double* A, const double* B, int64_t M, int64_t N, int K, double* C);
+// generic strides (FMA kernel): C(i,j) [at i*crs + j*ccs] = sum_k A(i,k) [i*ars + k*acs] B(k,j) [k*brs + j*bcs]
+void gemm_general_run(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs, int64_t bcs,
+                      int64_t M, int64_t N, int K, double* C, int64_t crs, int64_t ccs);
+// the same with the contraction split into slabs (few output tiles, long K); C dense column-major M x N
+void gemm_general_splitk_run(Ctx* c, const double* A, int64_t ars, int64_t acs, const double* B, int64_t brs,
+                             int64_t bcs, int64_t M, int64_t N, int K, double* C);
 // small: y(M) = A(M x K row-major) x(K)
 void gemv_run(Ctx* c, const double* A, const double* x, int64_t M, int K, double* y);
 // G(K x K, col-major) = V^T V and g = V^T y over n_rows rows of V (row-major n_rows x K); deterministic
@@ -137,6 +143,9 @@ void eigh_direct_run(Ctx* c, double* G, int s, int K, double* lam, double* Y);
 // chfsi.cu: Chebyshev-filtered subspace iteration (K << s, s even); G is only read.  false = not applicable or not
 // converged (outputs undefined).
 bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* Y, bool psd);
+// Cholesky factor and its inverse of an SPD matrix S (nb x nb column-major, nb <= 512) on one thread-block cluster:
+// Linv (nb x nb ROW-major, lower) = L^-1, S = L L^T.  false: a pivot was not positive.  *ratio = min / max diag(L).
+bool chol_inv_run(Ctx* c, const double* S, int nb, double* Linv, double* ratio);
 
 // ---- misc ------------------------------------------------------------------------------------
 double dfma_peak_run(Ctx* c, int iters);  // measured fp64 FMA TFLOP/s (roofline denominator)
