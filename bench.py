@@ -44,7 +44,7 @@ NCU_TRAFFIC = {
     "kmeans_assign_small": (311.2e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_kmeans_assign_small.ncu-rep)"),
     "tridiag_resident": (25.3e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_resident.ncu-rep)"),
     "tridiag_streaming": (37.6e6, "profiles/r1_ncu_full_summary.csv (r1_ncu_tridiag_streaming.ncu-rep)"),
-    "cheb_gemm": (40.2e6, "profiles/r2_ncu_full_summary.csv (r2_cheb_gemm_v2.ncu-rep, cheb_gemm_kernel<7>, one launch)"),
+    "cheb_gemm": (40.2e6, "profiles/r2_ncu_full_summary.csv (r2_ncu_cheb_gemm_v3.ncu-rep, cheb_gemm_kernel<7>, one launch)"),
 }
 
 PARS = (10.0, 0.01)   # (t, noise variance): fixed hyper-parameters
