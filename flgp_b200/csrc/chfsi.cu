@@ -493,13 +493,15 @@ cf_chol_inv_kernel(const double* __restrict__ S, int nb, double* M, double* Zg, 
 }
 
 // ---- Lanczos (density of states) -----------------------------------------------------------------------------------
-constexpr int LZ_NV = 8;       // simultaneous, independent Lanczos runs = one n-block of the DMMA
+constexpr int LZ_NB = 2;       // n-blocks of the DMMA
+constexpr int LZ_NV = 8 * LZ_NB;  // simultaneous, independent Lanczos runs (16: the quadrature's variance, not its
+                               // resolution, limits the cut estimate - 16 runs x 20 steps beat 8 x 32 at 0.6 of the cost)
 constexpr int LZ_BM = 16;      // rows of G per CTA (two consumer warps of 8 rows)
 constexpr int LZ_SUB = 4;      // 16-wide k slabs per ring stage (a slab is consumed in ~100 cycles: fewer, fatter stages)
 constexpr int LZ_STAGES = 8;
-constexpr uint32_t LZ_SLAB_BYTES = (LZ_BM + LZ_NV) * CF_K * sizeof(double);  // 3072: G box 16 x 16, V box 8 x 16
-// U = G V for the 8 runs at once on the tensor cores (V, Vp, U: s x 8 column-major, ld s), plus this CTA's share of
-// the inner products u.v, u.u, u.vp per run: partial[(cta * 3 + which) * 8 + run].
+constexpr uint32_t LZ_SLAB_BYTES = (LZ_BM + LZ_NV) * CF_K * sizeof(double);  // G box 16 x 16, V box LZ_NV x 16
+// U = G V for all runs at once on the tensor cores (V, Vp, U: s x LZ_NV column-major, ld s), plus this CTA's share of
+// the inner products u.v, u.u, u.vp per run: partial[(cta * 3 + which) * LZ_NV + run].
 __global__ void __launch_bounds__(96)
 lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapV, int s,
                     const double* __restrict__ V, const double* __restrict__ Vp, double* __restrict__ U,
@@ -546,21 +548,24 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
   }
   // one accumulator pair per k-slab position: a single pair would chain all 4 ceil(s/16) DMMAs of the row block
   // through the tensor pipe's latency (the kernel was 2x slower for it); the partial sums are added in a fixed order
-  double acc[LZ_SUB][2];
+  double acc[LZ_SUB][LZ_NB][2];
 #pragma unroll
-  for (int u = 0; u < LZ_SUB; ++u) acc[u][0] = acc[u][1] = 0.0;
+  for (int u = 0; u < LZ_SUB; ++u)
+#pragma unroll
+    for (int b = 0; b < LZ_NB; ++b) acc[u][b][0] = acc[u][b][1] = 0.0;
   for (int t = 0; t < nst; ++t) {
     const int st = t % LZ_STAGES;
     mbar_wait(&full[st], (t / LZ_STAGES) & 1);
     const int nsub = min(LZ_SUB, nslab - t * LZ_SUB);
-    double af[LZ_SUB][4], bf[LZ_SUB][4];
+    double af[LZ_SUB][4], bf[LZ_SUB][LZ_NB][4];
 #pragma unroll
     for (int u = 0; u < LZ_SUB; ++u) {
       const uint32_t sb = boxes + (uint32_t)(st * LZ_SUB + u) * LZ_SLAB_BYTES;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         af[u][q] = (u < nsub) ? lds_f64(sb + offA[q]) : 0.0;
-        bf[u][q] = (u < nsub) ? lds_f64(sb + offB[q]) : 0.0;
+#pragma unroll
+        for (int b = 0; b < LZ_NB; ++b) bf[u][b][q] = (u < nsub) ? lds_f64(sb + offB[q] + b * 1024) : 0.0;
       }
     }
     __syncwarp();
@@ -568,36 +573,40 @@ lanczos_symv_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_const
 #pragma unroll
     for (int q = 0; q < 4; ++q)
 #pragma unroll
-      for (int u = 0; u < LZ_SUB; ++u) dmma_m8n8k4(acc[u][0], acc[u][1], af[u][q], bf[u][q]);
+      for (int u = 0; u < LZ_SUB; ++u)
+#pragma unroll
+        for (int b = 0; b < LZ_NB; ++b) dmma_m8n8k4(acc[u][b][0], acc[u][b][1], af[u][q], bf[u][b][q]);
   }
-  const double acc0 = (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
-  const double acc1 = (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
   static_assert(LZ_SUB == 4, "the final sum is written out for four partial accumulators");
-  // epilogue: u(i, run) for run = 2 fk, 2 fk + 1; inner products over this warp's 8 rows, then over the two warps
+  // epilogue: u(i, run) for run = 8 b + pr(2 fk + q); inner products over this warp's 8 rows, then over the two warps
   const int i = i0 + wid * 8 + fr;
-  double p[3][2];
 #pragma unroll
-  for (int q = 0; q < 2; ++q) {
-    const double u = q ? acc1 : acc0;
-    const int n = 2 * fk + q;
-    const int64_t at = i + (int64_t)s * (((n & 3) << 1) | (n >> 2));
-    const double v = (i < s) ? V[at] : 0.0, vp = (i < s) ? Vp[at] : 0.0;
-    if (i < s) U[at] = u;
-    p[0][q] = (i < s) ? u * v : 0.0;
-    p[1][q] = (i < s) ? u * u : 0.0;
-    p[2][q] = (i < s) ? u * vp : 0.0;
-  }
-#pragma unroll
-  for (int w = 0; w < 3; ++w)
+  for (int b = 0; b < LZ_NB; ++b) {
+    double p[3][2];
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
-      double x = p[w][q];
-      x += __shfl_xor_sync(0xffffffffu, x, 4);
-      x += __shfl_xor_sync(0xffffffffu, x, 8);
-      x += __shfl_xor_sync(0xffffffffu, x, 16);
+      const double u = (acc[0][b][q] + acc[1][b][q]) + (acc[2][b][q] + acc[3][b][q]);
       const int n = 2 * fk + q;
-      if (fg == 0) wsum[wid][w][((n & 3) << 1) | (n >> 2)] = x;
+      const int run = 8 * b + (((n & 3) << 1) | (n >> 2));
+      const int64_t at = i + (int64_t)s * run;
+      const double v = (i < s) ? V[at] : 0.0, vp = (i < s) ? Vp[at] : 0.0;
+      if (i < s) U[at] = u;
+      p[0][q] = (i < s) ? u * v : 0.0;
+      p[1][q] = (i < s) ? u * u : 0.0;
+      p[2][q] = (i < s) ? u * vp : 0.0;
     }
+#pragma unroll
+    for (int w = 0; w < 3; ++w)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        double x = p[w][q];
+        x += __shfl_xor_sync(0xffffffffu, x, 4);
+        x += __shfl_xor_sync(0xffffffffu, x, 8);
+        x += __shfl_xor_sync(0xffffffffu, x, 16);
+        const int n = 2 * fk + q;
+        if (fg == 0) wsum[wid][w][8 * b + (((n & 3) << 1) | (n >> 2))] = x;
+      }
+  }
   // the two consumer warps meet on a named barrier (the producer warp has left)
   asm volatile("bar.sync 1, 64;" ::: "memory");
   if (tid < 3 * LZ_NV) {
@@ -809,7 +818,7 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
   double gnorm;
   {
     StageScope st(c, "eigh_chfsi_dos");
-    const int kl = std::min(32, s / 4);
+    const int kl = std::min(20, s / 4);
     const int nparts = ceil_div(s, LZ_BM);
     DevBuf<double> Vb[3] = {DevBuf<double>((size_t)s * LZ_NV), DevBuf<double>((size_t)s * LZ_NV),
                             DevBuf<double>((size_t)s * LZ_NV)};
@@ -1008,8 +1017,9 @@ bool chfsi_topk_run(Ctx* c, const double* G, int s, int K, double* lam, double* 
       if (g_cf_debug) fprintf(stderr, "[chfsi]   cholqr pass %d: min/max diag(L) = %.2e\n", pass, ratio);
       last_ratio = ratio;
       // one pass leaves |X^T X - I| ~ eps / ratio^2: enough for the next filter segment or a rough Rayleigh-Ritz
-      // step as long as that stays below ~1e-8; the pass before an accepted result must have ratio >= 0.05
-      if (ratio > 2e-4) break;
+      // step as long as that stays below ~1e-6 (the next Cholesky-QR repairs it); the pass before an accepted result
+      // must have ratio >= 0.05
+      if (ratio > 2e-5) break;
     }
     return true;
   };
