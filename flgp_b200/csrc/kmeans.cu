@@ -957,30 +957,183 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
 __device__ __forceinline__ float2 km_pack(double u, double l) {  // u rounded up, l rounded down
   return make_float2(__double2float_ru(u), __double2float_rd(l));
 }
-struct __align__(16) KmWork {
-  int p, a;  // position in the sorted layout, current centre
-  double l;  // lower bound after this pass's centre moves
-};
+// ---- one kernel per pruned pass -----------------------------------------------------------------------------------
+// Hamerly-style bounds are carried from pass to pass: u >= |x - c_a| and l <= |x - c_j| for every j != a, stored as
+// floats rounded outwards (u up, l down; the update below is single-precision arithmetic with directed rounding, so
+// every step errs on the safe side).  The centres have moved since the bounds were taken: c_a by move[a]; the centres
+// of a's current neighbour list by at most nbmove[a]; a centre outside the list is at least lthr[a] from c_a, hence
+// lthr[a] - u from x.  If u + eta <= l still holds, every other centre is farther than c_a by eta, its COMPUTED score
+// is strictly larger (eta^2 > 2 Delta) and the point keeps its centre - without its coordinates being read.
+// cl[a] = {move, nbmove, lthr, -}.
+//
+// One CTA takes a tile of KF_TILE consecutive (cluster-sorted) points through all of it, with the tile's bounds and
+// centre numbers staged in shared memory:
+//   1. every point: the moved bounds and the test; the points that fail are compacted into `sv`;
+//   2. the survivors, densely over the threads: u from one exact score against the point's own centre (one 32-byte
+//      sector per point); what still fails is compacted into `wk`;
+//   3. the walkers, densely again: the neighbour list of the point's centre (sorted by centre-centre distance) up to
+//      the point's own 2 ub + eta; new bounds; a reassignment is an exact -x / +x on the persistent integer sums;
+//   4. the tile's bounds are written back once, coalesced.
+// The earlier form (a bound-test kernel that wrote 16-byte work records, and a grid-stride evaluation kernel over
+// them) moved 557 MB per pass at C4 and walked the lists with 6 of 32 lanes; this one moves ~350 MB, never updates a
+// single 8-byte pair inside a 32-byte sector, and starts every walk with full warps.  Same arithmetic per point.
+__device__ __forceinline__ double4 km_ld_stream(const double4* p) {  // evict-first: the record is used once
+  const double2 lo = __ldcs(reinterpret_cast<const double2*>(p)), hi = __ldcs(reinterpret_cast<const double2*>(p) + 1);
+  return make_double4(lo.x, lo.y, hi.x, hi.y);
+}
+constexpr int KF_T = 256, KF_Q = 8, KF_TILE = KF_T * KF_Q, KF_R = 2;
 
-// Evaluation of the points on the work list, one thread per point: walks the neighbour list of the point's centre
-// (sorted by centre-centre distance) up to the point's own 2 ub + eta and leaves new bounds behind.  Sums are integer
-// limbs, so a reassignment is an exact -x / +x on the persistent accumulators.
 template <int D>
-__global__ void __launch_bounds__(256)
-kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__ rec, int s, Fx fx,
-                     int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
-                     const double* __restrict__ list_cc, const int32_t* __restrict__ len, double M, double delta2,
-                     double eta, unsigned long long* __restrict__ Rcur, const KmWork* __restrict__ work,
-                     const int* __restrict__ nwork, const double* __restrict__ lthr, float2* __restrict__ UL,
-                     unsigned long long* __restrict__ nfull) {
+__global__ void __launch_bounds__(KF_T, 4)
+kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __restrict__ rec, int s, Fx fx,
+                  int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
+                  const double* __restrict__ list_cc, const int32_t* __restrict__ len,
+                  const double* __restrict__ lthr, const float4* __restrict__ cl, double M, double delta2, double eta,
+                  float eta_up, unsigned long long* __restrict__ Rcur, float2* __restrict__ UL,
+                  unsigned long long* __restrict__ zero_maxmove, unsigned long long* __restrict__ prof,
+                  int* __restrict__ prof_surv) {
   constexpr int STR = (D + 2) / 2 * 2;
+  __shared__ __align__(16) float2 ul_t[KF_TILE];
+  __shared__ __align__(16) int as_t[KF_TILE];
+  __shared__ unsigned short sv[KF_TILE], wk[KF_TILE];
+  __shared__ int nsv_s, nwk_s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t c0 = (int64_t)blockIdx.x * KF_TILE;
+  if (tid == 0) {
+    nsv_s = 0;
+    nwk_s = 0;
+  }
+  if (blockIdx.x == 0 && tid == 1 && zero_maxmove) *zero_maxmove = 0;  // read by the lists kernel before, written by the update after
+  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
+  if (prof && tid == 0) tk0 = clock64();
+  __syncthreads();
+  // ---- 1. bound test, four consecutive points per thread and group (16-byte loads; `as` and `UL` are padded to a
+  // whole tile).  The survivors of a warp are placed with one prefix sum and one shared-memory atomic.
+  {
+    constexpr int NG = KF_Q / 4;
+    int4 a4[NG];
+    float4 u4[NG][2];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {  // everything is requested before the first value is looked at
+      const int64_t p = c0 + g * (KF_T * 4) + tid * 4;
+      a4[g] = __ldcs(reinterpret_cast<const int4*>(as + p));
+      u4[g][0] = __ldcs(reinterpret_cast<const float4*>(UL + p));
+      u4[g][1] = __ldcs(reinterpret_cast<const float4*>(UL + p) + 1);
+    }
+    unsigned fail = 0;  // bit 4 g + k: point k of group g needs its coordinates
+    int nvalid = 0;
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int i0 = g * (KF_T * 4) + tid * 4;
+      const int64_t left = n - (c0 + i0);  // points of this group inside the array
+      int av[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
+      const float uu[4] = {u4[g][0].x, u4[g][0].z, u4[g][1].x, u4[g][1].z};
+      const float ll[4] = {u4[g][0].y, u4[g][0].w, u4[g][1].y, u4[g][1].w};
+      float nu[4], nl[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const bool valid = k < left;
+        if (!valid) av[k] = 0;
+        const float4 ca = cl[av[k]];  // {move of c_a (rounded up), largest move in a's list (up), list radius (down)}
+        nu[k] = __fadd_ru(uu[k], ca.x);
+        nl[k] = fminf(__fsub_rd(ll[k], ca.y), __fsub_rd(ca.z, nu[k]));
+        if (valid) {
+          ++nvalid;
+          if (!(__fadd_ru(nu[k], eta_up) <= nl[k])) fail |= 1u << (4 * g + k);
+        }
+      }
+      *reinterpret_cast<float4*>(&ul_t[i0]) = make_float4(nu[0], nl[0], nu[1], nl[1]);
+      *reinterpret_cast<float4*>(&ul_t[i0 + 2]) = make_float4(nu[2], nl[2], nu[3], nl[3]);
+      *reinterpret_cast<int4*>(&as_t[i0]) = make_int4(av[0], av[1], av[2], av[3]);
+    }
+    const int mine = __popc(fail);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    int base = 0;
+    if (lane == 31 && incl) base = atomicAdd(&nsv_s, incl);
+    base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+#pragma unroll
+    for (int g = 0; g < NG; ++g)
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (fail & (1u << (4 * g + k))) sv[base++] = (unsigned short)(g * (KF_T * 4) + tid * 4 + k);
+    if (prof) {
+      int skipped = nvalid - mine;
+      for (int o = 16; o; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
+      if (lane == 0 && skipped) atomicAdd(prof, (unsigned long long)skipped);
+    }
+  }
+  __syncthreads();
+  if (prof && tid == 0) tk1 = clock64();
+  const int nsv = nsv_s;
+  if (prof_surv && tid == 0 && nsv) atomicAdd(prof_surv, nsv);
+  auto score = [&](const double (&x)[D], int j) {
+    const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
+    double cr[STR];
+#pragma unroll
+    for (int q = 0; q < STR / 2; ++q) {
+      double2 t = rj[q];
+      cr[2 * q] = t.x;
+      cr[2 * q + 1] = t.y;
+    }
+    double e = cr[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) e = fma(x[k], cr[k], e);
+    return e;
+  };
+  // ---- 2. tightening: u from one exact score against the point's own centre; KF_R survivors per thread and trip,
+  // their coordinates requested together
+  for (int t0 = 0; t0 < nsv; t0 += KF_T * KF_R) {
+    double4 xv[KF_R];
+    int ii[KF_R];
+#pragma unroll
+    for (int r = 0; r < KF_R; ++r) {
+      const int t = t0 + r * KF_T + tid;
+      ii[r] = (t < nsv) ? (int)sv[t] : -1;
+      if (ii[r] >= 0) xv[r] = km_ld_stream(Xs4 + c0 + ii[r]);  // one 32-byte sector per point, streamed past the L1
+    }
+#pragma unroll
+    for (int r = 0; r < KF_R; ++r) {
+      bool walk = false;
+      const int i = ii[r];
+      if (i >= 0) {
+        const double xa[4] = {xv[r].x, xv[r].y, xv[r].z, xv[r].w};
+        double x[D], xn = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          x[k] = xa[k];
+          xn = fma(x[k], x[k], xn);
+        }
+        const double ub0 = km_ub_fast(score(x, as_t[i]), M, xn, delta2);
+        const double l = (double)ul_t[i].y;
+        if (ub0 + eta <= l) ul_t[i] = km_pack(ub0, l);  // nothing can beat or tie centre a
+        else walk = true;
+      }
+      const unsigned mw = __ballot_sync(0xffffffffu, walk);
+      if (mw) {
+        const int lead = __ffs(mw) - 1;
+        int base = 0;
+        if (lane == lead) base = atomicAdd(&nwk_s, __popc(mw));
+        base = __shfl_sync(0xffffffffu, base, lead);
+        if (walk) wk[base + __popc(mw & ((1u << lane) - 1))] = (unsigned short)i;
+      }
+    }
+  }
+  __syncthreads();
+  if (prof && tid == 0) tk2 = clock64();
+  // ---- 3. the neighbour-list walk of what is left.  The list entries are requested ahead of their use (indices two
+  // entries ahead, score records one ahead), so that an entry costs one load latency instead of three in a row.
+  const int nwk = nwk_s;
   int changed = 0;
-  const int total = *nwork;
-  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-    const KmWork wr = work[idx];  // coalesced 16-byte records: position, centre, moved lower bound
-    const int64_t p = wr.p;
-    const int a = wr.a;
-    const double4 xv = Xs4[p];  // one 32-byte sector per point
+  for (int t = tid; t < nwk; t += KF_T) {
+    const int i = wk[t];
+    const int64_t p = c0 + i;
+    const int a = as_t[i];
+    const double4 xv = km_ld_stream(Xs4 + p);
     const double xa[4] = {xv.x, xv.y, xv.z, xv.w};
     double x[D], xn = 0.0;
 #pragma unroll
@@ -988,41 +1141,57 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
       x[k] = xa[k];
       xn = fma(x[k], x[k], xn);
     }
-    auto score = [&](int j) {
-      const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
-      double cr[STR];
-#pragma unroll
-      for (int q = 0; q < STR / 2; ++q) {
-        double2 t = rj[q];
-        cr[2 * q] = t.x;
-        cr[2 * q + 1] = t.y;
-      }
-      double e = cr[D];
-#pragma unroll
-      for (int k = 0; k < D; ++k) e = fma(x[k], cr[k], e);
-      return e;
-    };
-    double best = score(a), sec = INFINITY;  // sec: second smallest score seen
+    double best = score(x, a), sec = INFINITY;  // sec: second smallest score seen
     int bj = a;
     const double ub0 = km_ub_fast(best, M, xn, delta2);
-    if (ub0 + eta <= wr.l) {  // the tightened upper bound is enough: nothing can beat or tie centre a
-      UL[p] = km_pack(ub0, wr.l);
-      continue;
-    }
     const double thr = (2.0 * ub0 + eta) * (1.0 + 1e-9);
     const int L = len[a];
     double ccb = lthr[a];             // every centre that was NOT scanned is at least this far from centre a
-    bool full = (L < 0) || !(thr <= ccb);  // no list, or the bound reaches past the radius the list is complete to
+    const bool full = (L < 0) || !(thr <= ccb);  // no list, or the bound reaches past the radius the list is complete to
     if (!full) {
       const int32_t* lj = list_j + (size_t)a * KM_LMAX;
       const double* lc = list_cc + (size_t)a * KM_LMAX;
+      // entries past L are never used, but always inside the KM_LMAX-long row
+      double c1 = lc[0], c2 = lc[1];
+      int j1 = lj[0], j2 = lj[1];
+      double r1[STR];
+      {
+        const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)(L > 0 ? j1 : a) * STR);
+#pragma unroll
+        for (int k = 0; k < STR / 2; ++k) {
+          const double2 tt = rj[k];
+          r1[2 * k] = tt.x;
+          r1[2 * k + 1] = tt.y;
+        }
+      }
       for (int q = 0; q < L; ++q) {
-        if (lc[q] >= thr) {  // sorted by centre-centre distance: nothing further can win or tie
-          ccb = lc[q];
+        const double cq = c1;
+        const int j = j1;
+        double rq[STR];
+#pragma unroll
+        for (int k = 0; k < STR; ++k) rq[k] = r1[k];
+        c1 = c2;
+        j1 = j2;
+        if (q + 2 < L) {
+          c2 = lc[q + 2];
+          j2 = lj[q + 2];
+        }
+        if (cq >= thr) {  // sorted by centre-centre distance: nothing further can win or tie
+          ccb = cq;
           break;
         }
-        const int j = lj[q];
-        const double e = score(j);
+        if (q + 1 < L) {
+          const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j1 * STR);
+#pragma unroll
+          for (int k = 0; k < STR / 2; ++k) {
+            const double2 tt = rj[k];
+            r1[2 * k] = tt.x;
+            r1[2 * k + 1] = tt.y;
+          }
+        }
+        double e = rq[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) e = fma(x[k], rq[k], e);
         if (e < best || (e == best && j < bj)) {
           sec = best;
           best = e;
@@ -1032,11 +1201,11 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
         }
       }
     } else {  // scan every centre (list overflow; otherwise excluded by the slack in the list radius)
-      if (nfull) atomicAdd(nfull, 1ull);
+      if (prof) atomicAdd(prof + 1, 1ull);
       ccb = INFINITY;
       for (int j = 0; j < s; ++j) {
         if (j == a) continue;
-        const double e = score(j);
+        const double e = score(x, j);
         if (e < best || (e == best && j < bj)) {
           sec = best;
           best = e;
@@ -1048,7 +1217,7 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
     }
     // bounds for the passes that follow: u >= |x - c_bj|, l <= distance to every other centre
     const double ub = (bj == a) ? ub0 : km_ub_fast(best, M, xn, delta2);
-    UL[p] = km_pack(ub, fmin(km_lb_fast(sec, M, xn, delta2), (ccb - ub0) * (1.0 - 1e-14)));
+    ul_t[i] = km_pack(ub, fmin(km_lb_fast(sec, M, xn, delta2), (ccb - ub0) * (1.0 - 1e-14)));
     if (bj != a) {
       ++changed;
       as[p] = bj;
@@ -1067,84 +1236,20 @@ kmeans_assign_pruned(const double4* __restrict__ Xs4, const double* __restrict__
     km_radius(Rcur, bj, ub);  // radius of the (new) cluster for the next pass
   }
   if (changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
-}
-
-// Bound test, one streaming pass over the points (any order; the cluster-sorted order makes the per-cluster lookups
-// and the survivors' list walks coherent).  Hamerly-style bounds carried from pass to pass: u >= |x - c_a| and
-// l <= |x - c_j| for every j != a.  The centres have moved since they were taken: c_a by move[a]; the centres of a's
-// current neighbour list by at most nbmove[a]; a centre outside the list is at least lthr[a] from c_a, hence
-// lthr[a] - u from x.  If u + eta <= l still holds, every other centre is farther than c_a by eta, its COMPUTED
-// score is strictly larger (eta^2 > 2 Delta) and the point keeps its centre - without its coordinates being read.
-// The points that fail are compacted (per CTA in shared memory, one global atomic per CTA) into the work list that
-// kmeans_assign_pruned evaluates.  cl[a] = {move, nbmove, lthr, -}.
-constexpr int KM_BT = 256, KM_BQ = 4;  // threads per CTA, points per thread
-
-__global__ void __launch_bounds__(KM_BT)
-kmeans_bounds_kernel(int64_t n, const int32_t* __restrict__ as, const float4* __restrict__ cl, float eta_up,
-                     float2* __restrict__ UL, KmWork* __restrict__ work, int* __restrict__ nwork,
-                     unsigned long long* __restrict__ nskip, unsigned long long* __restrict__ zero_maxmove) {
-  __shared__ KmWork wl[KM_BT * KM_BQ];
-  __shared__ int wcount, wbase;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t c0 = (int64_t)blockIdx.x * (KM_BT * KM_BQ);
-  if (tid == 0) wcount = 0;
-  if (blockIdx.x == 0 && tid == 1 && zero_maxmove) *zero_maxmove = 0;  // read by the lists kernel before, written by the update after
   __syncthreads();
-  float2 ul_in[KM_BQ];
-  int as_in[KM_BQ];
-#pragma unroll
-  for (int q = 0; q < KM_BQ; ++q) {  // everything is requested before the first value is looked at
-    const int64_t p = c0 + q * KM_BT + tid;
-    const bool valid = p < n;
-    as_in[q] = valid ? as[p] : 0;
-    ul_in[q] = valid ? UL[p] : make_float2(0.f, 0.f);
+  if (prof && tid == 0) {
+    tk3 = clock64();
+    atomicAdd(prof + 2, (unsigned long long)(tk1 - tk0));
+    atomicAdd(prof + 3, (unsigned long long)(tk2 - tk1));
+    atomicAdd(prof + 4, (unsigned long long)(tk3 - tk2));
+    atomicAdd(prof + 5, (unsigned long long)nwk);
   }
-  int skipped = 0;
+  // ---- 4. the tile's bounds, written once
 #pragma unroll
-  for (int q = 0; q < KM_BQ; ++q) {  // uniform trip count: the ballot sees whole warps
-    const int64_t p = c0 + q * KM_BT + tid;
-    const bool valid = p < n;
-    bool need = false;
-    double l = 0.0;
-    if (valid) {
-      const float4 ca = cl[as_in[q]];  // {move of c_a (rounded up), largest move in a's list (up), list radius (down)}
-      // stored bounds are floats rounded outwards (u up, l down): half the traffic of a double pair; the update is
-      // single-precision arithmetic with directed rounding (every step errs on the safe side) and the decision is
-      // taken on the values as they will be stored
-      float2 nb;
-      nb.x = __fadd_ru(ul_in[q].x, ca.x);
-      nb.y = fminf(__fsub_rd(ul_in[q].y, ca.y), __fsub_rd(ca.z, nb.x));
-      l = (double)nb.y;
-      if (__fadd_ru(nb.x, eta_up) <= nb.y) {
-        UL[p] = nb;
-        ++skipped;
-      } else {
-        need = true;  // the evaluation receives the moved lower bound in its work record and rewrites UL[p]
-      }
-    }
-    const unsigned mw = __ballot_sync(0xffffffffu, need);
-    if (mw) {
-      const int lead = __ffs(mw) - 1;
-      int base = 0;
-      if (lane == lead) base = atomicAdd(&wcount, __popc(mw));
-      base = __shfl_sync(0xffffffffu, base, lead);
-      if (need) {
-        KmWork wr;
-        wr.p = (int)p;
-        wr.a = as_in[q];
-        wr.l = l;
-        wl[base + __popc(mw & ((1u << lane) - 1))] = wr;
-      }
-    }
-  }
-  __syncthreads();
-  const int nw = wcount;
-  if (tid == 0 && nw) wbase = atomicAdd(nwork, nw);
-  __syncthreads();
-  for (int w = tid; w < nw; w += KM_BT) work[wbase + w] = wl[w];
-  if (nskip) {
-    for (int o = 16; o; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
-    if (lane == 0 && skipped) atomicAdd(nskip, (unsigned long long)skipped);
+  for (int q = 0; q < KF_Q / 2; ++q) {
+    const int i = (q * KF_T + tid) * 2;
+    if (c0 + i + 1 < n) *reinterpret_cast<float4*>(UL + c0 + i) = *reinterpret_cast<const float4*>(&ul_t[i]);
+    else if (c0 + i < n) UL[c0 + i] = ul_t[i];
   }
 }
 
@@ -1378,7 +1483,6 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   DevBuf<double> ncc, move, lthr;
   DevBuf<double4> Xs4[2];
   DevBuf<float2> UL[2];
-  DevBuf<KmWork> work;
   DevBuf<double4> cl;
   DevBuf<float4> clf;
   const bool prof_skip = std::getenv("FLGP_KMEANS_PROF") != nullptr;
@@ -1397,18 +1501,17 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     cursor.alloc(s);
     seg_start.alloc(s + 1);
     nstrag.alloc(1);
-    work.alloc(std::max<int64_t>(n_local, 1));
     for (int b = 0; b < 2; ++b) {
       perm[b].alloc(std::max<int64_t>(n_local, 1));
-      as[b].alloc(std::max<int64_t>(n_local, 1));
+      as[b].alloc((int64_t)ceil_div(std::max<int64_t>(n_local, 1), KF_TILE) * KF_TILE);  // whole tiles: kmeans_pass_fused
       Xs4[b].alloc(std::max<int64_t>(n_local, 1));
-      UL[b].alloc(std::max<int64_t>(n_local, 1));
+      UL[b].alloc((int64_t)ceil_div(std::max<int64_t>(n_local, 1), KF_TILE) * KF_TILE);
     }
     lthr.alloc(s);
     cl.alloc(s);
     clf.alloc(s);
     maxmove.alloc(1);
-    nskip.alloc(2);
+    nskip.alloc(8);
     maxmove.zero(c->stream);
     nskip.zero(c->stream);
     Rbits[0].zero(c->stream);
@@ -1479,36 +1582,20 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
       unsigned long long* Rcur = Rbits[1 - rsel].p;
       FLGP_LAUNCH(c, kmeans_lists_kernel, s, 256, 0, C, s, d, Rprev, move.p, eta, nlist.p, ncc.p, nlen.p, lthr.p, cl.p,
                   maxmove.p, Rcur, clf.p, rec.p, str, Moff, acc.p + (words - 1), nstrag.p);
-      if (n_local == 0) maxmove.zero(c->stream);  // otherwise the bound-test kernel does it
+      if (n_local == 0) maxmove.zero(c->stream);  // otherwise kmeans_pass_fused does it
       if (n_local > 0) {
-        // a grid-stride kernel over a device-side item count: exactly one resident wave (a partial second wave
-        // would run with most SMs idle; ncu: 1.6 waves at the former sm_count * 8)
-        static int pruned_per_sm[5] = {0, 0, 0, 0, 0};
-        if (!pruned_per_sm[d]) {
-          int nb = 0;
-          switch (d) {
-            case 1: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<1>, 256, 0)); break;
-            case 2: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<2>, 256, 0)); break;
-            case 3: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<3>, 256, 0)); break;
-            default: FLGP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kmeans_assign_pruned<4>, 256, 0)); break;
-          }
-          pruned_per_sm[d] = std::max(nb, 1);
-        }
-        const int sgrid = c->sm_count * pruned_per_sm[d];
-        FLGP_LAUNCH(c, kmeans_bounds_kernel, ceil_div(n_local, KM_BT * KM_BQ), KM_BT, 0, n_local, as[cur].p, clf.p,
-                    std::nextafterf((float)eta, INFINITY),  // eta rounded up
-                    UL[cur].p, work.p, nstrag.p, prof_skip ? nskip.p : nullptr, maxmove.p);
-#define FLGP_PRUNED(D_)                                                                                          \
-  FLGP_LAUNCH(c, (kmeans_assign_pruned<D_>), sgrid, 256, 0, Xs4[cur].p, rec.p, s, fx, as[cur].p, uacc,            \
-              nlist.p, ncc.p, nlen.p, Moff, delta2, eta, Rcur, work.p, nstrag.p, lthr.p, UL[cur].p,               \
-              prof_skip ? nskip.p + 1 : nullptr)
+#define FLGP_FUSED(D_)                                                                                            \
+  FLGP_LAUNCH(c, (kmeans_pass_fused<D_>), ceil_div(n_local, KF_TILE), KF_T, 0, n_local, Xs4[cur].p, rec.p, s, fx,  \
+              as[cur].p, uacc, nlist.p, ncc.p, nlen.p, lthr.p, clf.p, Moff, delta2, eta,                           \
+              std::nextafterf((float)eta, INFINITY), Rcur, UL[cur].p, maxmove.p, prof_skip ? nskip.p : nullptr,    \
+              prof_skip ? nstrag.p : nullptr)
         switch (d) {
-          case 1: FLGP_PRUNED(1); break;
-          case 2: FLGP_PRUNED(2); break;
-          case 3: FLGP_PRUNED(3); break;
-          default: FLGP_PRUNED(4); break;
+          case 1: FLGP_FUSED(1); break;
+          case 2: FLGP_FUSED(2); break;
+          case 3: FLGP_FUSED(3); break;
+          default: FLGP_FUSED(4); break;
         }
-#undef FLGP_PRUNED
+#undef FLGP_FUSED
       }
       if (prof_skip && it < 128)
         FLGP_CUDA(cudaMemcpyAsync(prof_hist.p + it, nstrag.p, sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
@@ -1614,7 +1701,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     } else {
       comm_allreduce_i64(c, reinterpret_cast<int64_t*>(red), words);
     }
-    if (pruned && brute) maxmove.zero(c->stream);  // a pruned pass zeroes it in its bound-test kernel
+    if (pruned && brute) maxmove.zero(c->stream);  // a pruned pass zeroes it in kmeans_pass_fused
     if (small) {
       FLGP_LAUNCH(c, kmeans_update_kernel, ceil_div(s, 128), 128, 0, red, s, d, fx, C, sizes, pruned ? move.p : nullptr,
                   pruned ? maxmove.p : nullptr, it, kstate.p);
@@ -1650,11 +1737,14 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   if (have_sorted && n_local > 0)
     FLGP_LAUNCH(c, kmeans_unpermute_kernel, ceil_div(n_local, 256), 256, 0, as[cur].p, perm[cur].p, n_local, assign);
   if (pruned && std::getenv("FLGP_KMEANS_PROF")) {
-    unsigned long long h[2] = {0, 0};
-    nskip.download(h, 2, c->stream);
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    nskip.download(h, 8, c->stream);
     sync(c);
     fprintf(stderr, "[flgp kmeans prof] %d passes, %.1f%% of the point-passes after the first skipped by their bounds, "
             "%llu full scans\n", it, it > 1 ? 100.0 * (double)h[0] / ((double)n_local * (it - 1)) : 0.0, h[1]);
+    fprintf(stderr, "[flgp kmeans prof] fused pass, clocks per tile: bound test %.0f, tightening %.0f, walk %.0f; walkers %.1f%% of the point-passes\n",
+            (double)h[2] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)), (double)h[3] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)),
+            (double)h[4] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)), 100.0 * (double)h[5] / ((double)n_local * (it - 1)));
     int hist[128];
     prof_hist.download(hist, 128, c->stream);
     sync(c);
