@@ -848,10 +848,6 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
     if (zero_changed) *zero_changed = 0;
     if (zero_count) *zero_count = 0;
   }
-  for (int t = tid; t < KM_LMAX; t += 256) {
-    kcc[t] = INFINITY;
-    kj[t] = 0x7fffffff;
-  }
   __syncthreads();
   const double Ra = __longlong_as_double((long long)Rprev[a]) + move[a];
   // A member's freshly computed bound ub0 can exceed the carried radius by the rounding slack of a score
@@ -863,6 +859,7 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
     // members that keep centre a are within Ra of it (their bound grew by move[a]); evaluated points add theirs
     Rcur[a] = (unsigned long long)__double_as_longlong(Ra * (1.0 + 1e-15));
   }
+  const double thr2 = thr * thr * (1.0 + 1e-15);  // sqrt(cc2) < thr implies cc2 < thr2: the root only where it can matter
   for (int j = tid; j < s; j += 256) {
     if (j == a) continue;
     double cc = 0.0;
@@ -870,6 +867,7 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
       const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
       cc = fma(df, df, cc);
     }
+    if (!(cc < thr2)) continue;
     cc = sqrt(cc);
     if (cc < thr) {
       const int pos = atomicAdd(&count, 1);
@@ -915,6 +913,11 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
   // bitonic sort of (cc, j) ascending; padding is (+inf, INT_MAX)
   int npow = 1;
   while (npow < cnt) npow <<= 1;
+  for (int t = cnt + tid; t < npow; t += 256) {
+    kcc[t] = INFINITY;
+    kj[t] = 0x7fffffff;
+  }
+  __syncthreads();
   for (int k2 = 2; k2 <= npow; k2 <<= 1)
     for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
       for (int t = tid; t < npow; t += 256) {
@@ -981,7 +984,7 @@ __device__ __forceinline__ double4 km_ld_stream(const double4* p) {  // evict-fi
   const double2 lo = __ldcs(reinterpret_cast<const double2*>(p)), hi = __ldcs(reinterpret_cast<const double2*>(p) + 1);
   return make_double4(lo.x, lo.y, hi.x, hi.y);
 }
-constexpr int KF_T = 256, KF_Q = 8, KF_TILE = KF_T * KF_Q, KF_R = 2;
+constexpr int KF_T = 256, KF_Q = 8, KF_TILE = KF_T * KF_Q, KF_WT = 32 * KF_Q, KF_R = 2;
 
 template <int D>
 __global__ void __launch_bounds__(KF_T, 4)
@@ -993,29 +996,29 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
                   unsigned long long* __restrict__ zero_maxmove, unsigned long long* __restrict__ prof,
                   int* __restrict__ prof_surv) {
   constexpr int STR = (D + 2) / 2 * 2;
-  __shared__ __align__(16) float2 ul_t[KF_TILE];
-  __shared__ __align__(16) int as_t[KF_TILE];
-  __shared__ unsigned short sv[KF_TILE], wk[KF_TILE];
-  __shared__ int nsv_s, nwk_s;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int64_t c0 = (int64_t)blockIdx.x * KF_TILE;
-  if (tid == 0) {
-    nsv_s = 0;
-    nwk_s = 0;
-  }
+  __shared__ __align__(16) float2 ul_s[KF_TILE];
+  __shared__ __align__(16) int as_s[KF_TILE];
+  __shared__ unsigned char sv_s[KF_TILE], wk_s[KF_TILE];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (blockIdx.x == 0 && tid == 1 && zero_maxmove) *zero_maxmove = 0;  // read by the lists kernel before, written by the update after
-  long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0;
-  if (prof && tid == 0) tk0 = clock64();
-  __syncthreads();
-  // ---- 1. bound test, four consecutive points per thread and group (16-byte loads; `as` and `UL` are padded to a
-  // whole tile).  The survivors of a warp are placed with one prefix sum and one shared-memory atomic.
+  // every warp owns KF_WT consecutive points and its slice of the staging arrays: no CTA-wide barrier anywhere
+  const int64_t c0 = (int64_t)blockIdx.x * KF_TILE + wid * KF_WT;
+  if (c0 >= n) return;
+  float2* ul_t = ul_s + wid * KF_WT;
+  int* as_t = as_s + wid * KF_WT;
+  unsigned char* sv = sv_s + wid * KF_WT;
+  unsigned char* wk = wk_s + wid * KF_WT;
+  const unsigned lt_mask = (1u << lane) - 1;
+  // ---- 1. bound test, four consecutive points per lane and group (16-byte loads; `as` and `UL` are padded to a
+  // whole tile).  The survivors are placed with one prefix sum over the warp.
+  int nsv;
   {
     constexpr int NG = KF_Q / 4;
     int4 a4[NG];
     float4 u4[NG][2];
 #pragma unroll
     for (int g = 0; g < NG; ++g) {  // everything is requested before the first value is looked at
-      const int64_t p = c0 + g * (KF_T * 4) + tid * 4;
+      const int64_t p = c0 + g * 128 + lane * 4;
       a4[g] = __ldcs(reinterpret_cast<const int4*>(as + p));
       u4[g][0] = __ldcs(reinterpret_cast<const float4*>(UL + p));
       u4[g][1] = __ldcs(reinterpret_cast<const float4*>(UL + p) + 1);
@@ -1024,7 +1027,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     int nvalid = 0;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
-      const int i0 = g * (KF_T * 4) + tid * 4;
+      const int i0 = g * 128 + lane * 4;
       const int64_t left = n - (c0 + i0);  // points of this group inside the array
       int av[4] = {a4[g].x, a4[g].y, a4[g].z, a4[g].w};
       const float uu[4] = {u4[g][0].x, u4[g][0].z, u4[g][1].x, u4[g][1].z};
@@ -1053,24 +1056,21 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
       const int v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    int base = 0;
-    if (lane == 31 && incl) base = atomicAdd(&nsv_s, incl);
-    base = __shfl_sync(0xffffffffu, base, 31) + incl - mine;
+    nsv = __shfl_sync(0xffffffffu, incl, 31);
+    int base = incl - mine;
 #pragma unroll
     for (int g = 0; g < NG; ++g)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (fail & (1u << (4 * g + k))) sv[base++] = (unsigned short)(g * (KF_T * 4) + tid * 4 + k);
+        if (fail & (1u << (4 * g + k))) sv[base++] = (unsigned char)(g * 128 + lane * 4 + k);
     if (prof) {
       int skipped = nvalid - mine;
       for (int o = 16; o; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
       if (lane == 0 && skipped) atomicAdd(prof, (unsigned long long)skipped);
+      if (lane == 0 && nsv) atomicAdd(prof_surv, nsv);
     }
   }
-  __syncthreads();
-  if (prof && tid == 0) tk1 = clock64();
-  const int nsv = nsv_s;
-  if (prof_surv && tid == 0 && nsv) atomicAdd(prof_surv, nsv);
+  __syncwarp();
   auto score = [&](const double (&x)[D], int j) {
     const double2* rj = reinterpret_cast<const double2*>(rec + (size_t)j * STR);
     double cr[STR];
@@ -1085,14 +1085,15 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     for (int k = 0; k < D; ++k) e = fma(x[k], cr[k], e);
     return e;
   };
-  // ---- 2. tightening: u from one exact score against the point's own centre; KF_R survivors per thread and trip,
+  // ---- 2. tightening: u from one exact score against the point's own centre; KF_R survivors per lane and trip,
   // their coordinates requested together
-  for (int t0 = 0; t0 < nsv; t0 += KF_T * KF_R) {
+  int nwk = 0;
+  for (int t0 = 0; t0 < nsv; t0 += 32 * KF_R) {
     double4 xv[KF_R];
     int ii[KF_R];
 #pragma unroll
     for (int r = 0; r < KF_R; ++r) {
-      const int t = t0 + r * KF_T + tid;
+      const int t = t0 + r * 32 + lane;
       ii[r] = (t < nsv) ? (int)sv[t] : -1;
       if (ii[r] >= 0) xv[r] = km_ld_stream(Xs4 + c0 + ii[r]);  // one 32-byte sector per point, streamed past the L1
     }
@@ -1114,22 +1115,16 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
         else walk = true;
       }
       const unsigned mw = __ballot_sync(0xffffffffu, walk);
-      if (mw) {
-        const int lead = __ffs(mw) - 1;
-        int base = 0;
-        if (lane == lead) base = atomicAdd(&nwk_s, __popc(mw));
-        base = __shfl_sync(0xffffffffu, base, lead);
-        if (walk) wk[base + __popc(mw & ((1u << lane) - 1))] = (unsigned short)i;
-      }
+      if (walk) wk[nwk + __popc(mw & lt_mask)] = (unsigned char)i;
+      nwk += __popc(mw);
     }
   }
-  __syncthreads();
-  if (prof && tid == 0) tk2 = clock64();
+  if (prof && lane == 0 && nwk) atomicAdd(prof + 5, (unsigned long long)nwk);
+  __syncwarp();
   // ---- 3. the neighbour-list walk of what is left.  The list entries are requested ahead of their use (indices two
   // entries ahead, score records one ahead), so that an entry costs one load latency instead of three in a row.
-  const int nwk = nwk_s;
   int changed = 0;
-  for (int t = tid; t < nwk; t += KF_T) {
+  for (int t = lane; t < nwk; t += 32) {
     const int i = wk[t];
     const int64_t p = c0 + i;
     const int a = as_t[i];
@@ -1235,36 +1230,43 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     }
     km_radius(Rcur, bj, ub);  // radius of the (new) cluster for the next pass
   }
-  if (changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
-  __syncthreads();
-  if (prof && tid == 0) {
-    tk3 = clock64();
-    atomicAdd(prof + 2, (unsigned long long)(tk1 - tk0));
-    atomicAdd(prof + 3, (unsigned long long)(tk2 - tk1));
-    atomicAdd(prof + 4, (unsigned long long)(tk3 - tk2));
-    atomicAdd(prof + 5, (unsigned long long)nwk);
-  }
-  // ---- 4. the tile's bounds, written once
+  __syncwarp();
+  for (int o = 16; o; o >>= 1) changed += __shfl_xor_sync(0xffffffffu, changed, o);
+  if (lane == 0 && changed) atomicAdd(&acc[(size_t)2 * s * D + s], (unsigned long long)changed);
+  // ---- 4. the warp's bounds, written once
 #pragma unroll
   for (int q = 0; q < KF_Q / 2; ++q) {
-    const int i = (q * KF_T + tid) * 2;
+    const int i = (q * 32 + lane) * 2;
     if (c0 + i + 1 < n) *reinterpret_cast<float4*>(UL + c0 + i) = *reinterpret_cast<const float4*>(&ul_t[i]);
     else if (c0 + i < n) UL[c0 + i] = ul_t[i];
   }
 }
 
 // ---- cluster-sorted layout: counting sort by assignment -------------------------------------------------
-__global__ void kmeans_offsets_kernel(const long long* __restrict__ cnt, int s, int* __restrict__ cursor,
-                                      int* __restrict__ seg_start) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {  // s is a few thousand: a serial scan is a few microseconds
-    int run = 0;
-    for (int j = 0; j < s; ++j) {
-      cursor[j] = run;
-      seg_start[j] = run;
-      run += (int)cnt[j];
-    }
-    seg_start[s] = run;
+__global__ void __launch_bounds__(1024)
+kmeans_offsets_kernel(const long long* __restrict__ cnt, int s, int* __restrict__ cursor, int* __restrict__ seg_start) {
+  // exclusive prefix sum of the cluster sizes by ONE CTA: every thread sums a contiguous run, the run totals are
+  // scanned through shared memory (a serial scan by one thread took 70 us at s = 2000, per re-sort)
+  __shared__ int part[1024];
+  const int tid = threadIdx.x, per = (s + 1023) / 1024;
+  const int j0 = tid * per, j1 = min(s, j0 + per);
+  int sum = 0;
+  for (int j = j0; j < j1; ++j) sum += (int)cnt[j];
+  part[tid] = sum;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {
+    const int v = (tid >= o) ? part[tid - o] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
   }
+  int run = part[tid] - sum;
+  for (int j = j0; j < j1; ++j) {
+    cursor[j] = run;
+    seg_start[j] = run;
+    run += (int)cnt[j];
+  }
+  if (tid == 1023) seg_start[s] = part[1023];
 }
 
 // src_perm == nullptr: source is the original order (row i <-> index i)
@@ -1540,7 +1542,7 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
   auto resort = [&]() {
     // counting sort by cluster of the current assignment (local counts live in acc)
     StageScope st(c, "kmeans_sort");
-    FLGP_LAUNCH(c, kmeans_offsets_kernel, 1, 32, 0, acc.p + (size_t)2 * s * d, s, cursor.p, seg_start.p);
+    FLGP_LAUNCH(c, kmeans_offsets_kernel, 1, 1024, 0, acc.p + (size_t)2 * s * d, s, cursor.p, seg_start.p);
     const int nxt = have_sorted ? 1 - cur : 0;
     if (n_local > 0) {
       if (have_sorted) FLGP_CUDA(cudaMemsetAsync(Rbits[rsel].p, 0, sizeof(unsigned long long) * s, c->stream));
@@ -1742,9 +1744,8 @@ void kmeans_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, in
     sync(c);
     fprintf(stderr, "[flgp kmeans prof] %d passes, %.1f%% of the point-passes after the first skipped by their bounds, "
             "%llu full scans\n", it, it > 1 ? 100.0 * (double)h[0] / ((double)n_local * (it - 1)) : 0.0, h[1]);
-    fprintf(stderr, "[flgp kmeans prof] fused pass, clocks per tile: bound test %.0f, tightening %.0f, walk %.0f; walkers %.1f%% of the point-passes\n",
-            (double)h[2] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)), (double)h[3] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)),
-            (double)h[4] / ((double)(it - 1) * ceil_div(n_local, KF_TILE)), 100.0 * (double)h[5] / ((double)n_local * (it - 1)));
+    fprintf(stderr, "[flgp kmeans prof] neighbour lists walked for %.1f%% of the point-passes\n",
+            100.0 * (double)h[5] / ((double)std::max<int64_t>(n_local, 1) * std::max(it - 1, 1)));
     int hist[128];
     prof_hist.download(hist, 128, c->stream);
     sync(c);
