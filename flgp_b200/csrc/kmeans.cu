@@ -860,12 +860,24 @@ kmeans_lists_kernel(const double* __restrict__ C, int s, int d, const unsigned l
     Rcur[a] = (unsigned long long)__double_as_longlong(Ra * (1.0 + 1e-15));
   }
   const double thr2 = thr * thr * (1.0 + 1e-15);  // sqrt(cc2) < thr implies cc2 < thr2: the root only where it can matter
+  double ca4[4] = {0.0, 0.0, 0.0, 0.0};  // d <= 4: the centre's own coordinates stay in registers
+  if (d <= 4)
+    for (int k = 0; k < d; ++k) ca4[k] = C[a + (size_t)s * k];
   for (int j = tid; j < s; j += 256) {
     if (j == a) continue;
     double cc = 0.0;
-    for (int k = 0; k < d; ++k) {
-      const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
-      cc = fma(df, df, cc);
+    if (d <= 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (k < d) {
+          const double df = ca4[k] - C[j + s * k];
+          cc = fma(df, df, cc);
+        }
+    } else {
+      for (int k = 0; k < d; ++k) {
+        const double df = C[a + (size_t)s * k] - C[j + (size_t)s * k];
+        cc = fma(df, df, cc);
+      }
     }
     if (!(cc < thr2)) continue;
     cc = sqrt(cc);
@@ -980,14 +992,12 @@ __device__ __forceinline__ float2 km_pack(double u, double l) {  // u rounded up
 // The earlier form (a bound-test kernel that wrote 16-byte work records, and a grid-stride evaluation kernel over
 // them) moved 557 MB per pass at C4 and walked the lists with 6 of 32 lanes; this one moves ~350 MB, never updates a
 // single 8-byte pair inside a 32-byte sector, and starts every walk with full warps.  Same arithmetic per point.
-__device__ __forceinline__ double4 km_ld_stream(const double4* p) {  // evict-first: the record is used once
-  const double2 lo = __ldcs(reinterpret_cast<const double2*>(p)), hi = __ldcs(reinterpret_cast<const double2*>(p) + 1);
-  return make_double4(lo.x, lo.y, hi.x, hi.y);
-}
-constexpr int KF_T = 256, KF_Q = 8, KF_TILE = KF_T * KF_Q, KF_WT = 32 * KF_Q, KF_R = 2;
+// measured at C4 (99 pruned passes): 128 threads x 8 points 13.9 ms, 256 x 8 14.2, 128 x 4 14.7, 256 x 4 15.1, 128 x 16 19.2
+constexpr int KF_T = 128, KF_Q = 8, KF_TILE = KF_T * KF_Q, KF_WT = 32 * KF_Q, KF_R = 2;
+typedef unsigned short kf_idx;  // index of a point inside its warp's tile
 
 template <int D>
-__global__ void __launch_bounds__(KF_T, 4)
+__global__ void __launch_bounds__(KF_T, 8)
 kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __restrict__ rec, int s, Fx fx,
                   int32_t* __restrict__ as, unsigned long long* __restrict__ acc, const int32_t* __restrict__ list_j,
                   const double* __restrict__ list_cc, const int32_t* __restrict__ len,
@@ -998,7 +1008,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
   constexpr int STR = (D + 2) / 2 * 2;
   __shared__ __align__(16) float2 ul_s[KF_TILE];
   __shared__ __align__(16) int as_s[KF_TILE];
-  __shared__ unsigned char sv_s[KF_TILE], wk_s[KF_TILE];
+  __shared__ kf_idx sv_s[KF_TILE], wk_s[KF_TILE];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (blockIdx.x == 0 && tid == 1 && zero_maxmove) *zero_maxmove = 0;  // read by the lists kernel before, written by the update after
   // every warp owns KF_WT consecutive points and its slice of the staging arrays: no CTA-wide barrier anywhere
@@ -1006,8 +1016,8 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
   if (c0 >= n) return;
   float2* ul_t = ul_s + wid * KF_WT;
   int* as_t = as_s + wid * KF_WT;
-  unsigned char* sv = sv_s + wid * KF_WT;
-  unsigned char* wk = wk_s + wid * KF_WT;
+  kf_idx* sv = sv_s + wid * KF_WT;
+  kf_idx* wk = wk_s + wid * KF_WT;
   const unsigned lt_mask = (1u << lane) - 1;
   // ---- 1. bound test, four consecutive points per lane and group (16-byte loads; `as` and `UL` are padded to a
   // whole tile).  The survivors are placed with one prefix sum over the warp.
@@ -1062,7 +1072,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     for (int g = 0; g < NG; ++g)
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (fail & (1u << (4 * g + k))) sv[base++] = (unsigned char)(g * 128 + lane * 4 + k);
+        if (fail & (1u << (4 * g + k))) sv[base++] = (kf_idx)(g * 128 + lane * 4 + k);
     if (prof) {
       int skipped = nvalid - mine;
       for (int o = 16; o; o >>= 1) skipped += __shfl_xor_sync(0xffffffffu, skipped, o);
@@ -1095,7 +1105,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     for (int r = 0; r < KF_R; ++r) {
       const int t = t0 + r * 32 + lane;
       ii[r] = (t < nsv) ? (int)sv[t] : -1;
-      if (ii[r] >= 0) xv[r] = km_ld_stream(Xs4 + c0 + ii[r]);  // one 32-byte sector per point, streamed past the L1
+      if (ii[r] >= 0) xv[r] = Xs4[c0 + ii[r]];  // one 32-byte sector per point (a walker reads it again: kept cacheable)
     }
 #pragma unroll
     for (int r = 0; r < KF_R; ++r) {
@@ -1115,7 +1125,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
         else walk = true;
       }
       const unsigned mw = __ballot_sync(0xffffffffu, walk);
-      if (walk) wk[nwk + __popc(mw & lt_mask)] = (unsigned char)i;
+      if (walk) wk[nwk + __popc(mw & lt_mask)] = (kf_idx)i;
       nwk += __popc(mw);
     }
   }
@@ -1128,7 +1138,7 @@ kmeans_pass_fused(int64_t n, const double4* __restrict__ Xs4, const double* __re
     const int i = wk[t];
     const int64_t p = c0 + i;
     const int a = as_t[i];
-    const double4 xv = km_ld_stream(Xs4 + p);
+    const double4 xv = Xs4[p];
     const double xa[4] = {xv.x, xv.y, xv.z, xv.w};
     double x[D], xn = 0.0;
 #pragma unroll
