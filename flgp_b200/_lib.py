@@ -111,6 +111,8 @@ def _declare(lib):
         "flgp_logit_objective": (C.c_int, [H, p_f64, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, C.c_double, p_f64]),
         "flgp_train_logit": (C.c_int, [H, p_f64, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, p_f64, p_f64,
                                        C.POINTER(C.c_int)]),
+        "flgp_train_logit_mult": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_char_p, C.c_int, C.POINTER(C.c_int),
+                                            p_f64, p_f64]),
         "flgp_cobyla_minimize_1d": (C.c_int, [OBJECTIVE_FN, p_void, C.c_double, C.c_double, p_f64, p_f64, C.c_double,
                                               C.c_int, C.POINTER(C.c_int)]),
         "flgp_fit_lae_logit": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, C.c_int, p_f64,

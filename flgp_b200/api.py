@@ -564,6 +564,47 @@ def train_lae_logit_gp(eigenpair: EigenPair, Y, m_total: int, K: int, sigma: flo
     return float(t[0]), obj.value, nev.value
 
 
+def train_logit_mult_gp(eigenpair: EigenPair, Y, m_total: int, K: int, sigma: float = 1e-3,
+                        approach: str = "posterior", max_classes: int = 256):
+    """train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53): labels 0 .. J-1, one binary training per class
+    against the rest.  Returns (t[J], obj[J])."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    t = np.zeros(max_classes)
+    obj = np.zeros(max_classes)
+    J = C.c_int()
+    check(eigenpair.ctx._lib.flgp_train_logit_mult(eigenpair._h, _pf(Y), m_total, K, sigma, _b(approach), max_classes,
+                                                   C.byref(J), _pf(t), _pf(obj)))
+    return t[:J.value].copy(), obj[:J.value].copy()
+
+
+def fit_lae_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-3, approach="posterior",
+                               models=None, nstart: int = 1, *, init_idx=None, seed: int = 0, iter_max: int = 100,
+                               ctx: Optional[Context] = None):
+    """fit_lae_logit_mult_gp_rcpp (R/Fit.R -> src/Fit.cpp:603-662; BASELINE config 3): spectrum, then J one-vs-rest
+    trainings of the diffusion time.  The reference's Y_pred is the arg-max of Polya-Gamma-sampled class probabilities
+    (R RNG, stochastic) and is not produced; the deterministic part is returned: the per-class (t_j, objective_j) and
+    the per-class Laplace posterior means of the latent function on the test rows, with their arg-max."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    X = np.asarray(X, dtype=np.float64)
+    X_new = np.asarray(X_new, dtype=np.float64)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, m_new = X.shape[0], X_new.shape[0]
+    if K < 0:
+        K = s
+    ep = heat_kernel_spectrum_cpp(X, X_new, s, r, K, models=models, nstart=nstart, init_idx=init_idx, seed=seed,
+                                  iter_max=iter_max, ctx=ctx)
+    try:
+        t, obj = train_logit_mult_gp(ep, Y, m, K, sigma, approach)
+        means = np.zeros((m_new, len(t)))
+        for j in range(len(t)):
+            mean, _ = posterior_distribution_classification(ep, (Y == j).astype(np.float64), m, K, float(t[j]), sigma)
+            means[:, j] = mean[m:]
+    finally:
+        ep.close()
+    return {"pars": t, "obj": obj, "posterior_mean": means, "argmax_posterior_mean": means.argmax(axis=1)}
+
+
 def fit_lae_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma: float = 1e-3, approach="posterior",
                           models=None, output_cov: bool = False, nstart: int = 1, *, t: Optional[float] = None,
                           init_idx=None, seed: int = 0, iter_max: int = 100, ctx: Optional[Context] = None):

@@ -9,6 +9,7 @@
 #include <limits>
 #include <memory>
 #include <string>
+#include <atomic>
 #include <thread>
 #include <unordered_set>
 
@@ -1659,6 +1660,50 @@ int flgp_train_logit(flgp_spectrum* h, const double* Y, const double* N, int64_t
     auto fn = [&](double t) { return logit_objective(T, t); };
     *t_io = cobyla_minimize_1d(fn, std::max(t0, 1e-3), 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nevals);
     if (obj) *obj = -fmin;  // ReturnValue(t, -obj), src/train.cpp:70
+  });
+}
+
+int flgp_train_logit_mult(flgp_spectrum* h, const double* Y, int64_t m_total, int K, double sigma,
+                          const char* approach, int J_cap, int* J_out, double* t_out, double* obj_out) {
+  return guard([&] {
+    need(h && Y && J_out && t_out, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    // multi_train_split (src/MultiClassification.cpp:14-27): J = max(Y) + 1, class j against the rest
+    double ymax = 0.0;
+    for (int64_t i = 0; i < m_total; ++i) {
+      need(Y[i] >= 0.0 && Y[i] == std::floor(Y[i]), "multi-class labels must be the integers 0 .. J-1");
+      ymax = std::max(ymax, Y[i]);
+    }
+    const int J = (int)ymax + 1;
+    *J_out = J;
+    need(J <= J_cap, "more classes than the output arrays hold");
+    std::vector<double> ones((size_t)m_total, 0.0);
+    LogitTrain base = logit_train_prepare(h, ones.data(), nullptr, m_total, K, sigma, post);  // V, ev: shared by all classes
+    // the J binary trainings (src/MultiClassification.cpp:41-50) are independent host-side Newton / COBYLA loops
+    std::vector<std::string> errs(J);
+    auto one = [&](int j) {
+      try {
+        LogitTrain T = base;
+        for (int64_t i = 0; i < m_total; ++i) T.Y[i] = (Y[i] == (double)j) ? 1.0 : 0.0;
+        double fmin = 0.0;
+        auto fn = [&](double t) { return logit_objective(T, t); };
+        t_out[j] = cobyla_minimize_1d(fn, 10.0, 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nullptr);
+        if (obj_out) obj_out[j] = -fmin;
+      } catch (const std::exception& e) {
+        errs[j] = e.what();
+      }
+    };
+    const int nthr = std::max(1u, std::min<unsigned>(J, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    std::atomic<int> next{0};
+    for (int q = 0; q < nthr; ++q)
+      pool.emplace_back([&] {
+        for (int j = next++; j < J; j = next++) one(j);
+      });
+    for (auto& th : pool) th.join();
+    for (int j = 0; j < J; ++j)
+      if (!errs[j].empty()) fail(3, "class %d: %s", j, errs[j].c_str());
   });
 }
 

@@ -314,6 +314,21 @@ Rcpp::List fit_lae_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector
   return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
 }
 
+// train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53) for fit_lae_logit_mult_gp_cpp (src/Fit.cpp:603-662): the J
+// one-vs-rest trainings run behind the C ABI on the spectrum handle; the MultiClassifier keeps the reference's layout
+// (aug_y + one ReturnValue(t, obj) per class), so predict_logit_mult_gp_cpp (Polya-Gamma sampler, R RNG) is unchanged.
+struct ReturnValue { double t, obj; };                                  // src/train.h
+Eigen::MatrixXd multi_train_split(const Eigen::VectorXd& Y);             // reference, src/MultiClassification.cpp:14-27
+std::vector<ReturnValue> train_logit_mult_on_handle(flgp_spectrum* h, const Eigen::VectorXd& Y, int K, double sigma,
+                                                    const std::string& approach) {
+  int J = 0;
+  std::vector<double> t(256), obj(256);
+  ok(flgp_train_logit_mult(h, Y.data(), Y.size(), K, sigma, approach.c_str(), 256, &J, t.data(), obj.data()));
+  std::vector<ReturnValue> res(J);
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  return res;
+}
+
 // [[Rcpp::export(posterior_distribution_classification)]]  -- signature unchanged (src/Utils.h:77-80)
 Rcpp::List posterior_distribution_classification(const Eigen::MatrixXd& C11, const Eigen::MatrixXd& C21,
                                                  const Eigen::VectorXd& C22, const Eigen::VectorXd& Y, double tol,

@@ -255,6 +255,14 @@ int flgp_logit_objective(flgp_spectrum* h, const double* Y, const double* N, int
  * reference is to optimiser tolerance. */
 int flgp_train_logit(flgp_spectrum* h, const double* Y, const double* N, int64_t m_total, int K, double sigma,
                      const char* approach, double* t_io, double* obj, int* nevals);
+/* train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53), the training half of fit_lae_logit_mult_gp_cpp
+ * (src/Fit.cpp:603-662; BASELINE config 3): labels Y in {0 .. J-1}, J = max(Y) + 1 one-vs-rest binary trainings with
+ * N = 1, each from t0 = 10.  *J_out <- J; t_out / obj_out (J_cap entries; obj_out may be NULL) <- (t_j, -minimum_j).
+ * The trainings are independent host loops and run on as many threads.  predict_logit_mult_gp_cpp draws its labels
+ * with the Polya-Gamma sampler (R RNG): not part of this path; per class, flgp_classification_posterior_fixed at t_j
+ * gives the deterministic Laplace posterior. */
+int flgp_train_logit_mult(flgp_spectrum* h, const double* Y, int64_t m_total, int K, double sigma,
+                          const char* approach, int J_cap, int* J_out, double* t_out, double* obj_out);
 /* The optimiser itself behind an nlopt-style callback (n = 1); host only, no GPU needed. */
 int flgp_cobyla_minimize_1d(flgp_objective_fn f, void* data, double lb, double ub, double* x, double* minf,
                             double xtol_rel, int maxeval, int* nevals);

@@ -797,3 +797,14 @@ def train_lae_logit(V, values, Y, idx, K, sigma=1e-3, approach="posterior", t0=1
     """train_lae_logit_gp_cpp (src/train.cpp:38-71): (t, -minimum, evaluations)."""
     t, fmin, nev = cobyla_minimize_1d(lambda t: logit_objective(V, values, Y, idx, K, t, sigma, approach, N), t0)
     return t, -fmin, nev
+
+
+def train_logit_mult(V, values, Y, idx, K, sigma=1e-3, approach="posterior"):
+    """train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53): J = max(Y) + 1 one-vs-rest binary trainings
+    (multi_train_split, :14-27), each train_lae_logit_gp_cpp with N = 1 from t0 = 10.  Returns (t[J], obj[J])."""
+    Y = np.asarray(Y)
+    J = int(Y.max()) + 1
+    ts, objs = np.zeros(J), np.zeros(J)
+    for j in range(J):
+        ts[j], objs[j], _ = train_lae_logit(V, values, (Y == j).astype(np.float64), idx, K, sigma, approach)
+    return ts, objs

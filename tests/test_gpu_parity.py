@@ -959,3 +959,30 @@ def test_fit_lae_logit_config1_end_to_end(flgp, oracle, approach):
     np.testing.assert_allclose(res["C"][:m], C11, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(res["C"][m:], C21, rtol=1e-8, atol=1e-10)
     assert np.mean((res["posterior"]["mean"] > 0) == (lab[m:] > 0.5)) > 0.9   # README: error rate 0.027 after training
+
+
+@pytest.mark.gpu
+def test_fit_lae_logit_mult_three_classes(flgp, oracle):
+    """fit_lae_logit_mult_gp_rcpp's deterministic half (src/Fit.cpp:603-662, src/MultiClassification.cpp:30-53): three
+    concentric rings as three classes, one-vs-rest training of the diffusion time per class against the oracle twin
+    on the library's own eigenvectors (t to optimiser tolerance, objective to 1e-6), and the arg-max of the per-class
+    Laplace posterior means classifies the held-out rows."""
+    rng = np.random.default_rng(11)
+    n, m, s, r, K, sigma = 3000, 150, 300, 3, 60, 1e-3
+    lab = rng.integers(0, 3, size=n)
+    lab[:3] = [0, 1, 2]
+    ang = rng.uniform(0, 2 * np.pi, size=n)
+    rad = 1.0 + lab + 0.08 * rng.standard_normal(n)
+    X = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1)
+    init = _init(n, s, 1)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init, iter_max=50)
+    t_l, obj_l = flgp.train_logit_mult_gp(ep, lab[:m].astype(np.float64), m, K, sigma, "posterior")
+    t_o, obj_o = oracle.train_logit_mult(ep.vectors, ep.values, lab[:m], np.arange(m, dtype=np.int32), K, sigma, "posterior")
+    assert len(t_l) == 3
+    np.testing.assert_allclose(t_l, t_o, rtol=1e-3)
+    np.testing.assert_allclose(obj_l, obj_o, rtol=1e-6, atol=1e-6)
+    res = flgp.fit_lae_logit_mult_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, sigma=sigma, init_idx=init, iter_max=50)
+    np.testing.assert_allclose(res["pars"], t_l, rtol=1e-12)
+    assert np.mean(res["argmax_posterior_mean"] == lab[m:]) > 0.95
+    with pytest.raises(flgp.FlgpError):
+        flgp.train_logit_mult_gp(ep, np.array([0.5] * m), m, K, sigma, "posterior")
