@@ -26,6 +26,8 @@ def _csr_parts(Z):
 # ------------------------------------------------------------------------------------------- k-means
 @pytest.mark.parametrize("n,d,s", [(4000, 2, 500), (20000, 3, 200), (1500, 1, 20), (3000, 4, 64),
                                     (3000, 5, 70), (2500, 16, 100), (700, 37, 33),
+                                    # tile edges of the fused pruned pass: one point into a new warp / CTA, tiny inputs
+                                    (257, 3, 7), (2049, 2, 30), (1025, 4, 12), (33, 1, 5), (2, 3, 2),
                                     # s >= 512: the first pass goes through pivot groups
                                     (40000, 3, 600), (30000, 2, 1024), (9000, 4, 513), (5000, 1, 700)])
 def test_kmeans_bitexact(flgp, oracle, n, d, s):
