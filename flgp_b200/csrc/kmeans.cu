@@ -1,14 +1,20 @@
 // kmeans.cu — Lloyd k-means anchors (replaces the stats::kmeans callback at
 // /root/reference/src/Utils.cpp:36-45; contract in oracle/flgp_oracle.cpp orc_kmeans_*).
 //
-// Per iteration ONE fused kernel does: score every (point, centre) pair in fp64 FMA form,
-// arg-min with lowest-index ties, compare with the previous assignment, and accumulate the
-// centroid sums as two-limb int64 fixed point with integer atomics (associative => the sums are
-// bit-identical for any thread schedule and any number of GPUs).  The only collective is one
-// int64 all-reduce of 2*s*d + s + 1 words per iteration.
+// The contract per iteration: score every (point, centre) pair in fp64 FMA form, arg-min with lowest-index ties,
+// compare with the previous assignment, accumulate the centroid sums as two-limb int64 fixed point with integer
+// atomics (associative => the sums are bit-identical for any thread schedule and any number of GPUs).  The only
+// collective is one int64 all-reduce of 2*s*d + s + 1 words per iteration.
 //
-// Roofline: FP64 FMA pipe.  Algorithmic work = 2*s*d flop per point per iteration
-// (SURVEY.md §8d); bytes 8d + 4 per point (negligible: intensity = s/4 flop/byte).
+// How the passes are run (all of it returns the brute-force result bit for bit):
+//   d <= 4   pass 1: brute force (kmeans_assign_small), through 128 pivot centres when s >= 512 (kmeans_assign_listed);
+//            passes 2..: rows sorted by cluster, Hamerly bounds, ONE kernel per pass (kmeans_lists_kernel ->
+//            kmeans_pass_fused -> kmeans_update_kernel), persistent integer sums (a reassignment is -x / +x);
+//   d > 4    distances on the FP64 tensor cores with a certified selection (distsel.cu), the uncertified rows in the
+//            oracle's order, Hamerly bounds around it (kmeans_hbounds / kmeans_hcommit).
+//
+// Roofline: brute force = FP64 FMA pipe, 2*s*d flop per point per iteration, bytes 8d + 4 per point;
+// the pruned pass = HBM (20 B of bounds and centre numbers per point streamed, one 32-byte record per survivor).
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
