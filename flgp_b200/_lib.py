@@ -42,6 +42,7 @@ def _declare(lib):
         "flgp_ctx_stage_count": (C.c_int, [H]),
         "flgp_ctx_stage_get": (C.c_int, [H, C.c_int, C.c_char_p, C.c_int, p_f64, C.POINTER(c_u64), p_f64, p_f64]),
         "flgp_dfma_peak": (C.c_int, [H, C.c_int, p_f64]),
+        "flgp_copy_roundtrip": (C.c_int, [H, p_void, p_void, C.c_size_t]),
         "flgp_comm_unique_id": (C.c_int, [p_void]),
         "flgp_ctx_comm_init": (C.c_int, [H, p_void, C.c_int, C.c_int]),
         "flgp_default_init": (C.c_int, [c_i64, C.c_int, c_u64, p_i32]),

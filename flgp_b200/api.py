@@ -105,6 +105,15 @@ class Context:
         check(self._lib.flgp_dfma_peak(self._h, iters, C.byref(v)))
         return v.value
 
+    def copy_roundtrip(self, arr: np.ndarray) -> np.ndarray:
+        """Host -> device -> host through the library's copy path (pageable arrays of 8 MB and more are staged by
+        several host threads, csrc/hostcopy.cu)."""
+        src = np.ascontiguousarray(arr)
+        out = np.empty_like(src)
+        check(self._lib.flgp_copy_roundtrip(self._h, src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                            src.nbytes))
+        return out
+
     # -- multi-GPU
     @staticmethod
     def comm_unique_id() -> bytes:

@@ -880,6 +880,19 @@ int flgp_dfma_peak(flgp_ctx* ctx, int iters, double* tflops) {
   });
 }
 
+int flgp_copy_roundtrip(flgp_ctx* ctx, const void* in, void* out, size_t bytes) {
+  return guard([&] {
+    need(ctx && (bytes == 0 || (in && out)), "null argument");
+    Ctx* c = on_device(&ctx->c);
+    DevBuf<unsigned char> buf(std::max<size_t>(bytes, 1));
+    if (bytes) {
+      buf.upload(static_cast<const unsigned char*>(in), bytes, c->stream);
+      buf.download(static_cast<unsigned char*>(out), bytes, c->stream);
+    }
+    sync(c);
+  });
+}
+
 int flgp_comm_unique_id(void* out128) {
   return guard([&] {
     need(out128 != nullptr, "null output");

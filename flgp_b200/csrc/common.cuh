@@ -73,6 +73,9 @@ struct Ctx {
 // fit; a repeated fit asks for exactly the same sizes, so freed blocks are kept and handed back by size.
 // All work of a process runs on one stream, which orders reuse; with more than one live context the pool
 // is bypassed.  (capi.cu owns the singleton.)
+// hostcopy.cu: host <-> device copies; large copies from / to pageable memory are staged by several host threads
+void h2d_copy(void* d, const void* h, size_t bytes, cudaStream_t st);
+void d2h_copy(void* h, const void* d, size_t bytes, cudaStream_t st);
 void* pool_alloc(size_t bytes);
 void pool_free(void* p, size_t bytes);
 void pool_trim();
@@ -112,12 +115,8 @@ struct DevBuf {
   void zero(cudaStream_t st) {
     if (n) FLGP_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), st));
   }
-  void upload(const T* h, size_t count, cudaStream_t st) {
-    FLGP_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
-  }
-  void download(T* h, size_t count, cudaStream_t st) const {
-    FLGP_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, st));
-  }
+  void upload(const T* h, size_t count, cudaStream_t st) { h2d_copy(p, h, count * sizeof(T), st); }
+  void download(T* h, size_t count, cudaStream_t st) const { d2h_copy(h, p, count * sizeof(T), st); }
 };
 
 inline void sync(Ctx* c) { FLGP_CUDA(cudaStreamSynchronize(c->stream)); }

@@ -52,6 +52,11 @@ int flgp_ctx_stage_get(flgp_ctx* ctx, int i, char* name, int name_len, double* m
                        double* flops, double* bytes);
 /* measured fp64 FMA throughput of this GPU in TFLOP/s (the FP64 roofline denominator) */
 int flgp_dfma_peak(flgp_ctx* ctx, int iters, double* tflops);
+/* Host -> device -> host through the copy path every entry point uses for its arguments (self-test).  Every `const
+ * double*` / `int32_t*` argument of this header may be ordinary pageable memory (R vectors, numpy arrays): copies of
+ * 8 MB and more from / to such memory are staged through pinned bounce buffers by several host threads (csrc/hostcopy.cu,
+ * ~37 GB/s instead of the driver's ~13 GB/s); pinned or registered memory is copied directly. */
+int flgp_copy_roundtrip(flgp_ctx* ctx, const void* in, void* out, size_t bytes);
 
 /* ---- multi-GPU: one process per GPU, rows of X_all sharded in contiguous blocks -------------- */
 /* rank 0 calls flgp_comm_unique_id and ships the 128 bytes to the other ranks (torch.distributed);

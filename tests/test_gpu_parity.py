@@ -988,3 +988,20 @@ def test_fit_lae_logit_mult_three_classes(flgp, oracle):
     assert np.mean(res["argmax_posterior_mean"] == lab[m:]) > 0.95
     with pytest.raises(flgp.FlgpError):
         flgp.train_logit_mult_gp(ep, np.array([0.5] * m), m, K, sigma, "posterior")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nbytes", [(8 << 20) - 8, 8 << 20, (8 << 20) + 8, (37 << 20) + 4088, 200 << 20])
+def test_staged_pageable_copies_roundtrip(flgp, nbytes):
+    """csrc/hostcopy.cu: copies from / to pageable memory of 8 MB and more go through per-thread pinned bounce buffers
+    (partial last chunk, fewer chunks than threads, many chunks per thread); pinned memory takes the plain path.
+    Bit-exact round trip either way, and repeated calls reuse the bounce buffers."""
+    import torch
+
+    ctx = flgp.default_ctx()
+    rng = np.random.default_rng(nbytes % 1000)
+    src = rng.integers(0, 2 ** 63 - 1, size=nbytes // 8, dtype=np.int64)
+    for _ in range(2):
+        assert np.array_equal(ctx.copy_roundtrip(src), src)
+    pinned = torch.from_numpy(src[: (9 << 20) // 8].copy()).pin_memory().numpy()
+    assert np.array_equal(ctx.copy_roundtrip(pinned), pinned)
