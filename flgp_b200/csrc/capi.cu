@@ -1691,8 +1691,8 @@ int flgp_train_logit_mult(flgp_spectrum* h, const double* Y, int64_t m_total, in
     const int J = (int)ymax + 1;
     *J_out = J;
     need(J <= J_cap, "more classes than the output arrays hold");
-    std::vector<double> ones((size_t)m_total, 0.0);
-    LogitTrain base = logit_train_prepare(h, ones.data(), nullptr, m_total, K, sigma, post);  // V, ev: shared by all classes
+    std::vector<double> y0((size_t)m_total, 0.0);  // placeholder labels: every class fills in its own below
+    LogitTrain base = logit_train_prepare(h, y0.data(), nullptr, m_total, K, sigma, post);  // V, ev: shared by all classes
     // the J binary trainings (src/MultiClassification.cpp:41-50) are independent host-side Newton / COBYLA loops
     std::vector<std::string> errs(J);
     auto one = [&](int j) {
