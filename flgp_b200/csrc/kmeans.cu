@@ -1294,7 +1294,19 @@ kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc,
                       unsigned long long* __restrict__ Rnew) {
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
+  // everything the point carries is requested before its position is known (the atomic below is an L2 round trip)
   const int a = asrc[i];
+  const int32_t pv = src_perm ? src_perm[i] : (int32_t)i;
+  double4 xv;
+  if (X4src) {
+    xv = X4src[i];
+  } else {  // first sort: from the caller's column-major matrix to one 32-byte record per point
+    double v[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int k = 0; k < d; ++k) v[k] = Xsrc[i + ldsrc * k];
+    xv = make_double4(v[0], v[1], v[2], v[3]);
+  }
+  // bounds travel with the point; before the first sort there are none: u = inf, l = 0 force a full evaluation
+  const float2 ul = ULsrc ? ULsrc[i] : make_float2(INFINITY, 0.f);
   // one atomic per group of equal keys in the warp
   const unsigned active = __activemask();
   const unsigned peers = __match_any_sync(active, a);
@@ -1304,30 +1316,15 @@ kmeans_scatter_kernel(const double* __restrict__ Xsrc, int64_t n, int64_t ldsrc,
   if (lane == leader) base = atomicAdd(&cursor[a], __popc(peers));
   base = __shfl_sync(peers, base, leader);
   const int pos = base + __popc(peers & ((1u << lane) - 1));
-  dst_perm[pos] = src_perm ? src_perm[i] : (int32_t)i;
+  dst_perm[pos] = pv;
   adst[pos] = a;
-  if (X4src) {
-    Xdst[pos] = X4src[i];
-  } else {  // first sort: from the caller's column-major matrix to one 32-byte record per point
-    double v[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int k = 0; k < d; ++k) v[k] = Xsrc[i + ldsrc * k];
-    Xdst[pos] = make_double4(v[0], v[1], v[2], v[3]);
-  }
-  // bounds travel with the point; before the first sort there are none: u = inf, l = 0 force a full evaluation
-  const float2 ul = ULsrc ? ULsrc[i] : make_float2(INFINITY, 0.f);
+  Xdst[pos] = xv;
   ULdst[pos] = ul;
-  // the cluster radii are re-tightened at every sort (between sorts they only grow: R += move): one atomic per
-  // group of equal keys in the warp
+  // the cluster radii are re-tightened at every sort (between sorts they only grow: R += move): the largest upper
+  // bound of the group in one warp reduction (non-negative floats order like their bits), one atomic per group
   if (Rnew) {
-    double m = (double)ul.x;
-    // max over the peers of this key: every lane scans the peer mask (at most 32 steps, usually one group per warp)
-    unsigned rest = peers;
-    while (rest) {
-      const int src = __ffs(rest) - 1;
-      rest &= rest - 1;
-      m = fmax(m, (double)__shfl_sync(peers, ul.x, src));
-    }
-    if (lane == leader) atomicMax(&Rnew[a], (unsigned long long)__double_as_longlong(m));
+    const unsigned mb = __reduce_max_sync(peers, __float_as_uint(ul.x));
+    if (lane == leader) atomicMax(&Rnew[a], (unsigned long long)__double_as_longlong((double)__uint_as_float(mb)));
   }
 }
 
