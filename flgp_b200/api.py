@@ -647,6 +647,91 @@ def fit_lae_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigm
     return res
 
 
+def _default_a2s(a2s):
+    if a2s is None:  # R/Fit.R: exp(seq(log(0.1), log(10), length.out = 10))
+        a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    return np.ascontiguousarray(a2s, dtype=np.float64)
+
+
+def fit_se_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma: float = 1e-3, a2s=None,
+                         approach="posterior", models=None, output_cov: bool = False, nstart: int = 1, *,
+                         t: Optional[float] = None, init_idx=None, seed: int = 0, iter_max: int = 100,
+                         ctx: Optional[Context] = None):
+    """fit_se_logit_gp_rcpp (R/Fit.R -> src/Fit.cpp:668-794; the README's GPC call): squared-exponential weights on the
+    KNN graph, grid search over the bandwidth a2 with the diffusion time t trained per grid point (COBYLA restatement;
+    t given: the objective is evaluated there), Laplace posterior of the test rows at the winner.  models["kernel"] is
+    ignored, as in the reference (SURVEY.md appendix A.12).  Y_pred (Polya-Gamma sampler on R's RNG) is not produced;
+    returned: posterior$mean, posterior$cov, pars (= t), a2, obj, the winning eigenpair, optional C."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    a2s = _default_a2s(a2s)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    mean = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    Cm = np.zeros((m + m_new, m), order="F") if output_cov else None
+    tt = np.array([np.nan if t is None else t], dtype=np.float64)
+    a2 = C.c_double()
+    obj = C.c_double()
+    h = C.c_void_p()
+    check(ctx._lib.flgp_fit_se_logit(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, _pf(Nv), sigma,
+                                     _pf(a2s), a2s.size, _b(approach), _b(mo["subsample"]), _gl(mo["gl"]),
+                                     int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed, _pf(tt),
+                                     _pf(mean), _pf(cov), _pf(Cm), C.byref(a2), C.byref(obj), C.byref(h)))
+    res = {"posterior": {"mean": mean, "cov": cov}, "pars": float(tt[0]), "a2": a2.value, "obj": obj.value,
+           "eigenpair": EigenPair(ctx, h)}
+    if output_cov:
+        res["C"] = Cm
+    return res
+
+
+def fit_se_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-3, a2s=None,
+                              approach="posterior", models=None, nstart: int = 1, *, init_idx=None, seed: int = 0,
+                              iter_max: int = 100, ctx: Optional[Context] = None):
+    """fit_se_logit_mult_gp_rcpp (R/Fit.R -> src/Fit.cpp:797-895): the bandwidth grid with the J one-vs-rest trainings
+    per grid point; the a2 with the largest summed objective wins.  As for fit_lae_logit_mult_gp_rcpp the sampled labels
+    are not produced; returned: per-class (t_j, objective_j) of the winner, a2, the summed objective, the per-class
+    Laplace posterior means on the test rows with their arg-max, and the winning eigenpair."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    mo = dict(DEFAULT_MODELS)
+    mo.update(models or {})
+    a2s = _default_a2s(a2s)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    cap = 1024
+    tj = np.zeros(cap)
+    oj = np.zeros(cap)
+    J = C.c_int()
+    a2 = C.c_double()
+    obj = C.c_double()
+    h = C.c_void_p()
+    check(ctx._lib.flgp_fit_se_logit_mult(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma, _pf(a2s),
+                                          a2s.size, _b(approach), _b(mo["subsample"]), _gl(mo["gl"]),
+                                          int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed, cap,
+                                          C.byref(J), _pf(tj), _pf(oj), C.byref(a2), C.byref(obj), C.byref(h)))
+    ep = EigenPair(ctx, h)
+    tj, oj = tj[:J.value].copy(), oj[:J.value].copy()
+    Kk = s if K < 0 else K
+    means = np.zeros((m_new, len(tj)))
+    for j in range(len(tj)):
+        mean, _ = posterior_distribution_classification(ep, (Y == j).astype(np.float64), m, Kk, float(tj[j]), sigma)
+        means[:, j] = mean[m:]
+    return {"pars": tj, "obj_classes": oj, "obj": obj.value, "a2": a2.value, "posterior_mean": means,
+            "argmax_posterior_mean": means.argmax(axis=1), "eigenpair": ep}
+
+
 def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, approach="posterior",
                                noise="same", models=None, output_cov: bool = False, nstart: int = 1, *,
                                pars: Optional[Sequence[float]] = None, init_idx=None, seed: int = 0,

@@ -521,12 +521,14 @@ void dev_copy(Ctx* c, DevBuf<T>& dst, const DevBuf<T>& src) {
   if (src.n) FLGP_CUDA(cudaMemcpyAsync(dst.p, src.p, sizeof(T) * src.n, cudaMemcpyDeviceToDevice, c->stream));
 }
 
-std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int64_t n_local, int64_t n_total,
-                                                int64_t row_offset, int d, int s, int r, int K, const Models& mo,
-                                                const int32_t* init_idx, uint64_t seed, const double* Ydev,
-                                                int64_t m_total, double sigma, bool posterior, const double* a2s,
-                                                int n_a2, const double* fixed_pars, double* pars_out, double* best_a2,
-                                                double* best_obj) {
+// prepare(q, handle): device-side preparation of grid point q's training (runs on the caller's thread, in grid order);
+// train(q) -> objective to be maximised: host work, the grid points run concurrently when `concurrent`.
+template <class Prepare, class Train>
+std::unique_ptr<flgp_spectrum> se_grid_search(Ctx* c, const double* Xdev, int64_t n_local, int64_t n_total,
+                                              int64_t row_offset, int d, int s, int r, int K, const Models& mo,
+                                              const int32_t* init_idx, uint64_t seed, const double* a2s, int n_a2,
+                                              bool concurrent, Prepare prepare, Train train, int* best_q,
+                                              double* best_a2, double* best_obj) {
   need(n_local >= 0 && n_total >= 1 && d >= 1, "bad matrix shape");
   need(s >= 1 && s <= n_total, "need 1 <= s <= n");
   need(r >= 1 && r <= s, "need 1 <= r <= s");
@@ -570,7 +572,6 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
   // (hundreds of objective evaluations each: 70 ms at config 2, against 3 ms of device work per grid point) and run
   // concurrently, one thread per grid point, so the grid costs about one training instead of n_a2 of them.
   std::vector<std::unique_ptr<flgp_spectrum>> sps(n_a2);
-  std::vector<RegTrain> Ts(n_a2);
   for (int q = 0; q < n_a2; ++q) {
     std::unique_ptr<flgp_spectrum> sp(new flgp_spectrum);
     sp->c = c;
@@ -589,24 +590,15 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
     const double* nc = (mo.gl == FLGP_GL_CLUSTER_NORMALIZED) ? sp->U.p + (size_t)s * d : nullptr;
     stage_graph_laplacian(c, n_local, s, r, sp->Zj.p, sp->Zx.p, mo.gl, nc, n_total);
     stage_spectrum(c, sp.get(), K, mo.root);
-    Ts[q] = reg_train_prepare(sp.get(), Ydev, m_total, K, sigma);
+    prepare(q, sp.get());
     sps[q] = std::move(sp);
   }
-  std::vector<double> objs(n_a2), xs((size_t)2 * n_a2);
+  std::vector<double> objs(n_a2);
   std::vector<std::string> errs(n_a2);
   std::vector<int> codes(n_a2, 0);
   auto train_one = [&](int q) {
     try {
-      double x[2] = {std::nan(""), std::nan("")};
-      if (fixed_pars) {
-        x[0] = fixed_pars[0];
-        x[1] = fixed_pars[1];
-        objs[q] = -reg_objective(Ts[q], x, nullptr, posterior);
-      } else {
-        objs[q] = train_regression(Ts[q], posterior, x, nullptr);
-      }
-      xs[2 * q] = x[0];
-      xs[2 * q + 1] = x[1];
+      objs[q] = train(q);
     } catch (const Error& e) {
       codes[q] = e.code;
       errs[q] = e.what();
@@ -615,7 +607,7 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
       errs[q] = e.what();
     }
   };
-  if (n_a2 > 1 && !fixed_pars) {
+  if (n_a2 > 1 && concurrent) {
     std::vector<std::thread> th;
     for (int q = 0; q < n_a2; ++q) th.emplace_back(train_one, q);
     for (auto& t : th) t.join();
@@ -627,15 +619,49 @@ std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int6
   std::unique_ptr<flgp_spectrum> best;
   double max_obj = -std::numeric_limits<double>::infinity();
   for (int q = 0; q < n_a2; ++q) {
-    if (objs[q] > max_obj || !best) {  // src/Fit.cpp:169-174 (first candidate kept even when every objective is -inf)
+    // src/Fit.cpp:169-174, 741-746, 869-874 (the first candidate is kept even when every objective is -inf)
+    if (objs[q] > max_obj || !best) {
       max_obj = objs[q];
-      pars_out[0] = xs[2 * q];
-      pars_out[1] = xs[2 * q + 1];
+      *best_q = q;
       if (best_a2) *best_a2 = a2s[q];
       best = std::move(sps[q]);
     }
   }
   if (best_obj) *best_obj = max_obj;
+  return best;
+}
+
+// fit_se_regression_gp_cpp's trainings (src/Fit.cpp:158-168): (t, noise) by MMA, or the objective at fixed_pars
+std::unique_ptr<flgp_spectrum> se_grid_pipeline(Ctx* c, const double* Xdev, int64_t n_local, int64_t n_total,
+                                                int64_t row_offset, int d, int s, int r, int K, const Models& mo,
+                                                const int32_t* init_idx, uint64_t seed, const double* Ydev,
+                                                int64_t m_total, double sigma, bool posterior, const double* a2s,
+                                                int n_a2, const double* fixed_pars, double* pars_out, double* best_a2,
+                                                double* best_obj) {
+  need(n_a2 >= 1 && a2s, "empty bandwidth grid");
+  std::vector<RegTrain> Ts(n_a2);
+  std::vector<double> xs((size_t)2 * n_a2);
+  int bq = 0;
+  std::unique_ptr<flgp_spectrum> best = se_grid_search(
+      c, Xdev, n_local, n_total, row_offset, d, s, r, K, mo, init_idx, seed, a2s, n_a2, !fixed_pars,
+      [&](int q, flgp_spectrum* sp) { Ts[q] = reg_train_prepare(sp, Ydev, m_total, K < 0 ? s : K, sigma); },
+      [&](int q) {
+        double x[2] = {std::nan(""), std::nan("")};
+        double obj;
+        if (fixed_pars) {
+          x[0] = fixed_pars[0];
+          x[1] = fixed_pars[1];
+          obj = -reg_objective(Ts[q], x, nullptr, posterior);
+        } else {
+          obj = train_regression(Ts[q], posterior, x, nullptr);
+        }
+        xs[2 * q] = x[0];
+        xs[2 * q + 1] = x[1];
+        return obj;
+      },
+      &bq, best_a2, best_obj);
+  pars_out[0] = xs[2 * bq];
+  pars_out[1] = xs[2 * bq + 1];
   return best;
 }
 
@@ -1676,48 +1702,80 @@ int flgp_train_logit(flgp_spectrum* h, const double* Y, const double* N, int64_t
   });
 }
 
+// multi_train_split (src/MultiClassification.cpp:14-27): J = max(Y) + 1, class j against the rest
+static int multi_class_count(const double* Y, int64_t m_total) {
+  double ymax = 0.0;
+  for (int64_t i = 0; i < m_total; ++i) {
+    need(Y[i] >= 0.0 && Y[i] == std::floor(Y[i]), "multi-class labels must be the integers 0 .. J-1");
+    ymax = std::max(ymax, Y[i]);
+  }
+  return (int)ymax + 1;
+}
+
+// the J binary trainings (src/MultiClassification.cpp:41-50) are independent host-side Newton / COBYLA loops
+static void train_logit_classes(const LogitTrain& base, const double* Y, int64_t m_total, int J, double* t_out,
+                                double* obj_out) {
+  std::vector<std::string> errs(J);
+  auto one = [&](int j) {
+    try {
+      LogitTrain T = base;
+      for (int64_t i = 0; i < m_total; ++i) T.Y[i] = (Y[i] == (double)j) ? 1.0 : 0.0;
+      double fmin = 0.0;
+      auto fn = [&](double t) { return logit_objective(T, t); };
+      t_out[j] = cobyla_minimize_1d(fn, 10.0, 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nullptr);
+      if (obj_out) obj_out[j] = -fmin;
+    } catch (const std::exception& e) {
+      errs[j] = e.what();
+    }
+  };
+  const int nthr = std::max(1u, std::min<unsigned>(J, std::thread::hardware_concurrency()));
+  std::vector<std::thread> pool;
+  std::atomic<int> next{0};
+  for (int q = 0; q < nthr; ++q)
+    pool.emplace_back([&] {
+      for (int j = next++; j < J; j = next++) one(j);
+    });
+  for (auto& th : pool) th.join();
+  for (int j = 0; j < J; ++j)
+    if (!errs[j].empty()) fail(3, "class %d: %s", j, errs[j].c_str());
+}
+
 int flgp_train_logit_mult(flgp_spectrum* h, const double* Y, int64_t m_total, int K, double sigma,
                           const char* approach, int J_cap, int* J_out, double* t_out, double* obj_out) {
   return guard([&] {
     need(h && Y && J_out && t_out, "null argument");
     bool post = true;
     if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
-    // multi_train_split (src/MultiClassification.cpp:14-27): J = max(Y) + 1, class j against the rest
-    double ymax = 0.0;
-    for (int64_t i = 0; i < m_total; ++i) {
-      need(Y[i] >= 0.0 && Y[i] == std::floor(Y[i]), "multi-class labels must be the integers 0 .. J-1");
-      ymax = std::max(ymax, Y[i]);
-    }
-    const int J = (int)ymax + 1;
+    const int J = multi_class_count(Y, m_total);
     *J_out = J;
     need(J <= J_cap, "more classes than the output arrays hold");
     std::vector<double> y0((size_t)m_total, 0.0);  // placeholder labels: every class fills in its own below
     LogitTrain base = logit_train_prepare(h, y0.data(), nullptr, m_total, K, sigma, post);  // V, ev: shared by all classes
-    // the J binary trainings (src/MultiClassification.cpp:41-50) are independent host-side Newton / COBYLA loops
-    std::vector<std::string> errs(J);
-    auto one = [&](int j) {
-      try {
-        LogitTrain T = base;
-        for (int64_t i = 0; i < m_total; ++i) T.Y[i] = (Y[i] == (double)j) ? 1.0 : 0.0;
-        double fmin = 0.0;
-        auto fn = [&](double t) { return logit_objective(T, t); };
-        t_out[j] = cobyla_minimize_1d(fn, 10.0, 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nullptr);
-        if (obj_out) obj_out[j] = -fmin;
-      } catch (const std::exception& e) {
-        errs[j] = e.what();
-      }
-    };
-    const int nthr = std::max(1u, std::min<unsigned>(J, std::thread::hardware_concurrency()));
-    std::vector<std::thread> pool;
-    std::atomic<int> next{0};
-    for (int q = 0; q < nthr; ++q)
-      pool.emplace_back([&] {
-        for (int j = next++; j < J; j = next++) one(j);
-      });
-    for (auto& th : pool) th.join();
-    for (int j = 0; j < J; ++j)
-      if (!errs[j].empty()) fail(3, "class %d: %s", j, errs[j].c_str());
+    train_logit_classes(base, Y, m_total, J, t_out, obj_out);
   });
+}
+
+// the tail of the binary logit drivers: posterior_distribution_classification on the test rows and the optional
+// covariance block C = [Cvv + sigma I; Cnv] (src/Fit.cpp:566-582, 752-773)
+static void logit_fit_tail(flgp_spectrum* h, const double* Y, int64_t m, int64_t m_new, int K, double t, double sigma,
+                           double* post_mean, double* post_cov, double* C_out) {
+  const int64_t n = m + m_new;
+  if (post_mean) {
+    std::vector<double> mean(n), cov(n);
+    int rc2 = flgp_classification_posterior_fixed(h, Y, m, K, t, sigma, 1e-5, 100, mean.data(),
+                                                  post_cov ? cov.data() : nullptr);
+    if (rc2) fail(rc2, "%s", g_err.c_str());
+    if (m_new) std::memcpy(post_mean, mean.data() + m, sizeof(double) * m_new);
+    if (post_cov && m_new) std::memcpy(post_cov, cov.data() + m, sizeof(double) * m_new);
+  }
+  if (C_out) {
+    std::vector<int32_t> i0(n), i1(m);
+    for (int64_t i = 0; i < n; ++i) i0[i] = (int32_t)i;
+    for (int64_t i = 0; i < m; ++i) i1[i] = (int32_t)i;
+    int rc3 = flgp_hk_from_spectrum(h, K, t, i0.data(), n, i1.data(), m, C_out);
+    if (rc3) fail(rc3, "%s", g_err.c_str());
+    for (int64_t i = 0; i < m; ++i) C_out[i + n * i] += sigma;
+  }
 }
 
 int flgp_fit_lae_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m, int64_t m_new,
@@ -1746,23 +1804,93 @@ int flgp_fit_lae_logit(flgp_ctx* ctx, const double* X, const double* Y, const do
       if (rc1) fail(rc1, "%s", g_err.c_str());
       *obj = -*obj;
     }
+    logit_fit_tail(h, Y, m, m_new, K, *t_io, sigma, post_mean, post_cov, C_out);
+  });
+}
+
+// fit_se_logit_gp_cpp (src/Fit.cpp:668-794): one k-means + KNN, per bandwidth a2 the SE weights, graph Laplacian,
+// spectrum and the COBYLA training of t (or the objective at the given t); the a2 with the largest objective wins.
+int flgp_fit_se_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m, int64_t m_new,
+                      int d, int s, int r, int K, const double* N, double sigma, const double* a2s, int n_a2,
+                      const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,
+                      const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
+                      double* C_out, double* best_a2, double* best_obj, flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && X && Y && t_io && a2s, "null argument");
+    need(m >= 1 && m_new >= 0 && n_a2 >= 1, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = on_device(&ctx->c);
+    need(c->nranks == 1, "flgp_fit_se_logit is the single-process entry point");
     const int64_t n = m + m_new;
-    if (post_mean) {  // posterior_distribution_classification on the test rows (src/Fit.cpp:566-582)
-      std::vector<double> mean(n), cov(n);
-      int rc2 = flgp_classification_posterior_fixed(h, Y, m, K, *t_io, sigma, 1e-5, 100, mean.data(),
-                                                    post_cov ? cov.data() : nullptr);
-      if (rc2) fail(rc2, "%s", g_err.c_str());
-      if (m_new) std::memcpy(post_mean, mean.data() + m, sizeof(double) * m_new);
-      if (post_cov && m_new) std::memcpy(post_cov, cov.data() + m, sizeof(double) * m_new);
+    if (K < 0) K = s;  // src/Fit.cpp:686-688
+    DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+    const Models mo = make_models(subsample, "se", gl, root, nstart, 0.1, iter_max);
+    const bool fixed = (*t_io == *t_io);
+    const double t_fixed = *t_io;
+    std::vector<LogitTrain> Ts(n_a2);
+    std::vector<double> ts(n_a2);
+    int bq = 0;
+    std::unique_ptr<flgp_spectrum> sp = se_grid_search(
+        c, dX.p, n, n, 0, d, s, r, K, mo, init_idx, seed, a2s, n_a2, !fixed,
+        [&](int q, flgp_spectrum* h) { Ts[q] = logit_train_prepare(h, Y, N, m, K, sigma, post); },
+        [&](int q) {
+          if (fixed) {
+            ts[q] = t_fixed;
+            return -logit_objective(Ts[q], t_fixed);
+          }
+          double fmin = 0.0;
+          auto fn = [&](double t) { return logit_objective(Ts[q], t); };
+          ts[q] = cobyla_minimize_1d(fn, 10.0, 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nullptr);  // src/train.cpp:38-71
+          return -fmin;
+        },
+        &bq, best_a2, best_obj);
+    *t_io = ts[bq];
+    logit_fit_tail(sp.get(), Y, m, m_new, K, *t_io, sigma, post_mean, post_cov, C_out);
+    if (out) *out = sp.release();
+  });
+}
+
+// fit_se_logit_mult_gp_cpp (src/Fit.cpp:797-895): as above with the J one-vs-rest trainings of train_logit_mult_gp_cpp
+// per bandwidth; a grid point's objective is the sum of its J class objectives (:862-866).
+int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                           int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,
+                           const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,
+                           const int32_t* init_idx, uint64_t seed, int J_cap, int* J_out, double* t_out,
+                           double* obj_out, double* best_a2, double* best_obj, flgp_spectrum** out) {
+  return guard([&] {
+    need(ctx && X && Y && a2s && J_out && t_out, "null argument");
+    need(m >= 1 && m_new >= 0 && n_a2 >= 1, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = on_device(&ctx->c);
+    need(c->nranks == 1, "flgp_fit_se_logit_mult is the single-process entry point");
+    const int64_t n = m + m_new;
+    if (K < 0) K = s;  // src/Fit.cpp:813-815
+    const int J = multi_class_count(Y, m);
+    *J_out = J;
+    need(J <= J_cap, "more classes than the output arrays hold");
+    DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+    const Models mo = make_models(subsample, "se", gl, root, nstart, 0.1, iter_max);
+    std::vector<double> y0((size_t)m, 0.0);  // placeholder labels: every class fills in its own
+    std::vector<LogitTrain> Ts(n_a2);
+    std::vector<double> ts((size_t)n_a2 * J), os((size_t)n_a2 * J);
+    int bq = 0;
+    std::unique_ptr<flgp_spectrum> sp = se_grid_search(
+        c, dX.p, n, n, 0, d, s, r, K, mo, init_idx, seed, a2s, n_a2, false,
+        [&](int q, flgp_spectrum* h) { Ts[q] = logit_train_prepare(h, y0.data(), nullptr, m, K, sigma, post); },
+        [&](int q) {  // the J trainings of a grid point run on J threads; the grid points one after the other
+          train_logit_classes(Ts[q], Y, m, J, &ts[(size_t)q * J], &os[(size_t)q * J]);
+          double sum = 0.0;
+          for (int j = 0; j < J; ++j) sum += os[(size_t)q * J + j];
+          return sum;
+        },
+        &bq, best_a2, best_obj);
+    for (int j = 0; j < J; ++j) {
+      t_out[j] = ts[(size_t)bq * J + j];
+      if (obj_out) obj_out[j] = os[(size_t)bq * J + j];
     }
-    if (C_out) {  // output_cov: C = [Cvv + sigma I; Cnv], n x m (src/Fit.cpp:566-573)
-      std::vector<int32_t> i0(n), i1(m);
-      for (int64_t i = 0; i < n; ++i) i0[i] = (int32_t)i;
-      for (int64_t i = 0; i < m; ++i) i1[i] = (int32_t)i;
-      int rc3 = flgp_hk_from_spectrum(h, K, *t_io, i0.data(), n, i1.data(), m, C_out);
-      if (rc3) fail(rc3, "%s", g_err.c_str());
-      for (int64_t i = 0; i < m; ++i) C_out[i + n * i] += sigma;
-    }
+    if (out) *out = sp.release();
   });
 }
 

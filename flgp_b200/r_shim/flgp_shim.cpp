@@ -314,6 +314,36 @@ Rcpp::List fit_lae_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector
   return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
 }
 
+// fit_se_logit_gp_cpp (src/Fit.cpp:668-794), signature unchanged: the bandwidth grid with the COBYLA training of t per
+// grid point behind the C ABI; labels from the reference's sampler on the returned covariance block, as above.
+Rcpp::List fit_se_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                               int s, int r, int K, Rcpp::NumericVector N_train, double sigma, std::vector<double> a2s,
+                               std::string approach, Rcpp::List models, bool output_cov, int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const Eigen::Map<Eigen::VectorXd> N(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(N_train));
+  const int m = X.rows(), m_new = X_new.rows();
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]);
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  double t = NA_REAL, a2 = 0.0, obj = 0.0;  // NaN: train
+  Eigen::VectorXd mean(m_new), cov(m_new);
+  Eigen::MatrixXd C(m + m_new, m);
+  ok(flgp_fit_se_logit(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, N.data(), sigma,
+                       a2s.data(), (int)a2s.size(), approach.c_str(), sub.c_str(),
+                       gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]), nstart, 100,
+                       init.data(), 0, &t, mean.data(), cov.data(), C.data(), &a2, &obj, nullptr));
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", t = " << t
+              << ", the objective function is " << obj << "\n";
+  Eigen::VectorXd label = Rcpp::as<Eigen::VectorXd>(test_pgbinary_cpp(C.topRows(m), Y, C)["Y_pred"]);
+  Rcpp::List Y_pred = Rcpp::List::create(Rcpp::Named("train") = label.head(m), Rcpp::Named("test") = label.tail(m_new));
+  Rcpp::List post = Rcpp::List::create(Rcpp::Named("mean") = mean, Rcpp::Named("cov") = cov);
+  if (output_cov)
+    return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("C") = C, Rcpp::Named("posterior") = post,
+                              Rcpp::Named("pars") = t);
+  return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
+}
+
 // train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53) for fit_lae_logit_mult_gp_cpp (src/Fit.cpp:603-662): the J
 // one-vs-rest trainings run behind the C ABI on the spectrum handle; the MultiClassifier keeps the reference's layout
 // (aug_y + one ReturnValue(t, obj) per class), so predict_logit_mult_gp_cpp (Polya-Gamma sampler, R RNG) is unchanged.
@@ -324,6 +354,26 @@ std::vector<ReturnValue> train_logit_mult_on_handle(flgp_spectrum* h, const Eige
   int J = 0;
   std::vector<double> t(256), obj(256);
   ok(flgp_train_logit_mult(h, Y.data(), Y.size(), K, sigma, approach.c_str(), 256, &J, t.data(), obj.data()));
+  std::vector<ReturnValue> res(J);
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  return res;
+}
+
+// The grid loop of fit_se_logit_mult_gp_cpp (src/Fit.cpp:851-875) as one call: the winning handle and the per-class
+// ReturnValues; the caller builds the MultiClassifier from them and goes on with predict_logit_mult_gp_cpp unchanged.
+std::vector<ReturnValue> se_logit_mult_grid(const Eigen::MatrixXd& X, const Eigen::VectorXd& Y, const Eigen::MatrixXd& X_new,
+                                            int s, int r, int K, double sigma, const std::vector<double>& a2s,
+                                            const std::string& approach, Rcpp::List models, int nstart,
+                                            flgp_spectrum** best, double* best_a2, double* max_obj) {
+  const int m = X.rows(), m_new = X_new.rows();
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]);
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  int J = 0;
+  std::vector<double> t(256), obj(256);
+  ok(flgp_fit_se_logit_mult(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, sigma, a2s.data(),
+                            (int)a2s.size(), approach.c_str(), sub.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
+                            Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, 256, &J, t.data(), obj.data(),
+                            best_a2, max_obj, best));
   std::vector<ReturnValue> res(J);
   for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
   return res;

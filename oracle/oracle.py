@@ -808,3 +808,68 @@ def train_logit_mult(V, values, Y, idx, K, sigma=1e-3, approach="posterior"):
     for j in range(J):
         ts[j], objs[j], _ = train_lae_logit(V, values, (Y == j).astype(np.float64), idx, K, sigma, approach)
     return ts, objs
+
+
+def _se_grid(X, X_new, s, r, K, init_idx, a2s, gl, root, iter_max, nthreads):
+    """The part the fit_se_* drivers share (src/Fit.cpp:121-156, 690-733, 817-850): one k-means + KNN, then per a2
+    the SE weights on the KNN graph, the graph Laplacian and the spectrum.  Yields (a2, values, V)."""
+    X_all = np.asfortranarray(np.vstack([X, X_new]))
+    n = len(X_all)
+    U, assign, iters = kmeans_lloyd(X_all, s, init_idx, iter_max, nthreads)
+    ind, dist = knn(X_all, np.asfortranarray(U[:, :-1]), r, want_dist=True, nthreads=nthreads)
+    Zj, Dx = knn_csr(ind, dist)
+    dmean = Dx.sum() / (n * r)
+    for a2 in a2s:
+        Zx = se_weights(Dx, a2 * dmean)
+        nc = U[:, -1].copy() if gl == "cluster-normalized" else None
+        Zx = graph_laplacian(Zj, Zx, s, gl, nc)
+        values, V = spectrum_from_Z(Zj, Zx, s, K, root, nthreads=nthreads)
+        yield a2, values, V
+
+
+def fit_se_logit(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-3, approach="posterior", gl="cluster-normalized",
+                 root=True, iter_max=100, nthreads=1, N=None, t=None):
+    """fit_se_logit_gp_cpp (src/Fit.cpp:668-794) without the label sampler: the bandwidth grid with the diffusion time
+    trained per grid point (t given: the objective at t), the largest objective wins (:741-746); Laplace posterior of
+    the test rows at the winner (:752-773)."""
+    m = len(X)
+    n = m + len(X_new)
+    if K < 0:
+        K = s
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n, dtype=np.int32)
+    best = None
+    for a2, values, V in _se_grid(X, X_new, s, r, K, init_idx, a2s, gl, root, iter_max, nthreads):
+        if t is None:
+            tq, obj, _ = train_lae_logit(V, values, Y, idx0, K, sigma, approach, N=N)
+        else:
+            tq, obj = t, -logit_objective(V, values, Y, idx0, K, t, sigma, approach, N)
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, t=tq, a2=a2, values=values, V=V)
+    V, values, tq = best["V"], best["values"], best["t"]
+    C11 = hk_from_spectrum(V, values, K, tq, idx0, idx0)
+    C11[np.diag_indices(m)] += sigma
+    C21 = hk_from_spectrum(V, values, K, tq, idx1, idx0)
+    C22 = ((V[m:, :K] * np.exp(-tq * (1.0 - values[:K]))) * V[m:, :K]).sum(axis=1) + sigma
+    best["mean"], best["cov"] = posterior_distribution_classification(C11, C21, C22, Y)
+    best["C"] = np.vstack([C11, C21])
+    return best
+
+
+def fit_se_logit_mult(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-3, approach="posterior",
+                      gl="cluster-normalized", root=True, iter_max=100, nthreads=1):
+    """fit_se_logit_mult_gp_cpp (src/Fit.cpp:797-895) without the label sampler: per a2 the J one-vs-rest trainings;
+    the grid point's objective is the sum of the class objectives (:862-866)."""
+    m = len(X)
+    if K < 0:
+        K = s
+    idx0 = np.arange(m, dtype=np.int32)
+    best = None
+    for a2, values, V in _se_grid(X, X_new, s, r, K, init_idx, a2s, gl, root, iter_max, nthreads):
+        ts, objs = train_logit_mult(V, values, Y, idx0, K, sigma, approach)
+        obj = 0.0
+        for o in objs:
+            obj += o
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, t=ts, objs=objs, a2=a2, values=values, V=V)
+    return best

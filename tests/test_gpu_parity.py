@@ -990,6 +990,82 @@ def test_fit_lae_logit_mult_three_classes(flgp, oracle):
         flgp.train_logit_mult_gp(ep, np.array([0.5] * m), m, K, sigma, "posterior")
 
 
+def _noisy_rings(n, n_rings, n_classes, seed):
+    """Concentric rings, class = ring number modulo n_classes, 12 % of the labels moved to another class: the trained
+    diffusion time is then an interior optimum (on cleanly separated classes t runs to the evaluation cap)."""
+    rng = np.random.default_rng(seed)
+    ang = rng.uniform(0, 2 * np.pi, n)
+    ring = rng.integers(0, n_rings, n)
+    rad = 0.5 + 0.25 * ring + 0.05 * rng.standard_normal(n)
+    X = np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1)
+    lab = ring % n_classes
+    flip = rng.uniform(size=n) < 0.12
+    lab = np.where(flip, (lab + rng.integers(1, n_classes, n)) % n_classes, lab)
+    lab[:n_classes] = np.arange(n_classes)
+    return np.asfortranarray(X), lab.astype(np.float64)
+
+
+def test_fit_se_logit_config1_grid(flgp, oracle):
+    """fit_se_logit_gp_rcpp (src/Fit.cpp:668-794; the call of the README's GPC example) against the oracle twin running
+    its own pipeline (k-means, KNN, SE weights, graph Laplacian, LAPACK eigenvectors).  BASELINE config 1's rings
+    (n=4800, d=2, m=100, s=600, r=3, K=100), default ten bandwidths, at a fixed t — the whole path is deterministic:
+    same winning a2, objective to 1e-7, Laplace posterior to 1e-6.  Trained (COBYLA restatement per grid point) on
+    rings with noisy labels: same a2, t to optimiser tolerance."""
+    from flgp_b200.datasets import make
+
+    X, lab, cfg = make("C1")
+    m, s, r, K, sigma = cfg["m"], cfg["s"], cfg["r"], cfg["K"], 1e-3
+    init = _init(len(X), s, 1)
+    a2s = np.exp(np.linspace(np.log(0.1), np.log(10.0), 10))
+    res = flgp.fit_se_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, sigma=sigma, t=8.0, init_idx=init, iter_max=50,
+                                    output_cov=True)
+    ref = oracle.fit_se_logit(X[:m], lab[:m], X[m:], s, r, K, init, a2s, sigma=sigma, iter_max=50, nthreads=NT, t=8.0)
+    assert res["a2"] == ref["a2"] and res["pars"] == 8.0
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-7)
+    np.testing.assert_allclose(res["eigenpair"].values, ref["values"], rtol=1e-8, atol=1e-10)
+    sc = max(1.0, np.abs(ref["mean"]).max())
+    np.testing.assert_allclose(res["posterior"]["mean"], ref["mean"], rtol=1e-6, atol=1e-7 * sc)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-6, atol=1e-7 * max(1.0, np.abs(ref["cov"]).max()))
+    np.testing.assert_allclose(res["C"], ref["C"], rtol=1e-7, atol=1e-9)
+    assert np.mean((res["posterior"]["mean"] > 0) == (lab[m:] > 0.5)) > 0.9
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.fit_se_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, approach="evidence", init_idx=init)
+    # trained
+    X, lab = _noisy_rings(2400, 4, 2, 5)
+    m, s, r, K = 120, 240, 3, 60
+    init = _init(len(X), s, 1)
+    a2s = np.array([0.1, 0.5, 2.0, 10.0])
+    for approach in ("posterior", "marginal"):
+        res = flgp.fit_se_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, sigma=sigma, a2s=a2s, approach=approach,
+                                        init_idx=init, iter_max=50)
+        ref = oracle.fit_se_logit(X[:m], lab[:m], X[m:], s, r, K, init, a2s, sigma=sigma, approach=approach, iter_max=50,
+                                  nthreads=NT)
+        assert res["a2"] == ref["a2"]
+        assert abs(res["pars"] - ref["t"]) <= 2e-3 * max(1.0, ref["t"])
+        np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-6, atol=1e-6)
+        sc = max(1.0, np.abs(ref["mean"]).max())
+        np.testing.assert_allclose(res["posterior"]["mean"], ref["mean"], rtol=1e-2, atol=1e-2 * sc)
+
+
+def test_fit_se_logit_mult_three_classes_grid(flgp, oracle):
+    """fit_se_logit_mult_gp_rcpp's deterministic half (src/Fit.cpp:797-895): bandwidth grid with the J one-vs-rest
+    trainings per grid point, the summed objective selects a2; against the oracle twin's own pipeline."""
+    X, lab = _noisy_rings(2400, 6, 3, 7)
+    m, s, r, K, sigma = 150, 240, 3, 60, 1e-3
+    init = _init(len(X), s, 1)
+    a2s = np.array([0.1, 0.5, 2.0, 10.0])
+    res = flgp.fit_se_logit_mult_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, sigma=sigma, a2s=a2s, init_idx=init,
+                                         iter_max=50)
+    ref = oracle.fit_se_logit_mult(X[:m], lab[:m], X[m:], s, r, K, init, a2s, sigma=sigma, iter_max=50, nthreads=NT)
+    assert res["a2"] == ref["a2"] and len(res["pars"]) == 3
+    np.testing.assert_allclose(res["pars"], ref["t"], rtol=2e-3)
+    np.testing.assert_allclose(res["obj_classes"], ref["objs"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["eigenpair"].values, ref["values"], rtol=1e-8, atol=1e-10)
+    assert res["posterior_mean"].shape == (len(X) - m, 3)
+    assert np.mean(res["argmax_posterior_mean"] == lab[m:]) > 0.7   # 12 % of the held-out labels are noise too
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("nbytes", [(8 << 20) - 8, 8 << 20, (8 << 20) + 8, (37 << 20) + 4088, 200 << 20])
 def test_staged_pageable_copies_roundtrip(flgp, nbytes):

@@ -148,3 +148,33 @@ def test_laplace_mll_matches_direct_newton(oracle):
     B = np.eye(40) + np.sqrt(W)[:, None] * C * np.sqrt(W)[None, :]
     want = (Y * np.log(pi) + (1 - Y) * np.log(1 - pi)).sum() - 0.5 * f @ np.linalg.solve(C, f) - 0.5 * np.linalg.slogdet(B)[1]
     assert abs(got - want) <= 1e-6 * abs(want)
+
+
+def test_se_logit_grid_twins_select_the_largest_objective(oracle):
+    """The oracle twins of fit_se_logit_gp_cpp / fit_se_logit_mult_gp_cpp (src/Fit.cpp:718-747, 851-875): the grid
+    point with the largest (summed) objective wins, first one on ties; a one-point grid is that point's training;
+    at a fixed t the objective is the plain logit objective of the winning spectrum."""
+    rng = np.random.default_rng(4)
+    n, m, s, r, K = 600, 50, 60, 3, 20
+    ang = rng.uniform(0, 2 * np.pi, n)
+    ring = rng.integers(0, 4, n)
+    rad = 0.5 + 0.25 * ring + 0.05 * rng.standard_normal(n)
+    X = np.asfortranarray(np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1))
+    lab = np.where(rng.uniform(size=n) < 0.15, 1 - ring % 2, ring % 2).astype(np.float64)
+    init = np.sort(rng.choice(n, s, replace=False)).astype(np.int32)
+    a2s = np.array([0.2, 1.0, 5.0])
+    idx0 = np.arange(m, dtype=np.int32)
+    grid = list(oracle._se_grid(X[:m], X[m:], s, r, K, init, a2s, "cluster-normalized", True, 30, 2))
+    objs = [-oracle.logit_objective(V, values, lab[:m], idx0, K, 6.0, 1e-3, "posterior") for _, values, V in grid]
+    ref = oracle.fit_se_logit(X[:m], lab[:m], X[m:], s, r, K, init, a2s, iter_max=30, nthreads=2, t=6.0)
+    assert ref["a2"] == a2s[int(np.argmax(objs))] and ref["obj"] == max(objs) and ref["t"] == 6.0
+    assert ref["mean"].shape == (n - m,) and ref["C"].shape == (n, m) and np.all(ref["cov"] > 0)
+    one = oracle.fit_se_logit(X[:m], lab[:m], X[m:], s, r, K, init, a2s[1:2], iter_max=30, nthreads=2)
+    t1, o1, _ = oracle.train_lae_logit(grid[1][2], grid[1][1], lab[:m], idx0, K, 1e-3, "posterior")
+    assert one["t"] == t1 and one["obj"] == o1
+    lab3 = (ring % 3).astype(np.float64)
+    lab3[:3] = [0, 1, 2]
+    mult = oracle.fit_se_logit_mult(X[:m], lab3[:m], X[m:], s, r, K, init, a2s[:2], iter_max=30, nthreads=2)
+    sums = [oracle.train_logit_mult(V, values, lab3[:m], idx0, K, 1e-3, "posterior")[1].sum() for _, values, V in grid[:2]]
+    assert mult["a2"] == a2s[int(np.argmax(sums))] and abs(mult["obj"] - max(sums)) <= 1e-12 * abs(max(sums))
+    assert len(mult["t"]) == 3
