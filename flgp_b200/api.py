@@ -179,11 +179,13 @@ def _from_csr(Z, r=None):
 # ------------------------------------------------------------------------------------------------
 def subsample_cpp(X, s: int, method: str = "kmeans", nstart: int = 1, *, init_idx=None, seed: int = 0,
                   iter_max: int = 100, return_info: bool = False, ctx: Optional[Context] = None):
-    """subsample_cpp (src/Utils.cpp:32-68).  "kmeans": U = [centres, size] (s x (d+1)); "random": s x d."""
+    """subsample_cpp (src/Utils.cpp:32-68).  "kmeans" / "minibatchkmeans": U = [centres, size] (s x (d+1)); "random":
+    s x d.  "minibatchkmeans": mini-batch k-means from the start rows (at most iter_max batches of 10 s rows keyed by
+    seed), sizes = rows per nearest centre; return_info then gives the number of batches run (no assignments)."""
     ctx = ctx or default_ctx()
     X = _f64(X)
     n, d = X.shape
-    ucols = d + 1 if method == "kmeans" else d
+    ucols = d if method == "random" else d + 1
     U = np.zeros((s, ucols), order="F")
     assign = np.zeros(n, np.int32)
     iters = C.c_int(0)

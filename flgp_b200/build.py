@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libflgp_b200.so")
-SOURCES = ["capi.cu", "comm.cu", "kmeans.cu", "knn.cu", "distsel.cu", "lae.cu", "sparse.cu", "gemm.cu", "eigh.cu", "chfsi.cu", "misc.cu", "pool.cu", "tail.cu", "nystrom.cu", "hostcopy.cu"]
+SOURCES = ["capi.cu", "comm.cu", "kmeans.cu", "knn.cu", "distsel.cu", "lae.cu", "sparse.cu", "gemm.cu", "eigh.cu", "chfsi.cu", "misc.cu", "pool.cu", "tail.cu", "nystrom.cu", "hostcopy.cu", "minibatch.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",

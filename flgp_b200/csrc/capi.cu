@@ -238,6 +238,16 @@ void stage_subsample(Ctx* c, flgp_spectrum* sp, const double* X, const Models& m
     idx.upload(init_idx, s, c->stream);
     FLGP_LAUNCH(c, gather_rows_kernel, ceil_div(s * d, 256), 256, 0, X, sp->n_local, d, idx.p, s, sp->U.p);
     sync(c);
+  } else if (mo.subsample == "minibatchkmeans") {
+    // src/Utils.cpp:49-62: centroids by mini-batch k-means (ClusterR un-vendored: the contract of minibatch.cu), sizes
+    // by the reference's own 1-NN count.  ClusterR's num_init picks among kmeans++ starts; this path takes explicit
+    // start rows, so there is nothing for nstart > 1 to select from.
+    need(mo.nstart == 1, "subsample=\"minibatchkmeans\" takes one explicit start (nstart must be 1)");
+    need(c->nranks == 1, "subsample=\"minibatchkmeans\" is single-GPU only");
+    sp->ucols = d + 1;
+    sp->U.alloc((size_t)s * (d + 1));
+    StageScope st(c, "minibatchkmeans");
+    minibatch_kmeans_run(c, X, sp->n_local, sp->n_local, d, s, init_idx, mo.iter_max, seed, sp->U.p, &sp->kmeans_iters);
   } else {
     fail(2, "The subsample method is not supported!");
   }

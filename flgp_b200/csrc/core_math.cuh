@@ -426,4 +426,78 @@ FLGP_HD int sturm_count(const double* d, const double* e2, int n, double x, doub
   return cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Mini-batch k-means (subsample_cpp "minibatchkmeans", src/Utils.cpp:49-62; contract in DESIGN.md §2).
+// ---------------------------------------------------------------------------------------------
+FLGP_HD uint64_t mb_mix64(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// key of batch `it` (0-based)
+FLGP_HD uint64_t mb_batch_key(uint64_t seed, int it) { return mb_mix64(seed ^ ((uint64_t)(it + 1) * 0xD1B54A32D192ED03ull)); }
+// k -> perm(k): a bijection of [0, n) (4-round Feistel network on the smallest even number of bits covering n,
+// cycle-walked back into range), so that the first b values are b DISTINCT rows: a batch drawn without replacement.
+FLGP_HD int64_t mb_perm(int64_t k, int64_t n, uint64_t key) {
+  int bits = 2;
+  while (((int64_t)1 << bits) < n) bits += 2;
+  const int half = bits / 2;
+  const uint64_t mask = ((uint64_t)1 << half) - 1;
+  uint64_t x = (uint64_t)k;
+  do {
+    uint64_t L = x >> half, R = x & mask;
+    for (int rd = 0; rd < 4; ++rd) {
+      const uint64_t f = mb_mix64(R ^ (key + (uint64_t)rd * 0xA24BAED4963EE407ull)) & mask;
+      const uint64_t t = L ^ f;
+      L = R;
+      R = t;
+    }
+    x = (L << half) | R;
+  } while (x >= (uint64_t)n);
+  return (int64_t)x;
+}
+// The Lloyd score rule on a group of G centres at once (mb_assign_kernel's per-thread work): e[g] starts at
+// cn[g] = |c_g|^2 + 2 d maxabs^2 and takes fma(x_q, -2 c_gq, .) for q ascending; rec = G x dp records of -2 c, zero
+// padded from d to dp (a multiple of QC), x(q) = coordinate q of the point (read only for q < d): the padding adds
+// fma(0, 0, e) = e, so the chain equals the d-term chain of the oracle bit for bit.
+template <int G, int QC, class XAcc>
+FLGP_HD void mb_score_group(const XAcc& x, int d, int dp, const double* rec, const double* cn, double* e) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) e[g] = cn[g];
+  for (int q0 = 0; q0 < dp; q0 += QC) {
+    double xr[QC];
+#pragma unroll
+    for (int qq = 0; qq < QC; ++qq) xr[qq] = (q0 + qq < d) ? x(q0 + qq) : 0.0;
+#pragma unroll
+    for (int g = 0; g < G; ++g)
+#pragma unroll
+      for (int qq = 0; qq < QC; ++qq) e[g] = fma(xr[qq], rec[g * dp + q0 + qq], e[g]);
+  }
+}
+// arg-min over the group's live centres j0 .. min(j0 + G, s) - 1, lowest index on ties (centres come in index order)
+template <int G>
+FLGP_HD void mb_argmin_group(const double* e, int j0, int s, double* best, int* bj) {
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    const int j = j0 + g;
+    if (j < s && (j == 0 || e[g] < *best)) {
+      *best = e[g];
+      *bj = j;
+    }
+  }
+}
+// record of centre j for the group staging: -2 c (q < d), 0 beyond; cn = fma chain of c^2 plus m2
+FLGP_HD double mb_centre_norm(const double* C, int64_t ldc, int j, int d, double m2) {
+  double a = 0.0;
+  for (int q = 0; q < d; ++q) {
+    const double c = C[j + ldc * q];
+    a = fma(c, c, a);
+  }
+  return a + m2;
+}
+// Sculley's per-sample update with the per-centre learning rate eta = 1 / count: c <- (1 - eta) c + eta x, every
+// operation rounded separately
+FLGP_HD double mb_update_coord(double c, double x, double eta) { return (1.0 - eta) * c + eta * x; }
+
 }  // namespace flgp

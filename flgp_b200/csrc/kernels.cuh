@@ -29,6 +29,12 @@ double maxabs_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d);
 double kmeans_withinss_run(Ctx* c, const double* X, int64_t n_local, int64_t ldx, int d, const double* U, int s,
                            const int32_t* assign, int64_t n_total);
 
+// ---- minibatch.cu ----------------------------------------------------------------------------
+// subsample_cpp "minibatchkmeans" (src/Utils.cpp:49-62): U = s x (d+1), centroids by mini-batch k-means from the
+// start rows init_idx_h (batches keyed by seed, at most max_iters of them), sizes = rows per 1-NN label.  Single GPU.
+void minibatch_kmeans_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d, int s, const int32_t* init_idx_h,
+                          int max_iters, uint64_t seed, double* U, int* iters_out);
+
 // ---- knn.cu ----------------------------------------------------------------------------------
 // ind: n x r (ld n), ascending distance, libstdc++ partial_sort tie behaviour.  dist: optional.
 // sorted (optional): the cluster-sorted layout of the SAME rows left by kmeans_run; with it (d <= 4, r <= 5) every

@@ -72,6 +72,11 @@ int flgp_default_init(int64_t n, int s, uint64_t seed, int32_t* init_idx);
 /* subsample_cpp (src/Utils.cpp:32-68).  method "kmeans": U is s x (d+1) = [centres, cluster sizes];
  * "random": U is s x d = X[init_idx,] (no size column, as the reference).  assign (n, optional) and
  * iters (optional) report the final assignment and the Lloyd iterations run.
+ * "minibatchkmeans" (src/Utils.cpp:49-62): U is s x (d+1) = [centroids, rows per nearest centroid].  The reference's
+ * centroids come from ClusterR::MiniBatchKmeans (un-vendored, R-RNG start: parity unpinned); here Sculley's mini-batch
+ * k-means with ClusterR's defaults (early_stop_iter 10, tol 1e-4) from the start rows init_idx, at most iter_max
+ * batches of min(10 s, n) distinct rows drawn by a bijection keyed by (seed, batch); the sizes column is the
+ * reference's own 1-NN count (:57-62).  iters <- batches run; assign is not written; nstart must be 1; single GPU.
  * nstart > 1 (stats::kmeans's restarts): nstart Lloyd runs, start 0 from init_idx (or the seed's default rows),
  * start q from the default rows of a seed derived from (seed, q); the run with the smallest total within-cluster
  * sum of squares (exact fixed-point sum: the same choice on every rank) is returned.

@@ -247,6 +247,102 @@ int orc_kmeans_lloyd(const double* X, int64_t n, int64_t ldx, int d, int s, cons
 }
 
 // =========================================================================================
+// subsample_cpp "minibatchkmeans" (src/Utils.cpp:49-62).  The centroids come from
+// ClusterR::MiniBatchKmeans(data, clusters = s, batch_size = 10 s, init_fraction = 20 s / n,
+// num_init = nstart) — an un-vendored, unpinned R package (kmeans++ start on R's RNG): **parity
+// unpinned**; restated here as Sculley's mini-batch k-means (WWW 2010, Algorithm 1) with ClusterR's
+// defaults max_iters = 100, early_stop_iter = 10, tol = 1e-4, explicit start rows and a counter-based
+// batch sampler (contract defined HERE and in DESIGN.md §2):
+//   C = X[init];  cnt = 0;  per batch it = 0 ..:  rows = first b values of a keyed bijection of [0, n)
+//   (b = min(10 s, n) distinct rows);  every batch row goes to its nearest centre under the Lloyd score
+//   rule (lowest index on ties);  then, in batch order, cnt_j += 1, eta = 1 / cnt_j,
+//   c_j <- (1 - eta) c_j + eta x  (separately rounded);  delta = sum_j (sum_q (c_jq - c_jq_old)^2),
+//   both sums sequential;  stop after early_stop_iter consecutive batches with delta < tol.
+// What follows the centroids is the reference's own code (:57-62): labels = KNN_cpp(X, centroids, 1),
+// U(:, d) = number of rows per label — done by the caller with orc_knn.
+// =========================================================================================
+static uint64_t orc_mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// keyed bijection of [0, n): 4 Feistel rounds on the smallest even bit width covering n, cycle-walked into range
+int64_t orc_mb_perm(int64_t k, int64_t n, uint64_t key) {
+  int bits = 2;
+  while (((int64_t)1 << bits) < n) bits += 2;
+  const int half = bits / 2;
+  const uint64_t mask = ((uint64_t)1 << half) - 1;
+  uint64_t x = (uint64_t)k;
+  do {
+    uint64_t L = x >> half, R = x & mask;
+    for (int rd = 0; rd < 4; ++rd) {
+      uint64_t f = orc_mix64(R ^ (key + (uint64_t)rd * 0xA24BAED4963EE407ull)) & mask;
+      uint64_t t = L ^ f;
+      L = R;
+      R = t;
+    }
+    x = (L << half) | R;
+  } while (x >= (uint64_t)n);
+  return (int64_t)x;
+}
+uint64_t orc_mb_batch_key(uint64_t seed, int it) { return orc_mix64(seed ^ ((uint64_t)(it + 1) * 0xD1B54A32D192ED03ull)); }
+
+// C: s x d (ld s) centres out.  batch_rows (optional, max_iters x b): the rows of every batch that ran.
+int orc_minibatch_kmeans(const double* X, int64_t n, int64_t ldx, int d, int s, const int32_t* init_idx, int max_iters,
+                         uint64_t seed, int early_stop_iter, double tol, int nthreads, double* C, int* iters,
+                         int64_t* batch_rows) {
+  if (s < 1 || s > n || d < 1) return 1;
+  const int64_t b = std::min<int64_t>((int64_t)10 * s, n);
+  double maxabs = 0.0;
+  for (int k = 0; k < d; ++k) maxabs = std::max(maxabs, orc_maxabs(X + ldx * k, n));
+  for (int j = 0; j < s; ++j) {
+    if (init_idx[j] < 0 || init_idx[j] >= n) return 1;
+    for (int k = 0; k < d; ++k) C[j + (size_t)s * k] = X[init_idx[j] + ldx * k];
+  }
+  std::vector<double> Xb((size_t)b * d), Cold((size_t)s * d);
+  std::vector<int32_t> assign(b);
+  std::vector<int64_t> cnt(s, 0), acc((size_t)2 * s * d + s + 1);
+  int it = 0, calm = 0;
+  while (it < max_iters) {
+    const uint64_t key = orc_mb_batch_key(seed, it);
+    for (int64_t k = 0; k < b; ++k) {
+      const int64_t row = orc_mb_perm(k, n, key);
+      if (batch_rows) batch_rows[(size_t)it * b + k] = row;
+      for (int q = 0; q < d; ++q) Xb[k + (size_t)b * q] = X[row + ldx * q];
+    }
+    std::fill(assign.begin(), assign.end(), -1);
+    std::fill(acc.begin(), acc.end(), 0);
+    // the Lloyd score rule on the batch (the integer sums it also forms are not used)
+    if (orc_kmeans_step(Xb.data(), b, b, d, C, s, maxabs, n, assign.data(), acc.data(), nthreads)) return 1;
+    Cold.assign(C, C + (size_t)s * d);
+    for (int64_t k = 0; k < b; ++k) {
+      const int j = assign[k];
+      cnt[j] += 1;
+      const double eta = 1.0 / (double)cnt[j];
+      for (int q = 0; q < d; ++q) {
+        const double c = C[j + (size_t)s * q];
+        C[j + (size_t)s * q] = (1.0 - eta) * c + eta * Xb[k + (size_t)b * q];
+      }
+    }
+    double delta = 0.0;
+    for (int j = 0; j < s; ++j) {
+      double dj = 0.0;
+      for (int q = 0; q < d; ++q) {
+        const double df = C[j + (size_t)s * q] - Cold[j + (size_t)s * q];
+        dj = dj + df * df;
+      }
+      delta = delta + dj;
+    }
+    ++it;
+    calm = (delta < tol) ? calm + 1 : 0;
+    if (early_stop_iter > 0 && calm >= early_stop_iter) break;
+  }
+  if (iters) *iters = it;
+  return 0;
+}
+
+// =========================================================================================
 // KNN  (src/Utils.cpp:72-97, 102-192)
 //   D(i,j) = ((-2 * sum_k x_ik u_jk) + |x_i|^2) + |u_j|^2        (src/Utils.cpp:121)
 //   top-r by the LITERAL std::partial_sort(ind, ind+r, ind+s, D[i1] < D[i2])  (:91-94)

@@ -115,6 +115,43 @@ def kmeans_lloyd(X, s, init_idx, iter_max=100, nthreads=1):
     return U, assign, iters.value
 
 
+def mb_perm(k, n, key):
+    """The batch sampler of the mini-batch contract: value k of the keyed bijection of [0, n)."""
+    lib().orc_mb_perm.restype = C.c_int64
+    return int(lib().orc_mb_perm(I64(k), I64(n), C.c_uint64(key)))
+
+
+def mb_batch_key(seed, it):
+    lib().orc_mb_batch_key.restype = C.c_uint64
+    return int(lib().orc_mb_batch_key(C.c_uint64(seed), it))
+
+
+def minibatch_kmeans(X, s, init_idx, max_iters=100, seed=0, nthreads=1, early_stop_iter=10, tol=1e-4,
+                     want_batches=False):
+    """subsample_cpp(method="minibatchkmeans") contract (src/Utils.cpp:49-62): centroids by Sculley's mini-batch
+    k-means (ClusterR::MiniBatchKmeans is un-vendored: parity unpinned, contract in flgp_oracle.cpp), then the
+    reference's own lines :57-62 — labels = KNN_cpp(X, centroids, 1), U[:, d] = rows per label."""
+    X = _f(X)
+    n, d = X.shape
+    init_idx = _i32(init_idx)
+    Cc = np.zeros((s, d), order="F")
+    iters = C.c_int(0)
+    b = min(10 * s, n)
+    rows = np.zeros((max_iters, b), np.int64) if want_batches else None
+    rc = lib().orc_minibatch_kmeans(_p(X), I64(n), I64(n), d, s, _p(init_idx, C.c_int32), max_iters, C.c_uint64(seed),
+                                    early_stop_iter, C.c_double(tol), nthreads, _p(Cc), C.byref(iters),
+                                    _p(rows, C.c_int64) if want_batches else None)
+    if rc:
+        raise ValueError("orc_minibatch_kmeans failed")
+    labels = knn(X, Cc, 1, nthreads=nthreads)[:, 0]
+    U = np.zeros((s, d + 1), order="F")
+    U[:, :d] = Cc
+    U[:, d] = np.bincount(labels, minlength=s)
+    if want_batches:
+        return U, iters.value, rows[:iters.value]
+    return U, iters.value
+
+
 # ------------------------------------------------------------------ KNN / LAE
 def knn(X, U, r, want_dist=False, nthreads=1):
     """KNN_cpp (src/Utils.cpp:102-192): ind_knn n x r (0-based, ascending distance)."""

@@ -70,13 +70,52 @@ def test_kmeans_iter_cap_and_default_init(flgp, oracle):
     assert iters == io == 5 and np.array_equal(U, Uo) and np.array_equal(assign, ao)
 
 
+@pytest.mark.parametrize("n,d,s,iters,seed", [(3000, 2, 30, 100, 1), (2000, 3, 25, 40, 2), (900, 16, 12, 30, 3),
+                                              (700, 37, 9, 25, 4), (150, 5, 20, 15, 5), (5000, 1, 40, 100, 6),
+                                              (40000, 3, 600, 100, 7), (2500, 784, 64, 6, 8)])
+def test_subsample_minibatchkmeans_bitexact(flgp, oracle, n, d, s, iters, seed):
+    """subsample_cpp "minibatchkmeans" (src/Utils.cpp:49-62; ClusterR un-vendored: the mini-batch contract of
+    csrc/minibatch.cu and the oracle): centroids, number of batches and the 1-NN sizes column bit for bit — lattice
+    data with exact score ties (d = 2), tight clusters that end by the early stop (d = 3), batch = all rows (n < 10 s),
+    d below / at / above the register chunk, the tensor-core 1-NN (d = 784)."""
+    rng = np.random.default_rng(seed)
+    X = np.asfortranarray(rng.standard_normal((n, d)) * (0.01 if d == 3 else 1.0) + 3 * rng.integers(0, 4, (n, 1)))
+    if d == 2:
+        X = np.asfortranarray(np.round(X))
+    init = _init(n, s, seed)
+    U, _, it = flgp.subsample_cpp(X, s, "minibatchkmeans", init_idx=init, seed=seed, iter_max=iters, return_info=True)
+    Uo, it_o = oracle.minibatch_kmeans(X, s, init, max_iters=iters, seed=seed, nthreads=NT)
+    assert it == it_o
+    assert np.array_equal(U[:, :d], Uo[:, :d])
+    assert np.array_equal(U[:, d], Uo[:, d]) and U[:, d].sum() == n
+
+
+def test_pipeline_with_minibatch_anchors(flgp, oracle):
+    """heat_kernel_spectrum_cpp with models$subsample = "minibatchkmeans": anchors from the mini-batch contract, the
+    rest of the path unchanged (Z bit-exact, eigenvalues 1e-8 against the oracle fed the same anchors)."""
+    X, _ = swiss(6000, 5)
+    m, s, r, K = 300, 150, 3, 30
+    init = _init(len(X), s, 3)
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, models={"subsample": "minibatchkmeans"}, init_idx=init,
+                                       seed=3)
+    Uo, _ = oracle.minibatch_kmeans(X, s, init, seed=3, nthreads=NT)
+    assert np.array_equal(ep.anchors(), Uo)
+    Zj, Zx = oracle.cross_similarity_lae(X, Uo, r, "cluster-normalized", nthreads=NT)
+    Z = ep.Z()
+    assert np.array_equal(Z.indices.reshape(len(X), r), Zj) and np.array_equal(Z.data.reshape(len(X), r), Zx)
+    vo, _ = oracle.spectrum_from_Z(Zj, Zx, s, K, True, nthreads=NT)
+    np.testing.assert_allclose(ep.values, vo, rtol=1e-8, atol=1e-10)
+
+
 def test_subsample_random_and_errors(flgp):
     X, _ = spiral(500, 4)
     init = _init(500, 30, 1)
     U = flgp.subsample_cpp(X, 30, "random", init_idx=init)
     assert U.shape == (30, 2) and np.array_equal(U, X[init])
     with pytest.raises(flgp.FlgpError, match="not supported"):
-        flgp.subsample_cpp(X, 30, "minibatchkmeans")
+        flgp.subsample_cpp(X, 30, "kmedoids")
+    with pytest.raises(flgp.FlgpError, match="nstart"):
+        flgp.subsample_cpp(X, 30, "minibatchkmeans", nstart=2)
     with pytest.raises(flgp.FlgpError):
         flgp.subsample_cpp(X, 501, "kmeans")
 

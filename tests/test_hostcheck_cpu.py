@@ -137,3 +137,35 @@ def test_sturm_count_matches_eigenvalues(hostcheck):
     for x in np.r_[lam[:-1] + np.diff(lam) / 2, lam.min() - 1, lam.max() + 1]:
         got = hostcheck.hc_sturm(_pd(np.ascontiguousarray(d)), _pd(e2), n, C.c_double(x), C.c_double(1e-300))
         assert got == int((lam < x).sum())
+
+
+def test_minibatch_kernel_logic_matches_oracle(hostcheck, oracle):
+    """csrc/minibatch.cu's per-thread pieces (keyed batch bijection, grouped / zero-padded score chains, warp-per-centre
+    sequential updates, the stopping sums), run by virtual threads on the host, against the oracle's plain restatement
+    of the contract: centroids and iteration count bit for bit, for d below, at and above the chunk size."""
+    hostcheck.hc_mb_perm.restype = C.c_int64
+    hostcheck.hc_mb_batch_key.restype = C.c_uint64
+    for n in (1, 2, 5, 64, 1000, 4097):
+        key = hostcheck.hc_mb_batch_key(C.c_uint64(n), 3)
+        assert key == oracle.mb_batch_key(n, 3)
+        p = [hostcheck.hc_mb_perm(C.c_int64(k), C.c_int64(n), C.c_uint64(key)) for k in range(n)]
+        assert sorted(p) == list(range(n))                      # a bijection of [0, n)
+        assert p[: min(n, 50)] == [oracle.mb_perm(k, n, key) for k in range(min(n, 50))]
+    hostcheck.hc_minibatch_kmeans.restype = C.c_int
+    for n, d, s, iters, seed in [(3000, 2, 30, 100, 1), (2000, 3, 25, 40, 2), (900, 16, 12, 30, 3), (700, 37, 9, 25, 4),
+                                 (150, 5, 20, 15, 5), (5000, 1, 40, 100, 6)]:
+        rng = np.random.default_rng(seed)
+        X = np.asfortranarray(rng.standard_normal((n, d)) * (0.01 if d == 3 else 1.0) + 3 * rng.integers(0, 4, (n, 1)))
+        if d == 2:
+            X = np.asfortranarray(np.round(X))                  # lattice: exact score ties between centres
+        init = np.sort(rng.choice(n, s, replace=False)).astype(np.int32)
+        Uo, it_o = oracle.minibatch_kmeans(X, s, init, max_iters=iters, seed=seed)
+        if d == 3:
+            assert it_o < iters                                 # tight clusters: the early stop ends the run
+        Cc = np.zeros((s, d), order="F")
+        it_h = hostcheck.hc_minibatch_kmeans(_pd(X), C.c_int64(n), C.c_int64(n), d, s,
+                                             init.ctypes.data_as(P(C.c_int32)), iters, C.c_uint64(seed),
+                                             C.c_double(np.abs(X).max()), _pd(Cc))
+        assert it_h == it_o
+        assert np.array_equal(Cc, Uo[:, :d])
+        assert Uo[:, d].sum() == n
