@@ -39,34 +39,39 @@ mb_gather_kernel(const double* __restrict__ X, int64_t n, int64_t ldx, int d, in
 
 // score_j(x) = fma chain over q of x_q * (-2 c_jq), started from |c_j|^2 (fma chain) + 2 d maxabs^2; arg-min with the
 // lowest index on ties — the Lloyd score rule of kmeans.cu / the oracle's orc_kmeans_step.
-// Shared memory: rec[MB_GROUP][dp] (-2 c, zero padded to dp = multiple of MB_QCHUNK) and cn[MB_GROUP].
+// Shared memory: a tile of ng groups: rec[ng * MB_GROUP][dp] (-2 c, zero padded to dp = multiple of MB_QCHUNK) and
+// cn[ng * MB_GROUP]; one barrier pair per tile.
 __global__ void __launch_bounds__(MB_THREADS)
-mb_assign_kernel(const double* __restrict__ Xb, int64_t b, int d, int dp, const double* __restrict__ C, int s,
+mb_assign_kernel(const double* __restrict__ Xb, int64_t b, int d, int dp, int ng, const double* __restrict__ C, int s,
                  int64_t ldc, double m2, int32_t* __restrict__ assign) {
   extern __shared__ double sm[];
-  double* rec = sm;                   // MB_GROUP x dp
-  double* cn = sm + MB_GROUP * dp;    // MB_GROUP
+  const int tile = ng * MB_GROUP;     // centres per tile
+  double* rec = sm;                   // tile x dp
+  double* cn = sm + (size_t)tile * dp;  // tile
   const int64_t k = blockIdx.x * (int64_t)MB_THREADS + threadIdx.x;
   const bool live = k < b;
   const BatchRow xk{Xb, k, b};
   double best = 0.0;
   int bj = 0;
-  for (int j0 = 0; j0 < s; j0 += MB_GROUP) {
+  for (int j0 = 0; j0 < s; j0 += tile) {
     __syncthreads();
-    for (int t = threadIdx.x; t < MB_GROUP * dp; t += MB_THREADS) {
+    for (int t = threadIdx.x; t < tile * dp; t += MB_THREADS) {
       const int jj = t / dp, q = t - jj * dp;
       const int j = j0 + jj;
       rec[t] = (j < s && q < d) ? -2.0 * C[j + ldc * q] : 0.0;
     }
-    if (threadIdx.x < MB_GROUP) {
-      const int j = j0 + threadIdx.x;
-      cn[threadIdx.x] = (j < s) ? mb_centre_norm(C, ldc, j, d, m2) : 0.0;
+    for (int jj = threadIdx.x; jj < tile; jj += MB_THREADS) {
+      const int j = j0 + jj;
+      cn[jj] = (j < s) ? mb_centre_norm(C, ldc, j, d, m2) : 0.0;
     }
     __syncthreads();
     if (!live) continue;
-    double e[MB_GROUP];
-    mb_score_group<MB_GROUP, MB_QCHUNK>(xk, d, dp, rec, cn, e);
-    mb_argmin_group<MB_GROUP>(e, j0, s, &best, &bj);
+    for (int g = 0; g < ng; ++g) {
+      if (j0 + g * MB_GROUP >= s) break;
+      double e[MB_GROUP];
+      mb_score_group<MB_GROUP, MB_QCHUNK>(xk, d, dp, rec + (size_t)g * MB_GROUP * dp, cn + g * MB_GROUP, e);
+      mb_argmin_group<MB_GROUP>(e, j0 + g * MB_GROUP, s, &best, &bj);
+    }
   }
   if (live) assign[k] = bj;
 }
@@ -82,19 +87,25 @@ mb_update_kernel(const double* __restrict__ Xb, int64_t b, int d, const int32_t*
   if (j >= s) return;  // whole warps leave together
   long long n_j = cnt[j];
   bool touched = false;
-  for (int64_t k0 = 0; k0 < b; k0 += 32) {
-    const int64_t k = k0 + lane;
-    const int a = (k < b) ? assign[k] : -1;
-    unsigned bal = __ballot_sync(0xffffffffu, a == j);
-    while (bal) {
-      const int src = __ffs(bal) - 1;
-      bal &= bal - 1;
-      const int64_t km = k0 + src;
-      n_j += 1;
-      const double eta = 1.0 / (double)n_j;
-      for (int q = lane; q < d; q += 32) C[j + ldc * q] = mb_update_coord(C[j + ldc * q], Xb[km + b * q], eta);
-      touched = true;
+  for (int64_t k0 = 0; k0 < b; k0 += 128) {  // four independent loads in flight; members still taken in batch order
+    unsigned bal[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int64_t k = k0 + 32 * u + lane;
+      const int a = (k < b) ? assign[k] : -1;
+      bal[u] = __ballot_sync(0xffffffffu, a == j);
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      while (bal[u]) {
+        const int src = __ffs(bal[u]) - 1;
+        bal[u] &= bal[u] - 1;
+        const int64_t km = k0 + 32 * u + src;
+        n_j += 1;
+        const double eta = 1.0 / (double)n_j;
+        for (int q = lane; q < d; q += 32) C[j + ldc * q] = mb_update_coord(C[j + ldc * q], Xb[km + b * q], eta);
+        touched = true;
+      }
   }
   __syncwarp();
   if (lane == 0) {
@@ -153,7 +164,8 @@ void minibatch_kmeans_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d
   if (s < 1 || s > n || d < 1) fail(2, "minibatchkmeans: need 1 <= s <= n");
   if (c->nranks != 1) fail(2, "subsample=\"minibatchkmeans\" is single-GPU only");
   const int dp = (d + MB_QCHUNK - 1) / MB_QCHUNK * MB_QCHUNK;
-  const size_t smem = ((size_t)MB_GROUP * dp + MB_GROUP) * sizeof(double);
+  const int ng = std::max(1, std::min(16, 4096 / (MB_GROUP * dp)));  // groups of centres staged per barrier pair
+  const size_t smem = ((size_t)ng * MB_GROUP * dp + ng * MB_GROUP) * sizeof(double);
   if (smem > 200 * 1024) fail(2, "minibatchkmeans: d=%d exceeds the supported maximum", d);
   if (smem > 48 * 1024)
     FLGP_CUDA(cudaFuncSetAttribute(mb_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -175,7 +187,8 @@ void minibatch_kmeans_run(Ctx* c, const double* X, int64_t n, int64_t ldx, int d
   while (it < max_iters) {
     const uint64_t key = mb_batch_key(seed, it);
     FLGP_LAUNCH(c, mb_gather_kernel, ceil_div(b, 256), 256, 0, X, n, ldx, d, b, key, Xb.p);
-    FLGP_LAUNCH(c, mb_assign_kernel, ceil_div(b, MB_THREADS), MB_THREADS, smem, Xb.p, b, d, dp, U, s, ldc, m2, assign.p);
+    FLGP_LAUNCH(c, mb_assign_kernel, ceil_div(b, MB_THREADS), MB_THREADS, smem, Xb.p, b, d, dp, ng, U, s, ldc, m2,
+                assign.p);
     FLGP_LAUNCH(c, mb_copy_centres_kernel, ceil_div((int64_t)s * d, 256), 256, 0, U, s, ldc, d, Cold.p);
     FLGP_LAUNCH(c, mb_update_kernel, ceil_div((int64_t)s * 32, 256), 256, 0, Xb.p, b, d, assign.p, U, s, ldc, Cold.p,
                 cnt.p, dsq.p);
