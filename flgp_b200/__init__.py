@@ -13,7 +13,7 @@ from .api import (  # noqa: F401
     lae_eigenmap, local_anchor_embedding_cpp, mma_minimize, posterior_distribution_classification,
     posterior_distribution_classification_rcpp, regression_fixed, regression_objective, spectrum_from_Z_cpp, subsample_cpp, train_regression_gp,
     v_to_z_cpp, cobyla_minimize_1d, fit_lae_logit_gp_rcpp, fit_nystrom_regression_sharded, logit_objective, train_lae_logit_gp, train_logit_mult_gp, fit_lae_logit_mult_gp_rcpp,
-    fit_se_logit_gp_rcpp, fit_se_logit_mult_gp_rcpp,
+    fit_se_logit_gp_rcpp, fit_se_logit_mult_gp_rcpp, fit_nystrom_logit_gp_rcpp, fit_nystrom_logit_mult_gp_rcpp,
 )
 
 __version__ = "0.1.0"

@@ -126,6 +126,13 @@ def _declare(lib):
                                              C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
                                              C.c_int, C.c_int, p_i32, c_u64, C.c_int, C.POINTER(C.c_int), p_f64, p_f64,
                                              p_f64, p_f64, C.POINTER(H)]),
+        "flgp_fit_nystrom_logit": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, p_f64,
+                                             C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int, p_i32,
+                                             c_u64, p_f64, p_f64, p_f64, p_f64, p_f64, p_f64]),
+        "flgp_fit_nystrom_logit_mult": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int,
+                                                  C.c_double, p_f64, C.c_int, C.c_char_p, C.c_char_p, C.c_int, C.c_int,
+                                                  p_i32, c_u64, C.c_int, C.POINTER(C.c_int), p_f64, p_f64, p_f64, p_f64,
+                                                  p_f64, p_f64]),
         "flgp_classification_posterior_fixed": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_double, C.c_double,
                                                           C.c_int, p_f64, p_f64]),
         "flgp_posterior_distribution_classification": (C.c_int, [H, p_f64, p_f64, p_f64, p_f64, C.c_int, c_i64,

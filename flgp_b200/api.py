@@ -855,6 +855,74 @@ def fit_nystrom_regression_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: floa
             "a2": a2.value, "obj": obj.value}
 
 
+def fit_nystrom_logit_gp_rcpp(X, Y, X_new, s: int, K: int = -1, N=None, sigma: float = 1e-3, a2s=None,
+                              approach="posterior", subsample="kmeans", output_cov: bool = False, nstart: int = 1, *,
+                              t: Optional[float] = None, init_idx=None, seed: int = 0, iter_max: int = 100,
+                              ctx: Optional[Context] = None):
+    """fit_nystrom_logit_gp_rcpp (R/Fit.R -> src/Fit.cpp:896-1038) without the Polya-Gamma labels: Nystrom grid with
+    the diffusion time trained per bandwidth (t given: the objective there), Laplace posterior of the test rows at the
+    winner.  Returned: posterior$mean, posterior$cov, pars (= t), a2, obj, optional C."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    a2s = _default_a2s(a2s)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    mean = np.zeros(m_new)
+    cov = np.zeros(m_new)
+    Cm = np.zeros((m + m_new, m), order="F") if output_cov else None
+    tt = np.array([np.nan if t is None else t], dtype=np.float64)
+    a2 = C.c_double()
+    obj = C.c_double()
+    check(ctx._lib.flgp_fit_nystrom_logit(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, K, _pf(Nv), sigma,
+                                          _pf(a2s), a2s.size, _b(approach), _b(subsample), nstart, iter_max,
+                                          _pi(_idx(init_idx)), seed, _pf(tt), _pf(mean), _pf(cov), _pf(Cm),
+                                          C.byref(a2), C.byref(obj)))
+    res = {"posterior": {"mean": mean, "cov": cov}, "pars": float(tt[0]), "a2": a2.value, "obj": obj.value}
+    if output_cov:
+        res["C"] = Cm
+    return res
+
+
+def fit_nystrom_logit_mult_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: float = 1e-3, a2s=None,
+                                   approach="posterior", subsample="kmeans", nstart: int = 1, *,
+                                   return_eigenpair: bool = False, init_idx=None, seed: int = 0, iter_max: int = 100,
+                                   ctx: Optional[Context] = None):
+    """The training half of fit_nystrom_logit_mult_gp_rcpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+    trainings on the extended labelled rows, summed objective selects.  Returned: pars (t_j), obj_classes, obj, a2 and,
+    with return_eigenpair, the winning extended eigenpair (values K, vectors n x K) the reference's sampler consumes."""
+    if approach not in ("posterior", "marginal"):
+        raise FlgpError("This model selection approach is not supported!")
+    ctx = ctx or default_ctx()
+    a2s = _default_a2s(a2s)
+    X = _f64(X)
+    X_new = _f64(X_new)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    m, d = X.shape
+    m_new = X_new.shape[0]
+    Kk = s if K < 0 else K
+    cap = 1024
+    tj = np.zeros(cap)
+    oj = np.zeros(cap)
+    J = C.c_int()
+    a2 = C.c_double()
+    obj = C.c_double()
+    values = np.zeros(Kk) if return_eigenpair else None
+    vectors = np.zeros((m + m_new, Kk), order="F") if return_eigenpair else None
+    check(ctx._lib.flgp_fit_nystrom_logit_mult(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, K, sigma, _pf(a2s),
+                                               a2s.size, _b(approach), _b(subsample), nstart, iter_max,
+                                               _pi(_idx(init_idx)), seed, cap, C.byref(J), _pf(tj), _pf(oj),
+                                               _pf(values), _pf(vectors), C.byref(a2), C.byref(obj)))
+    res = {"pars": tj[:J.value].copy(), "obj_classes": oj[:J.value].copy(), "obj": obj.value, "a2": a2.value}
+    if return_eigenpair:
+        res["values"], res["vectors"] = values, vectors
+    return res
+
+
 def fit_nystrom_regression_sharded(X_local, n_total: int, row_offset: int, Y_local, m_total: int, s: int, K: int = -1,
                                    sigma: float = 1e-5, a2s=None, approach="posterior", subsample="kmeans",
                                    nstart: int = 1, *, pars: Optional[Sequence[float]] = None, init_idx=None,

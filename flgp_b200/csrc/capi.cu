@@ -733,6 +733,47 @@ void laplace_mode(const std::vector<double>& C11, const double* Y, int m, double
     for (int i = 0; i < m; ++i) beta[i + (size_t)m * j] = (sw[i] * beta[i + (size_t)m * j]) * sw[j];
 }
 
+// The m-sized half of posterior_distribution_classification as the logit drivers call it (src/Fit.cpp:563-582), from the
+// labelled rows Vh of the eigenvectors (m x KK row-major, the first K columns used) and ev = 1 - values:
+// C11 = V1 Lam V1^T + sigma I, Newton mode, then the two folded operators
+//   coef = Lam V1^T (Y - pi)   (KK, zero padded)        Mq = Lam - Lam V1^T beta V1 Lam   (KK x KK, zero padded)
+// so that for any row v of the eigenvectors  mean = v . coef  and  cov = v Mq v^T + sigma.
+void laplace_fold(const double* Vh, int KK, int K, const std::vector<double>& ev, const double* Yh, int m, double t,
+                  double sigma, double tol, int max_iter, std::vector<double>& coef, std::vector<double>& Mq) {
+  auto V = [&](int i, int k) { return Vh[(size_t)i * KK + k]; };
+  std::vector<double> lam(K);
+  for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * ev[k]);
+  std::vector<double> C11((size_t)m * m);
+  for (int j = 0; j < m; ++j)
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
+      C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
+    }
+  std::vector<double> pi, beta;
+  laplace_mode(C11, Yh, m, tol, max_iter, pi, beta);
+  std::vector<double> T1((size_t)m * K);
+  coef.assign(KK, 0.0);
+  Mq.assign((size_t)KK * KK, 0.0);
+  for (int k = 0; k < K; ++k) {
+    double acc = 0.0;
+    for (int i = 0; i < m; ++i) acc += V(i, k) * (Yh[i] - pi[i]);
+    coef[k] = lam[k] * acc;
+  }
+  for (int k = 0; k < K; ++k)  // T1 = beta V1 (m x K, column-major)
+    for (int i = 0; i < m; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += beta[i + (size_t)m * j] * V(j, k);
+      T1[i + (size_t)m * k] = acc;
+    }
+  for (int b2 = 0; b2 < K; ++b2)
+    for (int a2 = 0; a2 < K; ++a2) {
+      double acc = 0.0;
+      for (int i = 0; i < m; ++i) acc += V(i, a2) * T1[i + (size_t)m * b2];
+      Mq[a2 + (size_t)KK * b2] = (a2 == b2 ? lam[a2] : 0.0) - (lam[a2] * acc) * lam[b2];
+    }
+}
+
 // The n-sized half on a spectrum handle, folded like the GPR tail (C21 = V2 Lam V1^T is never formed):
 //   mean_i = V_i . (Lam V1^T (Y - pi)),   cov_i = V_i (Lam - Lam V1^T beta V1 Lam) V_i^T + sigma
 void classification_posterior_dev(flgp_spectrum* sp, const double* Ydev, int64_t m_total, int K, double t, double sigma,
@@ -757,36 +798,9 @@ void classification_posterior_dev(flgp_spectrum* sp, const double* Ydev, int64_t
   Vall.download(Vh.data(), Vh.size(), c->stream);
   sync(c);
   const double* Yh = Vh.data() + (size_t)m * KK;
-  auto V = [&](int i, int k) { return Vh[(size_t)i * KK + k]; };
-  std::vector<double> lam(K);
-  for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * (1.0 - sp->values[k]));
-  std::vector<double> C11((size_t)m * m);
-  for (int j = 0; j < m; ++j)
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
-      C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
-    }
-  std::vector<double> pi, beta;
-  laplace_mode(C11, Yh, m, tol, max_iter, pi, beta);
-  std::vector<double> coef(KK, 0.0), Mq((size_t)KK * KK, 0.0), T1((size_t)m * K);
-  for (int k = 0; k < K; ++k) {
-    double acc = 0.0;
-    for (int i = 0; i < m; ++i) acc += V(i, k) * (Yh[i] - pi[i]);
-    coef[k] = lam[k] * acc;
-  }
-  for (int k = 0; k < K; ++k)  // T1 = beta V1 (m x K, column-major)
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += beta[i + (size_t)m * j] * V(j, k);
-      T1[i + (size_t)m * k] = acc;
-    }
-  for (int b2 = 0; b2 < K; ++b2)
-    for (int a2 = 0; a2 < K; ++a2) {
-      double acc = 0.0;
-      for (int i = 0; i < m; ++i) acc += V(i, a2) * T1[i + (size_t)m * b2];
-      Mq[a2 + (size_t)KK * b2] = (a2 == b2 ? lam[a2] : 0.0) - (lam[a2] * acc) * lam[b2];
-    }
+  std::vector<double> ev(K), coef, Mq;
+  for (int k = 0; k < K; ++k) ev[k] = 1.0 - sp->values[k];
+  laplace_fold(Vh.data(), KK, K, ev, Yh, m, t, sigma, tol, max_iter, coef, Mq);
   DevBuf<double> dcoef(KK), dM((size_t)KK * KK);
   dcoef.upload(coef.data(), KK, c->stream);
   dM.upload(Mq.data(), (size_t)KK * KK, c->stream);
@@ -1901,6 +1915,236 @@ int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, cons
       if (obj_out) obj_out[j] = os[(size_t)bq * J + j];
     }
     if (out) *out = sp.release();
+  });
+}
+
+// fit_nystrom_logit_gp_cpp (src/Fit.cpp:896-1038) and the training half of fit_nystrom_logit_mult_gp_cpp
+// (src/Fit.cpp:1043-1150): the Nystrom grid of nystrom_fit with the logit trainings in place of MMA.  Single process.
+// J = 0: binary — t_io (NaN trains), Laplace posterior of the test rows, optional C = [Cvv + sigma I; Cnv] (n x m).
+// J > 0: the J one-vs-rest trainings per bandwidth, summed objective selects — t_out / obj_out of the winner.
+// values_out (K) / vectors_out (n x K column-major), optional: the winning extended eigenpair (what the reference's
+// prediction code consumes).
+static void nystrom_logit_run(Ctx* c, const double* X, const double* Y, const double* X_new, int64_t m, int64_t m_new,
+                              int d, int s, int K, const double* N, double sigma, const double* a2s, int n_a2,
+                              bool post, const char* subsample, int nstart, int iter_max, const int32_t* init_idx,
+                              uint64_t seed, int J, double* t_io, double* post_mean, double* post_cov, double* C_out,
+                              double* t_out, double* obj_out, double* values_out, double* vectors_out, double* best_a2,
+                              double* best_obj) {
+  const int64_t n = m + m_new;
+  need(m >= 1 && m <= 8192, "classification: need 1 <= m <= 8192 labelled rows");
+  DevBuf<double> dX = upload_concat(c, X, m, X_new, m_new, d);
+  flgp_spectrum base;  // anchors (src/Fit.cpp:919): subsample_cpp(...).leftCols(d)
+  base.c = c;
+  base.n_local = base.n_total = n;
+  base.d = d;
+  base.s = s;
+  base.r = 1;
+  const Models mo = make_models(subsample, "se", FLGP_GL_RW, 1, nstart, 0.1, iter_max);
+  stage_subsample(c, &base, dX.p, mo, init_idx, seed, nullptr);
+  base.sorted = KMeansSorted();
+  const double* U = base.U.p;
+  DevBuf<double> un(s), D((size_t)s * s);
+  double dmean = 0.0;
+  nys_anchor_distances_run(c, U, s, s, d, un.p, D.p, &dmean);
+  const int64_t nb_max = std::max<int64_t>(256, std::min<int64_t>(n, ((int64_t)64 << 20) / s));
+  DevBuf<double> Wx((size_t)std::min<int64_t>(nb_max, n) * s), V1((size_t)m * K);
+  struct Cand {
+    DevBuf<double> rs, Bt;
+    std::vector<double> lam;
+    double denom = 0.0;
+    LogitTrain T;
+  };
+  std::vector<Cand> cds(n_a2);
+  for (int q = 0; q < n_a2; ++q) {  // device side of the grid (src/Fit.cpp:942-968): anchor operator, labelled rows
+    Cand& cd = cds[q];
+    cd.rs.alloc(s);
+    cd.Bt.alloc((size_t)K * s);
+    cd.denom = a2s[q] * dmean;
+    DevBuf<double> lam(K);
+    nys_anchor_operator_run(c, D.p, s, K, cd.denom, cd.rs.p, lam.p, cd.Bt.p);
+    cd.lam.resize(K);
+    lam.download(cd.lam.data(), K, c->stream);
+    for (int64_t r0 = 0; r0 < m; r0 += nb_max) {
+      const int64_t nb = std::min<int64_t>(nb_max, m - r0);
+      nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, cd.rs.p, cd.denom, cd.Bt.p, K, Wx.p,
+                          V1.p + (size_t)r0 * K);
+    }
+    LogitTrain& T = cd.T;
+    T.m = (int)m;
+    T.K = K;
+    T.sigma = sigma;
+    T.posterior = post;
+    T.V.resize((size_t)m * K);
+    V1.download(T.V.data(), (size_t)m * K, c->stream);
+    sync(c);
+    T.ev.resize(K);
+    for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - cd.lam[k];
+    T.Y.assign(m, 0.0);
+    if (J == 0) T.Y.assign(Y, Y + m);
+    T.N.assign(m, 1.0);
+    if (N && J == 0) T.N.assign(N, N + m);
+  }
+  // the trainings: host work on m x K rows (src/Fit.cpp:970-990)
+  const bool fixed = J == 0 && (*t_io == *t_io);
+  const double t_fixed = J == 0 ? *t_io : 0.0;
+  const int Jn = std::max(J, 1);
+  std::vector<double> objs(n_a2), ts((size_t)n_a2 * Jn), os((size_t)n_a2 * Jn);
+  std::vector<std::string> errs(n_a2);
+  auto train_one = [&](int q) {
+    try {
+      const LogitTrain& T = cds[q].T;
+      if (J > 0) {
+        train_logit_classes(T, Y, m, J, &ts[(size_t)q * J], &os[(size_t)q * J]);
+        double sum = 0.0;
+        for (int j = 0; j < J; ++j) sum += os[(size_t)q * J + j];
+        objs[q] = sum;
+      } else if (fixed) {
+        ts[q] = t_fixed;
+        objs[q] = -logit_objective(T, t_fixed);
+      } else {
+        double fmin = 0.0;
+        auto fn = [&](double t) { return logit_objective(T, t); };
+        ts[q] = cobyla_minimize_1d(fn, 10.0, 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nullptr);
+        objs[q] = -fmin;
+      }
+    } catch (const std::exception& e) {
+      errs[q] = e.what();
+      if (errs[q].empty()) errs[q] = "training failed";
+    }
+  };
+  if (J == 0 && !fixed && n_a2 > 1) {
+    std::vector<std::thread> th;
+    for (int q = 0; q < n_a2; ++q) th.emplace_back(train_one, q);
+    for (auto& t : th) t.join();
+  } else {
+    for (int q = 0; q < n_a2; ++q) train_one(q);
+  }
+  for (int q = 0; q < n_a2; ++q)
+    if (!errs[q].empty()) fail(3, "%s", errs[q].c_str());
+  int bq = 0;
+  double max_obj = -std::numeric_limits<double>::infinity();
+  for (int q = 0; q < n_a2; ++q)
+    if (objs[q] > max_obj || q == 0) {  // src/Fit.cpp:992-998
+      max_obj = objs[q];
+      bq = q;
+    }
+  if (best_a2) *best_a2 = a2s[bq];
+  if (best_obj) *best_obj = max_obj;
+  Cand& best = cds[bq];
+  if (J > 0) {
+    for (int j = 0; j < J; ++j) {
+      t_out[j] = ts[(size_t)bq * J + j];
+      if (obj_out) obj_out[j] = os[(size_t)bq * J + j];
+    }
+  } else {
+    *t_io = ts[bq];
+  }
+  if (values_out) std::memcpy(values_out, best.lam.data(), sizeof(double) * K);
+  const bool want_post = J == 0 && post_mean;
+  if (!want_post && !vectors_out && !(J == 0 && C_out)) return;
+  // the winning bandwidth's extension of every row (src/Fit.cpp:1003-1010), in blocks; binary: Laplace posterior folded
+  // through coef / Mq (classification_posterior_dev), covariance block C = V Lam V1^T
+  DevBuf<double> dcoef, dM, dlamt, V1b, Cdev;
+  const double t = J == 0 ? *t_io : 0.0;
+  if (J == 0) {
+    std::vector<double> coef, Mq, lamt(K);
+    if (want_post) {
+      laplace_fold(best.T.V.data(), K, K, best.T.ev, Y, (int)m, t, sigma, 1e-5, 100, coef, Mq);
+      dcoef.alloc(K);
+      dM.alloc((size_t)K * K);
+      dcoef.upload(coef.data(), K, c->stream);
+      dM.upload(Mq.data(), (size_t)K * K, c->stream);
+    }
+    if (C_out) {
+      for (int k = 0; k < K; ++k) lamt[k] = std::exp(-t * best.T.ev[k]);
+      dlamt.alloc(K);
+      dlamt.upload(lamt.data(), K, c->stream);
+      V1b.alloc((size_t)m * K);
+      V1b.upload(best.T.V.data(), (size_t)m * K, c->stream);
+      Cdev.alloc((size_t)n * m);
+    }
+  }
+  const int64_t nbv = std::min<int64_t>(nb_max, n);
+  DevBuf<double> Vb((size_t)nbv * K), Tb((size_t)nbv * K), dmean_all(n), dcov_all(n);
+  std::vector<double> blk;
+  for (int64_t r0 = 0; r0 < n; r0 += nb_max) {
+    const int64_t nb = std::min<int64_t>(nb_max, n - r0);
+    nys_extend_rows_run(c, dX.p, n, r0, nb, d, U, s, s, un.p, best.rs.p, best.denom, best.Bt.p, K, Wx.p, Vb.p);
+    if (want_post) {
+      gemv_run(c, Vb.p, dcoef.p, nb, K, dmean_all.p + r0);
+      gemm_nn_run(c, Vb.p, dM.p, nb, K, K, Tb.p);  // Mq symmetric up to rounding, as in classification_posterior_dev
+      nys_rowdot_run(c, Tb.p, Vb.p, nb, K, sigma, dcov_all.p + r0);
+    }
+    if (J == 0 && C_out) gemm_nt_run(c, Vb.p, V1b.p, dlamt.p, nb, m, K, Cdev.p + r0, n);
+    if (vectors_out) {
+      blk.resize((size_t)nb * K);
+      Vb.download(blk.data(), (size_t)nb * K, c->stream);
+      sync(c);
+      for (int64_t i = 0; i < nb; ++i)
+        for (int k = 0; k < K; ++k) vectors_out[(r0 + i) + n * (int64_t)k] = blk[(size_t)i * K + k];
+    }
+  }
+  if (want_post) {
+    std::vector<double> mean(n), cov(n);
+    dmean_all.download(mean.data(), n, c->stream);
+    dcov_all.download(cov.data(), n, c->stream);
+    sync(c);
+    if (m_new) std::memcpy(post_mean, mean.data() + m, sizeof(double) * m_new);
+    if (post_cov && m_new) std::memcpy(post_cov, cov.data() + m, sizeof(double) * m_new);
+  }
+  if (J == 0 && C_out) {
+    Cdev.download(C_out, (size_t)n * m, c->stream);
+    sync(c);
+    for (int64_t i = 0; i < m; ++i) C_out[i + n * i] += sigma;  // Cvv.diagonal() += sigma (src/Fit.cpp:1015)
+  }
+  sync(c);
+}
+
+int flgp_fit_nystrom_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                           int64_t m_new, int d, int s, int K, const double* N, double sigma, const double* a2s,
+                           int n_a2, const char* approach, const char* subsample, int nstart, int iter_max,
+                           const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
+                           double* C_out, double* best_a2, double* best_obj) {
+  return guard([&] {
+    need(ctx && X && Y && t_io && a2s, "null argument");
+    need(m >= 1 && m_new >= 0 && d >= 1 && n_a2 >= 1, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = on_device(&ctx->c);
+    need(c->nranks == 1, "flgp_fit_nystrom_logit is the single-process entry point");
+    const int64_t n = m + m_new;
+    need(s >= 1 && s <= n && n < ((int64_t)1 << 31), "need 1 <= s <= n");
+    if (K < 0) K = s;
+    need(K >= 1 && K <= s, "need 1 <= K <= s");
+    nystrom_logit_run(c, X, Y, X_new, m, m_new, d, s, K, N, sigma, a2s, n_a2, post, subsample, nstart, iter_max,
+                      init_idx, seed, 0, t_io, post_mean, post_cov, C_out, nullptr, nullptr, nullptr, nullptr, best_a2,
+                      best_obj);
+  });
+}
+
+int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
+                                const char* approach, const char* subsample, int nstart, int iter_max,
+                                const int32_t* init_idx, uint64_t seed, int J_cap, int* J_out, double* t_out,
+                                double* obj_out, double* values_out, double* vectors_out, double* best_a2,
+                                double* best_obj) {
+  return guard([&] {
+    need(ctx && X && Y && a2s && J_out && t_out, "null argument");
+    need(m >= 1 && m_new >= 0 && d >= 1 && n_a2 >= 1, "bad matrix shape");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    Ctx* c = on_device(&ctx->c);
+    need(c->nranks == 1, "flgp_fit_nystrom_logit_mult is the single-process entry point");
+    const int64_t n = m + m_new;
+    need(s >= 1 && s <= n && n < ((int64_t)1 << 31), "need 1 <= s <= n");
+    if (K < 0) K = s;
+    need(K >= 1 && K <= s, "need 1 <= K <= s");
+    const int J = multi_class_count(Y, m);
+    *J_out = J;
+    need(J <= J_cap, "more classes than the output arrays hold");
+    nystrom_logit_run(c, X, Y, X_new, m, m_new, d, s, K, nullptr, sigma, a2s, n_a2, post, subsample, nstart, iter_max,
+                      init_idx, seed, J, nullptr, nullptr, nullptr, nullptr, t_out, obj_out, values_out, vectors_out,
+                      best_a2, best_obj);
   });
 }
 

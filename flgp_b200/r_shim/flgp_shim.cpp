@@ -344,6 +344,34 @@ Rcpp::List fit_se_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector 
   return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
 }
 
+// fit_nystrom_logit_gp_cpp (src/Fit.cpp:896-1038), signature unchanged: Nystrom grid, COBYLA training of t per bandwidth
+// and the Laplace posterior behind the C ABI; labels from the reference's sampler on the returned covariance block.
+Rcpp::List fit_nystrom_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                    int s, int K, Rcpp::NumericVector N_train, double sigma, std::vector<double> a2s,
+                                    std::string approach, std::string subsample, bool output_cov, int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const Eigen::Map<Eigen::VectorXd> N(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(N_train));
+  const int m = X.rows(), m_new = X_new.rows();
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  double t = NA_REAL, a2 = 0.0, obj = 0.0;  // NaN: train
+  Eigen::VectorXd mean(m_new), cov(m_new);
+  Eigen::MatrixXd C(m + m_new, m);
+  ok(flgp_fit_nystrom_logit(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, K, N.data(), sigma,
+                            a2s.data(), (int)a2s.size(), approach.c_str(), subsample.c_str(), nstart, 100, init.data(), 0,
+                            &t, mean.data(), cov.data(), C.data(), &a2, &obj));
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", t = " << t
+              << ", the objective function is " << obj << "\n";
+  Eigen::VectorXd label = Rcpp::as<Eigen::VectorXd>(test_pgbinary_cpp(C.topRows(m), Y, C)["Y_pred"]);
+  Rcpp::List Y_pred = Rcpp::List::create(Rcpp::Named("train") = label.head(m), Rcpp::Named("test") = label.tail(m_new));
+  Rcpp::List post = Rcpp::List::create(Rcpp::Named("mean") = mean, Rcpp::Named("cov") = cov);
+  if (output_cov)
+    return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("C") = C, Rcpp::Named("posterior") = post,
+                              Rcpp::Named("pars") = t);
+  return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post, Rcpp::Named("pars") = t);
+}
+
 // train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53) for fit_lae_logit_mult_gp_cpp (src/Fit.cpp:603-662): the J
 // one-vs-rest trainings run behind the C ABI on the spectrum handle; the MultiClassifier keeps the reference's layout
 // (aug_y + one ReturnValue(t, obj) per class), so predict_logit_mult_gp_cpp (Polya-Gamma sampler, R RNG) is unchanged.
@@ -374,6 +402,28 @@ std::vector<ReturnValue> se_logit_mult_grid(const Eigen::MatrixXd& X, const Eige
                             (int)a2s.size(), approach.c_str(), sub.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
                             Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, 256, &J, t.data(), obj.data(),
                             best_a2, max_obj, best));
+  std::vector<ReturnValue> res(J);
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  return res;
+}
+
+// The grid loop of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1088-1147) as one call: per-class ReturnValues and the
+// winning extended EigenPair (values K, vectors n x K); predict_logit_mult_gp_cpp goes on unchanged from there.
+std::vector<ReturnValue> nystrom_logit_mult_grid(const Eigen::MatrixXd& X, const Eigen::VectorXd& Y,
+                                                 const Eigen::MatrixXd& X_new, int s, int K, double sigma,
+                                                 const std::vector<double>& a2s, const std::string& approach,
+                                                 const std::string& subsample, int nstart, Eigen::VectorXd& values,
+                                                 Eigen::MatrixXd& vectors, double* best_a2, double* max_obj) {
+  const int m = X.rows(), m_new = X_new.rows();
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  values.resize(K);
+  vectors.resize(m + m_new, K);
+  int J = 0;
+  std::vector<double> t(256), obj(256);
+  ok(flgp_fit_nystrom_logit_mult(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, K, sigma,
+                                 a2s.data(), (int)a2s.size(), approach.c_str(), subsample.c_str(), nstart, 100,
+                                 init.data(), 0, 256, &J, t.data(), obj.data(), values.data(), vectors.data(), best_a2,
+                                 max_obj));
   std::vector<ReturnValue> res(J);
   for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
   return res;

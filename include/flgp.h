@@ -305,6 +305,27 @@ int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, cons
                            const int32_t* init_idx, uint64_t seed, int J_cap, int* J_out, double* t_out,
                            double* obj_out, double* best_a2, double* best_obj, flgp_spectrum** out);
 
+/* fit_nystrom_logit_gp_cpp (src/Fit.cpp:896-1038) without the label sampler: the Nystrom grid of
+ * flgp_fit_nystrom_regression (anchors, dense SE anchor kernel, eigs_sym, extension of the labelled rows) with the COBYLA
+ * training of t per bandwidth; then the winning extension of every row, posterior_distribution_classification on the
+ * test rows (post_mean / post_cov, m_new each, may be NULL) and, if C_out != NULL, the n x m block [Cvv + sigma I; Cnv].
+ * *t_io = NaN trains, a finite value is used at every bandwidth as given.  Single process. */
+int flgp_fit_nystrom_logit(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                           int64_t m_new, int d, int s, int K, const double* N, double sigma, const double* a2s,
+                           int n_a2, const char* approach, const char* subsample, int nstart, int iter_max,
+                           const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
+                           double* C_out, double* best_a2, double* best_obj);
+/* The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+ * trainings on the extended labelled rows, summed objective selects.  t_out / obj_out (J_cap entries) of the winner;
+ * values_out (K) and vectors_out (n x K column-major), both optional: the winning extended eigenpair, which is what
+ * predict_logit_mult_gp_cpp (Polya-Gamma sampler, stays in R) consumes. */
+int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                int64_t m_new, int d, int s, int K, double sigma, const double* a2s, int n_a2,
+                                const char* approach, const char* subsample, int nstart, int iter_max,
+                                const int32_t* init_idx, uint64_t seed, int J_cap, int* J_out, double* t_out,
+                                double* obj_out, double* values_out, double* vectors_out, double* best_a2,
+                                double* best_obj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -648,6 +648,90 @@ def _sqdist(A, B):
     return ((-2.0 * dot) + an[:, None]) + bn[None, :]
 
 
+def _nystrom_grid(X, X_new, s, K, init_idx, a2s, iter_max, nthreads):
+    """The part the fit_nystrom_* drivers share (src/Fit.cpp:242-292, 919-968), dense and literal: anchors, the doubly
+    normalised SE anchor kernel per bandwidth, its top-K eigenpairs (RSpectra::eigs_sym -> LAPACK), the rescaled anchor
+    eigenvectors and the extension formula.  Yields (a2, values, extend) with extend(D rows x s) -> rows x K."""
+    X_all = np.asfortranarray(np.vstack([X, X_new]))
+    U = kmeans_lloyd(X_all, s, init_idx, iter_max, nthreads)[0][:, :-1]
+    D_UU = _sqdist(U, U)
+    D_all = _sqdist(X_all, U)
+    dmean = D_UU.sum() / (s * s)
+    for a2 in a2s:
+        Z_UU = np.exp(-D_UU / (a2 * dmean))
+        rs = Z_UU.sum(axis=1) + 1e-9
+        A_UU = (1.0 / rs)[:, None] * Z_UU * (1.0 / rs)[None, :]
+        sdi = 1.0 / np.sqrt(A_UU.sum(axis=1) + 1e-9)
+        W_UU = sdi[:, None] * A_UU * sdi[None, :]
+        w, Q = np.linalg.eigh((W_UU + W_UU.T) / 2)
+        values, vecs = w[::-1][:K].copy(), Q[:, ::-1][:, :K].copy()
+        vecs = sdi[:, None] * vecs
+        vecs = np.sqrt(s) * vecs * (1.0 / (np.linalg.norm(vecs, axis=0) + 1e-9))[None, :]
+
+        def extend(Dx, a2=a2, rs=rs, vecs=vecs, values=values):  # bound now: the closure outlives the loop
+            Zx = np.exp(-Dx / (a2 * dmean))
+            Ax = (1.0 / (Zx.sum(axis=1) + 1e-9))[:, None] * Zx * (1.0 / rs)[None, :]
+            Wx = (1.0 / (Ax.sum(axis=1) + 1e-9))[:, None] * Ax
+            return Wx @ vecs * (1.0 / (np.abs(values) + 1e-9))[None, :]
+
+        yield a2, values, extend, D_all
+
+
+def fit_nystrom_logit(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-3, approach="posterior", iter_max=100, nthreads=1,
+                      N=None, t=None):
+    """fit_nystrom_logit_gp_cpp (src/Fit.cpp:896-1038) without the label sampler: per bandwidth the diffusion time
+    trained on the extended labelled rows (t given: the objective at t); Laplace posterior of the test rows from the
+    winning extension (:1003-1022)."""
+    m = len(X)
+    n = m + len(X_new)
+    if K < 0:
+        K = s
+    idx0 = np.arange(m, dtype=np.int32)
+    idx1 = np.arange(m, n, dtype=np.int32)
+    best = None
+    for a2, values, extend, D_all in _nystrom_grid(X, X_new, s, K, init_idx, a2s, iter_max, nthreads):
+        Vm = extend(D_all[:m])
+        if t is None:
+            tq, obj, _ = train_lae_logit(Vm, values, Y, idx0, K, sigma, approach, N=N)
+        else:
+            tq, obj = t, -logit_objective(Vm, values, Y, idx0, K, t, sigma, approach, N)
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, t=tq, a2=a2, values=values, extend=extend)
+    V = best["extend"](D_all)
+    values, tq = best["values"], best["t"]
+    C11 = hk_from_spectrum(V, values, K, tq, idx0, idx0)
+    C11[np.diag_indices(m)] += sigma
+    C21 = hk_from_spectrum(V, values, K, tq, idx1, idx0)
+    C22 = ((V[m:, :K] * np.exp(-tq * (1.0 - values[:K]))) * V[m:, :K]).sum(axis=1) + sigma
+    best["mean"], best["cov"] = posterior_distribution_classification(C11, C21, C22, Y)
+    best["C"] = np.vstack([C11, C21])
+    best["V"] = V
+    del best["extend"]
+    return best
+
+
+def fit_nystrom_logit_mult(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-3, approach="posterior", iter_max=100,
+                           nthreads=1):
+    """The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+    trainings on the extended labelled rows; the summed objective selects."""
+    m = len(X)
+    if K < 0:
+        K = s
+    idx0 = np.arange(m, dtype=np.int32)
+    best = None
+    for a2, values, extend, D_all in _nystrom_grid(X, X_new, s, K, init_idx, a2s, iter_max, nthreads):
+        Vm = extend(D_all[:m])
+        ts, objs = train_logit_mult(Vm, values, Y, idx0, K, sigma, approach)
+        obj = 0.0
+        for o in objs:
+            obj += o
+        if best is None or obj > best["obj"]:
+            best = dict(obj=obj, t=ts, objs=objs, a2=a2, values=values, extend=extend)
+    best["V"] = best["extend"](D_all)
+    del best["extend"]
+    return best
+
+
 def fit_nystrom_regression(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-5, approach="posterior", iter_max=100,
                            nthreads=1, pars=None):
     """fit_nystrom_regression_gp_cpp (src/Fit.cpp:222-357), dense and literal; RSpectra::eigs_sym replaced by LAPACK

@@ -1105,6 +1105,57 @@ def test_fit_se_logit_mult_three_classes_grid(flgp, oracle):
     assert np.mean(res["argmax_posterior_mean"] == lab[m:]) > 0.55   # 12 % of the held-out labels are noise (chance: 0.33)
 
 
+def test_fit_nystrom_logit_grid(flgp, oracle):
+    """fit_nystrom_logit_gp_rcpp (src/Fit.cpp:896-1038) against the oracle's dense literal restatement on rings with
+    noisy labels: at a fixed t the same winning bandwidth, objective to 1e-6, Laplace posterior and the covariance block
+    to 1e-5 (the dense s x s normalisation and the n x s x K extension accumulate in different orders, as for the
+    regression driver); trained: same bandwidth, t to optimiser tolerance."""
+    X, lab = _noisy_rings(2400, 4, 2, 5)
+    m, s, K, sigma = 120, 240, 60, 1e-3
+    init = _init(len(X), s, 1)
+    a2s = np.array([0.1, 0.5, 2.0, 10.0])
+    res = flgp.fit_nystrom_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, K, sigma=sigma, a2s=a2s, t=8.0, init_idx=init,
+                                         iter_max=50, output_cov=True)
+    ref = oracle.fit_nystrom_logit(X[:m], lab[:m], X[m:], s, K, init, a2s, sigma=sigma, iter_max=50, nthreads=NT, t=8.0)
+    assert res["a2"] == ref["a2"] and res["pars"] == 8.0
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-6)
+    sc = max(1.0, np.abs(ref["mean"]).max())
+    np.testing.assert_allclose(res["posterior"]["mean"], ref["mean"], rtol=1e-5, atol=1e-6 * sc)
+    np.testing.assert_allclose(res["posterior"]["cov"], ref["cov"], rtol=1e-5, atol=1e-6 * max(1.0, np.abs(ref["cov"]).max()))
+    np.testing.assert_allclose(res["C"], ref["C"], rtol=1e-5, atol=1e-6 * max(1.0, np.abs(ref["C"]).max()))
+    res = flgp.fit_nystrom_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, K, sigma=sigma, a2s=a2s, init_idx=init, iter_max=50)
+    ref = oracle.fit_nystrom_logit(X[:m], lab[:m], X[m:], s, K, init, a2s, sigma=sigma, iter_max=50, nthreads=NT)
+    assert res["a2"] == ref["a2"]
+    assert abs(res["pars"] - ref["t"]) <= 2e-3 * max(1.0, ref["t"])
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-6, atol=1e-6)
+    assert np.mean((res["posterior"]["mean"] > 0) == (lab[m:] > 0.5)) > 0.6
+    with pytest.raises(flgp.FlgpError, match="not supported"):
+        flgp.fit_nystrom_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, K, approach="evidence", init_idx=init)
+
+
+def test_fit_nystrom_logit_mult_grid(flgp, oracle):
+    """The training half of fit_nystrom_logit_mult_gp_rcpp (src/Fit.cpp:1045-1162): per bandwidth the J one-vs-rest
+    trainings on the extended labelled rows, the summed objective selects; the winning extended eigenpair is returned
+    for the reference's sampler (eigenvalues 1e-8; the eigenvectors reproduce the oracle's heat kernel on the labelled
+    rows)."""
+    X, lab = _noisy_rings(2400, 6, 3, 7)
+    m, s, K, sigma = 150, 240, 60, 1e-3
+    init = _init(len(X), s, 1)
+    a2s = np.array([0.1, 0.5, 2.0, 10.0])
+    res = flgp.fit_nystrom_logit_mult_gp_rcpp(X[:m], lab[:m], X[m:], s, K, sigma=sigma, a2s=a2s, init_idx=init,
+                                              iter_max=50, return_eigenpair=True)
+    ref = oracle.fit_nystrom_logit_mult(X[:m], lab[:m], X[m:], s, K, init, a2s, sigma=sigma, iter_max=50, nthreads=NT)
+    assert res["a2"] == ref["a2"] and len(res["pars"]) == 3
+    np.testing.assert_allclose(res["pars"], ref["t"], rtol=2e-3)
+    np.testing.assert_allclose(res["obj_classes"], ref["objs"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["obj"], ref["obj"], rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(res["values"], ref["values"], rtol=1e-8, atol=1e-12)
+    idx0 = np.arange(m, dtype=np.int32)
+    Hl = oracle.hk_from_spectrum(res["vectors"], res["values"], K, 5.0, idx0, idx0)
+    Ho = oracle.hk_from_spectrum(ref["V"], ref["values"], K, 5.0, idx0, idx0)
+    np.testing.assert_allclose(Hl, Ho, rtol=1e-5, atol=1e-6 * np.abs(Ho).max())
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("nbytes", [(8 << 20) - 8, 8 << 20, (8 << 20) + 8, (37 << 20) + 4088, 200 << 20])
 def test_staged_pageable_copies_roundtrip(flgp, nbytes):

@@ -178,3 +178,31 @@ def test_se_logit_grid_twins_select_the_largest_objective(oracle):
     sums = [oracle.train_logit_mult(V, values, lab3[:m], idx0, K, 1e-3, "posterior")[1].sum() for _, values, V in grid[:2]]
     assert mult["a2"] == a2s[int(np.argmax(sums))] and abs(mult["obj"] - max(sums)) <= 1e-12 * abs(max(sums))
     assert len(mult["t"]) == 3
+
+
+def test_nystrom_logit_twins_select_the_largest_objective(oracle):
+    """The oracle twins of fit_nystrom_logit_gp_cpp / fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:942-998, 1088-1132)
+    against their own pieces: grid selection by the largest (summed) objective, a fixed t evaluates the objective there,
+    the regression twin's extension is the one the logit twins train on."""
+    rng = np.random.default_rng(8)
+    n, m, s, K = 500, 40, 50, 15
+    ang = rng.uniform(0, 2 * np.pi, n)
+    ring = rng.integers(0, 4, n)
+    rad = 0.5 + 0.25 * ring + 0.05 * rng.standard_normal(n)
+    X = np.asfortranarray(np.stack([rad * np.cos(ang), rad * np.sin(ang)], axis=1))
+    lab = np.where(rng.uniform(size=n) < 0.15, 1 - ring % 2, ring % 2).astype(np.float64)
+    init = np.sort(rng.choice(n, s, replace=False)).astype(np.int32)
+    a2s = np.array([0.3, 3.0])
+    idx0 = np.arange(m, dtype=np.int32)
+    grid = [(a2, values, extend(D_all[:m])) for a2, values, extend, D_all in
+            oracle._nystrom_grid(X[:m], X[m:], s, K, init, a2s, 30, 2)]
+    objs = [-oracle.logit_objective(Vm, values, lab[:m], idx0, K, 4.0, 1e-3, "marginal") for _, values, Vm in grid]
+    ref = oracle.fit_nystrom_logit(X[:m], lab[:m], X[m:], s, K, init, a2s, approach="marginal", iter_max=30, nthreads=2,
+                                   t=4.0)
+    assert ref["a2"] == a2s[int(np.argmax(objs))] and ref["obj"] == max(objs)
+    assert ref["V"].shape == (n, K) and ref["C"].shape == (n, m) and np.all(np.isfinite(ref["mean"]))
+    lab3 = (ring % 3).astype(np.float64)
+    lab3[:3] = [0, 1, 2]
+    mult = oracle.fit_nystrom_logit_mult(X[:m], lab3[:m], X[m:], s, K, init, a2s, iter_max=30, nthreads=2)
+    sums = [oracle.train_logit_mult(Vm, values, lab3[:m], idx0, K, 1e-3, "posterior")[1].sum() for _, values, Vm in grid]
+    assert mult["a2"] == a2s[int(np.argmax(sums))] and abs(mult["obj"] - max(sums)) <= 1e-12 * abs(max(sums))
