@@ -550,6 +550,53 @@ def cobyla_minimize_1d(f, x0: float, lb: float = 1e-3, ub: float = float("inf"),
     return float(x[0]), minf.value, nev.value
 
 
+def marginal_log_likelihood_logit_la_cpp(Cm, Y, N=None, tol: float = 1e-5, max_iter: int = 100) -> float:
+    """marginal_log_likelihood_logit_la_cpp (src/train.cpp:716-760; exported): Laplace-approximate marginal
+    log-likelihood of the labelled rows for the m x m covariance Cm.  Host only."""
+    Cm = _f64(Cm)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    out = C.c_double()
+    check(_lib.load().flgp_marginal_log_likelihood_logit_la(_pf(Cm), _pf(Y), _pf(Nv), Y.size, tol, max_iter,
+                                                            C.byref(out)))
+    return out.value
+
+
+def multi_train_split(Y) -> np.ndarray:
+    """multi_train_split (src/MultiClassification.cpp:14-27): m x J one-vs-rest indicator matrix, J = max(Y) + 1."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    J = C.c_int()
+    check(_lib.load().flgp_multi_train_split(_pf(Y), Y.size, 0, C.byref(J), None))
+    aug = np.zeros((Y.size, J.value), order="F")
+    check(_lib.load().flgp_multi_train_split(_pf(Y), Y.size, J.value, C.byref(J), _pf(aug)))
+    return aug
+
+
+def negative_log_likelihood(mean, cov, target, type: str = "regression") -> float:
+    """negative_log_likelihood (src/Utils.cpp:302-318), type "regression" (the other types sample from R's RNG)."""
+    mean = np.ascontiguousarray(mean, dtype=np.float64).reshape(-1)
+    cov = np.ascontiguousarray(cov, dtype=np.float64).reshape(-1)
+    target = np.ascontiguousarray(target, dtype=np.float64).reshape(-1)
+    if not (mean.size == cov.size == target.size):
+        raise FlgpError("negative_log_likelihood: mean, cov and target must have the same length")
+    out = C.c_double()
+    check(_lib.load().flgp_negative_log_likelihood(_pf(mean), _pf(cov), _pf(target), mean.size, _b(type), C.byref(out)))
+    return out.value
+
+
+def test_regression_cpp(Cm, Y, Cnv) -> np.ndarray:
+    """test_regression_cpp (src/Predict.cpp:29-37): Cnv C^{-1} Y by Cholesky.  Host only."""
+    Cm = _f64(Cm)
+    Cnv = _f64(Cnv)
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    out = np.zeros(Cnv.shape[0])
+    check(_lib.load().flgp_test_regression(_pf(Cm), _pf(Y), _pf(Cnv), Y.size, Cnv.shape[0], _pf(out)))
+    return out
+
+
+test_regression_cpp.__test__ = False  # the reference's export name; not a pytest case
+
+
 def logit_objective(eigenpair: EigenPair, Y, m_total: int, K: int, t: float, sigma: float = 1e-3,
                     approach: str = "posterior", N=None) -> float:
     """negative_marginal_likelihood_logit_cpp / negative_log_posterior_logit_cpp at diffusion time t

@@ -2148,6 +2148,66 @@ int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y,
   });
 }
 
+// ---- the small host-side exports of the reference (no device work: m-sized dense algebra, as in the reference) -------
+int flgp_marginal_log_likelihood_logit_la(const double* Cm, const double* Y, const double* N, int m, double tol,
+                                          int max_iter, double* out) {
+  return guard([&] {
+    need(Cm && Y && out, "null argument");
+    need(m >= 1 && m <= 8192, "classification: need 1 <= m <= 8192 labelled rows");
+    std::vector<double> Cv(Cm, Cm + (size_t)m * m), ones;
+    if (!N) {
+      ones.assign(m, 1.0);
+      N = ones.data();
+    }
+    *out = laplace_mll(Cv, Y, N, m, tol > 0.0 ? tol : 1e-5, max_iter > 0 ? max_iter : 100);
+  });
+}
+
+int flgp_multi_train_split(const double* Y, int64_t m, int J_cap, int* J_out, double* aug_y) {
+  return guard([&] {
+    need(Y && J_out, "null argument");
+    need(m >= 1, "bad matrix shape");
+    const int J = multi_class_count(Y, m);
+    *J_out = J;
+    if (!aug_y) return;
+    need(J <= J_cap, "more classes than the output array holds");
+    for (int j = 0; j < J; ++j)
+      for (int64_t i = 0; i < m; ++i) aug_y[i + m * (int64_t)j] = (Y[i] == (double)j) ? 1.0 : 0.0;
+  });
+}
+
+int flgp_negative_log_likelihood(const double* mean, const double* cov, const double* target, int64_t n,
+                                 const char* type, double* out) {
+  return guard([&] {
+    need(mean && cov && target && out && type, "null argument");
+    need(n >= 1, "bad matrix shape");
+    if (std::string(type) != "regression")
+      fail(2, "negative_log_likelihood: only type = \"regression\" is deterministic; \"binary\" / \"multinomial\" draw "
+              "rnorm samples from R's RNG and stay in R");
+    double acc = 0.0;  // ((target - mean)^2 / cov + log(cov + 1e-9)).mean(), sequential
+    for (int64_t i = 0; i < n; ++i) {
+      const double df = target[i] - mean[i];
+      acc += df * df / cov[i] + std::log(cov[i] + 1e-9);
+    }
+    *out = (acc / (double)n + std::log(2 * 3.1415926)) / 2;  // the reference's literal constant (src/Utils.cpp:306)
+  });
+}
+
+int flgp_test_regression(const double* Cm, const double* Y, const double* Cnv, int m, int64_t m_new, double* Y_pred) {
+  return guard([&] {
+    need(Cm && Y && Y_pred && (Cnv || m_new == 0), "null argument");
+    need(m >= 1 && m <= 8192 && m_new >= 0, "test_regression: need 1 <= m <= 8192 training rows");
+    std::vector<double> L(Cm, Cm + (size_t)m * m), alpha(Y, Y + m);
+    if (!chol_lower(L, m)) fail(2, "regression: m x m covariance is not positive definite");
+    chol_solve(L, m, alpha.data(), 1);
+    for (int64_t i = 0; i < m_new; ++i) {
+      double acc = 0.0;
+      for (int j = 0; j < m; ++j) acc += Cnv[i + m_new * (int64_t)j] * alpha[j];
+      Y_pred[i] = acc;
+    }
+  });
+}
+
 int flgp_classification_posterior_fixed(flgp_spectrum* h, const double* Y_local, int64_t m_total, int K, double t,
                                         double sigma, double tol, int max_iter, double* mean, double* cov) {
   return guard([&] {

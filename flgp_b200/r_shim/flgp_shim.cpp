@@ -429,6 +429,27 @@ std::vector<ReturnValue> nystrom_logit_mult_grid(const Eigen::MatrixXd& X, const
   return res;
 }
 
+// The small exported helpers, signatures unchanged (src/train.h, src/MultiClassification.h, src/Utils.h, src/Predict.h)
+double marginal_log_likelihood_logit_la_cpp(const Eigen::MatrixXd& C, const Eigen::VectorXd& Y, const Eigen::VectorXd& N,
+                                            double tol, int max_iter) {
+  double out = 0.0;
+  ok(flgp_marginal_log_likelihood_logit_la(C.data(), Y.data(), N.data(), (int)Y.size(), tol, max_iter, &out));
+  return out;
+}
+Eigen::MatrixXd multi_train_split(const Eigen::VectorXd& Y) {
+  int J = 0;
+  ok(flgp_multi_train_split(Y.data(), Y.size(), 0, &J, nullptr));
+  Eigen::MatrixXd aug(Y.size(), J);
+  ok(flgp_multi_train_split(Y.data(), Y.size(), J, &J, aug.data()));
+  return aug;
+}
+Eigen::VectorXd test_regression_cpp(const Eigen::MatrixXd& C, const Eigen::VectorXd& Y, const Eigen::MatrixXd& Cnv) {
+  Eigen::VectorXd out(Cnv.rows());
+  ok(flgp_test_regression(C.data(), Y.data(), Cnv.data(), (int)Y.size(), Cnv.rows(), out.data()));
+  return out;
+}
+// negative_log_likelihood: type == "regression" -> flgp_negative_log_likelihood; the sampled types keep the reference body.
+
 // [[Rcpp::export(posterior_distribution_classification)]]  -- signature unchanged (src/Utils.h:77-80)
 Rcpp::List posterior_distribution_classification(const Eigen::MatrixXd& C11, const Eigen::MatrixXd& C21,
                                                  const Eigen::VectorXd& C22, const Eigen::VectorXd& Y, double tol,

@@ -326,6 +326,23 @@ int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y,
                                 double* obj_out, double* values_out, double* vectors_out, double* best_a2,
                                 double* best_obj);
 
+/* ---- the reference's small exported helpers: m-sized dense host algebra, no device work (usable without a context) -- */
+/* marginal_log_likelihood_logit_la_cpp(C, Y, N, tol, max_iter) (src/train.cpp:716-760; export src/RcppExports.cpp:457-469):
+ * Laplace-approximate marginal log-likelihood of the m labelled rows for the covariance C (m x m, column-major);
+ * N = trials per row (NULL = all 1); tol <= 0 / max_iter <= 0 take the reference's defaults 1e-5 / 100. */
+int flgp_marginal_log_likelihood_logit_la(const double* C, const double* Y, const double* N, int m, double tol,
+                                          int max_iter, double* out);
+/* multi_train_split (src/MultiClassification.cpp:14-27): J = max(Y) + 1, aug_y (m x J column-major, may be NULL to
+ * query J) = one-vs-rest indicator columns. */
+int flgp_multi_train_split(const double* Y, int64_t m, int J_cap, int* J_out, double* aug_y);
+/* negative_log_likelihood(mean, cov, target, type) (src/Utils.cpp:302-318), type "regression": the mean over the rows of
+ * ((target - mean)^2 / cov + log(cov + 1e-9)), plus log(2 * 3.1415926), halved.  "binary" / "multinomial" average over
+ * rnorm draws from R's RNG (nll_classification, :321-336): not deterministic, rejected with status 2. */
+int flgp_negative_log_likelihood(const double* mean, const double* cov, const double* target, int64_t n,
+                                 const char* type, double* out);
+/* test_regression_cpp(C, Y, Cnv) (src/Predict.cpp:29-37): Y_pred = Cnv C^{-1} Y by Cholesky; C m x m, Cnv m_new x m. */
+int flgp_test_regression(const double* C, const double* Y, const double* Cnv, int m, int64_t m_new, double* Y_pred);
+
 #ifdef __cplusplus
 }
 #endif

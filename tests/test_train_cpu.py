@@ -206,3 +206,37 @@ def test_nystrom_logit_twins_select_the_largest_objective(oracle):
     mult = oracle.fit_nystrom_logit_mult(X[:m], lab3[:m], X[m:], s, K, init, a2s, iter_max=30, nthreads=2)
     sums = [oracle.train_logit_mult(Vm, values, lab3[:m], idx0, K, 1e-3, "posterior")[1].sum() for _, values, Vm in grid]
     assert mult["a2"] == a2s[int(np.argmax(sums))] and abs(mult["obj"] - max(sums)) <= 1e-12 * abs(max(sums))
+
+
+def test_small_host_exports_match_the_oracle(oracle):
+    """The reference's small exported helpers behind the C ABI (host algebra, usable without a GPU):
+    marginal_log_likelihood_logit_la_cpp against the oracle's laplace_mll, multi_train_split, negative_log_likelihood
+    (type "regression", the reference's literal constant), test_regression_cpp against a dense solve."""
+    V, values, Y, idx = _toy_logit_problem(seed=5, m=50, K=20)
+    K = V.shape[1]
+    Cm = oracle.hk_from_spectrum(V, values, K, 6.0, idx, idx)
+    Cm[np.diag_indices(len(idx))] += 1e-3
+    N = np.where(np.arange(len(idx)) % 3 == 0, 2.0, 1.0)
+    Yn = np.minimum(Y, N)
+    for nn, yy in ((None, Y), (N, Yn)):
+        got = F.marginal_log_likelihood_logit_la_cpp(Cm, yy, nn)
+        want = oracle.laplace_mll(Cm, yy, nn)
+        assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+    lab = np.array([2, 0, 1, 1, 3, 0], dtype=np.float64)
+    aug = F.multi_train_split(lab)
+    assert aug.shape == (6, 4) and np.array_equal(aug, (lab[:, None] == np.arange(4)[None, :]).astype(np.float64))
+    with pytest.raises(F.FlgpError):
+        F.multi_train_split([0.5, 1.0])
+    rng = np.random.default_rng(1)
+    mean, cov, tgt = rng.standard_normal(40), rng.uniform(0.1, 2.0, 40), rng.standard_normal(40)
+    want = (np.mean((tgt - mean) ** 2 / cov + np.log(cov + 1e-9)) + np.log(2 * 3.1415926)) / 2
+    assert abs(F.negative_log_likelihood(mean, cov, tgt, "regression") - want) <= 1e-13 * abs(want)
+    with pytest.raises(F.FlgpError, match="RNG"):
+        F.negative_log_likelihood(mean, cov, tgt, "binary")
+    A = rng.standard_normal((30, 30))
+    Cs = A @ A.T + 30 * np.eye(30)
+    Cnv = rng.standard_normal((7, 30))
+    y = rng.standard_normal(30)
+    np.testing.assert_allclose(F.test_regression_cpp(Cs, y, Cnv), Cnv @ np.linalg.solve(Cs, y), rtol=1e-11, atol=1e-13)
+    with pytest.raises(F.FlgpError, match="positive definite"):
+        F.test_regression_cpp(-Cs, y, Cnv)
