@@ -97,18 +97,21 @@ std::vector<int32_t> default_init(int64_t n, int s, uint64_t seed) {
 
 // ---- small dense host algebra for the m- and K-sized GP back-end (reference: Eigen LLT) ----------
 // column-major n x n, lower Cholesky in place; returns false if not positive definite
+// Column-oriented loop nests (every inner loop runs down a contiguous column); each element still receives its
+// updates in ascending k, so the factors are the same bits as from the textbook dot-product form.
 bool chol_lower(std::vector<double>& A, int n) {
   for (int j = 0; j < n; ++j) {
-    double dj = A[j + (size_t)n * j];
-    for (int k = 0; k < j; ++k) dj -= A[j + (size_t)n * k] * A[j + (size_t)n * k];
+    double* aj = &A[(size_t)n * j];
+    for (int k = 0; k < j; ++k) {
+      const double* ak = &A[(size_t)n * k];
+      const double ljk = ak[j];
+      for (int i = j; i < n; ++i) aj[i] -= ak[i] * ljk;
+    }
+    double dj = aj[j];
     if (!(dj > 0.0)) return false;
     dj = std::sqrt(dj);
-    A[j + (size_t)n * j] = dj;
-    for (int i = j + 1; i < n; ++i) {
-      double v = A[i + (size_t)n * j];
-      for (int k = 0; k < j; ++k) v -= A[i + (size_t)n * k] * A[j + (size_t)n * k];
-      A[i + (size_t)n * j] = v / dj;
-    }
+    aj[j] = dj;
+    for (int i = j + 1; i < n; ++i) aj[i] = aj[i] / dj;
   }
   return true;
 }
@@ -116,10 +119,11 @@ bool chol_lower(std::vector<double>& A, int n) {
 void chol_solve(const std::vector<double>& L, int n, double* B, int nrhs) {
   for (int c = 0; c < nrhs; ++c) {
     double* b = B + (size_t)n * c;
-    for (int i = 0; i < n; ++i) {
-      double v = b[i];
-      for (int k = 0; k < i; ++k) v -= L[i + (size_t)n * k] * b[k];
-      b[i] = v / L[i + (size_t)n * i];
+    for (int k = 0; k < n; ++k) {  // forward: column k of L leaves the rows below it
+      const double* lk = &L[(size_t)n * k];
+      const double bk = b[k] / lk[k];
+      b[k] = bk;
+      for (int i = k + 1; i < n; ++i) b[i] -= lk[i] * bk;
     }
     for (int i = n - 1; i >= 0; --i) {
       double v = b[i];
