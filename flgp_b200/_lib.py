@@ -137,6 +137,15 @@ def _declare(lib):
         "flgp_multi_train_split": (C.c_int, [p_f64, c_i64, C.c_int, C.POINTER(C.c_int), p_f64]),
         "flgp_negative_log_likelihood": (C.c_int, [p_f64, p_f64, p_f64, c_i64, C.c_char_p, p_f64]),
         "flgp_test_regression": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, c_i64, p_f64]),
+        "flgp_regression_objective_diff_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p,
+                                                          p_f64, p_f64, p_f64]),
+        "flgp_train_regression_diff_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p, p_f64,
+                                                      p_f64, C.POINTER(C.c_int)]),
+        "flgp_predict_coef_diff_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, p_f64, p_f64]),
+        "flgp_fit_lae_regression_diff_noise": (C.c_int, [H, p_f64, p_f64, p_f64, c_i64, c_i64, C.c_int, C.c_int, C.c_int,
+                                                         C.c_int, C.c_double, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int,
+                                                         C.c_int, C.c_int, C.c_int, p_i32, c_u64, p_f64, p_f64, p_f64,
+                                                         p_f64, p_f64]),
         "flgp_classification_posterior_fixed": (C.c_int, [H, p_f64, c_i64, C.c_int, C.c_double, C.c_double, C.c_double,
                                                           C.c_int, p_f64, p_f64]),
         "flgp_posterior_distribution_classification": (C.c_int, [H, p_f64, p_f64, p_f64, p_f64, C.c_int, c_i64,

@@ -508,6 +508,49 @@ def train_regression_gp(eigenpair: EigenPair, Y_local, m_total: int, K: int, sig
     return x, obj.value, nev.value
 
 
+def regression_objective_diff_rows(V1, values, Y, x, sigma: float = 1e-5, approach: str = "marginal"):
+    """negative_marginal_likelihood_diff_noise_regression_cpp / negative_log_posterior_diff_noise_regression_cpp
+    (src/train.cpp:438-556) on explicit training rows V1 (m x K) of the eigenvectors: (objective, grad[m + 1]).  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if Y.size != m or x.size != m + 1 or values.size != K:
+        raise FlgpError("noise=\"different\": need m labels, m + 1 parameters and K eigenvalues")
+    obj = C.c_double()
+    grad = np.zeros(m + 1)
+    check(_lib.load().flgp_regression_objective_diff_rows(_pf(V1), _pf(values), _pf(Y), m, K, sigma, _b(approach),
+                                                          _pf(x), C.byref(obj), _pf(grad)))
+    return obj.value, grad
+
+
+def train_regression_diff_rows(V1, values, Y, sigma: float = 1e-5, approach: str = "posterior", x0=None):
+    """train_regression_gp_cpp, noise = "different", on explicit training rows: (x[m + 1], objective, evaluations)."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    x = np.full(m + 1, np.nan) if x0 is None else np.array(x0, dtype=np.float64)
+    obj = C.c_double()
+    nev = C.c_int()
+    check(_lib.load().flgp_train_regression_diff_rows(_pf(V1), _pf(values), _pf(Y), m, K, sigma, _b(approach), _pf(x),
+                                                      C.byref(obj), C.byref(nev)))
+    return x, obj.value, nev.value
+
+
+def predict_coef_diff_rows(V1, values, Y, x, sigma: float = 1e-5) -> np.ndarray:
+    """predict_regression_cpp, noisepar = "different": coef (K) with Y_pred = V_new @ coef.  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    coef = np.zeros(K)
+    check(_lib.load().flgp_predict_coef_diff_rows(_pf(V1), _pf(values), _pf(Y), m, K, sigma, _pf(x), _pf(coef)))
+    return coef
+
+
 def mma_minimize(f, x0, lb, ub, xtol_rel: float = 1e-5, maxeval: int = 1000):
     """The library's NLOPT_LD_MMA restatement on a Python objective f(x) -> (value, grad).  Host only."""
     from ._lib import OBJECTIVE_FN, load
@@ -788,9 +831,8 @@ def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: 
     """fit_lae_regression_gp_rcpp (R/Fit.R:56-69 -> src/Fit.cpp:20-99).  pars = (t, noise variance) given: used as
     is; pars = None: trained by empirical Bayes as the reference does (src/train.cpp:557-671; the optimiser is a
     restatement of NLopt's MMA, so trained pars agree with the reference to optimiser tolerance)."""
-    if noise != "same":
-        raise FlgpError("The noise setting is illegal!" if noise != "different"
-                        else "noise=\"different\" (one variance per training point) is not part of this path")
+    if noise not in ("same", "different"):
+        raise FlgpError("The noise setting is illegal!")
     if approach not in ("posterior", "marginal"):
         raise FlgpError("This model selection approach is not supported!")
     ctx = ctx or default_ctx()
@@ -804,8 +846,19 @@ def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: 
     train = np.zeros(m)
     test = np.zeros(m_new)
     cov = np.zeros(m_new)
-    x = np.array(pars if pars is not None else (np.nan, np.nan), dtype=np.float64)
     obj = C.c_double()
+    if noise == "different":  # pars = (t, noise_1 .. noise_m); src/train.cpp:438-556, src/Predict.cpp:76-113
+        x = np.array(pars if pars is not None else np.full(m + 1, np.nan), dtype=np.float64)
+        if x.size != m + 1:
+            raise FlgpError("noise=\"different\" takes m + 1 parameters (t, one noise variance per training row)")
+        check(ctx._lib.flgp_fit_lae_regression_diff_noise(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma,
+                                                          _b(approach), _b(mo["subsample"]), _b(mo["kernel"]),
+                                                          _gl(mo["gl"]), int(bool(mo["root"])), nstart, iter_max,
+                                                          _pi(_idx(init_idx)), seed, _pf(x), _pf(train), _pf(test),
+                                                          _pf(cov), C.byref(obj)))
+        return {"Y_pred": {"train": train, "test": test}, "posterior": {"mean": test, "cov": cov}, "pars": list(x),
+                "obj": obj.value}
+    x = np.array(pars if pars is not None else (np.nan, np.nan), dtype=np.float64)
     check(ctx._lib.flgp_fit_lae_regression(ctx._h, _pf(X), _pf(Y), _pf(X_new), m, m_new, d, s, r, K, sigma,
                                            _b(approach), _b(mo["subsample"]), _b(mo["kernel"]), _gl(mo["gl"]),
                                            int(bool(mo["root"])), nstart, iter_max, _pi(_idx(init_idx)), seed, _pf(x),

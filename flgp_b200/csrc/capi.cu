@@ -1471,6 +1471,121 @@ int flgp_fit_lae_regression(flgp_ctx* ctx, const double* X, const double* Y, con
   });
 }
 
+// ---- noise = "different" (src/train.cpp:438-556, src/Predict.cpp:76-113): host algebra on the m training rows -----------
+static RegTrainDiff make_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma) {
+  need(V1 && values && Y, "null argument");
+  need(m >= 1 && K >= 1 && m <= 8192, "noise=\"different\": need 1 <= m <= 8192 training rows");
+  RegTrainDiff T;
+  T.m = m;
+  T.K = K;
+  T.sigma = sigma;
+  T.V.assign(V1, V1 + (size_t)m * K);
+  T.Y.assign(Y, Y + m);
+  T.ev.resize(K);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - values[k];
+  return T;
+}
+
+int flgp_regression_objective_diff_rows(const double* V1, const double* values, const double* Y, int m, int K,
+                                        double sigma, const char* approach, const double* x, double* obj,
+                                        double* grad) {
+  return guard([&] {
+    need(x && obj, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const RegTrainDiff T = make_diff_rows(V1, values, Y, m, K, sigma);
+    std::vector<double> g((size_t)m + 1);
+    *obj = reg_objective_diff(T, x, g.data(), post);
+    if (grad) std::memcpy(grad, g.data(), sizeof(double) * (m + 1));
+  });
+}
+
+int flgp_train_regression_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                    const char* approach, double* x_io, double* obj, int* nevals) {
+  return guard([&] {
+    need(x_io, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const RegTrainDiff T = make_diff_rows(V1, values, Y, m, K, sigma);
+    const double o = train_regression_diff(T, post, x_io, nevals);
+    if (obj) *obj = o;
+  });
+}
+
+int flgp_predict_coef_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                const double* x, double* coef) {
+  return guard([&] {
+    need(x && coef, "null argument");
+    const RegTrainDiff T = make_diff_rows(V1, values, Y, m, K, sigma);
+    std::vector<double> cf;
+    if (!reg_diff_coef(T, x, cf)) fail(2, "regression: the covariance of the training rows is not positive definite");
+    std::memcpy(coef, cf.data(), sizeof(double) * K);
+  });
+}
+
+// fit_lae_regression_gp_cpp with noise = "different" (src/Fit.cpp:20-99): spectrum, training of (t, noise_1 .. noise_m)
+// on the m training rows, mean folded through coef = Lam V1^T alpha; the posterior variance is the reference's
+// posterior_covariance_regression(eigenpair, idx0, idx1, K, res.x, sigma), which reads pars[1] — the FIRST row's noise —
+// as the common variance (src/Utils.cpp:218-220).
+int flgp_fit_lae_regression_diff_noise(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                       int64_t m_new, int d, int s, int r, int K, double sigma, const char* approach,
+                                       const char* subsample, const char* kernel, int gl, int root, int nstart,
+                                       int iter_max, const int32_t* init_idx, uint64_t seed, double* pars_io,
+                                       double* train, double* test, double* cov, double* obj) {
+  if (K < 0) K = s;  // src/Fit.cpp:37-39
+  bool post = true;
+  if (approach_flag(approach, &post)) {
+    g_err = "This model selection approach is not supported!";
+    return 2;
+  }
+  flgp_spectrum* h = nullptr;
+  int rc = flgp_heat_kernel_spectrum(ctx, X, m, X_new, m_new, d, s, r, K, subsample, kernel, gl, root, nstart, 0.1,
+                                     iter_max, init_idx, seed, &h);
+  if (rc) return rc;
+  std::unique_ptr<flgp_spectrum> own(h);
+  return guard([&] {
+    need(Y && train && pars_io, "null argument");
+    need(m >= 1 && m <= 8192, "noise=\"different\": need 1 <= m <= 8192 training rows");
+    Ctx* c = on_device(h->c);
+    const int KK = h->K;
+    // the m training rows of the eigenvectors on the host (row-major m x K)
+    DevBuf<double> V1((size_t)m * KK);
+    lift_rows_run(c, h->r, h->Zj.p, h->Zx.p, h->w.p, h->Wm.p, KK, nullptr, m, V1.p, KK, false);
+    std::vector<double> Vh((size_t)m * KK), Vk((size_t)m * K);
+    V1.download(Vh.data(), Vh.size(), c->stream);
+    sync(c);
+    for (int64_t i = 0; i < m; ++i)
+      for (int k = 0; k < K; ++k) Vk[(size_t)i * K + k] = Vh[(size_t)i * KK + k];
+    const RegTrainDiff T = make_diff_rows(Vk.data(), h->values.data(), Y, (int)m, K, sigma);
+    bool train_it = false;
+    for (int64_t i = 0; i <= m; ++i) train_it = train_it || !(pars_io[i] == pars_io[i]);
+    if (train_it) {
+      const double o = train_regression_diff(T, post, pars_io, nullptr);
+      if (obj) *obj = o;
+    } else if (obj) {
+      std::vector<double> g((size_t)m + 1);
+      *obj = -reg_objective_diff(T, pars_io, g.data(), post);
+    }
+    std::vector<double> coef;
+    if (!reg_diff_coef(T, pars_io, coef)) fail(2, "regression: the covariance of the training rows is not positive definite");
+    coef.resize(KK, 0.0);
+    const int64_t n = m + m_new;
+    DevBuf<double> dY(m), dcoef(KK), wv(h->s), dy(n), dtmp(n), dc(n);
+    dY.upload(Y, m, c->stream);
+    dcoef.upload(coef.data(), KK, c->stream);
+    gemv_run(c, h->Wm.p, dcoef.p, h->s, KK, wv.p);
+    sparse_rowdot_run(c, n, h->r, h->Zj.p, h->Zx.p, h->w.p, wv.p, dy.p);
+    regression_fixed_dev(h, dY.p, m, K, pars_io[0], pars_io[1], sigma, dtmp.p, dc.p);
+    std::vector<double> y(n), cv(n);
+    dy.download(y.data(), n, c->stream);
+    dc.download(cv.data(), n, c->stream);
+    sync(c);
+    std::memcpy(train, y.data(), sizeof(double) * m);
+    if (test && m_new) std::memcpy(test, y.data() + m, sizeof(double) * m_new);
+    if (cov && m_new) std::memcpy(cov, cv.data() + m, sizeof(double) * m_new);
+  });
+}
+
 int flgp_fit_se_regression(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
                            int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,
                            const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,

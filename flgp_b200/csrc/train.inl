@@ -295,6 +295,191 @@ double train_regression(const RegTrain& T, bool posterior, double* pars_io, int*
   return -minf;
 }
 
+// ---- noise = "different": one noise variance per training row --------------------------------------------------------
+//   reg_objective_diff  negative_marginal_likelihood_diff_noise_regression_cpp / negative_log_posterior_diff_noise_
+//                       regression_cpp (/root/reference/src/train.cpp:438-556), x = (t, noise_1 .. noise_m), a single
+//                       response column (q = 1).  m <= K: the m x m form; m > K: the Woodbury form through
+//                       V^T Z^-1 V (K x K), Z = diag(noise_i + sigma).  The reference's clipping of the noise gradients to
+//                       [-1, 1] in the Woodbury branch (:536-541) is reproduced; its value keeps the reference's terms
+//                       (the source itself remarks that the value "is wrong").
+//   train_regression_diff  train_regression_gp_cpp, noise = "different" (:588-611): MMA on m + 1 variables from
+//                       x0 = (10, 1, .., 1), lb = (1e-3, 1e-4, ..), ub = +inf.  The reference reads m for these vectors
+//                       through a pointer of the wrong struct type — undefined behaviour there;
+//                       here m is the number of training rows, the evident intent.
+//   reg_diff_coef       predict_regression_cpp, noisepar = "different" (src/Predict.cpp:76-113): both branches end in
+//                       Y_pred = V_new (Lam (V1^T alpha)); returns coef = Lam V1^T alpha (K) for the folded mean.
+struct RegTrainDiff {
+  int m = 0, K = 0;
+  double sigma = 1e-5;
+  std::vector<double> ev;  // 1 - values[:K]
+  std::vector<double> V;   // m x K row-major: the training rows of the eigenvectors
+  std::vector<double> Y;   // m
+};
+
+// alpha of both branches (GPML algorithm 2.1 / its Woodbury form); optionally the factors the gradient needs.
+// Returns false when a system is not positive definite.
+bool reg_diff_alpha(const RegTrainDiff& T, const double* x, std::vector<double>& alpha, std::vector<double>* Lout,
+                    std::vector<double>* Gout) {
+  const int m = T.m, K = T.K;
+  const double t = x[0];
+  alpha.assign(m, 0.0);
+  if (m <= K) {
+    std::vector<double> lam(K), L((size_t)m * m);
+    for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * T.ev[k]);
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) {
+        double a = 0.0;
+        for (int k = 0; k < K; ++k) a += (T.V[(size_t)i * K + k] * lam[k]) * T.V[(size_t)j * K + k];
+        L[i + (size_t)m * j] = a + (i == j ? T.sigma + x[i + 1] : 0.0);
+      }
+    if (!chol_lower(L, m)) return false;
+    alpha = T.Y;
+    chol_solve(L, m, alpha.data(), 1);
+    if (Lout) *Lout = std::move(L);
+    return true;
+  }
+  std::vector<double> ls(K), zi(m), G((size_t)K * K, 0.0), u(K, 0.0), L((size_t)K * K);
+  for (int k = 0; k < K; ++k) ls[k] = std::exp(-0.5 * t * T.ev[k]) + 0.0;
+  for (int i = 0; i < m; ++i) zi[i] = 1.0 / (x[i + 1] + T.sigma);
+  for (int i = 0; i < m; ++i) {  // G = V^T Z^-1 V,  u = V^T (Z^-1 Y)
+    const double* v = &T.V[(size_t)i * K];
+    const double zy = zi[i] * T.Y[i];
+    for (int b = 0; b < K; ++b) {
+      const double zb = zi[i] * v[b];
+      u[b] += v[b] * zy;
+      for (int a = 0; a < K; ++a) G[a + (size_t)K * b] += v[a] * zb;
+    }
+  }
+  for (int b = 0; b < K; ++b)
+    for (int a = 0; a < K; ++a) L[a + (size_t)K * b] = (ls[a] * G[a + (size_t)K * b]) * ls[b] + (a == b ? 1.0 : 0.0);
+  if (!chol_lower(L, K)) return false;
+  std::vector<double> w(K);
+  for (int k = 0; k < K; ++k) w[k] = ls[k] * u[k];
+  chol_solve(L, K, w.data(), 1);
+  for (int i = 0; i < m; ++i) {
+    const double* v = &T.V[(size_t)i * K];
+    double a = 0.0;
+    for (int k = 0; k < K; ++k) a += (v[k] * ls[k]) * w[k];
+    alpha[i] = zi[i] * T.Y[i] - zi[i] * a;
+  }
+  if (Lout) *Lout = std::move(L);
+  if (Gout) *Gout = std::move(G);
+  return true;
+}
+
+double reg_objective_diff(const RegTrainDiff& T, const double* x, double* grad, bool posterior) {
+  const int m = T.m, K = T.K;
+  const double t = x[0];
+  std::vector<double> alpha, L, G;
+  if (!reg_diff_alpha(T, x, alpha, &L, &G)) {
+    if (grad)
+      for (int i = 0; i <= m; ++i) grad[i] = 0.0;
+    return INFINITY;
+  }
+  double nmll = 0.0;
+  std::vector<double> dlam(K);
+  for (int k = 0; k < K; ++k) dlam[k] = -T.ev[k] * std::exp(-t * T.ev[k]);
+  double ya = 0.0;
+  for (int i = 0; i < m; ++i) ya += T.Y[i] * alpha[i];
+  if (m <= K) {
+    if (grad) {
+      const std::vector<double> Ci = chol_inverse(L, m);
+      double s0 = 0.0;
+      for (int j = 0; j < m; ++j)
+        for (int i = 0; i < m; ++i) {
+          double gt = 0.0;
+          for (int k = 0; k < K; ++k) gt += (T.V[(size_t)j * K + k] * dlam[k]) * T.V[(size_t)i * K + k];  // grad_t(j, i)
+          s0 += (alpha[i] * alpha[j] - Ci[i + (size_t)m * j]) * gt;
+        }
+      grad[0] = -0.5 * s0;
+      for (int i = 0; i < m; ++i) grad[i + 1] = -0.5 * (alpha[i] * alpha[i] - Ci[i + (size_t)m * i]);
+    }
+    double ld = 0.0;
+    for (int i = 0; i < m; ++i) ld += std::log(L[i + (size_t)m * i] + 1e-9);
+    nmll = 0.5 * ya + ld;
+  } else {
+    std::vector<double> ls(K);
+    for (int k = 0; k < K; ++k) ls[k] = std::exp(-0.5 * t * T.ev[k]) + 0.0;
+    if (grad) {
+      const std::vector<double> Qi = chol_inverse(L, K);
+      std::vector<double> wa(K, 0.0);
+      for (int i = 0; i < m; ++i)
+        for (int k = 0; k < K; ++k) wa[k] += T.V[(size_t)i * K + k] * alpha[i];
+      double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int k = 0; k < K; ++k) {
+        s1 += wa[k] * dlam[k] * wa[k];
+        s2 += dlam[k] * G[k + (size_t)K * k];
+      }
+      std::vector<double> P((size_t)K * K);  // P = Qi (ls G)
+      for (int j = 0; j < K; ++j)
+        for (int i = 0; i < K; ++i) {
+          double a = 0.0;
+          for (int k = 0; k < K; ++k) a += Qi[k + (size_t)K * i] * (ls[k] * G[k + (size_t)K * j]);  // Qi symmetric
+          P[i + (size_t)K * j] = a;
+        }
+      for (int j = 0; j < K; ++j)
+        for (int i = 0; i < K; ++i) s3 += P[i + (size_t)K * j] * ((dlam[j] * G[j + (size_t)K * i]) * ls[i]);
+      grad[0] = -0.5 * s1 + 0.5 * s2 - 0.5 * s3;
+      std::vector<double> tmp(K), qt(K);
+      for (int i = 0; i < m; ++i) {
+        const double zi = 1.0 / (x[i + 1] + T.sigma);
+        for (int k = 0; k < K; ++k) tmp[k] = (zi * T.V[(size_t)i * K + k]) * ls[k];
+        double quad = 0.0;
+        for (int b = 0; b < K; ++b) {
+          double a = 0.0;
+          for (int k = 0; k < K; ++k) a += tmp[k] * Qi[k + (size_t)K * b];
+          quad += a * tmp[b];
+        }
+        double g = -0.5 * (alpha[i] * alpha[i]) + 0.5 * (zi - quad);
+        if (std::fabs(g) >= 1.0) g = g / std::fabs(g) * 1.0;  // the reference's gradient clipping (:536-541)
+        grad[i + 1] = g;
+      }
+    }
+    double ld = 0.0, lz = 0.0;
+    for (int i = 0; i < K; ++i) ld += std::log(L[i + (size_t)K * i] + 1e-9);
+    for (int i = 0; i < m; ++i) lz += std::log((x[i + 1] + T.sigma) + 1e-9);
+    nmll = 0.5 * ya + ld + 0.5 * lz;
+  }
+  if (posterior) {  // src/train.cpp:438-458, PostOFDataReg defaults
+    const double p = 1.0, q = 10.0, tau = 2.0, al = 1e-1, be = 1e-3;
+    nmll += p * std::log(t + 1e-9) + std::pow(t / tau, -q);
+    if (grad) grad[0] += p / (t + 1e-9) - (q / tau) * std::pow(t / tau, -q - 1.0);
+    double pr1 = 0.0;
+    for (int i = 0; i < m; ++i) {
+      const double ns = x[i + 1] + T.sigma;
+      pr1 += ((al + 1.0) * std::log(ns) + be / ns) / m;
+      if (grad) grad[i + 1] += ((al + 1.0) / ns - be / (ns * ns)) / m;
+    }
+    nmll += pr1;
+  }
+  return nmll;
+}
+
+// x_io: m + 1 values, NaN entries take the reference's start (10, 1, .., 1).  Returns obj = -minimum.
+double train_regression_diff(const RegTrainDiff& T, bool posterior, double* x_io, int* nevals) {
+  const int n = T.m + 1;
+  std::vector<double> lb(n, 1e-4), ub(n, INFINITY);
+  lb[0] = 1e-3;
+  for (int i = 0; i < n; ++i)
+    if (!(x_io[i] == x_io[i])) x_io[i] = i == 0 ? 10.0 : 1.0;
+  double minf = 0.0;
+  const int nev = mma_minimize(n, [&](const double* xx, double* g) { return reg_objective_diff(T, xx, g, posterior); },
+                               lb.data(), ub.data(), x_io, &minf, 1e-5, 1000);
+  if (nevals) *nevals = nev;
+  return -minf;
+}
+
+// coef = Lam V1^T alpha  (K): Y_pred = V_new coef in both branches of predict_regression_cpp, noisepar = "different"
+bool reg_diff_coef(const RegTrainDiff& T, const double* x, std::vector<double>& coef) {
+  std::vector<double> alpha;
+  if (!reg_diff_alpha(T, x, alpha, nullptr, nullptr)) return false;
+  coef.assign(T.K, 0.0);
+  for (int i = 0; i < T.m; ++i)
+    for (int k = 0; k < T.K; ++k) coef[k] += T.V[(size_t)i * T.K + k] * alpha[i];
+  for (int k = 0; k < T.K; ++k) coef[k] *= std::exp(-x[0] * T.ev[k]);
+  return true;
+}
+
 // ---- binary GP classifier: training of the diffusion time t (second half) -----------------------
 //   laplace_mll       marginal_log_likelihood_logit_la_cpp (/root/reference/src/train.cpp:716-760): Newton iterations for
 //                     the posterior mode (GPML algorithm 3.1) from f = 0, stop when |f - f_new|_1 < tol; the value uses

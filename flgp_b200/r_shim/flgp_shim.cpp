@@ -205,7 +205,7 @@ Rcpp::List pack_fit(const Eigen::VectorXd& train, const Eigen::VectorXd& test, c
 Rcpp::List fit_lae_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
                                      int s, int r, int K, double sigma, std::string approach, std::string noise,
                                      Rcpp::List models, bool output_cov, int nstart) {
-  if (noise != "same") Rcpp::stop("noise=\"different\" is not offloaded; call the reference path");
+  if (noise != "same" && noise != "different") Rcpp::stop("The noise setting is illegal!");
   const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
   const Eigen::Map<Eigen::VectorXd> Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
   const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
@@ -215,6 +215,14 @@ Rcpp::List fit_lae_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericV
   std::vector<double> pars = {NA_REAL, NA_REAL};  // NaN: train
   Eigen::VectorXd train(m), test(m_new), cov(m_new);
   double obj = 0.0;
+  if (noise == "different") {  // (t, noise_1 .. noise_m): src/train.cpp:438-556, src/Predict.cpp:76-113
+    pars.assign(m + 1, NA_REAL);
+    ok(flgp_fit_lae_regression_diff_noise(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, sigma,
+                                          approach.c_str(), sub.c_str(), ker.c_str(),
+                                          gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]),
+                                          nstart, 100, init.data(), 0, pars.data(), train.data(), test.data(), cov.data(),
+                                          &obj));
+  } else
   ok(flgp_fit_lae_regression(ctx(), X.data(), Y.data(), X_new.data(), m, m_new, (int)X.cols(), s, r, K, sigma,
                              approach.c_str(), sub.c_str(), ker.c_str(), gl_code(Rcpp::as<std::string>(models["gl"])),
                              Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, pars.data(), train.data(),

@@ -343,6 +343,33 @@ int flgp_negative_log_likelihood(const double* mean, const double* cov, const do
 /* test_regression_cpp(C, Y, Cnv) (src/Predict.cpp:29-37): Y_pred = Cnv C^{-1} Y by Cholesky; C m x m, Cnv m_new x m. */
 int flgp_test_regression(const double* C, const double* Y, const double* Cnv, int m, int64_t m_new, double* Y_pred);
 
+/* ---- noise = "different": one noise variance per training row (src/train.cpp:438-556, src/Predict.cpp:76-113) -------
+ * x = (t, noise_1 .. noise_m).  The *_rows entries are host algebra on explicit training rows V1 (m x K ROW-major) of the
+ * eigenvectors and `values` (K, as exported: the Laplacian spectrum is 1 - values); no device work, no context.
+ * negative_marginal_likelihood_diff_noise_regression_cpp ("marginal") / negative_log_posterior_diff_noise_regression_cpp
+ * ("posterior"): *obj <- the value to be minimised, grad (m + 1, may be NULL) its gradient, the noise components clipped
+ * to [-1, 1] in the m > K branch as in the reference. */
+int flgp_regression_objective_diff_rows(const double* V1, const double* values, const double* Y, int m, int K,
+                                        double sigma, const char* approach, const double* x, double* obj,
+                                        double* grad);
+/* train_regression_gp_cpp, noise = "different" (src/train.cpp:588-611, 614-671): MMA on m + 1 variables from
+ * (10, 1 .. 1), lb = (1e-3, 1e-4 ..), ub = +inf, xtol_rel = 1e-5.  x_io: NaN entries take the start values.  The
+ * reference sizes these vectors with an m read through a pointer of the wrong struct type (undefined behaviour, SURVEY.md
+ * appendix A.10); m here is the number of training rows.  *obj <- -(minimum). */
+int flgp_train_regression_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                    const char* approach, double* x_io, double* obj, int* nevals);
+/* predict_regression_cpp, noisepar = "different": coef (K) = Lam V1^T alpha, so that Y_pred = V_new coef. */
+int flgp_predict_coef_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                const double* x, double* coef);
+/* fit_lae_regression_gp_cpp with noise = "different": spectrum, training (pars_io: m + 1 values, any NaN trains), mean of
+ * every row; cov = the reference's posterior_covariance_regression, which takes pars[1] (the first row's noise) as the
+ * common variance (src/Utils.cpp:218-220).  Single process. */
+int flgp_fit_lae_regression_diff_noise(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
+                                       int64_t m_new, int d, int s, int r, int K, double sigma, const char* approach,
+                                       const char* subsample, const char* kernel, int gl, int root, int nstart,
+                                       int iter_max, const int32_t* init_idx, uint64_t seed, double* pars_io,
+                                       double* train, double* test, double* cov, double* obj);
+
 #ifdef __cplusplus
 }
 #endif

@@ -520,6 +520,107 @@ def regression_objective(V, values, Y, idx, K, x, sigma=1e-5, approach="marginal
     return float(nmll), grad
 
 
+def regression_objective_diff(V, values, Y, idx, K, x, sigma=1e-5, approach="marginal",
+                              prior=(1.0, 10.0, 2.0, 0.1, 1e-3)):
+    """negative_marginal_likelihood_diff_noise_regression_cpp / negative_log_posterior_diff_noise_regression_cpp
+    (src/train.cpp:438-556), literal: x = (t, noise_1 .. noise_m).  Returns (objective, grad[m + 1]); the noise
+    gradients of the m > K branch are clipped to [-1, 1] as in the reference (:536-541)."""
+    import scipy.linalg as sla
+
+    x = np.asarray(x, dtype=np.float64)
+    t = float(x[0])
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+    m, q = Y.shape
+    ev = 1.0 - values[:K]
+    Vm = V[np.asarray(idx), :K]
+    grad = np.zeros(m + 1)
+    if m <= K:
+        C = (Vm * np.exp(-t * ev)) @ Vm.T
+        C[np.diag_indices(m)] += sigma
+        C[np.diag_indices(m)] += x[1:]
+        L = sla.cholesky(C, lower=True)
+        alpha = sla.cho_solve((L, True), Y)
+        C_inv = sla.cho_solve((L, True), np.eye(m))
+        U = alpha @ alpha.T / q - C_inv
+        grad_t = (Vm * (-ev * np.exp(-t * ev))) @ Vm.T
+        grad[0] = -0.5 * (U * grad_t.T).sum()
+        grad[1:] = -0.5 * np.diag(U)
+        nmll = 0.5 * (Y * alpha).sum() / q + np.log(np.diag(L) + 1e-9).sum()
+    else:
+        ls = np.exp(-0.5 * t * ev) + 0.0
+        Z = x[1:] + sigma
+        Zi = 1.0 / Z
+        VtZiV = Vm.T @ (Zi[:, None] * Vm)
+        Q = (ls[:, None] * VtZiV) * ls[None, :]
+        Q[np.diag_indices(K)] += 1.0
+        L = sla.cholesky(Q, lower=True)
+        ZiY = Zi[:, None] * Y
+        alpha = ZiY - Zi[:, None] * ((Vm * ls) @ sla.cho_solve((L, True), ls[:, None] * (Vm.T @ ZiY)))
+        Q_inv = sla.cho_solve((L, True), np.eye(K))
+        A = -ev * (np.exp(-t * ev) + 0.0) + 0.0
+        Vta = Vm.T @ alpha
+        grad[0] = -0.5 * (Vta * (A[:, None] * Vta)).sum() / q
+        grad[0] += 0.5 * np.trace(A[:, None] * VtZiV)
+        grad[0] += -0.5 * ((Q_inv @ (ls[:, None] * VtZiV)) * ((A[:, None] * VtZiV) * ls[None, :]).T).sum()
+        for i in range(m):
+            g = -0.5 * (alpha[i] * alpha[i]).sum() / q
+            tmp = Zi[i] * Vm[i] * ls
+            g += 0.5 * (Zi[i] - ((tmp @ Q_inv) * tmp).sum())
+            if abs(g) >= 1.0:
+                g = g / abs(g) * 1.0
+            grad[i + 1] = g
+        nmll = 0.5 * (Y * alpha).sum() / q + np.log(np.diag(L) + 1e-9).sum() + 0.5 * np.log(Z + 1e-9).sum()
+    if approach == "posterior":
+        p, qq, tau, al, be = prior
+        nmll += p * np.log(t + 1e-9) + (t / tau) ** (-qq)
+        grad[0] += p / (t + 1e-9) - (qq / tau) * (t / tau) ** (-qq - 1)
+        ns = x[1:] + sigma
+        nmll += (((al + 1) * np.log(ns) + be / ns) / m).sum()
+        grad[1:] += ((al + 1) / ns - be / ns ** 2) / m
+    elif approach != "marginal":
+        raise ValueError("This model selection approach is not supported!")
+    return float(nmll), grad
+
+
+def predict_regression_diff(V, values, Y, idx0, idx1, K, pars, sigma):
+    """predict_regression_cpp, noisepar = "different" (src/Predict.cpp:76-113), literal."""
+    import scipy.linalg as sla
+
+    pars = np.asarray(pars, dtype=np.float64)
+    t = float(pars[0])
+    Y = np.asarray(Y, dtype=np.float64).reshape(-1, 1)
+    m = Y.shape[0]
+    ev = 1.0 - values[:K]
+    V0 = V[np.asarray(idx0), :K]
+    V1 = V[np.asarray(idx1), :K]
+    if m <= K:
+        C = (V0 * np.exp(-t * ev)) @ V0.T
+        C[np.diag_indices(m)] += sigma
+        C[np.diag_indices(m)] += pars[1:]
+        Cnv = (V1 * np.exp(-t * ev)) @ V0.T
+        alpha = sla.cho_solve(sla.cho_factor(C, lower=True), Y)
+        return (Cnv @ alpha)[:, 0]
+    ls = np.exp(-0.5 * t * ev) + 0.0
+    Zi = 1.0 / (pars[1:] + sigma)
+    VtZV = V0.T @ (Zi[:, None] * V0)
+    Q = (ls[:, None] * VtZV) * ls[None, :]
+    Q[np.diag_indices(K)] += 1.0
+    ZiY = Zi[:, None] * Y
+    alpha = ZiY - Zi[:, None] * ((V0 * ls) @ sla.cho_solve(sla.cho_factor(Q, lower=True), ls[:, None] * (V0.T @ ZiY)))
+    return (V1 @ (np.exp(-t * ev + 0.0)[:, None] * (V0.T @ alpha)))[:, 0]
+
+
+def train_regression_diff(V, values, Y, idx, K, sigma=1e-5, approach="posterior", x0=None):
+    """train_regression_gp_cpp, noise = "different" (src/train.cpp:588-611, 614-671) with m = number of training rows
+    (the reference reads it through a mistyped pointer): (x[m + 1], -minimum)."""
+    m = len(idx)
+    x0 = np.concatenate([[10.0], np.ones(m)]) if x0 is None else np.asarray(x0, dtype=np.float64)
+    lb = np.concatenate([[1e-3], np.full(m, 1e-4)])
+    ub = np.full(m + 1, np.inf)
+    x, fmin, _ = mma_minimize(lambda z: regression_objective_diff(V, values, Y, idx, K, z, sigma, approach), x0, lb, ub)
+    return x, -fmin
+
+
 def mma_minimize(f, x0, lb, ub, xtol_rel=1e-5, maxeval=1000):
     """Svanberg's CCSA with MMA approximations for bound constraints only, as NLopt's NLOPT_LD_MMA runs it
     (nloptr is an un-vendored dependency of the reference, version unpinned: DESCRIPTION; call site

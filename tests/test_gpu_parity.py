@@ -379,6 +379,46 @@ def test_fit_lae_regression_fixed_pars(flgp, oracle, m, K):
     assert np.all(res["posterior"]["cov"] > 0)
 
 
+@pytest.mark.parametrize("m,K", [(150, 40), (30, 40)])
+def test_fit_lae_regression_noise_different(flgp, oracle, m, K):
+    """fit_lae_regression_gp_rcpp(noise = "different") (src/train.cpp:438-556, src/Predict.cpp:76-113): one noise variance
+    per training row.  At fixed parameters, mean of every row against the oracle's literal prediction on the library's
+    eigenvectors (1e-8), variance = the reference's posterior_covariance_regression at pars[1], objective 1e-9; trained:
+    the result is the objective at the returned parameters, better than at the start, within the bounds."""
+    X, Y = spiral(3000, 10)
+    n, s, r, sigma = len(X), 120, 3, 1e-3
+    init = _init(n, s, 10)
+    rng = np.random.default_rng(m)
+    pars = np.concatenate([[4.0], rng.uniform(0.02, 0.5, m)])
+    ep = flgp.heat_kernel_spectrum_cpp(X[:m], X[m:], s, r, K, init_idx=init)
+    V, values = ep.vectors, ep.values
+    idx0, idx1 = np.arange(m, dtype=np.int32), np.arange(m, n, dtype=np.int32)
+    for approach in ("marginal", "posterior"):
+        res = flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, sigma, approach=approach, noise="different",
+                                              pars=pars, init_idx=init)
+        want_tr = oracle.predict_regression_diff(V, values, Y[:m], idx0, idx0, K, pars, sigma)
+        want_te = oracle.predict_regression_diff(V, values, Y[:m], idx0, idx1, K, pars, sigma)
+        sc = np.abs(want_te).max()
+        assert np.abs(res["Y_pred"]["train"] - want_tr).max() <= 1e-8 * sc
+        assert np.abs(res["Y_pred"]["test"] - want_te).max() <= 1e-8 * sc
+        want_cov = oracle.posterior_covariance_regression(V, values, idx0, idx1, K, pars[:2], sigma)
+        assert np.abs(res["posterior"]["cov"] - want_cov).max() <= 1e-8 * np.abs(want_cov).max()
+        fo = oracle.regression_objective_diff(V, values, Y[:m], idx0, K, pars, sigma, approach)[0]
+        assert abs(res["obj"] + fo) <= 1e-9 * max(1.0, abs(fo))
+    res = flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, sigma, noise="different", init_idx=init)
+    x = np.array(res["pars"])
+    assert x.size == m + 1 and x[0] >= 1e-3 and x[1:].min() >= 1e-4
+    f_at = oracle.regression_objective_diff(V, values, Y[:m], idx0, K, x, sigma, "posterior")[0]
+    f_0 = oracle.regression_objective_diff(V, values, Y[:m], idx0, K, np.concatenate([[10.0], np.ones(m)]), sigma,
+                                           "posterior")[0]
+    assert abs(res["obj"] + f_at) <= 1e-8 * max(1.0, abs(f_at)) and f_at < f_0
+    want_te = oracle.predict_regression_diff(V, values, Y[:m], idx0, idx1, K, x, sigma)
+    assert np.abs(res["Y_pred"]["test"] - want_te).max() <= 1e-7 * np.abs(want_te).max()
+    with pytest.raises(flgp.FlgpError, match="m \\+ 1"):
+        flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, sigma, noise="different", pars=(4.0, 0.1),
+                                        init_idx=init)
+
+
 def test_errors_mirror_rcpp_stop(flgp):
     X, Y = spiral(300, 1)
     with pytest.raises(flgp.FlgpError, match="kernel type is not supported"):
