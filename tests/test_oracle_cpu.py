@@ -367,3 +367,84 @@ def test_spectrum_against_scipy_svds(oracle):
     gap = values[K - 1] - np.sqrt(max(np.linalg.eigvalsh(I["G"])[::-1][K], 0.0))
     if gap > 1e-4:
         assert np.abs(H_arpack - H_oracle).max() <= 1e-7 * np.abs(H_oracle).max()
+
+
+# ---- independent cross-checks (other people's implementations of the same mathematics) ------------------------------
+def test_knn_against_sklearn_brute_force(oracle):
+    """KNN_cpp restated vs scikit-learn's brute-force neighbours on tie-free data: same anchors in the same order, squared
+    distances to 1e-10 (sklearn expands the norm the same way but sums in BLAS order)."""
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(21)
+    for n, d, s, r in [(400, 3, 60, 3), (300, 16, 50, 5), (200, 37, 33, 1)]:
+        X = np.asfortranarray(rng.standard_normal((n, d)))
+        U = np.asfortranarray(rng.standard_normal((s, d)))
+        ind, dist = oracle.knn(X, U, r, want_dist=True)
+        dd, ii = NearestNeighbors(n_neighbors=r, algorithm="brute").fit(U).kneighbors(X)
+        assert np.array_equal(ind, ii)
+        np.testing.assert_allclose(dist, dd ** 2, rtol=1e-9, atol=1e-10)
+
+
+def test_lae_against_scipy_constrained_least_squares(oracle):
+    """local_anchor_embedding_cpp restated vs an independent solver of the same problem (min 1/2 |x - z U|^2 over the
+    simplex, scipy SLSQP): the accelerated projected gradient stops at |z - z_prev|^2 < 1e-5 (the reference's rule, not a
+    tight one), so its objective is within 2e-3 of the constrained optimum and its weights within 5e-2; never below it."""
+    import scipy.optimize as so
+
+    rng = np.random.default_rng(22)
+    for r, d in [(3, 2), (3, 3), (5, 16), (4, 8)]:
+        for _ in range(6):
+            U = rng.standard_normal((r, d))
+            x = rng.dirichlet(np.ones(r)) @ U + 0.3 * rng.standard_normal(d)
+            z = oracle.lae_point(x, np.asfortranarray(U))
+            assert abs(z.sum() - 1.0) <= 1e-12 and z.min() >= 0.0
+            f = lambda w: 0.5 * np.sum((x - w @ U) ** 2)  # noqa: E731
+            ref = so.minimize(f, np.full(r, 1.0 / r), method="SLSQP", bounds=[(0, 1)] * r,
+                              constraints=[dict(type="eq", fun=lambda w: w.sum() - 1.0)],
+                              options=dict(ftol=1e-14, maxiter=500))
+            assert ref.success
+            assert ref.fun - 1e-9 <= f(z) <= ref.fun + 2e-3 * max(1.0, x @ x)
+            assert np.abs(z - ref.x).max() <= 5e-2
+
+
+def test_minibatch_contract_is_a_sane_minibatch_kmeans(oracle):
+    """The mini-batch contract (ClusterR un-vendored) against scikit-learn's MiniBatchKMeans on separated blobs: another
+    implementation of Sculley's algorithm with its own sampling and learning-rate details, so only the quality is
+    comparable — the within-cluster sum of squares of the contract's centroids is within 25 % of scikit-learn's from the
+    same start, and far below that of the start itself; sizes add up to n."""
+    from sklearn.cluster import MiniBatchKMeans
+
+    rng = np.random.default_rng(23)
+    n, d, s = 6000, 2, 12
+    centres = rng.uniform(-10, 10, (s, d))
+    X = np.asfortranarray(centres[rng.integers(0, s, n)] + 0.4 * rng.standard_normal((n, d)))
+    init = np.sort(rng.choice(n, s, replace=False)).astype(np.int32)
+    U, iters = oracle.minibatch_kmeans(X, s, init, seed=4)
+
+    def wss(C):
+        return ((X[:, None, :] - C[None, :, :]) ** 2).sum(-1).min(1).sum()
+
+    sk = MiniBatchKMeans(n_clusters=s, init=X[init], n_init=1, batch_size=10 * s, max_iter=100, random_state=0).fit(X)
+    assert U[:, d].sum() == n and 1 <= iters <= 100
+    assert wss(U[:, :d]) <= 1.25 * wss(sk.cluster_centers_)
+    assert wss(U[:, :d]) <= 0.6 * wss(X[init])
+
+
+def test_regression_training_reaches_the_lbfgsb_optimum(oracle):
+    """The MMA restatement (NLopt un-vendored) against scipy's L-BFGS-B on the same bounded objective (marginal: smooth;
+    the reference's clipping of the noise gradient is inactive near the optimum): same minimum to 1e-6 relative."""
+    import scipy.optimize as so
+
+    rng = np.random.default_rng(24)
+    n, m, K = 300, 80, 20
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.3, 1.0, K))[::-1]
+    values[0] = 1.0
+    idx = np.arange(m, dtype=np.int32)
+    Y = V[:m, 1] + 0.7 * V[:m, 3] + 0.2 * rng.standard_normal(m)
+    x, obj = oracle.train_regression(V, values, Y, idx, K, 1e-5, "marginal")
+    f = lambda z: oracle.regression_objective(V, values, Y, idx, K, z, 1e-5, "marginal")  # noqa: E731
+    ref = so.minimize(lambda z: f(z)[0], [10.0, 1.0], jac=lambda z: f(z)[1], method="L-BFGS-B",
+                      bounds=[(1e-3, None), (1e-4, None)], options=dict(ftol=1e-15, gtol=1e-10))
+    assert abs(-obj - ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
+    np.testing.assert_allclose(x, ref.x, rtol=2e-2, atol=1e-3)
