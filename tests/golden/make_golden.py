@@ -41,3 +41,19 @@ np.savez_compressed(os.path.join(os.path.dirname(__file__), "oracle_train.npz"),
                     se_a2=se["a2"], se_obj=se["obj"], se_test=se["test"][:200], se_cov=se["cov"][:200],
                     ny_a2=ny["a2"], ny_obj=ny["obj"], ny_test=ny["test"][:200], ny_cov=ny["cov"][:200])
 print("wrote oracle_train.npz: pars", pars, "se a2", se["a2"], "nystrom a2", ny["a2"])
+
+# ---- third fixture: the callers added late in round 2 (mini-batch subsample, noise = "different", the SE / Nystrom
+# logit grids at a fixed diffusion time) ---------------------------------------------------------------------------
+Umb, it_mb = O.minibatch_kmeans(X, meta["s"], init, max_iters=40, seed=9)
+lab = (Y > np.median(Y)).astype(np.float64)
+xd = np.concatenate([[6.0], 0.1 + 0.4 * (np.arange(m) % 7) / 7.0])
+obj_d, grad_d = O.regression_objective_diff(V, values, Y[:m], idx, meta["K"], xd, 1e-5, "posterior")
+pred_d = O.predict_regression_diff(V, values, Y[:m], idx, np.arange(m, meta["n"], dtype=np.int32), meta["K"], xd, 1e-5)
+sl = O.fit_se_logit(X[:m], lab[:m], X[m:], meta["s"], meta["r"], meta["K"], init, a2s, iter_max=30, t=6.0)
+nl = O.fit_nystrom_logit(X[:m], lab[:m], X[m:], meta["s"], meta["K"], init, a2s, iter_max=30, t=6.0)
+np.savez_compressed(os.path.join(os.path.dirname(__file__), "oracle_round2b.npz"), Umb=Umb, it_mb=it_mb, xd=xd,
+                    obj_d=obj_d, grad_d=grad_d, pred_d=pred_d[:200],
+                    sl_a2=sl["a2"], sl_obj=sl["obj"], sl_mean=sl["mean"][:200], sl_cov=sl["cov"][:200],
+                    nl_a2=nl["a2"], nl_obj=nl["obj"], nl_mean=nl["mean"][:200], nl_cov=nl["cov"][:200])
+print("wrote oracle_round2b.npz: minibatch batches", it_mb, "se logit a2", sl["a2"], sl["obj"], "nystrom logit a2",
+      nl["a2"], nl["obj"])

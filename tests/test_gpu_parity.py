@@ -764,6 +764,38 @@ def test_cuda_path_against_golden_fixtures(flgp):
     np.testing.assert_allclose(ny["posterior"]["cov"][:200], g["ny_cov"], rtol=1e-6, atol=1e-8)
 
 
+def test_cuda_path_against_golden_fixtures_late_round2(flgp):
+    """The CUDA path against tests/golden/oracle_round2b.npz directly (no oracle call at run time): mini-batch anchors
+    bit for bit, noise = "different" objective and prediction, SE and Nystrom logit grids at a fixed diffusion time."""
+    import json
+    import os
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    g0 = np.load(os.path.join(gold, "oracle_small.npz"))
+    gt = np.load(os.path.join(gold, "oracle_train.npz"))
+    g = np.load(os.path.join(gold, "oracle_round2b.npz"))
+    meta = json.loads(str(g0["meta"]))
+    X, Y = spiral(meta["n"], meta["seed"])
+    init, s, r, K, m = g0["init"], meta["s"], meta["r"], meta["K"], int(gt["m"])
+    U, _, it = flgp.subsample_cpp(X, s, "minibatchkmeans", init_idx=init, seed=9, iter_max=40, return_info=True)
+    assert it == int(g["it_mb"]) and np.array_equal(U, g["Umb"])
+    res = flgp.fit_lae_regression_gp_rcpp(X[:m], Y[:m], X[m:], s, r, K, 1e-5, noise="different", pars=g["xd"],
+                                          init_idx=init)
+    np.testing.assert_allclose(-res["obj"], g["obj_d"], rtol=1e-8)
+    np.testing.assert_allclose(res["Y_pred"]["test"][:200], g["pred_d"], rtol=1e-7, atol=1e-8)
+    lab = (Y > np.median(Y)).astype(np.float64)
+    sl = flgp.fit_se_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, r, K, a2s=gt["a2s"], t=6.0, init_idx=init, iter_max=30)
+    assert sl["a2"] == float(g["sl_a2"])
+    np.testing.assert_allclose(sl["obj"], g["sl_obj"], rtol=1e-7)
+    np.testing.assert_allclose(sl["posterior"]["mean"][:200], g["sl_mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(sl["posterior"]["cov"][:200], g["sl_cov"], rtol=1e-6, atol=1e-7)
+    nl = flgp.fit_nystrom_logit_gp_rcpp(X[:m], lab[:m], X[m:], s, K, a2s=gt["a2s"], t=6.0, init_idx=init, iter_max=30)
+    assert nl["a2"] == float(g["nl_a2"])
+    np.testing.assert_allclose(nl["obj"], g["nl_obj"], rtol=1e-6)
+    np.testing.assert_allclose(nl["posterior"]["mean"][:200], g["nl_mean"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(nl["posterior"]["cov"][:200], g["nl_cov"], rtol=1e-5, atol=1e-6)
+
+
 # ------------------------------------------------------------------------------------------- edge shapes of the new paths
 @pytest.mark.parametrize("n,d,s,r,K", [(130, 16, 64, 5, 64), (64, 5, 64, 1, 10), (200, 9, 65, 5, 65), (97, 33, 64, 4, 7)])
 def test_large_d_minimum_shapes(flgp, oracle, n, d, s, r, K):

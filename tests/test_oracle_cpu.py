@@ -448,3 +448,34 @@ def test_regression_training_reaches_the_lbfgsb_optimum(oracle):
                       bounds=[(1e-3, None), (1e-4, None)], options=dict(ftol=1e-15, gtol=1e-10))
     assert abs(-obj - ref.fun) <= 1e-6 * max(1.0, abs(ref.fun))
     np.testing.assert_allclose(x, ref.x, rtol=2e-2, atol=1e-3)
+
+
+def test_golden_fixture_late_round2_rows(oracle):
+    """The callers added late in round 2 (mini-batch subsample, noise = "different", SE / Nystrom logit grids at a fixed
+    diffusion time) pinned by the committed fixture tests/golden/oracle_round2b.npz (same generator script)."""
+    g0 = np.load(os.path.join(GOLD, "oracle_small.npz"))
+    gt = np.load(os.path.join(GOLD, "oracle_train.npz"))
+    g = np.load(os.path.join(GOLD, "oracle_round2b.npz"))
+    meta = json.loads(str(g0["meta"]))
+    X, Y = spiral(meta["n"], meta["seed"])
+    init, m, K, s, r = g0["init"], int(gt["m"]), meta["K"], meta["s"], meta["r"]
+    Umb, it_mb = oracle.minibatch_kmeans(X, s, init, max_iters=40, seed=9)
+    assert it_mb == int(g["it_mb"]) and np.array_equal(Umb, g["Umb"])
+    U, _, _ = oracle.kmeans_lloyd(X, s, init)
+    Zj, Zx = oracle.cross_similarity_lae(X, U, r, "cluster-normalized")
+    values, V = oracle.spectrum_from_Z(Zj, Zx, s, K, True)
+    idx = np.arange(m, dtype=np.int32)
+    f, gr = oracle.regression_objective_diff(V, values, Y[:m], idx, K, g["xd"], 1e-5, "posterior")
+    np.testing.assert_allclose(f, g["obj_d"], rtol=1e-9)
+    np.testing.assert_allclose(gr, g["grad_d"], rtol=1e-7, atol=1e-9)
+    pred = oracle.predict_regression_diff(V, values, Y[:m], idx, np.arange(m, meta["n"], dtype=np.int32), K, g["xd"], 1e-5)
+    np.testing.assert_allclose(pred[:200], g["pred_d"], rtol=1e-8, atol=1e-9)
+    lab = (Y > np.median(Y)).astype(np.float64)
+    sl = oracle.fit_se_logit(X[:m], lab[:m], X[m:], s, r, K, init, gt["a2s"], iter_max=30, t=6.0)
+    assert sl["a2"] == float(g["sl_a2"])
+    np.testing.assert_allclose(sl["obj"], g["sl_obj"], rtol=1e-9)
+    np.testing.assert_allclose(sl["mean"][:200], g["sl_mean"], rtol=1e-7, atol=1e-8)
+    nl = oracle.fit_nystrom_logit(X[:m], lab[:m], X[m:], s, K, init, gt["a2s"], iter_max=30, t=6.0)
+    assert nl["a2"] == float(g["nl_a2"])
+    np.testing.assert_allclose(nl["obj"], g["nl_obj"], rtol=1e-8)
+    np.testing.assert_allclose(nl["mean"][:200], g["nl_mean"], rtol=1e-6, atol=1e-7)
