@@ -25,6 +25,49 @@ def test_library_exports_every_declared_symbol(flgp):
     assert set(flgp._lib.SIGNATURES) == set(syms)
 
 
+def _classify_c(arg: str) -> str:
+    """Coarse class of one C parameter of include/flgp.h."""
+    a = re.sub(r"\bconst\b", "", arg).strip()
+    if "*" in a or "flgp_objective_fn" in a:
+        if re.search(r"\bchar\s*\*", a):
+            return "str"
+        return "ptr"
+    base = a.rsplit(None, 1)[0].strip() if len(a.split()) > 1 else a
+    return {"int": "i32", "int64_t": "i64", "uint64_t": "u64", "double": "f64", "size_t": "u64"}[base]   # size_t = 64-bit here
+
+
+def _classify_ctypes(t) -> str:
+    if t is C.c_char_p:
+        return "str"
+    if t in (C.c_int, C.c_int32, C.c_uint):
+        return "i32"
+    if t is C.c_int64:
+        return "i64"
+    if t is C.c_uint64:
+        return "u64"
+    if t is C.c_double:
+        return "f64"
+    return "ptr"   # POINTER(...), c_void_p, CFUNCTYPE
+
+
+def test_ctypes_signatures_match_the_header(flgp):
+    """Every prototype of include/flgp.h against the ctypes mirror (flgp_b200/_lib.py): same number of parameters and
+    the same class (pointer / string / int / int64 / uint64 or size_t / double) in every position — a mismatch here
+    would corrupt the call frame silently."""
+    flgp._lib.load()
+    text = open(os.path.join(ROOT, "include", "flgp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = re.findall(r"\b[A-Za-z_][A-Za-z0-9_ \*]*?\b(flgp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S)
+    seen = {}
+    for name, args in protos:
+        args = " ".join(args.split())
+        seen[name] = [] if args in ("", "void") else [_classify_c(a) for a in args.split(",")]
+    assert set(seen) == set(flgp._lib.SIGNATURES)
+    for name, (_, argtypes) in flgp._lib.SIGNATURES.items():
+        got = [_classify_ctypes(t) for t in argtypes]
+        assert got == seen[name], (name, got, seen[name])
+
+
 def test_no_silent_fallback_without_gpu(flgp):
     import torch
 
