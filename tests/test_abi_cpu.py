@@ -68,6 +68,44 @@ def test_ctypes_signatures_match_the_header(flgp):
         assert got == seen[name], (name, got, seen[name])
 
 
+def _call_arities(text, name_re=r"flgp_[a-z0-9_]+"):
+    """(name, number of top-level arguments) for every call `name(...)` in a C++ source text."""
+    out = []
+    for m in re.finditer(r"\b(" + name_re + r")\s*\(", text):
+        depth, i, commas, empty = 1, m.end(), 0, True
+        while i < len(text) and depth:
+            ch = text[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            if depth and not ch.isspace():
+                empty = False
+            i += 1
+        out.append((m.group(1), 0 if empty else commas + 1))
+    return out
+
+
+def test_r_shim_calls_match_the_header_arity():
+    """The Rcpp shim (flgp_b200/r_shim/flgp_shim.cpp) cannot be compiled here (no R toolchain): at least every call it
+    makes into the C ABI passes as many arguments as include/flgp.h declares."""
+    text = open(os.path.join(ROOT, "include", "flgp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    want = {}
+    for name, args in re.findall(r"\b(flgp_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = " ".join(args.split())
+        want[name] = 0 if args in ("", "void") else len(args.split(","))
+    shim = open(os.path.join(ROOT, "flgp_b200", "r_shim", "flgp_shim.cpp")).read()
+    shim = re.sub(r"//[^\n]*", "", shim)
+    shim = re.sub(r"/\*.*?\*/", "", shim, flags=re.S)
+    calls = [(n, k) for n, k in _call_arities(shim) if n in want]
+    assert len(calls) >= 30
+    bad = [(n, k, want[n]) for n, k in calls if k != want[n]]
+    assert not bad, bad
+
+
 def test_no_silent_fallback_without_gpu(flgp):
     import torch
 
