@@ -134,6 +134,8 @@ def _declare(lib):
                                                   p_i32, c_u64, C.c_int, C.POINTER(C.c_int), p_f64, p_f64, p_f64, p_f64,
                                                   p_f64, p_f64]),
         "flgp_marginal_log_likelihood_logit_la": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_double, C.c_int, p_f64]),
+        "flgp_classification_fold_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_double,
+                                                    C.c_double, C.c_int, p_f64, p_f64]),
         "flgp_multi_train_split": (C.c_int, [p_f64, c_i64, C.c_int, C.POINTER(C.c_int), p_f64]),
         "flgp_negative_log_likelihood": (C.c_int, [p_f64, p_f64, p_f64, c_i64, C.c_char_p, p_f64]),
         "flgp_test_regression": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, c_i64, p_f64]),

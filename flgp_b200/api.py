@@ -605,6 +605,20 @@ def marginal_log_likelihood_logit_la_cpp(Cm, Y, N=None, tol: float = 1e-5, max_i
     return out.value
 
 
+def classification_fold_rows(V1, values, Y, t: float, sigma: float = 1e-3, tol: float = 1e-5, max_iter: int = 100):
+    """The m-sized half of posterior_distribution_classification as the logit drivers call it, folded onto the
+    eigenvector rows: (coef[K], Mq[K, K]) with mean = V_new @ coef, cov = rowsum((V_new @ Mq) * V_new) + sigma.  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    coef = np.zeros(K)
+    Mq = np.zeros((K, K), order="F")
+    check(_lib.load().flgp_classification_fold_rows(_pf(V1), _pf(values), _pf(Y), m, K, t, sigma, tol, max_iter,
+                                                    _pf(coef), _pf(Mq)))
+    return coef, Mq
+
+
 def multi_train_split(Y) -> np.ndarray:
     """multi_train_split (src/MultiClassification.cpp:14-27): m x J one-vs-rest indicator matrix, J = max(Y) + 1."""
     Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)

@@ -695,8 +695,11 @@ __global__ void coldot_sub_kernel(const double* __restrict__ A, const double* __
 //   pi = 1 / (1 + exp(-f)), W = pi (1 - pi), B = I + sqrt(W) C11 sqrt(W), b = W f + (Y - pi),
 //   a = b - sqrt(W) B^-1 sqrt(W) (C11 b), f <- C11 a, until |f - f_new|_1 < tol.
 // Returns pi (m) and beta = sqrt(W) B^-1 sqrt(W) (m x m, column-major) at the mode.
+// beta == nullptr: the caller takes the factors instead (sw_out = sqrt(W), Bchol_out = lower Cholesky factor of B) and
+// applies beta to what it needs by solves — m x K right-hand sides instead of the m x m inverse.
 void laplace_mode(const std::vector<double>& C11, const double* Y, int m, double tol, int max_iter,
-                  std::vector<double>& pi, std::vector<double>& beta) {
+                  std::vector<double>& pi, std::vector<double>* beta, std::vector<double>* sw_out = nullptr,
+                  std::vector<double>* Bchol_out = nullptr) {
   std::vector<double> f(m, 0.0), W(m), sw(m), b(m), cb(m), a(m), fn(m), B((size_t)m * m);
   pi.assign(m, 0.5);
   auto refresh = [&]() {
@@ -730,11 +733,15 @@ void laplace_mode(const std::vector<double>& C11, const double* Y, int m, double
     if (diff < tol) break;
   }
   refresh();
-  beta.assign((size_t)m * m, 0.0);
-  for (int i = 0; i < m; ++i) beta[i + (size_t)m * i] = 1.0;
-  chol_solve(B, m, beta.data(), m);
-  for (int j = 0; j < m; ++j)
-    for (int i = 0; i < m; ++i) beta[i + (size_t)m * j] = (sw[i] * beta[i + (size_t)m * j]) * sw[j];
+  if (beta) {
+    beta->assign((size_t)m * m, 0.0);
+    for (int i = 0; i < m; ++i) (*beta)[i + (size_t)m * i] = 1.0;
+    chol_solve(B, m, beta->data(), m);
+    for (int j = 0; j < m; ++j)
+      for (int i = 0; i < m; ++i) (*beta)[i + (size_t)m * j] = (sw[i] * (*beta)[i + (size_t)m * j]) * sw[j];
+  }
+  if (sw_out) *sw_out = sw;
+  if (Bchol_out) *Bchol_out = std::move(B);
 }
 
 // The m-sized half of posterior_distribution_classification as the logit drivers call it (src/Fit.cpp:563-582), from the
@@ -754,8 +761,8 @@ void laplace_fold(const double* Vh, int KK, int K, const std::vector<double>& ev
       for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
       C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
     }
-  std::vector<double> pi, beta;
-  laplace_mode(C11, Yh, m, tol, max_iter, pi, beta);
+  std::vector<double> pi, sw, Bc;
+  laplace_mode(C11, Yh, m, tol, max_iter, pi, nullptr, &sw, &Bc);
   std::vector<double> T1((size_t)m * K);
   coef.assign(KK, 0.0);
   Mq.assign((size_t)KK * KK, 0.0);
@@ -764,12 +771,12 @@ void laplace_fold(const double* Vh, int KK, int K, const std::vector<double>& ev
     for (int i = 0; i < m; ++i) acc += V(i, k) * (Yh[i] - pi[i]);
     coef[k] = lam[k] * acc;
   }
-  for (int k = 0; k < K; ++k)  // T1 = beta V1 (m x K, column-major)
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += beta[i + (size_t)m * j] * V(j, k);
-      T1[i + (size_t)m * k] = acc;
-    }
+  // T1 = beta V1 = sqrt(W) B^-1 (sqrt(W) V1)  (m x K, column-major): K solves with the factor of B, no m x m inverse
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < m; ++i) T1[i + (size_t)m * k] = sw[i] * V(i, k);
+  chol_solve(Bc, m, T1.data(), K);
+  for (int k = 0; k < K; ++k)
+    for (int i = 0; i < m; ++i) T1[i + (size_t)m * k] *= sw[i];
   for (int b2 = 0; b2 < K; ++b2)
     for (int a2 = 0; a2 < K; ++a2) {
       double acc = 0.0;
@@ -2282,6 +2289,19 @@ int flgp_marginal_log_likelihood_logit_la(const double* Cm, const double* Y, con
   });
 }
 
+int flgp_classification_fold_rows(const double* V1, const double* values, const double* Y, int m, int K, double t,
+                                  double sigma, double tol, int max_iter, double* coef, double* Mq) {
+  return guard([&] {
+    need(V1 && values && Y && coef && Mq, "null argument");
+    need(m >= 1 && m <= 8192 && K >= 1, "classification: need 1 <= m <= 8192 labelled rows");
+    std::vector<double> ev(K), cf, mq;
+    for (int k = 0; k < K; ++k) ev[k] = 1.0 - values[k];
+    laplace_fold(V1, K, K, ev, Y, m, t, sigma, tol > 0.0 ? tol : 1e-5, max_iter > 0 ? max_iter : 100, cf, mq);
+    std::memcpy(coef, cf.data(), sizeof(double) * K);
+    std::memcpy(Mq, mq.data(), sizeof(double) * K * K);
+  });
+}
+
 int flgp_multi_train_split(const double* Y, int64_t m, int J_cap, int* J_out, double* aug_y) {
   return guard([&] {
     need(Y && J_out, "null argument");
@@ -2354,7 +2374,7 @@ int flgp_posterior_distribution_classification(flgp_ctx* ctx, const double* C11,
     need(m >= 1 && m <= 8192 && m_new >= 0, "classification: need 1 <= m <= 8192 labelled rows");
     Ctx* c = on_device(&ctx->c);
     std::vector<double> c11(C11, C11 + (size_t)m * m), pi, beta;
-    laplace_mode(c11, Y, m, tol, max_iter > 0 ? max_iter : 100, pi, beta);
+    laplace_mode(c11, Y, m, tol, max_iter > 0 ? max_iter : 100, pi, &beta);
     if (m_new == 0) return;
     // C21 (m_new x m, column-major) is the row-major m x m_new matrix R = C21^T:
     //   mean = (Y - pi)^T R  (1 x m_new),   T^T = beta R  (m x m_new),   cov = C22 - colsum(T^T o R)

@@ -332,6 +332,14 @@ int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y,
  * N = trials per row (NULL = all 1); tol <= 0 / max_iter <= 0 take the reference's defaults 1e-5 / 100. */
 int flgp_marginal_log_likelihood_logit_la(const double* C, const double* Y, const double* N, int m, double tol,
                                           int max_iter, double* out);
+/* posterior_distribution_classification (src/Utils.cpp:252-299) as the logit drivers call it (src/Fit.cpp:563-582),
+ * folded onto the eigenvector rows: from the m labelled rows V1 (m x K ROW-major) and `values` (K), at diffusion time t,
+ * the Newton mode of the Laplace approximation and the two operators
+ *   coef (K) = Lam V1^T (Y - pi),   Mq (K x K column-major) = Lam - Lam V1^T beta V1 Lam,
+ * so that any row v of the eigenvectors has posterior mean v . coef and variance v Mq v^T + sigma.  This is the m-sized
+ * half of flgp_classification_posterior_fixed / flgp_fit_*_logit (their n-sized half runs on the device). */
+int flgp_classification_fold_rows(const double* V1, const double* values, const double* Y, int m, int K, double t,
+                                  double sigma, double tol, int max_iter, double* coef, double* Mq);
 /* multi_train_split (src/MultiClassification.cpp:14-27): J = max(Y) + 1, aug_y (m x J column-major, may be NULL to
  * query J) = one-vs-rest indicator columns. */
 int flgp_multi_train_split(const double* Y, int64_t m, int J_cap, int* J_out, double* aug_y);

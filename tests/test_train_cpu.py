@@ -287,3 +287,25 @@ def test_diff_noise_objective_training_and_prediction_rows(oracle, m, K):
         np.testing.assert_allclose(V[m:, :K] @ coef, pred, rtol=1e-8, atol=1e-9 * np.abs(pred).max())
     with pytest.raises(F.FlgpError):
         F.regression_objective_diff_rows(V[:m], values, Y, x[:-1])
+
+
+@pytest.mark.parametrize("m,K", [(60, 25), (20, 30)])
+def test_classification_fold_rows_matches_the_literal_posterior(oracle, m, K):
+    """posterior_distribution_classification (src/Utils.cpp:252-299) folded onto the eigenvector rows (library host code:
+    Newton mode, coef = Lam V1^T (Y - pi), Mq = Lam - Lam V1^T beta V1 Lam through solves with the factor of B) against
+    the oracle's literal restatement on explicit covariance blocks: mean and variance of the unlabelled rows to 1e-9."""
+    V, values, Y, idx = _toy_logit_problem(seed=m, m=m, K=K)
+    n, sigma = len(V), 1e-3
+    idx1 = np.arange(m, n, dtype=np.int32)
+    for t in (2.0, 9.0):
+        coef, Mq = F.classification_fold_rows(V[:m], values, Y, t, sigma)
+        mean = V[m:, :K] @ coef
+        cov = ((V[m:, :K] @ Mq) * V[m:, :K]).sum(axis=1) + sigma
+        C11 = oracle.hk_from_spectrum(V, values, K, t, idx, idx)
+        C11[np.diag_indices(m)] += sigma
+        C21 = oracle.hk_from_spectrum(V, values, K, t, idx1, idx)
+        C22 = ((V[m:, :K] * np.exp(-t * (1.0 - values[:K]))) * V[m:, :K]).sum(axis=1) + sigma
+        mo, co = oracle.posterior_distribution_classification(C11, C21, C22, Y)
+        np.testing.assert_allclose(mean, mo, rtol=1e-9, atol=1e-10 * max(1.0, np.abs(mo).max()))
+        np.testing.assert_allclose(cov, co, rtol=1e-8, atol=1e-9 * max(1.0, np.abs(co).max()))
+        np.testing.assert_allclose(Mq, Mq.T, rtol=0, atol=1e-12 * np.abs(Mq).max())
