@@ -309,3 +309,45 @@ def test_classification_fold_rows_matches_the_literal_posterior(oracle, m, K):
         np.testing.assert_allclose(mean, mo, rtol=1e-9, atol=1e-10 * max(1.0, np.abs(mo).max()))
         np.testing.assert_allclose(cov, co, rtol=1e-8, atol=1e-9 * max(1.0, np.abs(co).max()))
         np.testing.assert_allclose(Mq, Mq.T, rtol=0, atol=1e-12 * np.abs(Mq).max())
+
+
+def test_host_cholesky_is_the_textbook_form_bit_for_bit():
+    """The library's blocked, column-oriented Cholesky / substitutions (csrc/capi.cu: chol_lower, chol_solve) give the
+    bits of the textbook dot-product forms (every element updated in ascending k), across panel edges (n = 31, 32, 33,
+    70): checked through test_regression_cpp = Cnv (L L^T)^{-1} Y against a plain Python transcription."""
+    rng = np.random.default_rng(3)
+    for n in (1, 5, 31, 32, 33, 70):
+        A = rng.standard_normal((n, n))
+        Cs = A @ A.T + n * np.eye(n)
+        y = rng.standard_normal(n)
+        Cnv = rng.standard_normal((3, n))
+        L = [[0.0] * n for _ in range(n)]
+        for j in range(n):
+            d = float(Cs[j, j])
+            for k in range(j):
+                d -= L[j][k] * L[j][k]
+            d = d ** 0.5
+            L[j][j] = d
+            for i in range(j + 1, n):
+                v = float(Cs[i, j])
+                for k in range(j):
+                    v -= L[i][k] * L[j][k]
+                L[i][j] = v / d
+        b = [float(v) for v in y]
+        for i in range(n):
+            v = b[i]
+            for k in range(i):
+                v -= L[i][k] * b[k]
+            b[i] = v / L[i][i]
+        for i in range(n - 1, -1, -1):
+            v = b[i]
+            for k in range(i + 1, n):
+                v -= L[k][i] * b[k]
+            b[i] = v / L[i][i]
+        want = []
+        for i in range(3):
+            acc = 0.0
+            for j in range(n):
+                acc += float(Cnv[i, j]) * b[j]
+            want.append(acc)
+        assert np.array_equal(F.test_regression_cpp(Cs, y, Cnv), np.array(want))
