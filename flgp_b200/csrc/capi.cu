@@ -100,9 +100,45 @@ std::vector<int32_t> default_init(int64_t n, int s, uint64_t seed) {
 // Right-looking in panels of 32 columns, every inner loop down a contiguous column, four panel columns per sweep of a
 // trailing column; each element still receives its updates in ascending k, so the factor is the same bit pattern as
 // from the textbook dot-product form (the training objectives run hundreds of m x m factorisations: m = 1000 at
-// config 3).
+// config 3).  For large trailing blocks the columns are dealt round-robin to host threads — a column is always updated
+// by one thread in the same order, so the bits do not depend on the thread count.
+thread_local int g_outer_workers = 1;  // how many sibling host threads run dense algebra at the same time
+
+static void chol_trailing_columns(double* A, int n, int p0, int p1, int j_begin, int j_step) {
+  for (int j = j_begin; j < n; j += j_step) {
+    double* aj = A + (size_t)n * j;
+    int k = p0;
+    for (; k + 4 <= p1; k += 4) {
+      const double* a0 = A + (size_t)n * k;
+      const double* a1 = a0 + n;
+      const double* a2 = a1 + n;
+      const double* a3 = a2 + n;
+      const double l0 = a0[j], l1 = a1[j], l2 = a2[j], l3 = a3[j];
+      for (int i = j; i < n; ++i) {
+        double v = aj[i];
+        v -= a0[i] * l0;
+        v -= a1[i] * l1;
+        v -= a2[i] * l2;
+        v -= a3[i] * l3;
+        aj[i] = v;
+      }
+    }
+    for (; k < p1; ++k) {
+      const double* ak = A + (size_t)n * k;
+      const double ljk = ak[j];
+      for (int i = j; i < n; ++i) aj[i] -= ak[i] * ljk;
+    }
+  }
+}
+
 bool chol_lower(std::vector<double>& A, int n) {
   constexpr int NB = 32;
+  static const int hw = [] {
+    const char* e = std::getenv("FLGP_HOST_THREADS");  // 1 = no threading inside the host algebra
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : (int)std::max(1u, std::thread::hardware_concurrency());
+  }();
+  const int tmax = std::max(1, std::min(16, hw / std::max(1, g_outer_workers)));
   for (int p0 = 0; p0 < n; p0 += NB) {
     const int p1 = std::min(n, p0 + NB);
     for (int j = p0; j < p1; ++j) {  // the panel's own columns (earlier panels are already applied)
@@ -118,29 +154,15 @@ bool chol_lower(std::vector<double>& A, int n) {
       aj[j] = dj;
       for (int i = j + 1; i < n; ++i) aj[i] = aj[i] / dj;
     }
-    for (int j = p1; j < n; ++j) {  // trailing columns
-      double* aj = &A[(size_t)n * j];
-      int k = p0;
-      for (; k + 4 <= p1; k += 4) {
-        const double* a0 = &A[(size_t)n * k];
-        const double* a1 = a0 + n;
-        const double* a2 = a1 + n;
-        const double* a3 = a2 + n;
-        const double l0 = a0[j], l1 = a1[j], l2 = a2[j], l3 = a3[j];
-        for (int i = j; i < n; ++i) {
-          double v = aj[i];
-          v -= a0[i] * l0;
-          v -= a1[i] * l1;
-          v -= a2[i] * l2;
-          v -= a3[i] * l3;
-          aj[i] = v;
-        }
-      }
-      for (; k < p1; ++k) {
-        const double* ak = &A[(size_t)n * k];
-        const double ljk = ak[j];
-        for (int i = j; i < n; ++i) aj[i] -= ak[i] * ljk;
-      }
+    const int rest = n - p1;
+    const int T = rest >= 384 ? std::min(tmax, rest / 96) : 1;
+    if (T <= 1) {
+      chol_trailing_columns(A.data(), n, p0, p1, p1, 1);
+    } else {
+      std::vector<std::thread> th;
+      for (int q = 1; q < T; ++q) th.emplace_back(chol_trailing_columns, A.data(), n, p0, p1, p1 + q, T);
+      chol_trailing_columns(A.data(), n, p0, p1, p1, T);
+      for (auto& t : th) t.join();
     }
   }
   return true;
@@ -653,7 +675,11 @@ std::unique_ptr<flgp_spectrum> se_grid_search(Ctx* c, const double* Xdev, int64_
   };
   if (n_a2 > 1 && concurrent) {
     std::vector<std::thread> th;
-    for (int q = 0; q < n_a2; ++q) th.emplace_back(train_one, q);
+    for (int q = 0; q < n_a2; ++q)
+      th.emplace_back([&, q] {
+        g_outer_workers = n_a2;
+        train_one(q);
+      });
     for (auto& t : th) t.join();
   } else {
     for (int q = 0; q < n_a2; ++q) train_one(q);
@@ -745,20 +771,24 @@ void laplace_mode(const std::vector<double>& C11, const double* Y, int m, double
   for (int iter = 0; iter < max_iter; ++iter) {
     refresh();
     for (int i = 0; i < m; ++i) b[i] = W[i] * f[i] + (Y[i] - pi[i]);
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += C11[i + (size_t)m * j] * b[j];
-      cb[i] = sw[i] * acc;
+    // C11 b and C11 a as column sweeps (contiguous; every row still adds its terms in ascending j: the same bits)
+    std::fill(fn.begin(), fn.end(), 0.0);
+    for (int j = 0; j < m; ++j) {
+      const double bj = b[j];
+      const double* cj = &C11[(size_t)m * j];
+      for (int i = 0; i < m; ++i) fn[i] += cj[i] * bj;
     }
+    for (int i = 0; i < m; ++i) cb[i] = sw[i] * fn[i];
     chol_solve(B, m, cb.data(), 1);
     for (int i = 0; i < m; ++i) a[i] = b[i] - sw[i] * cb[i];
     double diff = 0.0;
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += C11[i + (size_t)m * j] * a[j];
-      fn[i] = acc;
-      diff += std::fabs(f[i] - acc);
+    std::fill(fn.begin(), fn.end(), 0.0);
+    for (int j = 0; j < m; ++j) {
+      const double aj = a[j];
+      const double* cj = &C11[(size_t)m * j];
+      for (int i = 0; i < m; ++i) fn[i] += cj[i] * aj;
     }
+    for (int i = 0; i < m; ++i) diff += std::fabs(f[i] - fn[i]);
     f = fn;
     if (diff < tol) break;
   }
@@ -1913,6 +1943,7 @@ static void train_logit_classes(const LogitTrain& base, const double* Y, int64_t
   std::atomic<int> next{0};
   for (int q = 0; q < nthr; ++q)
     pool.emplace_back([&] {
+      g_outer_workers = nthr;  // the dense algebra inside shares the cores with its siblings
       for (int j = next++; j < J; j = next++) one(j);
     });
   for (auto& th : pool) th.join();
@@ -2170,7 +2201,11 @@ static void nystrom_logit_run(Ctx* c, const double* X, const double* Y, const do
   };
   if (J == 0 && !fixed && n_a2 > 1) {
     std::vector<std::thread> th;
-    for (int q = 0; q < n_a2; ++q) th.emplace_back(train_one, q);
+    for (int q = 0; q < n_a2; ++q)
+      th.emplace_back([&, q] {
+        g_outer_workers = n_a2;
+        train_one(q);
+      });
     for (auto& t : th) t.join();
   } else {
     for (int q = 0; q < n_a2; ++q) train_one(q);

@@ -519,20 +519,24 @@ double laplace_mll(const std::vector<double>& C, const double* Y, const double* 
     logdet = 0.0;
     for (int i = 0; i < m; ++i) logdet += std::log(B[i + (size_t)m * i] + 1e-9);
     for (int i = 0; i < m; ++i) b[i] = W[i] * f[i] + Y[i] * (1.0 - pi[i]) + (N[i] - Y[i]) * (-pi[i]);
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += C[i + (size_t)m * j] * b[j];
-      cb[i] = sw[i] * acc;
+    // C b and C a as column sweeps (contiguous; every row still adds its terms in ascending j: the same bits)
+    std::fill(fn.begin(), fn.end(), 0.0);
+    for (int j = 0; j < m; ++j) {
+      const double bj = b[j];
+      const double* cj = &C[(size_t)m * j];
+      for (int i = 0; i < m; ++i) fn[i] += cj[i] * bj;
     }
+    for (int i = 0; i < m; ++i) cb[i] = sw[i] * fn[i];
     chol_solve(B, m, cb.data(), 1);
     for (int i = 0; i < m; ++i) a[i] = b[i] - sw[i] * cb[i];
     double diff = 0.0;
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int j = 0; j < m; ++j) acc += C[i + (size_t)m * j] * a[j];
-      fn[i] = acc;
-      diff += std::fabs(f[i] - acc);
+    std::fill(fn.begin(), fn.end(), 0.0);
+    for (int j = 0; j < m; ++j) {
+      const double aj = a[j];
+      const double* cj = &C[(size_t)m * j];
+      for (int i = 0; i < m; ++i) fn[i] += cj[i] * aj;
     }
+    for (int i = 0; i < m; ++i) diff += std::fabs(f[i] - fn[i]);
     f = fn;
     if (diff < tol) break;
   }
