@@ -134,6 +134,10 @@ def _declare(lib):
                                                   p_i32, c_u64, C.c_int, C.POINTER(C.c_int), p_f64, p_f64, p_f64, p_f64,
                                                   p_f64, p_f64]),
         "flgp_marginal_log_likelihood_logit_la": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_double, C.c_int, p_f64]),
+        "flgp_logit_objective_rows": (C.c_int, [p_f64, p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p,
+                                                C.c_double, p_f64]),
+        "flgp_train_logit_rows": (C.c_int, [p_f64, p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p, p_f64,
+                                            p_f64, C.POINTER(C.c_int)]),
         "flgp_classification_fold_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_double,
                                                     C.c_double, C.c_int, p_f64, p_f64]),
         "flgp_multi_train_split": (C.c_int, [p_f64, c_i64, C.c_int, C.POINTER(C.c_int), p_f64]),

@@ -605,6 +605,35 @@ def marginal_log_likelihood_logit_la_cpp(Cm, Y, N=None, tol: float = 1e-5, max_i
     return out.value
 
 
+def logit_objective_rows(V1, values, Y, t: float, sigma: float = 1e-3, approach: str = "posterior", N=None) -> float:
+    """negative_marginal_likelihood_logit_cpp / negative_log_posterior_logit_cpp (src/train.cpp:14-36) on explicit
+    labelled rows V1 (m x K) of the eigenvectors.  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    obj = C.c_double()
+    check(_lib.load().flgp_logit_objective_rows(_pf(V1), _pf(values), _pf(Y), _pf(Nv), m, K, sigma, _b(approach), t,
+                                                C.byref(obj)))
+    return obj.value
+
+
+def train_logit_rows(V1, values, Y, sigma: float = 1e-3, approach: str = "posterior", t0: Optional[float] = None, N=None):
+    """train_lae_logit_gp_cpp (src/train.cpp:38-71) on explicit labelled rows: (t, objective, evaluations).  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    Nv = np.ascontiguousarray(N, dtype=np.float64).reshape(-1) if N is not None else None
+    tt = np.array([np.nan if t0 is None else t0], dtype=np.float64)
+    obj = C.c_double()
+    nev = C.c_int()
+    check(_lib.load().flgp_train_logit_rows(_pf(V1), _pf(values), _pf(Y), _pf(Nv), m, K, sigma, _b(approach), _pf(tt),
+                                            C.byref(obj), C.byref(nev)))
+    return float(tt[0]), obj.value, nev.value
+
+
 def classification_fold_rows(V1, values, Y, t: float, sigma: float = 1e-3, tol: float = 1e-5, max_iter: int = 100):
     """The m-sized half of posterior_distribution_classification as the logit drivers call it, folded onto the
     eigenvector rows: (coef[K], Mq[K, K]) with mean = V_new @ coef, cov = rowsum((V_new @ Mq) * V_new) + sigma.  Host only."""

@@ -104,6 +104,28 @@ std::vector<int32_t> default_init(int64_t n, int s, uint64_t seed) {
 // by one thread in the same order, so the bits do not depend on the thread count.
 thread_local int g_outer_workers = 1;  // how many sibling host threads run dense algebra at the same time
 
+// host threads this call may use: the machine's cores (or FLGP_HOST_THREADS) divided among the sibling workers, <= 16
+static int host_threads() {
+  static const int hw = [] {
+    const char* e = std::getenv("FLGP_HOST_THREADS");  // 1 = no threading inside the host algebra
+    const int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : (int)std::max(1u, std::thread::hardware_concurrency());
+  }();
+  return std::max(1, std::min(16, hw / std::max(1, g_outer_workers)));
+}
+// fn(begin, step): the caller's loop over items begin, begin + step, ... — one item is always done by one thread
+template <class Fn>
+static void host_parallel(int T, Fn fn) {
+  if (T <= 1) {
+    fn(0, 1);
+    return;
+  }
+  std::vector<std::thread> th;
+  for (int q = 1; q < T; ++q) th.emplace_back(fn, q, T);
+  fn(0, T);
+  for (auto& t : th) t.join();
+}
+
 static void chol_trailing_columns(double* A, int n, int p0, int p1, int j_begin, int j_step) {
   for (int j = j_begin; j < n; j += j_step) {
     double* aj = A + (size_t)n * j;
@@ -133,12 +155,7 @@ static void chol_trailing_columns(double* A, int n, int p0, int p1, int j_begin,
 
 bool chol_lower(std::vector<double>& A, int n) {
   constexpr int NB = 32;
-  static const int hw = [] {
-    const char* e = std::getenv("FLGP_HOST_THREADS");  // 1 = no threading inside the host algebra
-    const int v = e ? std::atoi(e) : 0;
-    return v > 0 ? v : (int)std::max(1u, std::thread::hardware_concurrency());
-  }();
-  const int tmax = std::max(1, std::min(16, hw / std::max(1, g_outer_workers)));
+  const int tmax = host_threads();
   for (int p0 = 0; p0 < n; p0 += NB) {
     const int p1 = std::min(n, p0 + NB);
     for (int j = p0; j < p1; ++j) {  // the panel's own columns (earlier panels are already applied)
@@ -156,14 +173,7 @@ bool chol_lower(std::vector<double>& A, int n) {
     }
     const int rest = n - p1;
     const int T = rest >= 384 ? std::min(tmax, rest / 96) : 1;
-    if (T <= 1) {
-      chol_trailing_columns(A.data(), n, p0, p1, p1, 1);
-    } else {
-      std::vector<std::thread> th;
-      for (int q = 1; q < T; ++q) th.emplace_back(chol_trailing_columns, A.data(), n, p0, p1, p1 + q, T);
-      chol_trailing_columns(A.data(), n, p0, p1, p1, T);
-      for (auto& t : th) t.join();
-    }
+    host_parallel(T, [&](int q, int step) { chol_trailing_columns(A.data(), n, p0, p1, p1 + q, step); });
   }
   return true;
 }
@@ -2351,6 +2361,50 @@ int flgp_marginal_log_likelihood_logit_la(const double* Cm, const double* Y, con
       N = ones.data();
     }
     *out = laplace_mll(Cv, Y, N, m, tol > 0.0 ? tol : 1e-5, max_iter > 0 ? max_iter : 100);
+  });
+}
+
+static LogitTrain make_logit_rows(const double* V1, const double* values, const double* Y, const double* N, int m, int K,
+                                  double sigma, bool posterior) {
+  need(V1 && values && Y, "null argument");
+  need(m >= 1 && m <= 8192 && K >= 1, "classification: need 1 <= m <= 8192 labelled rows");
+  LogitTrain T;
+  T.m = m;
+  T.K = K;
+  T.sigma = sigma;
+  T.posterior = posterior;
+  T.V.assign(V1, V1 + (size_t)m * K);
+  T.ev.resize(K);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - values[k];
+  T.Y.assign(Y, Y + m);
+  T.N.assign(m, 1.0);
+  if (N) T.N.assign(N, N + m);
+  return T;
+}
+
+int flgp_logit_objective_rows(const double* V1, const double* values, const double* Y, const double* N, int m, int K,
+                              double sigma, const char* approach, double t, double* obj) {
+  return guard([&] {
+    need(obj != nullptr, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    *obj = logit_objective(make_logit_rows(V1, values, Y, N, m, K, sigma, post), t);
+  });
+}
+
+int flgp_train_logit_rows(const double* V1, const double* values, const double* Y, const double* N, int m, int K,
+                          double sigma, const char* approach, double* t_io, double* obj, int* nevals) {
+  return guard([&] {
+    need(t_io != nullptr, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const LogitTrain T = make_logit_rows(V1, values, Y, N, m, K, sigma, post);
+    double t0 = *t_io;
+    if (!(t0 == t0) || t0 < 0.0) t0 = 10.0;  // src/train.cpp:41-43
+    double fmin = 0.0;
+    auto fn = [&](double t) { return logit_objective(T, t); };
+    *t_io = cobyla_minimize_1d(fn, std::max(t0, 1e-3), 1e-3, HUGE_VAL, 1e-4, 1000, &fmin, nevals);
+    if (obj) *obj = -fmin;
   });
 }
 

@@ -554,14 +554,20 @@ double logit_objective(const LogitTrain& T, double t) {
   const int m = T.m, K = T.K;
   std::vector<double> lam(K), C((size_t)m * m);
   for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * T.ev[k]);
-  for (int j = 0; j < m; ++j)
-    for (int i = j; i < m; ++i) {
-      double acc = 0.0;
-      const double* vi = &T.V[(size_t)i * K];
-      const double* vj = &T.V[(size_t)j * K];
-      for (int k = 0; k < K; ++k) acc += (vi[k] * lam[k]) * vj[k];
-      C[i + (size_t)m * j] = C[j + (size_t)m * i] = acc + (i == j ? T.sigma : 0.0);
-    }
+  std::vector<double> VL((size_t)m * K);  // rows scaled by lam once: the product (v_ik lam_k) v_jk keeps its two roundings
+  for (int i = 0; i < m; ++i)
+    for (int k = 0; k < K; ++k) VL[(size_t)i * K + k] = T.V[(size_t)i * K + k] * lam[k];
+  const int Tn = m >= 256 ? std::min(host_threads(), m / 64) : 1;
+  host_parallel(Tn, [&](int q, int step) {  // column j by one thread: the same sums for any thread count
+    for (int j = q; j < m; j += step)
+      for (int i = j; i < m; ++i) {
+        double acc = 0.0;
+        const double* vi = &VL[(size_t)i * K];
+        const double* vj = &T.V[(size_t)j * K];
+        for (int k = 0; k < K; ++k) acc += vi[k] * vj[k];
+        C[i + (size_t)m * j] = C[j + (size_t)m * i] = acc + (i == j ? T.sigma : 0.0);
+      }
+  });
   const double mll = laplace_mll(C, T.Y.data(), T.N.data(), m, 1e-5, 100);
   double pr = 0.0;
   if (T.posterior) pr = T.p * std::log(t + 1e-9) + std::pow(t / T.tau, -T.q);

@@ -332,6 +332,12 @@ int flgp_fit_nystrom_logit_mult(flgp_ctx* ctx, const double* X, const double* Y,
  * N = trials per row (NULL = all 1); tol <= 0 / max_iter <= 0 take the reference's defaults 1e-5 / 100. */
 int flgp_marginal_log_likelihood_logit_la(const double* C, const double* Y, const double* N, int m, double tol,
                                           int max_iter, double* out);
+/* flgp_logit_objective / flgp_train_logit on explicit labelled rows V1 (m x K ROW-major) of the eigenvectors and
+ * `values` (K): the same host code the handle-based entries run after fetching those rows (src/train.cpp:14-71, 716-760). */
+int flgp_logit_objective_rows(const double* V1, const double* values, const double* Y, const double* N, int m, int K,
+                              double sigma, const char* approach, double t, double* obj);
+int flgp_train_logit_rows(const double* V1, const double* values, const double* Y, const double* N, int m, int K,
+                          double sigma, const char* approach, double* t_io, double* obj, int* nevals);
 /* posterior_distribution_classification (src/Utils.cpp:252-299) as the logit drivers call it (src/Fit.cpp:563-582),
  * folded onto the eigenvector rows: from the m labelled rows V1 (m x K ROW-major) and `values` (K), at diffusion time t,
  * the Newton mode of the Laplace approximation and the two operators

@@ -1,6 +1,8 @@
 """Host logic of the hyper-parameter training (no GPU): the CCSA/MMA optimiser exported by the library against its
 independent Python twin in the oracle and against known minima; the oracle's restatement of the reference's training
 objective (src/train.cpp:333-436) against finite differences."""
+import os
+
 import numpy as np
 import pytest
 
@@ -351,3 +353,42 @@ def test_host_cholesky_is_the_textbook_form_bit_for_bit():
                 acc += float(Cnv[i, j]) * b[j]
             want.append(acc)
         assert np.array_equal(F.test_regression_cpp(Cs, y, Cnv), np.array(want))
+
+
+def test_logit_objective_and_training_rows_match_the_twin(oracle):
+    """The host code of the logit training on explicit labelled rows (what flgp_logit_objective / flgp_train_logit run
+    after fetching the rows from the handle): objective against the oracle's literal restatement (1e-10, both approaches,
+    with trial counts N; m large enough for the threaded covariance build), the COBYLA training against the twin
+    evaluation for evaluation, and the same objective for any number of host threads."""
+    import subprocess
+    import sys
+
+    for m, K in ((60, 25), (300, 40)):
+        V, values, Y, idx = _toy_logit_problem(seed=m, m=m, K=K)
+        N = np.where(np.arange(m) % 4 == 0, 3.0, 1.0)
+        for approach in ("posterior", "marginal"):
+            for t in (1.5, 12.0):
+                got = F.logit_objective_rows(V[:m], values, Y, t, 1e-3, approach)
+                want = oracle.logit_objective(V, values, Y, idx, K, t, 1e-3, approach)
+                assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+            got = F.logit_objective_rows(V[:m], values, np.minimum(Y * 2, N), 5.0, 1e-3, approach, N=N)
+            want = oracle.logit_objective(V, values, np.minimum(Y * 2, N), idx, K, 5.0, 1e-3, approach, N)
+            assert abs(got - want) <= 1e-10 * max(1.0, abs(want))
+        if m == 60:
+            t_l, o_l, n_l = F.train_logit_rows(V[:m], values, Y, 1e-3, "posterior")
+            f_lib = lambda t: F.logit_objective_rows(V[:m], values, Y, t, 1e-3, "posterior")  # noqa: E731
+            t_p, f_p, n_p = oracle.cobyla_minimize_1d(f_lib, 10.0)      # the twin optimiser on the library's objective
+            assert (t_l, -o_l, n_l) == (t_p, f_p, n_p)
+            t_o, o_o, _ = oracle.train_lae_logit(V, values, Y, idx, K, 1e-3, "posterior")
+            assert abs(t_l - t_o) <= 2e-3 * max(1.0, t_o) and abs(o_l - o_o) <= 1e-6 * max(1.0, abs(o_o))
+    # thread-count independence of the bits (m = 300 uses the threaded covariance build and, from m >= 416, the Cholesky)
+    code = ("import sys; sys.path.insert(0, %r); import numpy as np, flgp_b200 as F\n"
+            "rng = np.random.default_rng(1); m, K = 500, 30\n"
+            "V = np.linalg.qr(rng.standard_normal((m, K)))[0] * np.sqrt(m); vals = np.sort(rng.uniform(0.2, 1, K))[::-1]\n"
+            "Y = (V[:, 1] + 0.3 * rng.standard_normal(m) > 0).astype(float)\n"
+            "print(repr(F.logit_objective_rows(V, vals, Y, 4.0)))" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    outs = []
+    for threads in ("1", "3", "8"):
+        env = dict(os.environ, FLGP_HOST_THREADS=threads)
+        outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
+    assert outs[0] == outs[1] == outs[2] and "nan" not in outs[0]
