@@ -825,12 +825,15 @@ void laplace_fold(const double* Vh, int KK, int K, const std::vector<double>& ev
   std::vector<double> lam(K);
   for (int k = 0; k < K; ++k) lam[k] = std::exp(-t * ev[k]);
   std::vector<double> C11((size_t)m * m);
-  for (int j = 0; j < m; ++j)
-    for (int i = 0; i < m; ++i) {
-      double acc = 0.0;
-      for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
-      C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
-    }
+  const int Tn = m >= 256 ? std::min(host_threads(), m / 64) : 1;
+  host_parallel(Tn, [&](int q, int step) {  // a column by one thread: the same sums for any thread count
+    for (int j = q; j < m; j += step)
+      for (int i = 0; i < m; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < K; ++k) acc += (V(i, k) * lam[k]) * V(j, k);
+        C11[i + (size_t)m * j] = acc + (i == j ? sigma : 0.0);  // Cvv.diagonal() += sigma (src/Fit.cpp:566)
+      }
+  });
   std::vector<double> pi, sw, Bc;
   laplace_mode(C11, Yh, m, tol, max_iter, pi, nullptr, &sw, &Bc);
   std::vector<double> T1((size_t)m * K);
