@@ -143,6 +143,10 @@ def _declare(lib):
         "flgp_multi_train_split": (C.c_int, [p_f64, c_i64, C.c_int, C.POINTER(C.c_int), p_f64]),
         "flgp_negative_log_likelihood": (C.c_int, [p_f64, p_f64, p_f64, c_i64, C.c_char_p, p_f64]),
         "flgp_test_regression": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, c_i64, p_f64]),
+        "flgp_regression_objective_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p, p_f64,
+                                                     p_f64, p_f64]),
+        "flgp_train_regression_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p, p_f64,
+                                                 p_f64, C.POINTER(C.c_int)]),
         "flgp_regression_objective_diff_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p,
                                                           p_f64, p_f64, p_f64]),
         "flgp_train_regression_diff_rows": (C.c_int, [p_f64, p_f64, p_f64, C.c_int, C.c_int, C.c_double, C.c_char_p, p_f64,

@@ -508,6 +508,36 @@ def train_regression_gp(eigenpair: EigenPair, Y_local, m_total: int, K: int, sig
     return x, obj.value, nev.value
 
 
+def regression_objective_rows(V1, values, Y, pars, sigma: float = 1e-5, approach: str = "marginal"):
+    """negative_marginal_likelihood_regression_cpp / negative_log_posterior_regression_cpp, noise = "same"
+    (src/train.cpp:333-436), on explicit training rows V1 (m x K): (objective, grad[2]).  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    x = np.ascontiguousarray(pars, dtype=np.float64)
+    obj = C.c_double()
+    grad = np.zeros(2)
+    check(_lib.load().flgp_regression_objective_rows(_pf(V1), _pf(values), _pf(Y), m, K, sigma, _b(approach), _pf(x),
+                                                     C.byref(obj), _pf(grad)))
+    return obj.value, grad
+
+
+def train_regression_rows(V1, values, Y, sigma: float = 1e-5, approach: str = "posterior", x0=None):
+    """train_regression_gp_cpp, noise = "same" (src/train.cpp:557-671), on explicit training rows:
+    (pars[2], objective, evaluations).  Host only."""
+    V1 = np.ascontiguousarray(V1, dtype=np.float64)
+    m, K = V1.shape
+    values = np.ascontiguousarray(values, dtype=np.float64)[:K].copy()
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    x = np.array(x0 if x0 is not None else (np.nan, np.nan), dtype=np.float64)
+    obj = C.c_double()
+    nev = C.c_int()
+    check(_lib.load().flgp_train_regression_rows(_pf(V1), _pf(values), _pf(Y), m, K, sigma, _b(approach), _pf(x),
+                                                 C.byref(obj), C.byref(nev)))
+    return x, obj.value, nev.value
+
+
 def regression_objective_diff_rows(V1, values, Y, x, sigma: float = 1e-5, approach: str = "marginal"):
     """negative_marginal_likelihood_diff_noise_regression_cpp / negative_log_posterior_diff_noise_regression_cpp
     (src/train.cpp:438-556) on explicit training rows V1 (m x K) of the eigenvectors: (objective, grad[m + 1]).  Host only."""

@@ -1551,6 +1551,63 @@ int flgp_fit_lae_regression(flgp_ctx* ctx, const double* X, const double* Y, con
   });
 }
 
+// ---- noise = "same" on explicit training rows (host only): the statistics the device path reduces on the GPU are
+// formed here by plain loops; the objective / optimiser code is the one the handle-based entries run --------------------
+static RegTrain make_reg_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma) {
+  need(V1 && values && Y, "null argument");
+  need(m >= 1 && K >= 1, "bad matrix shape");
+  RegTrain T;
+  T.m = m;
+  T.K = K;
+  T.sigma = sigma;
+  T.ev.resize(K);
+  for (int k = 0; k < K; ++k) T.ev[k] = 1.0 - values[k];
+  if (m > K) {
+    T.VtV.assign((size_t)K * K, 0.0);
+    T.b.assign(K, 0.0);
+    for (int i = 0; i < m; ++i) {
+      const double* v = V1 + (size_t)i * K;
+      for (int b = 0; b < K; ++b) {
+        T.b[b] += v[b] * Y[i];
+        for (int a = 0; a < K; ++a) T.VtV[a + (size_t)K * b] += v[a] * v[b];
+      }
+      T.yty += Y[i] * Y[i];
+    }
+  } else {
+    T.V.assign(V1, V1 + (size_t)m * K);
+    T.Y.assign(Y, Y + m);
+  }
+  return T;
+}
+
+int flgp_regression_objective_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                   const char* approach, const double* pars, double* obj, double* grad) {
+  return guard([&] {
+    need(pars && obj, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const RegTrain T = make_reg_rows(V1, values, Y, m, K, sigma);
+    double g[2] = {0.0, 0.0};
+    *obj = reg_objective(T, pars, g, post);
+    if (grad) {
+      grad[0] = g[0];
+      grad[1] = g[1];
+    }
+  });
+}
+
+int flgp_train_regression_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                               const char* approach, double* pars_io, double* obj, int* nevals) {
+  return guard([&] {
+    need(pars_io != nullptr, "null argument");
+    bool post = true;
+    if (approach_flag(approach, &post)) fail(2, "This model selection approach is not supported!");
+    const RegTrain T = make_reg_rows(V1, values, Y, m, K, sigma);
+    const double o = train_regression(T, post, pars_io, nevals);
+    if (obj) *obj = o;
+  });
+}
+
 // ---- noise = "different" (src/train.cpp:438-556, src/Predict.cpp:76-113): host algebra on the m training rows -----------
 static RegTrainDiff make_diff_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma) {
   need(V1 && values && Y, "null argument");

@@ -357,6 +357,14 @@ int flgp_negative_log_likelihood(const double* mean, const double* cov, const do
 /* test_regression_cpp(C, Y, Cnv) (src/Predict.cpp:29-37): Y_pred = Cnv C^{-1} Y by Cholesky; C m x m, Cnv m_new x m. */
 int flgp_test_regression(const double* C, const double* Y, const double* Cnv, int m, int64_t m_new, double* Y_pred);
 
+/* flgp_regression_objective / flgp_train_regression (noise = "same") on explicit training rows V1 (m x K ROW-major) of
+ * the eigenvectors and `values` (K): host only; the objective and optimiser code of the handle-based entries, with the
+ * K x K statistics formed by plain host loops instead of the device reduction (src/train.cpp:333-436, 557-671). */
+int flgp_regression_objective_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                                   const char* approach, const double* pars, double* obj, double* grad);
+int flgp_train_regression_rows(const double* V1, const double* values, const double* Y, int m, int K, double sigma,
+                               const char* approach, double* pars_io, double* obj, int* nevals);
+
 /* ---- noise = "different": one noise variance per training row (src/train.cpp:438-556, src/Predict.cpp:76-113) -------
  * x = (t, noise_1 .. noise_m).  The *_rows entries are host algebra on explicit training rows V1 (m x K ROW-major) of the
  * eigenvectors and `values` (K, as exported: the Laplacian spectrum is 1 - values); no device work, no context.

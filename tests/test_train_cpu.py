@@ -392,3 +392,29 @@ def test_logit_objective_and_training_rows_match_the_twin(oracle):
         env = dict(os.environ, FLGP_HOST_THREADS=threads)
         outs.append(subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, check=True).stdout)
     assert outs[0] == outs[1] == outs[2] and "nan" not in outs[0]
+
+
+@pytest.mark.parametrize("m,K", [(80, 20), (12, 20)])
+def test_regression_objective_and_training_rows_match_the_twin(oracle, m, K):
+    """noise = "same" on explicit training rows, the host code of flgp_regression_objective / flgp_train_regression:
+    value 1e-11 and gradient 1e-9 against the oracle's literal restatement in both branches (m > K through V^T V, m <= K)
+    and both approaches; the MMA training is the twin's run on the library's objective, step for step."""
+    rng = np.random.default_rng(m + K)
+    n = 300
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.3, 1.0, K))[::-1]
+    values[0] = 1.0
+    idx = np.arange(m, dtype=np.int32)
+    Y = V[:m, 1] + 0.7 * V[:m, 3] + 0.2 * rng.standard_normal(m)
+    for approach in ("marginal", "posterior"):
+        for x in ((6.0, 0.4), (1.2, 0.02), (30.0, 3.0)):
+            fo, go = oracle.regression_objective(V, values, Y, idx, K, x, 1e-5, approach)
+            fl, gl = F.regression_objective_rows(V[:m], values, Y, x, 1e-5, approach)
+            assert abs(fo - fl) <= 1e-11 * max(1.0, abs(fo))
+            np.testing.assert_allclose(gl, go, rtol=1e-9, atol=1e-10)
+        xl, ol, nev = F.train_regression_rows(V[:m], values, Y, 1e-5, approach)
+        f_lib = lambda z: F.regression_objective_rows(V[:m], values, Y, z, 1e-5, approach)  # noqa: E731
+        xt, ft, nt = oracle.mma_minimize(f_lib, (10.0, 1.0), (1e-3, 1e-4), (np.inf, np.inf))
+        assert nt == nev and np.array_equal(xt, xl) and -ft == ol
+        xo, oo = oracle.train_regression(V, values, Y, idx, K, 1e-5, approach)
+        assert abs(ol - oo) <= 1e-6 * max(1.0, abs(oo))
