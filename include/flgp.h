@@ -13,7 +13,9 @@
  *     (dgRMatrix slots j, x; p[i] = i*r is implicit), explicit zeros kept (src/lae.cpp:61-67).
  *   - every function returns 0 on success; otherwise flgp_last_error() holds the message that the
  *     R shim passes to Rcpp::stop.  2 = invalid argument, 3 = CUDA error, 4 = NCCL error.
- *   - there is NO CPU fallback: without a CUDA device flgp_ctx_create fails.
+ *   - there is NO CPU fallback: without a CUDA device flgp_ctx_create fails.  Entries that take neither a context nor a
+ *     spectrum handle (the *_rows training entries, the small exported helpers, the optimisers) are m- or K-sized dense
+ *     host algebra — the part the reference's drivers also run on the host (Eigen LLT, NLopt) — and need no device.
  *   - k-means: the reference calls R's stats::kmeans (Hartigan-Wong, R RNG).  This library runs
  *     Lloyd's algorithm from explicit initial row indices `init_idx` (s distinct rows of X), or, when
  *     init_idx is NULL, from flgp_default_init(n, s, seed); at most `iter_max` (reference: 100)
