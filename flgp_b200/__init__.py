@@ -15,7 +15,7 @@ from .api import (  # noqa: F401
     v_to_z_cpp, cobyla_minimize_1d, fit_lae_logit_gp_rcpp, fit_nystrom_regression_sharded, logit_objective, train_lae_logit_gp, train_logit_mult_gp, fit_lae_logit_mult_gp_rcpp,
     fit_se_logit_gp_rcpp, fit_se_logit_mult_gp_rcpp, fit_nystrom_logit_gp_rcpp, fit_nystrom_logit_mult_gp_rcpp,
     regression_objective_rows, train_regression_rows, regression_objective_diff_rows, train_regression_diff_rows, predict_coef_diff_rows,
-    marginal_log_likelihood_logit_la_cpp, classification_fold_rows, logit_objective_rows, train_logit_rows, multi_train_split, negative_log_likelihood, test_regression_cpp,
+    marginal_log_likelihood_logit_la_cpp, classification_fold_rows, posterior_distribution_multiclassification, logit_objective_rows, train_logit_rows, multi_train_split, negative_log_likelihood, test_regression_cpp,
 )
 
 __version__ = "0.1.0"

@@ -751,6 +751,31 @@ def train_logit_mult_gp(eigenpair: EigenPair, Y, m_total: int, K: int, sigma: fl
     return t[:J.value].copy(), obj[:J.value].copy()
 
 
+def posterior_distribution_multiclassification(eigenpair, Y, m_total: int, K: int, ts, sigma: float = 1e-3, idx_new=None,
+                                               block: int = 1 << 16):
+    """posterior_distribution_multiclassification (src/Utils.cpp:339-370): per class j the Laplace posterior of the
+    one-vs-rest labels at that class's diffusion time ts[j], on the rows idx_new (default: every row after the m_total
+    labelled ones).  As in the reference the labelled block C11 carries NO sigma on its diagonal here (the binary
+    drivers add it), C22 does.  The m-sized half is the library's host fold (flgp_classification_fold_rows) on the
+    labelled rows of the eigenvectors, the rest two products per block of rows.  Returns (mean, cov), len(idx_new) x J."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64).reshape(-1)
+    ts = np.ascontiguousarray(ts, dtype=np.float64).reshape(-1)
+    if idx_new is None:
+        idx_new = np.arange(m_total, eigenpair.n_local, dtype=np.int32)
+    idx_new = np.ascontiguousarray(idx_new, dtype=np.int32)
+    values = np.asarray(eigenpair.values, dtype=np.float64)[:K]
+    V1 = np.ascontiguousarray(eigenpair.rows(np.arange(m_total, dtype=np.int32))[:, :K])
+    folds = [classification_fold_rows(V1, values, (Y == j).astype(np.float64), float(ts[j]), 0.0) for j in range(ts.size)]
+    mean = np.zeros((idx_new.size, ts.size))
+    cov = np.zeros((idx_new.size, ts.size))
+    for b0 in range(0, idx_new.size, block):
+        V2 = eigenpair.rows(idx_new[b0:b0 + block])[:, :K]
+        for j, (coef, Mq) in enumerate(folds):
+            mean[b0:b0 + block, j] = V2 @ coef
+            cov[b0:b0 + block, j] = ((V2 @ Mq) * V2).sum(axis=1) + sigma
+    return mean, cov
+
+
 def fit_lae_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-3, approach="posterior",
                                models=None, nstart: int = 1, *, init_idx=None, seed: int = 0, iter_max: int = 100,
                                ctx: Optional[Context] = None):
@@ -770,13 +795,11 @@ def fit_lae_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: 
                                   iter_max=iter_max, ctx=ctx)
     try:
         t, obj = train_logit_mult_gp(ep, Y, m, K, sigma, approach)
-        means = np.zeros((m_new, len(t)))
-        for j in range(len(t)):
-            mean, _ = posterior_distribution_classification(ep, (Y == j).astype(np.float64), m, K, float(t[j]), sigma)
-            means[:, j] = mean[m:]
+        means, covs = posterior_distribution_multiclassification(ep, Y, m, K, t, sigma)   # src/Fit.cpp:655-656
     finally:
         ep.close()
-    return {"pars": t, "obj": obj, "posterior_mean": means, "argmax_posterior_mean": means.argmax(axis=1)}
+    return {"pars": t, "obj": obj, "posterior": {"mean": means, "cov": covs}, "posterior_mean": means,
+            "argmax_posterior_mean": means.argmax(axis=1)}
 
 
 def fit_lae_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma: float = 1e-3, approach="posterior",
@@ -889,12 +912,9 @@ def fit_se_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: f
     ep = EigenPair(ctx, h)
     tj, oj = tj[:J.value].copy(), oj[:J.value].copy()
     Kk = s if K < 0 else K
-    means = np.zeros((m_new, len(tj)))
-    for j in range(len(tj)):
-        mean, _ = posterior_distribution_classification(ep, (Y == j).astype(np.float64), m, Kk, float(tj[j]), sigma)
-        means[:, j] = mean[m:]
-    return {"pars": tj, "obj_classes": oj, "obj": obj.value, "a2": a2.value, "posterior_mean": means,
-            "argmax_posterior_mean": means.argmax(axis=1), "eigenpair": ep}
+    means, covs = posterior_distribution_multiclassification(ep, Y, m, Kk, tj, sigma)   # src/Fit.cpp:888-889
+    return {"pars": tj, "obj_classes": oj, "obj": obj.value, "a2": a2.value, "posterior": {"mean": means, "cov": covs},
+            "posterior_mean": means, "argmax_posterior_mean": means.argmax(axis=1), "eigenpair": ep}
 
 
 def fit_lae_regression_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-5, approach="posterior",

@@ -919,6 +919,23 @@ def posterior_distribution_classification(C11, C21, C22, Y, tol=1e-5, max_iter=1
 
 
 # ------------------------------------------------------------------ binary GP classifier: training of t (TEST ORACLE)
+def posterior_distribution_multiclassification(V, values, Y, idx, idx_new, K, ts, sigma):
+    """posterior_distribution_multiclassification (src/Utils.cpp:339-370), literal: per class j the Laplace posterior of
+    the one-vs-rest labels at the class's own diffusion time t_j.  Note the reference's blocks here: C11 WITHOUT sigma
+    on its diagonal (unlike the binary drivers, src/Fit.cpp:566), C22 with + sigma.  Returns (mean, cov), m_new x J."""
+    Y = np.asarray(Y)
+    J = len(ts)
+    mean = np.zeros((len(idx_new), J))
+    cov = np.zeros((len(idx_new), J))
+    V2 = V[np.asarray(idx_new), :K]
+    for j in range(J):
+        C11 = hk_from_spectrum(V, values, K, ts[j], idx, idx)
+        C21 = hk_from_spectrum(V, values, K, ts[j], idx_new, idx)
+        C22 = ((V2 * np.exp(-ts[j] * (1.0 - values[:K]))) * V2).sum(axis=1) + sigma
+        mean[:, j], cov[:, j] = posterior_distribution_classification(C11, C21, C22, (Y == j).astype(np.float64))
+    return mean, cov
+
+
 def laplace_mll(Cm, Y, N=None, tol=1e-5, max_iter=100):
     """marginal_log_likelihood_logit_la_cpp (src/train.cpp:716-760), literal: Newton from f = 0, value from the LAST
     Newton step's a and chol(B)."""

@@ -418,3 +418,35 @@ def test_regression_objective_and_training_rows_match_the_twin(oracle, m, K):
         assert nt == nev and np.array_equal(xt, xl) and -ft == ol
         xo, oo = oracle.train_regression(V, values, Y, idx, K, 1e-5, approach)
         assert abs(ol - oo) <= 1e-6 * max(1.0, abs(oo))
+
+
+def test_posterior_distribution_multiclassification_against_the_literal_form(oracle):
+    """posterior_distribution_multiclassification (src/Utils.cpp:339-370; C11 without sigma, C22 with): the Python mirror
+    (library host fold on the labelled rows + two products per block of rows) against the oracle's literal restatement
+    on explicit covariance blocks.  The eigenpair is a stand-in with the two members the mirror reads (.rows, .values),
+    so the composition is checked on the CPU box; on the GPU the same members come from the spectrum handle."""
+    V, values, _, idx = _toy_logit_problem(seed=9, m=70, K=22)
+    n, m, K, sigma = len(V), 70, 22, 1e-3
+    rng = np.random.default_rng(9)
+    lab = rng.integers(0, 3, m).astype(np.float64)
+    lab[:3] = [0, 1, 2]
+    ts = np.array([3.0, 8.0, 15.0])
+
+    class FakePair:
+        n_local = n
+
+        def __init__(self):
+            self.values = values
+
+        def rows(self, ii):
+            return np.asfortranarray(V[np.asarray(ii)])
+
+    idx_new = np.arange(m, n, dtype=np.int32)
+    mean, cov = F.posterior_distribution_multiclassification(FakePair(), lab, m, K, ts, sigma, block=97)
+    mo, co = oracle.posterior_distribution_multiclassification(V, values, lab, idx, idx_new, K, ts, sigma)
+    np.testing.assert_allclose(mean, mo, rtol=1e-8, atol=1e-9 * np.abs(mo).max())
+    np.testing.assert_allclose(cov, co, rtol=1e-8, atol=1e-9 * np.abs(co).max())
+    sub = np.array([75, 80, 399], dtype=np.int32)
+    m2, c2 = F.posterior_distribution_multiclassification(FakePair(), lab, m, K, ts, sigma, idx_new=sub)
+    np.testing.assert_allclose(m2, mo[sub - m], rtol=1e-8, atol=1e-10)
+    np.testing.assert_allclose(c2, co[sub - m], rtol=1e-8, atol=1e-10)
