@@ -5,9 +5,11 @@
 // Eigen::Map aliases R memory exactly as the reference does at src/Fit.cpp:29-32) and turns a non-zero
 // status into Rcpp::stop, the reference's own error convention (src/Utils.cpp:64,123,207).
 //
-// NOT COMPILED IN THIS REPOSITORY: the build environment has no R, Rcpp or RcppEigen.  It
-// is kept deliberately thin so that review suffices; the same entry points are exercised through ctypes by
-// flgp_b200/api.py and the -m gpu tests.  Link with: PKG_LIBS += -L<dir> -lflgp_b200  (see INTEGRATION.md).
+// NOT BUILT IN THIS REPOSITORY: the build environment has no R, Rcpp or RcppEigen.  It is
+// parsed and type-checked by g++ against the reference's own headers and include/flgp.h with a type-level
+// stand-in for <RcppEigen.h> (tests/r_mock/, tests/test_abi_cpu.py: every function defined here is the definition
+// of a reference prototype, every C-ABI call has the declared argument types); the same entry points are
+// exercised through ctypes by flgp_b200/api.py and the -m gpu tests.  Link with: PKG_LIBS += -L<dir> -lflgp_b200  (see INTEGRATION.md).
 //
 // Replaces (file:line in the reference):
 //   subsample_cpp                 src/Utils.cpp:32-68          -> flgp_subsample
@@ -28,8 +30,10 @@
 // [[Rcpp::depends(RcppEigen)]]
 #include <RcppEigen.h>
 
+#include "Fit.h"      // the fit_*_gp_cpp prototypes ([[Rcpp::export]]) re-defined at the end of this file
+#include "Predict.h"  // test_pgbinary_cpp, test_regression_cpp (and train.h: ReturnValue, the exported objectives)
 #include "Spectrum.h"
-#include "Utils.h"
+#include "Utils.h"    // also MultiClassification.h: MultiClassifier, multi_train_split
 #include "flgp.h"
 #include "lae.h"
 
@@ -73,7 +77,7 @@ Eigen::SparseMatrix<double, Eigen::RowMajor> to_sparse(int n, int s, int r, cons
 Eigen::MatrixXd subsample_cpp(const Eigen::MatrixXd& X, int s, std::string method, int nstart) {
   const int n = X.rows(), d = X.cols();
   std::vector<int32_t> init = r_init(n, s);
-  Eigen::MatrixXd U(s, method == "kmeans" ? d + 1 : d);
+  Eigen::MatrixXd U(s, method == "random" ? d : d + 1);  // "kmeans" / "minibatchkmeans": centres + sizes (src/Utils.cpp:43-62)
   ok(flgp_subsample(ctx(), X.data(), n, d, s, method.c_str(), 100, nstart, init.data(), 0, U.data(), nullptr, nullptr));
   return U;
 }
@@ -295,7 +299,6 @@ Rcpp::List fit_nystrom_regression_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::Nume
 // fit_lae_logit_gp_cpp (src/Fit.cpp:521-600), signature unchanged (src/Fit.h).  Spectrum, COBYLA training of t and the
 // Laplace posterior of the test rows run behind the C ABI; the labels still come from the reference's Polya-Gamma Gibbs
 // sampler (test_pgbinary_cpp, src/Predict.cpp:11-26: R's RNG) on the covariance block C the library returns.
-Rcpp::List test_pgbinary_cpp(const Eigen::MatrixXd& Cvv, const Eigen::VectorXd& Y, const Eigen::MatrixXd& C);  // reference
 Rcpp::List fit_lae_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
                                 int s, int r, int K, Rcpp::NumericVector N_train, double sigma, std::string approach,
                                 Rcpp::List models, bool output_cov, int nstart) {
@@ -383,15 +386,14 @@ Rcpp::List fit_nystrom_logit_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVe
 // train_logit_mult_gp_cpp (src/MultiClassification.cpp:30-53) for fit_lae_logit_mult_gp_cpp (src/Fit.cpp:603-662): the J
 // one-vs-rest trainings run behind the C ABI on the spectrum handle; the MultiClassifier keeps the reference's layout
 // (aug_y + one ReturnValue(t, obj) per class), so predict_logit_mult_gp_cpp (Polya-Gamma sampler, R RNG) is unchanged.
-struct ReturnValue { double t, obj; };                                  // src/train.h
-Eigen::MatrixXd multi_train_split(const Eigen::VectorXd& Y);             // reference, src/MultiClassification.cpp:14-27
+// (ReturnValue: src/train.h:173-181)
 std::vector<ReturnValue> train_logit_mult_on_handle(flgp_spectrum* h, const Eigen::VectorXd& Y, int K, double sigma,
                                                     const std::string& approach) {
   int J = 0;
   std::vector<double> t(256), obj(256);
   ok(flgp_train_logit_mult(h, Y.data(), Y.size(), K, sigma, approach.c_str(), 256, &J, t.data(), obj.data()));
   std::vector<ReturnValue> res(J);
-  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue(t[j], obj[j]);
   return res;
 }
 
@@ -411,7 +413,7 @@ std::vector<ReturnValue> se_logit_mult_grid(const Eigen::MatrixXd& X, const Eige
                             Rcpp::as<bool>(models["root"]), nstart, 100, init.data(), 0, 256, &J, t.data(), obj.data(),
                             best_a2, max_obj, best));
   std::vector<ReturnValue> res(J);
-  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue(t[j], obj[j]);
   return res;
 }
 
@@ -433,7 +435,7 @@ std::vector<ReturnValue> nystrom_logit_mult_grid(const Eigen::MatrixXd& X, const
                                  init.data(), 0, 256, &J, t.data(), obj.data(), values.data(), vectors.data(), best_a2,
                                  max_obj));
   std::vector<ReturnValue> res(J);
-  for (int j = 0; j < J; ++j) res[j] = ReturnValue{t[j], obj[j]};
+  for (int j = 0; j < J; ++j) res[j] = ReturnValue(t[j], obj[j]);
   return res;
 }
 

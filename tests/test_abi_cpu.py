@@ -106,6 +106,29 @@ def test_r_shim_calls_match_the_header_arity():
     assert not bad, bad
 
 
+def test_r_shim_typechecks_against_the_reference_headers():
+    """flgp_b200/r_shim/flgp_shim.cpp parsed and type-checked by g++ together with the reference's OWN headers
+    (Spectrum.h, Utils.h, lae.h, Predict.h, train.h, MultiClassification.h: every [[Rcpp::export]] prototype the shim
+    re-defines, EigenPair, ReturnValue, MultiClassifier) and include/flgp.h.  R, Rcpp and Eigen are not in the image:
+    <RcppEigen.h> is the type-level stand-in of tests/r_mock/ (interfaces only, nothing is linked or run).  Catches
+    undeclared names, clashes with the reference's declarations and wrong argument types at the C ABI."""
+    import shutil
+    import subprocess
+
+    ref = "/root/reference/src"
+    if not os.path.exists(os.path.join(ref, "Spectrum.h")) or not shutil.which("g++"):
+        pytest.skip("the reference headers are not on this machine")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wmissing-declarations", "-I", os.path.join(ROOT, "tests", "r_mock"),
+           "-I", ref, "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "flgp_b200", "r_shim", "flgp_shim.cpp")]
+    p = subprocess.run(cmd, capture_output=True, text=True, env=dict(os.environ, LC_ALL="C"))
+    assert p.returncode == 0, p.stderr[-3000:]
+    # every function the shim defines at namespace scope is the definition of a prototype in the reference's headers
+    # (same name AND same parameter types — otherwise it would be a new overload and R would still call the old body);
+    # the only definitions without one are the three helpers the shim adds for the multi-class drivers
+    undeclared = set(re.findall(r"no previous declaration for '[^']*?\b([A-Za-z_][A-Za-z0-9_]*)\(", p.stderr))
+    assert undeclared == {"train_logit_mult_on_handle", "se_logit_mult_grid", "nystrom_logit_mult_grid"}, p.stderr[-3000:]
+
+
 def test_no_silent_fallback_without_gpu(flgp):
     import torch
 
