@@ -24,6 +24,7 @@
 #ifndef FLGP_H
 #define FLGP_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus

@@ -129,6 +129,20 @@ def test_r_shim_typechecks_against_the_reference_headers():
     assert undeclared == {"train_logit_mult_on_handle", "se_logit_mult_grid", "nystrom_logit_mult_grid"}, p.stderr[-3000:]
 
 
+def test_header_is_plain_c99(tmp_path):
+    """include/flgp.h is the C ABI: it must compile as C (cgo / .Call / ctypes bindings parse it as such)."""
+    import shutil
+    import subprocess
+
+    if not shutil.which("gcc"):
+        pytest.skip("no C compiler")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "flgp.h"\nint main(void) { return flgp_version(); }\n')
+    p = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I",
+                        os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr
+
+
 def test_no_silent_fallback_without_gpu(flgp):
     import torch
 
