@@ -143,6 +143,13 @@ def test_header_is_plain_c99(tmp_path):
     assert p.returncode == 0, p.stderr
 
 
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps every symbol of include/flgp.h to the reference seam it replaces (or says it has none)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [s for s in _header_symbols() if ("`" + s + "`") not in doc]
+    assert not missing, missing
+
+
 def test_no_silent_fallback_without_gpu(flgp):
     import torch
 
