@@ -845,7 +845,7 @@ def fit_se_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma
                          approach="posterior", models=None, output_cov: bool = False, nstart: int = 1, *,
                          t: Optional[float] = None, init_idx=None, seed: int = 0, iter_max: int = 100,
                          ctx: Optional[Context] = None):
-    """fit_se_logit_gp_rcpp (R/Fit.R -> src/Fit.cpp:668-794; the README's GPC call): squared-exponential weights on the
+    """fit_se_logit_gp_rcpp (R/Fit.R:598-626 -> src/Fit.cpp:668-794; the README's GPC call): squared-exponential weights on the
     KNN graph, grid search over the bandwidth a2 with the diffusion time t trained per grid point (COBYLA restatement;
     t given: the objective is evaluated there), Laplace posterior of the test rows at the winner.  models["kernel"] is
     ignored, as in the reference (SURVEY.md appendix A.12).  Y_pred (Polya-Gamma sampler on R's RNG) is not produced;
@@ -883,7 +883,7 @@ def fit_se_logit_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, N=None, sigma
 def fit_se_logit_mult_gp_rcpp(X, Y, X_new, s: int, r: int, K: int = -1, sigma: float = 1e-3, a2s=None,
                               approach="posterior", models=None, nstart: int = 1, *, init_idx=None, seed: int = 0,
                               iter_max: int = 100, ctx: Optional[Context] = None):
-    """fit_se_logit_mult_gp_rcpp (R/Fit.R -> src/Fit.cpp:797-895): the bandwidth grid with the J one-vs-rest trainings
+    """fit_se_logit_mult_gp_rcpp (R/Fit.R:365-380 -> src/Fit.cpp:797-895): the bandwidth grid with the J one-vs-rest trainings
     per grid point; the a2 with the largest summed objective wins.  As for fit_lae_logit_mult_gp_rcpp the sampled labels
     are not produced; returned: per-class (t_j, objective_j) of the winner, a2, the summed objective, the per-class
     Laplace posterior means on the test rows with their arg-max, and the winning eigenpair."""
@@ -1052,7 +1052,7 @@ def fit_nystrom_logit_gp_rcpp(X, Y, X_new, s: int, K: int = -1, N=None, sigma: f
                               approach="posterior", subsample="kmeans", output_cov: bool = False, nstart: int = 1, *,
                               t: Optional[float] = None, init_idx=None, seed: int = 0, iter_max: int = 100,
                               ctx: Optional[Context] = None):
-    """fit_nystrom_logit_gp_rcpp (R/Fit.R -> src/Fit.cpp:896-1038) without the Polya-Gamma labels: Nystrom grid with
+    """fit_nystrom_logit_gp_rcpp (R/Fit.R:661-690 -> src/Fit.cpp:896-1038) without the Polya-Gamma labels: Nystrom grid with
     the diffusion time trained per bandwidth (t given: the objective there), Laplace posterior of the test rows at the
     winner.  Returned: posterior$mean, posterior$cov, pars (= t), a2, obj, optional C."""
     if approach not in ("posterior", "marginal"):
@@ -1085,7 +1085,7 @@ def fit_nystrom_logit_mult_gp_rcpp(X, Y, X_new, s: int, K: int = -1, sigma: floa
                                    approach="posterior", subsample="kmeans", nstart: int = 1, *,
                                    return_eigenpair: bool = False, init_idx=None, seed: int = 0, iter_max: int = 100,
                                    ctx: Optional[Context] = None):
-    """The training half of fit_nystrom_logit_mult_gp_rcpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+    """The training half of fit_nystrom_logit_mult_gp_rcpp (R/Fit.R:424-435 -> src/Fit.cpp:1045-1162): per bandwidth the J one-vs-rest
     trainings on the extended labelled rows, summed objective selects.  Returned: pars (t_j), obj_classes, obj, a2 and,
     with return_eigenpair, the winning extended eigenpair (values K, vectors n x K) the reference's sampler consumes."""
     if approach not in ("posterior", "marginal"):

@@ -2176,7 +2176,7 @@ int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, cons
 }
 
 // fit_nystrom_logit_gp_cpp (src/Fit.cpp:896-1038) and the training half of fit_nystrom_logit_mult_gp_cpp
-// (src/Fit.cpp:1043-1150): the Nystrom grid of nystrom_fit with the logit trainings in place of MMA.  Single process.
+// (src/Fit.cpp:1045-1162): the Nystrom grid of nystrom_fit with the logit trainings in place of MMA.  Single process.
 // J = 0: binary — t_io (NaN trains), Laplace posterior of the test rows, optional C = [Cvv + sigma I; Cnv] (n x m).
 // J > 0: the J one-vs-rest trainings per bandwidth, summed objective selects — t_out / obj_out of the winner.
 // values_out (K) / vectors_out (n x K column-major), optional: the winning extended eigenpair (what the reference's

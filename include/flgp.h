@@ -318,7 +318,7 @@ int flgp_fit_nystrom_logit(flgp_ctx* ctx, const double* X, const double* Y, cons
                            int n_a2, const char* approach, const char* subsample, int nstart, int iter_max,
                            const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
                            double* C_out, double* best_a2, double* best_obj);
-/* The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+/* The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1045-1162): per bandwidth the J one-vs-rest
  * trainings on the extended labelled rows, summed objective selects.  t_out / obj_out (J_cap entries) of the winner;
  * values_out (K) and vectors_out (n x K column-major), both optional: the winning extended eigenpair, which is what
  * predict_logit_mult_gp_cpp (Polya-Gamma sampler, stays in R) consumes. */

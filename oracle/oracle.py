@@ -813,7 +813,7 @@ def fit_nystrom_logit(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-3, approach="po
 
 def fit_nystrom_logit_mult(X, Y, X_new, s, K, init_idx, a2s, sigma=1e-3, approach="posterior", iter_max=100,
                            nthreads=1):
-    """The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1043-1150): per bandwidth the J one-vs-rest
+    """The training half of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1045-1162): per bandwidth the J one-vs-rest
     trainings on the extended labelled rows; the summed objective selects."""
     m = len(X)
     if K < 0:
