@@ -699,7 +699,7 @@ std::unique_ptr<flgp_spectrum> se_grid_search(Ctx* c, const double* Xdev, int64_
   std::unique_ptr<flgp_spectrum> best;
   double max_obj = -std::numeric_limits<double>::infinity();
   for (int q = 0; q < n_a2; ++q) {
-    // src/Fit.cpp:169-174, 741-746, 869-874 (the first candidate is kept even when every objective is -inf)
+    // src/Fit.cpp:169-174, 737-742, 861-866 (the first candidate is kept even when every objective is -inf)
     if (objs[q] > max_obj || !best) {
       max_obj = objs[q];
       *best_q = q;
@@ -2133,7 +2133,7 @@ int flgp_fit_se_logit(flgp_ctx* ctx, const double* X, const double* Y, const dou
 }
 
 // fit_se_logit_mult_gp_cpp (src/Fit.cpp:797-895): as above with the J one-vs-rest trainings of train_logit_mult_gp_cpp
-// per bandwidth; a grid point's objective is the sum of its J class objectives (:862-866).
+// per bandwidth; a grid point's objective is the sum of its J class objectives (:855-859).
 int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
                            int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,
                            const char* approach, const char* subsample, int gl, int root, int nstart, int iter_max,

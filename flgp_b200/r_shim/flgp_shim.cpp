@@ -397,7 +397,7 @@ std::vector<ReturnValue> train_logit_mult_on_handle(flgp_spectrum* h, const Eige
   return res;
 }
 
-// The grid loop of fit_se_logit_mult_gp_cpp (src/Fit.cpp:851-875) as one call: the winning handle and the per-class
+// The grid loop of fit_se_logit_mult_gp_cpp (src/Fit.cpp:839-867) as one call: the winning handle and the per-class
 // ReturnValues; the caller builds the MultiClassifier from them and goes on with predict_logit_mult_gp_cpp unchanged.
 std::vector<ReturnValue> se_logit_mult_grid(const Eigen::MatrixXd& X, const Eigen::VectorXd& Y, const Eigen::MatrixXd& X_new,
                                             int s, int r, int K, double sigma, const std::vector<double>& a2s,
@@ -417,7 +417,7 @@ std::vector<ReturnValue> se_logit_mult_grid(const Eigen::MatrixXd& X, const Eige
   return res;
 }
 
-// The grid loop of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1088-1147) as one call: per-class ReturnValues and the
+// The grid loop of fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:1087-1132) as one call: per-class ReturnValues and the
 // winning extended EigenPair (values K, vectors n x K); predict_logit_mult_gp_cpp goes on unchanged from there.
 std::vector<ReturnValue> nystrom_logit_mult_grid(const Eigen::MatrixXd& X, const Eigen::VectorXd& Y,
                                                  const Eigen::MatrixXd& X_new, int s, int K, double sigma,

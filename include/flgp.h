@@ -290,7 +290,7 @@ int flgp_fit_lae_logit(flgp_ctx* ctx, const double* X, const double* Y, const do
                        double* C_out, double* obj);
 /* fit_se_logit_gp_cpp (src/Fit.cpp:668-794; R wrapper fit_se_logit_gp_rcpp, the README's GPC example) without the
  * Polya-Gamma label sampler: one k-means + KNN, then per a2 of the grid Z = exp(-dist / (a2 * mean dist)) -> graph
- * Laplacian -> spectrum -> COBYLA training of t (src/Fit.cpp:718-747); the a2 with the largest objective wins.
+ * Laplacian -> spectrum -> COBYLA training of t (src/Fit.cpp:712-743); the a2 with the largest objective wins.
  * *t_io = NaN trains; a finite value is used at every grid point as given (the objective is then evaluated there).
  * post_mean / post_cov / C_out as flgp_fit_lae_logit; *best_a2, *best_obj, out (the winning handle; caller frees) may
  * be NULL.  Single process. */
@@ -300,7 +300,7 @@ int flgp_fit_se_logit(flgp_ctx* ctx, const double* X, const double* Y, const dou
                       const int32_t* init_idx, uint64_t seed, double* t_io, double* post_mean, double* post_cov,
                       double* C_out, double* best_a2, double* best_obj, flgp_spectrum** out);
 /* fit_se_logit_mult_gp_cpp (src/Fit.cpp:797-895) without the label sampler: the same grid with the J one-vs-rest
- * trainings of flgp_train_logit_mult per a2; a grid point's objective is the sum of its class objectives (:862-866).
+ * trainings of flgp_train_logit_mult per a2; a grid point's objective is the sum of its class objectives (:855-859).
  * t_out / obj_out (J_cap entries; obj_out may be NULL) <- (t_j, objective_j) of the winning a2. */
 int flgp_fit_se_logit_mult(flgp_ctx* ctx, const double* X, const double* Y, const double* X_new, int64_t m,
                            int64_t m_new, int d, int s, int r, int K, double sigma, const double* a2s, int n_a2,

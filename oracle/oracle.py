@@ -1069,7 +1069,7 @@ def _se_grid(X, X_new, s, r, K, init_idx, a2s, gl, root, iter_max, nthreads):
 def fit_se_logit(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-3, approach="posterior", gl="cluster-normalized",
                  root=True, iter_max=100, nthreads=1, N=None, t=None):
     """fit_se_logit_gp_cpp (src/Fit.cpp:668-794) without the label sampler: the bandwidth grid with the diffusion time
-    trained per grid point (t given: the objective at t), the largest objective wins (:741-746); Laplace posterior of
+    trained per grid point (t given: the objective at t), the largest objective wins (:737-742); Laplace posterior of
     the test rows at the winner (:752-773)."""
     m = len(X)
     n = m + len(X_new)
@@ -1098,7 +1098,7 @@ def fit_se_logit(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-3, approach="post
 def fit_se_logit_mult(X, Y, X_new, s, r, K, init_idx, a2s, sigma=1e-3, approach="posterior",
                       gl="cluster-normalized", root=True, iter_max=100, nthreads=1):
     """fit_se_logit_mult_gp_cpp (src/Fit.cpp:797-895) without the label sampler: per a2 the J one-vs-rest trainings;
-    the grid point's objective is the sum of the class objectives (:862-866)."""
+    the grid point's objective is the sum of the class objectives (:855-859)."""
     m = len(X)
     if K < 0:
         K = s

@@ -153,7 +153,7 @@ def test_laplace_mll_matches_direct_newton(oracle):
 
 
 def test_se_logit_grid_twins_select_the_largest_objective(oracle):
-    """The oracle twins of fit_se_logit_gp_cpp / fit_se_logit_mult_gp_cpp (src/Fit.cpp:718-747, 851-875): the grid
+    """The oracle twins of fit_se_logit_gp_cpp / fit_se_logit_mult_gp_cpp (src/Fit.cpp:712-743, 839-867): the grid
     point with the largest (summed) objective wins, first one on ties; a one-point grid is that point's training;
     at a fixed t the objective is the plain logit objective of the winning spectrum."""
     rng = np.random.default_rng(4)
@@ -183,7 +183,7 @@ def test_se_logit_grid_twins_select_the_largest_objective(oracle):
 
 
 def test_nystrom_logit_twins_select_the_largest_objective(oracle):
-    """The oracle twins of fit_nystrom_logit_gp_cpp / fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:942-998, 1088-1132)
+    """The oracle twins of fit_nystrom_logit_gp_cpp / fit_nystrom_logit_mult_gp_cpp (src/Fit.cpp:942-990, 1087-1132)
     against their own pieces: grid selection by the largest (summed) objective, a fixed t evaluates the objective there,
     the regression twin's extension is the one the logit twins train on."""
     rng = np.random.default_rng(8)
