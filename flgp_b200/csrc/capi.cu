@@ -699,7 +699,7 @@ std::unique_ptr<flgp_spectrum> se_grid_search(Ctx* c, const double* Xdev, int64_
   std::unique_ptr<flgp_spectrum> best;
   double max_obj = -std::numeric_limits<double>::infinity();
   for (int q = 0; q < n_a2; ++q) {
-    // src/Fit.cpp:169-174, 737-742, 861-866 (the first candidate is kept even when every objective is -inf)
+    // src/Fit.cpp:172-177, 737-742, 861-866 (the first candidate is kept even when every objective is -inf)
     if (objs[q] > max_obj || !best) {
       max_obj = objs[q];
       *best_q = q;
