@@ -439,26 +439,86 @@ std::vector<ReturnValue> nystrom_logit_mult_grid(const Eigen::MatrixXd& X, const
   return res;
 }
 
-// The small exported helpers, signatures unchanged (src/train.h, src/MultiClassification.h, src/Utils.h, src/Predict.h)
-double marginal_log_likelihood_logit_la_cpp(const Eigen::MatrixXd& C, const Eigen::VectorXd& Y, const Eigen::VectorXd& N,
-                                            double tol, int max_iter) {
-  double out = 0.0;
-  ok(flgp_marginal_log_likelihood_logit_la(C.data(), Y.data(), N.data(), (int)Y.size(), tol, max_iter, &out));
-  return out;
+// ---- the three multi-class drivers, signatures unchanged (src/Fit.h): spectrum / grids and the J one-vs-rest trainings
+// behind the C ABI; labels and the `posterior` entry through the reference's own predict_logit_mult_gp_cpp (Polya-Gamma
+// sampler on R's RNG) and posterior_distribution_multiclassification, on the EigenPair the library hands back --------------
+namespace {
+Rcpp::List mult_tail(const EigenPair& eigenpair, const Eigen::VectorXd& Y, const std::vector<ReturnValue>& res_vec, int m,
+                     int m_new, int K, double sigma) {
+  const MultiClassifier multiclassifier(multi_train_split(Y), res_vec);
+  const int n = m + m_new;
+  const Eigen::VectorXi idx = Eigen::VectorXi::LinSpaced(m, 0, m - 1);
+  const Eigen::VectorXi idx_pred = Eigen::VectorXi::LinSpaced(n, 0, n - 1);
+  const Eigen::VectorXi idx_new = Eigen::VectorXi::LinSpaced(m_new, m, n - 1);
+  const Eigen::VectorXd label_pred = predict_logit_mult_gp_cpp(multiclassifier, eigenpair, idx, idx_pred, K, sigma);
+  const Eigen::VectorXd train_pred = label_pred.head(m), test_pred = label_pred.tail(m_new);
+  Rcpp::List Y_pred = Rcpp::List::create(Rcpp::Named("train") = train_pred, Rcpp::Named("test") = test_pred);
+  Rcpp::List post = posterior_distribution_multiclassification(eigenpair, multiclassifier, idx, idx_new, K, sigma);
+  return Rcpp::List::create(Rcpp::Named("Y_pred") = Y_pred, Rcpp::Named("posterior") = post);
 }
-Eigen::MatrixXd multi_train_split(const Eigen::VectorXd& Y) {
-  int J = 0;
-  ok(flgp_multi_train_split(Y.data(), Y.size(), 0, &J, nullptr));
-  Eigen::MatrixXd aug(Y.size(), J);
-  ok(flgp_multi_train_split(Y.data(), Y.size(), J, &J, aug.data()));
-  return aug;
+}  // namespace
+
+Rcpp::List fit_lae_logit_mult_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                     int s, int r, int K, double sigma, std::string approach, Rcpp::List models,
+                                     int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::VectorXd Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows();
+  if (K < 0) K = s;
+  const std::string sub = Rcpp::as<std::string>(models["subsample"]), ker = Rcpp::as<std::string>(models["kernel"]);
+  std::vector<int32_t> init = r_init(m + m_new, s);
+  flgp_spectrum* h = nullptr;
+  ok(flgp_heat_kernel_spectrum(ctx(), X.data(), m, X_new.data(), m_new, (int)X.cols(), s, r, K, sub.c_str(), ker.c_str(),
+                               gl_code(Rcpp::as<std::string>(models["gl"])), Rcpp::as<bool>(models["root"]), nstart, 0.1,
+                               100, init.data(), 0, &h));
+  const std::vector<ReturnValue> res_vec = train_logit_mult_on_handle(h, Y, K, sigma, approach);
+  const EigenPair eigenpair = from_handle(h);  // materialises {values, vectors} and frees the handle
+  return mult_tail(eigenpair, Y, res_vec, m, m_new, K, sigma);
 }
-Eigen::VectorXd test_regression_cpp(const Eigen::MatrixXd& C, const Eigen::VectorXd& Y, const Eigen::MatrixXd& Cnv) {
-  Eigen::VectorXd out(Cnv.rows());
-  ok(flgp_test_regression(C.data(), Y.data(), Cnv.data(), (int)Y.size(), Cnv.rows(), out.data()));
-  return out;
+
+Rcpp::List fit_se_logit_mult_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train, Rcpp::NumericMatrix X_test,
+                                    int s, int r, int K, double sigma, std::vector<double> a2s, std::string approach,
+                                    Rcpp::List models, int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::VectorXd Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows();
+  if (K < 0) K = s;
+  flgp_spectrum* h = nullptr;
+  double a2 = 0.0, obj = 0.0;
+  const std::vector<ReturnValue> res_vec = se_logit_mult_grid(X, Y, X_new, s, r, K, sigma, a2s, approach, models, nstart, &h,
+                                                              &a2, &obj);
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", the objective function is "
+              << obj << "\n";
+  const EigenPair eigenpair = from_handle(h);
+  return mult_tail(eigenpair, Y, res_vec, m, m_new, K, sigma);
 }
-// negative_log_likelihood: type == "regression" -> flgp_negative_log_likelihood; the sampled types keep the reference body.
+
+Rcpp::List fit_nystrom_logit_mult_gp_cpp(Rcpp::NumericMatrix X_train, Rcpp::NumericVector Y_train,
+                                         Rcpp::NumericMatrix X_test, int s, int K, double sigma, std::vector<double> a2s,
+                                         std::string approach, std::string subsample, int nstart) {
+  const Eigen::Map<Eigen::MatrixXd> X(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_train));
+  const Eigen::VectorXd Y(Rcpp::as<Eigen::Map<Eigen::VectorXd>>(Y_train));
+  const Eigen::Map<Eigen::MatrixXd> X_new(Rcpp::as<Eigen::Map<Eigen::MatrixXd>>(X_test));
+  const int m = X.rows(), m_new = X_new.rows();
+  if (K < 0) K = s;
+  Eigen::VectorXd values;
+  Eigen::MatrixXd vectors;
+  double a2 = 0.0, obj = 0.0;
+  const std::vector<ReturnValue> res_vec = nystrom_logit_mult_grid(X, Y, X_new, s, K, sigma, a2s, approach, subsample, nstart,
+                                                                   values, vectors, &a2, &obj);
+  Rcpp::Rcout << "By " << approach << " method, optimal epsilon = " << std::sqrt(a2) << ", the objective function is "
+              << obj << "\n";
+  const EigenPair eigenpair(values, vectors);
+  return mult_tail(eigenpair, Y, res_vec, m, m_new, K, sigma);
+}
+
+// The small exported helpers (marginal_log_likelihood_logit_la_cpp, multi_train_split, test_regression_cpp,
+// negative_log_likelihood) are m-sized host algebra in the reference as well: their bodies stay where they are
+// (src/train.cpp, src/MultiClassification.cpp, src/Predict.cpp, src/Utils.cpp).  The library offers the same functions
+// to callers without R (flgp_marginal_log_likelihood_logit_la, flgp_multi_train_split, flgp_test_regression,
+// flgp_negative_log_likelihood); re-defining them here would only duplicate symbols the package already links.
 
 // [[Rcpp::export(posterior_distribution_classification)]]  -- signature unchanged (src/Utils.h:77-80)
 Rcpp::List posterior_distribution_classification(const Eigen::MatrixXd& C11, const Eigen::MatrixXd& C21,

@@ -57,6 +57,7 @@ class Matrix : public MatrixBase<Matrix<S, R, C, Opt, MR, MC>> {
   static Matrix Constant(Index, S) { return {}; }
   static Matrix Constant(Index, Index, S) { return {}; }
   static Matrix Zero(Index, Index = 1) { return {}; }
+  static Matrix LinSpaced(Index, S, S) { return {}; }
   template <class F>
   static CwiseNullaryOp<F, Matrix> NullaryExpr(Index, Index, const F&) { return {}; }
   // any dense matrix converts to any other (Eigen checks shapes at run time)
