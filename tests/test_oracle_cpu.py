@@ -479,3 +479,48 @@ def test_golden_fixture_late_round2_rows(oracle):
     assert nl["a2"] == float(g["nl_a2"])
     np.testing.assert_allclose(nl["obj"], g["nl_obj"], rtol=1e-8)
     np.testing.assert_allclose(nl["mean"][:200], g["nl_mean"], rtol=1e-6, atol=1e-7)
+
+
+def test_laplace_objective_against_sklearn_gpc(oracle):
+    """marginal_log_likelihood_logit_la_cpp and posterior_distribution_classification restated vs scikit-learn's
+    GaussianProcessClassifier (its own Newton iteration and Laplace formula, GPML algorithms 3.1 / 3.2, logistic link) on
+    the same precomputed covariance: approximate log marginal likelihood to 1e-6 (the reference adds 1e-9 inside the log
+    of the Cholesky diagonal and stops on |df|_1 < 1e-5), identical predicted labels on the held-out rows."""
+    from sklearn.gaussian_process import GaussianProcessClassifier
+    from sklearn.gaussian_process.kernels import Kernel
+
+    class Precomputed(Kernel):
+        """k(i, j) = C[i, j] on integer 'inputs' (no hyper-parameters)."""
+
+        def __init__(self, C):
+            self.C = C
+
+        def __call__(self, X, Y=None, eval_gradient=False):
+            i = np.asarray(X)[:, 0].astype(int)
+            j = i if Y is None else np.asarray(Y)[:, 0].astype(int)
+            Kij = self.C[np.ix_(i, j)]
+            return (Kij, np.empty((len(i), len(i), 0))) if eval_gradient else Kij
+
+        def diag(self, X):
+            return np.diag(self.C)[np.asarray(X)[:, 0].astype(int)].copy()
+
+        def is_stationary(self):
+            return False
+
+    rng = np.random.default_rng(0)
+    n, K, m = 400, 25, 60
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.2, 1.0, K))[::-1]
+    values[0] = 1.0
+    Y = (V[:m, 1] * 1.5 + V[:m, 2] + 0.3 * rng.standard_normal(m) > 0).astype(np.float64)
+    every = np.arange(n, dtype=np.int32)
+    for t in (2.0, 9.0):
+        C = oracle.hk_from_spectrum(V, values, K, t, every, every)
+        C[np.diag_indices(n)] += 1e-3
+        gpc = GaussianProcessClassifier(kernel=Precomputed(C), optimizer=None, max_iter_predict=200)
+        gpc.fit(np.arange(m, dtype=np.float64)[:, None], Y)
+        ours = oracle.laplace_mll(C[:m, :m].copy(), Y)
+        assert abs(ours - gpc.log_marginal_likelihood_value_) <= 1e-6 * abs(ours)
+        mean, cov = oracle.posterior_distribution_classification(C[:m, :m].copy(), C[m:, :m].copy(), np.diag(C)[m:].copy(), Y)
+        labels = gpc.predict(np.arange(m, n, dtype=np.float64)[:, None])
+        assert np.array_equal(mean > 0, labels > 0.5) and np.all(cov > 0)
