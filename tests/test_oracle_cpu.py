@@ -524,3 +524,50 @@ def test_laplace_objective_against_sklearn_gpc(oracle):
         mean, cov = oracle.posterior_distribution_classification(C[:m, :m].copy(), C[m:, :m].copy(), np.diag(C)[m:].copy(), Y)
         labels = gpc.predict(np.arange(m, n, dtype=np.float64)[:, None])
         assert np.array_equal(mean > 0, labels > 0.5) and np.all(cov > 0)
+
+
+@pytest.mark.parametrize("m", [80, 12])
+def test_regression_tail_and_objective_against_sklearn_gpr(oracle, m):
+    """predict_regression_cpp / posterior_covariance_regression / negative_marginal_likelihood_regression_cpp restated vs
+    scikit-learn's GaussianProcessRegressor on the same precomputed heat kernel (alpha = noise + sigma), in both branches
+    (m > K: Woodbury; m <= K: direct): predictive mean 1e-10, predictive variance (+ noise + sigma, as the reference
+    reports it) 1e-10, log marginal likelihood = -(objective) - m/2 log 2 pi to 1e-7 (the reference adds 1e-9 inside the
+    log of the Cholesky diagonal)."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import Kernel
+
+    class Precomputed(Kernel):
+        def __init__(self, C):
+            self.C = C
+
+        def __call__(self, X, Y=None, eval_gradient=False):
+            i = np.asarray(X)[:, 0].astype(int)
+            j = i if Y is None else np.asarray(Y)[:, 0].astype(int)
+            Kij = self.C[np.ix_(i, j)]
+            return (Kij, np.empty((len(i), len(i), 0))) if eval_gradient else Kij
+
+        def diag(self, X):
+            return np.diag(self.C)[np.asarray(X)[:, 0].astype(int)].copy()
+
+        def is_stationary(self):
+            return False
+
+    rng = np.random.default_rng(1)
+    n, K = 300, 20
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.3, 1.0, K))[::-1]
+    values[0] = 1.0
+    every = np.arange(n, dtype=np.int32)
+    idx, idx1 = every[:m], every[m:]
+    Y = V[:m, 1] + 0.7 * V[:m, 3] + 0.2 * rng.standard_normal(m)
+    t, noise, sigma = 5.0, 0.3, 1e-5
+    C = oracle.hk_from_spectrum(V, values, K, t, every, every)
+    gpr = GaussianProcessRegressor(kernel=Precomputed(C), alpha=noise + sigma, optimizer=None)
+    gpr.fit(np.arange(m, dtype=np.float64)[:, None], Y)
+    mu, sd = gpr.predict(np.arange(m, n, dtype=np.float64)[:, None], return_std=True)
+    pred = oracle.predict_regression(V, values, Y, idx, idx1, K, (t, noise), sigma)
+    cov = oracle.posterior_covariance_regression(V, values, idx, idx1, K, (t, noise), sigma)
+    np.testing.assert_allclose(pred, mu, rtol=1e-10, atol=1e-11)
+    np.testing.assert_allclose(cov, sd ** 2 + noise + sigma, rtol=1e-10, atol=1e-11)
+    f, _ = oracle.regression_objective(V, values, Y, idx, K, (t, noise), sigma, "marginal")
+    assert abs((-f - 0.5 * m * np.log(2 * np.pi)) - gpr.log_marginal_likelihood_value_) <= 1e-7
