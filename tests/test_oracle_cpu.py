@@ -571,3 +571,48 @@ def test_regression_tail_and_objective_against_sklearn_gpr(oracle, m):
     np.testing.assert_allclose(cov, sd ** 2 + noise + sigma, rtol=1e-10, atol=1e-11)
     f, _ = oracle.regression_objective(V, values, Y, idx, K, (t, noise), sigma, "marginal")
     assert abs((-f - 0.5 * m * np.log(2 * np.pi)) - gpr.log_marginal_likelihood_value_) <= 1e-7
+
+
+@pytest.mark.parametrize("m", [80, 12])
+def test_diff_noise_against_sklearn_heteroscedastic_gpr(oracle, m):
+    """noise = "different" restated (src/train.cpp:438-556, src/Predict.cpp:76-113) vs scikit-learn's
+    GaussianProcessRegressor with one alpha per training row on the same precomputed heat kernel, in both branches:
+    predictive mean 1e-10; log marginal likelihood = -(objective) - m/2 log 2 pi to 1e-6 (the reference adds 1e-9 inside
+    its logarithms) — the value the reference's source calls "wrong" is the exact one up to those regularisers."""
+    from sklearn.gaussian_process import GaussianProcessRegressor
+    from sklearn.gaussian_process.kernels import Kernel
+
+    class Precomputed(Kernel):
+        def __init__(self, C):
+            self.C = C
+
+        def __call__(self, X, Y=None, eval_gradient=False):
+            i = np.asarray(X)[:, 0].astype(int)
+            j = i if Y is None else np.asarray(Y)[:, 0].astype(int)
+            Kij = self.C[np.ix_(i, j)]
+            return (Kij, np.empty((len(i), len(i), 0))) if eval_gradient else Kij
+
+        def diag(self, X):
+            return np.diag(self.C)[np.asarray(X)[:, 0].astype(int)].copy()
+
+        def is_stationary(self):
+            return False
+
+    rng = np.random.default_rng(2)
+    n, K = 300, 20
+    V = np.linalg.qr(rng.standard_normal((n, K)))[0] * np.sqrt(n)
+    values = np.sort(rng.uniform(0.3, 1.0, K))[::-1]
+    values[0] = 1.0
+    every = np.arange(n, dtype=np.int32)
+    idx, idx1 = every[:m], every[m:]
+    Y = V[:m, 1] + 0.7 * V[:m, 3] + 0.2 * rng.standard_normal(m)
+    sigma = 1e-5
+    x = np.concatenate([[5.0], rng.uniform(0.05, 1.0, m)])
+    C = oracle.hk_from_spectrum(V, values, K, x[0], every, every)
+    gpr = GaussianProcessRegressor(kernel=Precomputed(C), alpha=x[1:] + sigma, optimizer=None)
+    gpr.fit(np.arange(m, dtype=np.float64)[:, None], Y)
+    mu = gpr.predict(np.arange(m, n, dtype=np.float64)[:, None])
+    np.testing.assert_allclose(oracle.predict_regression_diff(V, values, Y, idx, idx1, K, x, sigma), mu, rtol=1e-10,
+                               atol=1e-11)
+    f, _ = oracle.regression_objective_diff(V, values, Y, idx, K, x, sigma, "marginal")
+    assert abs((-f - 0.5 * m * np.log(2 * np.pi)) - gpr.log_marginal_likelihood_value_) <= 1e-6
