@@ -7,7 +7,14 @@ legs may import this module.  The product package (flgp_b200) never does.
 Stages that the reference delegates to un-vendored third-party code are restated here:
   * RSpectra::svds (src/TruncatedSVD.cpp:23-28)  -> scipy.linalg.eigh of the Gram A^T A
   * Eigen::LLT (src/Predict.cpp:57,66; src/Utils.cpp:234,242) -> scipy cho_factor/cho_solve
+  * nloptr / NLopt (LD_MMA, LN_COBYLA; src/train.cpp:38-71, 557-671) -> mma_minimize, cobyla_minimize_1d below
+  * ClusterR::MiniBatchKmeans (src/Utils.cpp:49-62) -> the mini-batch contract of flgp_oracle.cpp
 All citations are relative to /root/reference.
+
+What pins this oracle in the absence of reference-held vectors (tests/test_oracle_cpu.py): numpy twins of every stage,
+the committed fixtures of tests/golden/, and other people's implementations of the same mathematics — scikit-learn's
+Lloyd, brute-force neighbours, GaussianProcessRegressor / GaussianProcessClassifier on the precomputed heat kernel,
+MiniBatchKMeans; scipy's ARPACK svds, SLSQP, L-BFGS-B, COBYLA; LAPACK.
 """
 from __future__ import annotations
 
